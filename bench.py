@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- EEG trials/sec of the distillation train step (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (config[1] of BASELINE.json, the one the metric is quoted on): per GPU 256 raw trials of 128 channels x 440
+samples -> fused 5-95 Hz order-4 Butterworth band-pass -> 1-layer LSTM (hidden 128, bf16 tcgen05 recurrence)
+-> Linear(128, 384) -> DINO cross-entropy vs random 384-d teacher features (teacher-temperature warm-up, centre EMA)
+-> BPTT -> Adam.  Weak scaling: per-GPU batch fixed, gradients + centre all-reduced over NCCL.  Synthetic data
+(the reference's generator formula), random-init weights.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(batch_per_gpu=256, channels=128, samples=440, hidden=128, layers=1, feat=384, fs=1000.0, band=(5.0, 95.0),
+           order=4, lr=1e-3, seed=43, n_resident_batches=8)
+METRIC = "eeg_trials_per_sec_distill_train_step"
+UNIT = "trials/s"
+
+
+def algorithmic_work(B, C, T, H, L, K):
+    """Per-step algorithmic work (SURVEY.md section 8d / BASELINE.md section 4)."""
+    I = C
+    lstm_fwd_flop = 8.0 * T * H * sum((I if l == 0 else H) + H for l in range(L)) * B
+    rec_fwd_flop = 8.0 * T * H * H * L * B  # recurrent part only (the persistent kernel's MMAs)
+    return dict(filter_bytes=8.0 * C * T * B, loss_bytes=12.0 * K * B, lstm_fwd_flop=lstm_fwd_flop,
+                lstm_train_flop=3.0 * lstm_fwd_flop, rec_fwd_flop=rec_fwd_flop, rec_bwd_flop=rec_fwd_flop)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained"), source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+        out["sm_mhz"] = statistics.median(sm) if sm else None
+        try:
+            out["sm_max_mhz"] = float(rows[0][2])
+        except Exception:
+            pass
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in rows:
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(rows)
+        return out
+
+
+def make_inputs(torch, n_batches, B, C, T, K, seed, device):
+    """Synthetic Spampinato-shaped batches resident in HBM: N(0,1) + 0.5 sin(2 pi 40 t / fs)
+    (utils/PerilsEEGDataset.py:140-147), teacher features N(0,1)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    t = torch.arange(T, device=device, dtype=torch.float32) / CFG["fs"]
+    wave = 0.5 * torch.sin(2 * torch.pi * 40.0 * t)
+    eeg = [torch.randn(B, C, T, device=device, generator=g) + wave for _ in range(n_batches)]
+    feats = [torch.randn(B, K, device=device, generator=g) for _ in range(n_batches)]
+    return eeg, feats
+
+
+def cpu_reference_step_rate(batch, steps, warmup, threads=None):
+    """The reference PyTorch path on the host cores: scipy sosfilt -> restated Model on torch.nn.LSTM ->
+    DINOLoss -> backward -> Adam (oracle/distill.py).  Returns (trials/s, ms/step, cores)."""
+    import torch
+    from oracle.distill import DistillStepOracle, synthetic_batch
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    o = DistillStepOracle(CFG["channels"], CFG["hidden"], CFG["layers"], CFG["feat"], include_top=False, nepochs=100,
+                          lr=CFG["lr"], low_hz=CFG["band"][0], high_hz=CFG["band"][1], fs=CFG["fs"], order=CFG["order"],
+                          seed=CFG["seed"])
+    eeg, feats, _ = synthetic_batch(batch, CFG["channels"], CFG["samples"], CFG["feat"], seed=CFG["seed"])
+    for _ in range(warmup):
+        o.step(eeg, feats, 0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(eeg, feats, 0)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, 1e3 * dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    batch = 64  # bounded sample of the 256-trial step: keeps --steps 10 under ~2 minutes on 8 cores
+    rate, ms, cores = cpu_reference_step_rate(batch, args.steps, max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "distill_step cfg2: 128ch x 440 samples, LSTM L1 H128, 384-d targets, 5-95 Hz band-pass, Adam",
+                   "batch_per_step": batch},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{batch}-trial steps of the cfg2 workload (torch-CPU LSTM + scipy sosfilt + DINO loss + Adam)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--batch_per_gpu", type=int, default=CFG["batch_per_gpu"])
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import cerebralsignalnetworks_b200 as csn
+    from cerebralsignalnetworks_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus > 1 launch through torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    B, C, T, H, L, K = args.batch_per_gpu, CFG["channels"], CFG["samples"], CFG["hidden"], CFG["layers"], CFG["feat"]
+    dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
+    torch.manual_seed(CFG["seed"])  # identical initial weights on every rank (DDP broadcast equivalent)
+    model = csn.Model(C, H, L, K, include_top=False, compute_dtype=dtype).to(dev)
+    crit = csn.DINOLoss(K, 1, 1.5, 0.22, 50, 100).to(dev)
+    sos = csn.EEGFilters(CFG["fs"]).sos(CFG["band"][0], CFG["band"][1], CFG["order"])
+    step = csn.DistillTrainStep(model, crit, lr=CFG["lr"], sos=sos)
+
+    NB = CFG["n_resident_batches"]  # 8 x 57.7 MB of raw trials per GPU: the rotation exceeds the 126 MB L2
+    eeg, feats = make_inputs(torch, NB, B, C, T, K, CFG["seed"] + 1000 * rank, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for i in range(args.warmup):
+        step.step(eeg[i % NB], feats[i % NB], epoch=0)
+    barrier()
+    step.enable_stage_timing(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step.step(eeg[i % NB], feats[i % NB], epoch=0)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total)
+    stages = step.stage_times_ms()
+    step.enable_stage_timing(False)
+    final_loss = float(loss)
+
+    # ---------------- end to end through the public API with HOST buffers (`e2e`) ----------------
+    # pinned host trials -> H2D on a copy stream (double buffered, overlapped with the previous step) -> step ->
+    # D2H of the loss every step.
+    h_eeg = [e.cpu().pin_memory() for e in eeg[:2]]
+    h_feat = [f.cpu().pin_memory() for f in feats[:2]]
+    d_eeg = [torch.empty_like(eeg[0]) for _ in range(2)]
+    d_feat = [torch.empty_like(feats[0]) for _ in range(2)]
+    h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage_in(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            d_eeg[s].copy_(h_eeg[s], non_blocking=True)
+            d_feat[s].copy_(h_feat[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            consumed[s].record()
+        stage_in(0)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                stage_in(i + 1)
+            torch.cuda.current_stream().wait_event(ready[s])
+            l = step.step(d_eeg[s], d_feat[s], epoch=0)
+            consumed[s].record()
+            h_loss.copy_(l, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    barrier()
+    e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    work = algorithmic_work(B, C, T, H, L, K)
+    peaks = measured_peaks()
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+    # dominant stage: the encoder (fwd+bwd); its tensor-core roofline uses the LSTM's algorithmic flops
+    enc_ms = stages.get("encoder_fwd", 0.0) + stages.get("encoder_bwd", 0.0)
+    achieved_tflops = work["lstm_train_flop"] / (enc_ms * 1e-3) / 1e12 if enc_ms > 0 else None
+    peak_tf = peaks["tflops_sustained"] or peaks["tflops"]
+    filt_ms = stages.get("filter", 0.0)
+    filt_gbs = work["filter_bytes"] / (filt_ms * 1e-3) / 1e9 if filt_ms > 0 else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
+        "config": {"workload": "distill_step cfg2: 128ch x 440 samples, LSTM L1 H128 (bf16 tcgen05 recurrence), 384-d targets, "
+                               "fused 5-95 Hz band-pass, DINO CE + centre EMA, Adam",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2_policy": f"rotating {NB} resident input batches ({NB * B * C * T * 4 / 1e6:.0f} MB) > 126 MB L2"},
+        "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": B * C * T * 4 + B * K * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "LSTM encoder fwd+bwd (lstm_fwd_tc_kernel + lstm_bwd_tc_kernel + input-projection / dW GEMMs)",
+                     "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (achieved_tflops / peak_tf) if achieved_tflops else None, "traffic": None,
+                     "peak_source": peaks["source"] + " (sustained: kernel timed inside the step)"},
+        "roofline_filter": {"bound": "hbm", "kernel": "sosfilt_stream_kernel", "achieved": filt_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": (filt_gbs / peaks["hbm_gbs"]) if filt_gbs else None, "traffic": None,
+                            "peak_source": peaks["source"]},
+        "stages_ms": stages,
+        "loss": final_loss,
+    }
+    if not args.no_cpu_baseline:
+        rate, ms, cores = cpu_reference_step_rate(16, 10, 3)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+                                "sample": "10 steps of the cfg1 workload (batch 16, same model) on the host cores: torch-CPU LSTM + "
+                                          "scipy sosfilt + DINO loss + Adam"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,333 @@
+// DINO cross-entropy: teacher softmax (centred, sharpened), student log-softmax, loss, dLoss/dstudent and the
+// centre statistics, in ONE pass over HBM (every input element is read once, every gradient written once).
+//   single-view : LstmDistillFromDinoV2Train.py:62-105
+//   multi-crop  : LstmDistillation.py:118-159 (reference behaviour incl. chunk(1) quirk) / dino/main_dino.py:428-481
+//
+// Decomposition: a thread-block CLUSTER owns one batch row b across all views; CTA c of the cluster owns the
+// K/CS-wide column chunk c.  The teacher probabilities q[g] and the current student row live in registers
+// (<= 32 values per thread per row), row statistics (max, sum-exp, <Q,s>) are reduced with warp shuffles inside
+// the CTA and through distributed shared memory across the cluster.  So the K=65536 head (cfg 3) reads its
+// [6,B,K] + [2,B,K] inputs exactly once and never spills a row to HBM.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace csn {
+
+constexpr int kLossThreads = 256;
+constexpr int kMaxVt = 2;
+constexpr int kMaxVs = 16;
+constexpr int kMaxRounds = kMaxVt + kMaxVs;
+
+struct LossParams {
+  const float* student;
+  const float* teacher;
+  const float* center;
+  float* loss;
+  float* d_student;
+  float* batch_center;
+  int center_rows;  // 1 or B
+  int Vs, Vt, B, K, Kc;
+  int mode;
+  float inv_tau_s, inv_tau_t, coef, grad_coef;
+  unsigned mask[kMaxVs];  // bit g set: student view v is matched against teacher view g
+};
+
+struct Stat {
+  float m, z, d;
+};
+
+__device__ __forceinline__ Stat combine(Stat a, Stat b) {
+  Stat r;
+  r.m = fmaxf(a.m, b.m);
+  float ea = (a.m == -INFINITY) ? 0.f : __expf(a.m - r.m);
+  float eb = (b.m == -INFINITY) ? 0.f : __expf(b.m - r.m);
+  r.z = a.z * ea + b.z * eb;
+  r.d = a.d + b.d;
+  return r;
+}
+
+__device__ __forceinline__ Stat warp_combine(Stat s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Stat t;
+    t.m = __shfl_xor_sync(0xffffffffu, s.m, o);
+    t.z = __shfl_xor_sync(0xffffffffu, s.z, o);
+    t.d = __shfl_xor_sync(0xffffffffu, s.d, o);
+    s = combine(s, t);
+  }
+  return s;
+}
+
+// CTA-level then cluster-level reduction.  `slot` is this CTA's per-round mailbox in shared memory; peers read
+// it through DSMEM after one cluster barrier.  Rounds never reuse a slot, so one barrier per round suffices.
+__device__ __forceinline__ Stat cluster_reduce(Stat s, Stat* warp_buf, Stat* slot, cg::cluster_group& cluster, int cs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  s = warp_combine(s);
+  if (lane == 0) warp_buf[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    Stat t = (lane < kLossThreads / 32) ? warp_buf[lane] : Stat{-INFINITY, 0.f, 0.f};
+    t = warp_combine(t);
+    if (lane == 0) *slot = t;
+  }
+  if (cs > 1) {
+    cluster.sync();
+    Stat acc{-INFINITY, 0.f, 0.f};
+    for (int r = 0; r < cs; ++r) {
+      const Stat* peer = cluster.map_shared_rank(slot, r);
+      Stat t = *peer;
+      acc = combine(acc, t);
+    }
+    return acc;
+  }
+  __syncthreads();
+  return *slot;
+}
+
+template <int VEC, int NITER>
+__global__ void __launch_bounds__(kLossThreads) dino_loss_kernel(const LossParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int k0 = crank * p.Kc;
+  constexpr int EPT = VEC * NITER;
+
+  __shared__ Stat warp_buf[kLossThreads / 32];
+  __shared__ Stat slots[kMaxRounds];
+  int round = 0;
+
+  float q[kMaxVt][EPT];
+  float cen[EPT];
+  float bc[EPT];
+
+  auto elem = [&](int i) { return ((i / VEC) * kLossThreads + tid) * VEC + (i % VEC); };  // chunk-local index
+
+  auto load_row = [&](const float* base, float (&dst)[EPT]) {
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+      int e = (it * kLossThreads + tid) * VEC;
+      if (e < p.Kc) {
+        if constexpr (VEC == 4) {
+          float4 v = __ldcs(reinterpret_cast<const float4*>(base + k0 + e));
+          dst[it * 4 + 0] = v.x; dst[it * 4 + 1] = v.y; dst[it * 4 + 2] = v.z; dst[it * 4 + 3] = v.w;
+        } else {
+          dst[it] = __ldcs(base + k0 + e);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) dst[it * VEC + j] = 0.f;
+      }
+    }
+  };
+  auto store_row = [&](float* base, const float (&src)[EPT]) {
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+      int e = (it * kLossThreads + tid) * VEC;
+      if (e < p.Kc) {
+        if constexpr (VEC == 4) {
+          __stcs(reinterpret_cast<float4*>(base + k0 + e),
+                 make_float4(src[it * 4 + 0], src[it * 4 + 1], src[it * 4 + 2], src[it * 4 + 3]));
+        } else {
+          __stcs(base + k0 + e, src[it]);
+        }
+      }
+    }
+  };
+
+  {
+    const float* cbase = p.center + (p.center_rows > 1 ? size_t(b) * p.K : 0);
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+      int e = (it * kLossThreads + tid) * VEC;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) cen[it * VEC + j] = (e < p.Kc) ? cbase[k0 + e + j] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) bc[i] = 0.f;
+
+  // ---- teacher rows: q[g] = softmax((t - c) / tau_t) ----
+#pragma unroll
+  for (int g = 0; g < kMaxVt; ++g) {
+    if (g < p.Vt) {
+      load_row(p.teacher + (size_t(g) * p.B + b) * p.K, q[g]);
+      Stat s{-INFINITY, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        bc[i] += q[g][i];
+        q[g][i] = (q[g][i] - cen[i]) * p.inv_tau_t;
+        if (elem(i) < p.Kc) s.m = fmaxf(s.m, q[g][i]);
+      }
+#pragma unroll
+      for (int i = 0; i < EPT; ++i)
+        if (elem(i) < p.Kc) s.z += __expf(q[g][i] - s.m);
+      s = cluster_reduce(s, warp_buf, &slots[round++], cluster, cs);
+      const float inv_z = 1.f / s.z;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) q[g][i] = __expf(q[g][i] - s.m) * inv_z;
+    } else {
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) q[g][i] = 0.f;
+    }
+  }
+
+  // ---- centre statistics ----
+  if (p.mode == CSN_DINO_MULTICROP_REF) {
+    store_row(p.batch_center + size_t(b) * p.K, bc);
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      if (elem(i) < p.Kc) atomicAdd(p.batch_center + k0 + elem(i), bc[i]);
+  }
+
+  // ---- student rows ----
+  float loss_acc = 0.f;
+  for (int v = 0; v < p.Vs; ++v) {
+    const unsigned mask = p.mask[v];
+    float* gout = p.d_student + (size_t(v) * p.B + b) * p.K;
+    float u[EPT];
+    if (mask == 0) {  // view not matched against any teacher view: zero gradient (cluster-uniform branch)
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) u[i] = 0.f;
+      store_row(gout, u);
+      continue;
+    }
+    load_row(p.student + (size_t(v) * p.B + b) * p.K, u);
+    const float w0 = (mask & 1u) ? 1.f : 0.f, w1 = (mask & 2u) ? 1.f : 0.f;
+    const float W = w0 + w1;
+    Stat s{-INFINITY, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      u[i] *= p.inv_tau_s;
+      if (elem(i) < p.Kc) {
+        s.m = fmaxf(s.m, u[i]);
+        s.d += (w0 * q[0][i] + w1 * q[1][i]) * u[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      if (elem(i) < p.Kc) s.z += __expf(u[i] - s.m);
+    s = cluster_reduce(s, warp_buf, &slots[round++], cluster, cs);
+    loss_acc += p.coef * (W * (s.m + __logf(s.z)) - s.d);
+    const float inv_z = 1.f / s.z;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      u[i] = p.grad_coef * (W * __expf(u[i] - s.m) * inv_z - (w0 * q[0][i] + w1 * q[1][i]));
+    store_row(gout, u);
+  }
+  if (crank == 0 && tid == 0) atomicAdd(p.loss, loss_acc);
+  if (cs > 1) cluster.sync();  // peers may still be reading our mailboxes
+}
+
+template <int VEC, int NITER>
+static int launch_loss(const LossParams& p, int cs, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cs, p.B, 1);
+  cfg.blockDim = dim3(kLossThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSN_CUDA(cudaLaunchKernelEx(&cfg, dino_loss_kernel<VEC, NITER>, p));
+  return CSN_OK;
+}
+
+__global__ void center_ema_kernel(float* __restrict__ center, const float* __restrict__ bc, size_t n, float mom,
+                                  float scale) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) center[i] = center[i] * mom + bc[i] * scale * (1.f - mom);
+}
+
+}  // namespace csn
+
+using namespace csn;
+
+extern "C" int csn_dino_loss_fwd_bwd(const float* student, const float* teacher, const float* center, int center_rows,
+                                     float student_temp, float teacher_temp, float* loss, float* d_student,
+                                     float* batch_center, int Vs, int Vt, int B, int K, int mode, float grad_scale,
+                                     void* stream) {
+  CSN_REQUIRE(student && teacher && center && loss && d_student && batch_center, "csn_dino_loss_fwd_bwd: null pointer");
+  CSN_REQUIRE(Vs >= 1 && Vs <= kMaxVs && Vt >= 1 && Vt <= kMaxVt, "csn_dino_loss_fwd_bwd: need 1<=Vs<=%d, 1<=Vt<=%d", kMaxVs, kMaxVt);
+  CSN_REQUIRE(B >= 1 && K >= 1 && B <= 65535, "csn_dino_loss_fwd_bwd: bad B/K");
+  CSN_REQUIRE(center_rows == 1 || center_rows == B, "csn_dino_loss_fwd_bwd: center_rows must be 1 or B");
+  CSN_REQUIRE(student_temp > 0.f && teacher_temp != 0.f, "csn_dino_loss_fwd_bwd: bad temperature");
+  LossParams p{};
+  p.student = student; p.teacher = teacher; p.center = center; p.loss = loss; p.d_student = d_student;
+  p.batch_center = batch_center; p.center_rows = center_rows;
+  p.Vs = Vs; p.Vt = Vt; p.B = B; p.K = K; p.mode = mode;
+  p.inv_tau_s = 1.f / student_temp; p.inv_tau_t = 1.f / teacher_temp;
+  int n_terms = 0;
+  if (mode == CSN_DINO_SINGLE) {
+    CSN_REQUIRE(Vs == 1 && Vt == 1, "csn_dino_loss_fwd_bwd: SINGLE mode needs Vs == Vt == 1");
+    p.mask[0] = 1u;
+    p.coef = 1.f / B;
+  } else if (mode == CSN_DINO_MULTICROP_REF) {
+    // teacher.chunk(1) -> one "view" holding all Vt teacher views; student view 0 is skipped (v == iq),
+    // every other view is averaged over all Vt*B rows (LstmDistillation.py:128,136-144)
+    CSN_REQUIRE(Vs >= 2, "csn_dino_loss_fwd_bwd: MULTICROP_REF needs Vs >= 2");
+    p.mask[0] = 0u;
+    for (int v = 1; v < Vs; ++v) p.mask[v] = (1u << Vt) - 1u;
+    n_terms = Vs - 1;
+    p.coef = 1.f / (float(n_terms) * float(Vt) * float(B));
+  } else if (mode == CSN_DINO_MULTICROP_CANONICAL) {
+    for (int v = 0; v < Vs; ++v) {
+      p.mask[v] = ((1u << Vt) - 1u) & ~(1u << v);
+      n_terms += __builtin_popcount(p.mask[v]);
+    }
+    CSN_REQUIRE(n_terms > 0, "csn_dino_loss_fwd_bwd: no loss terms");
+    p.coef = 1.f / (float(n_terms) * float(B));
+  } else {
+    CSN_REQUIRE(false, "csn_dino_loss_fwd_bwd: bad mode %d", mode);
+  }
+  p.grad_coef = p.coef * p.inv_tau_s * grad_scale;
+
+  cudaStream_t s = as_stream(stream);
+  CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+
+  const bool aligned = ((reinterpret_cast<uintptr_t>(student) | reinterpret_cast<uintptr_t>(teacher) |
+                         reinterpret_cast<uintptr_t>(d_student) | reinterpret_cast<uintptr_t>(batch_center)) & 15) == 0;
+  int cs = 1;
+  // widen the cluster until a chunk fits the register budget (and to spread small batches over more SMs)
+  auto fits = [&](int c, int vec) { return K % (c * vec) == 0 && K / c <= kLossThreads * vec * 8; };
+  int vec = (aligned && K % 4 == 0) ? 4 : 1;
+  while (cs <= 8 && !fits(cs, vec)) cs *= 2;
+  if (cs > 8 && vec == 4) { vec = 1; cs = 1; while (cs <= 8 && !fits(cs, vec)) cs *= 2; }
+  CSN_REQUIRE(cs <= 8, "csn_dino_loss_fwd_bwd: K=%d not supported (needs K %% cluster == 0 and K <= 65536)", K);
+  while (cs < 8 && B * cs < sm_count() && fits(cs * 2, vec) && K / (cs * 2) >= kLossThreads * vec) cs *= 2;
+  p.Kc = K / cs;
+  const int per_thread = ceil_div(p.Kc, kLossThreads * vec);
+  int r;
+  if (vec == 4) {
+    if (per_thread <= 1) r = launch_loss<4, 1>(p, cs, s);
+    else if (per_thread <= 2) r = launch_loss<4, 2>(p, cs, s);
+    else if (per_thread <= 4) r = launch_loss<4, 4>(p, cs, s);
+    else r = launch_loss<4, 8>(p, cs, s);
+  } else {
+    if (per_thread <= 1) r = launch_loss<1, 1>(p, cs, s);
+    else if (per_thread <= 2) r = launch_loss<1, 2>(p, cs, s);
+    else if (per_thread <= 4) r = launch_loss<1, 4>(p, cs, s);
+    else r = launch_loss<1, 8>(p, cs, s);
+  }
+  return r;
+}
+
+extern "C" int csn_center_ema(float* center, const float* batch_center, size_t n, float momentum, float scale,
+                              void* stream) {
+  CSN_REQUIRE(center && batch_center, "csn_center_ema: null pointer");
+  if (n == 0) return CSN_OK;
+  int blocks = (int)std::min<size_t>(ceil_div<size_t>(n, 256), size_t(sm_count()) * 8);
+  center_ema_kernel<<<blocks, 256, 0, as_stream(stream)>>>(center, batch_center, n, momentum, scale);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}

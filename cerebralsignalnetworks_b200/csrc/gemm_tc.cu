@@ -1,0 +1,236 @@
+// bf16 tensor-core GEMM for sm_100a: TMA (128B swizzle) -> shared-memory ring -> tcgen05.mma (fp32 accumulators
+// in TMEM) -> tcgen05.ld epilogue.  Warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (single thread),
+// warps 2..5 = epilogue (one TMEM lane quadrant each).  CTA tile 128 x 128 x 64, up to 4 stages, optional split-K
+// with fp32 atomics.  Both operands may be K-major or MN-major (the dW = dG^T Z products of BPTT contract over
+// the row index of both stored matrices).
+//
+// D[M,N] = op(A)[M,K] * op(B)[K,N] (+ bias[N]);  A: transA=0 stored [M,K] (K-major), transA=1 stored [K,M]
+// (MN-major); B: transB=1 stored [N,K] (K-major), transB=0 stored [K,N] (MN-major).
+#include <cuda.h>
+#include <mutex>
+
+#include "tc.cuh"
+
+namespace csn {
+
+using namespace tc;
+
+constexpr int GBM = 128, GBN = 128, GBK = 64;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kStageBytes = (GBM * GBK + GBN * GBK) * 2;  // 32 KB
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor [outer, inner] with row pitch `pitch_elems`, box [box_outer, box_inner], 128B swizzle.
+static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                        uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return CSN_ECUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu pitch=%llu)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems);
+    return CSN_ECUDA;
+  }
+  return CSN_OK;
+}
+
+struct GemmEpi {
+  void* D;
+  const float* bias;
+  int ldd, d_dtype, M, N, K, k_per_split, atomic, stages;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  const GemmEpi p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(S) * kStageBytes);
+  uint64_t* empty = full + 4;
+  uint64_t* accfull = empty + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int kbeg = blockIdx.z * p.k_per_split;
+  const int klen = min(p.K - kbeg, p.k_per_split);
+  const int n_it = (klen + GBK - 1) / GBK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == 1) tmem_alloc(tmem_slot, GBN);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % S;
+        if (it >= S) mbar_wait(&empty[s], ((it / S) - 1) & 1);
+        uint8_t* sa = smem + size_t(s) * kStageBytes;
+        uint8_t* sb = sa + GBM * GBK * 2;
+        mbar_arrive_expect_tx(&full[s], kStageBytes);
+        const int k = kbeg + it * GBK;
+        if (A_MN) {
+          tma_load_2d(sa, &tmA, &full[s], m0, k);
+          tma_load_2d(sa + 8192, &tmA, &full[s], m0 + 64, k);
+        } else {
+          tma_load_2d(sa, &tmA, &full[s], k, m0);
+        }
+        if (B_MN) {
+          tma_load_2d(sb, &tmB, &full[s], n0, k);
+          tma_load_2d(sb + 8192, &tmB, &full[s], n0 + 64, k);
+        } else {
+          tma_load_2d(sb, &tmB, &full[s], k, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GBM, GBN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % S;
+        mbar_wait(&full[s], (it / S) & 1);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
+        const uint32_t sb = sa + GBM * GBK * 2;
+#pragma unroll
+        for (int kk = 0; kk < GBK / 16; ++kk) {
+          // K-major SW128: rows of 128 B, 8-row groups 1024 B apart, 16 K-elements = 32 B along the row.
+          // MN-major SW128: 8 k-rows x 128 B atoms 1024 B apart along K (SBO), 64-element MN chunks 8192 B apart (LBO).
+          uint64_t da = A_MN ? make_smem_desc(sa + kk * 2048, 8192, 1024, kLayoutSw128)
+                             : make_smem_desc(sa + kk * 32, 16, 1024, kLayoutSw128);
+          uint64_t db = B_MN ? make_smem_desc(sb + kk * 2048, 8192, 1024, kLayoutSw128)
+                             : make_smem_desc(sb + kk * 32, 16, 1024, kLayoutSw128);
+          umma_f16(tmem_base, da, db, idesc, (it | kk) != 0);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accfull);
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int gm = m0 + row;
+    if (n_it > 0) {
+      mbar_wait(accfull, 0);
+      tcgen05_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < GBN; c0 += 16) {
+      uint32_t r[16];
+      if (n_it > 0) {
+        tmem_ld<16>(tmem_base + (uint32_t(quad * 32) << 16) + c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+      if (gm < p.M) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int gn = n0 + c0 + j;
+          if (gn < p.N) {
+            float v = __uint_as_float(r[j]);
+            if (p.bias && blockIdx.z == 0) v += p.bias[gn];
+            if (p.d_dtype == CSN_F32) {
+              float* d = reinterpret_cast<float*>(p.D) + size_t(gm) * p.ldd + gn;
+              if (p.atomic) atomicAdd(d, v); else *d = v;
+            } else {
+              reinterpret_cast<__nv_bfloat16*>(p.D)[size_t(gm) * p.ldd + gn] = __float2bfloat16_rn(v);
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, GBN);
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& p, dim3 grid, cudaStream_t s) {
+  const size_t smem = size_t(p.stages) * kStageBytes + 1024 + 256;
+  auto kern = gemm_tc_kernel<A_MN, B_MN>;
+  CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kGemmThreads, smem, s>>>(ta, tb, p);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+}  // namespace csn
+
+using namespace csn;
+
+extern "C" int csn_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B,
+                                int ldb, void* D, int ldd, int d_dtype, const float* bias, int accumulate, int split_k,
+                                void* stream) {
+  CSN_REQUIRE(A && B && D, "csn_gemm_bf16_tc: null pointer");
+  CSN_REQUIRE(M >= 1 && N >= 1 && K >= 1, "csn_gemm_bf16_tc: dimensions must be positive");
+  CSN_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "csn_gemm_bf16_tc: lda/ldb must be multiples of 8 elements (TMA 16 B pitch)");
+  CSN_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
+              "csn_gemm_bf16_tc: operands must be 16-byte aligned");
+  CSN_REQUIRE(d_dtype == CSN_F32 || d_dtype == CSN_BF16, "csn_gemm_bf16_tc: bad d_dtype");
+  if (split_k < 1) split_k = 1;
+  CSN_REQUIRE(d_dtype == CSN_F32 || (split_k == 1 && !accumulate), "csn_gemm_bf16_tc: bf16 output cannot accumulate / split-K");
+  cudaStream_t s = as_stream(stream);
+
+  const int k_iters = ceil_div(K, GBK);
+  if (split_k > k_iters) split_k = k_iters;
+  const int it_per_split = ceil_div(k_iters, split_k);
+  split_k = ceil_div(k_iters, it_per_split);
+
+  CUtensorMap ta, tb;
+  if (transA) CSN_TRY(make_tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64));   // stored [K, M]
+  else        CSN_TRY(make_tmap_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 128));  // stored [M, K]
+  if (transB) CSN_TRY(make_tmap_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 128));  // stored [N, K]
+  else        CSN_TRY(make_tmap_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64));   // stored [K, N]
+
+  GemmEpi p{};
+  p.D = D; p.bias = bias; p.ldd = ldd; p.d_dtype = d_dtype; p.M = M; p.N = N; p.K = K;
+  p.k_per_split = it_per_split * GBK;
+  p.atomic = (accumulate || split_k > 1) ? 1 : 0;
+  p.stages = it_per_split < 4 ? (it_per_split < 2 ? 2 : it_per_split) : 4;
+  if (split_k > 1 && !accumulate) CSN_CUDA(cudaMemset2DAsync(D, size_t(ldd) * 4, 0, size_t(N) * 4, M, s));
+  dim3 grid(ceil_div(N, GBN), ceil_div(M, GBM), split_k);
+  CSN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "csn_gemm_bf16_tc: grid too large");
+  if (transA && !transB) return launch_gemm<true, true>(ta, tb, p, grid, s);
+  if (transA && transB) return launch_gemm<true, false>(ta, tb, p, grid, s);
+  if (!transA && !transB) return launch_gemm<false, true>(ta, tb, p, grid, s);
+  return launch_gemm<false, false>(ta, tb, p, grid, s);
+}

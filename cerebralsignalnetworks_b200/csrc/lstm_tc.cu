@@ -1,0 +1,537 @@
+// LSTM layer, bf16 tensor-core path: persistent tcgen05 recurrence + hand-written BPTT (H <= 128).
+//
+// Forward (one CTA per batch tile of NV trials, the whole time loop inside the kernel):
+//   * W_hh is converted to bf16 once and stays RESIDENT in shared memory for all T steps as four 128 x KP
+//     K-major operand blocks (one per gate: rows = hidden unit, so TMEM lane = unit and a thread owns all four
+//     gates of its unit -- no cross-thread exchange in the epilogue).
+//   * per step the single issuer thread runs 4*KP/16 tcgen05.mma (M=128 units, N=16 batch slots, K=16) :
+//     gates^T[g] = W_hh[g] . h_{t-1}^T, fp32 accumulators in TMEM.
+//   * the four epilogue warps tcgen05.ld their lanes, add the hoisted input projection x_t W_ih^T + b (prefetched
+//     from HBM one step ahead), apply sigmoid/tanh (tanh.approx), update the fp32 cell state held in REGISTERS,
+//     write h_t as bf16 straight into the shared-memory operand layout the next step's MMA reads
+//     (generic-proxy store -> fence.proxy.async -> mbarrier), and stream h_t / gate activations / c_t to HBM
+//     for BPTT.
+// Backward mirrors it: W_hh^T resident (A operand, M = hidden unit k, K = 4 gates x units), per step
+//   dh_{t-1}^T = W_hh^T . dG_t^T on tcgen05, gate derivatives + dc carry in registers, dG_t streamed to HBM in
+//   bf16; dW_ih / dW_hh / dX are then three large tcgen05 GEMMs (gemm_tc.cu), db is accumulated in registers.
+//
+// The serial chain (T steps) cannot be parallelised; what this design optimises is the per-step latency:
+// no HBM round trip, no grid-wide sync, one mbarrier hand-off in each direction per step.
+#include "tc.cuh"
+
+namespace csn {
+
+using namespace tc;
+
+constexpr int kRecThreads = 160;  // warps 0-3: epilogue (TMEM lane quadrants 0-3), warp 4: MMA issuer
+constexpr uint32_t kLboA = 2048, kSboA = 128;  // 128-row operand: 16 core matrices (128 B) per k-group
+constexpr uint32_t kLboB = 256, kSboB = 128;   // 16-row operand: 2 core matrices per k-group
+constexpr int kNslots = 16;                    // MMA N (batch slots per CTA); NV <= 16 of them are live
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+struct RecSmem {
+  uint8_t* w;      // 4 * 128 * KP * 2 bytes (fwd) / 128 * 4KP * 2 bytes (bwd)
+  uint8_t* opb;    // B operand: h^T (fwd, KP/8 * 256 B) or dG^T (bwd, 4KP/8 * 256 B)
+  uint64_t* bar_in;   // operand ready (epilogue -> issuer)
+  uint64_t* bar_acc;  // accumulators ready (issuer -> epilogue)
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t w_bytes, size_t b_bytes) {
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~uintptr_t(127));
+  RecSmem s;
+  s.w = base;
+  s.opb = base + w_bytes;
+  s.bar_in = reinterpret_cast<uint64_t*>(s.opb + b_bytes);
+  s.bar_acc = s.bar_in + 1;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_acc + 1);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int NV>
+__global__ void __launch_bounds__(kRecThreads, 1)
+lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+                   __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
+                   int T, int B, int H, int KP) {
+  extern __shared__ uint8_t smem_raw[];
+  const size_t w_bytes = size_t(4) * 128 * KP * 2, b_bytes = size_t(KP / 8) * kLboB;
+  RecSmem sm = carve(smem_raw, w_bytes, b_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b0 = blockIdx.x * NV;
+
+  // ---- one-time staging: W_hh -> bf16 canonical K-major blocks; zero the operand buffer ----
+  {
+    const int chunks = 4 * 128 * (KP / 8);  // 16-byte chunks: (g, u, k8)
+    for (int c = tid; c < chunks; c += kRecThreads) {
+      const int k8 = c % (KP / 8), u = (c / (KP / 8)) % 128, g = c / ((KP / 8) * 128);
+      uint32_t packed[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k8 * 8 + 2 * i;
+        float v0 = (u < H && k < H) ? w_hh[size_t(g * H + u) * H + k] : 0.f;
+        float v1 = (u < H && k + 1 < H) ? w_hh[size_t(g * H + u) * H + k + 1] : 0.f;
+        __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
+        packed[i] = *reinterpret_cast<uint32_t*>(&bb);
+      }
+      *reinterpret_cast<uint4*>(sm.w + size_t(g) * 128 * KP * 2 + canon_k_off(u, k8 * 8, kLboA, kSboA)) =
+          make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
+  }
+  if (tid == 0) {
+    mbar_init(sm.bar_in, 128);
+    mbar_init(sm.bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(sm.tmem_slot, 64);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+
+  if (warp == 4) {
+    // ================= MMA issuer =================
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
+      const uint32_t w_addr = smem_u32(sm.w), b_addr = smem_u32(sm.opb);
+      const int ksteps = KP / 16;
+      for (int t = 1; t < T; ++t) {
+        mbar_wait(sm.bar_in, (t - 1) & 1);  // h_{t-1} is in shared memory (and TMEM has been drained)
+        tcgen05_fence_after();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t da = make_smem_desc(w_addr + g * (128 * KP * 2) + kk * 2 * kLboA, kLboA, kSboA, kLayoutNone);
+            const uint64_t db = make_smem_desc(b_addr + kk * 2 * kLboB, kLboB, kSboB, kLayoutNone);
+            umma_f16(tmem_base + g * kNslots, da, db, idesc, kk != 0);
+          }
+        }
+        umma_commit(sm.bar_acc);
+      }
+    }
+  } else {
+    // ================= epilogue: thread = hidden unit u =================
+    const int u = tid;
+    const bool active = u < H;
+    const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+    float bias[4], c[NV], xcur[4][NV], xnext[4][NV];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bias[g] = active ? b_hh[g * H + u] : 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) c[j] = 0.f;
+
+    auto load_xp = [&](int t, float (&dst)[4][NV]) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const bool ok = active && (b0 + j < B) && (t < T);
+        const float* row = xp + (size_t(t) * B + (b0 + j)) * 4 * H + u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dst[g][j] = ok ? __ldcs(row + g * H) : 0.f;
+      }
+    };
+    load_xp(0, xcur);
+
+    for (int t = 0; t < T; ++t) {
+      load_xp(t + 1, xnext);  // in flight while this step computes
+      float pre[4][NV];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) pre[g][j] = xcur[g][j] + bias[g];
+      if (t > 0) {
+        mbar_wait(sm.bar_acc, (t - 1) & 1);
+        tcgen05_fence_after();
+        uint32_t r[4][NV];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld<NV>(lane_addr + g * kNslots, r[g]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int j = 0; j < NV; ++j) pre[g][j] += __uint_as_float(r[g][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float ig = sigmoid_fast(pre[0][j]), fg = sigmoid_fast(pre[1][j]);
+        const float gg = tanh_fast(pre[2][j]), og = sigmoid_fast(pre[3][j]);
+        c[j] = fmaf(fg, c[j], ig * gg);
+        const float h = og * tanh_fast(c[j]);
+        const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+        if (active) {
+          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, u, kLboB, kSboB)) = hb;
+          if (b0 + j < B) {
+            const size_t cell = (size_t(t) * B + (b0 + j)) * H + u;
+            h_seq[cell] = hb;
+            if (gates_out) {
+              __nv_bfloat16* gr = gates_out + (size_t(t) * B + (b0 + j)) * 4 * H + u;
+              gr[0] = __float2bfloat16_rn(ig);
+              gr[H] = __float2bfloat16_rn(fg);
+              gr[2 * H] = __float2bfloat16_rn(gg);
+              gr[3 * H] = __float2bfloat16_rn(og);
+              c_out[cell] = c[j];
+            }
+          }
+        }
+      }
+      // publish h_t to the async proxy, order our TMEM reads before the next MMA, hand over
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(sm.bar_in);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) xcur[g][j] = xnext[g][j];
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+template <int NV>
+__global__ void __launch_bounds__(kRecThreads, 1)
+lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
+                   const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
+                   float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP) {
+  extern __shared__ uint8_t smem_raw[];
+  const int K4 = 4 * KP;
+  const size_t w_bytes = size_t(128) * K4 * 2, b_bytes = size_t(K4 / 8) * kLboB;
+  RecSmem sm = carve(smem_raw, w_bytes, b_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b0 = blockIdx.x * NV;
+
+  // A operand: A(m = k, kk = g*KP + u) = W_hh[g*H + u][k]   (W_hh^T, K-major in kk)
+  {
+    const int chunks = 128 * (K4 / 8);
+    for (int c = tid; c < chunks; c += kRecThreads) {
+      const int m = c % 128, q8 = c / 128;      // q8: 8-wide kk group; consecutive threads -> consecutive k (coalesced rows)
+      const int g = (q8 * 8) / KP, u0 = (q8 * 8) % KP;
+      uint32_t packed[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ua = u0 + 2 * i, ub = ua + 1;
+        float v0 = (m < H && ua < H) ? w_hh[size_t(g * H + ua) * H + m] : 0.f;
+        float v1 = (m < H && ub < H) ? w_hh[size_t(g * H + ub) * H + m] : 0.f;
+        __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
+        packed[i] = *reinterpret_cast<uint32_t*>(&bb);
+      }
+      *reinterpret_cast<uint4*>(sm.w + canon_k_off(m, q8 * 8, kLboA, kSboA)) =
+          make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
+  }
+  if (tid == 0) {
+    mbar_init(sm.bar_in, 128);
+    mbar_init(sm.bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(sm.tmem_slot, 32);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+
+  if (warp == 4) {
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
+      const uint32_t w_addr = smem_u32(sm.w), b_addr = smem_u32(sm.opb);
+      const int ksteps = K4 / 16;
+      int n = 0;
+      for (int t = T - 1; t >= 1; --t, ++n) {
+        mbar_wait(sm.bar_in, n & 1);  // dG_t^T staged
+        tcgen05_fence_after();
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t da = make_smem_desc(w_addr + kk * 2 * kLboA, kLboA, kSboA, kLayoutNone);
+          const uint64_t db = make_smem_desc(b_addr + kk * 2 * kLboB, kLboB, kSboB, kLayoutNone);
+          umma_f16(tmem_base, da, db, idesc, kk != 0);
+        }
+        umma_commit(sm.bar_acc);
+      }
+    }
+  } else {
+    const int u = tid;
+    const bool active = u < H;
+    const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+    float dc[NV], dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NV; ++j) dc[j] = 0.f;
+
+    struct StepIn {
+      float i[NV], f[NV], g[NV], o[NV], c[NV], cp[NV], dh[NV];
+    };
+    auto load_step = [&](int t, StepIn& s) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const bool ok = active && (b0 + j < B) && (t >= 0);
+        const size_t cell = (size_t(t < 0 ? 0 : t) * B + (b0 + j)) * H + u;
+        const __nv_bfloat16* gr = gates + (size_t(t < 0 ? 0 : t) * B + (b0 + j)) * 4 * H + u;
+        s.i[j] = ok ? __bfloat162float(gr[0]) : 0.f;
+        s.f[j] = ok ? __bfloat162float(gr[H]) : 0.f;
+        s.g[j] = ok ? __bfloat162float(gr[2 * H]) : 0.f;
+        s.o[j] = ok ? __bfloat162float(gr[3 * H]) : 0.f;
+        s.c[j] = ok ? c_seq[cell] : 0.f;
+        s.cp[j] = (ok && t > 0) ? c_seq[cell - size_t(B) * H] : 0.f;
+        float d = 0.f;
+        if (ok && d_hseq) d += d_hseq[cell];
+        if (ok && d_hlast && t == T - 1) d += d_hlast[size_t(b0 + j) * H + u];
+        s.dh[j] = d;
+      }
+    };
+    StepIn cur, nxt;
+    load_step(T - 1, cur);
+    int n = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      load_step(t - 1, nxt);
+      float dh[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) dh[j] = cur.dh[j];
+      if (t < T - 1) {
+        mbar_wait(sm.bar_acc, (n - 1) & 1);
+        tcgen05_fence_after();
+        uint32_t r[NV];
+        tmem_ld<NV>(lane_addr, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < NV; ++j) dh[j] += __uint_as_float(r[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float tcn = tanh_fast(cur.c[j]);
+        const float dct = fmaf(dh[j] * cur.o[j], 1.f - tcn * tcn, dc[j]);
+        const float dgi = dct * cur.g[j] * cur.i[j] * (1.f - cur.i[j]);
+        const float dgf = dct * cur.cp[j] * cur.f[j] * (1.f - cur.f[j]);
+        const float dgg = dct * cur.i[j] * (1.f - cur.g[j] * cur.g[j]);
+        const float dgo = dh[j] * tcn * cur.o[j] * (1.f - cur.o[j]);
+        dc[j] = dct * cur.f[j];
+        if (active) {
+          const __nv_bfloat16 q0 = __float2bfloat16_rn(dgi), q1 = __float2bfloat16_rn(dgf),
+                              q2 = __float2bfloat16_rn(dgg), q3 = __float2bfloat16_rn(dgo);
+          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, 0 * KP + u, kLboB, kSboB)) = q0;
+          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, 1 * KP + u, kLboB, kSboB)) = q1;
+          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, 2 * KP + u, kLboB, kSboB)) = q2;
+          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, 3 * KP + u, kLboB, kSboB)) = q3;
+          if (b0 + j < B) {
+            __nv_bfloat16* gr = dG + (size_t(t) * B + (b0 + j)) * 4 * H + u;
+            gr[0] = q0; gr[H] = q1; gr[2 * H] = q2; gr[3 * H] = q3;
+            dbacc[0] += dgi; dbacc[1] += dgf; dbacc[2] += dgg; dbacc[3] += dgo;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(sm.bar_in);
+      ++n;
+      cur = nxt;
+    }
+    if (active) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        atomicAdd(db_ih + g * H + u, dbacc[g]);
+        atomicAdd(db_hh + g * H + u, dbacc[g]);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static int pick_nv(int B) {
+  // smallest batch tile that still fills the machine: per-step latency falls with NV (fewer MUFU ops per SM)
+  const int sms = sm_count();
+  if (ceil_div(B, 2) <= sms) return 2;
+  if (ceil_div(B, 4) <= sms) return 4;
+  return 8;
+}
+
+int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace) {
+  if (H > 128) {
+    set_error("bf16 tensor-core LSTM path supports hidden size <= 128 this round (got H=%d); use compute_dtype f32", H);
+    return CSN_EUNSUPPORTED;
+  }
+  if (I % 8 != 0 || H % 8 != 0) {
+    set_error("bf16 tensor-core LSTM path needs input and hidden sizes that are multiples of 8 (I=%d H=%d)", I, H);
+    return CSN_EUNSUPPORTED;
+  }
+  const size_t tb = size_t(T) * B;
+  *reserve = align256(tb * 4 * H * 2) + align256(tb * H * 4);
+  const size_t wf = align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2);
+  const size_t wb = align256(tb * 4 * H * 2) + align256(size_t(4) * H * I * 2);
+  *workspace = wf > wb ? wf : wb;
+  return CSN_OK;
+}
+
+template <int NV>
+static int launch_fwd(const float* xp, const float* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
+                      float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
+  const size_t smem = size_t(4) * 128 * KP * 2 + size_t(KP / 8) * kLboB + 64 + 128;
+  auto kern = lstm_fwd_tc_kernel<NV>;
+  CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+template <int NV>
+static int launch_bwd(const float* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
+                      const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
+                      cudaStream_t s) {
+  const size_t smem = size_t(128) * 4 * KP * 2 + size_t(4 * KP / 8) * kLboB + 64 + 128;
+  auto kern = lstm_bwd_tc_kernel<NV>;
+  CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                      void* h_seq, void* reserve, void* workspace, int T, int B, int I, int H, int training,
+                      cudaStream_t s) {
+  size_t rb, wb;
+  CSN_TRY(lstm_tc_bytes(T, B, I, H, &rb, &wb));
+  const size_t tb = size_t(T) * B;
+  const int KP = ceil_div(H, 16) * 16;
+  float* xp = reinterpret_cast<float*>(workspace);
+  __nv_bfloat16* wih_bf = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 4));
+  __nv_bfloat16* gates = reinterpret_cast<__nv_bfloat16*>(reserve);
+  float* c_out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(reserve) + align256(tb * 4 * H * 2));
+  CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
+  // hoisted input projection: Xp[T*B, 4H] = x[T*B, I] . W_ih[4H, I]^T + b_ih  (fp32 out)
+  CSN_TRY(csn_gemm_bf16_tc(0, 1, (int)tb, 4 * H, I, x, I, wih_bf, I, xp, 4 * H, CSN_F32, b_ih, 0, 1, s));
+  const int nv = pick_nv(B);
+  __nv_bfloat16* g = training ? gates : nullptr;
+  float* c = training ? c_out : nullptr;
+  if (nv == 2) return launch_fwd<2>(xp, w_hh, b_hh, (__nv_bfloat16*)h_seq, g, c, T, B, H, KP, s);
+  if (nv == 4) return launch_fwd<4>(xp, w_hh, b_hh, (__nv_bfloat16*)h_seq, g, c, T, B, H, KP, s);
+  return launch_fwd<8>(xp, w_hh, b_hh, (__nv_bfloat16*)h_seq, g, c, T, B, H, KP, s);
+}
+
+int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const void* h_seq, const void* reserve,
+                      const float* d_hseq, const float* d_hlast, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                      float* dx, void* workspace, int T, int B, int I, int H, int accumulate, cudaStream_t s) {
+  size_t rb, wb;
+  CSN_TRY(lstm_tc_bytes(T, B, I, H, &rb, &wb));
+  const size_t tb = size_t(T) * B;
+  const int KP = ceil_div(H, 16) * 16;
+  const __nv_bfloat16* gates = reinterpret_cast<const __nv_bfloat16*>(reserve);
+  const float* c_seq = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(reserve) + align256(tb * 4 * H * 2));
+  __nv_bfloat16* dG = reinterpret_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* wih_bf = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 2));
+  if (!accumulate) {
+    CSN_CUDA(cudaMemsetAsync(db_ih, 0, size_t(4) * H * 4, s));
+    CSN_CUDA(cudaMemsetAsync(db_hh, 0, size_t(4) * H * 4, s));
+  }
+  const int nv = pick_nv(B);
+  if (nv == 2) CSN_TRY(launch_bwd<2>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
+  else if (nv == 4) CSN_TRY(launch_bwd<4>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
+  else CSN_TRY(launch_bwd<8>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
+  // dW_ih[4H, I] = dG^T . x ; dW_hh[4H, H] = dG[1:]^T . h_seq[:-1]  (contraction over time*batch, split-K)
+  const int sms = sm_count();
+  const int tiles_ih = ceil_div(4 * H, 128) * ceil_div(I, 128), tiles_hh = ceil_div(4 * H, 128) * ceil_div(H, 128);
+  CSN_TRY(csn_gemm_bf16_tc(1, 0, 4 * H, I, (int)tb, dG, 4 * H, x, I, dw_ih, I, CSN_F32, nullptr, accumulate,
+                           max(1, sms / tiles_ih), s));
+  if (T > 1) {
+    CSN_TRY(csn_gemm_bf16_tc(1, 0, 4 * H, H, (int)(tb - B), dG + size_t(B) * 4 * H, 4 * H, h_seq, H, dw_hh, H, CSN_F32,
+                             nullptr, accumulate, max(1, sms / tiles_hh), s));
+  } else if (!accumulate) {
+    CSN_CUDA(cudaMemsetAsync(dw_hh, 0, size_t(4) * H * H * 4, s));
+  }
+  if (dx) {
+    CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
+    CSN_TRY(csn_gemm_bf16_tc(0, 0, (int)tb, I, 4 * H, dG, 4 * H, wih_bf, I, dx, I, CSN_F32, nullptr, 0, 1, s));
+  }
+  return CSN_OK;
+}
+
+// ---------------------------------------------------------------------------------------- bring-up hook
+// D[128, N] = A[128, K] . B[N, K]^T with both operands staged by threads into the no-swizzle canonical layouts
+// (K-major or MN-major), one tcgen05.mma chain, tcgen05.ld epilogue.  Exercises exactly the descriptor
+// conventions the recurrence kernels rely on.
+__global__ void __launch_bounds__(128, 1) dbg_umma_tile_kernel(const __nv_bfloat16* __restrict__ A,
+                                                              const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D,
+                                                              int N, int K, int a_mn, int b_mn) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const uint32_t a_bytes = 128 * K * 2, b_bytes = N * K * 2;
+  uint8_t* sa = base;
+  uint8_t* sb = base + a_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + b_bytes);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t lbo_a = 16 * 128, lbo_b = (N / 8) * 128, sbo = 128;
+  for (int e = tid; e < 128 * K; e += 128) {
+    int r = e / K, k = e % K;
+    uint32_t off = a_mn ? canon_mn_off(r, k, lbo_a, sbo) : canon_k_off(r, k, lbo_a, sbo);
+    *reinterpret_cast<__nv_bfloat16*>(sa + off) = A[e];
+  }
+  for (int e = tid; e < N * K; e += 128) {
+    int r = e / K, k = e % K;
+    uint32_t off = b_mn ? canon_mn_off(r, k, lbo_b, sbo) : canon_k_off(r, k, lbo_b, sbo);
+    *reinterpret_cast<__nv_bfloat16*>(sb + off) = Bm[e];
+  }
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) tmem_alloc(slot, ncols);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn);
+    for (int kk = 0; kk < K / 16; ++kk) {
+      uint64_t da = make_smem_desc(smem_u32(sa) + kk * 2 * lbo_a, lbo_a, sbo, kLayoutNone);
+      uint64_t db = make_smem_desc(smem_u32(sb) + kk * 2 * lbo_b, lbo_b, sbo, kLayoutNone);
+      umma_f16(tmem_base, da, db, idesc, kk != 0);
+    }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tcgen05_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld<16>(tmem_base + (uint32_t(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) D[size_t(tid) * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, ncols); }
+}
+
+}  // namespace csn
+
+using namespace csn;
+
+extern "C" int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, int K, int a_mn_major, int b_mn_major,
+                                 void* stream) {
+  CSN_REQUIRE(A && B && D, "csn_dbg_umma_tile: null pointer");
+  CSN_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, "csn_dbg_umma_tile: bad N/K");
+  const size_t smem = size_t(128) * K * 2 + size_t(N) * K * 2 + 256;
+  CSN_CUDA(cudaFuncSetAttribute(dbg_umma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dbg_umma_tile_kernel<<<1, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, N, K,
+                                                           a_mn_major, b_mn_major);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}

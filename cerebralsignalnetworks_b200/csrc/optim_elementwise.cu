@@ -1,0 +1,247 @@
+// Fused Adam/AdamW over a flat fp32 buffer, activations, row L2-normalise, weight-norm, column sums.
+// All HBM-streaming kernels: float4 where alignment allows, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace csn {
+
+// torch.optim.Adam / AdamW single-tensor semantics (LSTMDistill.py:322, LstmDistillation.py:469-471):
+//   g = grad*grad_scale (+ wd*p if coupled);  p *= 1 - lr*wd if decoupled
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                            int decoupled, float step_size, float inv_sqrt_bc2, float grad_scale) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t n4 = n >> 2;
+  for (; i < n4; i += stride) {
+    float4 P = reinterpret_cast<float4*>(p)[i];
+    float4 G = reinterpret_cast<const float4*>(g)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i];
+    float4 V = reinterpret_cast<float4*>(v)[i];
+    float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gr = gg[j] * grad_scale;
+      if (decoupled) pp[j] *= (1.f - lr * wd); else gr = fmaf(wd, pp[j], gr);
+      mm[j] = b1 * mm[j] + (1.f - b1) * gr;
+      vv[j] = b2 * vv[j] + (1.f - b2) * gr * gr;
+      float denom = sqrtf(vv[j]) * inv_sqrt_bc2 + eps;
+      pp[j] -= step_size * (mm[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+  }
+  // tail
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    size_t j = (n4 << 2) + threadIdx.x;
+    float gr = g[j] * grad_scale;
+    float pj = p[j];
+    if (decoupled) pj *= (1.f - lr * wd); else gr = fmaf(wd, pj, gr);
+    float mj = b1 * m[j] + (1.f - b1) * gr;
+    float vj = b2 * v[j] + (1.f - b2) * gr * gr;
+    pj -= step_size * (mj / (sqrtf(vj) * inv_sqrt_bc2 + eps));
+    p[j] = pj; m[j] = mj; v[j] = vj;
+  }
+}
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, int act) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = x[i];
+    y[i] = act == CSN_ACT_RELU ? fmaxf(v, 0.f) : (act == CSN_ACT_GELU ? gelu_f(v) : v);
+  }
+}
+__global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                               size_t n, int act) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = x[i];
+    float d = act == CSN_ACT_RELU ? (v > 0.f ? 1.f : 0.f) : (act == CSN_ACT_GELU ? gelu_grad_f(v) : 1.f);
+    dx[i] = dy[i] * d;
+  }
+}
+
+// out[n] (+)= sum_m x[m,n]: block = 32 columns x 8 row-lanes, grid.y splits rows; atomics across row splits.
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int ldx, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int m0 = blockIdx.y * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  float acc = 0.f;
+  if (col < N)
+    for (int m = m0 + threadIdx.y; m < m1; m += 8) acc += x[size_t(m) * ldx + col];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+    atomicAdd(out + col, s);
+  }
+}
+
+// one warp per row
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv_norm, int M, int N) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + size_t(row) * N;
+  float ss = 0.f;
+  for (int k = lane; k < N; k += 32) ss = fmaf(xr[k], xr[k], ss);
+  ss = warp_sum(ss);
+  float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int k = lane; k < N; k += 32) y[size_t(row) * N + k] = xr[k] * inv;
+  if (lane == 0) inv_norm[row] = inv;
+}
+// dx = inv * (dy - y * <dy, y>)
+__global__ void l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ inv_norm,
+                                  const float* __restrict__ dy, float* __restrict__ dx, int M, int N) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* yr = y + size_t(row) * N;
+  const float* gr = dy + size_t(row) * N;
+  float dot = 0.f;
+  for (int k = lane; k < N; k += 32) dot = fmaf(gr[k], yr[k], dot);
+  dot = warp_sum(dot);
+  const float inv = inv_norm[row];
+  for (int k = lane; k < N; k += 32) dx[size_t(row) * N + k] = inv * (gr[k] - yr[k] * dot);
+}
+
+__global__ void weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w,
+                                       float* __restrict__ inv_norm, int N, int K) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* vr = v + size_t(row) * K;
+  float ss = 0.f;
+  for (int k = lane; k < K; k += 32) ss = fmaf(vr[k], vr[k], ss);
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss);
+  const float sc = g[row] * inv;
+  for (int k = lane; k < K; k += 32) w[size_t(row) * K + k] = vr[k] * sc;
+  if (lane == 0) inv_norm[row] = inv;
+}
+__global__ void weight_norm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                       const float* __restrict__ inv_norm, const float* __restrict__ dw,
+                                       float* __restrict__ dv, float* __restrict__ dg, int N, int K) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* vr = v + size_t(row) * K;
+  const float* dr = dw + size_t(row) * K;
+  float dot = 0.f;
+  for (int k = lane; k < K; k += 32) dot = fmaf(dr[k], vr[k], dot);
+  dot = warp_sum(dot);
+  const float inv = inv_norm[row], gg = g[row];
+  const float c = dot * inv * inv;
+  for (int k = lane; k < K; k += 32) dv[size_t(row) * K + k] = gg * inv * (dr[k] - vr[k] * c);
+  if (dg && lane == 0) dg[row] = dot * inv;
+}
+
+__global__ void scale_kernel(float* __restrict__ x, size_t n, const float* __restrict__ scale_dev, float scale_host) {
+  const float sc = (scale_dev ? *scale_dev : 1.f) * scale_host;
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) x[i] *= sc;
+}
+
+static inline int stream_blocks(size_t n, int per_block) {
+  size_t b = ceil_div<size_t>(n, per_block);
+  size_t cap = size_t(sm_count()) * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace csn
+
+using namespace csn;
+
+extern "C" int csn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int decoupled, int step,
+                             float grad_scale, void* stream) {
+  CSN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "csn_adam_step: null pointer");
+  CSN_REQUIRE(step >= 1, "csn_adam_step: step is 1-based");
+  CSN_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
+              "csn_adam_step: buffers must be 16-byte aligned");
+  if (n == 0) return CSN_OK;
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  adam_kernel<<<stream_blocks(n, 256 * 4), 256, 0, as_stream(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled, (float)(lr / bc1),
+      (float)(1.0 / sqrt(bc2)), grad_scale);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_scale_f32(float* x, size_t n, const float* scale_dev, float scale_host, void* stream) {
+  CSN_REQUIRE(x, "csn_scale_f32: null pointer");
+  if (n == 0) return CSN_OK;
+  scale_kernel<<<stream_blocks(n, 256), 256, 0, as_stream(stream)>>>(x, n, scale_dev, scale_host);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_act_fwd(const float* x, float* y, size_t n, int act, void* stream) {
+  CSN_REQUIRE(x && y, "csn_act_fwd: null pointer");
+  if (n == 0) return CSN_OK;
+  act_fwd_kernel<<<stream_blocks(n, 256), 256, 0, as_stream(stream)>>>(x, y, n, act);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+extern "C" int csn_act_bwd(const float* x, const float* dy, float* dx, size_t n, int act, void* stream) {
+  CSN_REQUIRE(x && dy && dx, "csn_act_bwd: null pointer");
+  if (n == 0) return CSN_OK;
+  act_bwd_kernel<<<stream_blocks(n, 256), 256, 0, as_stream(stream)>>>(x, dy, dx, n, act);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_colsum_f32(const float* x, float* out, int M, int N, int ldx, int accumulate, void* stream) {
+  CSN_REQUIRE(x && out && M >= 0 && N >= 1 && ldx >= N, "csn_colsum_f32: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  if (!accumulate) CSN_CUDA(cudaMemsetAsync(out, 0, size_t(N) * 4, s));
+  if (M == 0) return CSN_OK;
+  int col_blocks = ceil_div(N, 32);
+  int row_splits = max(1, min(ceil_div(M, 64), ceil_div(sm_count() * 4, col_blocks)));
+  int rows_per_block = ceil_div(M, row_splits);
+  row_splits = ceil_div(M, rows_per_block);
+  colsum_kernel<<<dim3(col_blocks, row_splits), dim3(32, 8), 0, s>>>(x, out, M, N, ldx, rows_per_block);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_l2norm_fwd(const float* x, float* y, float* inv_norm, int M, int N, void* stream) {
+  CSN_REQUIRE(x && y && inv_norm && M >= 1 && N >= 1, "csn_l2norm_fwd: bad arguments");
+  l2norm_fwd_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(x, y, inv_norm, M, N);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+extern "C" int csn_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, float* dx, int M, int N, void* stream) {
+  CSN_REQUIRE(y && inv_norm && dy && dx && M >= 1 && N >= 1, "csn_l2norm_bwd: bad arguments");
+  l2norm_bwd_kernel<<<ceil_div(M, 8), 256, 0, as_stream(stream)>>>(y, inv_norm, dy, dx, M, N);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+extern "C" int csn_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int N, int K, void* stream) {
+  CSN_REQUIRE(v && g && w && inv_norm && N >= 1 && K >= 1, "csn_weight_norm_fwd: bad arguments");
+  weight_norm_fwd_kernel<<<ceil_div(N, 8), 256, 0, as_stream(stream)>>>(v, g, w, inv_norm, N, K);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+extern "C" int csn_weight_norm_bwd(const float* v, const float* g, const float* inv_norm, const float* dw, float* dv,
+                                   float* dg, int N, int K, void* stream) {
+  CSN_REQUIRE(v && g && inv_norm && dw && dv && N >= 1 && K >= 1, "csn_weight_norm_bwd: bad arguments");
+  weight_norm_bwd_kernel<<<ceil_div(N, 8), 256, 0, as_stream(stream)>>>(v, g, inv_norm, dw, dv, dg, N, K);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}

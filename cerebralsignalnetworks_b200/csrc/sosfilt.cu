@@ -1,0 +1,307 @@
+// Band-pass along time as a cascade of DF2T biquads (replaces scipy sosfilt / filtfilt as called at
+// utils/Utilities.py:421-427 with the designs of utils/EEGFilters.py:26-39).
+//
+// Layout: x is [B, C, T] fp32, i.e. N = B*C independent series of T contiguous samples.  One thread owns one
+// series (the recurrence is sequential in t); a block owns R consecutive series.  Global <-> shared traffic is
+// tile-wise and coalesced:
+//   * causal kernel: streams time in chunks of 32 samples, [R x 32] tiles double-buffered with cp.async (16 B),
+//     row stride 36 floats so the per-thread float4 row reads are bank-conflict free; results leave through a
+//     second tile written time-major when the output is the encoder's [T, B, C] layout (fused transpose + cast).
+//   * zero-phase kernel (sosfiltfilt semantics): whole series resident in shared memory, forward then backward
+//     sweep in place, odd extension of 3*ntaps samples generated on the fly, steady-state initial conditions.
+// HBM-bound by design: 8 bytes/sample of traffic against 5*n_sections FMA/sample.
+#include "common.cuh"
+
+namespace csn {
+
+constexpr int kMaxSec = 8;
+constexpr int kTC = 32;  // samples per streamed chunk
+constexpr int kRS = 36;  // shared row stride (floats): 144 B = 16 B * 9 -> conflict-free float4 rows
+
+struct SosCoef {
+  float b0[kMaxSec], b1[kMaxSec], b2[kMaxSec], a1[kMaxSec], a2[kMaxSec], zi1[kMaxSec], zi2[kMaxSec];
+  int padlen;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  int bytes = pred ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int NSEC>
+__device__ __forceinline__ float biquad_cascade(float v, float (&s1)[NSEC], float (&s2)[NSEC], const SosCoef& c) {
+#pragma unroll
+  for (int k = 0; k < NSEC; ++k) {
+    float y = fmaf(c.b0[k], v, s1[k]);
+    s1[k] = fmaf(-c.a1[k], y, fmaf(c.b1[k], v, s2[k]));
+    s2[k] = fmaf(-c.a2[k], y, c.b2[k] * v);
+    v = y;
+  }
+  return v;
+}
+
+__device__ __forceinline__ size_t out_index(int layout, long long r, int t, int Bn, int C, int T) {
+  // r = b*C + c
+  if (layout == CSN_LAYOUT_BCT) return size_t(r) * T + t;
+  if (layout == CSN_LAYOUT_TBC) return size_t(t) * (size_t(Bn) * C) + r;
+  long long b = r / C, cc = r - b * C;  // BTC
+  return (size_t(b) * T + t) * C + cc;
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store_out(OutT* y, size_t i, float v) {
+  if constexpr (sizeof(OutT) == 4) y[i] = v; else y[i] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------ causal
+template <int NSEC, typename OutT>
+__global__ void __launch_bounds__(128) sosfilt_stream_kernel(const float* __restrict__ x, OutT* __restrict__ y,
+                                                             const SosCoef coef, long long n_series, int T, int Bn,
+                                                             int C, int layout, int vec_ok) {
+  extern __shared__ __align__(16) float smem[];
+  const int R = blockDim.x;
+  float* in_tile = smem;                 // [2][R][kRS]
+  float* out_tile = smem + 2 * R * kRS;  // [kTC][R]   (transposed layouts only)
+  const int tid = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * R;
+  const int n_chunks = (T + kTC - 1) / kTC;
+  const bool transposed = (layout != CSN_LAYOUT_BCT);
+
+  float s1[NSEC], s2[NSEC];
+#pragma unroll
+  for (int k = 0; k < NSEC; ++k) s1[k] = s2[k] = 0.f;
+
+  auto issue_load = [&](int chunk, int buf) {
+    const int t0 = chunk * kTC;
+    float* dst = in_tile + buf * R * kRS;
+    if (vec_ok) {
+#pragma unroll
+      for (int j = 0; j < kTC / 4; ++j) {
+        int v = tid + j * R;
+        int row = v >> 3, c4 = v & 7;
+        long long r = r0 + row;
+        int t = t0 + c4 * 4;
+        bool ok = (r < n_series) && (t < T);
+        const float* src = ok ? (x + size_t(r) * T + t) : x;
+        cp_async16(dst + row * kRS + c4 * 4, src, ok);
+      }
+    } else {
+      for (int j = 0; j < kTC; ++j) {
+        int e = tid + j * R;
+        int row = e >> 5, cc = e & 31;
+        long long r = r0 + row;
+        int t = t0 + cc;
+        dst[row * kRS + cc] = (r < n_series && t < T) ? x[size_t(r) * T + t] : 0.f;
+      }
+    }
+    cp_async_commit();
+  };
+
+  issue_load(0, 0);
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const int buf = chunk & 1;
+    cp_async_wait<0>();
+    __syncthreads();  // tile `buf` visible to all; everyone is done with tile buf^1 and with out_tile
+    if (chunk + 1 < n_chunks) issue_load(chunk + 1, buf ^ 1);
+
+    float* row = in_tile + buf * R * kRS + tid * kRS;
+#pragma unroll
+    for (int q = 0; q < kTC / 4; ++q) {
+      float4 v = *reinterpret_cast<float4*>(row + q * 4);
+      v.x = biquad_cascade<NSEC>(v.x, s1, s2, coef);
+      v.y = biquad_cascade<NSEC>(v.y, s1, s2, coef);
+      v.z = biquad_cascade<NSEC>(v.z, s1, s2, coef);
+      v.w = biquad_cascade<NSEC>(v.w, s1, s2, coef);
+      if (transposed) {
+        out_tile[(q * 4 + 0) * R + tid] = v.x;
+        out_tile[(q * 4 + 1) * R + tid] = v.y;
+        out_tile[(q * 4 + 2) * R + tid] = v.z;
+        out_tile[(q * 4 + 3) * R + tid] = v.w;
+      } else {
+        *reinterpret_cast<float4*>(row + q * 4) = v;
+      }
+    }
+    __syncthreads();
+
+    const int t0 = chunk * kTC;
+    if (transposed) {
+      // out_tile[t][s]: consecutive threads -> consecutive series -> consecutive addresses in [T, B*C]
+      for (int j = 0; j < kTC; ++j) {
+        int t = t0 + j;
+        long long r = r0 + tid;
+        if (t < T && r < n_series) store_out<OutT>(y, out_index(layout, r, t, Bn, C, T), out_tile[j * R + tid]);
+      }
+    } else if (vec_ok && sizeof(OutT) == 4) {
+      const float* src = in_tile + buf * R * kRS;
+#pragma unroll
+      for (int j = 0; j < kTC / 4; ++j) {
+        int v = tid + j * R;
+        int rr = v >> 3, c4 = v & 7;
+        long long r = r0 + rr;
+        int t = t0 + c4 * 4;
+        if (r < n_series && t < T)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + size_t(r) * T + t) =
+              *reinterpret_cast<const float4*>(src + rr * kRS + c4 * 4);
+      }
+    } else {
+      const float* src = in_tile + buf * R * kRS;
+      for (int j = 0; j < kTC; ++j) {
+        int e = tid + j * R;
+        int rr = e >> 5, cc = e & 31;
+        long long r = r0 + rr;
+        int t = t0 + cc;
+        if (r < n_series && t < T) store_out<OutT>(y, size_t(r) * T + t, src[rr * kRS + cc]);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------- zero phase
+template <int NSEC, typename OutT>
+__global__ void __launch_bounds__(32) sosfiltfilt_kernel(const float* __restrict__ x, OutT* __restrict__ y,
+                                                         const SosCoef coef, long long n_series, int T, int Bn, int C,
+                                                         int layout, int rows, int row_stride) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * rows;
+  const int p = coef.padlen;
+
+  // coalesced load: one row at a time, lanes along time
+  for (int rr = 0; rr < rows; ++rr) {
+    long long r = r0 + rr;
+    if (r >= n_series) break;
+    const float* src = x + size_t(r) * T;
+    float* dst = smem + rr * row_stride;
+    for (int t = lane; t < T; t += 32) dst[t] = src[t];
+  }
+  __syncwarp();
+
+  if (lane < rows && r0 + lane < n_series) {
+    float* s = smem + lane * row_stride;  // odd stride -> lanes hit distinct banks
+    float s1[NSEC], s2[NSEC];
+    const float x0 = s[0], xl = s[T - 1];
+    // right-edge odd extension inputs, saved before the forward sweep overwrites the tail
+    for (int j = 1; j <= p; ++j) s[T + j - 1] = 2.f * xl - s[T - 1 - j];
+    // forward: steady-state initial condition scaled by the first extended sample
+    const float xe0 = 2.f * x0 - s[p];
+#pragma unroll
+    for (int k = 0; k < NSEC; ++k) { s1[k] = coef.zi1[k] * xe0; s2[k] = coef.zi2[k] * xe0; }
+    for (int j = p; j >= 1; --j) (void)biquad_cascade<NSEC>(2.f * x0 - s[j], s1, s2, coef);
+    for (int t = 0; t < T + p; ++t) s[t] = biquad_cascade<NSEC>(s[t], s1, s2, coef);
+    // backward
+    const float ye0 = s[T + p - 1];
+#pragma unroll
+    for (int k = 0; k < NSEC; ++k) { s1[k] = coef.zi1[k] * ye0; s2[k] = coef.zi2[k] * ye0; }
+    for (int t = T + p - 1; t >= T; --t) (void)biquad_cascade<NSEC>(s[t], s1, s2, coef);
+    for (int t = T - 1; t >= 0; --t) s[t] = biquad_cascade<NSEC>(s[t], s1, s2, coef);
+  }
+  __syncwarp();
+
+  if (layout == CSN_LAYOUT_BCT) {
+    for (int rr = 0; rr < rows; ++rr) {
+      long long r = r0 + rr;
+      if (r >= n_series) break;
+      const float* src = smem + rr * row_stride;
+      for (int t = lane; t < T; t += 32) store_out<OutT>(y, size_t(r) * T + t, src[t]);
+    }
+  } else {
+    // lanes along series: consecutive addresses in [T, B*C]; odd row stride keeps the column read conflict-free
+    for (int t = 0; t < T; ++t) {
+      long long r = r0 + lane;
+      if (lane < rows && r < n_series)
+        store_out<OutT>(y, out_index(layout, r, t, Bn, C, T), smem[lane * row_stride + t]);
+    }
+  }
+}
+
+template <int NSEC, typename OutT>
+static int launch_sosfilt(const float* x, void* y, const SosCoef& coef, int B, int C, int T, int zero_phase,
+                          int layout, cudaStream_t s) {
+  const long long n_series = (long long)B * C;
+  if (!zero_phase) {
+    // rows per block: keep >= 4 blocks per SM in flight when the problem allows, warps of 32 series
+    int R = 64;
+    if (n_series >= (long long)sm_count() * 4 * 128) R = 128;
+    if (n_series < (long long)sm_count() * 64) R = 32;
+    size_t smem = size_t(2) * R * kRS * 4 + size_t(kTC) * R * 4;
+    int vec_ok = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                 ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    unsigned grid = (unsigned)ceil_div<long long>(n_series, R);
+    sosfilt_stream_kernel<NSEC, OutT><<<grid, R, smem, s>>>(x, (OutT*)y, coef, n_series, T, B, C, layout, vec_ok);
+  } else {
+    int row_stride = (T + coef.padlen) | 1;
+    int rows = 32;
+    while (rows > 1 && size_t(rows) * row_stride * 4 > 200 * 1024) rows >>= 1;
+    size_t smem = size_t(rows) * row_stride * 4;
+    if (smem > 227 * 1024) {
+      set_error("csn_sosfilt_f32: zero-phase series too long for shared memory (T=%d)", T);
+      return CSN_EUNSUPPORTED;
+    }
+    auto kern = sosfiltfilt_kernel<NSEC, OutT>;
+    CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)ceil_div<long long>(n_series, rows);
+    kern<<<grid, 32, smem, s>>>(x, (OutT*)y, coef, n_series, T, B, C, layout, rows, row_stride);
+  }
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+template <typename OutT>
+static int dispatch_nsec(int nsec, const float* x, void* y, const SosCoef& coef, int B, int C, int T, int zp,
+                         int layout, cudaStream_t s) {
+  switch (nsec) {
+    case 1: return launch_sosfilt<1, OutT>(x, y, coef, B, C, T, zp, layout, s);
+    case 2: return launch_sosfilt<2, OutT>(x, y, coef, B, C, T, zp, layout, s);
+    case 3: return launch_sosfilt<3, OutT>(x, y, coef, B, C, T, zp, layout, s);
+    case 4: return launch_sosfilt<4, OutT>(x, y, coef, B, C, T, zp, layout, s);
+    case 5: return launch_sosfilt<5, OutT>(x, y, coef, B, C, T, zp, layout, s);
+    case 6: return launch_sosfilt<6, OutT>(x, y, coef, B, C, T, zp, layout, s);
+    case 7: return launch_sosfilt<7, OutT>(x, y, coef, B, C, T, zp, layout, s);
+    case 8: return launch_sosfilt<8, OutT>(x, y, coef, B, C, T, zp, layout, s);
+  }
+  set_error("csn_sosfilt_f32: n_sections must be in [1, 8], got %d", nsec);
+  return CSN_EINVAL;
+}
+
+}  // namespace csn
+
+using namespace csn;
+
+extern "C" int csn_sosfilt_f32(const float* x, void* y, const double* sos, int n_sections, int B, int C, int T,
+                               int zero_phase, int out_layout, int out_dtype, void* stream) {
+  CSN_REQUIRE(x && y && sos, "csn_sosfilt_f32: null pointer");
+  CSN_REQUIRE(n_sections >= 1 && n_sections <= kMaxSec, "csn_sosfilt_f32: n_sections must be in [1, %d]", kMaxSec);
+  CSN_REQUIRE(B >= 0 && C >= 0 && T >= 0, "csn_sosfilt_f32: negative dimension");
+  CSN_REQUIRE(out_layout >= CSN_LAYOUT_BCT && out_layout <= CSN_LAYOUT_TBC, "csn_sosfilt_f32: bad out_layout");
+  CSN_REQUIRE(out_dtype == CSN_F32 || out_dtype == CSN_BF16, "csn_sosfilt_f32: bad out_dtype");
+  if (B == 0 || C == 0 || T == 0) return CSN_OK;
+  SosCoef c{};
+  int nb2 = 0, na2 = 0;
+  double scale = 1.0;
+  for (int k = 0; k < n_sections; ++k) {
+    const double* r = sos + 6 * k;
+    CSN_REQUIRE(r[3] != 0.0, "csn_sosfilt_f32: a0 == 0 in section %d", k);
+    double b0 = r[0] / r[3], b1 = r[1] / r[3], b2 = r[2] / r[3], a1 = r[4] / r[3], a2 = r[5] / r[3];
+    c.b0[k] = (float)b0; c.b1[k] = (float)b1; c.b2[k] = (float)b2; c.a1[k] = (float)a1; c.a2[k] = (float)a2;
+    if (r[2] == 0.0) ++nb2;
+    if (r[5] == 0.0) ++na2;
+    // steady-state (unit-step) state of this DF2T section, scaled by the DC gain of the sections before it
+    double asum = 1.0 + a1 + a2;
+    double yss = (asum != 0.0) ? (b0 + b1 + b2) / asum : 0.0;
+    double z2 = b2 - a2 * yss;
+    double z1 = b1 - a1 * yss + z2;
+    c.zi1[k] = (float)(scale * z1);
+    c.zi2[k] = (float)(scale * z2);
+    scale *= yss;
+  }
+  int ntaps = 2 * n_sections + 1 - (nb2 < na2 ? nb2 : na2);
+  c.padlen = 3 * ntaps;
+  if (zero_phase) CSN_REQUIRE(T > c.padlen, "csn_sosfilt_f32: zero-phase needs T > padlen (%d), got T=%d", c.padlen, T);
+  cudaStream_t s = as_stream(stream);
+  if (out_dtype == CSN_F32) return dispatch_nsec<float>(n_sections, x, y, c, B, C, T, zero_phase, out_layout, s);
+  return dispatch_nsec<__nv_bfloat16>(n_sections, x, y, c, B, C, T, zero_phase, out_layout, s);
+}

@@ -1,0 +1,256 @@
+"""Tensor-level wrappers over the C-ABI.  torch is used for device memory and streams only; every
+arithmetic op here is a kernel of libcsn_b200.so launched on torch's current stream."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, call
+
+_LAYOUTS = {"BCT": _lib.LAYOUT_BCT, "BTC": _lib.LAYOUT_BTC, "TBC": _lib.LAYOUT_TBC}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _dt(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise _lib.CsnError("unsupported dtype %s (float32 / bfloat16 only)" % dtype)
+
+
+def _chk(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.CsnError("%s must live on a CUDA device (no CPU fallback)" % name)
+    if not t.is_contiguous():
+        raise _lib.CsnError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.CsnError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def device_info():
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    call("csn_device_info", C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+# ------------------------------------------------------------------------------------------------ filter
+def sosfilt(x, sos, zero_phase=False, out_layout="BCT", out_dtype=torch.float32, out=None):
+    """x: float32 [B, C, T] on the GPU; sos: float64 [n_sections, 6] (host).  Returns y in `out_layout`."""
+    _chk(x, torch.float32, "x")
+    if x.dim() != 3:
+        raise _lib.CsnError("sosfilt expects [B, C, T], got shape %s" % (tuple(x.shape),))
+    B, Cc, T = x.shape
+    sos = np.ascontiguousarray(np.asarray(sos, dtype=np.float64))
+    if sos.ndim != 2 or sos.shape[1] != 6:
+        raise _lib.CsnError("sos must have shape [n_sections, 6]")
+    shape = {"BCT": (B, Cc, T), "BTC": (B, T, Cc), "TBC": (T, B, Cc)}[out_layout]
+    y = out if out is not None else torch.empty(shape, dtype=out_dtype, device=x.device)
+    _chk(y, out_dtype, "out")
+    call("csn_sosfilt_f32", _p(x), _p(y), sos.ctypes.data_as(C.POINTER(C.c_double)), sos.shape[0], B, Cc, T,
+         1 if zero_phase else 0, _LAYOUTS[out_layout], _dt(out_dtype), _stream())
+    return y
+
+
+def btc_to_tbc(x, out_dtype=torch.float32):
+    _chk(x, torch.float32, "x")
+    B, T, Cc = x.shape
+    y = torch.empty((T, B, Cc), dtype=out_dtype, device=x.device)
+    call("csn_btc_to_tbc", _p(x), _p(y), B, T, Cc, _dt(out_dtype), _stream())
+    return y
+
+
+def cast(x, dtype):
+    _chk(x, name="x")
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    call("csn_cast", _p(x), _dt(x.dtype), _p(y), _dt(dtype), x.numel(), _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ dense
+def gemm_f32(a, b, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, out=None, alpha=1.0, beta=0.0):
+    """out[M,N] = alpha * op(a) @ op(b) + beta*out (+bias)(act).  op(a) [M,K], op(b) [K,N]."""
+    _chk(a, torch.float32, "a"); _chk(b, torch.float32, "b")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    K2, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+    if K != K2:
+        raise _lib.CsnError("gemm_f32: inner dimensions differ (%d vs %d)" % (K, K2))
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _chk(out, torch.float32, "out")
+    call("csn_gemm_f32", int(trans_a), int(trans_b), M, N, K, float(alpha), _p(a), a.shape[1], _p(b), b.shape[1],
+         float(beta), _p(out), N, _p(bias), int(act), _stream())
+    return out
+
+
+def gemm_bf16(a, b, trans_a=False, trans_b=False, bias=None, out=None, out_dtype=torch.float32, accumulate=False,
+              split_k=1):
+    """tcgen05 GEMM; a, b bfloat16.  Same op() convention as gemm_f32."""
+    _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    K2, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+    if K != K2:
+        raise _lib.CsnError("gemm_bf16: inner dimensions differ (%d vs %d)" % (K, K2))
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    _chk(out, name="out")
+    call("csn_gemm_bf16_tc", int(trans_a), int(trans_b), M, N, K, _p(a), a.shape[1], _p(b), b.shape[1], _p(out), N,
+         _dt(out.dtype), _p(bias), int(accumulate), int(split_k), _stream())
+    return out
+
+
+def colsum(x, out=None, accumulate=False):
+    _chk(x, torch.float32, "x")
+    M, N = x.shape
+    if out is None:
+        out = torch.empty((N,), dtype=torch.float32, device=x.device)
+    call("csn_colsum_f32", _p(x), _p(out), M, N, N, int(accumulate), _stream())
+    return out
+
+
+def scale_(x, scale_dev=None, scale_host=1.0):
+    """x *= scale_dev[0] * scale_host in place (scale_dev: 0-d device tensor or None)."""
+    _chk(x, torch.float32, "x")
+    call("csn_scale_f32", _p(x), x.numel(), _p(scale_dev), float(scale_host), _stream())
+    return x
+
+
+def act_fwd(x, act):
+    _chk(x, torch.float32, "x")
+    y = torch.empty_like(x)
+    call("csn_act_fwd", _p(x), _p(y), x.numel(), int(act), _stream())
+    return y
+
+
+def act_bwd(x, dy, act):
+    _chk(x, torch.float32, "x"); _chk(dy, torch.float32, "dy")
+    dx = torch.empty_like(x)
+    call("csn_act_bwd", _p(x), _p(dy), _p(dx), x.numel(), int(act), _stream())
+    return dx
+
+
+def l2norm_fwd(x):
+    _chk(x, torch.float32, "x")
+    M, N = x.shape
+    y = torch.empty_like(x)
+    inv = torch.empty((M,), dtype=torch.float32, device=x.device)
+    call("csn_l2norm_fwd", _p(x), _p(y), _p(inv), M, N, _stream())
+    return y, inv
+
+
+def l2norm_bwd(y, inv, dy):
+    M, N = y.shape
+    dx = torch.empty_like(y)
+    call("csn_l2norm_bwd", _p(y), _p(inv), _p(_chk(dy, torch.float32, "dy")), _p(dx), M, N, _stream())
+    return dx
+
+
+def weight_norm_fwd(v, g):
+    _chk(v, torch.float32, "v")
+    N, K = v.shape
+    w = torch.empty_like(v)
+    inv = torch.empty((N,), dtype=torch.float32, device=v.device)
+    call("csn_weight_norm_fwd", _p(v), _p(_chk(g.reshape(-1), torch.float32, "g")), _p(w), _p(inv), N, K, _stream())
+    return w, inv
+
+
+def weight_norm_bwd(v, g, inv, dw, need_dg=False):
+    N, K = v.shape
+    dv = torch.empty_like(v)
+    dg = torch.empty((N,), dtype=torch.float32, device=v.device) if need_dg else None
+    call("csn_weight_norm_bwd", _p(v), _p(g.reshape(-1)), _p(inv), _p(_chk(dw, torch.float32, "dw")), _p(dv), _p(dg),
+         N, K, _stream())
+    return dv, dg
+
+
+# ------------------------------------------------------------------------------------------------ LSTM
+def lstm_layer_bytes(T, B, I, H, compute_dtype):
+    r, w = C.c_size_t(), C.c_size_t()
+    call("csn_lstm_layer_bytes", T, B, I, H, _dt(compute_dtype), C.byref(r), C.byref(w))
+    return r.value, w.value
+
+
+def lstm_layer_fwd(x, w_ih, w_hh, b_ih, b_hh, compute_dtype, training=True):
+    """x [T,B,I] in compute_dtype -> (h_seq [T,B,H] compute_dtype, reserve, workspace)."""
+    _chk(x, compute_dtype, "x")
+    T, B, I = x.shape
+    H = w_hh.shape[1]
+    for n, w in (("w_ih", w_ih), ("w_hh", w_hh), ("b_ih", b_ih), ("b_hh", b_hh)):
+        _chk(w, torch.float32, n)
+    rb, wb = lstm_layer_bytes(T, B, I, H, compute_dtype)
+    reserve = torch.empty((rb,), dtype=torch.uint8, device=x.device)
+    workspace = torch.empty((wb,), dtype=torch.uint8, device=x.device)
+    h_seq = torch.empty((T, B, H), dtype=compute_dtype, device=x.device)
+    call("csn_lstm_layer_fwd", _p(x), _p(w_ih), _p(w_hh), _p(b_ih), _p(b_hh), _p(h_seq), _p(reserve), _p(workspace),
+         T, B, I, H, _dt(compute_dtype), int(training), _stream())
+    return h_seq, reserve, workspace
+
+
+def lstm_layer_bwd(x, w_ih, w_hh, h_seq, reserve, workspace, d_hseq, d_hlast, grads, need_dx, compute_dtype,
+                   accumulate=False):
+    """grads = (dw_ih, dw_hh, db_ih, db_hh) fp32 tensors written (or accumulated into).  Returns dx or None."""
+    T, B, I = x.shape
+    H = w_hh.shape[1]
+    dw_ih, dw_hh, db_ih, db_hh = grads
+    dx = torch.empty((T, B, I), dtype=torch.float32, device=x.device) if need_dx else None
+    call("csn_lstm_layer_bwd", _p(x), _p(w_ih), _p(w_hh), _p(h_seq), _p(reserve), _p(d_hseq), _p(d_hlast), _p(dw_ih),
+         _p(dw_hh), _p(db_ih), _p(db_hh), _p(dx), _p(workspace), T, B, I, H, _dt(compute_dtype), int(accumulate),
+         _stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ loss / optimiser
+def dino_loss_fwd_bwd(student, teacher, center, student_temp, teacher_temp, mode, grad_scale=1.0, batch_center=None):
+    """student [Vs,B,K] / teacher [Vt,B,K] fp32 (2-D inputs are treated as one view).
+    Returns (loss scalar tensor, d_student, batch_center)."""
+    s3 = student if student.dim() == 3 else student.unsqueeze(0)
+    t3 = teacher if teacher.dim() == 3 else teacher.unsqueeze(0)
+    _chk(s3, torch.float32, "student"); _chk(t3, torch.float32, "teacher"); _chk(center, torch.float32, "center")
+    Vs, B, K = s3.shape
+    Vt = t3.shape[0]
+    if t3.shape[1:] != (B, K):
+        raise _lib.CsnError("teacher shape %s does not match student %s" % (tuple(t3.shape), tuple(s3.shape)))
+    center_rows = center.numel() // K
+    loss = torch.empty((), dtype=torch.float32, device=s3.device)
+    d_student = torch.empty_like(s3)
+    if batch_center is None:
+        n = B * K if mode == _lib.DINO_MULTICROP_REF else K
+        batch_center = torch.zeros((n,), dtype=torch.float32, device=s3.device)
+    call("csn_dino_loss_fwd_bwd", _p(s3), _p(t3), _p(center), center_rows, float(student_temp), float(teacher_temp),
+         _p(loss), _p(d_student), _p(batch_center), Vs, Vt, B, K, int(mode), float(grad_scale), _stream())
+    return loss, d_student.view(student.shape), batch_center
+
+
+def center_ema(center, batch_center, momentum, scale):
+    call("csn_center_ema", _p(center), _p(batch_center), center.numel(), float(momentum), float(scale), _stream())
+    return center
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+              decoupled=False, step=1, grad_scale=1.0):
+    for n, t in (("params", params), ("grads", grads), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _chk(t, torch.float32, n)
+    call("csn_adam_step", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr), float(beta1),
+         float(beta2), float(eps), float(weight_decay), int(decoupled), int(step), float(grad_scale), _stream())
+
+
+def dbg_umma_tile(a, b, a_mn=False, b_mn=False):
+    """a [128,K], b [N,K] bf16 -> a @ b^T fp32 [128,N] through one tcgen05.mma chain (bring-up test hook)."""
+    _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b")
+    N, K = b.shape
+    d = torch.empty((128, N), dtype=torch.float32, device=a.device)
+    call("csn_dbg_umma_tile", _p(a), _p(b), _p(d), N, K, int(a_mn), int(b_mn), _stream())
+    return d

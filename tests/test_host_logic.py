@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference interface: names, signatures, state-dict compatibility, schedules,
+loud failure without the CUDA path."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+import cerebralsignalnetworks_b200 as csn
+from cerebralsignalnetworks_b200 import _lib
+from oracle import distill as od
+
+
+def test_model_signature_and_state_dict_compat():
+    from models.lstm import Model  # the import the reference scripts perform
+    sig = inspect.signature(Model.__init__)
+    assert list(sig.parameters)[1:6] == ["input_size", "lstm_size", "lstm_layers", "output_size", "include_top"]
+    torch.manual_seed(3)
+    ours = Model(input_size=12, lstm_size=16, lstm_layers=2, output_size=10, include_top=True)
+    torch.manual_seed(3)
+    ref = od.Model(input_size=12, lstm_size=16, lstm_layers=2, output_size=10, include_top=True)
+    sd_o, sd_r = ours.state_dict(), ref.state_dict()
+    assert set(sd_o) == set(sd_r)
+    for k in sd_r:  # same seed -> bit-identical initial weights
+        assert torch.equal(sd_o[k], sd_r[k]), k
+    ref.load_state_dict(sd_o)
+    # Eval.py:309-313 strips "backbone." from a MultiCropWrapper checkpoint and loads with strict=False
+    wrapped = {"backbone." + k: v for k, v in sd_o.items()}
+    stripped = {k.replace("backbone.", ""): v for k, v in wrapped.items()}
+    Model(12, 16, 2, 10, True).load_state_dict(stripped, strict=False)
+    # MultiCropWrapper assigns fc/head
+    ours.fc, ours.head = torch.nn.Identity(), torch.nn.Identity()
+
+
+def test_dino_head_param_names_match_reference_layout(golden):
+    g = golden("dino_head.npz")
+    head = csn.DINOHead(16, 24, nlayers=3, hidden_dim=32, bottleneck_dim=8)
+    names = {n for n, _ in head.named_parameters()}
+    assert names == {k[len("param."):] for k in g.files if k.startswith("param.")}
+    assert not head.last_layer.weight_g.requires_grad
+    assert torch.all(head.last_layer.weight_g == 1)
+    for n, p in head.named_parameters():
+        assert tuple(p.shape) == g["param." + n].shape, n
+
+
+def test_dino_loss_signature_and_schedule(golden):
+    g = golden("dino_loss_single.npz")
+    sig = inspect.signature(csn.DINOLoss.__init__)
+    assert list(sig.parameters)[1:9] == ["out_dim", "ncrops", "warmup_teacher_temp", "teacher_temp",
+                                         "warmup_teacher_temp_epochs", "nepochs", "student_temp", "center_momentum"]
+    crit = csn.DINOLoss(48, 4, 1.5, 0.22, 5, 12)
+    np.testing.assert_array_equal(crit.teacher_temp_schedule, g["schedule"])
+    assert crit.center.shape == (1, 48) and "center" in crit.state_dict()
+    assert list(inspect.signature(crit.forward).parameters) == ["student_output", "teacher_output", "epoch"]
+    with pytest.raises(ValueError):  # Q5: nepochs < warmup epochs makes np.ones(negative) raise, as in the reference
+        csn.DINOLoss(8, 1, 1.5, 0.22, 50, 10)
+
+
+def test_eegfilters_attributes(golden):
+    g = golden("filters.npz")
+    f = csn.EEGFilters(1000.0)
+    np.testing.assert_allclose([f.low_cutoff, f.high_cutoff, f.fs, f.low_cutoff_norm, f.high_cutoff_norm],
+                               g["eegfilters_attrs"], rtol=0, atol=0)
+    np.testing.assert_allclose(f.sos(5.0, 95.0, 4), g["sos_5_95"], rtol=1e-12)
+    assert f.sos(order=3).shape == (3, 6) and f.sos(order=5).shape == (5, 6)
+
+
+def test_no_cpu_fallback():
+    """The product path refuses to run without the CUDA device instead of silently computing on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from models.lstm import Model
+    m = Model(8, 8, 1, 8, include_top=False)
+    with pytest.raises(_lib.CsnError):
+        m(torch.zeros(2, 5, 8))
+    with pytest.raises(_lib.CsnError):
+        csn.DINOLoss(8, 1, 1.5, 0.22, 2, 4)(torch.zeros(2, 8), torch.zeros(2, 8), 0)
+    with pytest.raises(_lib.CsnError):
+        csn.EEGFilters(1000.0).apply(torch.zeros(1, 1, 64))
+
+
+def test_product_does_not_import_oracle():
+    import os
+    import re
+    root = os.path.dirname(os.path.abspath(csn.__file__))
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_cli_flags():
+    from cerebralsignalnetworks_b200 import cli
+    a = cli.build_parser().parse_args([])
+    assert a.batch_size == 16 and a.num_epochs == 100 and a.learning_rate == 0.001 and a.seed == 43
+    a = cli.build_parser().parse_args(["--batch_size", "256", "--num_epochs", "3"])
+    assert a.batch_size == 256 and a.num_epochs == 3
