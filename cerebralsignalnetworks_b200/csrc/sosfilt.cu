@@ -273,12 +273,12 @@ using namespace csn;
 
 extern "C" int csn_sosfilt_f32(const float* x, void* y, const double* sos, int n_sections, int B, int C, int T,
                                int zero_phase, int out_layout, int out_dtype, void* stream) {
+  CSN_REQUIRE(B >= 0 && C >= 0 && T >= 0, "csn_sosfilt_f32: negative dimension");
+  if (B == 0 || C == 0 || T == 0) return CSN_OK;  // empty batch: nothing to do (pointers may be null)
   CSN_REQUIRE(x && y && sos, "csn_sosfilt_f32: null pointer");
   CSN_REQUIRE(n_sections >= 1 && n_sections <= kMaxSec, "csn_sosfilt_f32: n_sections must be in [1, %d]", kMaxSec);
-  CSN_REQUIRE(B >= 0 && C >= 0 && T >= 0, "csn_sosfilt_f32: negative dimension");
   CSN_REQUIRE(out_layout >= CSN_LAYOUT_BCT && out_layout <= CSN_LAYOUT_TBC, "csn_sosfilt_f32: bad out_layout");
   CSN_REQUIRE(out_dtype == CSN_F32 || out_dtype == CSN_BF16, "csn_sosfilt_f32: bad out_dtype");
-  if (B == 0 || C == 0 || T == 0) return CSN_OK;
   SosCoef c{};
   int nb2 = 0, na2 = 0;
   double scale = 1.0;

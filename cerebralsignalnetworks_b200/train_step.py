@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _lib, ops
+from . import _lib, dp, ops
 from ._lib import ACT_NONE, ACT_RELU, DINO_SINGLE
 from .functional import encoder_bwd, encoder_fwd, linear_bwd, linear_fwd
 
@@ -31,7 +31,7 @@ class DistillTrainStep:
         self.sos = _IDENTITY_SOS if sos is None else np.asarray(sos, dtype=np.float64)
         self.zero_phase = zero_phase
         self.step_count = 0
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.world = dp.world_size()
         dev = next(model.parameters()).device
         self.device = dev
 
@@ -123,8 +123,7 @@ class DistillTrainStep:
             self.grad_of(m.classifier.weight).zero_()
             self.grad_of(m.classifier.bias).zero_()
         with self._stage("allreduce"):
-            if self.world > 1:
-                dist.all_reduce(self.flat_g)  # gradients and centre statistics in one NCCL call
+            dp.allreduce_flat_(self.flat_g)  # gradients and centre statistics in one NCCL call
         with self._stage("adam_center"):
             ops.adam_step(self.flat_p, self.flat_g[:self.n_param], self.exp_avg, self.exp_avg_sq, self.lr,
                           self.betas[0], self.betas[1], self.eps, self.weight_decay, self.decoupled, self.step_count,
