@@ -18,6 +18,8 @@ using namespace tc;
 constexpr int GBM = 128, GBN = 128, GBK = 64;
 constexpr int kGemmThreads = 192;
 constexpr uint32_t kStageBytes = (GBM * GBK + GBN * GBK) * 2;  // 32 KB
+constexpr int kEpiStride = 36;                                  // floats; 16-byte aligned rows, conflict-free float4
+constexpr uint32_t kEpiBytes = 4 * 32 * kEpiStride * 4;         // one 32x32 staging tile per epilogue warp
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -142,40 +144,81 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       umma_commit(accfull);
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32).  Each warp drains its 32 rows in 32-column
+    // chunks through a private padded shared tile so that global stores are row-contiguous (8 lanes x float4 = one
+    // 128-byte line per row) instead of one 4-byte store per lane per row.
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int gm = m0 + row;
+    float* tile = reinterpret_cast<float*>(smem + size_t(S) * kStageBytes + 256) + quad * (32 * kEpiStride);
     if (n_it > 0) {
       mbar_wait(accfull, 0);
       tcgen05_fence_after();
     }
+    const bool f32_out = (p.d_dtype == CSN_F32);
+    const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    const bool add_bias = p.bias && blockIdx.z == 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < GBN; c0 += 16) {
-      uint32_t r[16];
+    for (int c0 = 0; c0 < GBN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
       if (n_it > 0) {
-        tmem_ld<16>(tmem_base + (uint32_t(quad * 32) << 16) + c0, r);
+        tmem_ld<32>(tmem_base + (uint32_t(quad * 32) << 16) + c0, r);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = 0u;
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (gm < p.M) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int gn = n0 + c0 + j;
-          if (gn < p.N) {
-            float v = __uint_as_float(r[j]);
-            if (p.bias && blockIdx.z == 0) v += p.bias[gn];
-            if (p.d_dtype == CSN_F32) {
-              float* d = reinterpret_cast<float*>(p.D) + size_t(gm) * p.ldd + gn;
-              if (p.atomic) atomicAdd(d, v); else *d = v;
-            } else {
-              reinterpret_cast<__nv_bfloat16*>(p.D)[size_t(gm) * p.ldd + gn] = __float2bfloat16_rn(v);
-            }
+      for (int q4 = 0; q4 < 8; ++q4)
+        *reinterpret_cast<uint4*>(tile + lane * kEpiStride + q4 * 4) = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
+      __syncwarp();
+      const int col4 = (lane & 7) * 4;
+      const int gn = n0 + c0 + col4;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add_bias) {
+        bv.x = gn < p.N ? p.bias[gn] : 0.f;
+        bv.y = gn + 1 < p.N ? p.bias[gn + 1] : 0.f;
+        bv.z = gn + 2 < p.N ? p.bias[gn + 2] : 0.f;
+        bv.w = gn + 3 < p.N ? p.bias[gn + 3] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3);
+        const int gm = m0 + quad * 32 + rr;
+        float4 v = *reinterpret_cast<const float4*>(tile + rr * kEpiStride + col4);
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        if (gm >= p.M || gn >= p.N) continue;
+        if (f32_out) {
+          float* d = reinterpret_cast<float*>(p.D) + size_t(gm) * p.ldd + gn;
+          if (p.atomic) {
+            atomicAdd(d, v.x);
+            if (gn + 1 < p.N) atomicAdd(d + 1, v.y);
+            if (gn + 2 < p.N) atomicAdd(d + 2, v.z);
+            if (gn + 3 < p.N) atomicAdd(d + 3, v.w);
+          } else if (vec_ok && gn + 3 < p.N) {
+            *reinterpret_cast<float4*>(d) = v;
+          } else {
+            d[0] = v.x;
+            if (gn + 1 < p.N) d[1] = v.y;
+            if (gn + 2 < p.N) d[2] = v.z;
+            if (gn + 3 < p.N) d[3] = v.w;
+          }
+        } else {
+          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + size_t(gm) * p.ldd + gn;
+          if (vec_ok && gn + 3 < p.N) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo);
+            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(d) = o;
+          } else {
+            d[0] = __float2bfloat16_rn(v.x);
+            if (gn + 1 < p.N) d[1] = __float2bfloat16_rn(v.y);
+            if (gn + 2 < p.N) d[2] = __float2bfloat16_rn(v.z);
+            if (gn + 3 < p.N) d[3] = __float2bfloat16_rn(v.w);
           }
         }
       }
+      __syncwarp();
     }
   }
   tcgen05_fence_before();
@@ -185,7 +228,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
 template <bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& p, dim3 grid, cudaStream_t s) {
-  const size_t smem = size_t(p.stages) * kStageBytes + 1024 + 256;
+  const size_t smem = size_t(p.stages) * kStageBytes + 1024 + 256 + kEpiBytes;
   auto kern = gemm_tc_kernel<A_MN, B_MN>;
   CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kGemmThreads, smem, s>>>(ta, tb, p);

@@ -27,6 +27,7 @@ constexpr int kRecThreads = 160;  // warps 0-3: epilogue (TMEM lane quadrants 0-
 constexpr uint32_t kLboA = 2048, kSboA = 128;  // 128-row operand: 16 core matrices (128 B) per k-group
 constexpr uint32_t kLboB = 256, kSboB = 128;   // 16-row operand: 2 core matrices per k-group
 constexpr int kNslots = 16;                    // MMA N (batch slots per CTA); NV <= 16 of them are live
+constexpr int kProfSteps = 64;                 // bring-up instrumentation: clock64 stamps for the first steps of CTA 0
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -55,19 +56,21 @@ __device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t w_bytes, size_t b_
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int NV>
+template <int NV, bool ATMEM>
 __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                    __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
-                   int T, int B, int H, int KP) {
+                   int T, int B, int H, int KP, long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
-  const size_t w_bytes = size_t(4) * 128 * KP * 2, b_bytes = size_t(KP / 8) * kLboB;
+  const size_t w_bytes = ATMEM ? 0 : size_t(4) * 128 * KP * 2, b_bytes = size_t(KP / 8) * kLboB;
   RecSmem sm = carve(smem_raw, w_bytes, b_bytes);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b0 = blockIdx.x * NV;
+  constexpr uint32_t kTmemCols = ATMEM ? 512 : 64;
+  constexpr uint32_t kAcol0 = 64, kAgate = 64;  // A operand in TMEM: gate g at columns [64 + 64 g, +KP/2)
 
-  // ---- one-time staging: W_hh -> bf16 canonical K-major blocks; zero the operand buffer ----
-  {
+  // ---- one-time staging: W_hh -> bf16 (shared-memory canonical K-major blocks, or tensor memory) ----
+  if (!ATMEM) {
     const int chunks = 4 * 128 * (KP / 8);  // 16-byte chunks: (g, u, k8)
     for (int c = tid; c < chunks; c += kRecThreads) {
       const int k8 = c % (KP / 8), u = (c / (KP / 8)) % 128, g = c / ((KP / 8) * 128);
@@ -83,19 +86,47 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       *reinterpret_cast<uint4*>(sm.w + size_t(g) * 128 * KP * 2 + canon_k_off(u, k8 * 8, kLboA, kSboA)) =
           make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
-    for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   }
+  for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
     mbar_init(sm.bar_in, 128);
     mbar_init(sm.bar_acc, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(sm.tmem_slot, 64);
+  if (warp == 4) tmem_alloc(sm.tmem_slot, kTmemCols);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
+  if (ATMEM) {
+    // W_hh resident in TENSOR MEMORY: lane = hidden unit u (row of every gate block), 32-bit column c of gate g holds
+    // W_hh[g*H+u][2c], [2c+1] as packed bf16.  tcgen05.st by the four epilogue warps (lane quadrant = warp).
+    if (warp < 4) {
+      const int u = tid;
+      const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int k = (half * 32 + c) * 2;
+            const float v0 = (u < H && k < H) ? w_hh[size_t(g * H + u) * H + k] : 0.f;
+            const float v1 = (u < H && k + 1 < H) ? w_hh[size_t(g * H + u) * H + k + 1] : 0.f;
+            __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
+            r[c] = *reinterpret_cast<uint32_t*>(&bb);
+          }
+          tmem_st32(lane_addr + kAcol0 + g * kAgate + half * 32, r);
+        }
+      }
+      tmem_st_wait();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+  }
 
   if (warp == 4) {
     // ================= MMA issuer =================
@@ -103,18 +134,25 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
       const uint32_t w_addr = smem_u32(sm.w), b_addr = smem_u32(sm.opb);
       const int ksteps = KP / 16;
+      const uint64_t db0 = make_smem_desc(b_addr, kLboB, kSboB, kLayoutNone);
       for (int t = 1; t < T; ++t) {
         mbar_wait(sm.bar_in, (t - 1) & 1);  // h_{t-1} is in shared memory (and TMEM has been drained)
         tcgen05_fence_after();
+        if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 4] = clock64();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t da = make_smem_desc(w_addr + g * (128 * KP * 2) + kk * 2 * kLboA, kLboA, kSboA, kLayoutNone);
-            const uint64_t db = make_smem_desc(b_addr + kk * 2 * kLboB, kLboB, kSboB, kLayoutNone);
-            umma_f16(tmem_base + g * kNslots, da, db, idesc, kk != 0);
+            const uint64_t db = db0 + uint64_t((kk * 2 * kLboB) >> 4);
+            if (ATMEM) {
+              umma_f16_ts(tmem_base + g * kNslots, tmem_base + kAcol0 + g * kAgate + kk * 8, db, idesc, kk != 0);
+            } else {
+              const uint64_t da = make_smem_desc(w_addr + g * (128 * KP * 2) + kk * 2 * kLboA, kLboA, kSboA, kLayoutNone);
+              umma_f16(tmem_base + g * kNslots, da, db, idesc, kk != 0);
+            }
           }
         }
         umma_commit(sm.bar_acc);
+        if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 5] = clock64();
       }
     }
   } else {
@@ -146,13 +184,16 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       for (int g = 0; g < 4; ++g)
 #pragma unroll
         for (int j = 0; j < NV; ++j) pre[g][j] = xcur[g][j] + bias[g];
+      const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && t < kProfSteps;
       if (t > 0) {
         mbar_wait(sm.bar_acc, (t - 1) & 1);
         tcgen05_fence_after();
+        if (do_prof) prof[t * 8 + 0] = clock64();
         uint32_t r[4][NV];
 #pragma unroll
         for (int g = 0; g < 4; ++g) tmem_ld<NV>(lane_addr + g * kNslots, r[g]);
         tmem_ld_wait();
+        if (do_prof) prof[t * 8 + 1] = clock64();
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -182,9 +223,11 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
         }
       }
       // publish h_t to the async proxy, order our TMEM reads before the next MMA, hand over
+      if (do_prof) prof[t * 8 + 2] = clock64();
       fence_proxy_async_smem();
       tcgen05_fence_before();
       mbar_arrive(sm.bar_in);
+      if (do_prof) prof[t * 8 + 3] = clock64();
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -195,25 +238,27 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
   __syncthreads();
   if (warp == 4) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-template <int NV>
+template <int NV, bool ATMEM>
 __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
                    float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP) {
   extern __shared__ uint8_t smem_raw[];
   const int K4 = 4 * KP;
-  const size_t w_bytes = size_t(128) * K4 * 2, b_bytes = size_t(K4 / 8) * kLboB;
+  const size_t w_bytes = ATMEM ? 0 : size_t(128) * K4 * 2, b_bytes = size_t(K4 / 8) * kLboB;
   RecSmem sm = carve(smem_raw, w_bytes, b_bytes);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b0 = blockIdx.x * NV;
+  constexpr uint32_t kTmemCols = ATMEM ? 512 : 32;
+  constexpr uint32_t kAcol0 = 32, kAgate = 64;  // A operand in TMEM: kk = g*KP + u at column 32 + 64 g + u/2
 
   // A operand: A(m = k, kk = g*KP + u) = W_hh[g*H + u][k]   (W_hh^T, K-major in kk)
-  {
+  if (!ATMEM) {
     const int chunks = 128 * (K4 / 8);
     for (int c = tid; c < chunks; c += kRecThreads) {
       const int m = c % 128, q8 = c / 128;      // q8: 8-wide kk group; consecutive threads -> consecutive k (coalesced rows)
@@ -230,33 +275,70 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
       *reinterpret_cast<uint4*>(sm.w + canon_k_off(m, q8 * 8, kLboA, kSboA)) =
           make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
-    for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   }
+  for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
     mbar_init(sm.bar_in, 128);
     mbar_init(sm.bar_acc, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(sm.tmem_slot, 32);
+  if (warp == 4) tmem_alloc(sm.tmem_slot, kTmemCols);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
+  if (ATMEM) {
+    // W_hh^T resident in tensor memory: lane = m (= hidden unit k of the output dh), 32-bit column 32 + 64 g + c holds
+    // W_hh[g*H + 2c][m], W_hh[g*H + 2c + 1][m]   (contraction index kk = g*KP + u).
+    if (warp < 4) {
+      const int m = tid;
+      const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int ua = (half * 32 + c) * 2, ub = ua + 1;
+            const float v0 = (m < H && ua < H) ? w_hh[size_t(g * H + ua) * H + m] : 0.f;
+            const float v1 = (m < H && ub < H) ? w_hh[size_t(g * H + ub) * H + m] : 0.f;
+            __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
+            r[c] = *reinterpret_cast<uint32_t*>(&bb);
+          }
+          tmem_st32(lane_addr + kAcol0 + g * kAgate + half * 32, r);
+        }
+      }
+      tmem_st_wait();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+  }
 
   if (warp == 4) {
     if ((tid & 31) == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
       const uint32_t w_addr = smem_u32(sm.w), b_addr = smem_u32(sm.opb);
-      const int ksteps = K4 / 16;
+      const int ksteps_gate = KP / 16;
+      const uint64_t db0 = make_smem_desc(b_addr, kLboB, kSboB, kLayoutNone);
       int n = 0;
       for (int t = T - 1; t >= 1; --t, ++n) {
         mbar_wait(sm.bar_in, n & 1);  // dG_t^T staged
         tcgen05_fence_after();
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t da = make_smem_desc(w_addr + kk * 2 * kLboA, kLboA, kSboA, kLayoutNone);
-          const uint64_t db = make_smem_desc(b_addr + kk * 2 * kLboB, kLboB, kSboB, kLayoutNone);
-          umma_f16(tmem_base, da, db, idesc, kk != 0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          for (int k2 = 0; k2 < ksteps_gate; ++k2) {
+            const int kk = g * ksteps_gate + k2;  // 16-wide step of the contraction index g*KP + u
+            const uint64_t db = db0 + uint64_t((kk * 2 * kLboB) >> 4);
+            if (ATMEM) {
+              umma_f16_ts(tmem_base, tmem_base + kAcol0 + g * kAgate + k2 * 8, db, idesc, kk != 0);
+            } else {
+              const uint64_t da = make_smem_desc(w_addr + kk * 2 * kLboA, kLboA, kSboA, kLayoutNone);
+              umma_f16(tmem_base, da, db, idesc, kk != 0);
+            }
+          }
         }
         umma_commit(sm.bar_acc);
       }
@@ -348,7 +430,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
   __syncthreads();
   if (warp == 4) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 32);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -380,23 +462,33 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
   return CSN_OK;
 }
 
-template <int NV>
+// W_hh placement: tensor memory (default) or shared memory (CSN_LSTM_W_SMEM=1, kept for A/B measurements)
+static bool weights_in_tmem() {
+  static const bool v = [] {
+    const char* e = getenv("CSN_LSTM_W_SMEM");
+    return !(e && e[0] == '1');
+  }();
+  return v;
+}
+static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (bring-up only)
+
+template <int NV, bool ATMEM>
 static int launch_fwd(const float* xp, const float* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
                       float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
-  const size_t smem = size_t(4) * 128 * KP * 2 + size_t(KP / 8) * kLboB + 64 + 128;
-  auto kern = lstm_fwd_tc_kernel<NV>;
+  const size_t smem = (ATMEM ? 0 : size_t(4) * 128 * KP * 2) + size_t(KP / 8) * kLboB + 64 + 128;
+  auto kern = lstm_fwd_tc_kernel<NV, ATMEM>;
   CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP);
+  kern<<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
 
-template <int NV>
+template <int NV, bool ATMEM>
 static int launch_bwd(const float* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
-  const size_t smem = size_t(128) * 4 * KP * 2 + size_t(4 * KP / 8) * kLboB + 64 + 128;
-  auto kern = lstm_bwd_tc_kernel<NV>;
+  const size_t smem = (ATMEM ? 0 : size_t(128) * 4 * KP * 2) + size_t(4 * KP / 8) * kLboB + 64 + 128;
+  auto kern = lstm_bwd_tc_kernel<NV, ATMEM>;
   CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP);
   CSN_LAUNCH_CHECK();
@@ -420,9 +512,15 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   const int nv = pick_nv(B);
   __nv_bfloat16* g = training ? gates : nullptr;
   float* c = training ? c_out : nullptr;
-  if (nv == 2) return launch_fwd<2>(xp, w_hh, b_hh, (__nv_bfloat16*)h_seq, g, c, T, B, H, KP, s);
-  if (nv == 4) return launch_fwd<4>(xp, w_hh, b_hh, (__nv_bfloat16*)h_seq, g, c, T, B, H, KP, s);
-  return launch_fwd<8>(xp, w_hh, b_hh, (__nv_bfloat16*)h_seq, g, c, T, B, H, KP, s);
+  __nv_bfloat16* hs = (__nv_bfloat16*)h_seq;
+  if (weights_in_tmem()) {
+    if (nv == 2) return launch_fwd<2, true>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
+    if (nv == 4) return launch_fwd<4, true>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
+    return launch_fwd<8, true>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
+  }
+  if (nv == 2) return launch_fwd<2, false>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
+  if (nv == 4) return launch_fwd<4, false>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
+  return launch_fwd<8, false>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
 }
 
 int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const void* h_seq, const void* reserve,
@@ -441,9 +539,15 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
     CSN_CUDA(cudaMemsetAsync(db_hh, 0, size_t(4) * H * 4, s));
   }
   const int nv = pick_nv(B);
-  if (nv == 2) CSN_TRY(launch_bwd<2>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
-  else if (nv == 4) CSN_TRY(launch_bwd<4>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
-  else CSN_TRY(launch_bwd<8>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
+  if (weights_in_tmem()) {
+    if (nv == 2) CSN_TRY((launch_bwd<2, true>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
+    else if (nv == 4) CSN_TRY((launch_bwd<4, true>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
+    else CSN_TRY((launch_bwd<8, true>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
+  } else {
+    if (nv == 2) CSN_TRY((launch_bwd<2, false>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
+    else if (nv == 4) CSN_TRY((launch_bwd<4, false>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
+    else CSN_TRY((launch_bwd<8, false>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
+  }
   // dW_ih[4H, I] = dG^T . x ; dW_hh[4H, H] = dG[1:]^T . h_seq[:-1]  (contraction over time*batch, split-K)
   const int sms = sm_count();
   const int tiles_ih = ceil_div(4 * H, 128) * ceil_div(I, 128), tiles_hh = ceil_div(4 * H, 128) * ceil_div(H, 128);
@@ -468,7 +572,8 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
 // conventions the recurrence kernels rely on.
 __global__ void __launch_bounds__(128, 1) dbg_umma_tile_kernel(const __nv_bfloat16* __restrict__ A,
                                                               const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D,
-                                                              int N, int K, int a_mn, int b_mn) {
+                                                              int N, int K, int a_mode, int b_mn) {
+  // a_mode: 0 = K-major shared memory, 1 = MN-major shared memory, 2 = tensor memory (TS form of tcgen05.mma)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const uint32_t a_bytes = 128 * K * 2, b_bytes = N * K * 2;
@@ -478,10 +583,12 @@ __global__ void __launch_bounds__(128, 1) dbg_umma_tile_kernel(const __nv_bfloat
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t lbo_a = 16 * 128, lbo_b = (N / 8) * 128, sbo = 128;
-  for (int e = tid; e < 128 * K; e += 128) {
-    int r = e / K, k = e % K;
-    uint32_t off = a_mn ? canon_mn_off(r, k, lbo_a, sbo) : canon_k_off(r, k, lbo_a, sbo);
-    *reinterpret_cast<__nv_bfloat16*>(sa + off) = A[e];
+  if (a_mode != 2) {
+    for (int e = tid; e < 128 * K; e += 128) {
+      int r = e / K, k = e % K;
+      uint32_t off = a_mode ? canon_mn_off(r, k, lbo_a, sbo) : canon_k_off(r, k, lbo_a, sbo);
+      *reinterpret_cast<__nv_bfloat16*>(sa + off) = A[e];
+    }
   }
   for (int e = tid; e < N * K; e += 128) {
     int r = e / K, k = e % K;
@@ -489,20 +596,43 @@ __global__ void __launch_bounds__(128, 1) dbg_umma_tile_kernel(const __nv_bfloat
     *reinterpret_cast<__nv_bfloat16*>(sb + off) = Bm[e];
   }
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-  uint32_t ncols = 32;
-  while ((int)ncols < N) ncols <<= 1;
+  const uint32_t a_col0 = 256;  // A operand columns when it lives in tensor memory (K/2 <= 128 columns)
+  const uint32_t ncols = (a_mode == 2) ? 512 : (N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)));
   if (warp == 0) tmem_alloc(slot, ncols);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *slot;
+  if (a_mode == 2) {
+    const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+    for (int c0 = 0; c0 < K / 2; c0 += 32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = (c0 + c) * 2;
+        __nv_bfloat162 bb;
+        bb.x = (k < K) ? A[size_t(tid) * K + k] : __float2bfloat16(0.f);
+        bb.y = (k + 1 < K) ? A[size_t(tid) * K + k + 1] : __float2bfloat16(0.f);
+        r[c] = *reinterpret_cast<uint32_t*>(&bb);
+      }
+      tmem_st32(lane_addr + a_col0 + c0, r);
+    }
+    tmem_st_wait();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+  }
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn);
+    const uint32_t idesc = make_idesc_bf16(128, N, a_mode == 1 ? 1 : 0, b_mn);
     for (int kk = 0; kk < K / 16; ++kk) {
-      uint64_t da = make_smem_desc(smem_u32(sa) + kk * 2 * lbo_a, lbo_a, sbo, kLayoutNone);
       uint64_t db = make_smem_desc(smem_u32(sb) + kk * 2 * lbo_b, lbo_b, sbo, kLayoutNone);
-      umma_f16(tmem_base, da, db, idesc, kk != 0);
+      if (a_mode == 2) {
+        umma_f16_ts(tmem_base, tmem_base + a_col0 + kk * 8, db, idesc, kk != 0);
+      } else {
+        uint64_t da = make_smem_desc(smem_u32(sa) + kk * 2 * lbo_a, lbo_a, sbo, kLayoutNone);
+        umma_f16(tmem_base, da, db, idesc, kk != 0);
+      }
     }
     umma_commit(bar);
   }
@@ -524,10 +654,16 @@ __global__ void __launch_bounds__(128, 1) dbg_umma_tile_kernel(const __nv_bfloat
 
 using namespace csn;
 
+extern "C" int csn_dbg_lstm_profile_buffer(long long* buf) {
+  csn::g_prof_buf = buf;  // device buffer of at least 64*8 int64 (or NULL to switch the stamps off)
+  return CSN_OK;
+}
+
 extern "C" int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, int K, int a_mn_major, int b_mn_major,
                                  void* stream) {
   CSN_REQUIRE(A && B && D, "csn_dbg_umma_tile: null pointer");
   CSN_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, "csn_dbg_umma_tile: bad N/K");
+  CSN_REQUIRE(a_mn_major >= 0 && a_mn_major <= 2, "csn_dbg_umma_tile: a_mn_major must be 0 (K-major smem), 1 (MN-major smem) or 2 (tensor memory)");
   const size_t smem = size_t(128) * K * 2 + size_t(N) * K * 2 + 256;
   CSN_CUDA(cudaFuncSetAttribute(dbg_umma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dbg_umma_tile_kernel<<<1, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, N, K,

@@ -133,6 +133,10 @@ int csn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * One tcgen05.mma tile D[128,N] = A[128,K] * B[N,K]^T with operands staged in the no-swizzle canonical layouts
  * the recurrence kernel uses; a_mn_major / b_mn_major exercise the MN-major descriptors. */
 int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, int K, int a_mn_major, int b_mn_major, void* stream);
+/* a_mn_major = 2 stages A in tensor memory instead (the TS form the recurrence uses for the resident W_hh).
+ * csn_dbg_lstm_profile_buffer: device buffer of >= 64*8 int64 that receives clock64 stamps of the first 64 forward
+ * recurrence steps of CTA 0 (NULL switches the stamps off). */
+int csn_dbg_lstm_profile_buffer(long long* buf);
 
 #ifdef __cplusplus
 }

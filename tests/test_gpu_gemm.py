@@ -28,7 +28,7 @@ def test_gemm_f32(ta, tb, M, N, K):
     np.testing.assert_allclose(out.numpy(), ref.float().numpy(), rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, False), (1, False), (0, True), (1, True), (2, False), (2, True)])
 @pytest.mark.parametrize("N,K", [(16, 16), (16, 128), (64, 64), (256, 32)])
 def test_umma_tile_descriptors(a_mn, b_mn, N, K):
     """One tcgen05.mma chain on thread-staged canonical (no-swizzle) operands: the layout the recurrence uses."""
