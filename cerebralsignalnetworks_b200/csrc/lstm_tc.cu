@@ -24,7 +24,6 @@ namespace csn {
 using namespace tc;
 
 constexpr int kRecThreads = 160;  // warps 0-3: epilogue (TMEM lane quadrants 0-3), warp 4: MMA issuer
-constexpr uint32_t kLboA = 2048, kSboA = 128;  // 128-row operand: 16 core matrices (128 B) per k-group
 constexpr uint32_t kLboB = 256, kSboB = 128;   // 16-row operand: 2 core matrices per k-group
 constexpr int kNslots = 16;                    // MMA N (batch slots per CTA); NV <= 16 of them are live
 constexpr int kProfSteps = 64;                 // bring-up instrumentation: clock64 stamps for the first steps of CTA 0
@@ -37,59 +36,69 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 struct RecSmem {
-  uint8_t* w;      // 4 * 128 * KP * 2 bytes (fwd) / 128 * 4KP * 2 bytes (bwd)
-  uint8_t* opb;    // B operand: h^T (fwd, KP/8 * 256 B) or dG^T (bwd, 4KP/8 * 256 B)
-  uint64_t* bar_in;   // operand ready (epilogue -> issuer)
+  uint8_t* opb;       // B operand: h^T (fwd, KP/8 * 256 B) or dG^T (bwd, 4KP/8 * 256 B), canonical K-major
+  uint64_t* bar_in;   // operand ready (4 epilogue warps -> issuer)
   uint64_t* bar_acc;  // accumulators ready (issuer -> epilogue)
   uint32_t* tmem_slot;
 };
 
-__device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t w_bytes, size_t b_bytes) {
+__device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t b_bytes) {
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~uintptr_t(127));
   RecSmem s;
-  s.w = base;
-  s.opb = base + w_bytes;
+  s.opb = base;
   s.bar_in = reinterpret_cast<uint64_t*>(s.opb + b_bytes);
   s.bar_acc = s.bar_in + 1;
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_acc + 1);
   return s;
 }
 
+// Tensor-memory map (512 columns allocated; lane = hidden unit):
+//   [0, 256)   fp32 accumulators, 16 columns (batch slots) each
+//   [256, 512) resident weights as packed bf16 pairs: gate g at columns 256 + 64 g + k/2
+constexpr uint32_t kTmemCols = 512, kAcol0 = 256, kAgate = 64;
+
+// W block -> tensor memory.  Thread `row` (TMEM lane) writes, for each gate g, the 64 packed columns
+// (elem(g, 2c), elem(g, 2c+1)); elem() returns 0 outside the matrix.
+template <typename F>
+__device__ __forceinline__ void stage_weights_tmem(uint32_t lane_addr, F elem) {
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = (half * 32 + c) * 2;
+        __nv_bfloat162 bb = __floats2bfloat162_rn(elem(g, k), elem(g, k + 1));
+        r[c] = *reinterpret_cast<uint32_t*>(&bb);
+      }
+      tmem_st32(lane_addr + kAcol0 + g * kAgate + half * 32, r);
+    }
+  }
+  tmem_st_wait();
+}
+
 // ------------------------------------------------------------------------------------------------ forward
-template <int NV, bool ATMEM>
+// KS: number of independent accumulation chains per gate.  Consecutive tcgen05.mma into the SAME accumulator are
+// serialised by the tensor pipe (~70 cycles each at N=16, measured); issuing round-robin over 4*KS accumulators
+// keeps the pipe busy, the epilogue adds the KS partial sums.
+template <int NV, int KS>
 __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                    __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
                    int T, int B, int H, int KP, long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
-  const size_t w_bytes = ATMEM ? 0 : size_t(4) * 128 * KP * 2, b_bytes = size_t(KP / 8) * kLboB;
-  RecSmem sm = carve(smem_raw, w_bytes, b_bytes);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const size_t b_bytes = size_t(KP / 8) * kLboB;
+  RecSmem sm = carve(smem_raw, b_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * NV;
-  constexpr uint32_t kTmemCols = ATMEM ? 512 : 64;
-  constexpr uint32_t kAcol0 = 64, kAgate = 64;  // A operand in TMEM: gate g at columns [64 + 64 g, +KP/2)
+  const int ksteps = KP / 16;
+  const int per = (ksteps + KS - 1) / KS;      // K-steps per chain
+  const int nch = (ksteps + per - 1) / per;    // chains that actually receive an MMA (<= KS)
 
-  // ---- one-time staging: W_hh -> bf16 (shared-memory canonical K-major blocks, or tensor memory) ----
-  if (!ATMEM) {
-    const int chunks = 4 * 128 * (KP / 8);  // 16-byte chunks: (g, u, k8)
-    for (int c = tid; c < chunks; c += kRecThreads) {
-      const int k8 = c % (KP / 8), u = (c / (KP / 8)) % 128, g = c / ((KP / 8) * 128);
-      uint32_t packed[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = k8 * 8 + 2 * i;
-        float v0 = (u < H && k < H) ? w_hh[size_t(g * H + u) * H + k] : 0.f;
-        float v1 = (u < H && k + 1 < H) ? w_hh[size_t(g * H + u) * H + k + 1] : 0.f;
-        __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
-        packed[i] = *reinterpret_cast<uint32_t*>(&bb);
-      }
-      *reinterpret_cast<uint4*>(sm.w + size_t(g) * 128 * KP * 2 + canon_k_off(u, k8 * 8, kLboA, kSboA)) =
-          make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    }
-  }
   for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
-    mbar_init(sm.bar_in, 128);
+    mbar_init(sm.bar_in, 4);
     mbar_init(sm.bar_acc, 1);
     fence_mbar_init();
   }
@@ -99,55 +108,35 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
-  if (ATMEM) {
-    // W_hh resident in TENSOR MEMORY: lane = hidden unit u (row of every gate block), 32-bit column c of gate g holds
-    // W_hh[g*H+u][2c], [2c+1] as packed bf16.  tcgen05.st by the four epilogue warps (lane quadrant = warp).
-    if (warp < 4) {
-      const int u = tid;
-      const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
-#pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int k = (half * 32 + c) * 2;
-            const float v0 = (u < H && k < H) ? w_hh[size_t(g * H + u) * H + k] : 0.f;
-            const float v1 = (u < H && k + 1 < H) ? w_hh[size_t(g * H + u) * H + k + 1] : 0.f;
-            __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
-            r[c] = *reinterpret_cast<uint32_t*>(&bb);
-          }
-          tmem_st32(lane_addr + kAcol0 + g * kAgate + half * 32, r);
-        }
-      }
-      tmem_st_wait();
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
+  // W_hh resident in TENSOR MEMORY for the whole sequence: lane = hidden unit u (row of each gate block)
+  if (warp < 4) {
+    const int u = tid;
+    stage_weights_tmem(tmem_base + (uint32_t(warp * 32) << 16), [&](int g, int k) {
+      return (u < H && k < H) ? w_hh[size_t(g * H + u) * H + k] : 0.f;
+    });
   }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
 
   if (warp == 4) {
-    // ================= MMA issuer =================
-    if ((tid & 31) == 0) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
-      const uint32_t w_addr = smem_u32(sm.w), b_addr = smem_u32(sm.opb);
-      const int ksteps = KP / 16;
-      const uint64_t db0 = make_smem_desc(b_addr, kLboB, kSboB, kLayoutNone);
+      const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
       for (int t = 1; t < T; ++t) {
         mbar_wait(sm.bar_in, (t - 1) & 1);  // h_{t-1} is in shared memory (and TMEM has been drained)
         tcgen05_fence_after();
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 4] = clock64();
+        for (int k2 = 0; k2 < per; ++k2) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t db = db0 + uint64_t((kk * 2 * kLboB) >> 4);
-            if (ATMEM) {
-              umma_f16_ts(tmem_base + g * kNslots, tmem_base + kAcol0 + g * kAgate + kk * 8, db, idesc, kk != 0);
-            } else {
-              const uint64_t da = make_smem_desc(w_addr + g * (128 * KP * 2) + kk * 2 * kLboA, kLboA, kSboA, kLayoutNone);
-              umma_f16(tmem_base + g * kNslots, da, db, idesc, kk != 0);
+          for (int s = 0; s < KS; ++s) {
+            const int kk = s * per + k2;
+            if (kk < ksteps) {
+              const uint64_t db = db0 + uint64_t((kk * 2 * kLboB) >> 4);
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                umma_f16_ts(tmem_base + (s * 4 + g) * kNslots, tmem_base + kAcol0 + g * kAgate + kk * 8, db, idesc, k2 != 0);
             }
           }
         }
@@ -189,45 +178,61 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
         mbar_wait(sm.bar_acc, (t - 1) & 1);
         tcgen05_fence_after();
         if (do_prof) prof[t * 8 + 0] = clock64();
-        uint32_t r[4][NV];
+        uint32_t r[KS][4][NV];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld<NV>(lane_addr + g * kNslots, r[g]);
+        for (int s = 0; s < KS; ++s)
+          if (s < nch) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tmem_ld<NV>(lane_addr + (s * 4 + g) * kNslots, r[s][g]);
+          }
         tmem_ld_wait();
+        tcgen05_fence_before();  // our TMEM reads are ordered before the MMAs the next hand-off releases
         if (do_prof) prof[t * 8 + 1] = clock64();
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+        for (int s = 0; s < KS; ++s)
+          if (s < nch) {
 #pragma unroll
-          for (int j = 0; j < NV; ++j) pre[g][j] += __uint_as_float(r[g][j]);
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int j = 0; j < NV; ++j) pre[g][j] += __uint_as_float(r[s][g][j]);
+          }
       }
+      float gi[NV], gf[NV], gg[NV], go[NV];
+      __nv_bfloat16 hb[NV];
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const float ig = sigmoid_fast(pre[0][j]), fg = sigmoid_fast(pre[1][j]);
-        const float gg = tanh_fast(pre[2][j]), og = sigmoid_fast(pre[3][j]);
-        c[j] = fmaf(fg, c[j], ig * gg);
-        const float h = og * tanh_fast(c[j]);
-        const __nv_bfloat16 hb = __float2bfloat16_rn(h);
-        if (active) {
-          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, u, kLboB, kSboB)) = hb;
+        gi[j] = sigmoid_fast(pre[0][j]);
+        gf[j] = sigmoid_fast(pre[1][j]);
+        gg[j] = tanh_fast(pre[2][j]);
+        go[j] = sigmoid_fast(pre[3][j]);
+        c[j] = fmaf(gf[j], c[j], gi[j] * gg[j]);
+        hb[j] = __float2bfloat16_rn(go[j] * tanh_fast(c[j]));
+        if (active) *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, u, kLboB, kSboB)) = hb[j];
+      }
+      // publish h_t to the async proxy and hand over: one arrival per warp
+      if (do_prof) prof[t * 8 + 2] = clock64();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.bar_in);
+      if (do_prof) prof[t * 8 + 3] = clock64();
+      // ---- off the critical path: stream h_t and the BPTT reserve to HBM while the next MMAs run ----
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
           if (b0 + j < B) {
             const size_t cell = (size_t(t) * B + (b0 + j)) * H + u;
-            h_seq[cell] = hb;
+            h_seq[cell] = hb[j];
             if (gates_out) {
               __nv_bfloat16* gr = gates_out + (size_t(t) * B + (b0 + j)) * 4 * H + u;
-              gr[0] = __float2bfloat16_rn(ig);
-              gr[H] = __float2bfloat16_rn(fg);
-              gr[2 * H] = __float2bfloat16_rn(gg);
-              gr[3 * H] = __float2bfloat16_rn(og);
+              gr[0] = __float2bfloat16_rn(gi[j]);
+              gr[H] = __float2bfloat16_rn(gf[j]);
+              gr[2 * H] = __float2bfloat16_rn(gg[j]);
+              gr[3 * H] = __float2bfloat16_rn(go[j]);
               c_out[cell] = c[j];
             }
           }
         }
       }
-      // publish h_t to the async proxy, order our TMEM reads before the next MMA, hand over
-      if (do_prof) prof[t * 8 + 2] = clock64();
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      mbar_arrive(sm.bar_in);
-      if (do_prof) prof[t * 8 + 3] = clock64();
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -243,42 +248,26 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-template <int NV, bool ATMEM>
+// dh_{t-1}^T[k, b] = sum_{kk = g*KP + u} W_hh[g*H + u][k] * dG_t[b, kk]: M = hidden unit k (TMEM lane), K = 4*KP,
+// split over KS independent accumulation chains (see the forward kernel) that the epilogue sums.
+template <int NV, int KS>
 __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
                    float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP) {
   extern __shared__ uint8_t smem_raw[];
   const int K4 = 4 * KP;
-  const size_t w_bytes = ATMEM ? 0 : size_t(128) * K4 * 2, b_bytes = size_t(K4 / 8) * kLboB;
-  RecSmem sm = carve(smem_raw, w_bytes, b_bytes);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const size_t b_bytes = size_t(K4 / 8) * kLboB;
+  RecSmem sm = carve(smem_raw, b_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * NV;
-  constexpr uint32_t kTmemCols = ATMEM ? 512 : 32;
-  constexpr uint32_t kAcol0 = 32, kAgate = 64;  // A operand in TMEM: kk = g*KP + u at column 32 + 64 g + u/2
+  const int ksteps_gate = KP / 16, ksteps = 4 * ksteps_gate;
+  const int per = (ksteps + KS - 1) / KS;
+  const int nch = (ksteps + per - 1) / per;
 
-  // A operand: A(m = k, kk = g*KP + u) = W_hh[g*H + u][k]   (W_hh^T, K-major in kk)
-  if (!ATMEM) {
-    const int chunks = 128 * (K4 / 8);
-    for (int c = tid; c < chunks; c += kRecThreads) {
-      const int m = c % 128, q8 = c / 128;      // q8: 8-wide kk group; consecutive threads -> consecutive k (coalesced rows)
-      const int g = (q8 * 8) / KP, u0 = (q8 * 8) % KP;
-      uint32_t packed[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ua = u0 + 2 * i, ub = ua + 1;
-        float v0 = (m < H && ua < H) ? w_hh[size_t(g * H + ua) * H + m] : 0.f;
-        float v1 = (m < H && ub < H) ? w_hh[size_t(g * H + ub) * H + m] : 0.f;
-        __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
-        packed[i] = *reinterpret_cast<uint32_t*>(&bb);
-      }
-      *reinterpret_cast<uint4*>(sm.w + canon_k_off(m, q8 * 8, kLboA, kSboA)) =
-          make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    }
-  }
   for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
-    mbar_init(sm.bar_in, 128);
+    mbar_init(sm.bar_in, 4);
     mbar_init(sm.bar_acc, 1);
     fence_mbar_init();
   }
@@ -288,55 +277,33 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
-  if (ATMEM) {
-    // W_hh^T resident in tensor memory: lane = m (= hidden unit k of the output dh), 32-bit column 32 + 64 g + c holds
-    // W_hh[g*H + 2c][m], W_hh[g*H + 2c + 1][m]   (contraction index kk = g*KP + u).
-    if (warp < 4) {
-      const int m = tid;
-      const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
-#pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int ua = (half * 32 + c) * 2, ub = ua + 1;
-            const float v0 = (m < H && ua < H) ? w_hh[size_t(g * H + ua) * H + m] : 0.f;
-            const float v1 = (m < H && ub < H) ? w_hh[size_t(g * H + ub) * H + m] : 0.f;
-            __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
-            r[c] = *reinterpret_cast<uint32_t*>(&bb);
-          }
-          tmem_st32(lane_addr + kAcol0 + g * kAgate + half * 32, r);
-        }
-      }
-      tmem_st_wait();
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
+  // W_hh^T resident in tensor memory: lane = m (hidden unit k of dh), column 256 + 64 g + u/2 holds W_hh[g*H+u][m]
+  if (warp < 4) {
+    const int m = tid;
+    stage_weights_tmem(tmem_base + (uint32_t(warp * 32) << 16), [&](int g, int uu) {
+      return (m < H && uu < H) ? w_hh[size_t(g * H + uu) * H + m] : 0.f;
+    });
   }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
 
   if (warp == 4) {
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
-      const uint32_t w_addr = smem_u32(sm.w), b_addr = smem_u32(sm.opb);
-      const int ksteps_gate = KP / 16;
-      const uint64_t db0 = make_smem_desc(b_addr, kLboB, kSboB, kLayoutNone);
+      const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
       int n = 0;
       for (int t = T - 1; t >= 1; --t, ++n) {
         mbar_wait(sm.bar_in, n & 1);  // dG_t^T staged
         tcgen05_fence_after();
+        for (int k2 = 0; k2 < per; ++k2) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          for (int k2 = 0; k2 < ksteps_gate; ++k2) {
-            const int kk = g * ksteps_gate + k2;  // 16-wide step of the contraction index g*KP + u
-            const uint64_t db = db0 + uint64_t((kk * 2 * kLboB) >> 4);
-            if (ATMEM) {
-              umma_f16_ts(tmem_base, tmem_base + kAcol0 + g * kAgate + k2 * 8, db, idesc, kk != 0);
-            } else {
-              const uint64_t da = make_smem_desc(w_addr + kk * 2 * kLboA, kLboA, kSboA, kLayoutNone);
-              umma_f16(tmem_base, da, db, idesc, kk != 0);
+          for (int s = 0; s < KS; ++s) {
+            const int kk = s * per + k2;  // 16-wide step of the contraction index g*KP + u
+            if (kk < ksteps) {
+              const int g = kk / ksteps_gate, kg = kk - g * ksteps_gate;
+              const uint64_t db = db0 + uint64_t((kk * 2 * kLboB) >> 4);
+              umma_f16_ts(tmem_base + s * kNslots, tmem_base + kAcol0 + g * kAgate + kg * 8, db, idesc, k2 != 0);
             }
           }
         }
@@ -377,45 +344,63 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
     int n = 0;
     for (int t = T - 1; t >= 0; --t) {
       load_step(t - 1, nxt);
-      float dh[NV];
+      float dh[NV], tcn[NV], pref[NV];
+      // everything that does not need dh is done before the wait
 #pragma unroll
-      for (int j = 0; j < NV; ++j) dh[j] = cur.dh[j];
+      for (int j = 0; j < NV; ++j) {
+        dh[j] = cur.dh[j];
+        tcn[j] = tanh_fast(cur.c[j]);
+        pref[j] = cur.o[j] * (1.f - tcn[j] * tcn[j]);
+      }
       if (t < T - 1) {
         mbar_wait(sm.bar_acc, (n - 1) & 1);
         tcgen05_fence_after();
-        uint32_t r[NV];
-        tmem_ld<NV>(lane_addr, r);
-        tmem_ld_wait();
+        uint32_t r[KS][NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) dh[j] += __uint_as_float(r[j]);
+        for (int s = 0; s < KS; ++s)
+          if (s < nch) tmem_ld<NV>(lane_addr + s * kNslots, r[s]);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+          if (s < nch) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) dh[j] += __uint_as_float(r[s][j]);
+          }
       }
+      float dg[4][NV];
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const float tcn = tanh_fast(cur.c[j]);
-        const float dct = fmaf(dh[j] * cur.o[j], 1.f - tcn * tcn, dc[j]);
-        const float dgi = dct * cur.g[j] * cur.i[j] * (1.f - cur.i[j]);
-        const float dgf = dct * cur.cp[j] * cur.f[j] * (1.f - cur.f[j]);
-        const float dgg = dct * cur.i[j] * (1.f - cur.g[j] * cur.g[j]);
-        const float dgo = dh[j] * tcn * cur.o[j] * (1.f - cur.o[j]);
+        const float dct = fmaf(dh[j], pref[j], dc[j]);
+        dg[0][j] = dct * cur.g[j] * cur.i[j] * (1.f - cur.i[j]);
+        dg[1][j] = dct * cur.cp[j] * cur.f[j] * (1.f - cur.f[j]);
+        dg[2][j] = dct * cur.i[j] * (1.f - cur.g[j] * cur.g[j]);
+        dg[3][j] = dh[j] * tcn[j] * cur.o[j] * (1.f - cur.o[j]);
         dc[j] = dct * cur.f[j];
         if (active) {
-          const __nv_bfloat16 q0 = __float2bfloat16_rn(dgi), q1 = __float2bfloat16_rn(dgf),
-                              q2 = __float2bfloat16_rn(dgg), q3 = __float2bfloat16_rn(dgo);
-          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, 0 * KP + u, kLboB, kSboB)) = q0;
-          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, 1 * KP + u, kLboB, kSboB)) = q1;
-          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, 2 * KP + u, kLboB, kSboB)) = q2;
-          *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, 3 * KP + u, kLboB, kSboB)) = q3;
-          if (b0 + j < B) {
-            __nv_bfloat16* gr = dG + (size_t(t) * B + (b0 + j)) * 4 * H + u;
-            gr[0] = q0; gr[H] = q1; gr[2 * H] = q2; gr[3 * H] = q3;
-            dbacc[0] += dgi; dbacc[1] += dgf; dbacc[2] += dgg; dbacc[3] += dgo;
-          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, g * KP + u, kLboB, kSboB)) = __float2bfloat16_rn(dg[g][j]);
         }
       }
       fence_proxy_async_smem();
-      tcgen05_fence_before();
-      mbar_arrive(sm.bar_in);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.bar_in);
       ++n;
+      // ---- off the critical path ----
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          if (b0 + j < B) {
+            __nv_bfloat16* gr = dG + (size_t(t) * B + (b0 + j)) * 4 * H + u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              gr[g * H] = __float2bfloat16_rn(dg[g][j]);
+              dbacc[g] += dg[g][j];
+            }
+          }
+        }
+      }
       cur = nxt;
     }
     if (active) {
@@ -462,35 +447,27 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
   return CSN_OK;
 }
 
-// W_hh placement: tensor memory (default) or shared memory (CSN_LSTM_W_SMEM=1, kept for A/B measurements)
-static bool weights_in_tmem() {
-  static const bool v = [] {
-    const char* e = getenv("CSN_LSTM_W_SMEM");
-    return !(e && e[0] == '1');
-  }();
-  return v;
-}
 static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (bring-up only)
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
 
-template <int NV, bool ATMEM>
+template <int NV, int KS>
 static int launch_fwd(const float* xp, const float* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
                       float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
-  const size_t smem = (ATMEM ? 0 : size_t(4) * 128 * KP * 2) + size_t(KP / 8) * kLboB + 64 + 128;
-  auto kern = lstm_fwd_tc_kernel<NV, ATMEM>;
-  CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf);
+  const size_t smem = size_t(KP / 8) * kLboB + 64 + 128;
+  lstm_fwd_tc_kernel<NV, KS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
 
-template <int NV, bool ATMEM>
+template <int NV, int KS>
 static int launch_bwd(const float* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
-  const size_t smem = (ATMEM ? 0 : size_t(128) * 4 * KP * 2) + size_t(4 * KP / 8) * kLboB + 64 + 128;
-  auto kern = lstm_bwd_tc_kernel<NV, ATMEM>;
-  CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP);
+  const size_t smem = size_t(4 * KP / 8) * kLboB + 64 + 128;
+  lstm_bwd_tc_kernel<NV, KS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
@@ -513,14 +490,14 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   __nv_bfloat16* g = training ? gates : nullptr;
   float* c = training ? c_out : nullptr;
   __nv_bfloat16* hs = (__nv_bfloat16*)h_seq;
-  if (weights_in_tmem()) {
-    if (nv == 2) return launch_fwd<2, true>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
-    if (nv == 4) return launch_fwd<4, true>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
-    return launch_fwd<8, true>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
-  }
-  if (nv == 2) return launch_fwd<2, false>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
-  if (nv == 4) return launch_fwd<4, false>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
-  return launch_fwd<8, false>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
+  const int ks = env_int("CSN_LSTM_KS_F", 2);
+#define CSN_FWD(NVV, KSV) return launch_fwd<NVV, KSV>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s)
+  if (ks == 1) { if (nv == 2) CSN_FWD(2, 1); if (nv == 4) CSN_FWD(4, 1); CSN_FWD(8, 1); }
+  if (ks == 4) { if (nv == 2) CSN_FWD(2, 4); if (nv == 4) CSN_FWD(4, 4); CSN_FWD(8, 2); }
+  if (nv == 2) CSN_FWD(2, 2);
+  if (nv == 4) CSN_FWD(4, 2);
+  CSN_FWD(8, 2);
+#undef CSN_FWD
 }
 
 int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const void* h_seq, const void* reserve,
@@ -539,15 +516,12 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
     CSN_CUDA(cudaMemsetAsync(db_hh, 0, size_t(4) * H * 4, s));
   }
   const int nv = pick_nv(B);
-  if (weights_in_tmem()) {
-    if (nv == 2) CSN_TRY((launch_bwd<2, true>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
-    else if (nv == 4) CSN_TRY((launch_bwd<4, true>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
-    else CSN_TRY((launch_bwd<8, true>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
-  } else {
-    if (nv == 2) CSN_TRY((launch_bwd<2, false>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
-    else if (nv == 4) CSN_TRY((launch_bwd<4, false>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
-    else CSN_TRY((launch_bwd<8, false>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));
-  }
+  const int ks = env_int("CSN_LSTM_KS_B", 8);
+#define CSN_BWD(NVV, KSV) CSN_TRY((launch_bwd<NVV, KSV>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)))
+  if (ks == 1) { if (nv == 2) CSN_BWD(2, 1); else if (nv == 4) CSN_BWD(4, 1); else CSN_BWD(8, 1); }
+  else if (ks == 4) { if (nv == 2) CSN_BWD(2, 4); else if (nv == 4) CSN_BWD(4, 4); else CSN_BWD(8, 4); }
+  else { if (nv == 2) CSN_BWD(2, 8); else if (nv == 4) CSN_BWD(4, 8); else CSN_BWD(8, 4); }
+#undef CSN_BWD
   // dW_ih[4H, I] = dG^T . x ; dW_hh[4H, H] = dG[1:]^T . h_seq[:-1]  (contraction over time*batch, split-K)
   const int sms = sm_count();
   const int tiles_ih = ceil_div(4 * H, 128) * ceil_div(I, 128), tiles_hh = ceil_div(4 * H, 128) * ceil_div(H, 128);
