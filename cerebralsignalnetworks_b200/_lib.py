@@ -43,6 +43,7 @@ SIGNATURES = {
     "csn_adam_step": [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _i, _f, _vp],
     "csn_dbg_umma_tile": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "csn_dbg_lstm_profile_buffer": [_vp],
+    "csn_dbg_umma_bench": [_vp, _i, _i, _i, _i, _i, _vp],
 }
 EXTRA_SYMBOLS = ["csn_version", "csn_last_error", "csn_launch_count"]
 

@@ -78,6 +78,44 @@ __device__ __forceinline__ void stage_weights_tmem(uint32_t lane_addr, F elem) {
   tmem_st_wait();
 }
 
+// One timestep's MMAs, fully unrolled so every TMEM address is an immediate (CONST_BASE) or base + immediate.
+// Forward: gate g, K-step kk  ->  D = acc[(chain, g)], A = W_hh block g columns kk*8.., B = h^T k-groups 2kk, 2kk+1.
+template <int KS, bool CONST_BASE>
+__device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps, int per) {
+  const uint32_t tb = CONST_BASE ? 0u : base;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    if (kk < ksteps) {
+      const int s = (KS == 1) ? 0 : kk / per;  // chain of this K-step (uniform)
+      const bool first = (KS == 1) ? (kk == 0) : (kk - s * per == 0);
+      const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        umma_f16_ts(tb + (s * 4 + g) * kNslots, tb + kAcol0 + g * kAgate + kk * 8, db, idesc, first ? 0u : 1u);
+    }
+  }
+}
+// Backward: contraction index kk16 = g*ksteps_gate + kg.
+template <int KS, bool CONST_BASE>
+__device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_gate) {
+  const uint32_t tb = CONST_BASE ? 0u : base;
+  const int ksteps = 4 * ksteps_gate;
+  const int per = (ksteps + KS - 1) / KS;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+#pragma unroll
+    for (int kg = 0; kg < 8; ++kg) {
+      if (kg < ksteps_gate) {
+        const int kk = g * ksteps_gate + kg;
+        const int s = (KS == 1) ? 0 : kk / per;
+        const bool first = (KS == 1) ? (g == 0 && kg == 0) : (kk - s * per == 0);
+        const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
+        umma_f16_ts(tb + s * kNslots, tb + kAcol0 + g * kAgate + kg * 8, db, idesc, first ? 0u : 1u);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 // KS: number of independent accumulation chains per gate.  Consecutive tcgen05.mma into the SAME accumulator are
 // serialised by the tensor pipe (~70 cycles each at N=16, measured); issuing round-robin over 4*KS accumulators
@@ -120,29 +158,23 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
   tcgen05_fence_after();
 
   if (warp == 4) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
-      const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
-      for (int t = 1; t < T; ++t) {
-        mbar_wait(sm.bar_in, (t - 1) & 1);  // h_{t-1} is in shared memory (and TMEM has been drained)
-        tcgen05_fence_after();
+    // ================= MMA issuer: whole warp converged, one ELECTED lane issues =================
+    // (elect.sync lets ptxas feed tcgen05.mma from uniform registers directly; a plain `lane == 0` guard makes it
+    //  emit an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall around every MMA, ~60 cycles each, measured.)
+    constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
+    const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
+    const bool base0 = (tmem_base == 0);  // a 512-column allocation owns the whole TMEM: constant addresses
+    for (int t = 1; t < T; ++t) {
+      mbar_wait(sm.bar_in, (t - 1) & 1);  // h_{t-1} is in shared memory (and TMEM has been drained)
+      tcgen05_fence_after();
+      if (elect_one()) {
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 4] = clock64();
-        for (int k2 = 0; k2 < per; ++k2) {
-#pragma unroll
-          for (int s = 0; s < KS; ++s) {
-            const int kk = s * per + k2;
-            if (kk < ksteps) {
-              const uint64_t db = db0 + uint64_t((kk * 2 * kLboB) >> 4);
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                umma_f16_ts(tmem_base + (s * 4 + g) * kNslots, tmem_base + kAcol0 + g * kAgate + kk * 8, db, idesc, k2 != 0);
-            }
-          }
-        }
+        if (base0) issue_fwd<KS, true>(0u, db0, idesc, ksteps, per);
+        else issue_fwd<KS, false>(tmem_base, db0, idesc, ksteps, per);
         umma_commit(sm.bar_acc);
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 5] = clock64();
       }
+      __syncwarp();
     }
   } else {
     // ================= epilogue: thread = hidden unit u =================
@@ -289,26 +321,19 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
   tcgen05_fence_after();
 
   if (warp == 4) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
-      const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
-      int n = 0;
-      for (int t = T - 1; t >= 1; --t, ++n) {
-        mbar_wait(sm.bar_in, n & 1);  // dG_t^T staged
-        tcgen05_fence_after();
-        for (int k2 = 0; k2 < per; ++k2) {
-#pragma unroll
-          for (int s = 0; s < KS; ++s) {
-            const int kk = s * per + k2;  // 16-wide step of the contraction index g*KP + u
-            if (kk < ksteps) {
-              const int g = kk / ksteps_gate, kg = kk - g * ksteps_gate;
-              const uint64_t db = db0 + uint64_t((kk * 2 * kLboB) >> 4);
-              umma_f16_ts(tmem_base + s * kNslots, tmem_base + kAcol0 + g * kAgate + kg * 8, db, idesc, k2 != 0);
-            }
-          }
-        }
+    constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
+    const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
+    const bool base0 = (tmem_base == 0);
+    int n = 0;
+    for (int t = T - 1; t >= 1; --t, ++n) {
+      mbar_wait(sm.bar_in, n & 1);  // dG_t^T staged
+      tcgen05_fence_after();
+      if (elect_one()) {
+        if (base0) issue_bwd<KS, true>(0u, db0, idesc, ksteps_gate);
+        else issue_bwd<KS, false>(tmem_base, db0, idesc, ksteps_gate);
         umma_commit(sm.bar_acc);
       }
+      __syncwarp();
     }
   } else {
     const int u = tid;
@@ -624,6 +649,88 @@ __global__ void __launch_bounds__(128, 1) dbg_umma_tile_kernel(const __nv_bfloat
   if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, ncols); }
 }
 
+
+// ---- tcgen05.mma issue / completion cost microbenchmark (bring-up): one CTA, 32 unrolled MMAs per repetition ----
+// Addresses are immediates and the issue is elect-guarded, like the recurrence kernels.  NACC accumulators are used
+// round-robin (NACC = 1: every MMA accumulates into the same D).
+template <int NACC, bool TS>
+__device__ __forceinline__ void bench_issue32(uint64_t da0, uint64_t db0, uint32_t idesc, uint32_t lbo_a16, uint32_t lbo_b16) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int kk = i & 7;
+    const uint64_t db = db0 + uint64_t(kk) * (2 * lbo_b16);
+    if (TS) umma_f16_ts((i % NACC) * 16, 256 + kk * 8 + (i >> 3) * 64, db, idesc, 1u);
+    else umma_f16((i % NACC) * 16, da0 + uint64_t(kk) * (2 * lbo_a16), db, idesc, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(128, 1) dbg_umma_bench_kernel(long long* __restrict__ out, int M, int N, int n_acc, int a_mode,
+                                                               int reps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sa = base;                    // A: 128 rows x 128 K bf16 (smem mode)
+  uint8_t* sb = base + 128 * 128 * 2;    // B: up to 256 rows x 128 K bf16
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 256 * 128 * 2);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 * 128 * 2 + 256 * 128 * 2) / 4; i += 128) reinterpret_cast<uint32_t*>(base)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *slot;
+  {
+    uint32_t r[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) r[c] = 0x3c003c00u;
+    for (int c0 = 0; c0 < 512; c0 += 32) tmem_st32(tmem_base + (uint32_t(warp * 32) << 16) + c0, r);
+    tmem_st_wait();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 0 && tmem_base == 0) {
+    const uint32_t idesc = make_idesc_bf16(M, N, 0, 0);
+    const uint32_t lbo_a = (M / 8) * 128, lbo_b = (N / 8) * 128;
+    const uint64_t da0 = make_smem_desc(smem_u32(sa), lbo_a, 128, kLayoutNone);
+    const uint64_t db0 = make_smem_desc(smem_u32(sb), lbo_b, 128, kLayoutNone);
+    uint32_t phase = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+      long long t0 = 0, t1 = 0;
+      if (elect_one()) {
+        t0 = clock64();
+        if (a_mode == 2) {
+          if (n_acc == 1) bench_issue32<1, true>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
+          else if (n_acc == 4) bench_issue32<4, true>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
+          else bench_issue32<8, true>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
+        } else {
+          if (n_acc == 1) bench_issue32<1, false>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
+          else if (n_acc == 4) bench_issue32<4, false>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
+          else bench_issue32<8, false>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
+        }
+        t1 = clock64();
+        umma_commit(bar);
+      }
+      __syncwarp();
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      const long long t2 = clock64();
+      t0 = __shfl_sync(0xffffffffu, t0, 0) | 0;  // elected lane is lane 0 of a converged warp
+      if (tid == 0) {
+        out[rep * 2 + 0] = t1 - t0;
+        out[rep * 2 + 1] = t2 - t0;
+      }
+    }
+  } else if (tid == 0 && tmem_base != 0) {
+    out[0] = -1;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
 }  // namespace csn
 
 using namespace csn;
@@ -642,6 +749,16 @@ extern "C" int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, 
   CSN_CUDA(cudaFuncSetAttribute(dbg_umma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dbg_umma_tile_kernel<<<1, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, N, K,
                                                            a_mn_major, b_mn_major);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_dbg_umma_bench(long long* out, int M, int N, int n_acc, int a_mode, int reps, void* stream) {
+  CSN_REQUIRE(out && (M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && (n_acc == 1 || n_acc == 4 || n_acc == 8) &&
+                  reps >= 1 && reps <= 16, "csn_dbg_umma_bench: bad arguments");
+  const size_t smem = 128 * 128 * 2 + 256 * 128 * 2 + 256;
+  CSN_CUDA(cudaFuncSetAttribute(dbg_umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dbg_umma_bench_kernel<<<1, 128, smem, as_stream(stream)>>>(out, M, N, n_acc, a_mode, reps);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }

@@ -137,6 +137,8 @@ int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, int K, int 
  * csn_dbg_lstm_profile_buffer: device buffer of >= 64*8 int64 that receives clock64 stamps of the first 64 forward
  * recurrence steps of CTA 0 (NULL switches the stamps off). */
 int csn_dbg_lstm_profile_buffer(long long* buf);
+/* tcgen05.mma issue/completion cost microbenchmark: out[2*rep] = issue cycles, out[2*rep+1] = cycles until commit arrives */
+int csn_dbg_umma_bench(long long* out, int M, int N, int n_acc, int a_mode, int reps, void* stream);
 
 #ifdef __cplusplus
 }
