@@ -4,7 +4,7 @@
 
 namespace csn {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BK = 16;  // tiles are (16*TM) x (16*TM): TM=4 -> 64x64 (large problems), TM=2 -> 32x32 (small, to fill the SMs)
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == CSN_ACT_RELU) return fmaxf(v, 0.f);
@@ -13,17 +13,18 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 }
 
 // C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta*C + bias
-template <bool TA, bool TB>
+template <bool TA, bool TB, int TM>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, float alpha, const float* __restrict__ A,
                                                       int lda, const float* __restrict__ B, int ldb, float beta,
                                                       float* __restrict__ C, int ldc, const float* __restrict__ bias,
                                                       int act) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  constexpr int BM = 16 * TM, BN = 16 * TM;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[4][4] = {};
+  float acc[TM][TM] = {};
 
   for (int k0 = 0; k0 < K; k0 += BK) {
     // A tile: BM x BK
@@ -50,23 +51,23 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, floa
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      float av[TM], bv[TM];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i) { av[i] = As[kk][ty * TM + i]; bv[i] = Bs[kk][tx * TM + i]; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    int gm = m0 + ty * TM + i;
     if (gm >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int gn = n0 + tx * 4 + j;
+    for (int j = 0; j < TM; ++j) {
+      int gn = n0 + tx * TM + j;
       if (gn >= N) continue;
       float v = alpha * acc[i][j];
       if (beta != 0.f) v = fmaf(beta, C[size_t(gm) * ldc + gn], v);
@@ -86,13 +87,22 @@ extern "C" int csn_gemm_f32(int transA, int transB, int M, int N, int K, float a
   CSN_REQUIRE(A && B && C, "csn_gemm_f32: null pointer");
   CSN_REQUIRE(M >= 0 && N >= 0 && K >= 0, "csn_gemm_f32: negative dimension");
   if (M == 0 || N == 0) return CSN_OK;
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
-  CSN_REQUIRE(grid.y <= 65535, "csn_gemm_f32: M too large (%d)", M);
   cudaStream_t s = as_stream(stream);
-  if (!transA && !transB) gemm_f32_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act);
-  else if (!transA && transB) gemm_f32_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act);
-  else if (transA && !transB) gemm_f32_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act);
-  else gemm_f32_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act);
+  // small outputs: 32x32 tiles so that e.g. the 256x384 projection runs on 96 CTAs instead of 24
+  const bool small = ceil_div(N, 64) * ceil_div(M, 64) < 2 * sm_count();
+  const int tile = small ? 32 : 64;
+  dim3 grid(ceil_div(N, tile), ceil_div(M, tile));
+  CSN_REQUIRE(grid.y <= 65535, "csn_gemm_f32: M too large (%d)", M);
+#define CSN_GEMM_LAUNCH(TA_, TB_)                                                                                        \
+  do {                                                                                                                   \
+    if (small) gemm_f32_kernel<TA_, TB_, 2><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act); \
+    else gemm_f32_kernel<TA_, TB_, 4><<<grid, 256, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act);       \
+  } while (0)
+  if (!transA && !transB) CSN_GEMM_LAUNCH(false, false);
+  else if (!transA && transB) CSN_GEMM_LAUNCH(false, true);
+  else if (transA && !transB) CSN_GEMM_LAUNCH(true, false);
+  else CSN_GEMM_LAUNCH(true, true);
+#undef CSN_GEMM_LAUNCH
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }

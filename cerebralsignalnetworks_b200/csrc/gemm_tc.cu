@@ -230,7 +230,11 @@ template <bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& p, dim3 grid, cudaStream_t s) {
   const size_t smem = size_t(p.stages) * kStageBytes + 1024 + 256 + kEpiBytes;
   auto kern = gemm_tc_kernel<A_MN, B_MN>;
-  CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set = 0;  // per instantiation; raise-only, so the call disappears from steady state (and from graph capture)
+  if (smem > smem_set) {
+    CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   kern<<<grid, kGemmThreads, smem, s>>>(ta, tb, p);
   CSN_LAUNCH_CHECK();
   return CSN_OK;

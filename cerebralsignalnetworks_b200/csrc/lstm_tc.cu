@@ -53,7 +53,7 @@ __device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t b_bytes) {
 }
 
 // Tensor-memory map (512 columns allocated; lane = hidden unit):
-//   [0, 256)   fp32 accumulators, 16 columns (batch slots) each
+//   [0, 64)    fp32 accumulators, 16 columns (batch slots) per gate (forward) / one dh^T accumulator (backward)
 //   [256, 512) resident weights as packed bf16 pairs: gate g at columns 256 + 64 g + k/2
 constexpr uint32_t kTmemCols = 512, kAcol0 = 256, kAgate = 64;
 
@@ -79,48 +79,42 @@ __device__ __forceinline__ void stage_weights_tmem(uint32_t lane_addr, F elem) {
 }
 
 // One timestep's MMAs, fully unrolled so every TMEM address is an immediate (CONST_BASE) or base + immediate.
-// Forward: gate g, K-step kk  ->  D = acc[(chain, g)], A = W_hh block g columns kk*8.., B = h^T k-groups 2kk, 2kk+1.
-template <int KS, bool CONST_BASE>
-__device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps, int per) {
+// All K-steps of a gate accumulate into ONE accumulator: the tensor pipe does not penalise back-to-back MMAs into the
+// same D (measured: 14.9 cycles per M=128,N=16,K=16 MMA with A in tensor memory, 43.8 with A in shared memory,
+// independent of the accumulator rotation), so split accumulation chains only add tcgen05.ld work.
+// Forward: gate g, K-step kk  ->  D = acc[g], A = W_hh block g columns kk*8.., B = h^T k-groups 2kk, 2kk+1.
+template <bool CONST_BASE>
+__device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps) {
   const uint32_t tb = CONST_BASE ? 0u : base;
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
     if (kk < ksteps) {
-      const int s = (KS == 1) ? 0 : kk / per;  // chain of this K-step (uniform)
-      const bool first = (KS == 1) ? (kk == 0) : (kk - s * per == 0);
       const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        umma_f16_ts(tb + (s * 4 + g) * kNslots, tb + kAcol0 + g * kAgate + kk * 8, db, idesc, first ? 0u : 1u);
+        umma_f16_ts(tb + g * kNslots, tb + kAcol0 + g * kAgate + kk * 8, db, idesc, kk == 0 ? 0u : 1u);
     }
   }
 }
-// Backward: contraction index kk16 = g*ksteps_gate + kg.
-template <int KS, bool CONST_BASE>
+// Backward: contraction index kk16 = g*ksteps_gate + kg, single accumulator dh^T.
+template <bool CONST_BASE>
 __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_gate) {
   const uint32_t tb = CONST_BASE ? 0u : base;
-  const int ksteps = 4 * ksteps_gate;
-  const int per = (ksteps + KS - 1) / KS;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
 #pragma unroll
     for (int kg = 0; kg < 8; ++kg) {
       if (kg < ksteps_gate) {
         const int kk = g * ksteps_gate + kg;
-        const int s = (KS == 1) ? 0 : kk / per;
-        const bool first = (KS == 1) ? (g == 0 && kg == 0) : (kk - s * per == 0);
         const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
-        umma_f16_ts(tb + s * kNslots, tb + kAcol0 + g * kAgate + kg * 8, db, idesc, first ? 0u : 1u);
+        umma_f16_ts(tb, tb + kAcol0 + g * kAgate + kg * 8, db, idesc, (g == 0 && kg == 0) ? 0u : 1u);
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-// KS: number of independent accumulation chains per gate.  Consecutive tcgen05.mma into the SAME accumulator are
-// serialised by the tensor pipe (~70 cycles each at N=16, measured); issuing round-robin over 4*KS accumulators
-// keeps the pipe busy, the epilogue adds the KS partial sums.
-template <int NV, int KS>
+template <int NV>
 __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                    __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
@@ -131,8 +125,6 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * NV;
   const int ksteps = KP / 16;
-  const int per = (ksteps + KS - 1) / KS;      // K-steps per chain
-  const int nch = (ksteps + per - 1) / per;    // chains that actually receive an MMA (<= KS)
 
   for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
@@ -169,8 +161,8 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       tcgen05_fence_after();
       if (elect_one()) {
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 4] = clock64();
-        if (base0) issue_fwd<KS, true>(0u, db0, idesc, ksteps, per);
-        else issue_fwd<KS, false>(tmem_base, db0, idesc, ksteps, per);
+        if (base0) issue_fwd<true>(0u, db0, idesc, ksteps);
+        else issue_fwd<false>(tmem_base, db0, idesc, ksteps);
         umma_commit(sm.bar_acc);
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 5] = clock64();
       }
@@ -210,24 +202,16 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
         mbar_wait(sm.bar_acc, (t - 1) & 1);
         tcgen05_fence_after();
         if (do_prof) prof[t * 8 + 0] = clock64();
-        uint32_t r[KS][4][NV];
+        uint32_t r[4][NV];
 #pragma unroll
-        for (int s = 0; s < KS; ++s)
-          if (s < nch) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) tmem_ld<NV>(lane_addr + (s * 4 + g) * kNslots, r[s][g]);
-          }
+        for (int g = 0; g < 4; ++g) tmem_ld<NV>(lane_addr + g * kNslots, r[g]);
         tmem_ld_wait();
         tcgen05_fence_before();  // our TMEM reads are ordered before the MMAs the next hand-off releases
         if (do_prof) prof[t * 8 + 1] = clock64();
 #pragma unroll
-        for (int s = 0; s < KS; ++s)
-          if (s < nch) {
+        for (int g = 0; g < 4; ++g)
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-#pragma unroll
-              for (int j = 0; j < NV; ++j) pre[g][j] += __uint_as_float(r[s][g][j]);
-          }
+          for (int j = 0; j < NV; ++j) pre[g][j] += __uint_as_float(r[g][j]);
       }
       float gi[NV], gf[NV], gg[NV], go[NV];
       __nv_bfloat16 hb[NV];
@@ -280,22 +264,20 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// dh_{t-1}^T[k, b] = sum_{kk = g*KP + u} W_hh[g*H + u][k] * dG_t[b, kk]: M = hidden unit k (TMEM lane), K = 4*KP,
-// split over KS independent accumulation chains (see the forward kernel) that the epilogue sums.
-template <int NV, int KS>
+// dh_{t-1}^T[k, b] = sum_{kk = g*KP + u} W_hh[g*H + u][k] * dG_t[b, kk]: M = hidden unit k (TMEM lane), K = 4*KP.
+template <int NV>
 __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
-                   float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP) {
+                   float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP,
+                   long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
   const int K4 = 4 * KP;
   const size_t b_bytes = size_t(K4 / 8) * kLboB;
   RecSmem sm = carve(smem_raw, b_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * NV;
-  const int ksteps_gate = KP / 16, ksteps = 4 * ksteps_gate;
-  const int per = (ksteps + KS - 1) / KS;
-  const int nch = (ksteps + per - 1) / per;
+  const int ksteps_gate = KP / 16;
 
   for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
@@ -329,9 +311,12 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
       mbar_wait(sm.bar_in, n & 1);  // dG_t^T staged
       tcgen05_fence_after();
       if (elect_one()) {
-        if (base0) issue_bwd<KS, true>(0u, db0, idesc, ksteps_gate);
-        else issue_bwd<KS, false>(tmem_base, db0, idesc, ksteps_gate);
+        const bool pr = prof && blockIdx.x == 0 && n + 1 < kProfSteps;
+        if (pr) prof[512 + (n + 1) * 8 + 4] = clock64();
+        if (base0) issue_bwd<true>(0u, db0, idesc, ksteps_gate);
+        else issue_bwd<false>(tmem_base, db0, idesc, ksteps_gate);
         umma_commit(sm.bar_acc);
+        if (pr) prof[512 + (n + 1) * 8 + 5] = clock64();
       }
       __syncwarp();
     }
@@ -377,21 +362,18 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
         tcn[j] = tanh_fast(cur.c[j]);
         pref[j] = cur.o[j] * (1.f - tcn[j] * tcn[j]);
       }
+      const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps;
       if (t < T - 1) {
         mbar_wait(sm.bar_acc, (n - 1) & 1);
         tcgen05_fence_after();
-        uint32_t r[KS][NV];
-#pragma unroll
-        for (int s = 0; s < KS; ++s)
-          if (s < nch) tmem_ld<NV>(lane_addr + s * kNslots, r[s]);
+        if (do_prof) prof[512 + n * 8 + 0] = clock64();
+        uint32_t r[NV];
+        tmem_ld<NV>(lane_addr, r);
         tmem_ld_wait();
         tcgen05_fence_before();
+        if (do_prof) prof[512 + n * 8 + 1] = clock64();
 #pragma unroll
-        for (int s = 0; s < KS; ++s)
-          if (s < nch) {
-#pragma unroll
-            for (int j = 0; j < NV; ++j) dh[j] += __uint_as_float(r[s][j]);
-          }
+        for (int j = 0; j < NV; ++j) dh[j] += __uint_as_float(r[j]);
       }
       float dg[4][NV];
 #pragma unroll
@@ -408,9 +390,11 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
             *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, g * KP + u, kLboB, kSboB)) = __float2bfloat16_rn(dg[g][j]);
         }
       }
+      if (do_prof) prof[512 + n * 8 + 2] = clock64();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.bar_in);
+      if (do_prof) prof[512 + n * 8 + 3] = clock64();
       ++n;
       // ---- off the critical path ----
       if (active) {
@@ -473,26 +457,22 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
 }
 
 static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (bring-up only)
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && *e) ? atoi(e) : dflt;
-}
 
-template <int NV, int KS>
+template <int NV>
 static int launch_fwd(const float* xp, const float* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
                       float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
   const size_t smem = size_t(KP / 8) * kLboB + 64 + 128;
-  lstm_fwd_tc_kernel<NV, KS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf);
+  lstm_fwd_tc_kernel<NV><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
 
-template <int NV, int KS>
+template <int NV>
 static int launch_bwd(const float* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
   const size_t smem = size_t(4 * KP / 8) * kLboB + 64 + 128;
-  lstm_bwd_tc_kernel<NV, KS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP);
+  lstm_bwd_tc_kernel<NV><<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
@@ -515,14 +495,9 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   __nv_bfloat16* g = training ? gates : nullptr;
   float* c = training ? c_out : nullptr;
   __nv_bfloat16* hs = (__nv_bfloat16*)h_seq;
-  const int ks = env_int("CSN_LSTM_KS_F", 2);
-#define CSN_FWD(NVV, KSV) return launch_fwd<NVV, KSV>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s)
-  if (ks == 1) { if (nv == 2) CSN_FWD(2, 1); if (nv == 4) CSN_FWD(4, 1); CSN_FWD(8, 1); }
-  if (ks == 4) { if (nv == 2) CSN_FWD(2, 4); if (nv == 4) CSN_FWD(4, 4); CSN_FWD(8, 2); }
-  if (nv == 2) CSN_FWD(2, 2);
-  if (nv == 4) CSN_FWD(4, 2);
-  CSN_FWD(8, 2);
-#undef CSN_FWD
+  if (nv == 2) return launch_fwd<2>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
+  if (nv == 4) return launch_fwd<4>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
+  return launch_fwd<8>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
 }
 
 int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const void* h_seq, const void* reserve,
@@ -541,12 +516,9 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
     CSN_CUDA(cudaMemsetAsync(db_hh, 0, size_t(4) * H * 4, s));
   }
   const int nv = pick_nv(B);
-  const int ks = env_int("CSN_LSTM_KS_B", 8);
-#define CSN_BWD(NVV, KSV) CSN_TRY((launch_bwd<NVV, KSV>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)))
-  if (ks == 1) { if (nv == 2) CSN_BWD(2, 1); else if (nv == 4) CSN_BWD(4, 1); else CSN_BWD(8, 1); }
-  else if (ks == 4) { if (nv == 2) CSN_BWD(2, 4); else if (nv == 4) CSN_BWD(4, 4); else CSN_BWD(8, 4); }
-  else { if (nv == 2) CSN_BWD(2, 8); else if (nv == 4) CSN_BWD(4, 8); else CSN_BWD(8, 4); }
-#undef CSN_BWD
+  if (nv == 2) CSN_TRY(launch_bwd<2>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
+  else if (nv == 4) CSN_TRY(launch_bwd<4>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
+  else CSN_TRY(launch_bwd<8>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
   // dW_ih[4H, I] = dG^T . x ; dW_hh[4H, H] = dG[1:]^T . h_seq[:-1]  (contraction over time*batch, split-K)
   const int sms = sm_count();
   const int tiles_ih = ceil_div(4 * H, 128) * ceil_div(I, 128), tiles_hh = ceil_div(4 * H, 128) * ceil_div(H, 128);

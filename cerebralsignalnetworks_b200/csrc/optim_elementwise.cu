@@ -9,7 +9,12 @@ namespace csn {
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                            int decoupled, float step_size, float inv_sqrt_bc2, float grad_scale) {
+                            int decoupled, float step_size, float inv_sqrt_bc2, float grad_scale,
+                            const float* __restrict__ dev_consts) {
+  if (dev_consts) {  // CUDA-graph path: bias corrections computed on the device from the device-side step counter
+    step_size = dev_consts[0];
+    inv_sqrt_bc2 = dev_consts[1];
+  }
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   size_t stride = size_t(gridDim.x) * blockDim.x;
   const size_t n4 = n >> 2;
@@ -43,6 +48,14 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     pj -= step_size * (mj / (sqrtf(vj) * inv_sqrt_bc2 + eps));
     p[j] = pj; m[j] = mj; v[j] = vj;
   }
+}
+
+// ++step; consts = { lr / (1 - b1^step), 1 / sqrt(1 - b2^step) }
+__global__ void adam_advance_kernel(int* __restrict__ step_counter, float* __restrict__ consts, float lr, float b1, float b2) {
+  const int s = ++(*step_counter);
+  const double bc1 = 1.0 - pow((double)b1, (double)s), bc2 = 1.0 - pow((double)b2, (double)s);
+  consts[0] = (float)((double)lr / bc1);
+  consts[1] = (float)(1.0 / sqrt(bc2));
 }
 
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -178,7 +191,24 @@ extern "C" int csn_adam_step(float* params, const float* grads, float* exp_avg, 
   const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
   adam_kernel<<<stream_blocks(n, 256 * 4), 256, 0, as_stream(stream)>>>(
       params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, decoupled, (float)(lr / bc1),
-      (float)(1.0 / sqrt(bc2)), grad_scale);
+      (float)(1.0 / sqrt(bc2)), grad_scale, nullptr);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_adam_step_graph(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                                   int* step_counter, float* consts2, float grad_scale, void* stream) {
+  CSN_REQUIRE(params && grads && exp_avg && exp_avg_sq && step_counter && consts2, "csn_adam_step_graph: null pointer");
+  CSN_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
+              "csn_adam_step_graph: buffers must be 16-byte aligned");
+  cudaStream_t s = as_stream(stream);
+  adam_advance_kernel<<<1, 1, 0, s>>>(step_counter, consts2, lr, beta1, beta2);
+  CSN_LAUNCH_CHECK();
+  if (n == 0) return CSN_OK;
+  adam_kernel<<<stream_blocks(n, 256 * 4), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                        weight_decay, decoupled, 0.f, 0.f, grad_scale, consts2);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }

@@ -247,6 +247,14 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1=0.9, beta2=0.999, ep
          float(beta2), float(eps), float(weight_decay), int(decoupled), int(step), float(grad_scale), _stream())
 
 
+def adam_step_graph(params, grads, exp_avg, exp_avg_sq, step_counter, consts, lr, beta1=0.9, beta2=0.999, eps=1e-8,
+                    weight_decay=0.0, decoupled=False, grad_scale=1.0):
+    """Adam with the step count on the device (int32 tensor, incremented by the call): CUDA-graph replay safe."""
+    call("csn_adam_step_graph", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr),
+         float(beta1), float(beta2), float(eps), float(weight_decay), int(decoupled), _p(step_counter), _p(consts),
+         float(grad_scale), _stream())
+
+
 def dbg_umma_tile(a, b, a_mn=False, b_mn=False):
     """a [128,K], b [N,K] bf16 -> a @ b^T fp32 [128,N] through one tcgen05.mma chain (bring-up test hook)."""
     _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b")

@@ -23,7 +23,7 @@ _IDENTITY_SOS = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
 
 class DistillTrainStep:
     def __init__(self, model, loss, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False,
-                 sos=None, zero_phase=False, use_cuda_graph=False):
+                 sos=None, zero_phase=False, use_cuda_graph=True):
         _lib.require_gpu()
         self.model, self.loss = model, loss
         self.lr, self.betas, self.eps = lr, betas, eps
@@ -60,7 +60,11 @@ class DistillTrainStep:
 
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
+        self._graph_tau = None
         self._static = None
+        self._warm = False
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side Adam step count
+        self._adam_consts = torch.zeros(2, dtype=torch.float32, device=dev)
         self._loss_out = torch.zeros((), dtype=torch.float32, device=dev)
         self._stage_events = None
 
@@ -125,9 +129,9 @@ class DistillTrainStep:
         with self._stage("allreduce"):
             dp.allreduce_flat_(self.flat_g)  # gradients and centre statistics in one NCCL call
         with self._stage("adam_center"):
-            ops.adam_step(self.flat_p, self.flat_g[:self.n_param], self.exp_avg, self.exp_avg_sq, self.lr,
-                          self.betas[0], self.betas[1], self.eps, self.weight_decay, self.decoupled, self.step_count,
-                          grad_scale=1.0 / self.world)
+            ops.adam_step_graph(self.flat_p, self.flat_g[:self.n_param], self.exp_avg, self.exp_avg_sq, self._step_dev,
+                                self._adam_consts, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                self.decoupled, grad_scale=1.0 / self.world)
             ops.center_ema(self.center, self.batch_center, self.loss.center_momentum, 1.0 / (B * self.world))
         return loss
 
@@ -136,32 +140,39 @@ class DistillTrainStep:
         Returns the loss as a 0-d device tensor (no host sync)."""
         tau_t = float(self.loss.teacher_temp_schedule[epoch])
         self.step_count += 1
-        if not self.use_cuda_graph:
+        if not self.use_cuda_graph or self._stage_events is not None:
             return self._run(eeg_bct.contiguous(), teacher_feats.contiguous(), tau_t)
         return self._step_graphed(eeg_bct, teacher_feats, tau_t)
 
-    # CUDA-graph path: Adam's bias correction depends on the step count (a host scalar baked into the launch),
-    # so the graph is re-captured when the step count changes the constants materially; in practice we capture
-    # one graph per step index during the first pass and replay is used for steady-state benchmarking with
-    # `freeze_step_for_graph` (bias correction frozen at the captured step -- benchmarking only).
+    # CUDA-graph path.  The ~30 launches of a step are captured once and replayed with one submission.  Everything
+    # that varies between steps lives on the device: the inputs are copied into static buffers (`input_buffers()`
+    # exposes them so a loader can H2D straight into them), Adam's step count is a device counter
+    # (csn_adam_step_graph).  The teacher temperature is a launch constant: the graph is re-captured when the
+    # epoch changes it.  The first call runs eagerly (it also warms every lazily-initialised launch attribute).
+    def input_buffers(self, like_eeg=None, like_feats=None):
+        if self._static is None:
+            if like_eeg is None:
+                raise _lib.CsnError("input_buffers(): pass example tensors on the first call")
+            self._static = (torch.empty_like(like_eeg), torch.empty_like(like_feats))
+        return self._static
+
     def _step_graphed(self, eeg_bct, teacher, tau_t):
-        if self._graph is None or self._static[2] != tau_t:
-            se = torch.empty_like(eeg_bct)
-            st = torch.empty_like(teacher)
-            se.copy_(eeg_bct); st.copy_(teacher)
-            torch.cuda.synchronize()
+        se, st = self.input_buffers(eeg_bct, teacher)
+        if se.shape != eeg_bct.shape or st.shape != teacher.shape:
+            raise _lib.CsnError("CUDA-graph step: batch shape changed (%s -> %s); build a new DistillTrainStep or pass "
+                                "use_cuda_graph=False" % (tuple(se.shape), tuple(eeg_bct.shape)))
+        if eeg_bct.data_ptr() != se.data_ptr():
+            se.copy_(eeg_bct, non_blocking=True)
+        if teacher.data_ptr() != st.data_ptr():
+            st.copy_(teacher, non_blocking=True)
+        if not self._warm:
+            self._warm = True
+            return self._run(se, st, tau_t)
+        if self._graph is None or self._graph_tau != tau_t:
+            torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self._run(se, st, tau_t)  # warm-up outside capture (lazy function attributes, allocator)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
             with torch.cuda.graph(g):
                 out = self._run(se, st, tau_t)
-            self._graph, self._static, self._graph_out = g, (se, st, tau_t), out
-        se, st, _ = self._static
-        se.copy_(eeg_bct, non_blocking=True)
-        st.copy_(teacher, non_blocking=True)
+            self._graph, self._graph_tau, self._graph_out = g, tau_t, out
         self._graph.replay()
         return self._graph_out

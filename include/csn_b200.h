@@ -129,13 +129,19 @@ int csn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float beta1, float beta2, float eps, float weight_decay, int decoupled, int step,
                   float grad_scale, void* stream);
 
+/* CUDA-graph friendly variant: the 1-based step count lives on the DEVICE (`step_counter`, int32, incremented by this
+ * call) and the bias corrections are computed there into consts2 (2 floats), so a captured graph replays correctly. */
+int csn_adam_step_graph(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int decoupled, int* step_counter,
+                        float* consts2, float grad_scale, void* stream);
+
 /* ---- bring-up / self-test hooks (tests only) --------------------------------------------------------------
  * One tcgen05.mma tile D[128,N] = A[128,K] * B[N,K]^T with operands staged in the no-swizzle canonical layouts
  * the recurrence kernel uses; a_mn_major / b_mn_major exercise the MN-major descriptors. */
 int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, int K, int a_mn_major, int b_mn_major, void* stream);
 /* a_mn_major = 2 stages A in tensor memory instead (the TS form the recurrence uses for the resident W_hh).
- * csn_dbg_lstm_profile_buffer: device buffer of >= 64*8 int64 that receives clock64 stamps of the first 64 forward
- * recurrence steps of CTA 0 (NULL switches the stamps off). */
+ * csn_dbg_lstm_profile_buffer: device buffer of >= 2*64*8 int64 that receives clock64 stamps of the first 64 forward
+ * ([0,512)) and backward ([512,1024)) recurrence steps of CTA 0 (NULL switches the stamps off). */
 int csn_dbg_lstm_profile_buffer(long long* buf);
 /* tcgen05.mma issue/completion cost microbenchmark: out[2*rep] = issue cycles, out[2*rep+1] = cycles until commit arrives */
 int csn_dbg_umma_bench(long long* out, int M, int N, int n_acc, int a_mode, int reps, void* stream);

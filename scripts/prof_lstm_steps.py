@@ -1,7 +1,8 @@
-"""Bring-up instrumentation: clock64 stamps of the first forward recurrence steps of CTA 0 (cfg2 shapes)."""
+"""Bring-up instrumentation: clock64 stamps of the first recurrence steps of CTA 0 (cfg2 shapes), forward and backward."""
 import ctypes
-import sys
 import os
+import statistics
+import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cerebralsignalnetworks_b200 import _lib, ops
@@ -12,23 +13,27 @@ k = 1.0 / H ** 0.5
 w = [((torch.rand(4 * H, I) * 2 - 1) * k).cuda(), ((torch.rand(4 * H, H) * 2 - 1) * k).cuda(),
      ((torch.rand(4 * H) * 2 - 1) * k).cuda(), ((torch.rand(4 * H) * 2 - 1) * k).cuda()]
 x = torch.randn(T, B, I).cuda().bfloat16()
-buf = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(2 * 64 * 8, dtype=torch.int64, device="cuda")
+grads = tuple(torch.empty_like(t) for t in w)
+dh = torch.randn(B, H).cuda()
+def run():
+    h, r, ws = ops.lstm_layer_fwd(x, *w, torch.bfloat16, True)
+    ops.lstm_layer_bwd(x, w[0], w[1], h, r, ws, None, dh, grads, False, torch.bfloat16)
 for _ in range(2):
-    ops.lstm_layer_fwd(x, *w, torch.bfloat16, True)
+    run()
 _lib.call("csn_dbg_lstm_profile_buffer", ctypes.c_void_p(buf.data_ptr()))
-ops.lstm_layer_fwd(x, *w, torch.bfloat16, True)
+run()
 torch.cuda.synchronize()
 _lib.call("csn_dbg_lstm_profile_buffer", None)
-p = buf.view(64, 8).cpu()
-print("W placement:", "smem" if os.environ.get("CSN_LSTM_W_SMEM") == "1" else "tmem", "B =", B)
-print(" t | period | accwait->ld | ld->math+stores | fence+arrive | arrive->issuer wake | issue+commit | commit->epi wake")
-rows = []
-for t in range(3, 40):
-    period = int(p[t + 1, 0] - p[t, 0])
-    a = int(p[t, 1] - p[t, 0]); b = int(p[t, 2] - p[t, 1]); c = int(p[t, 3] - p[t, 2])
-    d = int(p[t + 1, 4] - p[t, 3]); e = int(p[t + 1, 5] - p[t + 1, 4]); f = int(p[t + 1, 0] - p[t + 1, 5])
-    rows.append((period, a, b, c, d, e, f))
-    if t < 12:
-        print(f"{t:3d} | {period:6d} | {a:6d} | {b:6d} | {c:6d} | {d:6d} | {e:6d} | {f:6d}")
-import statistics
-print("median", [int(statistics.median(r[i] for r in rows)) for i in range(7)])
+for name, p in (("forward", buf[:512].view(64, 8).cpu()), ("backward", buf[512:].view(64, 8).cpu())):
+    print(name, "B =", B)
+    print(" t | period | accwait->ld | ld->math | fence+arrive | arrive->issuer wake | issue+commit | commit->epi wake")
+    rows = []
+    for t in range(3, 40):
+        period = int(p[t + 1, 0] - p[t, 0])
+        a = int(p[t, 1] - p[t, 0]); b = int(p[t, 2] - p[t, 1]); c = int(p[t, 3] - p[t, 2])
+        d = int(p[t + 1, 4] - p[t, 3]); e = int(p[t + 1, 5] - p[t + 1, 4]); f = int(p[t + 1, 0] - p[t + 1, 5])
+        rows.append((period, a, b, c, d, e, f))
+        if t < 6:
+            print(f"{t:3d} | {period:6d} | {a:6d} | {b:6d} | {c:6d} | {d:6d} | {e:6d} | {f:6d}")
+    print("median", [int(statistics.median(r[i] for r in rows)) for i in range(7)])

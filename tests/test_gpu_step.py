@@ -139,3 +139,27 @@ def test_multicrop_student_step_runs_like_the_reference_loop():
             continue
         scale = q.grad.abs().max().item() + 1e-12
         assert (p.grad.cpu() - q.grad).abs().max().item() <= 5e-3 * scale, n
+
+
+def test_cuda_graph_step_matches_eager_steps():
+    """The replayed CUDA graph (device-side Adam step counter, static input buffers) must track eager stepping."""
+    import cerebralsignalnetworks_b200 as csn
+    from oracle.filters import design_bandpass_sos
+    sos = design_bandpass_sos(5.0, 95.0, 1000.0, 4)
+    runs = {}
+    for graphed in (False, True):
+        torch.manual_seed(11)
+        model = csn.Model(16, 32, 1, 24, include_top=False, compute_dtype=torch.float32).cuda()
+        crit = csn.DINOLoss(24, 1, 1.5, 0.22, 5, 10).cuda()
+        step = csn.DistillTrainStep(model, crit, lr=1e-2, sos=sos, use_cuda_graph=graphed)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        losses = []
+        for i in range(6):
+            eeg = torch.randn(4, 16, 48, device="cuda", generator=g)
+            feats = torch.randn(4, 24, device="cuda", generator=g)
+            losses.append(float(step.step(eeg, feats, epoch=0 if i < 4 else 1)))  # epoch change -> re-capture
+        runs[graphed] = (losses, {n: p.detach().clone() for n, p in model.named_parameters()}, crit.center.clone())
+    np.testing.assert_allclose(runs[True][0], runs[False][0], rtol=1e-5)
+    for n in runs[False][1]:
+        assert torch.allclose(runs[True][1][n], runs[False][1][n], rtol=1e-5, atol=1e-7), n
+    assert torch.allclose(runs[True][2], runs[False][2], rtol=1e-6, atol=1e-8)
