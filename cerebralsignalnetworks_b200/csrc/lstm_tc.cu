@@ -96,7 +96,8 @@ __device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t 
     }
   }
 }
-// Backward: contraction index kk16 = g*ksteps_gate + kg, single accumulator dh^T.
+// Backward: the dG^T operand keeps a FIXED stride of 128 contraction elements per gate (kk16 = 8 g + kg), so every
+// descriptor offset is an immediate; single accumulator dh^T.
 template <bool CONST_BASE>
 __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_gate) {
   const uint32_t tb = CONST_BASE ? 0u : base;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t 
 #pragma unroll
     for (int kg = 0; kg < 8; ++kg) {
       if (kg < ksteps_gate) {
-        const int kk = g * ksteps_gate + kg;
+        const int kk = g * 8 + kg;
         const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
         umma_f16_ts(tb, tb + kAcol0 + g * kAgate + kg * 8, db, idesc, (g == 0 && kg == 0) ? 0u : 1u);
       }
@@ -272,8 +273,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
                    float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP,
                    long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
-  const int K4 = 4 * KP;
-  const size_t b_bytes = size_t(K4 / 8) * kLboB;
+  const size_t b_bytes = size_t(4 * 128 / 8) * kLboB;  // gate stride fixed at 128 contraction elements
   RecSmem sm = carve(smem_raw, b_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * NV;
@@ -387,7 +387,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
         if (active) {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, g * KP + u, kLboB, kSboB)) = __float2bfloat16_rn(dg[g][j]);
+            *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, g * 128 + u, kLboB, kSboB)) = __float2bfloat16_rn(dg[g][j]);
         }
       }
       if (do_prof) prof[512 + n * 8 + 2] = clock64();
@@ -471,7 +471,7 @@ template <int NV>
 static int launch_bwd(const float* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
-  const size_t smem = size_t(4 * KP / 8) * kLboB + 64 + 128;
+  const size_t smem = size_t(4 * 128 / 8) * kLboB + 64 + 128;
   lstm_bwd_tc_kernel<NV><<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
