@@ -306,10 +306,22 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms)
 
-    if rank != 0:
+    def finish():
+        # Multi-rank teardown: every rank meets at a barrier, then leaves without tearing NCCL down.  (Destroying the
+        # process group while captured graphs still hold NCCL kernels hung rank teardown for minutes on the GPU box;
+        # the OS reclaims the communicator.)
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            step._graph = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
         return 0
+
+    if rank != 0:
+        return finish()
 
     work = algorithmic_work(B, C, T, H, L, K)
     peaks = measured_peaks()
@@ -353,9 +365,7 @@ def main():
                                 "sample": "10 steps of the cfg1 workload (batch 16, same model) on the host cores: torch-CPU LSTM + "
                                           "scipy sosfilt + DINO loss + Adam"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return finish()
 
 
 if __name__ == "__main__":
