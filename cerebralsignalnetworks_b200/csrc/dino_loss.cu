@@ -224,6 +224,231 @@ __global__ void __launch_bounds__(kLossThreads) dino_loss_kernel(const LossParam
   if (cs > 1) cluster.sync();  // peers may still be reading our mailboxes
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Staged variant (the HBM-bound shapes: K % 4 == 0, 16-byte aligned rows).  Same decomposition and arithmetic as
+// dino_loss_kernel, but the row chunks are pulled by the TMA unit: one thread issues 1-D bulk copies
+// (cp.async.bulk global -> shared, mbarrier complete_tx) for the next S rows into a shared-memory ring while the
+// CTA reduces / writes the current row, so S * Kc * 4 bytes per SM are always in flight without holding registers.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                 "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int NITER>
+__global__ void __launch_bounds__(kLossThreads) dino_loss_staged_kernel(const LossParams p, const int S) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int k0 = crank * p.Kc;
+  constexpr int EPT = 4 * NITER;
+  const uint32_t row_bytes = (uint32_t)p.Kc * 4u;
+
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  float* stages = reinterpret_cast<float*>(smem_dyn);            // [S][Kc]
+  float* cen_s = stages + size_t(S) * p.Kc;                      // [Kc]
+  uint64_t* full = reinterpret_cast<uint64_t*>(cen_s + p.Kc);    // [S] row barriers + [1] centre barrier
+  __shared__ Stat warp_buf[kLossThreads / 32];
+  __shared__ Stat slots[kMaxRounds];
+  __shared__ int vlist[kMaxVs];
+  __shared__ int n_active;
+
+  if (tid == 0) {
+    int n = 0;
+    for (int v = 0; v < p.Vs; ++v)
+      if (p.mask[v]) vlist[n++] = v;
+    n_active = n;
+    for (int i = 0; i <= S; ++i) mbar_init_(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nrows = p.Vt + n_active;
+  auto row_src = [&](int r) -> const float* {
+    if (r < p.Vt) return p.teacher + (size_t(r) * p.B + b) * p.K + k0;
+    return p.student + (size_t(vlist[r - p.Vt]) * p.B + b) * p.K + k0;
+  };
+  auto issue = [&](int r) {  // thread 0 only
+    uint64_t* bar = &full[r % S];
+    mbar_expect_tx_(bar, row_bytes);
+    bulk_g2s(stages + size_t(r % S) * p.Kc, row_src(r), row_bytes, bar);
+  };
+  if (tid == 0) {
+    mbar_expect_tx_(&full[S], row_bytes);
+    bulk_g2s(cen_s, p.center + (p.center_rows > 1 ? size_t(b) * p.K : 0) + k0, row_bytes, &full[S]);
+    for (int r = 0; r < S && r < nrows; ++r) issue(r);
+  }
+
+  auto in_range = [&](int it) { return (it * kLossThreads + tid) * 4 < p.Kc; };
+  // pull this thread's values of row r out of the ring; afterwards the stage is handed back to the TMA producer
+  auto take_row = [&](int r, float (&dst)[EPT]) {
+    mbar_wait_(&full[r % S], (uint32_t)((r / S) & 1));
+    const float* src = stages + size_t(r % S) * p.Kc;
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+      float4 v = in_range(it) ? *reinterpret_cast<const float4*>(src + (it * kLossThreads + tid) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dst[it * 4 + 0] = v.x; dst[it * 4 + 1] = v.y; dst[it * 4 + 2] = v.z; dst[it * 4 + 3] = v.w;
+    }
+    __syncthreads();
+    if (tid == 0 && r + S < nrows) issue(r + S);
+  };
+  auto store_row = [&](float* base, const float (&src)[EPT]) {
+#pragma unroll
+    for (int it = 0; it < NITER; ++it)
+      if (in_range(it))
+        __stcs(reinterpret_cast<float4*>(base + k0 + (it * kLossThreads + tid) * 4),
+               make_float4(src[it * 4 + 0], src[it * 4 + 1], src[it * 4 + 2], src[it * 4 + 3]));
+  };
+
+  // student views that are not matched against any teacher view: zero gradient
+  {
+    float z[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) z[i] = 0.f;
+    for (int v = 0; v < p.Vs; ++v)
+      if (p.mask[v] == 0) store_row(p.d_student + (size_t(v) * p.B + b) * p.K, z);
+  }
+
+  int round = 0;
+  float q[kMaxVt][EPT];
+  float bc[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) bc[i] = 0.f;
+  mbar_wait_(&full[S], 0);  // centre chunk
+
+  // ---- teacher rows: q[g] = softmax((t - c) / tau_t) ----
+#pragma unroll
+  for (int g = 0; g < kMaxVt; ++g) {
+    if (g < p.Vt) {
+      take_row(g, q[g]);
+      Stat s{-INFINITY, 0.f, 0.f};
+#pragma unroll
+      for (int it = 0; it < NITER; ++it) {
+        if (in_range(it)) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cen_s + (it * kLossThreads + tid) * 4);
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = it * 4 + j;
+            bc[i] += q[g][i];
+            q[g][i] = (q[g][i] - cc[j]) * p.inv_tau_t;
+            s.m = fmaxf(s.m, q[g][i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < NITER; ++it)
+        if (in_range(it)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s.z += __expf(q[g][it * 4 + j] - s.m);
+        }
+      s = cluster_reduce(s, warp_buf, &slots[round++], cluster, cs);
+      const float inv_z = 1.f / s.z;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) q[g][i] = __expf(q[g][i] - s.m) * inv_z;
+    } else {
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) q[g][i] = 0.f;
+    }
+  }
+
+  // ---- centre statistics ----
+  if (p.mode == CSN_DINO_MULTICROP_REF) {
+    store_row(p.batch_center + size_t(b) * p.K, bc);
+  } else {
+#pragma unroll
+    for (int it = 0; it < NITER; ++it)
+      if (in_range(it)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(p.batch_center + k0 + (it * kLossThreads + tid) * 4 + j, bc[it * 4 + j]);
+      }
+  }
+
+  // ---- student rows ----
+  float loss_acc = 0.f;
+  for (int a = 0; a < n_active; ++a) {
+    const int v = vlist[a];
+    const unsigned mask = p.mask[v];
+    float u[EPT];
+    take_row(p.Vt + a, u);
+    const float w0 = (mask & 1u) ? 1.f : 0.f, w1 = (mask & 2u) ? 1.f : 0.f;
+    const float W = w0 + w1;
+    Stat s{-INFINITY, 0.f, 0.f};
+#pragma unroll
+    for (int it = 0; it < NITER; ++it)
+      if (in_range(it)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = it * 4 + j;
+          u[i] *= p.inv_tau_s;
+          s.m = fmaxf(s.m, u[i]);
+          s.d += (w0 * q[0][i] + w1 * q[1][i]) * u[i];
+        }
+      }
+#pragma unroll
+    for (int it = 0; it < NITER; ++it)
+      if (in_range(it)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s.z += __expf(u[it * 4 + j] - s.m);
+      }
+    s = cluster_reduce(s, warp_buf, &slots[round++], cluster, cs);
+    loss_acc += p.coef * (W * (s.m + __logf(s.z)) - s.d);
+    const float inv_z = 1.f / s.z;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      u[i] = p.grad_coef * (W * __expf(u[i] - s.m) * inv_z - (w0 * q[0][i] + w1 * q[1][i]));
+    store_row(p.d_student + (size_t(v) * p.B + b) * p.K, u);
+  }
+  if (crank == 0 && tid == 0) atomicAdd(p.loss, loss_acc);
+  if (cs > 1) cluster.sync();  // peers may still be reading our mailboxes
+}
+
+template <int NITER>
+static int launch_loss_staged(const LossParams& p, int cs, int S, cudaStream_t s) {
+  const size_t smem = size_t(S + 1) * p.Kc * 4 + size_t(S + 1) * 8 + 128;
+  auto kern = dino_loss_staged_kernel<NITER>;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cs, p.B, 1);
+  cfg.blockDim = dim3(kLossThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSN_CUDA(cudaLaunchKernelEx(&cfg, kern, p, S));
+  return CSN_OK;
+}
+
 template <int VEC, int NITER>
 static int launch_loss(const LossParams& p, int cs, cudaStream_t s) {
   cudaLaunchConfig_t cfg{};
@@ -308,6 +533,26 @@ extern "C" int csn_dino_loss_fwd_bwd(const float* student, const float* teacher,
   p.Kc = K / cs;
   const int per_thread = ceil_div(p.Kc, kLossThreads * vec);
   int r;
+  static const bool no_stage = [] { const char* e = getenv("CSN_LOSS_NO_STAGE"); return e && e[0] == '1'; }();
+  if (vec == 4 && !no_stage && (reinterpret_cast<uintptr_t>(center) & 15) == 0) {
+    int n_act = 0;
+    for (int v = 0; v < Vs; ++v) n_act += p.mask[v] ? 1 : 0;
+    const int nrows = Vt + n_act;
+    // ring depth: row chunks that fit next to the centre chunk in ~100 KB (two CTAs per SM hide each other's
+    // reduction / cluster-barrier latency), at most 4 and at most nrows.  CSN_LOSS_STAGE_KB overrides the budget.
+    static const unsigned budget_kb = [] { const char* e = getenv("CSN_LOSS_STAGE_KB"); return e ? (unsigned)atoi(e) : 100u; }();
+    int S = (int)((budget_kb * 1024u) / (size_t(p.Kc) * 4u)) - 1;
+    S = S > 4 ? 4 : S;
+    S = S > nrows ? nrows : S;
+    if (S >= 1) {
+      if (per_thread <= 1) r = launch_loss_staged<1>(p, cs, S, s);
+      else if (per_thread <= 2) r = launch_loss_staged<2>(p, cs, S, s);
+      else if (per_thread <= 4) r = launch_loss_staged<4>(p, cs, S, s);
+      else r = launch_loss_staged<8>(p, cs, S, s);
+      if (r == CSN_OK) count_launches(1);
+      return r;
+    }
+  }
   if (vec == 4) {
     if (per_thread <= 1) r = launch_loss<4, 1>(p, cs, s);
     else if (per_thread <= 2) r = launch_loss<4, 2>(p, cs, s);
@@ -319,6 +564,7 @@ extern "C" int csn_dino_loss_fwd_bwd(const float* student, const float* teacher,
     else if (per_thread <= 4) r = launch_loss<1, 4>(p, cs, s);
     else r = launch_loss<1, 8>(p, cs, s);
   }
+  if (r == CSN_OK) count_launches(1);
   return r;
 }
 

@@ -42,8 +42,10 @@ struct RecSmem {
   uint32_t* tmem_slot;
 };
 
+// `raw` is the 128-byte aligned dynamic shared array itself (no runtime alignment arithmetic): its address is a
+// link-time constant, so the B-operand descriptors of the unrolled MMA issue become immediates in uniform registers.
 __device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t b_bytes) {
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~uintptr_t(127));
+  uint8_t* base = raw;
   RecSmem s;
   s.opb = base;
   s.bar_in = reinterpret_cast<uint64_t*>(s.opb + b_bytes);
@@ -83,9 +85,11 @@ __device__ __forceinline__ void stage_weights_tmem(uint32_t lane_addr, F elem) {
 // same D (measured: 14.9 cycles per M=128,N=16,K=16 MMA with A in tensor memory, 43.8 with A in shared memory,
 // independent of the accumulator rotation), so split accumulation chains only add tcgen05.ld work.
 // Forward: gate g, K-step kk  ->  D = acc[g], A = W_hh block g columns kk*8.., B = h^T k-groups 2kk, 2kk+1.
-template <bool CONST_BASE>
-__device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps) {
+// KSTEPS > 0: K-steps per gate known at compile time (no predicates in the issue sequence); 0: runtime.
+template <bool CONST_BASE, int KSTEPS>
+__device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_rt) {
   const uint32_t tb = CONST_BASE ? 0u : base;
+  const int ksteps = KSTEPS ? KSTEPS : ksteps_rt;
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
     if (kk < ksteps) {
@@ -98,9 +102,10 @@ __device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t 
 }
 // Backward: the dG^T operand keeps a FIXED stride of 128 contraction elements per gate (kk16 = 8 g + kg), so every
 // descriptor offset is an immediate; single accumulator dh^T.
-template <bool CONST_BASE>
-__device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_gate) {
+template <bool CONST_BASE, int KSTEPS>
+__device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_rt) {
   const uint32_t tb = CONST_BASE ? 0u : base;
+  const int ksteps_gate = KSTEPS ? KSTEPS : ksteps_rt;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
 #pragma unroll
@@ -115,12 +120,12 @@ __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int NV>
+template <int NV, int KSTEPS>
 __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                    __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
                    int T, int B, int H, int KP, long long* __restrict__ prof) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   const size_t b_bytes = size_t(KP / 8) * kLboB;
   RecSmem sm = carve(smem_raw, b_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -162,8 +167,8 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       tcgen05_fence_after();
       if (elect_one()) {
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 4] = clock64();
-        if (base0) issue_fwd<true>(0u, db0, idesc, ksteps);
-        else issue_fwd<false>(tmem_base, db0, idesc, ksteps);
+        if (base0) issue_fwd<true, KSTEPS>(0u, db0, idesc, ksteps);
+        else issue_fwd<false, KSTEPS>(tmem_base, db0, idesc, ksteps);
         umma_commit(sm.bar_acc);
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 5] = clock64();
       }
@@ -266,13 +271,13 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
 
 // ------------------------------------------------------------------------------------------------ backward
 // dh_{t-1}^T[k, b] = sum_{kk = g*KP + u} W_hh[g*H + u][k] * dG_t[b, kk]: M = hidden unit k (TMEM lane), K = 4*KP.
-template <int NV>
+template <int NV, int KSTEPS>
 __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
                    float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP,
                    long long* __restrict__ prof) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   const size_t b_bytes = size_t(4 * 128 / 8) * kLboB;  // gate stride fixed at 128 contraction elements
   RecSmem sm = carve(smem_raw, b_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -313,8 +318,8 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
       if (elect_one()) {
         const bool pr = prof && blockIdx.x == 0 && n + 1 < kProfSteps;
         if (pr) prof[512 + (n + 1) * 8 + 4] = clock64();
-        if (base0) issue_bwd<true>(0u, db0, idesc, ksteps_gate);
-        else issue_bwd<false>(tmem_base, db0, idesc, ksteps_gate);
+        if (base0) issue_bwd<true, KSTEPS>(0u, db0, idesc, ksteps_gate);
+        else issue_bwd<false, KSTEPS>(tmem_base, db0, idesc, ksteps_gate);
         umma_commit(sm.bar_acc);
         if (pr) prof[512 + (n + 1) * 8 + 5] = clock64();
       }
@@ -458,21 +463,21 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
 
 static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (bring-up only)
 
-template <int NV>
+template <int NV, int KSTEPS>
 static int launch_fwd(const float* xp, const float* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
                       float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
   const size_t smem = size_t(KP / 8) * kLboB + 64 + 128;
-  lstm_fwd_tc_kernel<NV><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf);
+  lstm_fwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
 
-template <int NV>
+template <int NV, int KSTEPS>
 static int launch_bwd(const float* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
   const size_t smem = size_t(4 * 128 / 8) * kLboB + 64 + 128;
-  lstm_bwd_tc_kernel<NV><<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf);
+  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
@@ -495,9 +500,18 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   __nv_bfloat16* g = training ? gates : nullptr;
   float* c = training ? c_out : nullptr;
   __nv_bfloat16* hs = (__nv_bfloat16*)h_seq;
-  if (nv == 2) return launch_fwd<2>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
-  if (nv == 4) return launch_fwd<4>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
-  return launch_fwd<8>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);
+  // hidden 128 / 96 / 64 get compile-time K-step counts (predicate-free MMA issue); other sizes take the runtime path
+#define CSN_FWD(KS)                                                                  \
+  do {                                                                               \
+    if (nv == 2) return launch_fwd<2, KS>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s); \
+    if (nv == 4) return launch_fwd<4, KS>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s); \
+    return launch_fwd<8, KS>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);              \
+  } while (0)
+  if (KP == 128) CSN_FWD(8);
+  if (KP == 96) CSN_FWD(6);
+  if (KP == 64) CSN_FWD(4);
+  CSN_FWD(0);
+#undef CSN_FWD
 }
 
 int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const void* h_seq, const void* reserve,
@@ -516,9 +530,17 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
     CSN_CUDA(cudaMemsetAsync(db_hh, 0, size_t(4) * H * 4, s));
   }
   const int nv = pick_nv(B);
-  if (nv == 2) CSN_TRY(launch_bwd<2>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
-  else if (nv == 4) CSN_TRY(launch_bwd<4>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
-  else CSN_TRY(launch_bwd<8>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s));
+#define CSN_BWD(KS)                                                                                                        \
+  do {                                                                                                                     \
+    if (nv == 2) CSN_TRY((launch_bwd<2, KS>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));      \
+    else if (nv == 4) CSN_TRY((launch_bwd<4, KS>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s))); \
+    else CSN_TRY((launch_bwd<8, KS>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));              \
+  } while (0)
+  if (KP == 128) CSN_BWD(8);
+  else if (KP == 96) CSN_BWD(6);
+  else if (KP == 64) CSN_BWD(4);
+  else CSN_BWD(0);
+#undef CSN_BWD
   // dW_ih[4H, I] = dG^T . x ; dW_hh[4H, H] = dG[1:]^T . h_seq[:-1]  (contraction over time*batch, split-K)
   const int sms = sm_count();
   const int tiles_ih = ceil_div(4 * H, 128) * ceil_div(I, 128), tiles_hh = ceil_div(4 * H, 128) * ceil_div(H, 128);

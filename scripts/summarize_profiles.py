@@ -1,0 +1,61 @@
+"""Turn gpurun_out/launches_<tag>.csv and gpurun_out/prof_<tag>.ncu-rep into small committed summaries under profiles/."""
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+out_dir = os.path.join(root, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+
+# ---- launch list: per-kernel share of the step ----
+lines = [l for l in open(os.path.join(root, "gpurun_out", f"launches_{tag}.csv")) if l.startswith('"')]
+agg, tot = collections.OrderedDict(), 0.0
+for row in csv.DictReader(lines):
+    if row.get("Metric Name") != "gpu__time_duration.sum":
+        continue
+    name = row["Kernel Name"].split("(")[0][:90]
+    val = float(row["Metric Value"].replace(",", ""))
+    u = row["Metric Unit"]
+    val = val / 1000 if u == "ns" else (val * 1000 if u == "ms" else val)
+    a = agg.setdefault(name, [0, 0.0])
+    a[0] += 1
+    a[1] += val
+    tot += val
+with open(os.path.join(out_dir, f"launches_{tag}.md"), "w") as f:
+    f.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 3 --no_cpu_baseline`\n\n")
+    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` -- cold-cache, serialised launches: compare SHARES, not absolutes.\n")
+    f.write("Covers warm-up + timed graph replays + the eager stage-timing steps + the loss roofline probe + input generation.\n\n")
+    f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write(f"| `{k}` | {n} | {t:.1f} | {t / n:.1f} | {100 * t / tot:.1f}% |\n")
+    f.write(f"\ntotal {tot:.0f} us over {sum(n for n, _ in agg.values())} launches\n")
+
+# ---- full capture: key metrics per kernel ----
+rep = os.path.join(root, "gpurun_out", f"prof_{tag}.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "sm__cycles_elapsed.max"]
+idx = [(w, hdr.index(w)) for w in want if w in hdr]
+seen = collections.OrderedDict()
+for r in rows[2:]:
+    name = r[hdr.index("Kernel Name")].split("(")[0][:80]
+    seen.setdefault(name, r)  # first capture of each kernel
+with open(os.path.join(out_dir, f"ncu_full_{tag}.md"), "w") as f:
+    f.write(f"# ncu --set full summary ({tag})\n\n`ncu --set full --clock-control none --import-source on` on `python bench.py --steps 2 --warmup 3`; one launch per kernel shown.\n")
+    f.write("`traffic` for bench.py's roofline = dram read + write below.\n\n")
+    for name, r in seen.items():
+        f.write(f"## `{name}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+        for w, i in idx[1:]:
+            f.write(f"| {w} | {r[i]} | {units[i]} |\n")
+        f.write("\n")
+print(open(os.path.join(out_dir, f"launches_{tag}.md")).read()[:2500])
+print(open(os.path.join(out_dir, f"ncu_full_{tag}.md")).read()[:6000])
