@@ -40,6 +40,22 @@ def algorithmic_work(B, C, T, H, L, K):
                 lstm_train_flop=3.0 * lstm_fwd_flop, rec_fwd_flop=rec_fwd_flop, rec_bwd_flop=rec_fwd_flop)
 
 
+def ncu_traffic(kernel_substrings):
+    """Per-launch DRAM bytes (read + write) of the named kernels from the committed ncu --set full summary
+    (profiles/traffic.json, written by scripts/summarize_profiles.py); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(p):
+        return None
+    ks = json.load(open(p))["kernels"]
+    total = 0.0
+    for sub in kernel_substrings:
+        hit = [v for k, v in ks.items() if sub in k]
+        if not hit:
+            return None
+        total += hit[0]["dram_read_bytes"] + hit[0]["dram_write_bytes"]
+    return total
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -350,10 +366,12 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "LSTM encoder fwd+bwd (lstm_fwd_tc_kernel + lstm_bwd_tc_kernel + input-projection / dW GEMMs)",
                      "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved_tflops / peak_tf) if achieved_tflops else None, "traffic": None,
+                     "frac": (achieved_tflops / peak_tf) if achieved_tflops else None,
+                     "traffic": ncu_traffic(["lstm_fwd_tc_kernel", "lstm_bwd_tc_kernel", "gemm_tc_kernel<0, 0>", "gemm_tc_kernel<1, 1>", "gemm_tc_kernel<1, 1>"]),
+                     "traffic_note": "DRAM read+write bytes per step of the encoder kernels (fwd + bwd recurrence, input-projection GEMM, 2 dW GEMMs), ncu --set full, profiles/traffic.json",
                      "peak_source": peaks["source"] + " (sustained: kernel timed inside the step)"},
         "roofline_filter": {"bound": "hbm", "kernel": "sosfilt_stream_kernel", "achieved": filt_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": (filt_gbs / peaks["hbm_gbs"]) if filt_gbs else None, "traffic": None,
+                            "frac": (filt_gbs / peaks["hbm_gbs"]) if filt_gbs else None, "traffic": ncu_traffic(["sosfilt_stream_kernel"]),
                             "peak_source": peaks["source"]},
         "roofline_loss": {"bound": "hbm", "kernel": "dino_loss_kernel (cfg3 shape: 6 student + 2 teacher views, 64 trials, K=65536)",
                           "achieved": loss_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "tc.cuh"
+#include "gemm_tc.cuh"
 
 namespace csn {
 
@@ -61,11 +62,13 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint6
   return CSN_OK;
 }
 
-struct GemmEpi {
-  void* D;
-  const float* bias;
-  int ldd, d_dtype, M, N, K, k_per_split, atomic, stages;
-};
+
+__device__ __forceinline__ float tanh_fast_g(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast_g(float x) { return fmaf(0.5f, tanh_fast_g(0.5f * x), 0.5f); }
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
   const int kbeg = blockIdx.z * p.k_per_split;
   const int klen = min(p.K - kbeg, p.k_per_split);
-  const int n_it = (klen + GBK - 1) / GBK;
+  const int n_it = p.zero_acc ? 0 : (klen + GBK - 1) / GBK;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -187,6 +190,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         float4 v = *reinterpret_cast<const float4*>(tile + rr * kEpiStride + col4);
         v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
         if (gm >= p.M || gn >= p.N) continue;
+        if (p.mode == 1) {
+          // ---- fused LSTM cell: (i,f,g,o) = act(acc + Xp); c = f c_prev + i g; h = o tanh(c) ----
+          const int u = gn >> 2;
+          const float4 x4 = *reinterpret_cast<const float4*>(p.xp + size_t(gm) * p.N + gn);
+          const float ig = sigmoid_fast_g(v.x + x4.x), fg = sigmoid_fast_g(v.y + x4.y);
+          const float gg = tanh_fast_g(v.z + x4.z), og = sigmoid_fast_g(v.w + x4.w);
+          const float cp = p.c_prev ? p.c_prev[size_t(gm) * p.H + u] : 0.f;
+          const float c = fmaf(fg, cp, ig * gg);
+          p.c_out[size_t(gm) * p.H + u] = c;
+          p.h_out[size_t(gm) * p.H + u] = __float2bfloat16_rn(og * tanh_fast_g(c));
+          if (p.gates_out) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(ig, fg), hi = __floats2bfloat162_rn(gg, og);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo);
+            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(p.gates_out + size_t(gm) * p.N + gn) = o;
+          }
+          continue;
+        }
         if (f32_out) {
           float* d = reinterpret_cast<float*>(p.D) + size_t(gm) * p.ldd + gn;
           if (p.atomic) {
@@ -247,7 +269,14 @@ using namespace csn;
 extern "C" int csn_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B,
                                 int ldb, void* D, int ldd, int d_dtype, const float* bias, int accumulate, int split_k,
                                 void* stream) {
-  CSN_REQUIRE(A && B && D, "csn_gemm_bf16_tc: null pointer");
+  return gemm_tc_run(transA, transB, M, N, K, A, lda, B, ldb, D, ldd, d_dtype, bias, accumulate, split_k, nullptr,
+                     as_stream(stream));
+}
+
+int csn::gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* D,
+                     int ldd, int d_dtype, const float* bias, int accumulate, int split_k, const GemmEpi* cell,
+                     cudaStream_t s) {
+  CSN_REQUIRE(A && B && (D || cell), "csn_gemm_bf16_tc: null pointer");
   CSN_REQUIRE(M >= 1 && N >= 1 && K >= 1, "csn_gemm_bf16_tc: dimensions must be positive");
   CSN_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "csn_gemm_bf16_tc: lda/ldb must be multiples of 8 elements (TMA 16 B pitch)");
   CSN_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
@@ -255,7 +284,10 @@ extern "C" int csn_gemm_bf16_tc(int transA, int transB, int M, int N, int K, con
   CSN_REQUIRE(d_dtype == CSN_F32 || d_dtype == CSN_BF16, "csn_gemm_bf16_tc: bad d_dtype");
   if (split_k < 1) split_k = 1;
   CSN_REQUIRE(d_dtype == CSN_F32 || (split_k == 1 && !accumulate), "csn_gemm_bf16_tc: bf16 output cannot accumulate / split-K");
-  cudaStream_t s = as_stream(stream);
+  if (cell) {
+    CSN_REQUIRE(split_k == 1 && !accumulate && N % 4 == 0 && cell->xp && cell->h_out && cell->c_out && cell->H * 4 == N,
+                "gemm_tc_run: bad LSTM-cell epilogue arguments");
+  }
 
   const int k_iters = ceil_div(K, GBK);
   if (split_k > k_iters) split_k = k_iters;
@@ -273,6 +305,10 @@ extern "C" int csn_gemm_bf16_tc(int transA, int transB, int M, int N, int K, con
   p.k_per_split = it_per_split * GBK;
   p.atomic = (accumulate || split_k > 1) ? 1 : 0;
   p.stages = it_per_split < 4 ? (it_per_split < 2 ? 2 : it_per_split) : 4;
+  if (cell) {
+    p.mode = 1; p.zero_acc = cell->zero_acc; p.H = cell->H; p.xp = cell->xp; p.c_prev = cell->c_prev;
+    p.h_out = cell->h_out; p.gates_out = cell->gates_out; p.c_out = cell->c_out;
+  }
   if (split_k > 1 && !accumulate) CSN_CUDA(cudaMemset2DAsync(D, size_t(ldd) * 4, 0, size_t(N) * 4, M, s));
   dim3 grid(ceil_div(N, GBN), ceil_div(M, GBM), split_k);
   CSN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "csn_gemm_bf16_tc: grid too large");

@@ -1,0 +1,25 @@
+// Internal interface of the tcgen05 GEMM (gemm_tc.cu) for the other translation units of libcsn_b200.
+#pragma once
+#include "common.cuh"
+
+namespace csn {
+
+struct GemmEpi {
+  void* D;
+  const float* bias;
+  int ldd, d_dtype, M, N, K, k_per_split, atomic, stages;
+  // mode 1: fused LSTM cell epilogue (large-hidden path, see lstm_tc_large.cu).  Columns are gate-interleaved
+  // (column 4u+g = gate g of hidden unit u), so the float4 a lane owns is one cell's (i,f,g,o) pre-activation.
+  int mode, zero_acc, H;
+  const float* xp;            // [M, N] fp32: hoisted input projection (+ biases) of this timestep
+  const float* c_prev;        // [M, H] fp32 or NULL (t = 0)
+  __nv_bfloat16* h_out;       // [M, H]
+  __nv_bfloat16* gates_out;   // [M, N] activated gates (BPTT reserve) or NULL
+  float* c_out;               // [M, H]
+};
+
+// Same contract as csn_gemm_bf16_tc; `cell` (may be NULL) switches the epilogue to the fused LSTM cell.
+int gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* D,
+                int ldd, int d_dtype, const float* bias, int accumulate, int split_k, const GemmEpi* cell, cudaStream_t s);
+
+}  // namespace csn

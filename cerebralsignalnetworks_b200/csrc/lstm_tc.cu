@@ -444,11 +444,15 @@ static int pick_nv(int B) {
   return 8;
 }
 
+int lstm_large_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace);
+int lstm_layer_fwd_large(const void* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, void* h_seq,
+                         void* reserve, void* workspace, int T, int B, int I, int H, int training, cudaStream_t s);
+int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, const void* h_seq, const void* reserve,
+                         const float* d_hseq, const float* d_hlast, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                         float* dx, void* workspace, int T, int B, int I, int H, int accumulate, cudaStream_t s);
+
 int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace) {
-  if (H > 128) {
-    set_error("bf16 tensor-core LSTM path supports hidden size <= 128 this round (got H=%d); use compute_dtype f32", H);
-    return CSN_EUNSUPPORTED;
-  }
+  if (H > 128) return lstm_large_bytes(T, B, I, H, reserve, workspace);  // per-step GEMM + fused cell epilogue
   if (I % 8 != 0 || H % 8 != 0) {
     set_error("bf16 tensor-core LSTM path needs input and hidden sizes that are multiples of 8 (I=%d H=%d)", I, H);
     return CSN_EUNSUPPORTED;
@@ -487,6 +491,7 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
                       cudaStream_t s) {
   size_t rb, wb;
   CSN_TRY(lstm_tc_bytes(T, B, I, H, &rb, &wb));
+  if (H > 128) return lstm_layer_fwd_large(x, w_ih, w_hh, b_ih, b_hh, h_seq, reserve, workspace, T, B, I, H, training, s);
   const size_t tb = size_t(T) * B;
   const int KP = ceil_div(H, 16) * 16;
   float* xp = reinterpret_cast<float*>(workspace);
@@ -519,6 +524,9 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
                       float* dx, void* workspace, int T, int B, int I, int H, int accumulate, cudaStream_t s) {
   size_t rb, wb;
   CSN_TRY(lstm_tc_bytes(T, B, I, H, &rb, &wb));
+  if (H > 128)
+    return lstm_layer_bwd_large(x, w_ih, w_hh, h_seq, reserve, d_hseq, d_hlast, dw_ih, dw_hh, db_ih, db_hh, dx, workspace, T,
+                                B, I, H, accumulate, s);
   const size_t tb = size_t(T) * B;
   const int KP = ceil_div(H, 16) * 16;
   const __nv_bfloat16* gates = reinterpret_cast<const __nv_bfloat16*>(reserve);

@@ -1,0 +1,213 @@
+// LSTM layer, bf16 tensor-core path for LARGE hidden sizes (H > 128, e.g. cfg 4: H = 512).
+//
+// W_hh (4H x H bf16 = 2 MB at H = 512) does not fit the tensor memory / shared memory of one SM, so the persistent
+// single-CTA recurrence of lstm_tc.cu does not apply.  Here every timestep is ONE tcgen05 GEMM over the whole batch
+// (gemm_tc.cu: TMA -> smem ring -> tcgen05.mma -> TMEM) whose epilogue IS the LSTM cell: the gate rows of the weights
+// are interleaved (row 4u+g = gate g of unit u) so that the four accumulator columns a lane holds are one cell's
+// (i,f,g,o); the epilogue adds the hoisted input projection, applies the nonlinearities, updates c and writes h_t
+// as bf16 directly in the K-major layout the next step's A operand is loaded from.  The T launches are captured in
+// the step's CUDA graph, so the chain costs one submission.  BPTT mirrors it: a pointwise cell-gradient kernel and
+// one GEMM (dh_{t-1} = dG_t W_hh) per step, then three batched GEMMs for dW_ih, dW_hh, dX and a ones-GEMM for db.
+//
+// A cluster-resident variant (W_hh split over a 16-CTA cluster, h exchanged through DSMEM) is the next step for this
+// size class; see DESIGN.md.
+#include "gemm_tc.cuh"
+
+namespace csn {
+
+static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+
+__device__ __forceinline__ float tanh_fast_l(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// rows: dst[4u+g, :] = bf16(src[g*H+u, :])
+__global__ void permute_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H, int N) {
+  const int r = blockIdx.x;  // destination row 4u+g
+  const int u = r >> 2, g = r & 3;
+  const float* s = src + size_t(g * H + u) * N;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) dst[size_t(r) * N + c] = __float2bfloat16_rn(s[c]);
+}
+__global__ void permute_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ dst, int H) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < 4 * H) {
+    const int u = r >> 2, g = r & 3;
+    dst[r] = b_ih[g * H + u] + b_hh[g * H + u];
+  }
+}
+// dst[g*H+u, :] (+)= src[4u+g, 0:N] (src leading dimension lds)
+__global__ void unpermute_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int N, int lds, int accumulate) {
+  const int r = blockIdx.x;
+  const int u = r >> 2, g = r & 3;
+  float* d = dst + size_t(g * H + u) * N;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    const float v = src[size_t(r) * lds + c];
+    d[c] = accumulate ? d[c] + v : v;
+  }
+}
+__global__ void fill_bf16_kernel(__nv_bfloat16* __restrict__ dst, size_t n, float v) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  for (; i < n; i += stride) dst[i] = b;
+}
+
+// Cell gradient of one timestep (gate-interleaved layouts).  dG_t = d(pre-activations); dc carried in place.
+__global__ void lstm_cell_bwd_kernel(const __nv_bfloat16* __restrict__ gates_t, const float* __restrict__ c_t,
+                                     const float* __restrict__ c_prev, const float* __restrict__ dh_rec,
+                                     const float* __restrict__ d_hseq_t, const float* __restrict__ d_hlast,
+                                     float* __restrict__ dc, __nv_bfloat16* __restrict__ dG_t, int B, int H) {
+  const size_t cell = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= size_t(B) * H) return;
+  const uint2 gq = *reinterpret_cast<const uint2*>(gates_t + cell * 4);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&gq.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&gq.y);
+  const float i = __bfloat162float(lo.x), f = __bfloat162float(lo.y), g = __bfloat162float(hi.x), o = __bfloat162float(hi.y);
+  float dh = 0.f;
+  if (dh_rec) dh += dh_rec[cell];
+  if (d_hseq_t) dh += d_hseq_t[cell];
+  if (d_hlast) dh += d_hlast[cell];
+  const float tc = tanh_fast_l(c_t[cell]);
+  const float cp = c_prev ? c_prev[cell] : 0.f;
+  const float dct = fmaf(dh * o, 1.f - tc * tc, dc[cell]);
+  const __nv_bfloat162 q0 = __floats2bfloat162_rn(dct * g * i * (1.f - i), dct * cp * f * (1.f - f));
+  const __nv_bfloat162 q1 = __floats2bfloat162_rn(dct * i * (1.f - g * g), dh * tc * o * (1.f - o));
+  uint2 out;
+  out.x = *reinterpret_cast<const uint32_t*>(&q0);
+  out.y = *reinterpret_cast<const uint32_t*>(&q1);
+  *reinterpret_cast<uint2*>(dG_t + cell * 4) = out;
+  dc[cell] = dct * f;
+}
+
+struct LargeWs {
+  float* xp;                 // fwd: [TB,4H] fp32 ; bwd: unused
+  __nv_bfloat16* dG;         // bwd: [TB,4H] bf16 (aliases xp)
+  __nv_bfloat16* wih;        // [4H, I] permuted bf16
+  __nv_bfloat16* whh;        // [4H, H] permuted bf16
+  float* bias;               // [4H] permuted b_ih + b_hh
+  float* dh_rec;             // [B, H]
+  float* dc;                 // [B, H]
+  float* dwp;                // [4H, max(I, H)] permuted dW scratch
+  __nv_bfloat16* ones;       // [TB, 8]
+  float* dbp;                // [4H, 8]
+  size_t total;
+};
+
+static LargeWs carve_ws(void* base, int T, int B, int I, int H) {
+  const size_t tb = size_t(T) * B;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* q = p ? p + off : nullptr; off += al256(bytes); return q; };
+  LargeWs w;
+  w.xp = reinterpret_cast<float*>(take(tb * 4 * H * 4));
+  w.dG = reinterpret_cast<__nv_bfloat16*>(w.xp);
+  w.wih = reinterpret_cast<__nv_bfloat16*>(take(size_t(4) * H * I * 2));
+  w.whh = reinterpret_cast<__nv_bfloat16*>(take(size_t(4) * H * H * 2));
+  w.bias = reinterpret_cast<float*>(take(size_t(4) * H * 4));
+  w.dh_rec = reinterpret_cast<float*>(take(size_t(B) * H * 4));
+  w.dc = reinterpret_cast<float*>(take(size_t(B) * H * 4));
+  w.dwp = reinterpret_cast<float*>(take(size_t(4) * H * (I > H ? I : H) * 4));
+  w.ones = reinterpret_cast<__nv_bfloat16*>(take(tb * 8 * 2));
+  w.dbp = reinterpret_cast<float*>(take(size_t(4) * H * 8 * 4));
+  w.total = off;
+  return w;
+}
+
+int lstm_large_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace) {
+  if (I % 8 != 0 || H % 8 != 0) {
+    set_error("bf16 tensor-core LSTM path needs input and hidden sizes that are multiples of 8 (I=%d H=%d)", I, H);
+    return CSN_EUNSUPPORTED;
+  }
+  const size_t tb = size_t(T) * B;
+  *reserve = al256(tb * 4 * H * 2) + al256(tb * H * 4);
+  *workspace = carve_ws(nullptr, T, B, I, H).total;
+  return CSN_OK;
+}
+
+static int prep_weights(const LargeWs& w, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int I,
+                        int H, cudaStream_t s) {
+  permute_rows_bf16_kernel<<<4 * H, 128, 0, s>>>(w_ih, w.wih, H, I);
+  CSN_LAUNCH_CHECK();
+  permute_rows_bf16_kernel<<<4 * H, 128, 0, s>>>(w_hh, w.whh, H, H);
+  CSN_LAUNCH_CHECK();
+  if (b_ih) {
+    permute_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, s>>>(b_ih, b_hh, w.bias, H);
+    CSN_LAUNCH_CHECK();
+  }
+  return CSN_OK;
+}
+
+int lstm_layer_fwd_large(const void* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, void* h_seq,
+                         void* reserve, void* workspace, int T, int B, int I, int H, int training, cudaStream_t s) {
+  const size_t tb = size_t(T) * B;
+  LargeWs w = carve_ws(workspace, T, B, I, H);
+  __nv_bfloat16* gates = reinterpret_cast<__nv_bfloat16*>(reserve);
+  float* c_seq = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(reserve) + al256(tb * 4 * H * 2));
+  __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(h_seq);
+  CSN_TRY(prep_weights(w, w_ih, w_hh, b_ih, b_hh, I, H, s));
+  // hoisted input projection in gate-interleaved column order
+  CSN_TRY(gemm_tc_run(0, 1, (int)tb, 4 * H, I, x, I, w.wih, I, w.xp, 4 * H, CSN_F32, w.bias, 0, 1, nullptr, s));
+  for (int t = 0; t < T; ++t) {
+    GemmEpi cell{};
+    cell.zero_acc = (t == 0);
+    cell.H = H;
+    cell.xp = w.xp + size_t(t) * B * 4 * H;
+    cell.c_prev = t ? c_seq + size_t(t - 1) * B * H : nullptr;
+    cell.h_out = hs + size_t(t) * B * H;
+    cell.gates_out = gates + size_t(t) * B * 4 * H;  // always kept: the reserve is also the scratch for c (c_seq below)
+    cell.c_out = c_seq + size_t(t) * B * H;
+    const __nv_bfloat16* a = t ? hs + size_t(t - 1) * B * H : hs;  // unused at t = 0 (zero_acc)
+    CSN_TRY(gemm_tc_run(0, 1, B, 4 * H, H, a, H, w.whh, H, nullptr, 4 * H, CSN_F32, nullptr, 0, 1, &cell, s));
+  }
+  (void)training;
+  return CSN_OK;
+}
+
+int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, const void* h_seq, const void* reserve,
+                         const float* d_hseq, const float* d_hlast, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                         float* dx, void* workspace, int T, int B, int I, int H, int accumulate, cudaStream_t s) {
+  const size_t tb = size_t(T) * B;
+  LargeWs w = carve_ws(workspace, T, B, I, H);
+  const __nv_bfloat16* gates = reinterpret_cast<const __nv_bfloat16*>(reserve);
+  const float* c_seq = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(reserve) + al256(tb * 4 * H * 2));
+  CSN_TRY(prep_weights(w, w_ih, w_hh, nullptr, nullptr, I, H, s));
+  CSN_CUDA(cudaMemsetAsync(w.dc, 0, size_t(B) * H * 4, s));
+  const int cells = B * H;
+  for (int t = T - 1; t >= 0; --t) {
+    lstm_cell_bwd_kernel<<<ceil_div(cells, 256), 256, 0, s>>>(
+        gates + size_t(t) * B * 4 * H, c_seq + size_t(t) * B * H, t ? c_seq + size_t(t - 1) * B * H : nullptr,
+        (t + 1 < T) ? w.dh_rec : nullptr, d_hseq ? d_hseq + size_t(t) * B * H : nullptr, (t == T - 1) ? d_hlast : nullptr,
+        w.dc, w.dG + size_t(t) * B * 4 * H, B, H);
+    CSN_LAUNCH_CHECK();
+    if (t > 0)  // dh_{t-1}[B,H] = dG_t[B,4H] . W_hh_perm[4H,H]
+      CSN_TRY(gemm_tc_run(0, 0, B, H, 4 * H, w.dG + size_t(t) * B * 4 * H, 4 * H, w.whh, H, w.dh_rec, H, CSN_F32, nullptr, 0, 1,
+                          nullptr, s));
+  }
+  const int sms = sm_count();
+  auto splits = [&](int M, int N) { return max(1, sms / (ceil_div(M, 128) * ceil_div(N, 128))); };
+  // dW_ih (permuted rows) = dG^T . x, then scatter the rows back to PyTorch gate order
+  CSN_TRY(gemm_tc_run(1, 0, 4 * H, I, (int)tb, w.dG, 4 * H, x, I, w.dwp, I, CSN_F32, nullptr, 0, splits(4 * H, I), nullptr, s));
+  unpermute_rows_kernel<<<4 * H, 128, 0, s>>>(w.dwp, dw_ih, H, I, I, accumulate);
+  CSN_LAUNCH_CHECK();
+  if (T > 1) {
+    CSN_TRY(gemm_tc_run(1, 0, 4 * H, H, (int)(tb - B), w.dG + size_t(B) * 4 * H, 4 * H, h_seq, H, w.dwp, H, CSN_F32, nullptr, 0,
+                        splits(4 * H, H), nullptr, s));
+    unpermute_rows_kernel<<<4 * H, 128, 0, s>>>(w.dwp, dw_hh, H, H, H, accumulate);
+    CSN_LAUNCH_CHECK();
+  } else if (!accumulate) {
+    CSN_CUDA(cudaMemsetAsync(dw_hh, 0, size_t(4) * H * H * 4, s));
+  }
+  // db = dG^T . 1  (tensor-core column sums of the bf16 dG)
+  fill_bf16_kernel<<<min(ceil_div<size_t>(tb * 8, 256), size_t(sms) * 8), 256, 0, s>>>(w.ones, tb * 8, 1.f);
+  CSN_LAUNCH_CHECK();
+  CSN_TRY(gemm_tc_run(1, 0, 4 * H, 8, (int)tb, w.dG, 4 * H, w.ones, 8, w.dbp, 8, CSN_F32, nullptr, 0, splits(4 * H, 8), nullptr, s));
+  unpermute_rows_kernel<<<4 * H, 32, 0, s>>>(w.dbp, db_ih, H, 1, 8, accumulate);
+  CSN_LAUNCH_CHECK();
+  unpermute_rows_kernel<<<4 * H, 32, 0, s>>>(w.dbp, db_hh, H, 1, 8, accumulate);
+  CSN_LAUNCH_CHECK();
+  if (dx) CSN_TRY(gemm_tc_run(0, 0, (int)tb, I, 4 * H, w.dG, 4 * H, w.wih, I, dx, I, CSN_F32, nullptr, 0, 1, nullptr, s));
+  return CSN_OK;
+}
+
+}  // namespace csn

@@ -89,8 +89,10 @@ int csn_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const void* A,
  * Replaces torch.nn.LSTM inside the (missing) models.lstm.Model -- call sites LstmDistillFromDinoV2Train.py:323,365;
  * analogue LSTMDistillRetreival.py:91,103.  Gate order i,f,g,o, zero initial state, one layer per call.
  * compute_dtype CSN_F32 : SIMT fp32 path (tight-tolerance parity mode, any H).
- * compute_dtype CSN_BF16: persistent tcgen05 recurrence (W_hh resident in shared memory, gate accumulators in
- *                         TMEM, fused sigmoid/tanh/cell epilogue), hoisted input projection on tcgen05; H <= 128.
+ * compute_dtype CSN_BF16: H <= 128: persistent tcgen05 recurrence (W_hh resident in tensor memory, gate accumulators
+ *                         in TMEM, fused sigmoid/tanh/cell epilogue), hoisted input projection on tcgen05.
+ *                         H > 128 : one tcgen05 GEMM per timestep with the LSTM cell fused into its epilogue.
+ *                         I and H must be multiples of 8 (16-byte TMA rows).
  * x [T,B,I] in x_dtype (must equal compute_dtype); h_seq [T,B,H] in compute_dtype; weights fp32 masters.
  * reserve: opaque per-step state kept for BPTT (training != 0); sizes from csn_lstm_layer_bytes. */
 int csn_lstm_layer_bytes(int T, int B, int I, int H, int compute_dtype, size_t* reserve_bytes, size_t* workspace_bytes);

@@ -57,5 +57,18 @@ with open(os.path.join(out_dir, f"ncu_full_{tag}.md"), "w") as f:
         for w, i in idx[1:]:
             f.write(f"| {w} | {r[i]} | {units[i]} |\n")
         f.write("\n")
+# ---- machine-readable per-launch DRAM traffic for bench.py's roofline.traffic ----
+import json
+traffic = {}
+ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+def _to_bytes(v, u):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+for name, r in seen.items():
+    key = name.replace("void ", "").replace("csn::", "")
+    traffic[key] = {"dram_read_bytes": _to_bytes(r[ir], units[ir]), "dram_write_bytes": _to_bytes(r[iw], units[iw]),
+                    "duration_us_under_ncu": float(r[it].replace(",", "")) * ({"ns": 1e-3, "us": 1, "ms": 1e3}.get(units[it], 1))}
+json.dump({"tag": tag, "source": f"ncu --set full, profiles/ncu_full_{tag}.md", "kernels": traffic},
+          open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out_dir, f"launches_{tag}.md")).read()[:2500])
 print(open(os.path.join(out_dir, f"ncu_full_{tag}.md")).read()[:6000])

@@ -69,7 +69,9 @@ def _cos(a, b):
 
 
 @pytest.mark.parametrize("T,B,I,H", [(6, 4, 16, 16), (50, 5, 32, 64), (30, 37, 128, 128), (24, 3, 96, 96), (440, 16, 128, 128),
-                                     (16, 300, 64, 128)])
+                                     (16, 300, 64, 128),
+                                     # large-hidden path (per-step tcgen05 GEMM with the fused cell epilogue), cfg 4 sizes
+                                     (12, 5, 64, 256), (20, 130, 128, 512), (9, 3, 24, 136)])
 @pytest.mark.parametrize("mode", ["last", "both"])
 def test_bf16_tensor_core_layer(T, B, I, H, mode):
     g = torch.Generator().manual_seed(T + B + I + H)
@@ -90,10 +92,12 @@ def test_bf16_tensor_core_layer(T, B, I, H, mode):
     assert _cos(dx, ref_dx) >= 0.995 and rel <= 6e-2, ("dx", rel)
 
 
-def test_bf16_unsupported_hidden_is_an_error_not_a_fallback():
+def test_bf16_unsupported_shape_is_an_error_not_a_fallback():
     from cerebralsignalnetworks_b200 import ops, _lib
     with pytest.raises(_lib.CsnError):
-        ops.lstm_layer_bytes(10, 4, 128, 512, torch.bfloat16)
+        ops.lstm_layer_bytes(10, 4, 63, 128, torch.bfloat16)  # TMA needs 16-byte rows: I % 8 != 0 is rejected
+    with pytest.raises(_lib.CsnError):
+        ops.lstm_layer_bytes(10, 4, 64, 100, torch.bfloat16)
 
 
 def test_zero_weights_give_zero_state():
