@@ -26,29 +26,49 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, floa
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   float acc[TM][TM] = {};
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    // A tile: BM x BK
+  // global -> registers for tile k0 (issued one tile ahead of its use: the loads of tile k+1 fly while tile k is
+  // multiplied out of shared memory)
+  constexpr int NA = (BM * BK) / 256, NB = (BN * BK) / 256;
+  float ra[NA], rb[NB];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < (BM * BK) / 256; ++i) {
+    for (int i = 0; i < NA; ++i) {
       int e = tid + i * 256;
       int mm, kk;
       if (TA) { mm = e % BM; kk = e / BM; } else { kk = e % BK; mm = e / BK; }
       int gm = m0 + mm, gk = k0 + kk;
-      float v = 0.f;
-      if (gm < M && gk < K) v = TA ? A[size_t(gk) * lda + gm] : A[size_t(gm) * lda + gk];
-      As[kk][mm] = v;
+      ra[i] = (gm < M && gk < K) ? (TA ? A[size_t(gk) * lda + gm] : A[size_t(gm) * lda + gk]) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < (BN * BK) / 256; ++i) {
+    for (int i = 0; i < NB; ++i) {
       int e = tid + i * 256;
       int nn, kk;
       if (TB) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
       int gn = n0 + nn, gk = k0 + kk;
-      float v = 0.f;
-      if (gn < N && gk < K) v = TB ? B[size_t(gn) * ldb + gk] : B[size_t(gk) * ldb + gn];
-      Bs[kk][nn] = v;
+      rb[i] = (gn < N && gk < K) ? (TB ? B[size_t(gn) * ldb + gk] : B[size_t(gk) * ldb + gn]) : 0.f;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      int e = tid + i * 256;
+      int mm, kk;
+      if (TA) { mm = e % BM; kk = e / BM; } else { kk = e % BK; mm = e / BK; }
+      As[kk][mm] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      int e = tid + i * 256;
+      int nn, kk;
+      if (TB) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
+      Bs[kk][nn] = rb[i];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    stash();
     __syncthreads();
+    if (k0 + BK < K) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float av[TM], bv[TM];

@@ -179,7 +179,9 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
     const int u = tid;
     const bool active = u < H;
     const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
-    float bias[4], c[NV], xcur[4][NV], xnext[4][NV];
+    // Xp prefetch: three rotating register sets, the time loop is unrolled by 3 so the rotation is a compile-time
+    // renaming (a register copy of a pending load would stall on it).  Loads run two steps (~2.3 k cycles) ahead.
+    float bias[4], c[NV], xbuf[3][4][NV];
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = active ? b_hh[g * H + u] : 0.f;
 #pragma unroll
@@ -194,15 +196,20 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
         for (int g = 0; g < 4; ++g) dst[g][j] = ok ? __ldcs(row + g * H) : 0.f;
       }
     };
-    load_xp(0, xcur);
+    load_xp(0, xbuf[0]);
+    load_xp(1, xbuf[1]);
 
-    for (int t = 0; t < T; ++t) {
-      load_xp(t + 1, xnext);  // in flight while this step computes
+    for (int t0 = 0; t0 < T; t0 += 3) {
+#pragma unroll
+     for (int ph = 0; ph < 3; ++ph) {
+      const int t = t0 + ph;
+      if (t >= T) break;
+      load_xp(t + 2, xbuf[(ph + 2) % 3]);  // in flight for two steps
       float pre[4][NV];
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int j = 0; j < NV; ++j) pre[g][j] = xcur[g][j] + bias[g];
+        for (int j = 0; j < NV; ++j) pre[g][j] = xbuf[ph][g][j] + bias[g];
       const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && t < kProfSteps;
       if (t > 0) {
         mbar_wait(sm.bar_acc, (t - 1) & 1);
@@ -255,10 +262,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
           }
         }
       }
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int j = 0; j < NV; ++j) xcur[g][j] = xnext[g][j];
+     }
     }
   }
   tcgen05_fence_before();
@@ -354,11 +358,17 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
         s.dh[j] = d;
       }
     };
-    StepIn cur, nxt;
-    load_step(T - 1, cur);
+    StepIn sbuf[3];  // rotating prefetch sets, loop unrolled by 3 (see the forward kernel)
+    load_step(T - 1, sbuf[0]);
+    load_step(T - 2, sbuf[1]);
     int n = 0;
-    for (int t = T - 1; t >= 0; --t) {
-      load_step(t - 1, nxt);
+    for (int t0 = T - 1; t0 >= 0; t0 -= 3) {
+#pragma unroll
+     for (int ph = 0; ph < 3; ++ph) {
+      const int t = t0 - ph;
+      if (t < 0) break;
+      load_step(t - 2, sbuf[(ph + 2) % 3]);
+      StepIn& cur = sbuf[ph];
       float dh[NV], tcn[NV], pref[NV];
       // everything that does not need dh is done before the wait
 #pragma unroll
@@ -415,7 +425,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
           }
         }
       }
-      cur = nxt;
+     }
     }
     if (active) {
 #pragma unroll
@@ -438,6 +448,8 @@ static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 static int pick_nv(int B) {
   // smallest batch tile that still fills the machine: per-step latency falls with NV (fewer MUFU ops per SM)
+  static const int forced = [] { const char* e = getenv("CSN_LSTM_NV"); return e ? atoi(e) : 0; }();
+  if (forced == 2 || forced == 4 || forced == 8) return forced;
   const int sms = sm_count();
   if (ceil_div(B, 2) <= sms) return 2;
   if (ceil_div(B, 4) <= sms) return 4;
