@@ -187,13 +187,18 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
 #pragma unroll
     for (int j = 0; j < NV; ++j) c[j] = 0.f;
 
+    // NOTE: nothing may CONSUME a prefetched value at issue time (a dependent instruction would stall this in-order
+    // warp for the whole memory latency): plain predicated loads into zero-initialised registers.
     auto load_xp = [&](int t, float (&dst)[4][NV]) {
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const bool ok = active && (b0 + j < B) && (t < T);
         const float* row = xp + (size_t(t) * B + (b0 + j)) * 4 * H + u;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) dst[g][j] = ok ? __ldcs(row + g * H) : 0.f;
+        for (int g = 0; g < 4; ++g) {
+          dst[g][j] = 0.f;
+          if (ok) dst[g][j] = __ldcs(row + g * H);
+        }
       }
     };
     load_xp(0, xbuf[0]);
@@ -212,6 +217,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
         for (int j = 0; j < NV; ++j) pre[g][j] = xbuf[ph][g][j] + bias[g];
       const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && t < kProfSteps;
       if (t > 0) {
+        if (do_prof) prof[t * 8 + 6] = clock64();
         mbar_wait(sm.bar_acc, (t - 1) & 1);
         tcgen05_fence_after();
         if (do_prof) prof[t * 8 + 0] = clock64();
@@ -337,27 +343,34 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
 #pragma unroll
     for (int j = 0; j < NV; ++j) dc[j] = 0.f;
 
+    // Prefetch record of one step, kept RAW: no conversion / addition may consume a loaded value at issue time (a
+    // dependent instruction would stall this in-order warp for the whole memory latency); decoded two steps later.
     struct StepIn {
-      float i[NV], f[NV], g[NV], o[NV], c[NV], cp[NV], dh[NV];
+      unsigned short i[NV], f[NV], g[NV], o[NV];
+      float c[NV], cp[NV], dhs[NV], dhl[NV];
     };
     auto load_step = [&](int t, StepIn& s) {
+      const unsigned short* graw = reinterpret_cast<const unsigned short*>(gates);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const bool ok = active && (b0 + j < B) && (t >= 0);
         const size_t cell = (size_t(t < 0 ? 0 : t) * B + (b0 + j)) * H + u;
-        const __nv_bfloat16* gr = gates + (size_t(t < 0 ? 0 : t) * B + (b0 + j)) * 4 * H + u;
-        s.i[j] = ok ? __bfloat162float(gr[0]) : 0.f;
-        s.f[j] = ok ? __bfloat162float(gr[H]) : 0.f;
-        s.g[j] = ok ? __bfloat162float(gr[2 * H]) : 0.f;
-        s.o[j] = ok ? __bfloat162float(gr[3 * H]) : 0.f;
-        s.c[j] = ok ? c_seq[cell] : 0.f;
-        s.cp[j] = (ok && t > 0) ? c_seq[cell - size_t(B) * H] : 0.f;
-        float d = 0.f;
-        if (ok && d_hseq) d += d_hseq[cell];
-        if (ok && d_hlast && t == T - 1) d += d_hlast[size_t(b0 + j) * H + u];
-        s.dh[j] = d;
+        const unsigned short* gr = graw + (size_t(t < 0 ? 0 : t) * B + (b0 + j)) * 4 * H + u;
+        s.i[j] = 0; s.f[j] = 0; s.g[j] = 0; s.o[j] = 0;
+        s.c[j] = 0.f; s.cp[j] = 0.f; s.dhs[j] = 0.f; s.dhl[j] = 0.f;
+        if (ok) {
+          s.i[j] = gr[0];
+          s.f[j] = gr[H];
+          s.g[j] = gr[2 * H];
+          s.o[j] = gr[3 * H];
+          s.c[j] = c_seq[cell];
+          if (t > 0) s.cp[j] = c_seq[cell - size_t(B) * H];
+          if (d_hseq) s.dhs[j] = d_hseq[cell];
+          if (d_hlast && t == T - 1) s.dhl[j] = d_hlast[size_t(b0 + j) * H + u];
+        }
       }
     };
+    auto bf = [](unsigned short r) { return __uint_as_float(uint32_t(r) << 16); };
     StepIn sbuf[3];  // rotating prefetch sets, loop unrolled by 3 (see the forward kernel)
     load_step(T - 1, sbuf[0]);
     load_step(T - 2, sbuf[1]);
@@ -368,17 +381,21 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
       const int t = t0 - ph;
       if (t < 0) break;
       load_step(t - 2, sbuf[(ph + 2) % 3]);
-      StepIn& cur = sbuf[ph];
+      StepIn& raw = sbuf[ph];
+      struct { float i[NV], f[NV], g[NV], o[NV], c[NV], cp[NV]; } cur;
       float dh[NV], tcn[NV], pref[NV];
       // everything that does not need dh is done before the wait
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        dh[j] = cur.dh[j];
+        cur.i[j] = bf(raw.i[j]); cur.f[j] = bf(raw.f[j]); cur.g[j] = bf(raw.g[j]); cur.o[j] = bf(raw.o[j]);
+        cur.c[j] = raw.c[j]; cur.cp[j] = raw.cp[j];
+        dh[j] = raw.dhs[j] + raw.dhl[j];
         tcn[j] = tanh_fast(cur.c[j]);
         pref[j] = cur.o[j] * (1.f - tcn[j] * tcn[j]);
       }
       const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps;
       if (t < T - 1) {
+        if (do_prof) prof[512 + n * 8 + 6] = clock64();
         mbar_wait(sm.bar_acc, (n - 1) & 1);
         tcgen05_fence_after();
         if (do_prof) prof[512 + n * 8 + 0] = clock64();
@@ -425,6 +442,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
           }
         }
       }
+      if (do_prof) prof[512 + (n - 1) * 8 + 7] = clock64();
      }
     }
     if (active) {
