@@ -23,7 +23,10 @@ namespace csn {
 
 using namespace tc;
 
-constexpr int kRecThreads = 160;  // warps 0-3: epilogue (TMEM lane quadrants 0-3), warp 4: MMA issuer
+// warps 0-7: epilogue -- warp w owns TMEM lane quadrant w % 4 (32 hidden units) and half (w / 4) of the CTA's batch
+// slots, so the per-step gate math / reserve traffic of a unit is split over two warps; warp 8: MMA issuer.
+constexpr int kEpiWarps = 8, kIssuerWarp = 8;
+constexpr int kRecThreads = (kEpiWarps + 1) * 32;
 constexpr uint32_t kLboB = 256, kSboB = 128;   // 16-row operand: 2 core matrices per k-group
 constexpr int kNslots = 16;                    // MMA N (batch slots per CTA); NV <= 16 of them are live
 constexpr int kProfSteps = 64;                 // bring-up instrumentation: clock64 stamps for the first steps of CTA 0
@@ -134,11 +137,11 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
 
   for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
-    mbar_init(sm.bar_in, 4);
+    mbar_init(sm.bar_in, kEpiWarps);
     mbar_init(sm.bar_acc, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(sm.tmem_slot, kTmemCols);
+  if (warp == kIssuerWarp) tmem_alloc(sm.tmem_slot, kTmemCols);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -151,11 +154,12 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       return (u < H && k < H) ? w_hh[size_t(g * H + u) * H + k] : 0.f;
     });
   }
+  constexpr int NVT = NV / 2;  // cells per epilogue thread
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
 
-  if (warp == 4) {
+  if (warp == kIssuerWarp) {
     // ================= MMA issuer: whole warp converged, one ELECTED lane issues =================
     // (elect.sync lets ptxas feed tcgen05.mma from uniform registers directly; a plain `lane == 0` guard makes it
     //  emit an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall around every MMA, ~60 cycles each, measured.)
@@ -175,29 +179,33 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       __syncwarp();
     }
   } else {
-    // ================= epilogue: thread = hidden unit u =================
-    const int u = tid;
+    // ================= epilogue: thread = (hidden unit u, half of the batch slots) =================
+    const int u = tid & 127;
+    const int jb = (tid >> 7) * NVT;  // first batch slot of this thread
     const bool active = u < H;
-    const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+    const uint32_t lane_addr = tmem_base + (uint32_t((warp & 3) * 32) << 16) + jb;
     // Xp prefetch: three rotating register sets, the time loop is unrolled by 3 so the rotation is a compile-time
-    // renaming (a register copy of a pending load would stall on it).  Loads run two steps (~2.3 k cycles) ahead.
-    float bias[4], c[NV], xbuf[3][4][NV];
+    // renaming (a register copy of a pending load would stall on it).  Loads run two steps (~2 k cycles) ahead.
+    float bias[4], c[NVT], xbuf[3][4][NVT];
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = active ? b_hh[g * H + u] : 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) c[j] = 0.f;
+    for (int j = 0; j < NVT; ++j) c[j] = 0.f;
+    bool valid[NVT];
+#pragma unroll
+    for (int j = 0; j < NVT; ++j) valid[j] = active && (b0 + jb + j < B);
+    const size_t step_cells = size_t(B) * H;
 
     // NOTE: nothing may CONSUME a prefetched value at issue time (a dependent instruction would stall this in-order
     // warp for the whole memory latency): plain predicated loads into zero-initialised registers.
-    auto load_xp = [&](int t, float (&dst)[4][NV]) {
+    auto load_xp = [&](int t, float (&dst)[4][NVT]) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const bool ok = active && (b0 + j < B) && (t < T);
-        const float* row = xp + (size_t(t) * B + (b0 + j)) * 4 * H + u;
+      for (int j = 0; j < NVT; ++j) {
+        const float* row = xp + (size_t(t) * B + (b0 + jb + j)) * 4 * H + u;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           dst[g][j] = 0.f;
-          if (ok) dst[g][j] = __ldcs(row + g * H);
+          if (valid[j] && t < T) dst[g][j] = __ldcs(row + g * H);
         }
       }
     };
@@ -210,39 +218,39 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       const int t = t0 + ph;
       if (t >= T) break;
       load_xp(t + 2, xbuf[(ph + 2) % 3]);  // in flight for two steps
-      float pre[4][NV];
+      float pre[4][NVT];
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int j = 0; j < NV; ++j) pre[g][j] = xbuf[ph][g][j] + bias[g];
+        for (int j = 0; j < NVT; ++j) pre[g][j] = xbuf[ph][g][j] + bias[g];
       const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && t < kProfSteps;
       if (t > 0) {
         if (do_prof) prof[t * 8 + 6] = clock64();
         mbar_wait(sm.bar_acc, (t - 1) & 1);
         tcgen05_fence_after();
         if (do_prof) prof[t * 8 + 0] = clock64();
-        uint32_t r[4][NV];
+        uint32_t r[4][NVT];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld<NV>(lane_addr + g * kNslots, r[g]);
+        for (int g = 0; g < 4; ++g) tmem_ld<NVT>(lane_addr + g * kNslots, r[g]);
         tmem_ld_wait();
         tcgen05_fence_before();  // our TMEM reads are ordered before the MMAs the next hand-off releases
         if (do_prof) prof[t * 8 + 1] = clock64();
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int j = 0; j < NV; ++j) pre[g][j] += __uint_as_float(r[g][j]);
+          for (int j = 0; j < NVT; ++j) pre[g][j] += __uint_as_float(r[g][j]);
       }
-      float gi[NV], gf[NV], gg[NV], go[NV];
-      __nv_bfloat16 hb[NV];
+      float gi[NVT], gf[NVT], gg[NVT], go[NVT];
+      __nv_bfloat16 hb[NVT];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
+      for (int j = 0; j < NVT; ++j) {
         gi[j] = sigmoid_fast(pre[0][j]);
         gf[j] = sigmoid_fast(pre[1][j]);
         gg[j] = tanh_fast(pre[2][j]);
         go[j] = sigmoid_fast(pre[3][j]);
         c[j] = fmaf(gf[j], c[j], gi[j] * gg[j]);
         hb[j] = __float2bfloat16_rn(go[j] * tanh_fast(c[j]));
-        if (active) *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, u, kLboB, kSboB)) = hb[j];
+        if (active) *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(jb + j, u, kLboB, kSboB)) = hb[j];
       }
       // publish h_t to the async proxy and hand over: one arrival per warp
       if (do_prof) prof[t * 8 + 2] = clock64();
@@ -251,20 +259,18 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       if (lane == 0) mbar_arrive(sm.bar_in);
       if (do_prof) prof[t * 8 + 3] = clock64();
       // ---- off the critical path: stream h_t and the BPTT reserve to HBM while the next MMAs run ----
-      if (active) {
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          if (b0 + j < B) {
-            const size_t cell = (size_t(t) * B + (b0 + j)) * H + u;
-            h_seq[cell] = hb[j];
-            if (gates_out) {
-              __nv_bfloat16* gr = gates_out + (size_t(t) * B + (b0 + j)) * 4 * H + u;
-              gr[0] = __float2bfloat16_rn(gi[j]);
-              gr[H] = __float2bfloat16_rn(gf[j]);
-              gr[2 * H] = __float2bfloat16_rn(gg[j]);
-              gr[3 * H] = __float2bfloat16_rn(go[j]);
-              c_out[cell] = c[j];
-            }
+      for (int j = 0; j < NVT; ++j) {
+        if (valid[j]) {
+          const size_t cell = size_t(t) * step_cells + size_t(b0 + jb + j) * H + u;
+          h_seq[cell] = hb[j];
+          if (gates_out) {
+            __nv_bfloat16* gr = gates_out + (size_t(t) * B + (b0 + jb + j)) * 4 * H + u;
+            gr[0] = __float2bfloat16_rn(gi[j]);
+            gr[H] = __float2bfloat16_rn(gf[j]);
+            gr[2 * H] = __float2bfloat16_rn(gg[j]);
+            gr[3 * H] = __float2bfloat16_rn(go[j]);
+            c_out[cell] = c[j];
           }
         }
       }
@@ -273,7 +279,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kIssuerWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -296,11 +302,11 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
 
   for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
-    mbar_init(sm.bar_in, 4);
+    mbar_init(sm.bar_in, kEpiWarps);
     mbar_init(sm.bar_acc, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(sm.tmem_slot, kTmemCols);
+  if (warp == kIssuerWarp) tmem_alloc(sm.tmem_slot, kTmemCols);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -317,7 +323,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
   __syncthreads();
   tcgen05_fence_after();
 
-  if (warp == 4) {
+  if (warp == kIssuerWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
     const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
     const bool base0 = (tmem_base == 0);
@@ -336,26 +342,31 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
       __syncwarp();
     }
   } else {
-    const int u = tid;
+    constexpr int NVT = NV / 2;  // cells per epilogue thread
+    const int u = tid & 127;
+    const int jb = (tid >> 7) * NVT;
     const bool active = u < H;
-    const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
-    float dc[NV], dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t lane_addr = tmem_base + (uint32_t((warp & 3) * 32) << 16) + jb;
+    float dc[NVT], dbacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < NV; ++j) dc[j] = 0.f;
+    for (int j = 0; j < NVT; ++j) dc[j] = 0.f;
+    bool valid[NVT];
+#pragma unroll
+    for (int j = 0; j < NVT; ++j) valid[j] = active && (b0 + jb + j < B);
 
     // Prefetch record of one step, kept RAW: no conversion / addition may consume a loaded value at issue time (a
     // dependent instruction would stall this in-order warp for the whole memory latency); decoded two steps later.
     struct StepIn {
-      unsigned short i[NV], f[NV], g[NV], o[NV];
-      float c[NV], cp[NV], dhs[NV], dhl[NV];
+      unsigned short i[NVT], f[NVT], g[NVT], o[NVT];
+      float c[NVT], cp[NVT], dhs[NVT], dhl[NVT];
     };
     auto load_step = [&](int t, StepIn& s) {
       const unsigned short* graw = reinterpret_cast<const unsigned short*>(gates);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const bool ok = active && (b0 + j < B) && (t >= 0);
-        const size_t cell = (size_t(t < 0 ? 0 : t) * B + (b0 + j)) * H + u;
-        const unsigned short* gr = graw + (size_t(t < 0 ? 0 : t) * B + (b0 + j)) * 4 * H + u;
+      for (int j = 0; j < NVT; ++j) {
+        const bool ok = valid[j] && (t >= 0);
+        const size_t cell = (size_t(t < 0 ? 0 : t) * B + (b0 + jb + j)) * H + u;
+        const unsigned short* gr = graw + (size_t(t < 0 ? 0 : t) * B + (b0 + jb + j)) * 4 * H + u;
         s.i[j] = 0; s.f[j] = 0; s.g[j] = 0; s.o[j] = 0;
         s.c[j] = 0.f; s.cp[j] = 0.f; s.dhs[j] = 0.f; s.dhl[j] = 0.f;
         if (ok) {
@@ -366,7 +377,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
           s.c[j] = c_seq[cell];
           if (t > 0) s.cp[j] = c_seq[cell - size_t(B) * H];
           if (d_hseq) s.dhs[j] = d_hseq[cell];
-          if (d_hlast && t == T - 1) s.dhl[j] = d_hlast[size_t(b0 + j) * H + u];
+          if (d_hlast && t == T - 1) s.dhl[j] = d_hlast[size_t(b0 + jb + j) * H + u];
         }
       }
     };
@@ -382,11 +393,11 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
       if (t < 0) break;
       load_step(t - 2, sbuf[(ph + 2) % 3]);
       StepIn& raw = sbuf[ph];
-      struct { float i[NV], f[NV], g[NV], o[NV], c[NV], cp[NV]; } cur;
-      float dh[NV], tcn[NV], pref[NV];
+      struct { float i[NVT], f[NVT], g[NVT], o[NVT], c[NVT], cp[NVT]; } cur;
+      float dh[NVT], tcn[NVT], pref[NVT];
       // everything that does not need dh is done before the wait
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
+      for (int j = 0; j < NVT; ++j) {
         cur.i[j] = bf(raw.i[j]); cur.f[j] = bf(raw.f[j]); cur.g[j] = bf(raw.g[j]); cur.o[j] = bf(raw.o[j]);
         cur.c[j] = raw.c[j]; cur.cp[j] = raw.cp[j];
         dh[j] = raw.dhs[j] + raw.dhl[j];
@@ -399,17 +410,17 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
         mbar_wait(sm.bar_acc, (n - 1) & 1);
         tcgen05_fence_after();
         if (do_prof) prof[512 + n * 8 + 0] = clock64();
-        uint32_t r[NV];
-        tmem_ld<NV>(lane_addr, r);
+        uint32_t r[NVT];
+        tmem_ld<NVT>(lane_addr, r);
         tmem_ld_wait();
         tcgen05_fence_before();
         if (do_prof) prof[512 + n * 8 + 1] = clock64();
 #pragma unroll
-        for (int j = 0; j < NV; ++j) dh[j] += __uint_as_float(r[j]);
+        for (int j = 0; j < NVT; ++j) dh[j] += __uint_as_float(r[j]);
       }
-      float dg[4][NV];
+      float dg[4][NVT];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
+      for (int j = 0; j < NVT; ++j) {
         const float dct = fmaf(dh[j], pref[j], dc[j]);
         dg[0][j] = dct * cur.g[j] * cur.i[j] * (1.f - cur.i[j]);
         dg[1][j] = dct * cur.cp[j] * cur.f[j] * (1.f - cur.f[j]);
@@ -419,7 +430,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
         if (active) {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(j, g * 128 + u, kLboB, kSboB)) = __float2bfloat16_rn(dg[g][j]);
+            *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(jb + j, g * 128 + u, kLboB, kSboB)) = __float2bfloat16_rn(dg[g][j]);
         }
       }
       if (do_prof) prof[512 + n * 8 + 2] = clock64();
@@ -429,16 +440,14 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
       if (do_prof) prof[512 + n * 8 + 3] = clock64();
       ++n;
       // ---- off the critical path ----
-      if (active) {
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          if (b0 + j < B) {
-            __nv_bfloat16* gr = dG + (size_t(t) * B + (b0 + j)) * 4 * H + u;
+      for (int j = 0; j < NVT; ++j) {
+        if (valid[j]) {
+          __nv_bfloat16* gr = dG + (size_t(t) * B + (b0 + jb + j)) * 4 * H + u;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              gr[g * H] = __float2bfloat16_rn(dg[g][j]);
-              dbacc[g] += dg[g][j];
-            }
+          for (int g = 0; g < 4; ++g) {
+            gr[g * H] = __float2bfloat16_rn(dg[g][j]);
+            dbacc[g] += dg[g][j];
           }
         }
       }
@@ -455,7 +464,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kIssuerWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
   }
