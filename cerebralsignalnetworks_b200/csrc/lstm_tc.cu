@@ -27,6 +27,11 @@ using namespace tc;
 // slots, so the per-step gate math / reserve traffic of a unit is split over two warps; warp 8: MMA issuer.
 constexpr int kEpiWarps = 8, kIssuerWarp = 8;
 constexpr int kRecThreads = (kEpiWarps + 1) * 32;
+// epilogue -> issuer hand-off: hardware named barrier 1 over all 288 threads (the 256 epilogue threads ARRIVE without
+// blocking, the issuer warp SYNCs); ~2x lower latency than an mbarrier round trip, measured on the step stamps.
+__device__ __forceinline__ void handoff_arrive() { asm volatile("bar.arrive 1, 288;" ::: "memory"); }
+__device__ __forceinline__ void handoff_wait() { asm volatile("bar.sync 1, 288;" ::: "memory"); }
+static_assert(kRecThreads == 288, "named-barrier thread count is spelled out in the PTX above");
 constexpr uint32_t kLboB = 256, kSboB = 128;   // 16-row operand: 2 core matrices per k-group
 constexpr int kNslots = 16;                    // MMA N (batch slots per CTA); NV <= 16 of them are live
 constexpr int kProfSteps = 64;                 // bring-up instrumentation: clock64 stamps for the first steps of CTA 0
@@ -62,20 +67,44 @@ __device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t b_bytes) {
 //   [256, 512) resident weights as packed bf16 pairs: gate g at columns 256 + 64 g + k/2
 constexpr uint32_t kTmemCols = 512, kAcol0 = 256, kAgate = 64;
 
-// W block -> tensor memory.  Thread `row` (TMEM lane) writes, for each gate g, the 64 packed columns
-// (elem(g, 2c), elem(g, 2c+1)); elem() returns 0 outside the matrix.
-template <typename F>
-__device__ __forceinline__ void stage_weights_tmem(uint32_t lane_addr, F elem) {
+// The resident weight operand is prepared once per call by a small packing kernel as the exact TMEM image
+// [gate][lane][64 columns] of packed bf16 pairs (column c = K elements 2c, 2c+1; zero padded), so that every
+// recurrence CTA fills its tensor memory with 64 coalescable 16-byte loads per thread instead of 512 strided
+// scalar fp32 loads.  transposed = 0: forward operand, lane = hidden unit u, K = input unit k  (W_hh[g*H+u][k]);
+// transposed = 1: backward operand, lane = k, K = u (W_hh^T).
+__global__ void pack_whh_tmem_image_kernel(const float* __restrict__ w_hh, uint32_t* __restrict__ img, int H, int transposed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 4 * 128 * 64
+  if (idx >= 4 * 128 * 64) return;
+  int g, lane, c;
+  if (!transposed) { c = idx & 63; lane = (idx >> 6) & 127; g = idx >> 13; }   // consecutive threads -> consecutive k
+  else { lane = idx & 127; c = (idx >> 7) & 63; g = idx >> 13; }               // consecutive threads -> consecutive k (= lane)
+  const int k0 = 2 * c, k1 = 2 * c + 1;
+  float v0 = 0.f, v1 = 0.f;
+  if (lane < H) {
+    if (!transposed) {
+      if (k0 < H) v0 = w_hh[size_t(g * H + lane) * H + k0];
+      if (k1 < H) v1 = w_hh[size_t(g * H + lane) * H + k1];
+    } else {
+      if (k0 < H) v0 = w_hh[size_t(g * H + k0) * H + lane];
+      if (k1 < H) v1 = w_hh[size_t(g * H + k1) * H + lane];
+    }
+  }
+  __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
+  img[(size_t(g) * 128 + lane) * 64 + c] = *reinterpret_cast<uint32_t*>(&bb);
+}
+
+// image -> tensor memory: thread `row` (TMEM lane) copies its 4 x 64 packed columns
+__device__ __forceinline__ void stage_weights_tmem(uint32_t lane_addr, const uint32_t* __restrict__ img, int row) {
 #pragma unroll 1
   for (int g = 0; g < 4; ++g) {
+    const uint4* src = reinterpret_cast<const uint4*>(img + (size_t(g) * 128 + row) * 64);
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       uint32_t r[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int k = (half * 32 + c) * 2;
-        __nv_bfloat162 bb = __floats2bfloat162_rn(elem(g, k), elem(g, k + 1));
-        r[c] = *reinterpret_cast<uint32_t*>(&bb);
+      for (int q = 0; q < 8; ++q) {
+        const uint4 v = __ldg(src + half * 8 + q);
+        r[q * 4 + 0] = v.x; r[q * 4 + 1] = v.y; r[q * 4 + 2] = v.z; r[q * 4 + 3] = v.w;
       }
       tmem_st32(lane_addr + kAcol0 + g * kAgate + half * 32, r);
     }
@@ -125,7 +154,7 @@ __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t 
 // ------------------------------------------------------------------------------------------------ forward
 template <int NV, int KSTEPS>
 __global__ void __launch_bounds__(kRecThreads, 1)
-lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_img, const float* __restrict__ b_hh,
                    __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
                    int T, int B, int H, int KP, long long* __restrict__ prof) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -148,12 +177,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
   tcgen05_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
   // W_hh resident in TENSOR MEMORY for the whole sequence: lane = hidden unit u (row of each gate block)
-  if (warp < 4) {
-    const int u = tid;
-    stage_weights_tmem(tmem_base + (uint32_t(warp * 32) << 16), [&](int g, int k) {
-      return (u < H && k < H) ? w_hh[size_t(g * H + u) * H + k] : 0.f;
-    });
-  }
+  if (warp < 4) stage_weights_tmem(tmem_base + (uint32_t(warp * 32) << 16), w_img, tid);
   constexpr int NVT = NV / 2;  // cells per epilogue thread
   tcgen05_fence_before();
   __syncthreads();
@@ -166,8 +190,9 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
     constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
     const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
     const bool base0 = (tmem_base == 0);  // a 512-column allocation owns the whole TMEM: constant addresses
-    for (int t = 1; t < T; ++t) {
-      mbar_wait(sm.bar_in, (t - 1) & 1);  // h_{t-1} is in shared memory (and TMEM has been drained)
+    for (int t = 1; t <= T; ++t) {
+      handoff_wait();  // h_{t-1} is in shared memory (and TMEM has been drained)
+      if (t == T) break;  // the last hand-off only balances the barrier
       tcgen05_fence_after();
       if (elect_one()) {
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 4] = clock64();
@@ -255,8 +280,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
       // publish h_t to the async proxy and hand over: one arrival per warp
       if (do_prof) prof[t * 8 + 2] = clock64();
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sm.bar_in);
+      handoff_arrive();
       if (do_prof) prof[t * 8 + 3] = clock64();
       // ---- off the critical path: stream h_t and the BPTT reserve to HBM while the next MMAs run ----
 #pragma unroll
@@ -289,7 +313,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh,
 // dh_{t-1}^T[k, b] = sum_{kk = g*KP + u} W_hh[g*H + u][k] * dG_t[b, kk]: M = hidden unit k (TMEM lane), K = 4*KP.
 template <int NV, int KSTEPS>
 __global__ void __launch_bounds__(kRecThreads, 1)
-lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
+lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
                    float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP,
                    long long* __restrict__ prof) {
@@ -313,12 +337,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
   tcgen05_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
   // W_hh^T resident in tensor memory: lane = m (hidden unit k of dh), column 256 + 64 g + u/2 holds W_hh[g*H+u][m]
-  if (warp < 4) {
-    const int m = tid;
-    stage_weights_tmem(tmem_base + (uint32_t(warp * 32) << 16), [&](int g, int uu) {
-      return (m < H && uu < H) ? w_hh[size_t(g * H + uu) * H + m] : 0.f;
-    });
-  }
+  if (warp < 4) stage_weights_tmem(tmem_base + (uint32_t(warp * 32) << 16), w_img, tid);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -328,8 +347,9 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
     const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
     const bool base0 = (tmem_base == 0);
     int n = 0;
-    for (int t = T - 1; t >= 1; --t, ++n) {
-      mbar_wait(sm.bar_in, n & 1);  // dG_t^T staged
+    for (int t = T - 1; t >= 0; --t, ++n) {
+      handoff_wait();  // dG_t^T staged
+      if (t == 0) break;  // the last hand-off only balances the barrier
       tcgen05_fence_after();
       if (elect_one()) {
         const bool pr = prof && blockIdx.x == 0 && n + 1 < kProfSteps;
@@ -435,8 +455,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
       }
       if (do_prof) prof[512 + n * 8 + 2] = clock64();
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sm.bar_in);
+      handoff_arrive();
       if (do_prof) prof[512 + n * 8 + 3] = clock64();
       ++n;
       // ---- off the critical path ----
@@ -472,6 +491,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ w_hh, const __nv_bfloat16* __restri
 
 // ------------------------------------------------------------------------------------------------ host side
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+constexpr size_t kWimgBytes = size_t(4) * 128 * 64 * 4;  // TMEM image of the resident weight operand
 
 static int pick_nv(int B) {
   // smallest batch tile that still fills the machine: per-step latency falls with NV (fewer MUFU ops per SM)
@@ -498,8 +518,8 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
   }
   const size_t tb = size_t(T) * B;
   *reserve = align256(tb * 4 * H * 2) + align256(tb * H * 4);
-  const size_t wf = align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2);
-  const size_t wb = align256(tb * 4 * H * 2) + align256(size_t(4) * H * I * 2);
+  const size_t wf = align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2) + kWimgBytes;
+  const size_t wb = align256(tb * 4 * H * 2) + align256(size_t(4) * H * I * 2) + kWimgBytes;
   *workspace = wf > wb ? wf : wb;
   return CSN_OK;
 }
@@ -507,7 +527,7 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
 static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (bring-up only)
 
 template <int NV, int KSTEPS>
-static int launch_fwd(const float* xp, const float* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
+static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
                       float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
   const size_t smem = size_t(KP / 8) * kLboB + 64 + 128;
   lstm_fwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf);
@@ -516,7 +536,7 @@ static int launch_fwd(const float* xp, const float* w_hh, const float* b_hh, __n
 }
 
 template <int NV, int KSTEPS>
-static int launch_bwd(const float* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
+static int launch_bwd(const uint32_t* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
   const size_t smem = size_t(4 * 128 / 8) * kLboB + 64 + 128;
@@ -544,12 +564,16 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   __nv_bfloat16* g = training ? gates : nullptr;
   float* c = training ? c_out : nullptr;
   __nv_bfloat16* hs = (__nv_bfloat16*)h_seq;
+  uint32_t* w_img = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 4) +
+                                                align256(size_t(4) * H * I * 2));
+  pack_whh_tmem_image_kernel<<<4 * 128 * 64 / 256, 256, 0, s>>>(w_hh, w_img, H, 0);
+  CSN_LAUNCH_CHECK();
   // hidden 128 / 96 / 64 get compile-time K-step counts (predicate-free MMA issue); other sizes take the runtime path
 #define CSN_FWD(KS)                                                                  \
   do {                                                                               \
-    if (nv == 2) return launch_fwd<2, KS>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s); \
-    if (nv == 4) return launch_fwd<4, KS>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s); \
-    return launch_fwd<8, KS>(xp, w_hh, b_hh, hs, g, c, T, B, H, KP, s);              \
+    if (nv == 2) return launch_fwd<2, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, s); \
+    if (nv == 4) return launch_fwd<4, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, s); \
+    return launch_fwd<8, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, s);              \
   } while (0)
   if (KP == 128) CSN_FWD(8);
   if (KP == 96) CSN_FWD(6);
@@ -577,11 +601,15 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
     CSN_CUDA(cudaMemsetAsync(db_hh, 0, size_t(4) * H * 4, s));
   }
   const int nv = pick_nv(B);
+  uint32_t* w_img = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 2) +
+                                                align256(size_t(4) * H * I * 2));
+  pack_whh_tmem_image_kernel<<<4 * 128 * 64 / 256, 256, 0, s>>>(w_hh, w_img, H, 1);
+  CSN_LAUNCH_CHECK();
 #define CSN_BWD(KS)                                                                                                        \
   do {                                                                                                                     \
-    if (nv == 2) CSN_TRY((launch_bwd<2, KS>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));      \
-    else if (nv == 4) CSN_TRY((launch_bwd<4, KS>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s))); \
-    else CSN_TRY((launch_bwd<8, KS>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));              \
+    if (nv == 2) CSN_TRY((launch_bwd<2, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));      \
+    else if (nv == 4) CSN_TRY((launch_bwd<4, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s))); \
+    else CSN_TRY((launch_bwd<8, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));              \
   } while (0)
   if (KP == 128) CSN_BWD(8);
   else if (KP == 96) CSN_BWD(6);
