@@ -34,6 +34,7 @@ __device__ __forceinline__ void handoff_wait() { asm volatile("bar.sync 1, 288;"
 static_assert(kRecThreads == 288, "named-barrier thread count is spelled out in the PTX above");
 constexpr uint32_t kLboB = 256, kSboB = 128;   // 16-row operand: 2 core matrices per k-group
 constexpr int kNslots = 16;                    // MMA N (batch slots per CTA); NV <= 16 of them are live
+constexpr int kBwdAcc = 4;                     // accumulators the backward K-steps rotate over
 constexpr int kProfSteps = 64;                 // bring-up instrumentation: clock64 stamps for the first steps of CTA 0
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -133,7 +134,9 @@ __device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t 
   }
 }
 // Backward: the dG^T operand keeps a FIXED stride of 128 contraction elements per gate (kk16 = 8 g + kg), so every
-// descriptor offset is an immediate; single accumulator dh^T.
+// descriptor offset is an immediate.  The 32 K-steps rotate over kBwdAcc accumulators (summed by the epilogue):
+// with all 128 SMs running, back-to-back MMAs into ONE accumulator measured ~23 cycles each against ~11 when
+// consecutive MMAs target different accumulators (the forward kernel's four gate accumulators).
 template <bool CONST_BASE, int KSTEPS>
 __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_rt) {
   const uint32_t tb = CONST_BASE ? 0u : base;
@@ -144,8 +147,10 @@ __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t 
     for (int kg = 0; kg < 8; ++kg) {
       if (kg < ksteps_gate) {
         const int kk = g * 8 + kg;
+        const int acc = kg % kBwdAcc;
+        const bool first = (g == 0 && kg < kBwdAcc);
         const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
-        umma_f16_ts(tb, tb + kAcol0 + g * kAgate + kg * 8, db, idesc, (g == 0 && kg == 0) ? 0u : 1u);
+        umma_f16_ts(tb + acc * kNslots, tb + kAcol0 + g * kAgate + kg * 8, db, idesc, first ? 0u : 1u);
       }
     }
   }
@@ -430,13 +435,21 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
         mbar_wait(sm.bar_acc, (n - 1) & 1);
         tcgen05_fence_after();
         if (do_prof) prof[512 + n * 8 + 0] = clock64();
-        uint32_t r[NVT];
-        tmem_ld<NVT>(lane_addr, r);
+        // accumulators that received at least one K-step: kg % kBwdAcc for kg < ksteps_gate
+        const int nacc = ksteps_gate < kBwdAcc ? ksteps_gate : kBwdAcc;
+        uint32_t r[kBwdAcc][NVT];
+#pragma unroll
+        for (int a = 0; a < kBwdAcc; ++a)
+          if (a < nacc) tmem_ld<NVT>(lane_addr + a * kNslots, r[a]);
         tmem_ld_wait();
         tcgen05_fence_before();
         if (do_prof) prof[512 + n * 8 + 1] = clock64();
 #pragma unroll
-        for (int j = 0; j < NVT; ++j) dh[j] += __uint_as_float(r[j]);
+        for (int a = 0; a < kBwdAcc; ++a)
+          if (a < nacc) {
+#pragma unroll
+            for (int j = 0; j < NVT; ++j) dh[j] += __uint_as_float(r[a][j]);
+          }
       }
       float dg[4][NVT];
 #pragma unroll
