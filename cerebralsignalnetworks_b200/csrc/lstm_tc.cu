@@ -121,7 +121,7 @@ __device__ __forceinline__ void stage_weights_tmem(uint32_t lane_addr, const uin
 // KSTEPS > 0: K-steps per gate known at compile time (no predicates in the issue sequence); 0: runtime.
 template <bool CONST_BASE, int KSTEPS>
 __device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_rt) {
-  const uint32_t tb = CONST_BASE ? 0u : base;
+  const uint32_t tb = base;  // CONST_BASE: `base` is a kernel-parameter zero, i.e. a UNIFORM value: addresses stay in the uniform datapath
   const int ksteps = KSTEPS ? KSTEPS : ksteps_rt;
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
@@ -139,19 +139,20 @@ __device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t 
 // consecutive MMAs target different accumulators (the forward kernel's four gate accumulators).
 template <bool CONST_BASE, int KSTEPS>
 __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_rt) {
-  const uint32_t tb = CONST_BASE ? 0u : base;
   const int ksteps_gate = KSTEPS ? KSTEPS : ksteps_rt;
-#pragma unroll
+  // Both the A address (256 + 8 kk) and the B descriptor (db0 + 32 kk) are linear in the K-step index kk = 8 g + kg.
+  // They are advanced as RUNNING uniform values in a rolled loop: fully unrolling (as the forward issue does, where
+  // four MMAs share each B descriptor) makes ptxas hoist 32 descriptors + 32 addresses out of the time loop and
+  // spill the uniform register file (MOV.SPILL / R2UR per MMA, ~23 cycles each, measured).
+#pragma unroll 1
   for (int g = 0; g < 4; ++g) {
-#pragma unroll
-    for (int kg = 0; kg < 8; ++kg) {
-      if (kg < ksteps_gate) {
-        const int kk = g * 8 + kg;
-        const int acc = kg % kBwdAcc;
-        const bool first = (g == 0 && kg < kBwdAcc);
-        const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
-        umma_f16_ts(tb + acc * kNslots, tb + kAcol0 + g * kAgate + kg * 8, db, idesc, first ? 0u : 1u);
-      }
+    uint32_t a = base + kAcol0 + g * kAgate;
+    uint64_t db = db0 + uint64_t(g * 8 * ((2 * kLboB) >> 4));
+#pragma unroll 2
+    for (int kg = 0; kg < ksteps_gate; ++kg) {
+      umma_f16_ts(base + (kg % kBwdAcc) * kNslots, a, db, idesc, (g == 0 && kg < kBwdAcc) ? 0u : 1u);
+      a += 8;
+      db += (2 * kLboB) >> 4;
     }
   }
 }
@@ -161,7 +162,7 @@ template <int NV, int KSTEPS>
 __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_img, const float* __restrict__ b_hh,
                    __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
-                   int T, int B, int H, int KP, long long* __restrict__ prof) {
+                   int T, int B, int H, int KP, long long* __restrict__ prof, const uint32_t uz) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const size_t b_bytes = size_t(KP / 8) * kLboB;
   RecSmem sm = carve(smem_raw, b_bytes);
@@ -201,7 +202,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
       tcgen05_fence_after();
       if (elect_one()) {
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 4] = clock64();
-        if (base0) issue_fwd<true, KSTEPS>(0u, db0, idesc, ksteps);
+        if (base0) issue_fwd<true, KSTEPS>(uz, db0, idesc, ksteps);
         else issue_fwd<false, KSTEPS>(tmem_base, db0, idesc, ksteps);
         umma_commit(sm.bar_acc);
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 5] = clock64();
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kRecThreads, 1)
 lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
                    float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP,
-                   long long* __restrict__ prof) {
+                   long long* __restrict__ prof, const uint32_t uz) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const size_t b_bytes = size_t(4 * 128 / 8) * kLboB;  // gate stride fixed at 128 contraction elements
   RecSmem sm = carve(smem_raw, b_bytes);
@@ -359,7 +360,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
       if (elect_one()) {
         const bool pr = prof && blockIdx.x == 0 && n + 1 < kProfSteps;
         if (pr) prof[512 + (n + 1) * 8 + 4] = clock64();
-        if (base0) issue_bwd<true, KSTEPS>(0u, db0, idesc, ksteps_gate);
+        if (base0) issue_bwd<true, KSTEPS>(uz, db0, idesc, ksteps_gate);
         else issue_bwd<false, KSTEPS>(tmem_base, db0, idesc, ksteps_gate);
         umma_commit(sm.bar_acc);
         if (pr) prof[512 + (n + 1) * 8 + 5] = clock64();
@@ -543,7 +544,7 @@ template <int NV, int KSTEPS>
 static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
                       float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
   const size_t smem = size_t(KP / 8) * kLboB + 64 + 128;
-  lstm_fwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf);
+  lstm_fwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf, 0u);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
@@ -553,7 +554,7 @@ static int launch_bwd(const uint32_t* w_hh, const __nv_bfloat16* gates, const fl
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
   const size_t smem = size_t(4 * 128 / 8) * kLboB + 64 + 128;
-  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf);
+  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf, 0u);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
@@ -735,11 +736,11 @@ __global__ void __launch_bounds__(128, 1) dbg_umma_tile_kernel(const __nv_bfloat
 // ---- tcgen05.mma issue / completion cost microbenchmark (bring-up): one CTA, 32 unrolled MMAs per repetition ----
 // Addresses are immediates and the issue is elect-guarded, like the recurrence kernels.  NACC accumulators are used
 // round-robin (NACC = 1: every MMA accumulates into the same D).
-template <int NACC, bool TS>
+template <int NACC, bool TS, int BREUSE = 1>
 __device__ __forceinline__ void bench_issue32(uint64_t da0, uint64_t db0, uint32_t idesc, uint32_t lbo_a16, uint32_t lbo_b16) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    const int kk = i & 7;
+    const int kk = (i / BREUSE) & 7;  // BREUSE consecutive MMAs share one B operand
     const uint64_t db = db0 + uint64_t(kk) * (2 * lbo_b16);
     if (TS) umma_f16_ts((i % NACC) * 16, 256 + kk * 8 + (i >> 3) * 64, db, idesc, 1u);
     else umma_f16((i % NACC) * 16, da0 + uint64_t(kk) * (2 * lbo_a16), db, idesc, 1u);
@@ -783,7 +784,9 @@ __global__ void __launch_bounds__(128, 1) dbg_umma_bench_kernel(long long* __res
       long long t0 = 0, t1 = 0;
       if (elect_one()) {
         t0 = clock64();
-        if (a_mode == 2) {
+        if (a_mode == 3) {  // TMEM A, four consecutive MMAs share one B descriptor (the forward kernel's pattern)
+          bench_issue32<4, true, 4>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
+        } else if (a_mode == 2) {
           if (n_acc == 1) bench_issue32<1, true>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
           else if (n_acc == 4) bench_issue32<4, true>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
           else bench_issue32<8, true>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
@@ -800,12 +803,12 @@ __global__ void __launch_bounds__(128, 1) dbg_umma_bench_kernel(long long* __res
       phase ^= 1;
       const long long t2 = clock64();
       t0 = __shfl_sync(0xffffffffu, t0, 0) | 0;  // elected lane is lane 0 of a converged warp
-      if (tid == 0) {
+      if (tid == 0 && blockIdx.x == 0) {
         out[rep * 2 + 0] = t1 - t0;
         out[rep * 2 + 1] = t2 - t0;
       }
     }
-  } else if (tid == 0 && tmem_base != 0) {
+  } else if (tid == 0 && tmem_base != 0 && blockIdx.x == 0) {
     out[0] = -1;
   }
   tcgen05_fence_before();
@@ -836,11 +839,12 @@ extern "C" int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, 
 }
 
 extern "C" int csn_dbg_umma_bench(long long* out, int M, int N, int n_acc, int a_mode, int reps, void* stream) {
+  static const int grid = [] { const char* e = getenv("CSN_UMMA_BENCH_GRID"); return e ? atoi(e) : 1; }();
   CSN_REQUIRE(out && (M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && (n_acc == 1 || n_acc == 4 || n_acc == 8) &&
                   reps >= 1 && reps <= 16, "csn_dbg_umma_bench: bad arguments");
   const size_t smem = 128 * 128 * 2 + 256 * 128 * 2 + 256;
   CSN_CUDA(cudaFuncSetAttribute(dbg_umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dbg_umma_bench_kernel<<<1, 128, smem, as_stream(stream)>>>(out, M, N, n_acc, a_mode, reps);
+  dbg_umma_bench_kernel<<<grid, 128, smem, as_stream(stream)>>>(out, M, N, n_acc, a_mode, reps);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
