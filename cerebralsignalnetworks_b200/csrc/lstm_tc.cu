@@ -17,6 +17,8 @@
 //
 // The serial chain (T steps) cannot be parallelised; what this design optimises is the per-step latency:
 // no HBM round trip, no grid-wide sync, one mbarrier hand-off in each direction per step.
+#include <type_traits>
+
 #include "tc.cuh"
 
 namespace csn {
@@ -26,12 +28,14 @@ using namespace tc;
 // warps 0-7: epilogue -- warp w owns TMEM lane quadrant w % 4 (32 hidden units) and half (w / 4) of the CTA's batch
 // slots, so the per-step gate math / reserve traffic of a unit is split over two warps; warp 8: MMA issuer.
 constexpr int kEpiWarps = 8, kIssuerWarp = 8;
-constexpr int kRecThreads = (kEpiWarps + 1) * 32;
-// epilogue -> issuer hand-off: hardware named barrier 1 over all 288 threads (the 256 epilogue threads ARRIVE without
-// blocking, the issuer warp SYNCs); ~2x lower latency than an mbarrier round trip, measured on the step stamps.
-__device__ __forceinline__ void handoff_arrive() { asm volatile("bar.arrive 1, 288;" ::: "memory"); }
-__device__ __forceinline__ void handoff_wait() { asm volatile("bar.sync 1, 288;" ::: "memory"); }
-static_assert(kRecThreads == 288, "named-barrier thread count is spelled out in the PTX above");
+constexpr int kRecThreads = (kEpiWarps + 1) * 32;     // forward: one issuer warp
+constexpr int kRecThreadsBwd = (kEpiWarps + 2) * 32;  // backward: two issuer warps (see issue_bwd)
+// epilogue -> issuer hand-off: hardware named barrier 1 over all threads (the 256 epilogue threads ARRIVE without
+// blocking, the issuer warp(s) SYNC); ~2x lower latency than an mbarrier round trip, measured on the step stamps.
+template <int NTHREADS>
+__device__ __forceinline__ void handoff_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(NTHREADS) : "memory"); }
+template <int NTHREADS>
+__device__ __forceinline__ void handoff_wait() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 constexpr uint32_t kLboB = 256, kSboB = 128;   // 16-row operand: 2 core matrices per k-group
 constexpr int kNslots = 16;                    // MMA N (batch slots per CTA); NV <= 16 of them are live
 constexpr int kBwdAcc = 4;                     // accumulators the backward K-steps rotate over
@@ -137,22 +141,27 @@ __device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t 
 // descriptor offset is an immediate.  The 32 K-steps rotate over kBwdAcc accumulators (summed by the epilogue):
 // with all 128 SMs running, back-to-back MMAs into ONE accumulator measured ~23 cycles each against ~11 when
 // consecutive MMAs target different accumulators (the forward kernel's four gate accumulators).
-template <bool CONST_BASE, int KSTEPS>
+// HALF selects the issuer warp: warp 0 issues gates 0-1 into accumulators {0,1}, warp 1 gates 2-3 into {2,3}.
+// Everything is unrolled to immediates so each warp's ~50 operands (16 B descriptors, 16 A addresses, 2 accumulators)
+// stay in its own uniform register file: one warp issuing all 32 K-steps needs ~100 uniform registers and ptxas
+// spills them (MOV.SPILL / R2UR per MMA, ~23 cycles each); a rolled loop with running operands is worse still
+// (~37 cycles per MMA: UIADD3 -> UTCHMMA dependency latency).  Measured with scripts/prof_lstm_steps.py.
+template <bool CONST_BASE, int KSTEPS, int HALF>
 __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_rt) {
+  const uint32_t tb = base;
   const int ksteps_gate = KSTEPS ? KSTEPS : ksteps_rt;
-  // Both the A address (256 + 8 kk) and the B descriptor (db0 + 32 kk) are linear in the K-step index kk = 8 g + kg.
-  // They are advanced as RUNNING uniform values in a rolled loop: fully unrolling (as the forward issue does, where
-  // four MMAs share each B descriptor) makes ptxas hoist 32 descriptors + 32 addresses out of the time loop and
-  // spill the uniform register file (MOV.SPILL / R2UR per MMA, ~23 cycles each, measured).
-#pragma unroll 1
-  for (int g = 0; g < 4; ++g) {
-    uint32_t a = base + kAcol0 + g * kAgate;
-    uint64_t db = db0 + uint64_t(g * 8 * ((2 * kLboB) >> 4));
-#pragma unroll 2
-    for (int kg = 0; kg < ksteps_gate; ++kg) {
-      umma_f16_ts(base + (kg % kBwdAcc) * kNslots, a, db, idesc, (g == 0 && kg < kBwdAcc) ? 0u : 1u);
-      a += 8;
-      db += (2 * kLboB) >> 4;
+#pragma unroll
+  for (int gg = 0; gg < 2; ++gg) {
+    const int g = HALF * 2 + gg;
+#pragma unroll
+    for (int kg = 0; kg < 8; ++kg) {
+      if (kg < ksteps_gate) {
+        const int kk = g * 8 + kg;
+        const int acc = HALF * 2 + (kg & 1);
+        const bool first = (gg == 0 && kg < 2);
+        const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
+        umma_f16_ts(tb + acc * kNslots, tb + kAcol0 + g * kAgate + kg * 8, db, idesc, first ? 0u : 1u);
+      }
     }
   }
 }
@@ -197,7 +206,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
     const bool base0 = (tmem_base == 0);  // a 512-column allocation owns the whole TMEM: constant addresses
     for (int t = 1; t <= T; ++t) {
-      handoff_wait();  // h_{t-1} is in shared memory (and TMEM has been drained)
+      handoff_wait<kRecThreads>();  // h_{t-1} is in shared memory (and TMEM has been drained)
       if (t == T) break;  // the last hand-off only balances the barrier
       tcgen05_fence_after();
       if (elect_one()) {
@@ -286,7 +295,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
       // publish h_t to the async proxy and hand over: one arrival per warp
       if (do_prof) prof[t * 8 + 2] = clock64();
       fence_proxy_async_smem();
-      handoff_arrive();
+      handoff_arrive<kRecThreads>();
       if (do_prof) prof[t * 8 + 3] = clock64();
       // ---- off the critical path: stream h_t and the BPTT reserve to HBM while the next MMAs run ----
 #pragma unroll
@@ -318,7 +327,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
 // ------------------------------------------------------------------------------------------------ backward
 // dh_{t-1}^T[k, b] = sum_{kk = g*KP + u} W_hh[g*H + u][k] * dG_t[b, kk]: M = hidden unit k (TMEM lane), K = 4*KP.
 template <int NV, int KSTEPS>
-__global__ void __launch_bounds__(kRecThreads, 1)
+__global__ void __launch_bounds__(kRecThreadsBwd, 1)
 lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
                    float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP,
@@ -330,10 +339,10 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
   const int b0 = blockIdx.x * NV;
   const int ksteps_gate = KP / 16;
 
-  for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
+  for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreadsBwd) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
     mbar_init(sm.bar_in, kEpiWarps);
-    mbar_init(sm.bar_acc, 1);
+    mbar_init(sm.bar_acc, 2);  // one tcgen05.commit per issuer warp
     fence_mbar_init();
   }
   if (warp == kIssuerWarp) tmem_alloc(sm.tmem_slot, kTmemCols);
@@ -348,25 +357,31 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
   __syncthreads();
   tcgen05_fence_after();
 
-  if (warp == kIssuerWarp) {
+  if (warp >= kIssuerWarp) {
     constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
     const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
     const bool base0 = (tmem_base == 0);
-    int n = 0;
-    for (int t = T - 1; t >= 0; --t, ++n) {
-      handoff_wait();  // dG_t^T staged
-      if (t == 0) break;  // the last hand-off only balances the barrier
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const bool pr = prof && blockIdx.x == 0 && n + 1 < kProfSteps;
-        if (pr) prof[512 + (n + 1) * 8 + 4] = clock64();
-        if (base0) issue_bwd<true, KSTEPS>(uz, db0, idesc, ksteps_gate);
-        else issue_bwd<false, KSTEPS>(tmem_base, db0, idesc, ksteps_gate);
-        umma_commit(sm.bar_acc);
-        if (pr) prof[512 + (n + 1) * 8 + 5] = clock64();
+    // one time loop PER issuer warp: the hoisted operand sets of the two halves must not be live together
+    auto issue_loop = [&](auto half_tag) {
+      constexpr int HALF = decltype(half_tag)::value;
+      int n = 0;
+      for (int t = T - 1; t >= 0; --t, ++n) {
+        handoff_wait<kRecThreadsBwd>();  // dG_t^T staged
+        if (t == 0) break;  // the last hand-off only balances the barrier
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const bool pr = prof && blockIdx.x == 0 && n + 1 < kProfSteps && HALF == 0;
+          if (pr) prof[512 + (n + 1) * 8 + 4] = clock64();
+          if (base0) issue_bwd<true, KSTEPS, HALF>(uz, db0, idesc, ksteps_gate);
+          else issue_bwd<false, KSTEPS, HALF>(tmem_base, db0, idesc, ksteps_gate);
+          umma_commit(sm.bar_acc);
+          if (pr) prof[512 + (n + 1) * 8 + 5] = clock64();
+        }
+        __syncwarp();
       }
-      __syncwarp();
-    }
+    };
+    if (warp == kIssuerWarp) issue_loop(std::integral_constant<int, 0>{});
+    else issue_loop(std::integral_constant<int, 1>{});
   } else {
     constexpr int NVT = NV / 2;  // cells per epilogue thread
     const int u = tid & 127;
@@ -436,18 +451,17 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
         mbar_wait(sm.bar_acc, (n - 1) & 1);
         tcgen05_fence_after();
         if (do_prof) prof[512 + n * 8 + 0] = clock64();
-        // accumulators that received at least one K-step: kg % kBwdAcc for kg < ksteps_gate
-        const int nacc = ksteps_gate < kBwdAcc ? ksteps_gate : kBwdAcc;
+        // accumulators {0,1} belong to issuer warp 0, {2,3} to issuer warp 1; the odd ones exist iff ksteps_gate > 1
         uint32_t r[kBwdAcc][NVT];
 #pragma unroll
         for (int a = 0; a < kBwdAcc; ++a)
-          if (a < nacc) tmem_ld<NVT>(lane_addr + a * kNslots, r[a]);
+          if ((a & 1) < ksteps_gate) tmem_ld<NVT>(lane_addr + a * kNslots, r[a]);
         tmem_ld_wait();
         tcgen05_fence_before();
         if (do_prof) prof[512 + n * 8 + 1] = clock64();
 #pragma unroll
         for (int a = 0; a < kBwdAcc; ++a)
-          if (a < nacc) {
+          if ((a & 1) < ksteps_gate) {
 #pragma unroll
             for (int j = 0; j < NVT; ++j) dh[j] += __uint_as_float(r[a][j]);
           }
@@ -469,7 +483,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
       }
       if (do_prof) prof[512 + n * 8 + 2] = clock64();
       fence_proxy_async_smem();
-      handoff_arrive();
+      handoff_arrive<kRecThreadsBwd>();
       if (do_prof) prof[512 + n * 8 + 3] = clock64();
       ++n;
       // ---- off the critical path ----
@@ -554,7 +568,7 @@ static int launch_bwd(const uint32_t* w_hh, const __nv_bfloat16* gates, const fl
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
   const size_t smem = size_t(4 * 128 / 8) * kLboB + 64 + 128;
-  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf, 0u);
+  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreadsBwd, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf, 0u);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
