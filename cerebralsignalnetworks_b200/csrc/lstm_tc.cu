@@ -178,6 +178,13 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * NV;
   const int ksteps = KP / 16;
+  const bool phase_prof = prof && blockIdx.x == 0 && tid == 0;
+  if (phase_prof) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    prof[1024 + 0] = (long long)gt;
+    prof[1024 + 1] = clock64();
+  }
 
   for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
@@ -191,12 +198,14 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
+  if (phase_prof) prof[1024 + 2] = clock64();
   // W_hh resident in TENSOR MEMORY for the whole sequence: lane = hidden unit u (row of each gate block)
   if (warp < 4) stage_weights_tmem(tmem_base + (uint32_t(warp * 32) << 16), w_img, tid);
   constexpr int NVT = NV / 2;  // cells per epilogue thread
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  if (phase_prof) prof[1024 + 3] = clock64();
 
   if (warp == kIssuerWarp) {
     // ================= MMA issuer: whole warp converged, one ELECTED lane issues =================
@@ -224,9 +233,13 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     const int jb = (tid >> 7) * NVT;  // first batch slot of this thread
     const bool active = u < H;
     const uint32_t lane_addr = tmem_base + (uint32_t((warp & 3) * 32) << 16) + jb;
-    // Xp prefetch: three rotating register sets, the time loop is unrolled by 3 so the rotation is a compile-time
-    // renaming (a register copy of a pending load would stall on it).  Loads run two steps (~2 k cycles) ahead.
-    float bias[4], c[NVT], xbuf[3][4][NVT];
+    // Xp prefetch: cp.async (LDGSTS) into a 4-deep per-thread shared-memory ring, three steps ahead.  Register
+    // prefetch was tried first: the pending loads share the six scoreboard slots with the per-step tcgen05.ld / MUFU
+    // work, and every third (unrolled) step stalled ~1 k cycles on a slot that also tracked in-flight loads.
+    // cp.async groups are tracked separately, and every thread only ever reads back its own bytes (no block sync).
+    float bias[4], c[NVT];
+    float* xring = reinterpret_cast<float*>(sm.opb + b_bytes + 64);  // [4 stages][4*NVT][256 threads]
+    constexpr int kRingStage = 4 * NVT * (kEpiWarps * 32);
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = active ? b_hh[g * H + u] : 0.f;
 #pragma unroll
@@ -236,34 +249,39 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     for (int j = 0; j < NVT; ++j) valid[j] = active && (b0 + jb + j < B);
     const size_t step_cells = size_t(B) * H;
 
-    // NOTE: nothing may CONSUME a prefetched value at issue time (a dependent instruction would stall this in-order
-    // warp for the whole memory latency): plain predicated loads into zero-initialised registers.
-    auto load_xp = [&](int t, float (&dst)[4][NVT]) {
+    auto prefetch_xp = [&](int t) {  // one cp.async group per step (zero-filled when out of range)
+      float* dst = xring + (t & 3) * kRingStage + tid;
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
-        const float* row = xp + (size_t(t) * B + (b0 + jb + j)) * 4 * H + u;
+        const bool ok = valid[j] && t < T;
+        const float* row = ok ? xp + (size_t(t) * B + (b0 + jb + j)) * 4 * H + u : xp;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          dst[g][j] = 0.f;
-          if (valid[j] && t < T) dst[g][j] = __ldcs(row + g * H);
+          const uint32_t d = smem_u32(dst + (g * NVT + j) * (kEpiWarps * 32));
+          const int nbytes = ok ? 4 : 0;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(row + g * H), "r"(nbytes) : "memory");
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    load_xp(0, xbuf[0]);
-    load_xp(1, xbuf[1]);
+    prefetch_xp(0);
+    prefetch_xp(1);
+    prefetch_xp(2);
 
-    for (int t0 = 0; t0 < T; t0 += 3) {
-#pragma unroll
-     for (int ph = 0; ph < 3; ++ph) {
-      const int t = t0 + ph;
-      if (t >= T) break;
-      load_xp(t + 2, xbuf[(ph + 2) % 3]);  // in flight for two steps
+    for (int t = 0; t < T; ++t) {
+     {
+      prefetch_xp(t + 3);
+      asm volatile("cp.async.wait_group 3;" ::: "memory");  // the group of step t has landed
       float pre[4][NVT];
+      {
+        const float* src = xring + (t & 3) * kRingStage + tid;
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+        for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int j = 0; j < NVT; ++j) pre[g][j] = xbuf[ph][g][j] + bias[g];
+          for (int j = 0; j < NVT; ++j) pre[g][j] = src[(g * NVT + j) * (kEpiWarps * 32)] + bias[g];
+      }
       const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && t < kProfSteps;
+      if (phase_prof && (t == 1 || t == 8 || t == 64 || t == 200 || t == 400)) prof[1024 + 6 + (t == 1 ? 0 : t == 8 ? 1 : t == 64 ? 2 : t == 200 ? 3 : 4)] = clock64();
       if (t > 0) {
         if (do_prof) prof[t * 8 + 6] = clock64();
         mbar_wait(sm.bar_acc, (t - 1) & 1);
@@ -314,6 +332,12 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
         }
       }
      }
+    }
+    if (phase_prof) {
+      unsigned long long gt;
+      prof[1024 + 4] = clock64();
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      prof[1024 + 5] = (long long)gt;
     }
   }
   tcgen05_fence_before();
@@ -557,7 +581,12 @@ static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (
 template <int NV, int KSTEPS>
 static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
                       float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
-  const size_t smem = size_t(KP / 8) * kLboB + 64 + 128;
+  const size_t smem = size_t(KP / 8) * kLboB + 64 + size_t(4) * 4 * (NV / 2) * (kEpiWarps * 32) * 4 + 128;  // + Xp ring
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    CSN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<NV, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   lstm_fwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf, 0u);
   CSN_LAUNCH_CHECK();
   return CSN_OK;

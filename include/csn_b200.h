@@ -142,7 +142,7 @@ int csn_adam_step_graph(float* params, const float* grads, float* exp_avg, float
  * the recurrence kernel uses; a_mn_major / b_mn_major exercise the MN-major descriptors. */
 int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, int K, int a_mn_major, int b_mn_major, void* stream);
 /* a_mn_major = 2 stages A in tensor memory instead (the TS form the recurrence uses for the resident W_hh).
- * csn_dbg_lstm_profile_buffer: device buffer of >= 2*64*8 int64 that receives clock64 stamps of the first 64 forward
+ * csn_dbg_lstm_profile_buffer: device buffer of >= 2*64*8 + 16 int64 that receives clock64 stamps of the first 64 forward
  * ([0,512)) and backward ([512,1024)) recurrence steps of CTA 0 (NULL switches the stamps off). */
 int csn_dbg_lstm_profile_buffer(long long* buf);
 /* tcgen05.mma issue/completion cost microbenchmark: out[2*rep] = issue cycles, out[2*rep+1] = cycles until commit arrives */

@@ -13,7 +13,7 @@ k = 1.0 / H ** 0.5
 w = [((torch.rand(4 * H, I) * 2 - 1) * k).cuda(), ((torch.rand(4 * H, H) * 2 - 1) * k).cuda(),
      ((torch.rand(4 * H) * 2 - 1) * k).cuda(), ((torch.rand(4 * H) * 2 - 1) * k).cuda()]
 x = torch.randn(T, B, I).cuda().bfloat16()
-buf = torch.zeros(2 * 64 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(2 * 64 * 8 + 16, dtype=torch.int64, device="cuda")
 grads = tuple(torch.empty_like(t) for t in w)
 dh = torch.randn(B, H).cuda()
 def run():
@@ -25,7 +25,15 @@ _lib.call("csn_dbg_lstm_profile_buffer", ctypes.c_void_p(buf.data_ptr()))
 run()
 torch.cuda.synchronize()
 _lib.call("csn_dbg_lstm_profile_buffer", None)
-for name, p in (("forward", buf[:512].view(64, 8).cpu()), ("backward", buf[512:].view(64, 8).cpu())):
+ph = buf[1024:1040].cpu()
+print("forward kernel phases (CTA 0): alloc %d cyc, weight staging %d cyc, time loop %d cyc; wall %d ns => %.0f MHz" % (
+    int(ph[2] - ph[1]), int(ph[3] - ph[2]), int(ph[4] - ph[3]), int(ph[5] - ph[0]), 1e3 * float(ph[4] - ph[1]) / max(1.0, float(ph[5] - ph[0]))))
+print("   cycles since kernel start at t=1,8,64,200,400:", [int(ph[6 + i] - ph[1]) for i in range(5)], "loop end:", int(ph[4] - ph[1]))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+h, r, ws = ops.lstm_layer_fwd(x, *w, torch.bfloat16, True)
+torch.cuda.synchronize(); e0.record(); h, r, ws = ops.lstm_layer_fwd(x, *w, torch.bfloat16, True); e1.record(); torch.cuda.synchronize()
+print("lstm_layer_fwd (cast + pack + GEMM + recurrence) event time: %.1f us" % (1e3 * e0.elapsed_time(e1)))
+for name, p in (("forward", buf[:512].view(64, 8).cpu()), ("backward", buf[512:1024].view(64, 8).cpu())):
     print(name, "B =", B)
     print(" t | period | accwait->ld | ld->math | fence+arrive | arrive->issuer wake | issue+commit | commit->epi wake")
     rows = []
@@ -38,4 +46,6 @@ for name, p in (("forward", buf[:512].view(64, 8).cpu()), ("backward", buf[512:]
         rows.append((period, a, b, c, d, e, f, w, st))
         if t < 6:
             print(f"{t:3d} | {period:6d} | {a:6d} | {b:6d} | {c:6d} | {d:6d} | {e:6d} | {f:6d}")
+    print("periods t=3..39:", [r[0] for r in rows])
+    print("wait-on-acc   :", [r[7] for r in rows])
     print("median", [int(statistics.median(r[i] for r in rows)) for i in range(9)], "(last two: time actually spent waiting on bar_acc, off-path stores)")
