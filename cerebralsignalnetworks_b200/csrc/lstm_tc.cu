@@ -247,20 +247,31 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     bool valid[NVT];
 #pragma unroll
     for (int j = 0; j < NVT; ++j) valid[j] = active && (b0 + jb + j < B);
+    // running pointers (advanced by one timestep per iteration): no 64-bit index arithmetic inside the loop
     const size_t step_cells = size_t(B) * H;
-
+    const float* xp_pf[NVT];          // Xp row of the step being prefetched
+    __nv_bfloat16* h_ptr[NVT];        // h_seq[t][b][u]
+    uint2* g_ptr[NVT];                // reserve gates [t][b][u][i,f,g,o] bf16 (one 8-byte store per cell)
+    float* c_ptr[NVT];                // reserve cell state [t][b][u]
+#pragma unroll
+    for (int j = 0; j < NVT; ++j) {
+      const size_t row = size_t(b0 + jb + j);
+      xp_pf[j] = xp + (valid[j] ? row * 4 * H + u : 0);
+      h_ptr[j] = h_seq + (valid[j] ? row * H + u : 0);
+      g_ptr[j] = reinterpret_cast<uint2*>(gates_out) + (valid[j] ? row * H + u : 0);
+      c_ptr[j] = c_out + (valid[j] ? row * H + u : 0);
+    }
+    const uint32_t ring_base = smem_u32(xring + tid);
     auto prefetch_xp = [&](int t) {  // one cp.async group per step (zero-filled when out of range)
-      float* dst = xring + (t & 3) * kRingStage + tid;
+      const uint32_t dst = ring_base + uint32_t((t & 3) * kRingStage * 4);
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
-        const bool ok = valid[j] && t < T;
-        const float* row = ok ? xp + (size_t(t) * B + (b0 + jb + j)) * 4 * H + u : xp;
+        const int nbytes = (valid[j] && t < T) ? 4 : 0;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t d = smem_u32(dst + (g * NVT + j) * (kEpiWarps * 32));
-          const int nbytes = ok ? 4 : 0;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(row + g * H), "r"(nbytes) : "memory");
-        }
+        for (int g = 0; g < 4; ++g)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                       ::"r"(dst + uint32_t((g * NVT + j) * (kEpiWarps * 32) * 4)), "l"(xp_pf[j] + g * H), "r"(nbytes) : "memory");
+        xp_pf[j] += size_t(B) * 4 * H;
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -319,17 +330,19 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
         if (valid[j]) {
-          const size_t cell = size_t(t) * step_cells + size_t(b0 + jb + j) * H + u;
-          h_seq[cell] = hb[j];
+          *h_ptr[j] = hb[j];
           if (gates_out) {
-            __nv_bfloat16* gr = gates_out + (size_t(t) * B + (b0 + jb + j)) * 4 * H + u;
-            gr[0] = __float2bfloat16_rn(gi[j]);
-            gr[H] = __float2bfloat16_rn(gf[j]);
-            gr[2 * H] = __float2bfloat16_rn(gg[j]);
-            gr[3 * H] = __float2bfloat16_rn(go[j]);
-            c_out[cell] = c[j];
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(gi[j], gf[j]), hi = __floats2bfloat162_rn(gg[j], go[j]);
+            uint2 packed;
+            packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *g_ptr[j] = packed;
+            *c_ptr[j] = c[j];
           }
         }
+        h_ptr[j] += step_cells;
+        g_ptr[j] += step_cells;
+        c_ptr[j] += step_cells;
       }
      }
     }
@@ -419,55 +432,79 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
 #pragma unroll
     for (int j = 0; j < NVT; ++j) valid[j] = active && (b0 + jb + j < B);
 
-    // Prefetch record of one step, kept RAW: no conversion / addition may consume a loaded value at issue time (a
-    // dependent instruction would stall this in-order warp for the whole memory latency); decoded two steps later.
-    struct StepIn {
-      unsigned short i[NVT], f[NVT], g[NVT], o[NVT];
-      float c[NVT], cp[NVT], dhs[NVT], dhl[NVT];
+    // Per-step inputs (gate activations, c_t, c_{t-1}, upstream dh) are prefetched with cp.async into a 4-deep
+    // per-thread shared-memory ring three steps ahead (see the forward kernel); slots: [0,1] gates (8 B), [2] c_t,
+    // [3] c_{t-1}, [4] d_hseq, [5] d_hlast.  Every thread reads back only its own bytes.
+    constexpr int kSlots = 6;
+    float* ring = reinterpret_cast<float*>(sm.opb + b_bytes + 64);  // [4 stages][kSlots*NVT][256 threads]
+    constexpr int kRingStage = kSlots * NVT * (kEpiWarps * 32);
+    const uint32_t ring_base = smem_u32(ring + tid);
+    const size_t step_cells = size_t(B) * H;
+    const uint2* g_pf[NVT];     // reserve gates of the step being prefetched
+    const float* c_pf[NVT];     // c_t of the step being prefetched
+    const float* dhs_pf[NVT];   // d_hseq of the step being prefetched
+    __nv_bfloat16* dg_ptr[NVT]; // dG[t][b][.] output row
+#pragma unroll
+    for (int j = 0; j < NVT; ++j) {
+      const size_t row = size_t(b0 + jb + j);
+      const size_t cell_last = size_t(T - 1) * step_cells + row * H + u;
+      g_pf[j] = reinterpret_cast<const uint2*>(gates) + (valid[j] ? cell_last : 0);
+      c_pf[j] = c_seq + (valid[j] ? cell_last : 0);
+      dhs_pf[j] = d_hseq ? d_hseq + (valid[j] ? cell_last : 0) : nullptr;
+      dg_ptr[j] = dG + (valid[j] ? (size_t(T - 1) * B + row) * 4 * H + u : 0);
+    }
+    auto cp4 = [](uint32_t dst, const void* src, int nbytes) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
     };
-    auto load_step = [&](int t, StepIn& s) {
-      const unsigned short* graw = reinterpret_cast<const unsigned short*>(gates);
+    auto prefetch = [&](int t) {  // one cp.async group per step; zero fill when out of range
+      const uint32_t dst = ring_base + uint32_t((t & 3) * kRingStage * 4);
+      constexpr uint32_t kSlotBytes = (kEpiWarps * 32) * 4;
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
-        const bool ok = valid[j] && (t >= 0);
-        const size_t cell = (size_t(t < 0 ? 0 : t) * B + (b0 + jb + j)) * H + u;
-        const unsigned short* gr = graw + (size_t(t < 0 ? 0 : t) * B + (b0 + jb + j)) * 4 * H + u;
-        s.i[j] = 0; s.f[j] = 0; s.g[j] = 0; s.o[j] = 0;
-        s.c[j] = 0.f; s.cp[j] = 0.f; s.dhs[j] = 0.f; s.dhl[j] = 0.f;
-        if (ok) {
-          s.i[j] = gr[0];
-          s.f[j] = gr[H];
-          s.g[j] = gr[2 * H];
-          s.o[j] = gr[3 * H];
-          s.c[j] = c_seq[cell];
-          if (t > 0) s.cp[j] = c_seq[cell - size_t(B) * H];
-          if (d_hseq) s.dhs[j] = d_hseq[cell];
-          if (d_hlast && t == T - 1) s.dhl[j] = d_hlast[size_t(b0 + jb + j) * H + u];
+        const bool ok = valid[j] && t >= 0;
+        const uint32_t d = dst + uint32_t(j * kSlots) * kSlotBytes;
+        const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(g_pf[j]);
+        cp4(d + 0 * kSlotBytes, gsrc, ok ? 4 : 0);
+        cp4(d + 1 * kSlotBytes, gsrc + 1, ok ? 4 : 0);
+        cp4(d + 2 * kSlotBytes, c_pf[j], ok ? 4 : 0);
+        cp4(d + 3 * kSlotBytes, c_pf[j] - step_cells, (ok && t > 0) ? 4 : 0);
+        cp4(d + 4 * kSlotBytes, dhs_pf[j] ? (const void*)dhs_pf[j] : (const void*)c_pf[j], (ok && dhs_pf[j]) ? 4 : 0);
+        cp4(d + 5 * kSlotBytes, d_hlast ? (const void*)(d_hlast + size_t(b0 + jb + j) * H + u) : (const void*)c_pf[j],
+            (ok && d_hlast && t == T - 1) ? 4 : 0);
+        if (t > 0) {  // keep the pointers inside the allocation
+          g_pf[j] -= step_cells;
+          c_pf[j] -= step_cells;
+          if (dhs_pf[j]) dhs_pf[j] -= step_cells;
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto bf = [](unsigned short r) { return __uint_as_float(uint32_t(r) << 16); };
-    StepIn sbuf[3];  // rotating prefetch sets, loop unrolled by 3 (see the forward kernel)
-    load_step(T - 1, sbuf[0]);
-    load_step(T - 2, sbuf[1]);
+    auto bf_lo = [](uint32_t w) { return __uint_as_float(w << 16); };
+    auto bf_hi = [](uint32_t w) { return __uint_as_float(w & 0xffff0000u); };
+    prefetch(T - 1);
+    prefetch(T - 2);
+    prefetch(T - 3);
     int n = 0;
-    for (int t0 = T - 1; t0 >= 0; t0 -= 3) {
-#pragma unroll
-     for (int ph = 0; ph < 3; ++ph) {
-      const int t = t0 - ph;
-      if (t < 0) break;
-      load_step(t - 2, sbuf[(ph + 2) % 3]);
-      StepIn& raw = sbuf[ph];
+    for (int t = T - 1; t >= 0; --t) {
+     {
+      prefetch(t - 3);
+      asm volatile("cp.async.wait_group 3;" ::: "memory");  // the group of step t has landed
       struct { float i[NVT], f[NVT], g[NVT], o[NVT], c[NVT], cp[NVT]; } cur;
       float dh[NVT], tcn[NVT], pref[NVT];
       // everything that does not need dh is done before the wait
+      {
+        const float* src = ring + (t & 3) * kRingStage + tid;
 #pragma unroll
-      for (int j = 0; j < NVT; ++j) {
-        cur.i[j] = bf(raw.i[j]); cur.f[j] = bf(raw.f[j]); cur.g[j] = bf(raw.g[j]); cur.o[j] = bf(raw.o[j]);
-        cur.c[j] = raw.c[j]; cur.cp[j] = raw.cp[j];
-        dh[j] = raw.dhs[j] + raw.dhl[j];
-        tcn[j] = tanh_fast(cur.c[j]);
-        pref[j] = cur.o[j] * (1.f - tcn[j] * tcn[j]);
+        for (int j = 0; j < NVT; ++j) {
+          const float* sj = src + j * kSlots * (kEpiWarps * 32);
+          const uint32_t w0 = __float_as_uint(sj[0]), w1 = __float_as_uint(sj[(kEpiWarps * 32)]);
+          cur.i[j] = bf_lo(w0); cur.f[j] = bf_hi(w0); cur.g[j] = bf_lo(w1); cur.o[j] = bf_hi(w1);
+          cur.c[j] = sj[2 * (kEpiWarps * 32)];
+          cur.cp[j] = sj[3 * (kEpiWarps * 32)];
+          dh[j] = sj[4 * (kEpiWarps * 32)] + sj[5 * (kEpiWarps * 32)];
+          tcn[j] = tanh_fast(cur.c[j]);
+          pref[j] = cur.o[j] * (1.f - tcn[j] * tcn[j]);
+        }
       }
       const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps;
       if (t < T - 1) {
@@ -514,12 +551,12 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
         if (valid[j]) {
-          __nv_bfloat16* gr = dG + (size_t(t) * B + (b0 + jb + j)) * 4 * H + u;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            gr[g * H] = __float2bfloat16_rn(dg[g][j]);
+            dg_ptr[j][g * H] = __float2bfloat16_rn(dg[g][j]);
             dbacc[g] += dg[g][j];
           }
+          dg_ptr[j] -= size_t(B) * 4 * H;
         }
       }
       if (do_prof) prof[512 + (n - 1) * 8 + 7] = clock64();
@@ -596,7 +633,12 @@ template <int NV, int KSTEPS>
 static int launch_bwd(const uint32_t* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
-  const size_t smem = size_t(4 * 128 / 8) * kLboB + 64 + 128;
+  const size_t smem = size_t(4 * 128 / 8) * kLboB + 64 + size_t(4) * 6 * (NV / 2) * (kEpiWarps * 32) * 4 + 128;  // + prefetch ring
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    CSN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<NV, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreadsBwd, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf, 0u);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
