@@ -281,8 +281,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
 
     for (int t = 0; t < T; ++t) {
      {
-      prefetch_xp(t + 3);
-      asm volatile("cp.async.wait_group 3;" ::: "memory");  // the group of step t has landed
+      asm volatile("cp.async.wait_group 2;" ::: "memory");  // the group of step t has landed (t+1, t+2 may be in flight)
       float pre[4][NVT];
       {
         const float* src = xring + (t & 3) * kRingStage + tid;
@@ -326,7 +325,10 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
       fence_proxy_async_smem();
       handoff_arrive<kRecThreads>();
       if (do_prof) prof[t * 8 + 3] = clock64();
-      // ---- off the critical path: stream h_t and the BPTT reserve to HBM while the next MMAs run ----
+      // ---- off the critical path: prefetch Xp three steps ahead (issued HERE, after this step's tcgen05.wait::ld:
+      // measured, wait::ld also waits for cp.async groups in flight, +200 cycles when the prefetch was issued first),
+      // then stream h_t and the BPTT reserve to HBM while the next MMAs run ----
+      prefetch_xp(t + 3);
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
         if (valid[j]) {
@@ -487,8 +489,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
     int n = 0;
     for (int t = T - 1; t >= 0; --t) {
      {
-      prefetch(t - 3);
-      asm volatile("cp.async.wait_group 3;" ::: "memory");  // the group of step t has landed
+      asm volatile("cp.async.wait_group 2;" ::: "memory");  // the group of step t has landed
       struct { float i[NVT], f[NVT], g[NVT], o[NVT], c[NVT], cp[NVT]; } cur;
       float dh[NVT], tcn[NVT], pref[NVT];
       // everything that does not need dh is done before the wait
@@ -547,7 +548,8 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
       handoff_arrive<kRecThreadsBwd>();
       if (do_prof) prof[512 + n * 8 + 3] = clock64();
       ++n;
-      // ---- off the critical path ----
+      // ---- off the critical path (prefetch first: see the forward kernel) ----
+      prefetch(t - 3);
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
         if (valid[j]) {
