@@ -50,10 +50,13 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 
 struct RecSmem {
   uint8_t* opb;       // B operand: h^T (fwd, KP/8 * 256 B) or dG^T (bwd, 4KP/8 * 256 B), canonical K-major
-  uint64_t* bar_in;   // operand ready (4 epilogue warps -> issuer)
+  uint64_t* bar_in;   // (unused since the named-barrier hand-off; kept initialised)
   uint64_t* bar_acc;  // accumulators ready (issuer -> epilogue)
+  uint64_t* bar_pf;   // [4] prefetch ring stages filled (TMA bulk copies -> epilogue)
   uint32_t* tmem_slot;
+  uint8_t* ring;      // prefetch ring (after a 128-byte barrier block)
 };
+constexpr int kPfStages = 4;
 
 // `raw` is the 128-byte aligned dynamic shared array itself (no runtime alignment arithmetic): its address is a
 // link-time constant, so the B-operand descriptors of the unrolled MMA issue become immediates in uniform registers.
@@ -63,7 +66,9 @@ __device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t b_bytes) {
   s.opb = base;
   s.bar_in = reinterpret_cast<uint64_t*>(s.opb + b_bytes);
   s.bar_acc = s.bar_in + 1;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_acc + 1);
+  s.bar_pf = s.bar_acc + 1;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_pf + kPfStages);
+  s.ring = s.opb + b_bytes + 128;
   return s;
 }
 
@@ -190,6 +195,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
   if (tid == 0) {
     mbar_init(sm.bar_in, kEpiWarps);
     mbar_init(sm.bar_acc, 1);
+    for (int i = 0; i < kPfStages; ++i) mbar_init(sm.bar_pf + i, 1);
     fence_mbar_init();
   }
   if (warp == kIssuerWarp) tmem_alloc(sm.tmem_slot, kTmemCols);
@@ -214,6 +220,24 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
     const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
     const bool base0 = (tmem_base == 0);  // a 512-column allocation owns the whole TMEM: constant addresses
+    // This warp is also the TMA producer of the hoisted input projection: the NV rows Xp[t][b0..b0+NV) (4H floats
+    // each, contiguous) are bulk-copied into a 4-stage shared-memory ring three steps ahead; completion is counted on
+    // an mbarrier per stage, so the prefetch never touches the epilogue warps' scoreboards (register prefetch stalled
+    // every third step on shared scoreboard slots, and tcgen05.wait::ld also waits for in-flight cp.async groups).
+    const int rows_valid = min(NV, B - b0);
+    const uint32_t row_bytes = uint32_t(4 * H) * 4u;
+    auto prefetch_xp = [&](int t) {  // elected lane only
+      if (t >= T) return;
+      uint64_t* bar = sm.bar_pf + (t & (kPfStages - 1));
+      mbar_arrive_expect_tx(bar, row_bytes * rows_valid);
+      float* dst = reinterpret_cast<float*>(sm.ring) + size_t(t & (kPfStages - 1)) * NV * 4 * H;
+      const float* src = xp + (size_t(t) * B + b0) * 4 * H;
+      for (int j = 0; j < rows_valid; ++j) bulk_g2s(dst + size_t(j) * 4 * H, src + size_t(j) * 4 * H, row_bytes, bar);
+    };
+    if (elect_one()) {
+      for (int t = 0; t < kPfStages; ++t) prefetch_xp(t);
+    }
+    __syncwarp();
     for (int t = 1; t <= T; ++t) {
       handoff_wait<kRecThreads>();  // h_{t-1} is in shared memory (and TMEM has been drained)
       if (t == T) break;  // the last hand-off only balances the barrier
@@ -224,6 +248,8 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
         else issue_fwd<false, KSTEPS>(tmem_base, db0, idesc, ksteps);
         umma_commit(sm.bar_acc);
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 5] = clock64();
+        // every epilogue thread has consumed ring stage (t-1) % 4 before the hand-off above: refill it
+        prefetch_xp(t + kPfStages - 1);
       }
       __syncwarp();
     }
@@ -233,13 +259,8 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     const int jb = (tid >> 7) * NVT;  // first batch slot of this thread
     const bool active = u < H;
     const uint32_t lane_addr = tmem_base + (uint32_t((warp & 3) * 32) << 16) + jb;
-    // Xp prefetch: cp.async (LDGSTS) into a 4-deep per-thread shared-memory ring, three steps ahead.  Register
-    // prefetch was tried first: the pending loads share the six scoreboard slots with the per-step tcgen05.ld / MUFU
-    // work, and every third (unrolled) step stalled ~1 k cycles on a slot that also tracked in-flight loads.
-    // cp.async groups are tracked separately, and every thread only ever reads back its own bytes (no block sync).
     float bias[4], c[NVT];
-    float* xring = reinterpret_cast<float*>(sm.opb + b_bytes + 64);  // [4 stages][4*NVT][256 threads]
-    constexpr int kRingStage = 4 * NVT * (kEpiWarps * 32);
+    const float* xring = reinterpret_cast<const float*>(sm.ring);  // [4 stages][NV rows][4H] filled by the TMA producer
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = active ? b_hh[g * H + u] : 0.f;
 #pragma unroll
@@ -249,46 +270,26 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     for (int j = 0; j < NVT; ++j) valid[j] = active && (b0 + jb + j < B);
     // running pointers (advanced by one timestep per iteration): no 64-bit index arithmetic inside the loop
     const size_t step_cells = size_t(B) * H;
-    const float* xp_pf[NVT];          // Xp row of the step being prefetched
     __nv_bfloat16* h_ptr[NVT];        // h_seq[t][b][u]
     uint2* g_ptr[NVT];                // reserve gates [t][b][u][i,f,g,o] bf16 (one 8-byte store per cell)
     float* c_ptr[NVT];                // reserve cell state [t][b][u]
 #pragma unroll
     for (int j = 0; j < NVT; ++j) {
       const size_t row = size_t(b0 + jb + j);
-      xp_pf[j] = xp + (valid[j] ? row * 4 * H + u : 0);
       h_ptr[j] = h_seq + (valid[j] ? row * H + u : 0);
       g_ptr[j] = reinterpret_cast<uint2*>(gates_out) + (valid[j] ? row * H + u : 0);
       c_ptr[j] = c_out + (valid[j] ? row * H + u : 0);
     }
-    const uint32_t ring_base = smem_u32(xring + tid);
-    auto prefetch_xp = [&](int t) {  // one cp.async group per step (zero-filled when out of range)
-      const uint32_t dst = ring_base + uint32_t((t & 3) * kRingStage * 4);
-#pragma unroll
-      for (int j = 0; j < NVT; ++j) {
-        const int nbytes = (valid[j] && t < T) ? 4 : 0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
-                       ::"r"(dst + uint32_t((g * NVT + j) * (kEpiWarps * 32) * 4)), "l"(xp_pf[j] + g * H), "r"(nbytes) : "memory");
-        xp_pf[j] += size_t(B) * 4 * H;
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    prefetch_xp(0);
-    prefetch_xp(1);
-    prefetch_xp(2);
-
     for (int t = 0; t < T; ++t) {
      {
-      asm volatile("cp.async.wait_group 2;" ::: "memory");  // the group of step t has landed (t+1, t+2 may be in flight)
+      mbar_wait(sm.bar_pf + (t & (kPfStages - 1)), (t / kPfStages) & 1);  // Xp rows of step t have landed (long ago)
       float pre[4][NVT];
       {
-        const float* src = xring + (t & 3) * kRingStage + tid;
+        const float* src = xring + size_t(t & (kPfStages - 1)) * NV * 4 * H + u;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int j = 0; j < NVT; ++j) pre[g][j] = src[(g * NVT + j) * (kEpiWarps * 32)] + bias[g];
+          for (int j = 0; j < NVT; ++j) pre[g][j] = (valid[j] ? src[(jb + j) * 4 * H + g * H] : 0.f) + bias[g];
       }
       const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && t < kProfSteps;
       if (phase_prof && (t == 1 || t == 8 || t == 64 || t == 200 || t == 400)) prof[1024 + 6 + (t == 1 ? 0 : t == 8 ? 1 : t == 64 ? 2 : t == 200 ? 3 : 4)] = clock64();
@@ -325,10 +326,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
       fence_proxy_async_smem();
       handoff_arrive<kRecThreads>();
       if (do_prof) prof[t * 8 + 3] = clock64();
-      // ---- off the critical path: prefetch Xp three steps ahead (issued HERE, after this step's tcgen05.wait::ld:
-      // measured, wait::ld also waits for cp.async groups in flight, +200 cycles when the prefetch was issued first),
-      // then stream h_t and the BPTT reserve to HBM while the next MMAs run ----
-      prefetch_xp(t + 3);
+      // ---- off the critical path: stream h_t and the BPTT reserve to HBM while the next MMAs run ----
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
         if (valid[j]) {
@@ -620,7 +618,7 @@ static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (
 template <int NV, int KSTEPS>
 static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
                       float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
-  const size_t smem = size_t(KP / 8) * kLboB + 64 + size_t(4) * 4 * (NV / 2) * (kEpiWarps * 32) * 4 + 128;  // + Xp ring
+  const size_t smem = size_t(KP / 8) * kLboB + 128 + size_t(kPfStages) * NV * 4 * H * 4 + 128;  // operand + barriers + Xp ring
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
     CSN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<NV, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
