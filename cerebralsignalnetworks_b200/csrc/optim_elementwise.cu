@@ -169,6 +169,64 @@ __global__ void scale_kernel(float* __restrict__ x, size_t n, const float* __res
   for (; i < n; i += stride) x[i] *= sc;
 }
 
+// teacher <- m * teacher + (1 - m) * student   (EMA teacher, LstmDistillation.py:616-619)
+__global__ void ema_update_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n, float m) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) dst[i] = dst[i] * m + src[i] * (1.f - m);
+}
+
+// Per-parameter gradient clipping (utils/utils.py:132-141: clip_coef = clip / (||g_p|| + 1e-6), applied when < 1) over a
+// flat gradient buffer cut into segments [seg_off[i], seg_off[i+1]); no host synchronisation.
+__device__ __forceinline__ int find_segment(const long long* __restrict__ seg_off, int n_seg, long long idx) {
+  int lo = 0, hi = n_seg;  // invariant: seg_off[lo] <= idx < seg_off[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (seg_off[mid] <= idx) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+constexpr int kClipChunk = 2048;
+__global__ void seg_sumsq_kernel(const float* __restrict__ g, const long long* __restrict__ seg_off, int n_seg,
+                                 float* __restrict__ sumsq) {
+  // each block handles one chunk of kClipChunk elements that never straddles a segment (chunks are per segment)
+  __shared__ float red[8];
+  long long chunk = blockIdx.x;
+  // locate the segment of this chunk: chunk_off[i] = number of chunks before segment i, computed on the fly
+  int seg = 0;
+  long long first = 0;
+  for (; seg < n_seg; ++seg) {
+    long long len = seg_off[seg + 1] - seg_off[seg];
+    long long nc = (len + kClipChunk - 1) / kClipChunk;
+    if (chunk < first + nc) break;
+    first += nc;
+  }
+  if (seg >= n_seg) return;
+  const long long beg = seg_off[seg] + (chunk - first) * kClipChunk;
+  const long long end = min(beg + (long long)kClipChunk, seg_off[seg + 1]);
+  float acc = 0.f;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) acc = fmaf(g[i], g[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    atomicAdd(sumsq + seg, s);
+  }
+}
+__global__ void seg_clip_kernel(float* __restrict__ g, const long long* __restrict__ seg_off, int n_seg,
+                                const float* __restrict__ sumsq, float clip) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = seg_off[n_seg];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int seg = find_segment(seg_off, n_seg, i);
+    const float coef = clip / (sqrtf(sumsq[seg]) + 1e-6f);
+    if (coef < 1.f) g[i] *= coef;
+  }
+}
+
 static inline int stream_blocks(size_t n, int per_block) {
   size_t b = ceil_div<size_t>(n, per_block);
   size_t cap = size_t(sm_count()) * 8;
@@ -217,6 +275,26 @@ extern "C" int csn_scale_f32(float* x, size_t n, const float* scale_dev, float s
   CSN_REQUIRE(x, "csn_scale_f32: null pointer");
   if (n == 0) return CSN_OK;
   scale_kernel<<<stream_blocks(n, 256), 256, 0, as_stream(stream)>>>(x, n, scale_dev, scale_host);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_ema_update(float* dst, const float* src, size_t n, float momentum, void* stream) {
+  CSN_REQUIRE(dst && src, "csn_ema_update: null pointer");
+  if (n == 0) return CSN_OK;
+  ema_update_kernel<<<stream_blocks(n, 256), 256, 0, as_stream(stream)>>>(dst, src, n, momentum);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_clip_grad_segments(float* grads, const long long* seg_off_dev, int n_seg, long long n_chunks,
+                                      float* sumsq_dev, float clip, void* stream) {
+  CSN_REQUIRE(grads && seg_off_dev && sumsq_dev && n_seg >= 1 && n_chunks >= 1 && clip > 0.f, "csn_clip_grad_segments: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  CSN_CUDA(cudaMemsetAsync(sumsq_dev, 0, size_t(n_seg) * 4, s));
+  seg_sumsq_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(grads, seg_off_dev, n_seg, sumsq_dev);
+  CSN_LAUNCH_CHECK();
+  seg_clip_kernel<<<sm_count() * 8, 256, 0, s>>>(grads, seg_off_dev, n_seg, sumsq_dev, clip);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }

@@ -255,6 +255,13 @@ def adam_step_graph(params, grads, exp_avg, exp_avg_sq, step_counter, consts, lr
          float(grad_scale), _stream())
 
 
+def ema_update_(dst, src, momentum):
+    """dst = momentum * dst + (1 - momentum) * src, in place (flat fp32 buffers)."""
+    _chk(dst, torch.float32, "dst"); _chk(src, torch.float32, "src")
+    call("csn_ema_update", _p(dst), _p(src), dst.numel(), float(momentum), _stream())
+    return dst
+
+
 def dbg_umma_tile(a, b, a_mn=False, b_mn=False):
     """a [128,K], b [N,K] bf16 -> a @ b^T fp32 [128,N] through one tcgen05.mma chain (bring-up test hook)."""
     _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b")

@@ -137,6 +137,15 @@ int csn_adam_step_graph(float* params, const float* grads, float* exp_avg, float
                         float beta1, float beta2, float eps, float weight_decay, int decoupled, int* step_counter,
                         float* consts2, float grad_scale, void* stream);
 
+/* EMA teacher update over flat buffers: dst = momentum * dst + (1 - momentum) * src  (LstmDistillation.py:616-619) */
+int csn_ema_update(float* dst, const float* src, size_t n, float momentum, void* stream);
+
+/* Per-parameter gradient clipping without host syncs (utils/utils.py:132-141).  The flat gradient buffer is cut into
+ * n_seg segments [seg_off[i], seg_off[i+1]) (device int64 array of n_seg+1 offsets); n_chunks = sum_i ceil(len_i/2048);
+ * sumsq_dev: n_seg floats of scratch, left holding the squared norms (the norms the reference returns). */
+int csn_clip_grad_segments(float* grads, const long long* seg_off_dev, int n_seg, long long n_chunks, float* sumsq_dev,
+                           float clip, void* stream);
+
 /* ---- bring-up / self-test hooks (tests only) --------------------------------------------------------------
  * One tcgen05.mma tile D[128,N] = A[128,K] * B[N,K]^T with operands staged in the no-swizzle canonical layouts
  * the recurrence kernel uses; a_mn_major / b_mn_major exercise the MN-major descriptors. */

@@ -1,0 +1,64 @@
+"""cfg 3 of BASELINE.json on one GPU: the LstmDistillation.py step (lines 537-626) -- 2 global (300-sample) + 4 local
+(200-sample) crops of [64, 495, 96] trials, 4-layer LSTM (hidden 128) student/teacher backbones in MultiCropWrapper,
+DINOHead with a 65536-d output, reference multi-crop DINO loss, AdamW with the get_params_groups split, per-parameter
+gradient clipping, EMA teacher.  Everything runs on libcsn_b200 kernels through the autograd bridges."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import cerebralsignalnetworks_b200 as csn
+from cerebralsignalnetworks_b200.optim import EMATeacher, FusedAdam, get_params_groups
+
+B, C, T, H, K = int(os.environ.get("PB", "64")), 96, 495, 128, int(os.environ.get("PK", "65536"))
+dtype = torch.bfloat16
+torch.manual_seed(43); np.random.seed(43)
+def make():
+    return csn.MultiCropWrapper(csn.Model(C, H, 4, H, include_top=False, compute_dtype=dtype),
+                                csn.DINOHead(H, K, compute_dtype=dtype)).cuda()
+student, teacher = make(), make()
+teacher.load_state_dict(student.state_dict())
+for p in teacher.parameters():
+    p.requires_grad = False
+crit = csn.DINOLoss(K, 6, 0.04, 0.04, 30, 100).cuda()
+opt = FusedAdam(get_params_groups(student), lr=5e-4, weight_decay=0.04, decoupled=True)
+ema = EMATeacher(teacher, opt, student)
+g = torch.Generator(device="cuda").manual_seed(1)
+eeg = torch.randn(B, T, C, device="cuda", generator=g)
+
+def crops():
+    out = []
+    for n, length in ((2, 300), (4, 200)):
+        for _ in range(n):
+            s = np.random.randint(0, T)
+            if s + length > T:
+                s -= s + length - T
+            out.append(eeg[:, s:s + length, :].contiguous())
+    return out[:2], out[2:]
+
+def step(epoch=0):
+    gv, lv = crops()
+    with torch.no_grad():
+        t_out = torch.stack([teacher(v) for v in gv], dim=0)
+    s_out = torch.stack([student(v) for v in gv + lv], dim=0)
+    loss = crit(s_out, t_out, epoch)
+    opt.zero_grad()
+    loss.backward()
+    opt.clip_gradients(3.0)
+    opt.step()
+    ema.update(0.996)
+    return loss
+
+t0 = time.time()
+for _ in range(2):
+    l = step()
+torch.cuda.synchronize()
+print("warm-up s", round(time.time() - t0, 2), "loss", float(l), "center shape", tuple(crit.center.shape))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n = 5
+e0.record()
+for _ in range(n):
+    l = step()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+print(f"cfg3 (L4 H128, head K={K}, 2x300+4x200 crops) B={B}: {ms:.2f} ms/step  {B / ms * 1e3:.0f} trials/s  loss {float(l):.4f}")
+print("peak memory GB", round(torch.cuda.max_memory_allocated() / 1e9, 2))

@@ -163,3 +163,49 @@ def test_cuda_graph_step_matches_eager_steps():
     for n in runs[False][1]:
         assert torch.allclose(runs[True][1][n], runs[False][1][n], rtol=1e-5, atol=1e-7), n
     assert torch.allclose(runs[True][2], runs[False][2], rtol=1e-6, atol=1e-8)
+
+
+def test_fused_adam_groups_clip_and_ema_match_torch(golden):
+    """FusedAdam (AdamW, get_params_groups split, per-parameter clipping, frozen group) + EMATeacher vs torch."""
+    import cerebralsignalnetworks_b200 as csn
+    from cerebralsignalnetworks_b200.optim import EMATeacher, FusedAdam, get_params_groups
+    torch.manual_seed(21)
+    def make():
+        torch.manual_seed(21)
+        return torch.nn.Sequential(torch.nn.Linear(13, 17), torch.nn.Linear(17, 5)).cuda()
+    ours, ref, teacher, ref_teacher = make(), make(), make(), make()
+    opt = FusedAdam(get_params_groups(ours), lr=2e-3, weight_decay=0.04, decoupled=True)
+    ropt = torch.optim.AdamW(get_params_groups(ref), lr=2e-3, weight_decay=0.04)
+    ema = EMATeacher(teacher, opt, ours)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for it in range(4):
+        x = torch.randn(9, 13, device="cuda", generator=g)
+        opt.zero_grad(); ropt.zero_grad()
+        (ours(x) ** 2).sum().backward()
+        (ref(x) ** 2).sum().backward()
+        # reference clip_gradients semantics (utils/utils.py:132-141)
+        for p in ref.parameters():
+            n = p.grad.norm(2)
+            coef = 0.7 / (n + 1e-6)
+            if coef < 1:
+                p.grad.mul_(coef)
+        opt.clip_gradients(0.7)
+        opt.step(); ropt.step()
+        ema.update(0.9)
+        with torch.no_grad():
+            for q, k in zip(ref.parameters(), ref_teacher.parameters()):
+                k.mul_(0.9).add_(0.1 * q)
+    for a, b in zip(ours.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    for a, b in zip(teacher.parameters(), ref_teacher.parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    # reference clip vectors generated from utils.clip_gradients itself
+    gold = golden("utils.npz")
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3)).cuda()
+    o2 = FusedAdam(list(lin.parameters()), lr=1e-3)
+    for i, p in enumerate(lin.parameters()):
+        p.grad.copy_(torch.from_numpy(gold[f"clip_gin{i}"]).cuda())
+    sq = o2.clip_gradients(1.5)
+    np.testing.assert_allclose(sq.sqrt().cpu().numpy(), gold["clip_norms"], rtol=1e-5)
+    for i, p in enumerate(lin.parameters()):
+        np.testing.assert_allclose(p.grad.cpu().numpy(), gold[f"clip_gout{i}"], rtol=1e-5, atol=1e-7)
