@@ -35,11 +35,23 @@ def crops():
             out.append(eeg[:, s:s + length, :].contiguous())
     return out[:2], out[2:]
 
+BATCH_VIEWS = os.environ.get("BATCH_VIEWS", "1") == "1"
+
 def step(epoch=0):
     gv, lv = crops()
-    with torch.no_grad():
-        t_out = torch.stack([teacher(v) for v in gv], dim=0)
-    s_out = torch.stack([student(v) for v in gv + lv], dim=0)
+    if BATCH_VIEWS:
+        # Same arithmetic as the reference loop (:581-589, one view per call), but crops of equal length share one
+        # backbone pass (the LSTM treats trials independently): 3 backbone passes instead of 8.  (The reference's
+        # MultiCropWrapper groups by the LAST dimension, which is the channel count for [B,T,C] EEG, so it cannot
+        # group by length itself.)
+        with torch.no_grad():
+            t_out = teacher.head(teacher.backbone(torch.cat(gv))).view(2, B, K)
+        feats = torch.cat([student.backbone(torch.cat(gv)), student.backbone(torch.cat(lv))])
+        s_out = student.head(feats).view(6, B, K)
+    else:
+        with torch.no_grad():
+            t_out = torch.stack([teacher(v) for v in gv], dim=0)
+        s_out = torch.stack([student(v) for v in gv + lv], dim=0)
     loss = crit(s_out, t_out, epoch)
     opt.zero_grad()
     loss.backward()
