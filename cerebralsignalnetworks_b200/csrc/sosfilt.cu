@@ -17,6 +17,7 @@ namespace csn {
 constexpr int kMaxSec = 8;
 constexpr int kTC = 32;  // samples per streamed chunk
 constexpr int kRS = 36;  // shared row stride (floats): 144 B = 16 B * 9 -> conflict-free float4 rows
+constexpr int kStages = 4;  // cp.async ring depth: three 32-sample chunks in flight per block hide the HBM latency
 
 struct SosCoef {
   float b0[kMaxSec], b1[kMaxSec], b2[kMaxSec], a1[kMaxSec], a2[kMaxSec], zi1[kMaxSec], zi2[kMaxSec];
@@ -64,8 +65,8 @@ __global__ void __launch_bounds__(128) sosfilt_stream_kernel(const float* __rest
                                                              int C, int layout, int vec_ok) {
   extern __shared__ __align__(16) float smem[];
   const int R = blockDim.x;
-  float* in_tile = smem;                 // [2][R][kRS]
-  float* out_tile = smem + 2 * R * kRS;  // [kTC][R]   (transposed layouts only)
+  float* in_tile = smem;                        // [kStages][R][kRS]
+  float* out_tile = smem + kStages * R * kRS;   // [kTC][R]   (transposed layouts only)
   const int tid = threadIdx.x;
   const long long r0 = (long long)blockIdx.x * R;
   const int n_chunks = (T + kTC - 1) / kTC;
@@ -101,12 +102,16 @@ __global__ void __launch_bounds__(128) sosfilt_stream_kernel(const float* __rest
     cp_async_commit();
   };
 
-  issue_load(0, 0);
+  // prologue: kStages-1 chunks in flight (one cp.async group per chunk, empty groups past the end keep the count uniform)
+  for (int c = 0; c < kStages - 1; ++c) {
+    if (c < n_chunks) issue_load(c, c); else cp_async_commit();
+  }
   for (int chunk = 0; chunk < n_chunks; ++chunk) {
-    const int buf = chunk & 1;
-    cp_async_wait<0>();
-    __syncthreads();  // tile `buf` visible to all; everyone is done with tile buf^1 and with out_tile
-    if (chunk + 1 < n_chunks) issue_load(chunk + 1, buf ^ 1);
+    const int buf = chunk % kStages;
+    cp_async_wait<kStages - 2>();
+    __syncthreads();  // tile `buf` visible to all; everyone is done with the tile of chunk-1 and with out_tile
+    if (chunk + kStages - 1 < n_chunks) issue_load(chunk + kStages - 1, (chunk + kStages - 1) % kStages);
+    else cp_async_commit();
 
     float* row = in_tile + buf * R * kRS + tid * kRS;
 #pragma unroll
@@ -227,10 +232,19 @@ static int launch_sosfilt(const float* x, void* y, const SosCoef& coef, int B, i
     int R = 64;
     if (n_series >= (long long)sm_count() * 4 * 128) R = 128;
     if (n_series < (long long)sm_count() * 64) R = 32;
-    size_t smem = size_t(2) * R * kRS * 4 + size_t(kTC) * R * 4;
+    static const int forced_r = [] { const char* e = getenv("CSN_FILTER_R"); return e ? atoi(e) : 0; }();
+    if (forced_r == 32 || forced_r == 64 || forced_r == 128) R = forced_r;
+    size_t smem = size_t(kStages) * R * kRS * 4 + size_t(kTC) * R * 4;
     int vec_ok = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                  ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
     unsigned grid = (unsigned)ceil_div<long long>(n_series, R);
+    if (smem > 48 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        CSN_CUDA(cudaFuncSetAttribute(sosfilt_stream_kernel<NSEC, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+      }
+    }
     sosfilt_stream_kernel<NSEC, OutT><<<grid, R, smem, s>>>(x, (OutT*)y, coef, n_series, T, B, C, layout, vec_ok);
   } else {
     int row_stride = (T + coef.padlen) | 1;
