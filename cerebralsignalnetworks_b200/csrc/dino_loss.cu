@@ -226,21 +226,27 @@ __global__ void __launch_bounds__(kLossThreads) dino_loss_kernel(const LossParam
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Staged variant (the HBM-bound shapes: K % 4 == 0, 16-byte aligned rows).  Same decomposition and arithmetic as
-// dino_loss_kernel, but the row chunks are pulled by the TMA unit: one thread issues 1-D bulk copies
-// (cp.async.bulk global -> shared, mbarrier complete_tx) for the next S rows into a shared-memory ring while the
-// CTA reduces / writes the current row, so S * Kc * 4 bytes per SM are always in flight without holding registers.
+// Staged variant (the HBM-bound shapes: K % 4 == 0, 16-byte aligned rows).  Same decomposition as dino_loss_kernel,
+// rebuilt around three rules measured with ncu on the cfg3 shape (profiles/ncu_loss_r01d.md):
+//   * row chunks are pulled by the TMA unit: one thread issues 1-D bulk copies (cp.async.bulk global -> shared,
+//     mbarrier complete_tx) for the next S rows into a shared-memory ring while the CTA works on the current row;
+//   * instruction diet: logits are scaled into the log2 domain once, every element costs ONE ex2 (taken against the
+//     thread-local maximum and rescaled by a per-thread scalar once the row statistics are known), the teacher
+//     probabilities are pre-summed when every student view is matched against all teacher views (ALLSAME);
+//   * the cluster exchange is a PUSH: warp 0 sends the CTA's (max, sum, dot) to every peer's mailbox with st.async
+//     (data + mbarrier complete_tx in one DSMEM packet), everybody waits on a local mbarrier.  No cluster.sync (and
+//     its L1 flush) and no remote loads on the critical path.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
-                 "r"((uint32_t)__cvta_generic_to_shared(bar))
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
 __device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -250,75 +256,141 @@ __device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   }
 }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// 16 bytes into a peer CTA's shared memory + complete_tx(16) on the peer's mbarrier, one DSMEM packet
+__device__ __forceinline__ void st_async_f4(uint32_t remote_addr, float a, float b, float c, float d, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-template <int NITER>
-__global__ void __launch_bounds__(kLossThreads) dino_loss_staged_kernel(const LossParams p, const int S) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int cs = (int)cluster.num_blocks();
-  const int crank = (int)cluster.block_rank();
+constexpr float kNegBig = -1.0e30f;   // padding logit: never the maximum, ex2(kNegBig - m) == 0, 0 * kNegBig == -0
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct RowStat {
+  float m, z, d;  // log2-domain maximum, sum of 2^(x - m), <Q, x>
+};
+
+template <int NITER, bool ALLSAME>
+__global__ void __launch_bounds__(kLossThreads, 2) dino_loss_staged_kernel(const LossParams p, const int S) {
+  uint32_t cs, crank;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const int b = blockIdx.y;
-  const int tid = threadIdx.x;
-  const int k0 = crank * p.Kc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k0 = (int)crank * p.Kc;
   constexpr int EPT = 4 * NITER;
+  constexpr int NQ = ALLSAME ? 1 : kMaxVt;
   const uint32_t row_bytes = (uint32_t)p.Kc * 4u;
 
   extern __shared__ __align__(128) uint8_t smem_dyn[];
-  float* stages = reinterpret_cast<float*>(smem_dyn);            // [S][Kc]
-  float* cen_s = stages + size_t(S) * p.Kc;                      // [Kc]
-  uint64_t* full = reinterpret_cast<uint64_t*>(cen_s + p.Kc);    // [S] row barriers + [1] centre barrier
-  __shared__ Stat warp_buf[kLossThreads / 32];
-  __shared__ Stat slots[kMaxRounds];
+  float* stages = reinterpret_cast<float*>(smem_dyn);                   // [S][Kc]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + size_t(S) * p.Kc);  // [S] row barriers
+  __shared__ __align__(16) float4 mailbox[kMaxRounds][8];  // [round][sender rank] = (m, z, d, -)
+  __shared__ __align__(16) float4 warp_buf[kLossThreads / 32];
+  __shared__ __align__(8) uint64_t xbar[kMaxRounds];       // one exchange barrier per round, never reused
   __shared__ int vlist[kMaxVs];
-  __shared__ int n_active;
+  __shared__ int n_active_s;
 
   if (tid == 0) {
     int n = 0;
     for (int v = 0; v < p.Vs; ++v)
       if (p.mask[v]) vlist[n++] = v;
-    n_active = n;
-    for (int i = 0; i <= S; ++i) mbar_init_(&full[i], 1);
+    n_active_s = n;
+    for (int i = 0; i < S; ++i) mbar_init_(&full[i], 1);
+    for (int r = 0; r < p.Vt + n; ++r) {
+      mbar_init_(&xbar[r], 1);
+      mbar_expect_tx_(&xbar[r], cs * 16u);  // the phase completes when all cs mailboxes of the round have landed
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  cluster_arrive_();  // peers may push into our mailboxes once they have seen this arrive (waited for before push 0)
+  const int n_active = n_active_s;
   const int nrows = p.Vt + n_active;
   auto row_src = [&](int r) -> const float* {
     if (r < p.Vt) return p.teacher + (size_t(r) * p.B + b) * p.K + k0;
     return p.student + (size_t(vlist[r - p.Vt]) * p.B + b) * p.K + k0;
   };
-  auto issue = [&](int r) {  // thread 0 only
+  constexpr int kProducer = 32;  // warp 1 lane 0 feeds the ring; warp 0 owns the exchange
+  auto issue = [&](int r) {
     uint64_t* bar = &full[r % S];
     mbar_expect_tx_(bar, row_bytes);
     bulk_g2s(stages + size_t(r % S) * p.Kc, row_src(r), row_bytes, bar);
   };
-  if (tid == 0) {
-    mbar_expect_tx_(&full[S], row_bytes);
-    bulk_g2s(cen_s, p.center + (p.center_rows > 1 ? size_t(b) * p.K : 0) + k0, row_bytes, &full[S]);
+  if (tid == kProducer)
     for (int r = 0; r < S && r < nrows; ++r) issue(r);
-  }
 
   auto in_range = [&](int it) { return (it * kLossThreads + tid) * 4 < p.Kc; };
-  // pull this thread's values of row r out of the ring; afterwards the stage is handed back to the TMA producer
-  auto take_row = [&](int r, float (&dst)[EPT]) {
-    mbar_wait_(&full[r % S], (uint32_t)((r / S) & 1));
-    const float* src = stages + size_t(r % S) * p.Kc;
-#pragma unroll
-    for (int it = 0; it < NITER; ++it) {
-      float4 v = in_range(it) ? *reinterpret_cast<const float4*>(src + (it * kLossThreads + tid) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      dst[it * 4 + 0] = v.x; dst[it * 4 + 1] = v.y; dst[it * 4 + 2] = v.z; dst[it * 4 + 3] = v.w;
-    }
-    __syncthreads();
-    if (tid == 0 && r + S < nrows) issue(r + S);
-  };
   auto store_row = [&](float* base, const float (&src)[EPT]) {
 #pragma unroll
     for (int it = 0; it < NITER; ++it)
       if (in_range(it))
         __stcs(reinterpret_cast<float4*>(base + k0 + (it * kLossThreads + tid) * 4),
                make_float4(src[it * 4 + 0], src[it * 4 + 1], src[it * 4 + 2], src[it * 4 + 3]));
+  };
+
+  // CTA reduction of the per-thread (max, sum 2^(x - max), dot), push to every peer, combine the cs mailboxes.
+  // The __syncthreads also certifies that every thread has pulled its values of row r out of the ring, so the
+  // producer refills that stage right behind it.
+  bool first_push = true;
+  auto reduce = [&](float mt, float zt, float dt, int r) -> RowStat {
+    const float wm = warp_max(mt);
+    zt *= ex2_(mt - wm);
+    zt = warp_sum(zt);
+    dt = warp_sum(dt);
+    if (lane == 0) warp_buf[warp] = make_float4(wm, zt, dt, 0.f);
+    if (first_push) { cluster_wait_(); first_push = false; }
+    __syncthreads();
+    if (tid == kProducer && r + S < nrows) issue(r + S);
+    if (warp == 0) {
+      float4 t = (lane < kLossThreads / 32) ? warp_buf[lane] : make_float4(kNegBig, 0.f, 0.f, 0.f);
+      float cm = t.x;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+      float cz = t.y * ex2_(t.x - cm), cd = t.z;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        cz += __shfl_xor_sync(0xffffffffu, cz, o);
+        cd += __shfl_xor_sync(0xffffffffu, cd, o);
+      }
+      if (lane < (int)cs)
+        st_async_f4(map_to_cta(smem_u32(&mailbox[r][crank]), lane), cm, cz, cd, 0.f, map_to_cta(smem_u32(&xbar[r]), lane));
+    }
+    mbar_wait_(&xbar[r], 0);
+    RowStat o{kNegBig, 0.f, 0.f};
+    float4 mb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mb[j] = (j < (int)cs) ? mailbox[r][j] : make_float4(kNegBig, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.m = fmaxf(o.m, mb[j].x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o.z = fmaf(mb[j].y, ex2_(mb[j].x - o.m), o.z);
+      o.d += mb[j].z;
+    }
+    return o;
   };
 
   // student views that are not matched against any teacher view: zero gradient
@@ -330,46 +402,64 @@ __global__ void __launch_bounds__(kLossThreads) dino_loss_staged_kernel(const Lo
       if (p.mask[v] == 0) store_row(p.d_student + (size_t(v) * p.B + b) * p.K, z);
   }
 
-  int round = 0;
-  float q[kMaxVt][EPT];
+  float q[NQ][EPT];  // teacher probabilities (ALLSAME: their sum over the teacher views)
   float bc[EPT];
 #pragma unroll
   for (int i = 0; i < EPT; ++i) bc[i] = 0.f;
-  mbar_wait_(&full[S], 0);  // centre chunk
+  const float ts = p.inv_tau_t * kLog2e, ss = p.inv_tau_s * kLog2e;
+  const float* cbase = p.center + (p.center_rows > 1 ? size_t(b) * p.K : 0) + k0;
 
   // ---- teacher rows: q[g] = softmax((t - c) / tau_t) ----
 #pragma unroll
   for (int g = 0; g < kMaxVt; ++g) {
     if (g < p.Vt) {
-      take_row(g, q[g]);
-      Stat s{-INFINITY, 0.f, 0.f};
+      float e[EPT];
+      // centre chunk straight from L2/HBM while the row's bulk copy is still in flight
+#pragma unroll
+      for (int it = 0; it < NITER; ++it) {
+        const float4 c4 = in_range(it) ? __ldg(reinterpret_cast<const float4*>(cbase + (it * kLossThreads + tid) * 4))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        e[it * 4 + 0] = c4.x; e[it * 4 + 1] = c4.y; e[it * 4 + 2] = c4.z; e[it * 4 + 3] = c4.w;
+      }
+      mbar_wait_(&full[g % S], (uint32_t)((g / S) & 1));
+      const float* src = stages + size_t(g % S) * p.Kc;
+      float mx[4] = {kNegBig, kNegBig, kNegBig, kNegBig};
 #pragma unroll
       for (int it = 0; it < NITER; ++it) {
         if (in_range(it)) {
-          const float4 c4 = *reinterpret_cast<const float4*>(cen_s + (it * kLossThreads + tid) * 4);
-          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+          const float4 t4 = *reinterpret_cast<const float4*>(src + (it * kLossThreads + tid) * 4);
+          const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int i = it * 4 + j;
-            bc[i] += q[g][i];
-            q[g][i] = (q[g][i] - cc[j]) * p.inv_tau_t;
-            s.m = fmaxf(s.m, q[g][i]);
+            bc[i] += tt[j];
+            e[i] = (tt[j] - e[i]) * ts;
+            mx[j] = fmaxf(mx[j], e[i]);
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[it * 4 + j] = kNegBig;
         }
       }
+      const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      float zs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int it = 0; it < NITER; ++it)
-        if (in_range(it)) {
+      for (int i = 0; i < EPT; ++i) {
+        e[i] = ex2_(e[i] - mt);
+        zs[i & 3] += e[i];
+      }
+      const RowStat st = reduce(mt, (zs[0] + zs[1]) + (zs[2] + zs[3]), 0.f, g);
+      const float A = __fdividef(ex2_(mt - st.m), st.z);
+      if (ALLSAME && g > 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) s.z += __expf(q[g][it * 4 + j] - s.m);
-        }
-      s = cluster_reduce(s, warp_buf, &slots[round++], cluster, cs);
-      const float inv_z = 1.f / s.z;
+        for (int i = 0; i < EPT; ++i) q[0][i] = fmaf(e[i], A, q[0][i]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) q[g][i] = __expf(q[g][i] - s.m) * inv_z;
-    } else {
+        for (int i = 0; i < EPT; ++i) q[ALLSAME ? 0 : g][i] = e[i] * A;
+      }
+    } else if (!ALLSAME) {
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) q[g][i] = 0.f;
+      for (int i = 0; i < EPT; ++i) q[ALLSAME ? 0 : g][i] = 0.f;
     }
   }
 
@@ -388,46 +478,61 @@ __global__ void __launch_bounds__(kLossThreads) dino_loss_staged_kernel(const Lo
   // ---- student rows ----
   float loss_acc = 0.f;
   for (int a = 0; a < n_active; ++a) {
+    const int r = p.Vt + a;
     const int v = vlist[a];
     const unsigned mask = p.mask[v];
-    float u[EPT];
-    take_row(p.Vt + a, u);
     const float w0 = (mask & 1u) ? 1.f : 0.f, w1 = (mask & 2u) ? 1.f : 0.f;
-    const float W = w0 + w1;
-    Stat s{-INFINITY, 0.f, 0.f};
+    const float W = ALLSAME ? float(p.Vt) : (w0 + w1);
+    auto Qv = [&](int i) -> float {
+      if constexpr (ALLSAME) return q[0][i];
+      else return fmaf(w1, q[NQ - 1][i], w0 * q[0][i]);
+    };
+    float e[EPT];
+    mbar_wait_(&full[r % S], (uint32_t)((r / S) & 1));
+    const float* src = stages + size_t(r % S) * p.Kc;
+    float mx[4] = {kNegBig, kNegBig, kNegBig, kNegBig};
+    float ds[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int it = 0; it < NITER; ++it)
+    for (int it = 0; it < NITER; ++it) {
       if (in_range(it)) {
+        const float4 u4 = *reinterpret_cast<const float4*>(src + (it * kLossThreads + tid) * 4);
+        const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int i = it * 4 + j;
-          u[i] *= p.inv_tau_s;
-          s.m = fmaxf(s.m, u[i]);
-          s.d += (w0 * q[0][i] + w1 * q[1][i]) * u[i];
+          e[i] = uu[j] * ss;
+          mx[j] = fmaxf(mx[j], e[i]);
+          ds[j] = fmaf(Qv(i), e[i], ds[j]);
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[it * 4 + j] = kNegBig;
       }
+    }
+    const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    float zs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int it = 0; it < NITER; ++it)
-      if (in_range(it)) {
+    for (int i = 0; i < EPT; ++i) {
+      e[i] = ex2_(e[i] - mt);
+      zs[i & 3] += e[i];
+    }
+    const RowStat st = reduce(mt, (zs[0] + zs[1]) + (zs[2] + zs[3]), (ds[0] + ds[1]) + (ds[2] + ds[3]), r);
+    loss_acc += p.coef * kLn2 * (W * (st.m + lg2_(st.z)) - st.d);
+    const float A = W * __fdividef(ex2_(mt - st.m), st.z);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s.z += __expf(u[it * 4 + j] - s.m);
-      }
-    s = cluster_reduce(s, warp_buf, &slots[round++], cluster, cs);
-    loss_acc += p.coef * (W * (s.m + __logf(s.z)) - s.d);
-    const float inv_z = 1.f / s.z;
-#pragma unroll
-    for (int i = 0; i < EPT; ++i)
-      u[i] = p.grad_coef * (W * __expf(u[i] - s.m) * inv_z - (w0 * q[0][i] + w1 * q[1][i]));
-    store_row(p.d_student + (size_t(v) * p.B + b) * p.K, u);
+    for (int i = 0; i < EPT; ++i) e[i] = p.grad_coef * fmaf(e[i], A, -Qv(i));
+    store_row(p.d_student + (size_t(v) * p.B + b) * p.K, e);
   }
   if (crank == 0 && tid == 0) atomicAdd(p.loss, loss_acc);
-  if (cs > 1) cluster.sync();  // peers may still be reading our mailboxes
+  if (first_push) cluster_wait_();  // (no rows at all: still pair the arrive)
+  cluster_arrive_();                // nobody leaves while a peer could still be pushing to it / reading from it
+  cluster_wait_();
 }
 
-template <int NITER>
+template <int NITER, bool ALLSAME>
 static int launch_loss_staged(const LossParams& p, int cs, int S, cudaStream_t s) {
-  const size_t smem = size_t(S + 1) * p.Kc * 4 + size_t(S + 1) * 8 + 128;
-  auto kern = dino_loss_staged_kernel<NITER>;
+  const size_t smem = size_t(S) * p.Kc * 4 + size_t(S) * 8 + 128;
+  auto kern = dino_loss_staged_kernel<NITER, ALLSAME>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -447,6 +552,14 @@ static int launch_loss_staged(const LossParams& p, int cs, int S, cudaStream_t s
   cfg.numAttrs = 1;
   CSN_CUDA(cudaLaunchKernelEx(&cfg, kern, p, S));
   return CSN_OK;
+}
+
+template <bool ALLSAME>
+static int dispatch_loss_staged(int per_thread, const LossParams& p, int cs, int S, cudaStream_t s) {
+  if (per_thread <= 1) return launch_loss_staged<1, ALLSAME>(p, cs, S, s);
+  if (per_thread <= 2) return launch_loss_staged<2, ALLSAME>(p, cs, S, s);
+  if (per_thread <= 4) return launch_loss_staged<4, ALLSAME>(p, cs, S, s);
+  return launch_loss_staged<8, ALLSAME>(p, cs, S, s);
 }
 
 template <int VEC, int NITER>
@@ -536,19 +649,20 @@ extern "C" int csn_dino_loss_fwd_bwd(const float* student, const float* teacher,
   static const bool no_stage = [] { const char* e = getenv("CSN_LOSS_NO_STAGE"); return e && e[0] == '1'; }();
   if (vec == 4 && !no_stage && (reinterpret_cast<uintptr_t>(center) & 15) == 0) {
     int n_act = 0;
-    for (int v = 0; v < Vs; ++v) n_act += p.mask[v] ? 1 : 0;
+    bool all_same = true;  // every matched student view is matched against ALL teacher views (REF and SINGLE modes)
+    for (int v = 0; v < Vs; ++v) {
+      n_act += p.mask[v] ? 1 : 0;
+      if (p.mask[v] && p.mask[v] != (1u << Vt) - 1u) all_same = false;
+    }
     const int nrows = Vt + n_act;
-    // ring depth: row chunks that fit next to the centre chunk in ~100 KB (two CTAs per SM hide each other's
-    // reduction / cluster-barrier latency), at most 4 and at most nrows.  CSN_LOSS_STAGE_KB overrides the budget.
+    // ring depth: row chunks that fit in ~100 KB (two CTAs per SM overlap each other's exchange latency), at most 4
+    // and at most nrows.  CSN_LOSS_STAGE_KB overrides the budget.
     static const unsigned budget_kb = [] { const char* e = getenv("CSN_LOSS_STAGE_KB"); return e ? (unsigned)atoi(e) : 100u; }();
-    int S = (int)((budget_kb * 1024u) / (size_t(p.Kc) * 4u)) - 1;
+    int S = (int)((budget_kb * 1024u) / (size_t(p.Kc) * 4u));
     S = S > 4 ? 4 : S;
     S = S > nrows ? nrows : S;
     if (S >= 1) {
-      if (per_thread <= 1) r = launch_loss_staged<1>(p, cs, S, s);
-      else if (per_thread <= 2) r = launch_loss_staged<2>(p, cs, S, s);
-      else if (per_thread <= 4) r = launch_loss_staged<4>(p, cs, S, s);
-      else r = launch_loss_staged<8>(p, cs, S, s);
+      r = all_same ? dispatch_loss_staged<true>(per_thread, p, cs, S, s) : dispatch_loss_staged<false>(per_thread, p, cs, S, s);
       if (r == CSN_OK) count_launches(1);
       return r;
     }
