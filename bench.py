@@ -65,33 +65,117 @@ def measured_peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed regions.  NVML is polled from a thread every few ms (the timed
+    region of a default run is short; `nvidia-smi -lms` needs ~0.5 s to produce its first row); nvidia-smi is the
+    fallback when pynvml cannot be initialised.  start()/pause() bracket each timed region, summary() reports."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, torch, device_index, period_s=0.004):
+        import threading
+        self.period = period_s
+        self.samples = []          # (sm_mhz, reasons_bitmask, power_w)
+        self.sm_max = None
+        self.h = None
+        self.nv = None
+        self._on = threading.Event()
+        self._quit = False
+        self.backend = "none"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.backend = "nvml"
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        except Exception:
+            self.h = None
+            self._smi_index = device_index
+            self._smi = None
+            self._smi_file = None
+
+    def _reasons(self):
+        nv = self.nv
+        for name in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            fn = getattr(nv, name, None)
+            if fn is not None:
+                try:
+                    return int(fn(self.h))
+                except Exception:
+                    continue
+        return 0
+
+    def _loop(self):
+        nv = self.nv
+        while not self._quit:
+            self._on.wait()
+            if self._quit:
+                break
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((mhz, self._reasons(), pw))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        if self.h is not None:
+            self._on.set()
+            return
+        try:  # fallback: nvidia-smi loop (coarse)
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            if self._smi is None:
+                self._smi_file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+                self._smi = subprocess.Popen(["nvidia-smi", "-i", str(self._smi_index), "--query-gpu=" + q,
+                                              "--format=csv,noheader,nounits", "-lms", "50"],
+                                             stdout=self._smi_file, stderr=subprocess.DEVNULL)
+                self.backend = "nvidia-smi"
         except Exception:
-            self.p = None
+            self._smi = None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+    def pause(self):
+        if self.h is not None:
+            self._on.clear()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "backend": self.backend}
+        if self.h is not None:
+            self._quit = True
+            self._on.set()
+            rows = list(self.samples)
+            if rows:
+                out["sm_mhz"] = statistics.median(r[0] for r in rows)
+                out["sm_min_mhz"] = min(r[0] for r in rows)
+                mask = 0
+                for r in rows:
+                    mask |= r[1]
+                out["reasons"] = sorted(n for bit, n in self.REASONS.items() if mask & bit)
+                pw = [r[2] for r in rows if r[2] is not None]
+                if pw:
+                    out["power_w_max"] = max(pw)
+                out["samples"] = len(rows)
             return out
-        self.p.terminate()
+        if getattr(self, "_smi", None) is None:
+            return out
+        self._smi.terminate()
         try:
-            self.p.wait(timeout=5)
+            self._smi.wait(timeout=5)
         except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
-        os.unlink(self.f.name)
+            self._smi.kill()
+        self._smi_file.flush()
+        rows = [r.split(",") for r in open(self._smi_file.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self._smi_file.name)
         if not rows:
             return out
         sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
@@ -147,7 +231,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    batch = 64  # bounded sample of the 256-trial step: keeps --steps 10 under ~2 minutes on 8 cores
+    # bounded sample of the 256-trial cfg2 step: the largest of 64/32/16 trials per step whose K steps fit ~2 minutes
+    # of host time (probed with one timed step each; CPU step time is linear in the batch)
+    budget_s = float(os.environ.get("CSN_REF_BUDGET_S", "120"))
+    batch = 16
+    for cand in (64, 32, 16):
+        _, ms_probe, _ = cpu_reference_step_rate(cand, 1, 1)
+        batch = cand
+        if ms_probe * 1e-3 * (args.steps + min(args.warmup, 3)) <= budget_s:
+            break
     rate, ms, cores = cpu_reference_step_rate(batch, args.steps, max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -166,8 +258,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--batch_per_gpu", type=int, default=CFG["batch_per_gpu"])
@@ -218,7 +310,7 @@ def main():
     for i in range(args.warmup):
         step.step(eeg[i % NB], feats[i % NB], epoch=0)
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(torch, local) if rank == 0 else None
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
@@ -229,7 +321,8 @@ def main():
         loss = step.step(eeg[i % NB], feats[i % NB], epoch=0)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.pause()
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
@@ -275,7 +368,7 @@ def main():
         l1.record()
         torch.cuda.synchronize()
         loss_ms = l0.elapsed_time(l1) / 9
-        loss_bytes = (Vs + Vt + Vs) * 4.0 * Kl * Bl + 2 * 4.0 * Bl * Kl  # student + teacher + gradient + centre in/out
+        loss_bytes = (Vs + Vt + Vs) * 4.0 * Kl * Bl  # student + teacher read, gradient written (3 670 016 B/trial)
         loss_gbs = loss_bytes / (loss_ms * 1e-3) / 1e9
         del sets, outs, bc, cen
     except Exception as exc:  # report, do not hide
@@ -317,9 +410,12 @@ def main():
 
     e2e_loop(3)
     barrier()
+    if rank == 0:
+        sampler.start()
     t0 = time.perf_counter()
     e2e_loop(args.steps)
     barrier()
+    clocks = sampler.summary() if rank == 0 else None
     e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)

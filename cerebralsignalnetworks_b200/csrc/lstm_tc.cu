@@ -53,8 +53,10 @@ struct RecSmem {
   uint64_t* bar_in;   // (unused since the named-barrier hand-off; kept initialised)
   uint64_t* bar_acc;  // accumulators ready (issuer -> epilogue)
   uint64_t* bar_pf;   // [4] prefetch ring stages filled (TMA bulk copies -> epilogue)
+  uint64_t* bar_xp;   // [2] fused input projection: Xp accumulator set filled (issuer -> epilogue / x-ring reuse)
+  uint64_t* bar_w;    // fused input projection: W_ih operand image landed in shared memory
   uint32_t* tmem_slot;
-  uint8_t* ring;      // prefetch ring (after a 128-byte barrier block)
+  uint8_t* ring;      // prefetch ring / fused-projection operands (after a 128-byte barrier block)
 };
 constexpr int kPfStages = 4;
 
@@ -67,7 +69,9 @@ __device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t b_bytes) {
   s.bar_in = reinterpret_cast<uint64_t*>(s.opb + b_bytes);
   s.bar_acc = s.bar_in + 1;
   s.bar_pf = s.bar_acc + 1;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_pf + kPfStages);
+  s.bar_xp = s.bar_pf + kPfStages;
+  s.bar_w = s.bar_xp + 2;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_w + 1);
   s.ring = s.opb + b_bytes + 128;
   return s;
 }
@@ -75,7 +79,20 @@ __device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t b_bytes) {
 // Tensor-memory map (512 columns allocated; lane = hidden unit):
 //   [0, 64)    fp32 accumulators, 16 columns (batch slots) per gate (forward) / one dh^T accumulator (backward)
 //   [256, 512) resident weights as packed bf16 pairs: gate g at columns 256 + 64 g + k/2
-constexpr uint32_t kTmemCols = 512, kAcol0 = 256, kAgate = 64;
+//   [64, 192)  (forward, fused input projection) two sets of 4 x 16 columns: x_t W_ih^T of the current / next block of
+//              16/NV timesteps, column = (timestep in block) * NV + batch slot
+constexpr uint32_t kTmemCols = 512, kAcol0 = 256, kAgate = 64, kXpCol0 = 64;
+constexpr uint32_t kLboA = 2048, kSboA = 128;  // W_ih operand in shared memory: 128 rows per k-group (K-major canonical)
+
+// W_ih [4H, I] fp32 -> the bf16 shared-memory image of the four 128 x KI K-major A-operand blocks (zero padded), so a
+// recurrence CTA stages it with four bulk copies.
+__global__ void pack_wih_smem_image_kernel(const float* __restrict__ w_ih, __nv_bfloat16* __restrict__ img, int H, int I, int KI) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 4 * 128 * KI, k fastest
+  if (idx >= 4 * 128 * KI) return;
+  const int k = idx % KI, r = (idx / KI) & 127, g = idx / (KI * 128);
+  const float v = (r < H && k < I) ? w_ih[size_t(g * H + r) * I + k] : 0.f;
+  img[(size_t(g) * 128 * KI * 2 + canon_k_off(r, k, kLboA, kSboA)) / 2] = __float2bfloat16_rn(v);
+}
 
 // The resident weight operand is prepared once per call by a small packing kernel as the exact TMEM image
 // [gate][lane][64 columns] of packed bf16 pairs (column c = K elements 2c, 2c+1; zero padded), so that every
@@ -172,11 +189,24 @@ __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int NV, int KSTEPS>
-__global__ void __launch_bounds__(kRecThreads, 1)
+// FX = fused input projection: instead of reading a precomputed Xp[T,B,4H] from HBM, the CTA multiplies its own
+// trials' inputs by W_ih on the tensor pipe's idle slots.  W_ih (bf16) is resident in shared memory as the A operand,
+// the inputs of a BLOCK of TB = 16/NV timesteps x NV trials form one 16-row B operand (cp.async by the issuer warp,
+// two blocks ahead), and the 4*KI/16 MMAs of block n+1 are issued a few per step behind the recurrent MMAs of block
+// n into the second of two Xp accumulator sets in tensor memory; the epilogue adds its column of the current set
+// with one more tcgen05.ld per gate.  No Xp round trip through HBM (230 MB written + read per cfg2 step), no separate
+// projection GEMM.
+template <int NV, int KSTEPS, bool FX>
+__global__ void __launch_bounds__(kRecThreadsBwd, 1)
 lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_img, const float* __restrict__ b_hh,
                    __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
-                   int T, int B, int H, int KP, long long* __restrict__ prof, const uint32_t uz) {
+                   int T, int B, int H, int KP, long long* __restrict__ prof, const uint32_t uz,
+                   const __nv_bfloat16* __restrict__ x_in, const uint8_t* __restrict__ wih_img,
+                   const float* __restrict__ b_ih, int I, int KI) {
+  // FX adds warp 9: the input-projection issuer / x loader, with its own uniform register file (sharing the
+  // recurrent issuer's warp pushed that warp's MMA operands out of uniform registers: one R2UR per MMA on the chain)
+  constexpr int kThreads = FX ? kRecThreadsBwd : kRecThreads;
+  constexpr int kXWarp = kIssuerWarp + 1;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const size_t b_bytes = size_t(KP / 8) * kLboB;
   RecSmem sm = carve(smem_raw, b_bytes);
@@ -191,11 +221,15 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     prof[1024 + 1] = clock64();
   }
 
-  for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
+  for (int i = tid; i < (int)(b_bytes / 4); i += kThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
     mbar_init(sm.bar_in, kEpiWarps);
     mbar_init(sm.bar_acc, 1);
     for (int i = 0; i < kPfStages; ++i) mbar_init(sm.bar_pf + i, 1);
+    mbar_init(sm.bar_xp, 1);
+    mbar_init(sm.bar_xp + 1, 1);
+    mbar_init(sm.bar_w, 1);
+    *reinterpret_cast<volatile int*>(sm.tmem_slot + 1) = 0;
     fence_mbar_init();
   }
   if (warp == kIssuerWarp) tmem_alloc(sm.tmem_slot, kTmemCols);
@@ -204,6 +238,17 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
+  // fused-projection operands: two x blocks (16 rows x KI, same canonical layout as the h operand), then W_ih
+  constexpr int TB = kNslots / NV;  // timesteps per Xp block
+  const uint32_t x_bytes = uint32_t(KI / 8) * kLboB;
+  uint8_t* const xbuf = sm.ring;
+  uint8_t* const wih_s = sm.ring + 2 * x_bytes;
+  volatile int* const issued_step = reinterpret_cast<volatile int*>(sm.tmem_slot + 1);  // last step whose MMAs are queued
+  if (FX && tid == kXWarp * 32) {
+    const uint32_t gate_bytes = 128u * uint32_t(KI) * 2u;
+    mbar_arrive_expect_tx(sm.bar_w, 4 * gate_bytes);
+    for (int g = 0; g < 4; ++g) bulk_g2s(wih_s + size_t(g) * gate_bytes, wih_img + size_t(g) * gate_bytes, gate_bytes, sm.bar_w);
+  }
   if (phase_prof) prof[1024 + 2] = clock64();
   // W_hh resident in TENSOR MEMORY for the whole sequence: lane = hidden unit u (row of each gate block)
   if (warp < 4) stage_weights_tmem(tmem_base + (uint32_t(warp * 32) << 16), w_img, tid);
@@ -234,10 +279,12 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
       const float* src = xp + (size_t(t) * B + b0) * 4 * H;
       for (int j = 0; j < rows_valid; ++j) bulk_g2s(dst + size_t(j) * 4 * H, src + size_t(j) * 4 * H, row_bytes, bar);
     };
-    if (elect_one()) {
-      for (int t = 0; t < kPfStages; ++t) prefetch_xp(t);
+    if (!FX) {
+      if (elect_one()) {
+        for (int t = 0; t < kPfStages; ++t) prefetch_xp(t);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     for (int t = 1; t <= T; ++t) {
       handoff_wait<kRecThreads>();  // h_{t-1} is in shared memory (and TMEM has been drained)
       if (t == T) break;  // the last hand-off only balances the barrier
@@ -249,9 +296,84 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
         umma_commit(sm.bar_acc);
         if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 5] = clock64();
         // every epilogue thread has consumed ring stage (t-1) % 4 before the hand-off above: refill it
-        prefetch_xp(t + kPfStages - 1);
+        if (!FX) prefetch_xp(t + kPfStages - 1);
+        else *issued_step = t;  // the projection warp queues its MMAs behind this step's
       }
       __syncwarp();
+    }
+  } else if (FX && warp == kXWarp) {
+    // ================= fused input projection: x loader + Xp MMA issuer (own warp, own uniform registers) ==========
+    constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
+    const int n_blocks = (T + TB - 1) / TB;
+    const int n_x = 4 * (KI / 16);                 // Xp MMAs per block, k-step major / gate minor
+    const int per_step = (n_x + TB - 1) / TB;
+    const uint64_t dx0 = make_smem_desc(smem_u32(xbuf), kLboB, kSboB, kLayoutNone);
+    const uint64_t da0 = make_smem_desc(smem_u32(wih_s), kLboA, kSboA, kLayoutNone);
+    // all lanes: 16-byte cp.async chunks of block m's rows (zero fill out of range); lane = (row parity, k-chunk)
+    auto load_x_block = [&](int m) {
+      uint8_t* dst = xbuf + size_t(m & 1) * x_bytes;
+      const int kc = lane & 15, sub = lane >> 4;
+      const bool kc_ok = kc * 8 < I;
+#pragma unroll
+      for (int i = 0; i < kNslots / 2; ++i) {
+        const int row = 2 * i + sub;
+        const int tt = row / NV, j = row % NV;  // NV is a power of two
+        const int t = m * TB + tt, b = b0 + j;
+        const bool ok = kc_ok && (t < T) && (b < B);
+        const __nv_bfloat16* src = ok ? x_in + (size_t(t) * B + b) * I + kc * 8 : x_in;
+        const uint32_t d = smem_u32(dst + uint32_t(kc) * kLboB + uint32_t(row >> 3) * kSboB + uint32_t(row & 7) * 16);
+        const int nbytes = ok ? 16 : 0;
+        if (kc * 8 < KI) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto x_landed = [&]() {  // all lanes: every cp.async of this warp is complete and visible to the tensor pipe
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+    };
+    auto issue_x_chunk = [&](int m, int c) {  // elected lane: chunk c of block m's projection into set m & 1
+      const int set = m & 1;
+      const int q1 = min(n_x, (c + 1) * per_step);
+      for (int q = c * per_step; q < q1; ++q) {
+        const int kk = q >> 2, g = q & 3;
+        umma_f16(tmem_base + kXpCol0 + uint32_t(set) * 64u + uint32_t(g) * kNslots,
+                 da0 + uint64_t((uint32_t(g) * 128u * uint32_t(KI) * 2u + uint32_t(kk) * 2u * kLboA) >> 4),
+                 dx0 + uint64_t((uint32_t(set) * x_bytes + uint32_t(kk) * 2u * kLboB) >> 4), idesc, kk != 0);
+      }
+    };
+    load_x_block(0);
+    if (n_blocks > 1) load_x_block(1);
+    mbar_wait(sm.bar_w, 0);
+    x_landed();
+    if (elect_one()) {
+      for (int c = 0; c < TB; ++c) issue_x_chunk(0, c);
+      umma_commit(sm.bar_xp);
+      if (n_blocks > 1) issue_x_chunk(1, 0);
+    }
+    __syncwarp();
+    int blk = 0, c = 0;  // block / position in block of step t
+    for (int t = 1; t <= T; ++t) {
+      if (++c == TB) { c = 0; ++blk; }
+      if (t == T) break;
+      // Follow the recurrent issuer through shared memory (NOT through the hand-off barrier: a bar.sync also drains
+      // this warp's in-flight cp.async, one HBM round trip on the chain per block).  issued_step >= t also certifies
+      // that every epilogue thread finished step t-1, the last reader of the set this warp starts to overwrite.
+      while (*issued_step < t) {
+      }
+      tcgen05_fence_after();
+      const bool next_blk = blk + 1 < n_blocks;
+      if (c == 0 && next_blk) x_landed();  // block blk+1's inputs (requested one block ago) are in place
+      if (next_blk && elect_one()) {
+        issue_x_chunk(blk + 1, c);
+        if (c == TB - 1) umma_commit(sm.bar_xp + ((blk + 1) & 1));
+      }
+      __syncwarp();
+      if (c == 1 && blk + 2 < n_blocks) {
+        // block blk's projection is complete (its inputs are dead): fetch block blk+2 into the same buffer
+        mbar_wait(sm.bar_xp + (blk & 1), (blk >> 1) & 1);
+        load_x_block(blk + 2);
+      }
     }
   } else {
     // ================= epilogue: thread = (hidden unit u, half of the batch slots) =================
@@ -262,9 +384,10 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     float bias[4], c[NVT];
     const float* xring = reinterpret_cast<const float*>(sm.ring);  // [4 stages][NV rows][4H] filled by the TMA producer
 #pragma unroll
-    for (int g = 0; g < 4; ++g) bias[g] = active ? b_hh[g * H + u] : 0.f;
+    for (int g = 0; g < 4; ++g) bias[g] = active ? (b_hh[g * H + u] + (FX ? b_ih[g * H + u] : 0.f)) : 0.f;
 #pragma unroll
     for (int j = 0; j < NVT; ++j) c[j] = 0.f;
+    int xblk = 0, xtt = 0;  // FX: Xp block / timestep within the block of step t
     bool valid[NVT];
 #pragma unroll
     for (int j = 0; j < NVT; ++j) valid[j] = active && (b0 + jb + j < B);
@@ -282,9 +405,19 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     }
     for (int t = 0; t < T; ++t) {
      {
-      mbar_wait(sm.bar_pf + (t & (kPfStages - 1)), (t / kPfStages) & 1);  // Xp rows of step t have landed (long ago)
       float pre[4][NVT];
-      {
+      uint32_t xr[4][NVT];
+      if constexpr (FX) {
+        if (xtt == 0) {
+          mbar_wait(sm.bar_xp + (xblk & 1), (xblk >> 1) & 1);  // this block's x_t W_ih^T is in tensor memory
+          tcgen05_fence_after();
+        }
+        const uint32_t xaddr = lane_addr + kXpCol0 + uint32_t(xblk & 1) * 64u + uint32_t(xtt * NV);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld<NVT>(xaddr + g * kNslots, xr[g]);  // waited for together with the accumulators
+        if (++xtt == TB) { xtt = 0; ++xblk; }
+      } else {
+        mbar_wait(sm.bar_pf + (t & (kPfStages - 1)), (t / kPfStages) & 1);  // Xp rows of step t have landed (long ago)
         const float* src = xring + size_t(t & (kPfStages - 1)) * NV * 4 * H + u;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -304,10 +437,24 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
         tmem_ld_wait();
         tcgen05_fence_before();  // our TMEM reads are ordered before the MMAs the next hand-off releases
         if (do_prof) prof[t * 8 + 1] = clock64();
+        if constexpr (FX) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int j = 0; j < NVT; ++j) pre[g][j] = (__uint_as_float(xr[g][j]) + bias[g]) + __uint_as_float(r[g][j]);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int j = 0; j < NVT; ++j) pre[g][j] += __uint_as_float(r[g][j]);
+        }
+      } else if constexpr (FX) {
+        tmem_ld_wait();
+        tcgen05_fence_before();
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int j = 0; j < NVT; ++j) pre[g][j] += __uint_as_float(r[g][j]);
+          for (int j = 0; j < NVT; ++j) pre[g][j] = __uint_as_float(xr[g][j]) + bias[g];
       }
       float gi[NVT], gf[NVT], gg[NVT], go[NVT];
       __nv_bfloat16 hb[NVT];
@@ -581,6 +728,13 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
 // ------------------------------------------------------------------------------------------------ host side
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 constexpr size_t kWimgBytes = size_t(4) * 128 * 64 * 4;  // TMEM image of the resident weight operand
+constexpr size_t kWihImgBytes = size_t(4) * 128 * 128 * 2;  // shared-memory image of W_ih (fused input projection, I <= 128)
+
+// the recurrence computes x_t W_ih^T itself when the input fits the resident shared-memory operand
+static bool fused_projection(int I) {
+  static const bool off = [] { const char* e = getenv("CSN_LSTM_NO_FUSED_X"); return e && e[0] == '1'; }();
+  return !off && I <= 128 && I % 8 == 0;
+}
 
 static int pick_nv(int B) {
   // smallest batch tile that still fills the machine: per-step latency falls with NV (fewer MUFU ops per SM)
@@ -607,7 +761,7 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
   }
   const size_t tb = size_t(T) * B;
   *reserve = align256(tb * 4 * H * 2) + align256(tb * H * 4);
-  const size_t wf = align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2) + kWimgBytes;
+  const size_t wf = align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2) + kWimgBytes + kWihImgBytes;
   const size_t wb = align256(tb * 4 * H * 2) + align256(size_t(4) * H * I * 2) + kWimgBytes;
   *workspace = wf > wb ? wf : wb;
   return CSN_OK;
@@ -615,16 +769,37 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
 
 static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (bring-up only)
 
+struct FusedX {  // fused input projection operands (x == nullptr: read the precomputed Xp instead)
+  const __nv_bfloat16* x;
+  const uint8_t* wih_img;
+  const float* b_ih;
+  int I, KI;
+};
+
 template <int NV, int KSTEPS>
 static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
-                      float* c_out, int T, int B, int H, int KP, cudaStream_t s) {
+                      float* c_out, int T, int B, int H, int KP, const FusedX& fx, cudaStream_t s) {
+  if (fx.x) {
+    // operand + barriers + two x blocks + W_ih image
+    const size_t smem = size_t(KP / 8) * kLboB + 128 + 2 * size_t(fx.KI / 8) * kLboB + size_t(4) * 128 * fx.KI * 2;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      CSN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<NV, KSTEPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    lstm_fwd_tc_kernel<NV, KSTEPS, true><<<ceil_div(B, NV), kRecThreadsBwd, smem, s>>>(
+        nullptr, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf, 0u, fx.x, fx.wih_img, fx.b_ih, fx.I, fx.KI);
+    CSN_LAUNCH_CHECK();
+    return CSN_OK;
+  }
   const size_t smem = size_t(KP / 8) * kLboB + 128 + size_t(kPfStages) * NV * 4 * H * 4 + 128;  // operand + barriers + Xp ring
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
-    CSN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<NV, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CSN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<NV, KSTEPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  lstm_fwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreads, smem, s>>>(xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf, 0u);
+  lstm_fwd_tc_kernel<NV, KSTEPS, false><<<ceil_div(B, NV), kRecThreads, smem, s>>>(
+      xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf, 0u, nullptr, nullptr, nullptr, 0, 16);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
@@ -656,9 +831,18 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   __nv_bfloat16* wih_bf = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 4));
   __nv_bfloat16* gates = reinterpret_cast<__nv_bfloat16*>(reserve);
   float* c_out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(reserve) + align256(tb * 4 * H * 2));
-  CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
-  // hoisted input projection: Xp[T*B, 4H] = x[T*B, I] . W_ih[4H, I]^T + b_ih  (fp32 out)
-  CSN_TRY(csn_gemm_bf16_tc(0, 1, (int)tb, 4 * H, I, x, I, wih_bf, I, xp, 4 * H, CSN_F32, b_ih, 0, 1, s));
+  FusedX fx{nullptr, nullptr, nullptr, 0, 16};
+  if (fused_projection(I)) {
+    uint8_t* img = reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2) + kWimgBytes;
+    const int KI = ceil_div(I, 16) * 16;
+    pack_wih_smem_image_kernel<<<ceil_div(4 * 128 * KI, 256), 256, 0, s>>>(w_ih, reinterpret_cast<__nv_bfloat16*>(img), H, I, KI);
+    CSN_LAUNCH_CHECK();
+    fx = FusedX{reinterpret_cast<const __nv_bfloat16*>(x), img, b_ih, I, KI};
+  } else {
+    CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
+    // hoisted input projection: Xp[T*B, 4H] = x[T*B, I] . W_ih[4H, I]^T + b_ih  (fp32 out)
+    CSN_TRY(csn_gemm_bf16_tc(0, 1, (int)tb, 4 * H, I, x, I, wih_bf, I, xp, 4 * H, CSN_F32, b_ih, 0, 1, s));
+  }
   const int nv = pick_nv(B);
   __nv_bfloat16* g = training ? gates : nullptr;
   float* c = training ? c_out : nullptr;
@@ -670,9 +854,9 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   // hidden 128 / 96 / 64 get compile-time K-step counts (predicate-free MMA issue); other sizes take the runtime path
 #define CSN_FWD(KS)                                                                  \
   do {                                                                               \
-    if (nv == 2) return launch_fwd<2, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, s); \
-    if (nv == 4) return launch_fwd<4, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, s); \
-    return launch_fwd<8, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, s);              \
+    if (nv == 2) return launch_fwd<2, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, s); \
+    if (nv == 4) return launch_fwd<4, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, s); \
+    return launch_fwd<8, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, s);              \
   } while (0)
   if (KP == 128) CSN_FWD(8);
   if (KP == 96) CSN_FWD(6);
