@@ -304,10 +304,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    for e_, f_ in zip(eeg, feats):  # resident batches are read in place by their own captured graph
+        step.register_inputs(e_, f_)
+
     # ---------------- device-resident throughput (`value`) ----------------
     # The step runs as one replayed CUDA graph (DistillTrainStep default).  Warm-up covers the eager first call and
     # the capture.
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, NB + 1)):  # first call is eager; every resident batch gets its capture here
         step.step(eeg[i % NB], feats[i % NB], epoch=0)
     barrier()
     sampler = ClockSampler(torch, local) if rank == 0 else None
@@ -382,6 +385,8 @@ def main():
     d_eeg = [torch.empty_like(eeg[0]) for _ in range(2)]
     d_feat = [torch.empty_like(feats[0]) for _ in range(2)]
     h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+    for s_ in range(2):  # the loader's double buffer: read in place by the step
+        step.register_inputs(d_eeg[s_], d_feat[s_])
     copy_stream = torch.cuda.Stream()
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]

@@ -26,6 +26,7 @@ SIGNATURES = {
     "csn_btc_to_tbc": [_vp, _vp, _i, _i, _i, _i, _vp],
     "csn_cast": [_vp, _i, _vp, _i, _sz, _vp],
     "csn_gemm_f32": [_i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _f, _vp, _i, _vp, _i, _vp],
+    "csn_gemm_f32_rowsum": [_i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _f, _vp, _i, _vp, _i, _vp, _i, _vp],
     "csn_colsum_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
     "csn_scale_f32": [_vp, _sz, _vp, _f, _vp],
     "csn_act_fwd": [_vp, _vp, _sz, _i, _vp],

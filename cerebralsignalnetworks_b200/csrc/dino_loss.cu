@@ -562,6 +562,145 @@ static int dispatch_loss_staged(int per_thread, const LossParams& p, int cs, int
   return launch_loss_staged<8, ALLSAME>(p, cs, S, s);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Narrow heads (K <= 1024: the 384 / 768-d DINOv2 feature targets of LstmDistillFromDinoV2Train.py): ONE WARP per
+// batch row, values strided over the lanes (coalesced 128-byte loads), every row statistic is a warp-shuffle
+// reduction -- no shared-memory staging, no block or cluster barrier on the row path.  Same log2-domain arithmetic
+// as the staged kernel.  The centre statistics of the CTA's rows are folded in shared memory first (one atomic per
+// column per CTA instead of one per row).
+constexpr int kRowWarps = 8;
+
+template <int EPT>
+__global__ void __launch_bounds__(kRowWarps * 32) dino_loss_rowwarp_kernel(const LossParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * kRowWarps + warp;
+  const bool row_ok = b < p.B;
+  const int K = p.K;
+  __shared__ float loss_part[kRowWarps];
+  extern __shared__ float bc_s[];  // [kRowWarps][K] (shared-centre modes only)
+  const float ts = p.inv_tau_t * kLog2e, ss = p.inv_tau_s * kLog2e;
+  float loss_acc = 0.f;
+  float bc[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) bc[i] = 0.f;
+
+  if (row_ok) {
+    float q[kMaxVt][EPT];
+    const float* cbase = p.center + (p.center_rows > 1 ? size_t(b) * K : 0);
+#pragma unroll
+    for (int g = 0; g < kMaxVt; ++g) {
+      if (g < p.Vt) {
+        const float* trow = p.teacher + (size_t(g) * p.B + b) * K;
+        float mt = kNegBig;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          const int k = lane + 32 * i;
+          if (k < K) {
+            const float t = __ldcs(trow + k);
+            bc[i] += t;
+            q[g][i] = (t - __ldg(cbase + k)) * ts;
+            mt = fmaxf(mt, q[g][i]);
+          } else {
+            q[g][i] = kNegBig;
+          }
+        }
+        const float m = warp_max(mt);
+        float z = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          q[g][i] = ex2_(q[g][i] - m);
+          z += q[g][i];
+        }
+        const float inv_z = __fdividef(1.f, warp_sum(z));
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) q[g][i] *= inv_z;
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) q[g][i] = 0.f;
+      }
+    }
+    if (p.mode == CSN_DINO_MULTICROP_REF) {  // per-row centre statistics (reference quirk Q3): plain stores
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        const int k = lane + 32 * i;
+        if (k < K) p.batch_center[size_t(b) * K + k] = bc[i];
+      }
+    }
+    for (int v = 0; v < p.Vs; ++v) {
+      const unsigned mask = p.mask[v];
+      float* gout = p.d_student + (size_t(v) * p.B + b) * K;
+      if (mask == 0) {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          const int k = lane + 32 * i;
+          if (k < K) __stcs(gout + k, 0.f);
+        }
+        continue;
+      }
+      const float w0 = (mask & 1u) ? 1.f : 0.f, w1 = (mask & 2u) ? 1.f : 0.f;
+      const float W = w0 + w1;
+      const float* srow = p.student + (size_t(v) * p.B + b) * K;
+      float e[EPT];
+      float mt = kNegBig, d = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        const int k = lane + 32 * i;
+        e[i] = (k < K) ? __ldcs(srow + k) * ss : kNegBig;
+        mt = fmaxf(mt, e[i]);
+        d = fmaf(fmaf(w1, q[1][i], w0 * q[0][i]), e[i], d);
+      }
+      const float m = warp_max(mt);
+      float z = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        e[i] = ex2_(e[i] - m);
+        z += e[i];
+      }
+      z = warp_sum(z);
+      d = warp_sum(d);
+      loss_acc += p.coef * kLn2 * (W * (m + lg2_(z)) - d);
+      const float A = W * __fdividef(1.f, z);
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        const int k = lane + 32 * i;
+        if (k < K) __stcs(gout + k, p.grad_coef * fmaf(e[i], A, -fmaf(w1, q[1][i], w0 * q[0][i])));
+      }
+    }
+  }
+  // ---- CTA-level folds: loss (one atomic per CTA) and shared-centre statistics (one atomic per column per CTA) ----
+  if (lane == 0) loss_part[warp] = loss_acc;
+  if (p.mode != CSN_DINO_MULTICROP_REF) {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) bc_s[warp * K + k] = bc[i];  // zero for rows past the batch
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kRowWarps; ++w) t += loss_part[w];
+    atomicAdd(p.loss, t);
+  }
+  if (p.mode != CSN_DINO_MULTICROP_REF) {
+    for (int k = threadIdx.x; k < K; k += kRowWarps * 32) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) t += bc_s[w * K + k];
+      atomicAdd(p.batch_center + k, t);
+    }
+  }
+}
+
+template <int EPT>
+static int launch_loss_rowwarp(const LossParams& p, cudaStream_t s) {
+  const size_t smem = (p.mode != CSN_DINO_MULTICROP_REF) ? size_t(kRowWarps) * p.K * 4 : 0;
+  dino_loss_rowwarp_kernel<EPT><<<ceil_div(p.B, kRowWarps), kRowWarps * 32, smem, s>>>(p);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
 template <int VEC, int NITER>
 static int launch_loss(const LossParams& p, int cs, cudaStream_t s) {
   cudaLaunchConfig_t cfg{};
@@ -632,6 +771,15 @@ extern "C" int csn_dino_loss_fwd_bwd(const float* student, const float* teacher,
 
   cudaStream_t s = as_stream(stream);
   CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+
+  static const bool no_rowwarp = [] { const char* e = getenv("CSN_LOSS_NO_ROWWARP"); return e && e[0] == '1'; }();
+  if (K <= 1024 && !no_rowwarp) {  // narrow heads: one warp per batch row
+    p.Kc = K;
+    if (K <= 128) return launch_loss_rowwarp<4>(p, s);
+    if (K <= 256) return launch_loss_rowwarp<8>(p, s);
+    if (K <= 512) return launch_loss_rowwarp<16>(p, s);
+    return launch_loss_rowwarp<32>(p, s);
+  }
 
   const bool aligned = ((reinterpret_cast<uintptr_t>(student) | reinterpret_cast<uintptr_t>(teacher) |
                          reinterpret_cast<uintptr_t>(d_student) | reinterpret_cast<uintptr_t>(batch_center)) & 15) == 0;

@@ -79,8 +79,13 @@ def linear_bwd(x, w, pre, dy, act=ACT_NONE, compute_dtype=torch.float32, need_dx
         dw = ops.gemm_bf16(dpre_b, x_b, True, False, out=dw_out, split_k=max(1, min(16, M // 256)))
         dx = ops.gemm_bf16(dpre_b, ops.cast(w, torch.bfloat16), False, False) if need_dx else None
     else:
-        dw = ops.gemm_f32(dpre, x, True, False, out=dw_out)
+        # fp32: the bias gradient rides on the dW product (row sums of dY^T from the same shared-memory strip)
+        db = None
+        if has_bias:
+            db = db_out if db_out is not None else torch.empty((dpre.shape[1],), dtype=torch.float32, device=dpre.device)
+        dw = ops.gemm_f32(dpre, x, True, False, out=dw_out, rowsum=db)
         dx = ops.gemm_f32(dpre, w, False, False) if need_dx else None
+        return dx, dw, db
     db = ops.colsum(dpre, out=db_out) if has_bias else None
     return dx, dw, db
 

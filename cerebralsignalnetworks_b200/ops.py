@@ -81,8 +81,9 @@ def cast(x, dtype):
 
 
 # ------------------------------------------------------------------------------------------------ dense
-def gemm_f32(a, b, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, out=None, alpha=1.0, beta=0.0):
-    """out[M,N] = alpha * op(a) @ op(b) + beta*out (+bias)(act).  op(a) [M,K], op(b) [K,N]."""
+def gemm_f32(a, b, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, out=None, alpha=1.0, beta=0.0, rowsum=None):
+    """out[M,N] = alpha * op(a) @ op(b) + beta*out (+bias)(act).  op(a) [M,K], op(b) [K,N].
+    rowsum: optional [M] tensor that receives the row sums of op(a) from the same pass (bias gradient of dW = dY^T X)."""
     _chk(a, torch.float32, "a"); _chk(b, torch.float32, "b")
     M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
     K2, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
@@ -91,6 +92,13 @@ def gemm_f32(a, b, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, out=No
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     _chk(out, torch.float32, "out")
+    if rowsum is not None:
+        _chk(rowsum, torch.float32, "rowsum")
+        if rowsum.numel() != M:
+            raise _lib.CsnError("gemm_f32: rowsum must have %d elements" % M)
+        call("csn_gemm_f32_rowsum", int(trans_a), int(trans_b), M, N, K, float(alpha), _p(a), a.shape[1], _p(b),
+             b.shape[1], float(beta), _p(out), N, _p(bias), int(act), _p(rowsum), 0, _stream())
+        return out
     call("csn_gemm_f32", int(trans_a), int(trans_b), M, N, K, float(alpha), _p(a), a.shape[1], _p(b), b.shape[1],
          float(beta), _p(out), N, _p(bias), int(act), _stream())
     return out

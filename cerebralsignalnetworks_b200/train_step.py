@@ -62,6 +62,9 @@ class DistillTrainStep:
         self._graph = None
         self._graph_tau = None
         self._static = None
+        self._resident = {}        # (eeg ptr, teacher ptr) -> (eeg, teacher): buffers with their own captured graph
+        self._resident_graphs = {}  # (eeg ptr, teacher ptr, tau) -> (graph, loss tensor)
+        self._pool = None
         self._warm = False
         self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side Adam step count
         self._adam_consts = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -156,7 +159,35 @@ class DistillTrainStep:
             self._static = (torch.empty_like(like_eeg), torch.empty_like(like_feats))
         return self._static
 
+    def register_inputs(self, eeg_bct, teacher_feats):
+        """Declare a RESIDENT (eeg, teacher) buffer pair that step() will be handed again and again (a loader's
+        double buffer, a device-resident dataset shard).  Such a pair gets its own captured graph, so a replay reads
+        the trials in place instead of first copying them into the graph's static input buffers (57.7 MB per cfg2
+        step).  All graphs of a step object share one memory pool: they never run concurrently."""
+        if not (eeg_bct.is_contiguous() and teacher_feats.is_contiguous()):
+            raise _lib.CsnError("register_inputs: buffers must be contiguous")
+        self._resident[(eeg_bct.data_ptr(), teacher_feats.data_ptr())] = (eeg_bct, teacher_feats)
+
+    def _capture(self, eeg, teacher, tau_t):
+        torch.cuda.current_stream().synchronize()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self._pool):
+            out = self._run(eeg, teacher, tau_t)
+        return g, out
+
     def _step_graphed(self, eeg_bct, teacher, tau_t):
+        key = (eeg_bct.data_ptr(), teacher.data_ptr())
+        if key in self._resident and self._warm:
+            gkey = key + (tau_t,)
+            hit = self._resident_graphs.get(gkey)
+            if hit is None:
+                if len(self._resident_graphs) >= 64:  # epochs change tau: drop the stale captures
+                    self._resident_graphs.clear()
+                hit = self._resident_graphs[gkey] = self._capture(eeg_bct, teacher, tau_t)
+            hit[0].replay()
+            return hit[1]
         se, st = self.input_buffers(eeg_bct, teacher)
         if se.shape != eeg_bct.shape or st.shape != teacher.shape:
             raise _lib.CsnError("CUDA-graph step: batch shape changed (%s -> %s); build a new DistillTrainStep or pass "
@@ -169,10 +200,7 @@ class DistillTrainStep:
             self._warm = True
             return self._run(se, st, tau_t)
         if self._graph is None or self._graph_tau != tau_t:
-            torch.cuda.current_stream().synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = self._run(se, st, tau_t)
+            g, out = self._capture(se, st, tau_t)
             self._graph, self._graph_tau, self._graph_out = g, tau_t, out
         self._graph.replay()
         return self._graph_out

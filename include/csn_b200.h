@@ -62,6 +62,11 @@ int csn_cast(const void* x, int x_dtype, void* y, int y_dtype, size_t n, void* s
  * (LstmDistillation.py:65-99) in fp32 mode. */
 int csn_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                  const float* B, int ldb, float beta, float* C, int ldc, const float* bias, int act, void* stream);
+/* Same product, plus rowsum[M] (+)= row sums of op(A) from the same pass: with transA=1, A = dY^T this is the bias
+ * gradient that rides on the weight-gradient product dW = dY^T X (autograd of nn.Linear). */
+int csn_gemm_f32_rowsum(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                        const float* B, int ldb, float beta, float* C, int ldc, const float* bias, int act,
+                        float* rowsum, int rowsum_accumulate, void* stream);
 /* out[n] (+)= sum_m x[m, n]   (bias gradients) */
 int csn_colsum_f32(const float* x, float* out, int M, int N, int ldx, int accumulate, void* stream);
 /* y = act(x); dx = dy * act'(x)  (x is the PRE-activation) */

@@ -28,6 +28,28 @@ def test_gemm_f32(ta, tb, M, N, K):
     np.testing.assert_allclose(out.numpy(), ref.float().numpy(), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(256, 384, 128), (384, 128, 256), (256, 128, 384), (20, 68, 4), (36, 200, 512), (16, 64, 36)])
+def test_gemm_f32_resident_strip(ta, tb, M, N, K):
+    """Short-contraction shapes (the projection head and its gradients) take the whole-K-resident kernel
+    (16-byte aligned strips); the row sums of op(A) ride along (bias gradient of dW = dY^T X)."""
+    ops = _ops()
+    a = _mk((K, M) if ta else (M, K), 11)
+    b = _mk((N, K) if tb else (K, N), 12)
+    bias = _mk((N,), 13)
+    opa = (a.t() if ta else a).double()
+    ref = opa @ (b.t() if tb else b).double() + bias.double()
+    rs = torch.full((M,), float("nan"), device="cuda")
+    out = ops.gemm_f32(a.cuda(), b.cuda(), ta, tb, bias=bias.cuda(), rowsum=rs).cpu()
+    np.testing.assert_allclose(out.numpy(), ref.float().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(rs.cpu().numpy(), opa.sum(1).float().numpy(), rtol=1e-4, atol=1e-4)
+    # accumulate into C (beta) and activation epilogue
+    c0 = _mk((M, N), 14)
+    out2 = ops.gemm_f32(a.cuda(), b.cuda(), ta, tb, out=c0.clone().cuda(), alpha=0.5, beta=2.0).cpu()
+    ref2 = 0.5 * (opa @ (b.t() if tb else b).double()) + 2.0 * c0.double()
+    np.testing.assert_allclose(out2.numpy(), ref2.float().numpy(), rtol=1e-4, atol=1e-4)
+
+
 @pytest.mark.parametrize("a_mn,b_mn", [(0, False), (1, False), (0, True), (1, True), (2, False), (2, True)])
 @pytest.mark.parametrize("N,K", [(16, 16), (16, 128), (64, 64), (256, 32)])
 def test_umma_tile_descriptors(a_mn, b_mn, N, K):

@@ -165,6 +165,33 @@ def test_cuda_graph_step_matches_eager_steps():
     assert torch.allclose(runs[True][2], runs[False][2], rtol=1e-6, atol=1e-8)
 
 
+def test_resident_input_graphs_match_eager_steps():
+    """register_inputs(): rotating resident buffers each replay their own captured graph (trials read in place, no
+    staging copy) and must track eager stepping over the same sequence of batches, including an epoch change."""
+    import cerebralsignalnetworks_b200 as csn
+    from oracle.filters import design_bandpass_sos
+    sos = design_bandpass_sos(5.0, 95.0, 1000.0, 4)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bufs = [(torch.randn(4, 16, 48, device="cuda", generator=g), torch.randn(4, 24, device="cuda", generator=g)) for _ in range(3)]
+    runs = {}
+    for resident in (False, True):
+        torch.manual_seed(11)
+        model = csn.Model(16, 32, 1, 24, include_top=False, compute_dtype=torch.float32).cuda()
+        crit = csn.DINOLoss(24, 1, 1.5, 0.22, 5, 10).cuda()
+        step = csn.DistillTrainStep(model, crit, lr=1e-2, sos=sos, use_cuda_graph=resident)
+        if resident:
+            for e, f in bufs:
+                step.register_inputs(e, f)
+        losses = [float(step.step(*bufs[i % 3], epoch=0 if i < 7 else 1)) for i in range(10)]
+        if resident:
+            assert len(step._resident_graphs) == 6  # 3 buffers x 2 teacher temperatures
+        runs[resident] = (losses, {n: p.detach().clone() for n, p in model.named_parameters()}, crit.center.clone())
+    np.testing.assert_allclose(runs[True][0], runs[False][0], rtol=1e-5)
+    for n in runs[False][1]:
+        assert torch.allclose(runs[True][1][n], runs[False][1][n], rtol=1e-5, atol=1e-7), n
+    assert torch.allclose(runs[True][2], runs[False][2], rtol=1e-6, atol=1e-8)
+
+
 def test_fused_adam_groups_clip_and_ema_match_torch(golden):
     """FusedAdam (AdamW, get_params_groups split, per-parameter clipping, frozen group) + EMATeacher vs torch."""
     import cerebralsignalnetworks_b200 as csn
