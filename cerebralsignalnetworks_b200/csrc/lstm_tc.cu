@@ -17,6 +17,7 @@
 //
 // The serial chain (T steps) cannot be parallelised; what this design optimises is the per-step latency:
 // no HBM round trip, no grid-wide sync, one mbarrier hand-off in each direction per step.
+#include <mutex>
 #include <type_traits>
 
 #include "tc.cuh"
@@ -769,6 +770,31 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
 
 static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (bring-up only)
 
+// internal helper stream (one per device) for fork / join inside a C-ABI call; nullptr when disabled or on failure
+struct SideStream {
+  cudaStream_t st;
+  cudaEvent_t fork, join;
+};
+static SideStream* side_stream() {
+  static const bool off = [] { const char* e = getenv("CSN_NO_SIDE_STREAM"); return e && e[0] == '1'; }();
+  if (off) return nullptr;
+  static SideStream table[64];
+  static bool made[64] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!made[dev]) {
+    SideStream ss{};
+    if (cudaStreamCreateWithFlags(&ss.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    table[dev] = ss;
+    made[dev] = true;
+  }
+  return &table[dev];
+}
+
 struct FusedX {  // fused input projection operands (x == nullptr: read the precomputed Xp instead)
   const __nv_bfloat16* x;
   const uint8_t* wih_img;
@@ -899,14 +925,28 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   else if (KP == 64) CSN_BWD(4);
   else CSN_BWD(0);
 #undef CSN_BWD
-  // dW_ih[4H, I] = dG^T . x ; dW_hh[4H, H] = dG[1:]^T . h_seq[:-1]  (contraction over time*batch, split-K)
+  // dW_ih[4H, I] = dG^T . x ; dW_hh[4H, H] = dG[1:]^T . h_seq[:-1]  (contraction over time*batch, split-K).
+  // Both products stream the same dG (the dominant operand, 115 MB at cfg2): they run SIDE BY SIDE on half the SMs
+  // each (fork / join on an internal stream, also valid under stream capture), so the second reader finds dG in L2.
   const int sms = sm_count();
   const int tiles_ih = ceil_div(4 * H, 128) * ceil_div(I, 128), tiles_hh = ceil_div(4 * H, 128) * ceil_div(H, 128);
+  SideStream* side = (T > 1) ? side_stream() : nullptr;
+  const int share = side ? 2 : 1;
+  if (side) {
+    CSN_CUDA(cudaEventRecord(side->fork, s));
+    CSN_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+  }
   CSN_TRY(csn_gemm_bf16_tc(1, 0, 4 * H, I, (int)tb, dG, 4 * H, x, I, dw_ih, I, CSN_F32, nullptr, accumulate,
-                           max(1, sms / tiles_ih), s));
+                           max(1, sms / (share * tiles_ih)), s));
   if (T > 1) {
-    CSN_TRY(csn_gemm_bf16_tc(1, 0, 4 * H, H, (int)(tb - B), dG + size_t(B) * 4 * H, 4 * H, h_seq, H, dw_hh, H, CSN_F32,
-                             nullptr, accumulate, max(1, sms / tiles_hh), s));
+    cudaStream_t s2 = side ? side->st : s;
+    int r2 = csn_gemm_bf16_tc(1, 0, 4 * H, H, (int)(tb - B), dG + size_t(B) * 4 * H, 4 * H, h_seq, H, dw_hh, H, CSN_F32,
+                              nullptr, accumulate, max(1, sms / (share * tiles_hh)), s2);
+    if (side) {  // always rejoin (a capture must not end with a dangling fork)
+      CSN_CUDA(cudaEventRecord(side->join, side->st));
+      CSN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+    }
+    CSN_TRY(r2);
   } else if (!accumulate) {
     CSN_CUDA(cudaMemsetAsync(dw_hh, 0, size_t(4) * H * H * 4, s));
   }

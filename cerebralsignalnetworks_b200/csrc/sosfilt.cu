@@ -190,6 +190,120 @@ __global__ void __launch_bounds__(128) sosfilt_stream_kernel(const float* __rest
   }
 }
 
+
+// ------------------------------------------------------------------------------------- causal, lean fast path
+// ncu on the general kernel above at cfg2 (profiles/ncu_full_r01d.md): 15.1 M warp instructions, 56 % issue-slot
+// utilisation, no dominant stall -- the kernel is INSTRUCTION bound, and only 20 of its 33 instructions per sample
+// are the biquad FMAs; the rest is generic index / predicate arithmetic around the cp.async issue (250 instructions
+// per 32-sample chunk) and the tile store (200).  This variant serves the common case (16-byte aligned rows, full
+// blocks of 32 series, time-major bf16/fp32 or channel-major fp32 output) with running pointers, a predicate-free
+// body for full chunks and one warp per block (warp-level barriers only): ~24 instructions per sample.
+template <int NSEC, typename OutT, bool TIME_MAJOR>
+__global__ void __launch_bounds__(32) sosfilt_warp_kernel(const float* __restrict__ x, OutT* __restrict__ y,
+                                                         const SosCoef coef, int T, long long N) {
+  constexpr int R = 32;
+  extern __shared__ __align__(16) float smem[];
+  float* in_tile = smem;                        // [kStages][R][kRS]
+  float* out_tile = smem + kStages * R * kRS;   // [kTC][R]   (time-major output only)
+  const int lane = threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * R;
+  const int n_chunks = (T + kTC - 1) / kTC;
+
+  float s1[NSEC], s2[NSEC];
+#pragma unroll
+  for (int k = 0; k < NSEC; ++k) s1[k] = s2[k] = 0.f;
+
+  // cp.async of a chunk: lane -> (row lane/8 + 4 j, 16-byte column lane%8), j = 0..7
+  const int row8 = lane >> 3, c4 = lane & 7;
+  const float* src = x + size_t(r0 + row8) * T + c4 * 4;   // advanced by kTC floats per issued chunk
+  const size_t src_jstride = size_t(4) * T;
+  const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(in_tile + row8 * kRS + c4 * 4);
+  int t_issue = c4 * 4;                                     // first sample this lane fetches in the next chunk
+  auto issue_load = [&](int buf) {
+    const uint32_t d = dst0 + uint32_t(buf) * (R * kRS * 4);
+    const int bytes = (t_issue < T) ? 16 : 0;               // T % 4 == 0: a 16-byte piece is in range or not at all
+    const float* s = (t_issue < T) ? src : x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d + uint32_t(j) * (4 * kRS * 4)),
+                   "l"(s + (bytes ? j * src_jstride : 0)), "r"(bytes));
+    cp_async_commit();
+    src += kTC;
+    t_issue += kTC;
+  };
+
+  // store side
+  OutT* yrow = nullptr;        // channel-major: this lane's piece of row (row8 + 4 j)
+  OutT* ytm = nullptr;         // time-major: 8 consecutive series (lane % 4) of sample (lane / 4 + 8 i)
+  if constexpr (TIME_MAJOR) ytm = y + size_t(lane >> 2) * N + r0 + (lane & 3) * 8;
+  else yrow = y + size_t(r0 + row8) * T + c4 * 4;
+
+  for (int c = 0; c < kStages - 1; ++c) {
+    if (c < n_chunks) issue_load(c); else cp_async_commit();
+  }
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const int buf = chunk % kStages;
+    cp_async_wait<kStages - 2>();
+    __syncwarp();  // tile `buf` visible to every lane; everyone is done with the tile of chunk-1 and with out_tile
+    if (chunk + kStages - 1 < n_chunks) issue_load((chunk + kStages - 1) % kStages);
+    else cp_async_commit();
+
+    float* row = in_tile + buf * R * kRS + lane * kRS;
+#pragma unroll
+    for (int q = 0; q < kTC / 4; ++q) {
+      float4 v = *reinterpret_cast<float4*>(row + q * 4);
+      v.x = biquad_cascade<NSEC>(v.x, s1, s2, coef);
+      v.y = biquad_cascade<NSEC>(v.y, s1, s2, coef);
+      v.z = biquad_cascade<NSEC>(v.z, s1, s2, coef);
+      v.w = biquad_cascade<NSEC>(v.w, s1, s2, coef);
+      if constexpr (TIME_MAJOR) {
+        out_tile[(q * 4 + 0) * R + lane] = v.x;
+        out_tile[(q * 4 + 1) * R + lane] = v.y;
+        out_tile[(q * 4 + 2) * R + lane] = v.z;
+        out_tile[(q * 4 + 3) * R + lane] = v.w;
+      } else {
+        *reinterpret_cast<float4*>(row + q * 4) = v;
+      }
+    }
+    __syncwarp();
+
+    const int t0 = chunk * kTC;
+    if constexpr (TIME_MAJOR) {
+      const float* ot = out_tile + (lane >> 2) * R + (lane & 3) * 8;
+      const int tl = t0 + (lane >> 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (tl + 8 * i < T) {
+          const float4 a = *reinterpret_cast<const float4*>(ot + i * 8 * R);
+          const float4 b = *reinterpret_cast<const float4*>(ot + i * 8 * R + 4);
+          OutT* dst = ytm + size_t(8 * i) * N;
+          if constexpr (sizeof(OutT) == 4) {
+            *reinterpret_cast<float4*>(dst) = a;
+            *reinterpret_cast<float4*>(dst + 4) = b;
+          } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(dst) = o;
+          }
+        }
+      }
+      ytm += size_t(kTC) * N;
+    } else {
+      const float* st = in_tile + buf * R * kRS + row8 * kRS + c4 * 4;
+      if (t0 + c4 * 4 < T) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(yrow) + j * src_jstride) =
+              *reinterpret_cast<const float4*>(st + j * 4 * kRS);
+      }
+      yrow += kTC;
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------- zero phase
 template <int NSEC, typename OutT>
 __global__ void __launch_bounds__(32) sosfiltfilt_kernel(const float* __restrict__ x, OutT* __restrict__ y,
@@ -252,6 +366,21 @@ template <int NSEC, typename OutT>
 static int launch_sosfilt(const float* x, void* y, const SosCoef& coef, int B, int C, int T, int zero_phase,
                           int layout, cudaStream_t s) {
   const long long n_series = (long long)B * C;
+  static const bool no_fast = [] { const char* e = getenv("CSN_FILTER_NO_FAST"); return e && e[0] == '1'; }();
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (!zero_phase && !no_fast && aligned16 && T % 4 == 0 && n_series % 32 == 0 &&
+      (layout == CSN_LAYOUT_TBC || (layout == CSN_LAYOUT_BCT && sizeof(OutT) == 4))) {
+    const unsigned grid = (unsigned)(n_series / 32);
+    if (layout == CSN_LAYOUT_TBC) {
+      const size_t smem = size_t(kStages) * 32 * kRS * 4 + size_t(kTC) * 32 * 4;
+      sosfilt_warp_kernel<NSEC, OutT, true><<<grid, 32, smem, s>>>(x, (OutT*)y, coef, T, n_series);
+    } else {
+      const size_t smem = size_t(kStages) * 32 * kRS * 4;
+      sosfilt_warp_kernel<NSEC, OutT, false><<<grid, 32, smem, s>>>(x, (OutT*)y, coef, T, n_series);
+    }
+    CSN_LAUNCH_CHECK();
+    return CSN_OK;
+  }
   if (!zero_phase) {
     // rows per block: keep >= 4 blocks per SM in flight when the problem allows, warps of 32 series
     int R = 64;
