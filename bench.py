@@ -479,6 +479,7 @@ def main():
                           "frac": (loss_gbs / peaks["hbm_gbs"]) if loss_gbs else None, "traffic": None, "peak_source": peaks["source"]},
         "stages_ms": stages,
         "step_submission": "cuda_graph_replay",
+        "dp_exchange": step.dp_exchange,
         "loss": final_loss,
     }
     if not args.no_cpu_baseline:

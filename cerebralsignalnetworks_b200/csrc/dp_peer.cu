@@ -1,0 +1,183 @@
+// Data-parallel gradient exchange fused into the optimiser: every rank reads the flat [gradients | centre sums] buffer
+// of EVERY rank straight over NVLink (peer-mapped symmetric memory), sums in rank order -- so all replicas compute
+// bit-identical sums -- and applies Adam + the DINO centre EMA in the same pass.  Replaces ncclAllReduce + adam +
+// centre-EMA launches of the step (DDP gradient averaging, LstmDistillation.py:445; update_center all-reduce,
+// LstmDistillation.py:154-156).  Cross-rank ordering uses epoch flags in peer memory (system-scope release/acquire):
+//   READY[src] = t : rank src finished writing its step-t gradients        (set at the start of the fused kernel)
+//   DONE[src]  = t : rank src finished reading everybody's step-t gradients (set by its last CTA)
+// A rank may overwrite its gradient buffer for step t+1 only after every DONE[src] >= t (csn_dp_wait_done_zero,
+// which also zeroes the centre-sum tail in place of a memset).  Epochs come from the device-side Adam step counter,
+// so the kernels are CUDA-graph replay safe.
+#include "common.cuh"
+
+namespace csn {
+
+constexpr int kMaxWorld = 8;
+constexpr int kFlagReady = 0, kFlagDone = kMaxWorld;  // uint32 slots in each rank's flag block (>= 2 * kMaxWorld words)
+
+struct PeerSet {
+  const float* grad[kMaxWorld];
+  unsigned* flags[kMaxWorld];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {  // never served from a stale local cache line
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer_f(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *flag >= target; a peer that never arrives (crashed rank) traps after ~10 s instead of hanging the GPU
+__device__ __forceinline__ void wait_flag_ge(const unsigned* flag, unsigned target) {
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
+  while ((int)(ld_acquire_sys(flag) - target) < 0) {
+    if ((++spins & 1023u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 10000000000ull) __trap();
+    }
+  }
+}
+
+__global__ void dp_wait_done_zero_kernel(const unsigned* __restrict__ flags_local, int world, const int* __restrict__ step_dev,
+                                         float* __restrict__ zero_ptr, size_t n) {
+  if (threadIdx.x < world) wait_flag_ge(flags_local + kFlagDone + threadIdx.x, (unsigned)*step_dev);
+  __syncthreads();
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) zero_ptr[i] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) dp_adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                          size_t n_param, const PeerSet ps, int world, int rank,
+                                                          float* __restrict__ center, size_t K, float center_momentum,
+                                                          float center_scale, int* __restrict__ step_dev, float lr, float b1,
+                                                          float b2, float eps, float wd, int decoupled, float grad_scale,
+                                                          unsigned* __restrict__ ticket) {
+  __shared__ float s_consts[2];
+  __shared__ int s_last;
+  const int t = *step_dev + 1;  // this step's 1-based count (the counter is advanced by the last CTA)
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(ps.flags[threadIdx.x] + kFlagReady + rank, (unsigned)t);
+  }
+  if (threadIdx.x < world) wait_flag_ge(ps.flags[rank] + kFlagReady + threadIdx.x, (unsigned)t);
+  if (threadIdx.x == 32) {
+    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+    s_consts[0] = (float)((double)lr / bc1);
+    s_consts[1] = (float)(1.0 / sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_consts[0], inv_sqrt_bc2 = s_consts[1];
+
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t n4 = n_param >> 2;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 G[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < world) G[r] = ld_peer_f4(ps.grad[r] + 4 * i);
+    float4 S = G[0];
+#pragma unroll
+    for (int r = 1; r < kMaxWorld; ++r)
+      if (r < world) { S.x += G[r].x; S.y += G[r].y; S.z += G[r].z; S.w += G[r].w; }
+    float4 P = reinterpret_cast<float4*>(p)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i];
+    float4 V = reinterpret_cast<float4*>(v)[i];
+    float* pp = &P.x; float* gg = &S.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gr = gg[j] * grad_scale;
+      if (decoupled) pp[j] *= (1.f - lr * wd); else gr = fmaf(wd, pp[j], gr);
+      mm[j] = b1 * mm[j] + (1.f - b1) * gr;
+      vv[j] = b2 * vv[j] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(vv[j]) * inv_sqrt_bc2 + eps;
+      pp[j] -= step_size * (mm[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+  }
+  // centre EMA over the tail of the exchanged buffer: center = center * mom + (sum over ranks) * scale * (1 - mom)
+  for (size_t k = size_t(blockIdx.x) * blockDim.x + threadIdx.x; k < K; k += stride) {
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < world) sum += ld_peer_f(ps.grad[r] + n_param + k);
+    center[k] = center[k] * center_momentum + sum * center_scale * (1.f - center_momentum);
+  }
+  // last CTA: advance the step counter and tell every rank that this rank is done reading
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(ticket, 1u);
+    s_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) {
+      *ticket = 0u;
+      *step_dev = t;
+    }
+    if (threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(ps.flags[threadIdx.x] + kFlagDone + rank, (unsigned)t);
+    }
+  }
+}
+
+}  // namespace csn
+
+using namespace csn;
+
+extern "C" int csn_dp_wait_done_zero(const void* flags_local, int world, const int* step_counter, float* zero_ptr,
+                                     size_t n, void* stream) {
+  CSN_REQUIRE(flags_local && step_counter, "csn_dp_wait_done_zero: null pointer");
+  CSN_REQUIRE(world >= 1 && world <= kMaxWorld, "csn_dp_wait_done_zero: world must be in [1, %d]", kMaxWorld);
+  const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>(ceil_div<size_t>(n, 256), size_t(sm_count())));
+  dp_wait_done_zero_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned*>(flags_local), world,
+                                                                  step_counter, zero_ptr, zero_ptr ? n : 0);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_dp_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, size_t n_param,
+                                     const void* const* grad_ptrs, void* const* flag_ptrs, int world, int rank,
+                                     float* center, size_t K, float center_momentum, float center_scale,
+                                     int* step_counter, unsigned* ticket, float lr, float beta1, float beta2, float eps,
+                                     float weight_decay, int decoupled, float grad_scale, void* stream) {
+  CSN_REQUIRE(params && exp_avg && exp_avg_sq && grad_ptrs && flag_ptrs && step_counter && ticket,
+              "csn_dp_adam_step_peer: null pointer");
+  CSN_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
+              "csn_dp_adam_step_peer: need 1 <= world <= %d and 0 <= rank < world", kMaxWorld);
+  CSN_REQUIRE(n_param % 4 == 0, "csn_dp_adam_step_peer: parameter count must be a multiple of 4 (flat buffers are padded)");
+  CSN_REQUIRE(K == 0 || center, "csn_dp_adam_step_peer: centre pointer missing");
+  PeerSet ps{};
+  for (int r = 0; r < world; ++r) {
+    CSN_REQUIRE(grad_ptrs[r] && flag_ptrs[r], "csn_dp_adam_step_peer: null peer pointer for rank %d", r);
+    CSN_REQUIRE((reinterpret_cast<uintptr_t>(grad_ptrs[r]) & 15) == 0, "csn_dp_adam_step_peer: peer buffer %d not 16-byte aligned", r);
+    ps.grad[r] = reinterpret_cast<const float*>(grad_ptrs[r]);
+    ps.flags[r] = reinterpret_cast<unsigned*>(flag_ptrs[r]);
+  }
+  CSN_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(exp_avg) |
+                reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, "csn_dp_adam_step_peer: buffers must be 16-byte aligned");
+  // every CTA spins on the READY flags: the whole grid must be resident (<= 8 CTAs of 256 threads per SM)
+  const size_t want = std::max<size_t>(1, ceil_div<size_t>(std::max(n_param / 4, K), 256));
+  const unsigned blocks = (unsigned)std::min<size_t>(want, size_t(sm_count()) * 4);
+  dp_adam_peer_kernel<<<blocks, 256, 0, as_stream(stream)>>>(params, exp_avg, exp_avg_sq, n_param, ps, world, rank, center, K,
+                                                             center_momentum, center_scale, step_counter, lr, beta1, beta2, eps,
+                                                             weight_decay, decoupled, grad_scale, ticket);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}

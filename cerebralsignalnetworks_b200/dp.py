@@ -30,3 +30,33 @@ def allreduce_flat_(flat: torch.Tensor) -> torch.Tensor:
 def split_flat(flat: torch.Tensor, n_param: int, world: int, local_batch: int):
     """-> (mean gradients, batch centre) with the reference's normalisation."""
     return flat[:n_param] / world, flat[n_param:] / (local_batch * world)
+
+
+class PeerExchange:
+    """Peer-mapped flat buffer [gradients | centre sums] + flag block for the fused all-reduce/Adam kernel
+    (csn_dp_adam_step_peer).  torch's symmetric-memory allocator does the plumbing (allocation + exchange of the
+    mappings over the process group's store); the arithmetic and the cross-rank ordering are ours."""
+
+    def __init__(self, n_floats: int, device: torch.device):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if self.world > 8:
+            raise RuntimeError("peer exchange supports up to 8 ranks (one NVSwitch domain)")
+        self.buf = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self._h_buf = symm_mem.rendezvous(self.buf, group)
+        self._h_flags = symm_mem.rendezvous(self.flags, group)
+        self.buf.zero_()
+        self.flags.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier()  # nobody signals before every flag block is zero
+        gp, fp = list(self._h_buf.buffer_ptrs), list(self._h_flags.buffer_ptrs)
+        if len(gp) != self.world or len(fp) != self.world or gp[self.rank] != self.buf.data_ptr():
+            raise RuntimeError("symmetric-memory rendezvous returned an unexpected mapping")
+        self.grad_ptrs = (ctypes.c_void_p * self.world)(*gp)
+        self.flag_ptrs = (ctypes.c_void_p * self.world)(*fp)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)

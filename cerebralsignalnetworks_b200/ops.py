@@ -263,6 +263,26 @@ def adam_step_graph(params, grads, exp_avg, exp_avg_sq, step_counter, consts, lr
          float(grad_scale), _stream())
 
 
+def dp_wait_done_zero(flags_local, world, step_counter, zero_tensor):
+    """Wait (on the stream) until every peer has finished reading this rank's previous gradients, then zero
+    `zero_tensor` (the centre-sum tail of the exchanged buffer)."""
+    call("csn_dp_wait_done_zero", _p(flags_local), int(world), _p(step_counter), _p(zero_tensor),
+         0 if zero_tensor is None else zero_tensor.numel(), _stream())
+
+
+def dp_adam_step_peer(params, exp_avg, exp_avg_sq, grad_ptr_array, flag_ptr_array, world, rank, center,
+                      center_momentum, center_scale, step_counter, ticket, lr, beta1=0.9, beta2=0.999, eps=1e-8,
+                      weight_decay=0.0, decoupled=False, grad_scale=1.0):
+    """Fused peer all-reduce + Adam + centre EMA (see include/csn_b200.h).  grad_ptr_array / flag_ptr_array are
+    ctypes arrays of `world` device pointers (rank order)."""
+    for n, t in (("params", params), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _chk(t, torch.float32, n)
+    call("csn_dp_adam_step_peer", _p(params), _p(exp_avg), _p(exp_avg_sq), params.numel(), grad_ptr_array,
+         flag_ptr_array, int(world), int(rank), _p(center), 0 if center is None else center.numel(),
+         float(center_momentum), float(center_scale), _p(step_counter), _p(ticket), float(lr), float(beta1),
+         float(beta2), float(eps), float(weight_decay), int(decoupled), float(grad_scale), _stream())
+
+
 def ema_update_(dst, src, momentum):
     """dst = momentum * dst + (1 - momentum) * src, in place (flat fp32 buffers)."""
     _chk(dst, torch.float32, "dst"); _chk(src, torch.float32, "src")

@@ -23,7 +23,7 @@ _IDENTITY_SOS = np.array([[1.0, 0.0, 0.0, 1.0, 0.0, 0.0]])
 
 class DistillTrainStep:
     def __init__(self, model, loss, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False,
-                 sos=None, zero_phase=False, use_cuda_graph=True):
+                 sos=None, zero_phase=False, use_cuda_graph=True, dp_exchange="auto"):
         _lib.require_gpu()
         self.model, self.loss = model, loss
         self.lr, self.betas, self.eps = lr, betas, eps
@@ -44,7 +44,20 @@ class DistillTrainStep:
         K = loss.center.shape[-1]
         self.n_param = total
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total + K, dtype=torch.float32, device=dev)  # [grads | sum_b teacher]
+        # [grads | sum_b teacher].  Data parallel: the buffer is peer-mapped so that every rank's fused Adam reads all
+        # ranks' gradients straight over NVLink (dp_exchange "peer"); "nccl" keeps one ncclAllReduce + local kernels;
+        # "auto" tries peer and falls back to nccl when symmetric memory cannot be set up (no P2P / gloo group).
+        self.peer = None
+        if self.world > 1 and dev.type == "cuda" and dp_exchange in ("auto", "peer"):
+            try:
+                self.peer = dp.PeerExchange(total + K, dev)
+            except Exception as exc:  # noqa: BLE001 - report and fall back to the NCCL exchange
+                if dp_exchange == "peer":
+                    raise
+                import warnings
+                warnings.warn("peer gradient exchange unavailable (%s: %s); using ncclAllReduce" % (type(exc).__name__, exc))
+        self.dp_exchange = "peer_fused_adam" if self.peer is not None else ("nccl_allreduce" if self.world > 1 else "single")
+        self.flat_g = self.peer.buf if self.peer is not None else torch.zeros(total + K, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self._grad_views = {}
@@ -118,7 +131,10 @@ class DistillTrainStep:
         act = ACT_RELU if m.include_top else ACT_NONE
         with self._stage("head_loss"):
             emb, pre = linear_fwd(h_last, m.output.weight, m.output.bias, act)
-            self.flat_g[self.n_param:].zero_()
+            if self.peer is not None:  # peers are done with the previous gradients; zero the centre-sum tail
+                ops.dp_wait_done_zero(self.peer.flags, self.world, self._step_dev, self.batch_center)
+            else:
+                self.flat_g[self.n_param:].zero_()
             loss, d_emb, _ = ops.dino_loss_fwd_bwd(emb, teacher, self.center, self.loss.student_temp, tau_t,
                                                    DINO_SINGLE, batch_center=self.batch_center)
             d_hlast, _, _ = linear_bwd(h_last, m.output.weight, pre, d_emb, act, need_dx=True,
@@ -129,6 +145,14 @@ class DistillTrainStep:
         if m.include_top:  # the DINO loss does not reach the class head: zero gradient
             self.grad_of(m.classifier.weight).zero_()
             self.grad_of(m.classifier.bias).zero_()
+        if self.peer is not None:
+            with self._stage("adam_center"):  # all-reduce + Adam + centre EMA in one kernel over peer memory
+                pe = self.peer
+                ops.dp_adam_step_peer(self.flat_p, self.exp_avg, self.exp_avg_sq, pe.grad_ptrs, pe.flag_ptrs, self.world,
+                                      pe.rank, self.center, self.loss.center_momentum, 1.0 / (B * self.world),
+                                      self._step_dev, pe.ticket, self.lr, self.betas[0], self.betas[1], self.eps,
+                                      self.weight_decay, self.decoupled, grad_scale=1.0 / self.world)
+            return loss
         with self._stage("allreduce"):
             dp.allreduce_flat_(self.flat_g)  # gradients and centre statistics in one NCCL call
         with self._stage("adam_center"):

@@ -142,6 +142,23 @@ int csn_adam_step_graph(float* params, const float* grads, float* exp_avg, float
                         float beta1, float beta2, float eps, float weight_decay, int decoupled, int* step_counter,
                         float* consts2, float grad_scale, void* stream);
 
+/* ---- data-parallel exchange fused into the optimiser (peer-mapped buffers over NVLink) --------------------
+ * Replaces DDP's gradient all-reduce (LstmDistillation.py:445) + optimizer.step() + DINOLoss.update_center's all-reduce
+ * and EMA (LstmDistillation.py:149-159) by ONE kernel per rank.  grad_ptrs[r] is rank r's flat fp32 buffer
+ * [n_param gradients | K centre column sums], mapped into this process (symmetric memory); flag_ptrs[r] is rank r's
+ * flag block (>= 16 zero-initialised uint32, same mapping).  Sums run in rank order on every rank (bit-identical
+ * replicas); grads are scaled by grad_scale (1/world), the centre by center_scale (1/(B_local*world)).  step_counter
+ * is the device-side count of completed steps (advanced by the call); ticket is one zero-initialised device word.
+ * csn_dp_wait_done_zero must run on the stream before a rank writes the next step's gradients: it waits until every
+ * peer has finished reading the previous ones, then zeroes n floats at zero_ptr (the centre-sum tail). */
+int csn_dp_wait_done_zero(const void* flags_local, int world, const int* step_counter, float* zero_ptr, size_t n,
+                          void* stream);
+int csn_dp_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, size_t n_param,
+                          const void* const* grad_ptrs, void* const* flag_ptrs, int world, int rank, float* center,
+                          size_t K, float center_momentum, float center_scale, int* step_counter, unsigned* ticket,
+                          float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                          float grad_scale, void* stream);
+
 /* EMA teacher update over flat buffers: dst = momentum * dst + (1 - momentum) * src  (LstmDistillation.py:616-619) */
 int csn_ema_update(float* dst, const float* src, size_t n, float momentum, void* stream);
 
