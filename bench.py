@@ -465,18 +465,19 @@ def main():
                 "h2d_bytes_per_step": B * C * T * 4 + B * K * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "LSTM encoder fwd+bwd (lstm_fwd_tc_kernel + lstm_bwd_tc_kernel + input-projection / dW GEMMs)",
+        "roofline": {"bound": "tensor", "kernel": "LSTM encoder fwd+bwd (lstm_fwd_tc_kernel with fused input projection + lstm_bwd_tc_kernel + 2 dW GEMMs)",
                      "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved_tflops / peak_tf) if achieved_tflops else None,
-                     "traffic": ncu_traffic(["lstm_fwd_tc_kernel", "lstm_bwd_tc_kernel", "gemm_tc_kernel<0, 0>", "gemm_tc_kernel<1, 1>", "gemm_tc_kernel<1, 1>"]),
-                     "traffic_note": "DRAM read+write bytes per step of the encoder kernels (fwd + bwd recurrence, input-projection GEMM, 2 dW GEMMs), ncu --set full, profiles/traffic.json",
+                     "traffic": ncu_traffic(["lstm_fwd_tc_kernel", "lstm_bwd_tc_kernel", "gemm_tc_kernel<1, 1>", "gemm_tc_kernel<1, 1>"]),
+                     "traffic_note": "DRAM read+write bytes per step of the encoder kernels (fwd recurrence with fused input projection, bwd recurrence, 2 dW GEMMs), ncu --set full, profiles/traffic.json",
                      "peak_source": peaks["source"] + " (sustained: kernel timed inside the step)"},
-        "roofline_filter": {"bound": "hbm", "kernel": "sosfilt_stream_kernel", "achieved": filt_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": (filt_gbs / peaks["hbm_gbs"]) if filt_gbs else None, "traffic": ncu_traffic(["sosfilt_stream_kernel"]),
+        "roofline_filter": {"bound": "hbm", "kernel": "sosfilt_warp_kernel", "achieved": filt_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": (filt_gbs / peaks["hbm_gbs"]) if filt_gbs else None, "traffic": ncu_traffic(["sosfilt_warp_kernel"]),
                             "peak_source": peaks["source"]},
-        "roofline_loss": {"bound": "hbm", "kernel": "dino_loss_kernel (cfg3 shape: 6 student + 2 teacher views, 64 trials, K=65536)",
+        "roofline_loss": {"bound": "hbm", "kernel": "dino_loss_staged_kernel (cfg3 shape: 6 student + 2 teacher views, 64 trials, K=65536)",
                           "achieved": loss_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                          "frac": (loss_gbs / peaks["hbm_gbs"]) if loss_gbs else None, "traffic": None, "peak_source": peaks["source"]},
+                          "frac": (loss_gbs / peaks["hbm_gbs"]) if loss_gbs else None, "traffic": ncu_traffic(["dino_loss_staged_kernel"]),
+                          "peak_source": peaks["source"]},
         "stages_ms": stages,
         "step_submission": "cuda_graph_replay",
         "dp_exchange": step.dp_exchange,

@@ -68,6 +68,24 @@ for name, r in seen.items():
     key = name.replace("void ", "").replace("csn::", "")
     traffic[key] = {"dram_read_bytes": _to_bytes(r[ir], units[ir]), "dram_write_bytes": _to_bytes(r[iw], units[iw]),
                     "duration_us_under_ncu": float(r[it].replace(",", "")) * ({"ns": 1e-3, "us": 1, "ms": 1e3}.get(units[it], 1))}
+# the cfg3-shape DINO loss kernel is captured separately (scripts/gpu_ncu_loss.sh -> gpurun_out/prof_loss.ncu-rep)
+loss_rep = os.path.join(root, "gpurun_out", "prof_loss.ncu-rep")
+if os.path.isfile(loss_rep):
+    lraw = subprocess.run(["ncu", "-i", loss_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    lrows = list(csv.reader(lraw.splitlines()))
+    lh, lu = lrows[0], lrows[1]
+    r = lrows[2]
+    name = r[lh.index("Kernel Name")].split("(")[0].replace("void ", "").replace("csn::", "")
+    traffic[name + " [cfg3 shape, scripts/loss_bench.py]"] = {
+        "dram_read_bytes": _to_bytes(r[lh.index("dram__bytes_read.sum")], lu[lh.index("dram__bytes_read.sum")]),
+        "dram_write_bytes": _to_bytes(r[lh.index("dram__bytes_write.sum")], lu[lh.index("dram__bytes_write.sum")]),
+        "duration_us_under_ncu": float(r[lh.index("gpu__time_duration.sum")].replace(",", ""))}
+    with open(os.path.join(out_dir, f"ncu_full_{tag}.md"), "a") as f:
+        f.write(f"## `{name}` (cfg3 shape: 6 student + 2 teacher views, 64 trials, K = 65536; `scripts/gpu_ncu_loss.sh`)\n\n| metric | value | unit |\n|---|---:|---|\n")
+        for w in want[1:] + ["launch__cluster_max_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]:
+            if w in lh:
+                f.write(f"| {w} | {r[lh.index(w)]} | {lu[lh.index(w)]} |\n")
+        f.write("\n")
 json.dump({"tag": tag, "source": f"ncu --set full, profiles/ncu_full_{tag}.md", "kernels": traffic},
           open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out_dir, f"launches_{tag}.md")).read()[:2500])
