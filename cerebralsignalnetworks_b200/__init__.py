@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import CsnError, LIB_PATH
 
 __all__ = ["CsnError", "LIB_PATH", "Model", "DINOHead", "DINOLoss", "MultiCropWrapper", "EEGFilters",
-           "DistillTrainStep", "ops"]
+           "DistillTrainStep", "ops", "IndexFlatL2", "IndexFlatIP", "retrieval"]
 
 
 def __getattr__(name):  # lazy: keep `import cerebralsignalnetworks_b200` cheap and torch-free until used
@@ -24,6 +24,10 @@ def __getattr__(name):  # lazy: keep `import cerebralsignalnetworks_b200` cheap 
     if name == "DistillTrainStep":
         from .train_step import DistillTrainStep
         return DistillTrainStep
+    if name in ("IndexFlatL2", "IndexFlatIP", "retrieval"):
+        import importlib
+        mod = importlib.import_module(".retrieval", __name__)
+        return mod if name == "retrieval" else getattr(mod, name)
     if name == "ops":
         import importlib
         return importlib.import_module(".ops", __name__)

@@ -77,6 +77,33 @@ class Model(nn.Module):
             return ActFunction.apply(feat, ACT_RELU), cls
         return feat
 
+    @torch.no_grad()
+    def encode_trials(self, eeg_bct, sos=None, zero_phase=False):
+        """Inference from RAW stored-layout trials [B, C, T] float32 (BASELINE.json config 5: 63-channel, 2000-sample
+        Perils trials): fused band-pass -> [T, B, C] -> LSTM stack (no BPTT reserve) -> projection.  Returns the
+        embeddings [B, output_size] (the features LstmDistillFromDinoV2Eval.py:333-380 hands to the faiss search).
+        The bf16 tensor-core path needs 16-byte input rows: a channel count that is not a multiple of 8 is padded with
+        zero channels (and W_ih with zero columns) -- zero inputs through zero weights, the result is unchanged."""
+        from .functional import encoder_fwd, linear_fwd
+        _lib.require_gpu()
+        B, Cc, T = eeg_bct.shape
+        if Cc != self.input_size:
+            raise ValueError("Model expects [B, %d, T] trials, got %s" % (self.input_size, tuple(eeg_bct.shape)))
+        x = eeg_bct.contiguous().float()
+        layers = self.lstm.layer_weights()
+        pad = (-Cc) % 8 if self.compute_dtype == torch.bfloat16 else 0
+        if pad:
+            x = torch.nn.functional.pad(x, (0, 0, 0, pad))  # [B, C + pad, T], zero channels
+            w_ih0 = torch.nn.functional.pad(layers[0][0].detach(), (0, pad))
+            layers = [(w_ih0,) + tuple(layers[0][1:])] + layers[1:]
+        if sos is not None:
+            x_tbc = ops.sosfilt(x, sos, zero_phase=zero_phase, out_layout="TBC", out_dtype=self.compute_dtype)
+        else:
+            x_tbc = ops.btc_to_tbc(x.transpose(1, 2).contiguous(), self.compute_dtype)
+        h_last, _ = encoder_fwd(x_tbc, [tuple(w.detach() for w in l) for l in layers], self.compute_dtype, training=False)
+        feat, _ = linear_fwd(h_last, self.output.weight.detach(), self.output.bias.detach(), ACT_NONE)
+        return feat
+
     def forward(self, x):
         """x: float32 [B, T, C] (batch_first, as the reference DataLoader yields it)."""
         if x.dim() != 3 or x.shape[-1] != self.input_size:

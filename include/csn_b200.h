@@ -159,6 +159,16 @@ int csn_dp_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, size
                           float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled,
                           float grad_scale, void* stream);
 
+/* ---- exact top-k retrieval -------------------------------------------------------
+ * Replaces faiss.IndexFlatL2(d).add(gallery) / .search(query, k) as called by utils/Utilities.py:45-58 (evaluate) from
+ * LstmDistillFromDinoV2Eval.py:333-380.  gallery [nb, d], query [nq, d] fp32 row-major on the device.  metric 0: squared
+ * L2 distance, ascending (what IndexFlatL2 returns in D); metric 1: inner product, descending (IndexFlatIP; cosine on
+ * L2-normalised rows).  out_dist [nq, k] fp32, out_idx [nq, k] int64 (faiss' idx_t), best first, ties to the lower
+ * gallery index; slots beyond nb hold index -1.  1 <= k <= 32.  workspace: csn_topk_workspace_bytes(). */
+int csn_topk_workspace_bytes(int nq, int nb, int k, size_t* bytes);
+int csn_topk_search(const float* gallery, const float* query, int nb, int nq, int d, int k, int metric,
+                    float* out_dist, long long* out_idx, void* workspace, void* stream);
+
 /* EMA teacher update over flat buffers: dst = momentum * dst + (1 - momentum) * src  (LstmDistillation.py:616-619) */
 int csn_ema_update(float* dst, const float* src, size_t n, float momentum, void* stream);
 
