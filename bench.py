@@ -56,6 +56,22 @@ def ncu_traffic(kernel_substrings):
     return total
 
 
+def ncu_tensor_pipe():
+    """Active-SM tensor-pipe utilisation of the two recurrence kernels from the committed ncu --set full summary
+    (sm__pipe_tensor_cycles_active / sm__pipe_tc_cycles_active, % of peak sustained on active SMs)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(p):
+        return None
+    d = json.load(open(p))
+    out = {"source": d.get("source"), "tag": d.get("tag")}
+    for k, v in d["kernels"].items():
+        for short in ("lstm_fwd_tc_kernel", "lstm_bwd_tc_kernel"):
+            if short in k and v.get("tensor_pipe_active_pct") is not None:
+                out[short] = {"sm__pipe_tensor_cycles_active_pct": v["tensor_pipe_active_pct"],
+                              "sm__pipe_tc_cycles_active_pct": v.get("tc_pipe_active_pct")}
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -470,7 +486,8 @@ def main():
                      "frac": (achieved_tflops / peak_tf) if achieved_tflops else None,
                      "traffic": ncu_traffic(["lstm_fwd_tc_kernel", "lstm_bwd_tc_kernel", "gemm_tc_kernel<1, 1>", "gemm_tc_kernel<1, 1>"]),
                      "traffic_note": "DRAM read+write bytes per step of the encoder kernels (fwd recurrence with fused input projection, bwd recurrence, 2 dW GEMMs), ncu --set full, profiles/traffic.json",
-                     "peak_source": peaks["source"] + " (sustained: kernel timed inside the step)"},
+                     "peak_source": peaks["source"] + " (sustained: kernel timed inside the step)",
+                     "tensor_pipe_active_sm": ncu_tensor_pipe()},
         "roofline_filter": {"bound": "hbm", "kernel": "sosfilt_warp_kernel", "achieved": filt_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": (filt_gbs / peaks["hbm_gbs"]) if filt_gbs else None, "traffic": ncu_traffic(["sosfilt_warp_kernel"]),
                             "peak_source": peaks["source"]},

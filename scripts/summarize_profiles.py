@@ -64,10 +64,14 @@ ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum
 def _to_bytes(v, u):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+def _opt(r, h, name):
+    return float(r[h.index(name)].replace(",", "")) if name in h and r[h.index(name)] not in ("", "n/a") else None
 for name, r in seen.items():
     key = name.replace("void ", "").replace("csn::", "")
     traffic[key] = {"dram_read_bytes": _to_bytes(r[ir], units[ir]), "dram_write_bytes": _to_bytes(r[iw], units[iw]),
-                    "duration_us_under_ncu": float(r[it].replace(",", "")) * ({"ns": 1e-3, "us": 1, "ms": 1e3}.get(units[it], 1))}
+                    "duration_us_under_ncu": float(r[it].replace(",", "")) * ({"ns": 1e-3, "us": 1, "ms": 1e3}.get(units[it], 1)),
+                    "tensor_pipe_active_pct": _opt(r, hdr, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "tc_pipe_active_pct": _opt(r, hdr, "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active")}
 # the cfg3-shape DINO loss kernel is captured separately (scripts/gpu_ncu_loss.sh -> gpurun_out/prof_loss.ncu-rep)
 loss_rep = os.path.join(root, "gpurun_out", "prof_loss.ncu-rep")
 if os.path.isfile(loss_rep):
