@@ -39,6 +39,7 @@ SIGNATURES = {
     "csn_lstm_layer_bytes": [_i, _i, _i, _i, _i, C.POINTER(_sz), C.POINTER(_sz)],
     "csn_lstm_layer_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "csn_lstm_layer_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "csn_lstm_set_cta_budget": [_i],
     "csn_dino_loss_fwd_bwd": [_vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "csn_center_ema": [_vp, _vp, _sz, _f, _f, _vp],
     "csn_adam_step": [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _i, _f, _vp],

@@ -737,11 +737,16 @@ static bool fused_projection(int I) {
   return !off && I <= 128 && I % 8 == 0;
 }
 
+// Upper bound on the CTAs (= SMs: a recurrence CTA owns a whole SM's tensor memory) one recurrence launch may use; 0 = all.
+// A caller that runs independent recurrences side by side on several streams (the crops of different length and the
+// teacher pass of LstmDistillation.py:581-589) gives each a share so that they are co-resident instead of queueing.
+static int g_cta_budget = 0;
+
 static int pick_nv(int B) {
   // smallest batch tile that still fills the machine: per-step latency falls with NV (fewer MUFU ops per SM)
   static const int forced = [] { const char* e = getenv("CSN_LSTM_NV"); return e ? atoi(e) : 0; }();
   if (forced == 2 || forced == 4 || forced == 8) return forced;
-  const int sms = sm_count();
+  const int sms = g_cta_budget > 0 ? std::min(g_cta_budget, sm_count()) : sm_count();
   if (ceil_div(B, 2) <= sms) return 2;
   if (ceil_div(B, 4) <= sms) return 4;
   return 8;
@@ -954,6 +959,12 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
     CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
     CSN_TRY(csn_gemm_bf16_tc(0, 0, (int)tb, I, 4 * H, dG, 4 * H, wih_bf, I, dx, I, CSN_F32, nullptr, 0, 1, s));
   }
+  return CSN_OK;
+}
+
+extern "C" int csn_lstm_set_cta_budget(int max_ctas) {
+  CSN_REQUIRE(max_ctas >= 0, "csn_lstm_set_cta_budget: negative budget");
+  g_cta_budget = max_ctas;
   return CSN_OK;
 }
 

@@ -191,6 +191,12 @@ def lstm_layer_bytes(T, B, I, H, compute_dtype):
     return r.value, w.value
 
 
+def set_lstm_cta_budget(max_ctas):
+    """Cap the SMs one persistent recurrence launch may occupy (0 = all): lets independent recurrences issued on
+    different CUDA streams (crops of different length, the teacher pass) run side by side."""
+    call("csn_lstm_set_cta_budget", int(max_ctas))
+
+
 def lstm_layer_fwd(x, w_ih, w_hh, b_ih, b_hh, compute_dtype, training=True):
     """x [T,B,I] in compute_dtype -> (h_seq [T,B,H] compute_dtype, reserve, workspace)."""
     _chk(x, compute_dtype, "x")

@@ -142,6 +142,11 @@ int csn_adam_step_graph(float* params, const float* grads, float* exp_avg, float
                         float beta1, float beta2, float eps, float weight_decay, int decoupled, int* step_counter,
                         float* consts2, float grad_scale, void* stream);
 
+/* Cap on the CTAs (one per SM) a persistent recurrence launch may occupy; 0 (default) = all SMs.  Lets independent
+ * recurrences issued on different streams run side by side -- the crops of different length and the teacher pass of
+ * LstmDistillation.py:581-589 -- instead of queueing behind each other.  Process-wide setting. */
+int csn_lstm_set_cta_budget(int max_ctas);
+
 /* ---- data-parallel exchange fused into the optimiser (peer-mapped buffers over NVLink) --------------------
  * Replaces DDP's gradient all-reduce (LstmDistillation.py:445) + optimizer.step() + DINOLoss.update_center's all-reduce
  * and EMA (LstmDistillation.py:149-159) by ONE kernel per rank.  grad_ptrs[r] is rank r's flat fp32 buffer

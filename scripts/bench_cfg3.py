@@ -36,10 +36,35 @@ def crops():
     return out[:2], out[2:]
 
 BATCH_VIEWS = os.environ.get("BATCH_VIEWS", "1") == "1"
+# Independent recurrences side by side: the teacher pass, the student's global crops and its local crops are three
+# serial chains with nothing in common; each gets its own stream and a share of the SMs (autograd replays every
+# backward node on its forward stream, so the two student BPTT chains overlap as well).
+CONCURRENT = os.environ.get("CONCURRENT", "1") == "1"
+BUDGET = int(os.environ.get("CTA_BUDGET", "64"))
+if CONCURRENT:
+    from cerebralsignalnetworks_b200 import ops as _ops
+    _ops.set_lstm_cta_budget(BUDGET)
+    s_t, s_g, s_l = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
 def step(epoch=0):
     gv, lv = crops()
-    if BATCH_VIEWS:
+    if BATCH_VIEWS and CONCURRENT:
+        cur = torch.cuda.current_stream()
+        gcat, lcat = torch.cat(gv), torch.cat(lv)
+        for st in (s_t, s_g, s_l):
+            st.wait_stream(cur)
+        with torch.cuda.stream(s_t), torch.no_grad():
+            t_feat = teacher.backbone(gcat)
+        with torch.cuda.stream(s_g):
+            f_g = student.backbone(gcat)
+        with torch.cuda.stream(s_l):
+            f_l = student.backbone(lcat)
+        for st in (s_t, s_g, s_l):
+            cur.wait_stream(st)
+        with torch.no_grad():
+            t_out = teacher.head(t_feat).view(2, B, K)
+        s_out = student.head(torch.cat([f_g, f_l])).view(6, B, K)
+    elif BATCH_VIEWS:
         # Same arithmetic as the reference loop (:581-589, one view per call), but crops of equal length share one
         # backbone pass (the LSTM treats trials independently): 3 backbone passes instead of 8.  (The reference's
         # MultiCropWrapper groups by the LAST dimension, which is the channel count for [B,T,C] EEG, so it cannot
