@@ -152,6 +152,76 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     // 128-byte line per row) instead of one 4-byte store per lane per row.
     const int quad = warp & 3;
     float* tile = reinterpret_cast<float*>(smem + size_t(S) * kStageBytes + 256) + quad * (32 * kEpiStride);
+    if (p.mode == 1) {
+      // ---- fused LSTM cell: (i,f,g,o) = act(acc + Xp); c = f c_prev + i g; h = o tanh(c) ----
+      // The cell's other inputs (Xp float4, c_prev) do not depend on the MMAs: they are fetched one 32-column chunk
+      // AHEAD into registers (the first chunk before the accumulator wait), so their HBM/L2 latency hides behind the
+      // TMA/MMA pipeline instead of being paid eight dependent times per chunk (the stores of one cell may alias the
+      // loads of the next as far as the compiler can tell, so it cannot hoist them itself).
+      const int col4 = (lane & 7) * 4;
+      constexpr int kChunks = GBN / 32;
+      auto fetch = [&](int c, float4 (&x4)[8], float (&cp)[8]) {
+        const int gn = n0 + c * 32 + col4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int gm = m0 + quad * 32 + i * 4 + (lane >> 3);
+          const bool ok = gm < p.M && gn < p.N;
+          x4[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.xp + size_t(gm) * p.N + gn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          cp[i] = (ok && p.c_prev) ? __ldg(p.c_prev + size_t(gm) * p.H + (gn >> 2)) : 0.f;
+        }
+      };
+      float4 xa[8];
+      float ca[8];
+      fetch(0, xa, ca);
+      if (n_it > 0) {
+        mbar_wait(accfull, 0);
+        tcgen05_fence_after();
+      }
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        float4 xb[8];
+        float cb[8];
+        const bool more = (c + 1 < kChunks) && (n0 + (c + 1) * 32 < p.N);
+        if (more) fetch(c + 1, xb, cb);
+        uint32_t r[32];
+        if (n_it > 0) {
+          tmem_ld<32>(tmem_base + (uint32_t(quad * 32) << 16) + c * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          *reinterpret_cast<uint4*>(tile + lane * kEpiStride + q4 * 4) = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
+        __syncwarp();
+        const int gn = n0 + c * 32 + col4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3);
+          const int gm = m0 + quad * 32 + rr;
+          if (gm >= p.M || gn >= p.N) continue;
+          const float4 v = *reinterpret_cast<const float4*>(tile + rr * kEpiStride + col4);
+          const int u = gn >> 2;
+          const float ig = sigmoid_fast_g(v.x + xa[i].x), fg = sigmoid_fast_g(v.y + xa[i].y);
+          const float gg = tanh_fast_g(v.z + xa[i].z), og = sigmoid_fast_g(v.w + xa[i].w);
+          const float cc = fmaf(fg, ca[i], ig * gg);
+          p.c_out[size_t(gm) * p.H + u] = cc;
+          p.h_out[size_t(gm) * p.H + u] = __float2bfloat16_rn(og * tanh_fast_g(cc));
+          if (p.gates_out) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(ig, fg), hi = __floats2bfloat162_rn(gg, og);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo);
+            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(p.gates_out + size_t(gm) * p.N + gn) = o;
+          }
+        }
+        __syncwarp();
+        if (!more) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { xa[i] = xb[i]; ca[i] = cb[i]; }
+      }
+    } else {
     if (n_it > 0) {
       mbar_wait(accfull, 0);
       tcgen05_fence_after();
@@ -190,25 +260,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         float4 v = *reinterpret_cast<const float4*>(tile + rr * kEpiStride + col4);
         v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
         if (gm >= p.M || gn >= p.N) continue;
-        if (p.mode == 1) {
-          // ---- fused LSTM cell: (i,f,g,o) = act(acc + Xp); c = f c_prev + i g; h = o tanh(c) ----
-          const int u = gn >> 2;
-          const float4 x4 = *reinterpret_cast<const float4*>(p.xp + size_t(gm) * p.N + gn);
-          const float ig = sigmoid_fast_g(v.x + x4.x), fg = sigmoid_fast_g(v.y + x4.y);
-          const float gg = tanh_fast_g(v.z + x4.z), og = sigmoid_fast_g(v.w + x4.w);
-          const float cp = p.c_prev ? p.c_prev[size_t(gm) * p.H + u] : 0.f;
-          const float c = fmaf(fg, cp, ig * gg);
-          p.c_out[size_t(gm) * p.H + u] = c;
-          p.h_out[size_t(gm) * p.H + u] = __float2bfloat16_rn(og * tanh_fast_g(c));
-          if (p.gates_out) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(ig, fg), hi = __floats2bfloat162_rn(gg, og);
-            uint2 o;
-            o.x = *reinterpret_cast<uint32_t*>(&lo);
-            o.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(p.gates_out + size_t(gm) * p.N + gn) = o;
-          }
-          continue;
-        }
         if (f32_out) {
           float* d = reinterpret_cast<float*>(p.D) + size_t(gm) * p.ldd + gn;
           if (p.atomic) {
@@ -241,6 +292,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
       }
       __syncwarp();
+    }
     }
   }
   tcgen05_fence_before();

@@ -17,7 +17,7 @@ for i in range(3):
 torch.cuda.synchronize()
 print("warmup+capture s", round(time.time() - t0, 2), "loss", float(l))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-n = 10
+n = int(os.environ.get("NSTEPS", "10"))
 e0.record()
 for i in range(n):
     l = step.step(eeg[i % 4], feats[i % 4], 0)
