@@ -16,9 +16,10 @@ namespace csn {
 
 using namespace tc;
 
-constexpr int GBM = 128, GBN = 128, GBK = 64;
+constexpr int GBM = 128, GBK = 64;  // the N tile (GBN) is a template parameter: 128, or 32 for the per-timestep LSTM-cell GEMM
 constexpr int kGemmThreads = 192;
-constexpr uint32_t kStageBytes = (GBM * GBK + GBN * GBK) * 2;  // 32 KB
+template <int GBN>
+constexpr uint32_t stage_bytes() { return uint32_t(GBM * GBK + GBN * GBK) * 2u; }  // 32 KB at GBN = 128
 constexpr int kEpiStride = 36;                                  // floats; 16-byte aligned rows, conflict-free float4
 constexpr uint32_t kEpiBytes = 4 * 32 * kEpiStride * 4;         // one 32x32 staging tile per epilogue warp
 
@@ -70,10 +71,12 @@ __device__ __forceinline__ float tanh_fast_g(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast_g(float x) { return fmaf(0.5f, tanh_fast_g(0.5f * x), 0.5f); }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int GBN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB,
                                                                   const GemmEpi p) {
+  static_assert(GBN == 128 || (GBN == 32 && !B_MN), "N tile: 128, or 32 with a K-major B operand");
+  constexpr uint32_t kStageBytes = stage_bytes<GBN>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.stages;
@@ -227,7 +230,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       tcgen05_fence_after();
     }
     const bool f32_out = (p.d_dtype == CSN_F32);
-    const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    // split-K into per-split slabs (no atomics): split z owns D + z * split_stride elements; the consumer sums them
+    void* const Dz = p.split_stride ? static_cast<void*>(reinterpret_cast<float*>(p.D) + size_t(blockIdx.z) * p.split_stride) : p.D;
+    const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(Dz) & 15) == 0);
     const bool add_bias = p.bias && blockIdx.z == 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < GBN; c0 += 32) {
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
         if (gm >= p.M || gn >= p.N) continue;
         if (f32_out) {
-          float* d = reinterpret_cast<float*>(p.D) + size_t(gm) * p.ldd + gn;
+          float* d = reinterpret_cast<float*>(Dz) + size_t(gm) * p.ldd + gn;
           if (p.atomic) {
             atomicAdd(d, v.x);
             if (gn + 1 < p.N) atomicAdd(d + 1, v.y);
@@ -300,10 +305,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, GBN);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int GBN = 128>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& p, dim3 grid, cudaStream_t s) {
-  const size_t smem = size_t(p.stages) * kStageBytes + 1024 + 256 + kEpiBytes;
-  auto kern = gemm_tc_kernel<A_MN, B_MN>;
+  const size_t smem = size_t(p.stages) * stage_bytes<GBN>() + 1024 + 256 + kEpiBytes;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, GBN>;
   static size_t smem_set = 0;  // per instantiation; raise-only, so the call disappears from steady state (and from graph capture)
   if (smem > smem_set) {
     CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -336,7 +341,7 @@ int csn::gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A,
   CSN_REQUIRE(d_dtype == CSN_F32 || d_dtype == CSN_BF16, "csn_gemm_bf16_tc: bad d_dtype");
   if (split_k < 1) split_k = 1;
   CSN_REQUIRE(d_dtype == CSN_F32 || (split_k == 1 && !accumulate), "csn_gemm_bf16_tc: bf16 output cannot accumulate / split-K");
-  if (cell) {
+  if (cell && !cell->split_stride) {
     CSN_REQUIRE(split_k == 1 && !accumulate && N % 4 == 0 && cell->xp && cell->h_out && cell->c_out && cell->H * 4 == N,
                 "gemm_tc_run: bad LSTM-cell epilogue arguments");
   }
@@ -349,23 +354,32 @@ int csn::gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A,
   CUtensorMap ta, tb;
   if (transA) CSN_TRY(make_tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64));   // stored [K, M]
   else        CSN_TRY(make_tmap_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 128));  // stored [M, K]
-  if (transB) CSN_TRY(make_tmap_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 128));  // stored [N, K]
+  // LSTM-cell epilogue on a small batch: 32-column tiles put 4x more CTAs on each step of the serial chain
+  const bool narrow = cell && transB && !transA && ceil_div(N, 128) * ceil_div(M, GBM) * 4 <= 2 * sm_count();
+  const int gbn = narrow ? 32 : 128;
+  if (transB) CSN_TRY(make_tmap_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, gbn));  // stored [N, K]
   else        CSN_TRY(make_tmap_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64));   // stored [K, N]
 
   GemmEpi p{};
   p.D = D; p.bias = bias; p.ldd = ldd; p.d_dtype = d_dtype; p.M = M; p.N = N; p.K = K;
   p.k_per_split = it_per_split * GBK;
-  p.atomic = (accumulate || split_k > 1) ? 1 : 0;
+  p.split_stride = 0;
+  if (cell && cell->split_stride) {  // caller-provided slabs: plain stores, split z -> D + z * split_stride
+    CSN_REQUIRE(!cell->xp && d_dtype == CSN_F32 && !accumulate, "gemm_tc_run: split slabs need fp32 output without accumulation");
+    p.split_stride = cell->split_stride;
+  }
+  p.atomic = (!p.split_stride && (accumulate || split_k > 1)) ? 1 : 0;
   p.stages = it_per_split < 4 ? (it_per_split < 2 ? 2 : it_per_split) : 4;
-  if (cell) {
+  if (cell && !cell->split_stride) {
     p.mode = 1; p.zero_acc = cell->zero_acc; p.H = cell->H; p.xp = cell->xp; p.c_prev = cell->c_prev;
     p.h_out = cell->h_out; p.gates_out = cell->gates_out; p.c_out = cell->c_out;
   }
-  if (split_k > 1 && !accumulate) CSN_CUDA(cudaMemset2DAsync(D, size_t(ldd) * 4, 0, size_t(N) * 4, M, s));
-  dim3 grid(ceil_div(N, GBN), ceil_div(M, GBM), split_k);
+  if (split_k > 1 && !accumulate && !p.split_stride) CSN_CUDA(cudaMemset2DAsync(D, size_t(ldd) * 4, 0, size_t(N) * 4, M, s));
+  dim3 grid(ceil_div(N, gbn), ceil_div(M, GBM), split_k);
   CSN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "csn_gemm_bf16_tc: grid too large");
   if (transA && !transB) return launch_gemm<true, true>(ta, tb, p, grid, s);
   if (transA && transB) return launch_gemm<true, false>(ta, tb, p, grid, s);
   if (!transA && !transB) return launch_gemm<false, true>(ta, tb, p, grid, s);
+  if (narrow) return launch_gemm<false, false, 32>(ta, tb, p, grid, s);
   return launch_gemm<false, false>(ta, tb, p, grid, s);
 }

@@ -59,15 +59,16 @@ __global__ void lstm_cell_bwd_kernel(const __nv_bfloat16* __restrict__ gates_t, 
                                      const float* __restrict__ c_prev, const float* __restrict__ dh_rec,
                                      const float* __restrict__ d_hseq_t, const float* __restrict__ d_hlast,
                                      float* __restrict__ dc, __nv_bfloat16* __restrict__ dG_t, int B, int H,
-                                     float* __restrict__ zero_next) {
+                                     int dh_parts) {
   const size_t cell = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (cell >= size_t(B) * H) return;
-  if (zero_next) zero_next[cell] = 0.f;  // the split-K GEMM of this step accumulates dh_{t-1} into the other buffer
+  const size_t cells = size_t(B) * H;
+  if (cell >= cells) return;
   const uint2 gq = *reinterpret_cast<const uint2*>(gates_t + cell * 4);
   const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&gq.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&gq.y);
   const float i = __bfloat162float(lo.x), f = __bfloat162float(lo.y), g = __bfloat162float(hi.x), o = __bfloat162float(hi.y);
   float dh = 0.f;
-  if (dh_rec) dh += dh_rec[cell];
+  if (dh_rec)  // the split-K partial products of dh = dG_{t+1} W_hh, one slab per split
+    for (int z = 0; z < dh_parts; ++z) dh += dh_rec[size_t(z) * cells + cell];
   if (d_hseq_t) dh += d_hseq_t[cell];
   if (d_hlast) dh += d_hlast[cell];
   const float tc = tanh_fast_l(c_t[cell]);
@@ -88,7 +89,7 @@ struct LargeWs {
   __nv_bfloat16* wih;        // [4H, I] permuted bf16
   __nv_bfloat16* whh;        // [4H, H] permuted bf16
   float* bias;               // [4H] permuted b_ih + b_hh
-  float* dh_rec;             // 2 x [B, H]: ping-pong (split-K accumulation target / current recurrent gradient)
+  float* dh_rec;             // 8 x [B, H]: split-K slabs of the recurrent gradient (summed by the cell kernel)
   float* dc;                 // [B, H]
   float* dwp;                // [4H, max(I, H)] permuted dW scratch
   __nv_bfloat16* ones;       // [TB, 8]
@@ -107,7 +108,7 @@ static LargeWs carve_ws(void* base, int T, int B, int I, int H) {
   w.wih = reinterpret_cast<__nv_bfloat16*>(take(size_t(4) * H * I * 2));
   w.whh = reinterpret_cast<__nv_bfloat16*>(take(size_t(4) * H * H * 2));
   w.bias = reinterpret_cast<float*>(take(size_t(4) * H * 4));
-  w.dh_rec = reinterpret_cast<float*>(take(size_t(2) * B * H * 4));
+  w.dh_rec = reinterpret_cast<float*>(take(size_t(8) * B * H * 4));
   w.dc = reinterpret_cast<float*>(take(size_t(B) * H * 4));
   w.dwp = reinterpret_cast<float*>(take(size_t(4) * H * (I > H ? I : H) * 4));
   w.ones = reinterpret_cast<__nv_bfloat16*>(take(tb * 8 * 2));
@@ -177,24 +178,26 @@ int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, co
   CSN_CUDA(cudaMemsetAsync(w.dc, 0, size_t(B) * H * 4, s));
   const int cells = B * H;
   // dh_{t-1}[B,H] = dG_t[B,4H] . W_hh_perm[4H,H]: a contraction of 4H with only H/128 output tiles per batch tile, so
-  // it is split over K (fp32 atomics) to put 8x more CTAs on each step of the chain; the two dh buffers alternate and
-  // the cell kernel of step t clears the one the GEMM of step t accumulates into.
+  // it is split over K to put up to 8x more CTAs on each step of the chain; every split stores its partial product to
+  // its own slab (no atomics, no memset) and the cell kernel of the next step adds the slabs while it reads dh.
   const int sms0 = sm_count();
-  const int kparts = max(1, min(8, sms0 / max(1, ceil_div(B, 128) * ceil_div(H, 128))));
-  float* dh_buf[2] = {w.dh_rec, w.dh_rec + size_t(B) * H};
-  int cur = 0;
+  int kparts = max(1, min(8, sms0 / max(1, ceil_div(B, 128) * ceil_div(H, 128))));
+  kparts = min(kparts, ceil_div(4 * H, 64));
+  {  // the GEMM rounds the split: use the count it will really launch
+    const int k_iters = ceil_div(4 * H, 64), per = ceil_div(k_iters, kparts);
+    kparts = ceil_div(k_iters, per);
+  }
+  GemmEpi slabs{};
+  slabs.split_stride = size_t(B) * H;
   for (int t = T - 1; t >= 0; --t) {
-    float* dh_in = dh_buf[cur];
-    float* dh_out = dh_buf[cur ^ 1];
     lstm_cell_bwd_kernel<<<ceil_div(cells, 256), 256, 0, s>>>(
         gates + size_t(t) * B * 4 * H, c_seq + size_t(t) * B * H, t ? c_seq + size_t(t - 1) * B * H : nullptr,
-        (t + 1 < T) ? dh_in : nullptr, d_hseq ? d_hseq + size_t(t) * B * H : nullptr, (t == T - 1) ? d_hlast : nullptr,
-        w.dc, w.dG + size_t(t) * B * 4 * H, B, H, t > 0 ? dh_out : nullptr);
+        (t + 1 < T) ? w.dh_rec : nullptr, d_hseq ? d_hseq + size_t(t) * B * H : nullptr, (t == T - 1) ? d_hlast : nullptr,
+        w.dc, w.dG + size_t(t) * B * 4 * H, B, H, kparts);
     CSN_LAUNCH_CHECK();
     if (t > 0)
-      CSN_TRY(gemm_tc_run(0, 0, B, H, 4 * H, w.dG + size_t(t) * B * 4 * H, 4 * H, w.whh, H, dh_out, H, CSN_F32, nullptr,
-                          /*accumulate=*/1, kparts, nullptr, s));
-    cur ^= 1;
+      CSN_TRY(gemm_tc_run(0, 0, B, H, 4 * H, w.dG + size_t(t) * B * 4 * H, 4 * H, w.whh, H, w.dh_rec, H, CSN_F32, nullptr, 0,
+                          kparts, &slabs, s));
   }
   const int sms = sm_count();
   auto splits = [&](int M, int N) { return max(1, sms / (ceil_div(M, 128) * ceil_div(N, 128))); };
