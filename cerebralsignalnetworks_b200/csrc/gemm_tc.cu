@@ -96,12 +96,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     mbar_init(accfull, 1);
     fence_mbar_init();
   }
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step's grid may start its prologue
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
   if (warp == 1) tmem_alloc(tmem_slot, GBN);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched no global data; from here on the predecessor grid's results are needed
+  if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -314,6 +317,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
+  if (p.pdl) {
+    // programmatic dependent launch: this grid may be scheduled (and run its prologue: barrier init, TMEM allocation,
+    // descriptor prefetch) while its predecessor in the stream drains; griddepcontrol.wait in the kernel orders the data
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CSN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    count_launches(1);
+    return CSN_OK;
+  }
   kern<<<grid, kGemmThreads, smem, s>>>(ta, tb, p);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
@@ -364,6 +384,7 @@ int csn::gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A,
   p.D = D; p.bias = bias; p.ldd = ldd; p.d_dtype = d_dtype; p.M = M; p.N = N; p.K = K;
   p.k_per_split = it_per_split * GBK;
   p.split_stride = 0;
+  p.pdl = cell ? cell->pdl : 0;
   if (cell && cell->split_stride) {  // caller-provided slabs: plain stores, split z -> D + z * split_stride
     CSN_REQUIRE(!cell->xp && d_dtype == CSN_F32 && !accumulate, "gemm_tc_run: split slabs need fp32 output without accumulation");
     p.split_stride = cell->split_stride;

@@ -11,6 +11,7 @@ struct GemmEpi {
   // split-K without atomics: when non-zero, split z stores its partial product to D + z * split_stride (fp32 elements);
   // the consumer adds the slabs (lstm_cell_bwd_kernel does, lstm_tc_large.cu).  Set in a `cell` argument with xp == NULL.
   size_t split_stride;
+  int pdl;  // launch with programmatic stream serialization (the per-timestep chains of lstm_tc_large.cu)
   // mode 1: fused LSTM cell epilogue (large-hidden path, see lstm_tc_large.cu).  Columns are gate-interleaved
   // (column 4u+g = gate g of hidden unit u), so the float4 a lane owns is one cell's (i,f,g,o) pre-activation.
   int mode, zero_acc, H;

@@ -17,6 +17,9 @@ namespace csn {
 
 static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
 
+// programmatic dependent launch for the per-timestep kernels (CSN_NO_PDL=1 switches it off for A/B measurements)
+static const int kPdl = [] { const char* e = getenv("CSN_NO_PDL"); return (e && e[0] == '1') ? 0 : 1; }();
+
 __device__ __forceinline__ float tanh_fast_l(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -60,6 +63,10 @@ __global__ void lstm_cell_bwd_kernel(const __nv_bfloat16* __restrict__ gates_t, 
                                      const float* __restrict__ d_hseq_t, const float* __restrict__ d_hlast,
                                      float* __restrict__ dc, __nv_bfloat16* __restrict__ dG_t, int B, int H,
                                      int dh_parts) {
+  // launched with programmatic stream serialization: let the next grid (the dh GEMM) start its prologue, then wait for
+  // the previous one (the dh GEMM of step t+1) before touching its output
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const size_t cell = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t cells = size_t(B) * H;
   if (cell >= cells) return;
@@ -153,6 +160,7 @@ int lstm_layer_fwd_large(const void* x, const float* w_ih, const float* w_hh, co
   CSN_TRY(gemm_tc_run(0, 1, (int)tb, 4 * H, I, x, I, w.wih, I, w.xp, 4 * H, CSN_F32, w.bias, 0, 1, nullptr, s));
   for (int t = 0; t < T; ++t) {
     GemmEpi cell{};
+    cell.pdl = kPdl;
     cell.zero_acc = (t == 0);
     cell.H = H;
     cell.xp = w.xp + size_t(t) * B * 4 * H;
@@ -189,12 +197,28 @@ int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, co
   }
   GemmEpi slabs{};
   slabs.split_stride = size_t(B) * H;
+  slabs.pdl = kPdl;
   for (int t = T - 1; t >= 0; --t) {
-    lstm_cell_bwd_kernel<<<ceil_div(cells, 256), 256, 0, s>>>(
-        gates + size_t(t) * B * 4 * H, c_seq + size_t(t) * B * H, t ? c_seq + size_t(t - 1) * B * H : nullptr,
-        (t + 1 < T) ? w.dh_rec : nullptr, d_hseq ? d_hseq + size_t(t) * B * H : nullptr, (t == T - 1) ? d_hlast : nullptr,
-        w.dc, w.dG + size_t(t) * B * 4 * H, B, H, kparts);
-    CSN_LAUNCH_CHECK();
+    {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(ceil_div(cells, 256), 1, 1);
+      cfg.blockDim = dim3(256, 1, 1);
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = kPdl;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      const __nv_bfloat16* a_gates = gates + size_t(t) * B * 4 * H;
+      const float* a_ct = c_seq + size_t(t) * B * H;
+      const float* a_cp = t ? c_seq + size_t(t - 1) * B * H : nullptr;
+      const float* a_dh = (t + 1 < T) ? w.dh_rec : nullptr;
+      const float* a_dhs = d_hseq ? d_hseq + size_t(t) * B * H : nullptr;
+      const float* a_dhl = (t == T - 1) ? d_hlast : nullptr;
+      __nv_bfloat16* a_dg = w.dG + size_t(t) * B * 4 * H;
+      CSN_CUDA(cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel, a_gates, a_ct, a_cp, a_dh, a_dhs, a_dhl, w.dc, a_dg, B, H, kparts));
+      count_launches(1);
+    }
     if (t > 0)
       CSN_TRY(gemm_tc_run(0, 0, B, H, 4 * H, w.dG + size_t(t) * B * 4 * H, 4 * H, w.whh, H, w.dh_rec, H, CSN_F32, nullptr, 0,
                           kparts, &slabs, s));
