@@ -54,8 +54,10 @@ __device__ __forceinline__ void wait_flag_ge(const unsigned* flag, unsigned targ
 
 __global__ void dp_wait_done_zero_kernel(const unsigned* __restrict__ flags_local, int world, const int* __restrict__ step_dev,
                                          float* __restrict__ zero_ptr, size_t n) {
-  if (threadIdx.x < world) wait_flag_ge(flags_local + kFlagDone + threadIdx.x, (unsigned)*step_dev);
-  __syncthreads();
+  if (world > 1) {
+    if (threadIdx.x < world) wait_flag_ge(flags_local + kFlagDone + threadIdx.x, (unsigned)*step_dev);
+    __syncthreads();
+  }
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) zero_ptr[i] = 0.f;
 }
 
@@ -68,15 +70,19 @@ __global__ void __launch_bounds__(256) dp_adam_peer_kernel(float* __restrict__ p
   __shared__ float s_consts[2];
   __shared__ int s_last;
   const int t = *step_dev + 1;  // this step's 1-based count (the counter is advanced by the last CTA)
-  if (blockIdx.x == 0 && threadIdx.x < world) {
-    __threadfence_system();
-    st_release_sys(ps.flags[threadIdx.x] + kFlagReady + rank, (unsigned)t);
+  if (world > 1) {  // (one rank: stream order already is the ordering)
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(ps.flags[threadIdx.x] + kFlagReady + rank, (unsigned)t);
+    }
+    if (threadIdx.x < world) wait_flag_ge(ps.flags[rank] + kFlagReady + threadIdx.x, (unsigned)t);
   }
-  if (threadIdx.x < world) wait_flag_ge(ps.flags[rank] + kFlagReady + threadIdx.x, (unsigned)t);
+  // bias corrections 1 - beta^t = -expm1(t log beta): accurate in fp32 for small and large t alike, and cheap enough
+  // to recompute in every CTA (a double-precision pow here, or in the last CTA, costs ~3 us of every step)
   if (threadIdx.x == 32) {
-    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
-    s_consts[0] = (float)((double)lr / bc1);
-    s_consts[1] = (float)(1.0 / sqrt(bc2));
+    const float bc1 = -expm1f((float)t * logf(b1)), bc2 = -expm1f((float)t * logf(b2));
+    s_consts[0] = lr / bc1;
+    s_consts[1] = rsqrtf(bc2);
   }
   __syncthreads();
   const float step_size = s_consts[0], inv_sqrt_bc2 = s_consts[1];
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(256) dp_adam_peer_kernel(float* __restrict__ p
       *ticket = 0u;
       *step_dev = t;
     }
-    if (threadIdx.x < world) {
+    if (world > 1 && threadIdx.x < world) {
       __threadfence_system();
       st_release_sys(ps.flags[threadIdx.x] + kFlagDone + rank, (unsigned)t);
     }

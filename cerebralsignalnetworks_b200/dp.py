@@ -59,4 +59,19 @@ class PeerExchange:
             raise RuntimeError("symmetric-memory rendezvous returned an unexpected mapping")
         self.grad_ptrs = (ctypes.c_void_p * self.world)(*gp)
         self.flag_ptrs = (ctypes.c_void_p * self.world)(*fp)
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=device)
+
+
+class LocalExchange:
+    """World size 1: the same fused kernel (sum over one rank + Adam + centre EMA + step counter in ONE launch instead
+    of three), on ordinary device memory."""
+
+    def __init__(self, n_floats: int, device: torch.device):
+        import ctypes
+
+        self.world, self.rank = 1, 0
+        self.buf = torch.zeros(n_floats, dtype=torch.float32, device=device)
+        self.flags = torch.zeros(64, dtype=torch.int32, device=device)
+        self.grad_ptrs = (ctypes.c_void_p * 1)(self.buf.data_ptr())
+        self.flag_ptrs = (ctypes.c_void_p * 1)(self.flags.data_ptr())
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=device)

@@ -57,6 +57,8 @@ class DistillTrainStep:
                 import warnings
                 warnings.warn("peer gradient exchange unavailable (%s: %s); using ncclAllReduce" % (type(exc).__name__, exc))
         self.dp_exchange = "peer_fused_adam" if self.peer is not None else ("nccl_allreduce" if self.world > 1 else "single")
+        if self.world == 1 and dev.type == "cuda":
+            self.peer = dp.LocalExchange(total + K, dev)  # same fused optimiser kernel, one rank
         self.flat_g = self.peer.buf if self.peer is not None else torch.zeros(total + K, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)

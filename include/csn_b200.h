@@ -153,7 +153,8 @@ int csn_lstm_set_cta_budget(int max_ctas);
  * [n_param gradients | K centre column sums], mapped into this process (symmetric memory); flag_ptrs[r] is rank r's
  * flag block (>= 16 zero-initialised uint32, same mapping).  Sums run in rank order on every rank (bit-identical
  * replicas); grads are scaled by grad_scale (1/world), the centre by center_scale (1/(B_local*world)).  step_counter
- * is the device-side count of completed steps (advanced by the call); ticket is one zero-initialised device word.
+ * is the device-side count of completed steps (advanced by the call); ticket is one zero-initialised device word (CTA arrival
+ * counter).
  * csn_dp_wait_done_zero must run on the stream before a rank writes the next step's gradients: it waits until every
  * peer has finished reading the previous ones, then zeroes n floats at zero_ptr (the centre-sum tail). */
 int csn_dp_wait_done_zero(const void* flags_local, int world, const int* step_counter, float* zero_ptr, size_t n,
