@@ -8,7 +8,8 @@ from . import _lib
 from ._lib import CsnError, LIB_PATH
 
 __all__ = ["CsnError", "LIB_PATH", "Model", "DINOHead", "DINOLoss", "MultiCropWrapper", "EEGFilters",
-           "DistillTrainStep", "ops", "IndexFlatL2", "IndexFlatIP", "retrieval"]
+           "DistillTrainStep", "ops", "IndexFlatL2", "IndexFlatIP", "retrieval",
+           "FeatureDistributionLoss", "CosineSimilarityLoss", "HyperParams"]
 
 
 def __getattr__(name):  # lazy: keep `import cerebralsignalnetworks_b200` cheap and torch-free until used
@@ -24,6 +25,9 @@ def __getattr__(name):  # lazy: keep `import cerebralsignalnetworks_b200` cheap 
     if name == "DistillTrainStep":
         from .train_step import DistillTrainStep
         return DistillTrainStep
+    if name in ("FeatureDistributionLoss", "CosineSimilarityLoss", "HyperParams"):
+        from . import losses
+        return getattr(losses, name)
     if name in ("IndexFlatL2", "IndexFlatIP", "retrieval"):
         import importlib
         mod = importlib.import_module(".retrieval", __name__)

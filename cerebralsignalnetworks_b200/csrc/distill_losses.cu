@@ -1,0 +1,192 @@
+// The distillation losses LstmDistillFromDinoV2Train.py actually calls today, forward +
+// backward in one pass, one WARP per batch row (K = 384 / 768 feature targets, 40 classes):
+//   * FeatureDistributionLoss (LstmDistillFromDinoV2Train.py:107-140, live at :371):
+//       term1 = alpha * cross_entropy(pred_label, label)
+//       term2 = beta  * F.cross_entropy(softmax(teacher / T), softmax(student / T))
+//     i.e. the teacher PROBABILITIES are used as logits (log-softmaxed once more) and the student probabilities are the
+//     soft target: term2 = -mean_b sum_k p_s[b,k] * log_softmax(q_t[b,:])[k].  Reproduced as written.
+//   * CosineSimilarityLoss (LstmDistillFromDinoV2Train.py:36-43): 1 - mean_b cos(student_b, teacher_b)
+//     (nn.CosineSimilarity: dim = 1, eps = 1e-8, each norm clamped).
+#include "common.cuh"
+
+namespace csn {
+
+constexpr int kLossWarps = 8;
+
+__device__ __forceinline__ float ex2f_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kL2e = 1.4426950408889634f;
+
+// block-level fold of one float per warp into one atomicAdd
+__device__ __forceinline__ void block_atomic_sum(float v, float* dst, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kLossWarps; ++w) t += scratch[w];
+    atomicAdd(dst, t);
+  }
+}
+
+template <int EPT>
+__global__ void __launch_bounds__(kLossWarps * 32) feature_dist_loss_kernel(
+    const float* __restrict__ student, const float* __restrict__ teacher, const float* __restrict__ pred,
+    const long long* __restrict__ label, float* __restrict__ loss, float* __restrict__ d_student,
+    float* __restrict__ d_pred, int B, int K, int n_classes, float inv_T, float alpha, float beta, float grad_scale) {
+  __shared__ float scratch[kLossWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * kLossWarps + warp;
+  float term2_row = 0.f;   // warp-uniform
+  float term1_lane = 0.f;  // non-zero in the label's lane only
+  if (b < B) {
+    // ---- term2: q = softmax(t/T); c = -(q - logsumexp(q)); p = softmax(s/T); loss = sum p c; ds = p (c - <p,c>) / T ----
+    float q[EPT], p[EPT];
+    float mt = -INFINITY, ms = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int k = lane + 32 * i;
+      q[i] = (k < K) ? teacher[size_t(b) * K + k] * inv_T : -INFINITY;
+      p[i] = (k < K) ? student[size_t(b) * K + k] * inv_T : -INFINITY;
+      mt = fmaxf(mt, q[i]);
+      ms = fmaxf(ms, p[i]);
+    }
+    mt = warp_max(mt);
+    ms = warp_max(ms);
+    float zt = 0.f, zs = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      q[i] = ex2f_((q[i] - mt) * kL2e);
+      p[i] = ex2f_((p[i] - ms) * kL2e);
+      zt += q[i];
+      zs += p[i];
+    }
+    const float izt = 1.f / warp_sum(zt), izs = 1.f / warp_sum(zs);
+    float se = 0.f;  // sum_k exp(q_k) over the VALID columns (q <= 1: no max subtraction needed)
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      q[i] *= izt;
+      p[i] *= izs;
+      if (lane + 32 * i < K) se += __expf(q[i]);
+    }
+    const float lse = __logf(warp_sum(se));
+    // row loss = sum_k p_k (lse - q_k) = lse - <p, q>   (sum p = 1);  d/ds_j = p_j (<p, q> - q_j) / T: written without
+    // lse so that the difference is taken between numbers in [0, 1], not between numbers near log(K)
+    float pq = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) pq = fmaf(p[i], q[i], pq);
+    pq = warp_sum(pq);
+    term2_row = beta * (lse - pq) / B;
+    const float gs = grad_scale * beta * inv_T / B;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) d_student[size_t(b) * K + k] = gs * p[i] * (pq - q[i]);
+    }
+    // ---- term1: alpha * CE(pred, label), classes strided over the lanes ----
+    if (pred) {
+      const long long y = label[b];
+      float m = -INFINITY;
+      for (int c = lane; c < n_classes; c += 32) m = fmaxf(m, pred[size_t(b) * n_classes + c]);
+      m = warp_max(m);
+      float z = 0.f;
+      for (int c = lane; c < n_classes; c += 32) z += __expf(pred[size_t(b) * n_classes + c] - m);
+      z = warp_sum(z);
+      const float logz = m + __logf(z);
+      const float g1 = grad_scale * alpha / B;
+      for (int c = lane; c < n_classes; c += 32) {
+        const float v = pred[size_t(b) * n_classes + c];
+        d_pred[size_t(b) * n_classes + c] = g1 * (__expf(v - logz) - (c == y ? 1.f : 0.f));
+        if (c == y) term1_lane = alpha * (logz - v) / B;  // exactly one lane
+      }
+    }
+  }
+  float lane_part = term1_lane + (lane == 0 ? term2_row : 0.f);
+  lane_part = warp_sum(lane_part);
+  block_atomic_sum(lane_part, loss, scratch);
+}
+
+template <int EPT>
+__global__ void __launch_bounds__(kLossWarps * 32) cosine_loss_kernel(const float* __restrict__ student,
+                                                                    const float* __restrict__ teacher,
+                                                                    float* __restrict__ loss, float* __restrict__ d_student,
+                                                                    int B, int K, float eps, float grad_scale) {
+  __shared__ float scratch[kLossWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * kLossWarps + warp;
+  float contrib = 0.f;
+  if (b < B) {
+    float s[EPT], t[EPT];
+    float ss = 0.f, tt = 0.f, st = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int k = lane + 32 * i;
+      s[i] = (k < K) ? student[size_t(b) * K + k] : 0.f;
+      t[i] = (k < K) ? teacher[size_t(b) * K + k] : 0.f;
+      ss = fmaf(s[i], s[i], ss);
+      tt = fmaf(t[i], t[i], tt);
+      st = fmaf(s[i], t[i], st);
+    }
+    ss = warp_sum(ss); tt = warp_sum(tt); st = warp_sum(st);
+    const float ns = fmaxf(sqrtf(ss), eps), nt = fmaxf(sqrtf(tt), eps);
+    const float cosv = st / (ns * nt);
+    contrib = (lane == 0) ? -cosv / B : 0.f;
+    if (b == 0 && lane == 0) contrib += 1.f;  // loss = 1 - mean cos
+    // d(-cos/B)/ds = -(1/B) (t / (ns nt) - cos s / ns^2)   (norm clamp inactive unless ||s|| < eps)
+    const float a = -grad_scale / (B * ns * nt), c2 = grad_scale * cosv / (B * ns * ns);
+    const bool clamped = sqrtf(ss) < eps;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) d_student[size_t(b) * K + k] = a * t[i] + (clamped ? 0.f : c2 * s[i]);
+    }
+  }
+  contrib = warp_sum(contrib);
+  block_atomic_sum(contrib, loss, scratch);
+}
+
+}  // namespace csn
+
+using namespace csn;
+
+extern "C" int csn_feature_dist_loss_fwd_bwd(const float* student, const float* teacher, const float* pred,
+                                             const long long* label, float* loss, float* d_student, float* d_pred, int B,
+                                             int K, int n_classes, float temperature, float alpha, float beta,
+                                             float grad_scale, void* stream) {
+  CSN_REQUIRE(student && teacher && loss && d_student, "csn_feature_dist_loss_fwd_bwd: null pointer");
+  CSN_REQUIRE(B >= 1 && K >= 1 && K <= 1024, "csn_feature_dist_loss_fwd_bwd: need B >= 1 and 1 <= K <= 1024 (got B=%d K=%d)", B, K);
+  CSN_REQUIRE(temperature != 0.f, "csn_feature_dist_loss_fwd_bwd: temperature must be non-zero");
+  CSN_REQUIRE(!pred || (label && d_pred && n_classes >= 1), "csn_feature_dist_loss_fwd_bwd: pred needs label, d_pred and n_classes");
+  cudaStream_t s = as_stream(stream);
+  CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  const int blocks = ceil_div(B, kLossWarps);
+#define CSN_FD(E) feature_dist_loss_kernel<E><<<blocks, kLossWarps * 32, 0, s>>>(student, teacher, pred, label, loss, d_student, \
+                                                                                 d_pred, B, K, n_classes, 1.f / temperature, alpha, beta, grad_scale)
+  if (K <= 128) CSN_FD(4);
+  else if (K <= 256) CSN_FD(8);
+  else if (K <= 512) CSN_FD(16);
+  else CSN_FD(32);
+#undef CSN_FD
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_cosine_loss_fwd_bwd(const float* student, const float* teacher, float* loss, float* d_student, int B, int K,
+                                       float eps, float grad_scale, void* stream) {
+  CSN_REQUIRE(student && teacher && loss && d_student, "csn_cosine_loss_fwd_bwd: null pointer");
+  CSN_REQUIRE(B >= 1 && K >= 1 && K <= 1024, "csn_cosine_loss_fwd_bwd: need B >= 1 and 1 <= K <= 1024 (got B=%d K=%d)", B, K);
+  cudaStream_t s = as_stream(stream);
+  CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  const int blocks = ceil_div(B, kLossWarps);
+#define CSN_CL(E) cosine_loss_kernel<E><<<blocks, kLossWarps * 32, 0, s>>>(student, teacher, loss, d_student, B, K, eps, grad_scale)
+  if (K <= 128) CSN_CL(4);
+  else if (K <= 256) CSN_CL(8);
+  else if (K <= 512) CSN_CL(16);
+  else CSN_CL(32);
+#undef CSN_CL
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}

@@ -165,6 +165,20 @@ int csn_dp_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, size
                           float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled,
                           float grad_scale, void* stream);
 
+/* ---- the losses LstmDistillFromDinoV2Train.py runs today, forward + backward -------------
+ * FeatureDistributionLoss.forward (LstmDistillFromDinoV2Train.py:118-140, live at :371):
+ *   loss = alpha * cross_entropy(pred, label) + beta * F.cross_entropy(softmax(teacher / T), softmax(student / T))
+ * -- the teacher probabilities are log-softmaxed once more and the student probabilities are the soft target, as
+ * written in the reference.  student/teacher [B,K] fp32 (K <= 1024), pred [B,n_classes] fp32 or NULL, label [B] int64.
+ * loss: device scalar (overwritten); d_student [B,K], d_pred [B,n_classes] = gradients * grad_scale.
+ * CosineSimilarityLoss.forward (LstmDistillFromDinoV2Train.py:36-43): loss = 1 - mean_b cos(student_b, teacher_b),
+ * nn.CosineSimilarity semantics (dim 1, each norm clamped at eps). */
+int csn_feature_dist_loss_fwd_bwd(const float* student, const float* teacher, const float* pred, const long long* label,
+                                  float* loss, float* d_student, float* d_pred, int B, int K, int n_classes,
+                                  float temperature, float alpha, float beta, float grad_scale, void* stream);
+int csn_cosine_loss_fwd_bwd(const float* student, const float* teacher, float* loss, float* d_student, int B, int K,
+                            float eps, float grad_scale, void* stream);
+
 /* ---- exact top-k retrieval -------------------------------------------------------
  * Replaces faiss.IndexFlatL2(d).add(gallery) / .search(query, k) as called by utils/Utilities.py:45-58 (evaluate) from
  * LstmDistillFromDinoV2Eval.py:333-380.  gallery [nb, d], query [nq, d] fp32 row-major on the device.  metric 0: squared

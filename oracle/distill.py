@@ -240,3 +240,21 @@ class DistillStepOracle:
         loss.backward()
         self.opt.step()
         return float(loss)
+
+
+# ---- the losses LstmDistillFromDinoV2Train.py runs today (pinned by tests/golden/alt_losses.npz, which the reference's
+# ---- own classes generated) ------------------------------------------------------------------------------------------
+def feature_distribution_loss(student, teacher, temperature, label, pred_label, alpha=0.5, beta=0.5):
+    """LstmDistillFromDinoV2Train.py:118-140: alpha * CE(pred_label, label) + beta * F.cross_entropy(softmax(teacher/T),
+    softmax(student/T)) -- teacher probabilities as the logits argument, student probabilities as the soft target."""
+    import torch.nn.functional as F
+    teacher_p = F.softmax(teacher / temperature, dim=-1)       # :124
+    student_p = F.softmax(student / temperature, dim=-1)       # :125
+    term1 = alpha * F.cross_entropy(pred_label, label)         # :128
+    term2 = beta * F.cross_entropy(teacher_p, student_p)       # :129
+    return term1 + term2
+
+
+def cosine_similarity_loss(student, teacher):
+    """LstmDistillFromDinoV2Train.py:36-43."""
+    return 1 - nn.CosineSimilarity()(student, teacher).mean()

@@ -168,15 +168,50 @@ def golden_lstm_step():
         np.savez(os.path.join(GOLD, f"distill_step_{tag}.npz"), versions=str(VERS), **out)
 
 
+def golden_alt_losses():
+    """FeatureDistributionLoss (live in LstmDistillFromDinoV2Train.py:371) and CosineSimilarityLoss (:36-43), run
+    through the REFERENCE'S OWN classes: inputs, loss, gradients w.r.t. the student features and the class logits."""
+    ref = import_reference("LstmDistillFromDinoV2Train")
+    g = torch.Generator().manual_seed(49)
+    out = {}
+    crit = ref.FeatureDistributionLoss(nepochs=12, warmup_teacher_temp=1.5, teacher_temp=0.22, warmup_teacher_temp_epochs=5)
+    out["fd_schedule"] = crit.teacher_temp_schedule.copy()
+    for i, (B, K, C, epoch) in enumerate([(6, 48, 40, 0), (5, 384, 40, 3), (9, 100, 7, 8)]):
+        s = torch.randn(B, K, generator=g, requires_grad=True)
+        t = torch.randn(B, K, generator=g) * 1.5
+        pred = torch.randn(B, C, generator=g, requires_grad=True)
+        label = torch.randint(0, C, (B,), generator=g)
+        loss = crit(s, t, epoch, label, pred_label=pred)
+        loss.backward()
+        out.update({f"fd_student{i}": s.detach().numpy(), f"fd_teacher{i}": t.numpy(), f"fd_pred{i}": pred.detach().numpy(),
+                    f"fd_label{i}": label.numpy(), f"fd_epoch{i}": np.int64(epoch), f"fd_loss{i}": loss.detach().numpy(),
+                    f"fd_dstudent{i}": s.grad.numpy(), f"fd_dpred{i}": pred.grad.numpy()})
+    out["fd_alpha"], out["fd_beta"] = np.float64(ref.HyperParams.alpha), np.float64(ref.HyperParams.beta)
+    cos = ref.CosineSimilarityLoss()
+    for i, (B, K) in enumerate([(4, 24), (7, 384)]):
+        s = torch.randn(B, K, generator=g, requires_grad=True)
+        t = torch.randn(B, K, generator=g)
+        loss = cos(s, t)
+        loss.backward()
+        out.update({f"cos_student{i}": s.detach().numpy(), f"cos_teacher{i}": t.numpy(), f"cos_loss{i}": loss.detach().numpy(),
+                    f"cos_dstudent{i}": s.grad.numpy()})
+    np.savez(os.path.join(GOLD, "alt_losses.npz"), versions=str(VERS), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     _init_pg()
+    if "--only-alt-losses" in sys.argv:
+        golden_alt_losses()
+        print("alt_losses.npz written")
+        return 0
     golden_dino_single()
     golden_dino_multicrop()
     golden_dino_head()
     golden_utils()
     golden_filters()
     golden_lstm_step()
+    golden_alt_losses()
     print("golden vectors written to", GOLD)
     for f in sorted(os.listdir(GOLD)):
         print("  ", f, os.path.getsize(os.path.join(GOLD, f)))
