@@ -96,3 +96,38 @@ def test_cli_flags():
     assert a.batch_size == 16 and a.num_epochs == 100 and a.learning_rate == 0.001 and a.seed == 43
     a = cli.build_parser().parse_args(["--batch_size", "256", "--num_epochs", "3"])
     assert a.batch_size == 256 and a.num_epochs == 3
+
+
+def test_schedules_match_reference_goldens(golden, tmp_path):
+    """cosine_scheduler against vectors produced by utils/utils.py:187-198; schedule application, last-layer freeze and
+    checkpoint round trip as LstmDistillation.py:540-544, :602, :634-646 use them."""
+    import torch
+    from cerebralsignalnetworks_b200 import schedules as S
+    g = golden("utils.npz")
+    np.testing.assert_allclose(S.cosine_scheduler(0.0005, 1e-6, 10, 7, warmup_epochs=2), g["cos_a"], rtol=1e-12)
+    np.testing.assert_allclose(S.cosine_scheduler(0.04, 0.4, 5, 3), g["cos_b"], rtol=1e-12)
+    np.testing.assert_allclose(S.cosine_scheduler(0.996, 1.0, 4, 5), g["cos_c"], rtol=1e-12)
+
+    class Opt:
+        param_groups = [{"lr": 0.0, "weight_decay": 0.0}, {"lr": 0.0, "weight_decay": 0.0}]
+    S.apply_schedules(Opt, 3, g["cos_a"], g["cos_b"])
+    assert Opt.param_groups[0] == {"lr": float(g["cos_a"][3]), "weight_decay": float(g["cos_b"][3])}
+    assert Opt.param_groups[1] == {"lr": float(g["cos_a"][3]), "weight_decay": 0.0}
+
+    net = torch.nn.ModuleDict({"mlp": torch.nn.Linear(3, 3), "last_layer": torch.nn.Linear(3, 2)})
+    for p in net.parameters():
+        p.grad = torch.ones_like(p)
+    S.cancel_gradients_last_layer(0, net, freeze_last_layer=1)
+    assert net["last_layer"].weight.grad is None and net["mlp"].weight.grad is not None
+    for p in net.parameters():
+        p.grad = torch.ones_like(p)
+    S.cancel_gradients_last_layer(1, net, freeze_last_layer=1)
+    assert net["last_layer"].weight.grad is not None
+
+    path = str(tmp_path / "checkpoint.pth")
+    S.save_checkpoint(path, student=net, epoch=7)
+    other = torch.nn.ModuleDict({"mlp": torch.nn.Linear(3, 3), "last_layer": torch.nn.Linear(3, 2)})
+    run = {"epoch": 0}
+    assert S.restart_from_checkpoint(path, run_variables=run, student=other) and run["epoch"] == 7
+    assert torch.equal(other["mlp"].weight, net["mlp"].weight)
+    assert S.restart_from_checkpoint(str(tmp_path / "missing.pth")) is False
