@@ -93,3 +93,29 @@ def test_full_size_properties():
     y_tbc = ops.sosfilt(a, sos, out_layout="TBC", out_dtype=torch.bfloat16)
     assert y_tbc.shape == (440, 256, 128)
     assert torch.allclose(y_tbc.float(), ya.permute(2, 0, 1), atol=3e-2)
+
+
+@pytest.mark.parametrize("B,C,T", [(2, 16, 36), (4, 16, 100), (1, 32, 440), (3, 5, 37), (2, 16, 4)])
+@pytest.mark.parametrize("layout,dtype", [("TBC", torch.bfloat16), ("TBC", torch.float32), ("BCT", torch.float32), ("BTC", torch.float32)])
+def test_filter_writes_stay_inside_the_output(B, C, T, layout, dtype):
+    """Guard bands around the input and the output (the pool has no compute-sanitizer): the streaming kernels read in
+    16-byte pieces and write whole tiles, so a tail bug would show up as a clobbered guard or a NaN pulled in."""
+    from cerebralsignalnetworks_b200 import ops
+    from oracle.filters import design_bandpass_sos, sosfilt_np
+    sos = design_bandpass_sos(5.0, 95.0, 1000.0, 4)
+    n = B * C * T
+    pad = 256
+    xin = torch.full((n + 2 * pad,), float("nan"), device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T)
+    x = xin[pad:pad + n].view(B, C, T)
+    x.copy_(torch.randn(B, C, T, device="cuda", generator=g))
+    yout = torch.full((n + 2 * pad,), 12288.0, device="cuda", dtype=dtype)
+    shape = {"BCT": (B, C, T), "BTC": (B, T, C), "TBC": (T, B, C)}[layout]
+    y = ops.sosfilt(x, sos, out_layout=layout, out_dtype=dtype, out=yout[pad:pad + n].view(shape))
+    torch.cuda.synchronize()
+    assert (yout[:pad].float() == 12288.0).all() and (yout[pad + n:].float() == 12288.0).all()
+    assert torch.isfinite(y.float()).all()
+    ref = sosfilt_np(sos, x.cpu().numpy())
+    perm = {"BCT": (0, 1, 2), "BTC": (0, 2, 1), "TBC": (2, 0, 1)}[layout]
+    tol = 2e-4 if dtype == torch.float32 else 3e-2
+    np.testing.assert_allclose(y.float().cpu().numpy(), ref.transpose(perm), atol=tol * max(1.0, np.abs(ref).max()))
