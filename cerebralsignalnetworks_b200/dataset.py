@@ -1,0 +1,88 @@
+"""GPU-resident EEG dataset.
+
+Takes the .pth dictionary written by ConvertToPth.py:170-201 ({"dataset": [{"eeg": Tensor[C, T_raw], "image": i,
+"label": k, "subject": s}, ...], "labels": [...], "images": [...], ...}) -- the file utils/PerilsEEGDataset.EEGDataset
+loads (:62) -- uploads the EEG tensors ONCE as a [N, C, T_raw] fp32 tensor and serves batches with one gather kernel
+(csn_gather_trials) instead of a per-item Python `__getitem__` + DataLoader collate + host-to-device copy.  Same item
+semantics as EEGDataset.__getitem__ (:541-573): crop [time_low, time_high), optional (x - mean) / std with the
+dataset-level scalars of :93-103 (mean of the per-item means, mean of the per-item unbiased stds)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_BCT, LAYOUT_BTC
+from .ops import _p, _stream, call
+
+
+class DeviceEEGDataset:
+    def __init__(self, loaded, time_low=20, time_high=480, apply_norm_with_stds_and_means=False, device="cuda"):
+        _lib.require_gpu()
+        if isinstance(loaded, str):
+            loaded = torch.load(loaded, map_location="cpu", weights_only=False)
+        items = loaded["dataset"]
+        if len(items) == 0:
+            raise _lib.CsnError("empty dataset")
+        self.class_labels = list(loaded.get("labels", []))
+        self.image_names = list(loaded.get("images", []))
+        self.time_low, self.time_high = int(time_low), int(time_high)
+        self.apply_norm_with_stds_and_means = bool(apply_norm_with_stds_and_means)
+        # dataset-level scalars exactly as utils/PerilsEEGDataset.py:93-103 accumulates them (stored dtype, torch's
+        # unbiased std, arithmetic mean over items)
+        mean = sum(it["eeg"].mean() for it in items) / len(items)
+        std = sum(it["eeg"].std() for it in items) / len(items)
+        self.mean, self.std = float(mean), float(std)
+        shapes = {tuple(it["eeg"].shape) for it in items}
+        if len(shapes) != 1:
+            raise _lib.CsnError("trials of different shape cannot share one resident tensor: %s" % sorted(shapes))
+        self.device = torch.device(device)
+        self.eeg = torch.stack([it["eeg"].float() for it in items]).contiguous().to(self.device)  # [N, C, T_raw]
+        self.labels = torch.tensor([int(it["label"]) for it in items], dtype=torch.int64, device=self.device)
+        self.image_index = torch.tensor([int(it["image"]) for it in items], dtype=torch.int64, device=self.device)
+        self.N, self.C, self.T_raw = self.eeg.shape
+        if not (0 <= self.time_low < self.time_high <= self.T_raw):
+            raise _lib.CsnError("need 0 <= time_low < time_high <= %d" % self.T_raw)
+
+    def __len__(self):
+        return self.N
+
+    @property
+    def samples(self):
+        return self.time_high - self.time_low
+
+    def _gather(self, indices, layout):
+        idx = torch.as_tensor(indices, dtype=torch.int64, device=self.device).contiguous()
+        if idx.dim() != 1:
+            raise _lib.CsnError("indices must be one-dimensional")
+        if idx.numel() and (int(idx.max()) >= self.N or int(idx.min()) < -self.N):
+            raise IndexError("trial index out of range for %d trials" % self.N)
+        B, T = idx.numel(), self.samples
+        shape = (B, self.C, T) if layout == LAYOUT_BCT else (B, T, self.C)
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        mean, std = (self.mean, self.std) if self.apply_norm_with_stds_and_means else (0.0, 1.0)
+        call("csn_gather_trials", _p(self.eeg), _p(idx), _p(out), self.N, self.C, self.T_raw, B, self.time_low,
+             self.time_high, float(mean), float(std), layout, _stream())
+        return out, idx
+
+    def batch(self, indices):
+        """-> (eeg [B, C, T] float32 in the stored layout -- feed it to DistillTrainStep.step / Model.encode_trials --,
+        labels [B] int64, image indices [B] int64), all on the GPU."""
+        out, idx = self._gather(indices, LAYOUT_BCT)
+        return out, self.labels[idx], self.image_index[idx]
+
+    def batch_btc(self, indices):
+        """Same batch in the DataLoader layout [B, T, C] (`eeg.t()[time_low:time_high]` per item), for Model.forward."""
+        out, idx = self._gather(indices, LAYOUT_BTC)
+        return out, self.labels[idx], self.image_index[idx]
+
+    def epoch_batches(self, batch_size, shuffle=True, generator=None, drop_last=True, rank=0, world=1):
+        """Index batches of one epoch; with world > 1 every rank takes its contiguous share of each global batch
+        (DistributedSampler + drop_last of LstmDistillation.py:406-414)."""
+        order = torch.randperm(self.N, generator=generator, device="cpu") if shuffle else torch.arange(self.N)
+        per = batch_size * world
+        n_full = self.N // per
+        for k in range(n_full):
+            g = order[k * per:(k + 1) * per]
+            yield g[rank * batch_size:(rank + 1) * batch_size]
+        if not drop_last and world == 1 and self.N % per:
+            yield order[n_full * per:]

@@ -179,6 +179,14 @@ int csn_feature_dist_loss_fwd_bwd(const float* student, const float* teacher, co
 int csn_cosine_loss_fwd_bwd(const float* student, const float* teacher, float* loss, float* d_student, int B, int K,
                             float eps, float grad_scale, void* stream);
 
+/* ---- GPU-resident dataset batches ------------------------------------------------------
+ * src [N, C, T_raw] fp32: the stacked "eeg" tensors of the .pth file ConvertToPth.py:170-201 writes.  For every b:
+ * trial idx[b] (int64, negative counts from the end), samples [time_low, time_high), (x - mean) / std (pass 0 / 1 for no
+ * normalisation) -- the per-item work of EEGDataset.__getitem__, utils/PerilsEEGDataset.py:541-573.  out is
+ * [B, C, T] (CSN_LAYOUT_BCT, what csn_sosfilt_f32 consumes) or [B, T, C] (CSN_LAYOUT_BTC, the DataLoader layout). */
+int csn_gather_trials(const float* src, const long long* idx, float* out, int N, int C, int T_raw, int B, int time_low,
+                      int time_high, float mean, float std, int out_layout, void* stream);
+
 /* ---- exact top-k retrieval -------------------------------------------------------
  * Replaces faiss.IndexFlatL2(d).add(gallery) / .search(query, k) as called by utils/Utilities.py:45-58 (evaluate) from
  * LstmDistillFromDinoV2Eval.py:333-380.  gallery [nb, d], query [nq, d] fp32 row-major on the device.  metric 0: squared

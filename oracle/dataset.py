@@ -1,0 +1,26 @@
+"""ORACLE (test infrastructure only).  CPU restatement of what utils/PerilsEEGDataset.EEGDataset does to the EEG
+tensors of the .pth file (ConvertToPth.py:170-201): dataset-level mean / std (:93-103) and the per-item transform of
+`__getitem__` on the default path (:541-573: float, transpose to [T_raw, C], crop [time_low, time_high), optional
+(x - mean) / std).  Pinned by tests/golden/dataset.npz, which oracle/make_golden.py produced by running the reference's
+own EEGDataset class on a small synthetic .pth file."""
+from __future__ import annotations
+
+import torch
+
+
+def dataset_scalars(items):
+    """:93-103 -- mean of the per-item means and mean of the per-item (unbiased) standard deviations."""
+    mean = std = 0
+    for it in items:
+        mean += it["eeg"].mean()
+        std += it["eeg"].std()
+    return float(mean / len(items)), float(std / len(items))
+
+
+def item_transform(eeg_ct, time_low, time_high, mean=None, std=None):
+    """:541-573 on the default path -> [T, C] float32."""
+    eeg = eeg_ct.float().t()                 # :542, :551
+    eeg = eeg[time_low:time_high, :]          # :569
+    if mean is not None:
+        eeg = (eeg - mean) / std              # :572-573
+    return eeg

@@ -198,9 +198,53 @@ def golden_alt_losses():
     np.savez(os.path.join(GOLD, "alt_losses.npz"), versions=str(VERS), **out)
 
 
+def golden_dataset():
+    """The reference's own EEGDataset (utils/PerilsEEGDataset.py) on a small synthetic .pth file in the schema of
+    ConvertToPth.py:170-201: dataset-level mean / std and the EEG tensor of every item, with and without normalisation."""
+    import tempfile
+    from PIL import Image
+    mod = import_reference("utils.PerilsEEGDataset")
+    rng = np.random.default_rng(50)
+    N, C, T_raw, lo, hi = 7, 6, 50, 5, 41
+    classes = ["n01440764", "n01443537", "n01484850"]
+    images = [f"{classes[i % 3]}_{100 + i}" for i in range(N)]
+    data = {"dataset": [], "labels": classes, "images": images, "means": [], "stddevs": []}
+    for i in range(N):
+        data["dataset"].append({"eeg": torch.from_numpy(rng.normal(3.0, 2.0, size=(C, T_raw))), "image": i,
+                                "label": i % 3, "subject": 1})
+    out = {"eeg_raw": np.stack([d["eeg"].numpy() for d in data["dataset"]]), "labels": np.array([d["label"] for d in data["dataset"]]),
+           "time_low": np.int64(lo), "time_high": np.int64(hi)}
+    with tempfile.TemporaryDirectory() as tmp:
+        pth = os.path.join(tmp, "spampinato-1-synthetic.pth")
+        torch.save(data, pth)
+        root = os.path.join(tmp, "images")
+        with open(os.path.join(tmp, "labels.txt"), "w"):
+            pass
+        os.makedirs(root)
+        with open(os.path.join(root, "labels.txt"), "w") as f:
+            for k, c in enumerate(classes):
+                f.write(f"{c} {k + 1} class{k}\n")
+        for name in images:
+            os.makedirs(os.path.join(root, name.split("_")[0]), exist_ok=True)
+            Image.new("RGB", (8, 8), (10, 20, 30)).save(os.path.join(root, name.split("_")[0], name + ".JPEG"))
+        for tag, norm in (("plain", False), ("norm", True)):
+            ds = mod.EEGDataset(pth, None, subset="train", time_low=lo, time_high=hi, imagesRoot=root,
+                                apply_norm_with_stds_and_means=norm, inference_mode=False)
+            ds.isDataTransformed = False  # the constructor marks the data "transformed"; __getitem__ crops only when it is not
+            out[f"mean_{tag}"], out[f"std_{tag}"] = np.float64(float(ds.mean)), np.float64(float(ds.std))
+            items = [ds[i] for i in range(len(ds))]
+            out[f"items_{tag}"] = np.stack([it[0].numpy() for it in items])   # [N, T, C]
+            out[f"labels_{tag}"] = np.array([int(it[1]) for it in items])
+    np.savez(os.path.join(GOLD, "dataset.npz"), versions=str(VERS), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     _init_pg()
+    if "--only-dataset" in sys.argv:
+        golden_dataset()
+        print("dataset.npz written")
+        return 0
     if "--only-alt-losses" in sys.argv:
         golden_alt_losses()
         print("alt_losses.npz written")
@@ -212,6 +256,7 @@ def main():
     golden_filters()
     golden_lstm_step()
     golden_alt_losses()
+    golden_dataset()
     print("golden vectors written to", GOLD)
     for f in sorted(os.listdir(GOLD)):
         print("  ", f, os.path.getsize(os.path.join(GOLD, f)))

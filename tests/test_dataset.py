@@ -1,0 +1,83 @@
+"""GPU-resident dataset: oracle restatement against vectors produced by the reference's own
+EEGDataset (CPU), and the gather kernel against the same vectors (GPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD, allow_pickle=True)
+
+
+def _loaded(gold):
+    raw = gold["eeg_raw"]
+    return {"dataset": [{"eeg": torch.from_numpy(raw[i]), "image": i, "label": int(gold["labels"][i]), "subject": 1}
+                        for i in range(len(raw))],
+            "labels": ["a", "b", "c"], "images": [f"img{i}" for i in range(len(raw))]}
+
+
+def test_oracle_item_transform_matches_reference_dataset(gold):
+    from oracle.dataset import dataset_scalars, item_transform
+    loaded = _loaded(gold)
+    mean, std = dataset_scalars(loaded["dataset"])
+    assert mean == pytest.approx(float(gold["mean_plain"]), rel=1e-12) and std == pytest.approx(float(gold["std_plain"]), rel=1e-12)
+    lo, hi = int(gold["time_low"]), int(gold["time_high"])
+    for i, it in enumerate(loaded["dataset"]):
+        np.testing.assert_array_equal(item_transform(it["eeg"], lo, hi).numpy(), gold["items_plain"][i])
+        np.testing.assert_allclose(item_transform(it["eeg"], lo, hi, mean, std).numpy(), gold["items_norm"][i], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("norm", [False, True])
+def test_device_dataset_batches_match_reference_items(gold, norm):
+    from cerebralsignalnetworks_b200.dataset import DeviceEEGDataset
+    lo, hi = int(gold["time_low"]), int(gold["time_high"])
+    ds = DeviceEEGDataset(_loaded(gold), time_low=lo, time_high=hi, apply_norm_with_stds_and_means=norm)
+    assert len(ds) == 7 and ds.samples == hi - lo
+    assert ds.mean == pytest.approx(float(gold["mean_plain"]), rel=1e-12) and ds.std == pytest.approx(float(gold["std_plain"]), rel=1e-12)
+    items = gold["items_norm" if norm else "items_plain"]            # [N, T, C]
+    idx = [3, 0, 6, 6, -1, 2]
+    btc, labels, img = ds.batch_btc(idx)
+    bct, labels2, _ = ds.batch(idx)
+    want = items[[3, 0, 6, 6, 6, 2]]
+    if norm:
+        np.testing.assert_allclose(btc.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+    else:
+        np.testing.assert_array_equal(btc.cpu().numpy(), want)
+    assert torch.equal(bct, btc.transpose(1, 2))
+    np.testing.assert_array_equal(labels.cpu().numpy(), gold["labels"][[3, 0, 6, 6, 6, 2]])
+    assert torch.equal(labels, labels2) and img.tolist() == [3, 0, 6, 6, 6, 2]
+    full = DeviceEEGDataset(_loaded(gold), time_low=0, time_high=50)   # the reference's default state: no crop
+    np.testing.assert_array_equal(full.batch(range(7))[0].cpu().numpy(), gold["eeg_raw"].astype(np.float32))
+    with pytest.raises(IndexError):
+        ds.batch([7])
+    assert ds.batch([])[0].shape == (0, 6, hi - lo)
+
+
+@pytest.mark.gpu
+def test_device_dataset_feeds_the_train_step(gold):
+    """Wide trials (more than one channel tile, T not a multiple of 32) + epoch batching + one fused step."""
+    import cerebralsignalnetworks_b200 as csn
+    from cerebralsignalnetworks_b200.dataset import DeviceEEGDataset
+    g = torch.Generator().manual_seed(1)
+    N, C, T_raw = 20, 40, 75
+    loaded = {"dataset": [{"eeg": torch.randn(C, T_raw, generator=g), "image": i, "label": i % 4} for i in range(N)],
+              "labels": list("abcd"), "images": [str(i) for i in range(N)]}
+    ds = DeviceEEGDataset(loaded, time_low=7, time_high=71)
+    batches = list(ds.epoch_batches(8, generator=torch.Generator().manual_seed(0)))
+    assert len(batches) == 2 and all(len(b) == 8 for b in batches)
+    shares = [list(ds.epoch_batches(4, shuffle=False, rank=r, world=2)) for r in range(2)]
+    assert shares[0][0].tolist() == [0, 1, 2, 3] and shares[1][0].tolist() == [4, 5, 6, 7]
+    eeg, labels, _ = ds.batch(batches[0])
+    ref = torch.stack([loaded["dataset"][i]["eeg"][:, 7:71] for i in batches[0].tolist()])
+    assert torch.equal(eeg.cpu(), ref)
+    model = csn.Model(C, 32, 1, 24, include_top=False, compute_dtype=torch.float32).cuda()
+    step = csn.DistillTrainStep(model, csn.DINOLoss(24, 1, 1.5, 0.22, 5, 10).cuda(), lr=1e-3,
+                                sos=csn.EEGFilters(1000.0).sos(5.0, 95.0, 4), use_cuda_graph=False)
+    loss = step.step(eeg, torch.randn(8, 24, device="cuda"), 0)
+    assert torch.isfinite(loss)
