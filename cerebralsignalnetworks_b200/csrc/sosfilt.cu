@@ -45,6 +45,32 @@ __device__ __forceinline__ float biquad_cascade(float v, float (&s1)[NSEC], floa
   return v;
 }
 
+// One 32-sample chunk through the cascade with the sections SKEWED in time: in iteration j section k works on sample
+// j - k, fed by what section k-1 produced one iteration earlier, so the NSEC section updates of an iteration are
+// independent of each other (instruction-level parallelism NSEC instead of one dependent chain per sample; a warp
+// issues in order and only ~1.7 warps share a scheduler at cfg2).  Same operations on the same operands as
+// biquad_cascade sample by sample: results are bit-identical.  `emit(idx, y)` receives the outputs in order.
+template <int NSEC, typename Emit>
+__device__ __forceinline__ void cascade_chunk_skewed(const float (&x)[kTC], float (&s1)[NSEC], float (&s2)[NSEC],
+                                                     const SosCoef& c, Emit emit) {
+  float p[NSEC];
+#pragma unroll
+  for (int j = 0; j < kTC + NSEC - 1; ++j) {
+#pragma unroll
+    for (int k = NSEC - 1; k >= 0; --k) {
+      const int idx = j - k;
+      if (idx >= 0 && idx < kTC) {
+        const float v = (k == 0) ? x[idx] : p[k - 1];
+        const float y = fmaf(c.b0[k], v, s1[k]);
+        s1[k] = fmaf(-c.a1[k], y, fmaf(c.b1[k], v, s2[k]));
+        s2[k] = fmaf(-c.a2[k], y, c.b2[k] * v);
+        p[k] = y;
+        if (k == NSEC - 1) emit(idx, y);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ size_t out_index(int layout, long long r, int t, int Bn, int C, int T) {
   // r = b*C + c
   if (layout == CSN_LAYOUT_BCT) return size_t(r) * T + t;
@@ -249,21 +275,16 @@ __global__ void __launch_bounds__(32) sosfilt_warp_kernel(const float* __restric
     else cp_async_commit();
 
     float* row = in_tile + buf * R * kRS + lane * kRS;
+    float xin[kTC];
 #pragma unroll
     for (int q = 0; q < kTC / 4; ++q) {
-      float4 v = *reinterpret_cast<float4*>(row + q * 4);
-      v.x = biquad_cascade<NSEC>(v.x, s1, s2, coef);
-      v.y = biquad_cascade<NSEC>(v.y, s1, s2, coef);
-      v.z = biquad_cascade<NSEC>(v.z, s1, s2, coef);
-      v.w = biquad_cascade<NSEC>(v.w, s1, s2, coef);
-      if constexpr (TIME_MAJOR) {
-        out_tile[(q * 4 + 0) * R + lane] = v.x;
-        out_tile[(q * 4 + 1) * R + lane] = v.y;
-        out_tile[(q * 4 + 2) * R + lane] = v.z;
-        out_tile[(q * 4 + 3) * R + lane] = v.w;
-      } else {
-        *reinterpret_cast<float4*>(row + q * 4) = v;
-      }
+      const float4 v = *reinterpret_cast<const float4*>(row + q * 4);
+      xin[q * 4 + 0] = v.x; xin[q * 4 + 1] = v.y; xin[q * 4 + 2] = v.z; xin[q * 4 + 3] = v.w;
+    }
+    if constexpr (TIME_MAJOR) {
+      cascade_chunk_skewed<NSEC>(xin, s1, s2, coef, [&](int idx, float yv) { out_tile[idx * R + lane] = yv; });
+    } else {
+      cascade_chunk_skewed<NSEC>(xin, s1, s2, coef, [&](int idx, float yv) { row[idx] = yv; });
     }
     __syncwarp();
 
