@@ -70,6 +70,9 @@ def _cos(a, b):
 
 @pytest.mark.parametrize("T,B,I,H", [(6, 4, 16, 16), (50, 5, 32, 64), (30, 37, 128, 128), (24, 3, 96, 96), (440, 16, 128, 128),
                                      (16, 300, 64, 128),
+                                     # edges of the fused-projection kernel: T below one block of timesteps, single trial,
+                                     # NV = 8 tiles (two timesteps per block), smallest sizes, and I > 128 (hoisted projection)
+                                     (1, 2, 8, 8), (2, 1, 16, 32), (3, 5, 8, 128), (9, 700, 32, 32), (17, 640, 16, 64), (5, 4, 136, 64),
                                      # large-hidden path (per-step tcgen05 GEMM with the fused cell epilogue), cfg 4 sizes
                                      (12, 5, 64, 256), (20, 130, 128, 512), (9, 3, 24, 136)])
 @pytest.mark.parametrize("mode", ["last", "both"])
@@ -86,6 +89,9 @@ def test_bf16_tensor_core_layer(T, B, I, H, mode):
     assert (h - ref_h).abs().max().item() <= 3e-2, (h - ref_h).abs().max().item()
     for a, b, n in zip(gr, ref_g, ["dw_ih", "dw_hh", "db_ih", "db_hh"]):
         assert torch.isfinite(a).all(), n
+        if b.norm().item() == 0.0:  # T = 1: no recurrent term, dW_hh is exactly zero
+            assert a.abs().max().item() == 0.0, n
+            continue
         rel = ((a - b).norm() / (b.norm() + 1e-30)).item()
         assert _cos(a, b) >= 0.995 and rel <= 6e-2, (n, _cos(a, b), rel)
     rel = ((dx - ref_dx).norm() / (ref_dx.norm() + 1e-30)).item()
@@ -98,6 +104,20 @@ def test_bf16_unsupported_shape_is_an_error_not_a_fallback():
         ops.lstm_layer_bytes(10, 4, 63, 128, torch.bfloat16)  # TMA needs 16-byte rows: I % 8 != 0 is rejected
     with pytest.raises(_lib.CsnError):
         ops.lstm_layer_bytes(10, 4, 64, 100, torch.bfloat16)
+
+
+@pytest.mark.parametrize("T,B,I,H", [(13, 6, 64, 128), (2000, 4, 64, 128), (7, 3, 136, 96), (11, 9, 32, 256)])
+def test_bf16_inference_only_forward(T, B, I, H):
+    """training = 0 (no BPTT reserve): the path Model.encode_trials takes, including the 2000-sample trials of config 5."""
+    from cerebralsignalnetworks_b200 import ops
+    g = torch.Generator().manual_seed(T + H)
+    x = torch.randn(T, B, I, generator=g) * 0.5
+    w = _weights(I, H, 3)
+    ref_h, _, _ = _ref_layer(x.bfloat16().float(), w, None, torch.zeros(B, H))
+    h, _, _ = ops.lstm_layer_fwd(x.cuda().bfloat16().contiguous(), *[t.cuda() for t in w], torch.bfloat16, False)
+    torch.cuda.synchronize()
+    # bf16 round-off accumulates slowly along a long sequence (the cell state is fp32): same 3e-2 bound holds
+    assert (h.float().cpu() - ref_h).abs().max().item() <= 3e-2
 
 
 def test_zero_weights_give_zero_state():
