@@ -3,8 +3,10 @@
 The reference trainer's CLI surface (LstmDistillFromDinoV2Train.py:150-231: --batch_size, --num_epochs,
 --learning_rate, --seed, --log_dir ...) driving the B200 train step.  There is no dataset or DINOv2 checkpoint
 offline, so trials and teacher features are synthetic unless --eeg_dataset points at a .pth written by
-ConvertToPth.py:170-201 that carries precomputed `image_features`.  Launch under torchrun for data parallel:
-one process per GPU, batch sharded, NCCL all-reduce of gradients + centre.
+ConvertToPth.py:170-201: its trials are then served from HBM by dataset.DeviceEEGDataset (crop
+[--time_low, --time_high)), and the teacher features come from its `image_features` entry ([n_images, output_size],
+one row per entry of "images") when present, else from a seeded random table (one fixed row per image).  Launch under
+torchrun for data parallel: one process per GPU, batch sharded, gradients + centre exchanged once per step.
 """
 from __future__ import annotations
 
@@ -26,6 +28,8 @@ def build_parser():
     p.add_argument("--lstm_layers", type=int, default=1)
     p.add_argument("--output_size", type=int, default=384, help="teacher feature width (384 ViT-S, 768 ViT-B)")
     p.add_argument("--samples", type=int, default=440)
+    p.add_argument("--time_low", type=int, default=20, help="first sample kept of a stored trial (EEGDataset time_low)")
+    p.add_argument("--time_high", type=int, default=460, help="one past the last sample kept (EEGDataset time_high)")
     p.add_argument("--trials_per_epoch", type=int, default=2048)
     p.add_argument("--warmup_teacher_temp", type=float, default=1.5)
     p.add_argument("--teacher_temp", type=float, default=0.22)
@@ -69,11 +73,37 @@ def main(argv=None):
     if per_rank * world != FLAGS.batch_size:
         raise SystemExit("--batch_size must be divisible by the number of ranks")
     gen = torch.Generator(device="cuda").manual_seed(FLAGS.seed + rank)
+    ds = feats_table = None
+    if FLAGS.eeg_dataset:
+        from .dataset import DeviceEEGDataset
+        loaded = torch.load(FLAGS.eeg_dataset, map_location="cpu", weights_only=False)
+        ds = DeviceEEGDataset(loaded, time_low=FLAGS.time_low, time_high=FLAGS.time_high)
+        if ds.C != FLAGS.input_size:
+            raise SystemExit("--input_size %d does not match the dataset's %d channels" % (FLAGS.input_size, ds.C))
+        n_images = max(len(ds.image_names), int(ds.image_index.max()) + 1)
+        if "image_features" in loaded:
+            feats_table = torch.as_tensor(loaded["image_features"]).float().reshape(n_images, -1).cuda()
+            if feats_table.shape[1] != FLAGS.output_size:
+                raise SystemExit("image_features are %d-d, --output_size is %d" % (feats_table.shape[1], FLAGS.output_size))
+        else:
+            if rank == 0:
+                print("no image_features in the dataset file: using a seeded random teacher-feature table", flush=True)
+            feats_table = torch.randn(n_images, FLAGS.output_size, device="cuda",
+                                      generator=torch.Generator(device="cuda").manual_seed(FLAGS.seed))
+        steps = len(ds) // FLAGS.batch_size
+        if steps == 0:
+            raise SystemExit("--batch_size %d exceeds the dataset (%d trials)" % (FLAGS.batch_size, len(ds)))
     t_axis = torch.arange(FLAGS.samples, device="cuda") / FLAGS.fs
-    steps = max(1, FLAGS.trials_per_epoch // FLAGS.batch_size)
+    if ds is None:
+        steps = max(1, FLAGS.trials_per_epoch // FLAGS.batch_size)
     for epoch in range(FLAGS.num_epochs):
         t0, losses = time.time(), []
-        for _ in range(steps):
+        if ds is not None:
+            order = torch.Generator().manual_seed(FLAGS.seed + epoch)  # same permutation on every rank
+            for idx in ds.epoch_batches(per_rank, shuffle=True, generator=order, rank=rank, world=world):
+                eeg, _, img = ds.batch(idx)
+                losses.append(step.step(eeg, feats_table[img].contiguous(), epoch))
+        for _ in range(steps if ds is None else 0):
             eeg = torch.randn(per_rank, FLAGS.input_size, FLAGS.samples, device="cuda", generator=gen)
             eeg += 0.5 * torch.sin(2 * torch.pi * 40.0 * t_axis)  # utils/PerilsEEGDataset.py:140-147
             feats = torch.randn(per_rank, FLAGS.output_size, device="cuda", generator=gen)

@@ -41,9 +41,9 @@ for name, p in (("forward", buf[:512].view(64, 8).cpu()), ("backward", buf[512:1
         period = int(p[t + 1, 0] - p[t, 0])
         a = int(p[t, 1] - p[t, 0]); b = int(p[t, 2] - p[t, 1]); c = int(p[t, 3] - p[t, 2])
         d = int(p[t + 1, 4] - p[t, 3]); e = int(p[t + 1, 5] - p[t + 1, 4]); f = int(p[t + 1, 0] - p[t + 1, 5])
-        w = int(p[t + 1, 0] - p[t + 1, 6])   # how long thread 0 actually waited on the accumulator barrier
+        wa = int(p[t + 1, 0] - p[t + 1, 6])   # how long thread 0 actually waited on the accumulator barrier
         st = int(p[t, 7] - p[t, 3]) if name == "backward" else 0  # off-path stores after the arrive
-        rows.append((period, a, b, c, d, e, f, w, st))
+        rows.append((period, a, b, c, d, e, f, wa, st))
         if t < 6:
             print(f"{t:3d} | {period:6d} | {a:6d} | {b:6d} | {c:6d} | {d:6d} | {e:6d} | {f:6d}")
     print("periods t=3..39:", [r[0] for r in rows])

@@ -81,3 +81,22 @@ def test_device_dataset_feeds_the_train_step(gold):
                                 sos=csn.EEGFilters(1000.0).sos(5.0, 95.0, 4), use_cuda_graph=False)
     loss = step.step(eeg, torch.randn(8, 24, device="cuda"), 0)
     assert torch.isfinite(loss)
+
+
+@pytest.mark.gpu
+def test_cli_trains_from_a_pth_dataset(tmp_path, capsys):
+    """--batch_size / --num_epochs CLI (LstmDistillFromDinoV2Train.py:150-231) on a ConvertToPth-style file served from HBM."""
+    from cerebralsignalnetworks_b200 import cli
+    g = torch.Generator().manual_seed(2)
+    N, C, T_raw = 24, 16, 120
+    loaded = {"dataset": [{"eeg": torch.randn(C, T_raw, generator=g), "image": i % 10, "label": i % 4, "subject": 1} for i in range(N)],
+              "labels": list("abcd"), "images": [f"n0_{i}" for i in range(10)], "image_features": torch.randn(10, 24, generator=g)}
+    path = str(tmp_path / "spampinato-synthetic.pth")
+    torch.save(loaded, path)
+    cli.main(["--eeg_dataset", path, "--batch_size", "8", "--num_epochs", "2", "--input_size", "16", "--lstm_size", "32",
+              "--output_size", "24", "--time_low", "10", "--time_high", "110", "--log_dir", str(tmp_path / "logs"),
+              "--warmup_teacher_temp_epochs", "1", "--precision", "fp32"])
+    out = capsys.readouterr().out
+    assert "EPOCH 0 train_loss" in out and "EPOCH 1 train_loss" in out
+    sd = torch.load(str(tmp_path / "logs" / "lstm_dinov2_last.pth"))
+    assert "lstm.weight_ih_l0" in sd and all(torch.isfinite(v).all() for v in sd.values())
