@@ -87,8 +87,8 @@ constexpr uint32_t kLboA = 2048, kSboA = 128;  // W_ih operand in shared memory:
 
 // W_ih [4H, I] fp32 -> the bf16 shared-memory image of the four 128 x KI K-major A-operand blocks (zero padded), so a
 // recurrence CTA stages it with four bulk copies.
-__global__ void pack_wih_smem_image_kernel(const float* __restrict__ w_ih, __nv_bfloat16* __restrict__ img, int H, int I, int KI) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 4 * 128 * KI, k fastest
+__device__ __forceinline__ void pack_wih_element(const float* __restrict__ w_ih, __nv_bfloat16* __restrict__ img, int H, int I,
+                                                 int KI, int idx) {  // idx over 4 * 128 * KI, k fastest
   if (idx >= 4 * 128 * KI) return;
   const int k = idx % KI, r = (idx / KI) & 127, g = idx / (KI * 128);
   const float v = (r < H && k < I) ? w_ih[size_t(g * H + r) * I + k] : 0.f;
@@ -100,8 +100,8 @@ __global__ void pack_wih_smem_image_kernel(const float* __restrict__ w_ih, __nv_
 // recurrence CTA fills its tensor memory with 64 coalescable 16-byte loads per thread instead of 512 strided
 // scalar fp32 loads.  transposed = 0: forward operand, lane = hidden unit u, K = input unit k  (W_hh[g*H+u][k]);
 // transposed = 1: backward operand, lane = k, K = u (W_hh^T).
-__global__ void pack_whh_tmem_image_kernel(const float* __restrict__ w_hh, uint32_t* __restrict__ img, int H, int transposed) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 4 * 128 * 64
+__device__ __forceinline__ void pack_whh_element(const float* __restrict__ w_hh, uint32_t* __restrict__ img, int H, int transposed,
+                                                 int idx) {  // idx over 4 * 128 * 64
   if (idx >= 4 * 128 * 64) return;
   int g, lane, c;
   if (!transposed) { c = idx & 63; lane = (idx >> 6) & 127; g = idx >> 13; }   // consecutive threads -> consecutive k
@@ -119,6 +119,21 @@ __global__ void pack_whh_tmem_image_kernel(const float* __restrict__ w_hh, uint3
   }
   __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
   img[(size_t(g) * 128 + lane) * 64 + c] = *reinterpret_cast<uint32_t*>(&bb);
+}
+
+// ONE preparation launch per layer call: the W_hh tensor-memory image, plus (forward, fused projection) the W_ih
+// shared-memory image, or (backward) the zeroing of the bias-gradient accumulators -- three tiny launches folded into
+// one (each boundary costs ~2.5 us of a 600 us step).
+__global__ void lstm_prepare_kernel(const float* __restrict__ w_hh, uint32_t* __restrict__ whh_img, int H, int transposed,
+                                    const float* __restrict__ w_ih, __nv_bfloat16* __restrict__ wih_img, int I, int KI,
+                                    float* __restrict__ zero_a, float* __restrict__ zero_b, int n_zero) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  pack_whh_element(w_hh, whh_img, H, transposed, idx);
+  if (wih_img) pack_wih_element(w_ih, wih_img, H, I, KI, idx);
+  if (idx < n_zero) {
+    if (zero_a) zero_a[idx] = 0.f;
+    if (zero_b) zero_b[idx] = 0.f;
+  }
 }
 
 // image -> tensor memory: thread `row` (TMEM lane) copies its 4 x 64 packed columns
@@ -866,8 +881,6 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   if (fused_projection(I)) {
     uint8_t* img = reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2) + kWimgBytes;
     const int KI = ceil_div(I, 16) * 16;
-    pack_wih_smem_image_kernel<<<ceil_div(4 * 128 * KI, 256), 256, 0, s>>>(w_ih, reinterpret_cast<__nv_bfloat16*>(img), H, I, KI);
-    CSN_LAUNCH_CHECK();
     fx = FusedX{reinterpret_cast<const __nv_bfloat16*>(x), img, b_ih, I, KI};
   } else {
     CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
@@ -880,8 +893,13 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   __nv_bfloat16* hs = (__nv_bfloat16*)h_seq;
   uint32_t* w_img = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 4) +
                                                 align256(size_t(4) * H * I * 2));
-  pack_whh_tmem_image_kernel<<<4 * 128 * 64 / 256, 256, 0, s>>>(w_hh, w_img, H, 0);
-  CSN_LAUNCH_CHECK();
+  {
+    const int n_idx = std::max(4 * 128 * 64, fx.x ? 4 * 128 * fx.KI : 0);
+    lstm_prepare_kernel<<<ceil_div(n_idx, 256), 256, 0, s>>>(
+        w_hh, w_img, H, 0, w_ih, fx.x ? reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(fx.wih_img)) : nullptr, I, fx.KI,
+        nullptr, nullptr, 0);
+    CSN_LAUNCH_CHECK();
+  }
   // hidden 128 / 96 / 64 get compile-time K-step counts (predicate-free MMA issue); other sizes take the runtime path
 #define CSN_FWD(KS)                                                                  \
   do {                                                                               \
@@ -910,14 +928,12 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   const float* c_seq = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(reserve) + align256(tb * 4 * H * 2));
   __nv_bfloat16* dG = reinterpret_cast<__nv_bfloat16*>(workspace);
   __nv_bfloat16* wih_bf = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 2));
-  if (!accumulate) {
-    CSN_CUDA(cudaMemsetAsync(db_ih, 0, size_t(4) * H * 4, s));
-    CSN_CUDA(cudaMemsetAsync(db_hh, 0, size_t(4) * H * 4, s));
-  }
   const int nv = pick_nv(B);
   uint32_t* w_img = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 2) +
                                                 align256(size_t(4) * H * I * 2));
-  pack_whh_tmem_image_kernel<<<4 * 128 * 64 / 256, 256, 0, s>>>(w_hh, w_img, H, 1);
+  // W_hh^T image + (unless accumulating) zero the bias-gradient accumulators the recurrence adds into
+  lstm_prepare_kernel<<<4 * 128 * 64 / 256, 256, 0, s>>>(w_hh, w_img, H, 1, nullptr, nullptr, 0, 16, accumulate ? nullptr : db_ih,
+                                                         accumulate ? nullptr : db_hh, 4 * H);
   CSN_LAUNCH_CHECK();
 #define CSN_BWD(KS)                                                                                                        \
   do {                                                                                                                     \
