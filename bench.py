@@ -394,42 +394,45 @@ def main():
         print("loss roofline probe failed:", exc, file=sys.stderr)
 
     # ---------------- end to end through the public API with HOST buffers (`e2e`) ----------------
-    # pinned host trials -> H2D on a copy stream (double buffered, overlapped with the previous step) -> step ->
+    # pinned host trials -> H2D on a copy stream (three staging buffers, copies run back to back under the steps) -> step ->
     # D2H of the loss every step.
+    NBUF = 3  # device staging buffers: the copy of batch i+1 never waits for the step that used its buffer last
     h_eeg = [e.cpu().pin_memory() for e in eeg[:2]]
     h_feat = [f.cpu().pin_memory() for f in feats[:2]]
-    d_eeg = [torch.empty_like(eeg[0]) for _ in range(2)]
-    d_feat = [torch.empty_like(feats[0]) for _ in range(2)]
+    d_eeg = [torch.empty_like(eeg[0]) for _ in range(NBUF)]
+    d_feat = [torch.empty_like(feats[0]) for _ in range(NBUF)]
     h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
-    for s_ in range(2):  # the loader's double buffer: read in place by the step
+    for s_ in range(NBUF):  # the loader's staging buffers: read in place by the step
         step.register_inputs(d_eeg[s_], d_feat[s_])
     copy_stream = torch.cuda.Stream()
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(NBUF)]
+    consumed = [torch.cuda.Event() for _ in range(NBUF)]
 
     def stage_in(i):
-        s = i % 2
+        s = i % NBUF
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[s])
-            d_eeg[s].copy_(h_eeg[s], non_blocking=True)
-            d_feat[s].copy_(h_feat[s], non_blocking=True)
+            d_eeg[s].copy_(h_eeg[i % 2], non_blocking=True)
+            d_feat[s].copy_(h_feat[i % 2], non_blocking=True)
             ready[s].record(copy_stream)
 
     def e2e_loop(n):
-        for s in range(2):
+        for s in range(NBUF):
             consumed[s].record()
         stage_in(0)
+        if n > 1:
+            stage_in(1)
         for i in range(n):
-            s = i % 2
-            if i + 1 < n:
-                stage_in(i + 1)
+            s = i % NBUF
+            if i + 2 < n:
+                stage_in(i + 2)
             torch.cuda.current_stream().wait_event(ready[s])
             l = step.step(d_eeg[s], d_feat[s], epoch=0)
             consumed[s].record()
             h_loss.copy_(l, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    e2e_loop(3)
+    e2e_loop(2 * NBUF)
     barrier()
     if rank == 0:
         sampler.start()
