@@ -103,22 +103,31 @@ __device__ __forceinline__ void pack_wih_element(const float* __restrict__ w_ih,
 __device__ __forceinline__ void pack_whh_element(const float* __restrict__ w_hh, uint32_t* __restrict__ img, int H, int transposed,
                                                  int idx) {  // idx over 4 * 128 * 64
   if (idx >= 4 * 128 * 64) return;
-  int g, lane, c;
-  if (!transposed) { c = idx & 63; lane = (idx >> 6) & 127; g = idx >> 13; }   // consecutive threads -> consecutive k
-  else { lane = idx & 127; c = (idx >> 7) & 63; g = idx >> 13; }               // consecutive threads -> consecutive k (= lane)
-  const int k0 = 2 * c, k1 = 2 * c + 1;
-  float v0 = 0.f, v1 = 0.f;
-  if (lane < H) {
-    if (!transposed) {
+  if (!transposed) {
+    const int c = idx & 63, lane = (idx >> 6) & 127, g = idx >> 13;  // consecutive threads -> consecutive k
+    const int k0 = 2 * c, k1 = 2 * c + 1;
+    float v0 = 0.f, v1 = 0.f;
+    if (lane < H) {
       if (k0 < H) v0 = w_hh[size_t(g * H + lane) * H + k0];
       if (k1 < H) v1 = w_hh[size_t(g * H + lane) * H + k1];
-    } else {
-      if (k0 < H) v0 = w_hh[size_t(g * H + k0) * H + lane];
-      if (k1 < H) v1 = w_hh[size_t(g * H + k1) * H + lane];
     }
+    __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
+    img[(size_t(g) * 128 + lane) * 64 + c] = *reinterpret_cast<uint32_t*>(&bb);
+    return;
+  }
+  // backward operand: lane = m (hidden unit of dh), contraction index K' = 4 u + g (GATE-INTERLEAVED, so the four gate
+  // gradients of a cell are 8 contiguous bytes of the dG^T operand and leave the epilogue as one 64-bit store).
+  // Column c' in [0, 256) of the lane's row holds K' = 2c', 2c'+1 = gates (0,1) or (2,3) of unit u = c' / 2; the image
+  // keeps the [4][128][64] addressing of the forward one: column c' lives in block c' / 64.
+  const int lane = idx & 127, cp = idx >> 7;  // consecutive threads -> consecutive m (contiguous in W_hh rows)
+  const int u = cp >> 1, g0 = (cp & 1) * 2;
+  float v0 = 0.f, v1 = 0.f;
+  if (lane < H && u < H) {
+    v0 = w_hh[size_t(g0 * H + u) * H + lane];
+    v1 = w_hh[size_t((g0 + 1) * H + u) * H + lane];
   }
   __nv_bfloat162 bb = __floats2bfloat162_rn(v0, v1);
-  img[(size_t(g) * 128 + lane) * 64 + c] = *reinterpret_cast<uint32_t*>(&bb);
+  img[(size_t(cp >> 6) * 128 + lane) * 64 + (cp & 63)] = *reinterpret_cast<uint32_t*>(&bb);
 }
 
 // ONE preparation launch per layer call: the W_hh tensor-memory image, plus (forward, fused projection) the W_ih
@@ -175,31 +184,27 @@ __device__ __forceinline__ void issue_fwd(uint32_t base, uint64_t db0, uint32_t 
     }
   }
 }
-// Backward: the dG^T operand keeps a FIXED stride of 128 contraction elements per gate (kk16 = 8 g + kg), so every
-// descriptor offset is an immediate.  The 32 K-steps rotate over kBwdAcc accumulators (summed by the epilogue):
-// with all 128 SMs running, back-to-back MMAs into ONE accumulator measured ~23 cycles each against ~11 when
-// consecutive MMAs target different accumulators (the forward kernel's four gate accumulators).
-// HALF selects the issuer warp: warp 0 issues gates 0-1 into accumulators {0,1}, warp 1 gates 2-3 into {2,3}.
-// Everything is unrolled to immediates so each warp's ~50 operands (16 B descriptors, 16 A addresses, 2 accumulators)
-// stay in its own uniform register file: one warp issuing all 32 K-steps needs ~100 uniform registers and ptxas
-// spills them (MOV.SPILL / R2UR per MMA, ~23 cycles each); a rolled loop with running operands is worse still
-// (~37 cycles per MMA: UIADD3 -> UTCHMMA dependency latency).  Measured with scripts/prof_lstm_steps.py.
+// Backward: the contraction index of dh^T = W_hh^T . dG^T is gate-interleaved (K' = 4 u + g), 4*KP elements = KP/4
+// K-steps, contiguous from zero.  The K-steps rotate over kBwdAcc accumulators (summed by the epilogue): with all 128
+// SMs running, back-to-back MMAs into ONE accumulator measured ~23 cycles each against ~11 when consecutive MMAs
+// target different accumulators (the forward kernel's four gate accumulators).
+// HALF selects the issuer warp: warp 0 issues the first half of the K-steps into accumulators {0,1}, warp 1 the second
+// half into {2,3}.  Everything is unrolled to immediates so each warp's ~50 operands (16 B descriptors, 16 A addresses,
+// 2 accumulators) stay in its own uniform register file: one warp issuing all 32 K-steps needs ~100 uniform registers
+// and ptxas spills them (MOV.SPILL / R2UR per MMA, ~23 cycles each); a rolled loop with running operands is worse
+// still (~37 cycles per MMA: UIADD3 -> UTCHMMA dependency latency).  Measured with scripts/prof_lstm_steps.py.
+// KSTEPS = KP / 16 (K-steps per gate in the forward kernel's terms): each half issues 2 * KSTEPS steps.
 template <bool CONST_BASE, int KSTEPS, int HALF>
 __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t idesc, int ksteps_rt) {
   const uint32_t tb = base;
-  const int ksteps_gate = KSTEPS ? KSTEPS : ksteps_rt;
+  const int per_half = 2 * (KSTEPS ? KSTEPS : ksteps_rt);
 #pragma unroll
-  for (int gg = 0; gg < 2; ++gg) {
-    const int g = HALF * 2 + gg;
-#pragma unroll
-    for (int kg = 0; kg < 8; ++kg) {
-      if (kg < ksteps_gate) {
-        const int kk = g * 8 + kg;
-        const int acc = HALF * 2 + (kg & 1);
-        const bool first = (gg == 0 && kg < 2);
-        const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
-        umma_f16_ts(tb + acc * kNslots, tb + kAcol0 + g * kAgate + kg * 8, db, idesc, first ? 0u : 1u);
-      }
+  for (int i = 0; i < 16; ++i) {
+    if (i < per_half) {
+      const int kk = HALF * per_half + i;  // compile-time when KSTEPS > 0
+      const int acc = HALF * 2 + (i & 1);
+      const uint64_t db = db0 + uint64_t(kk * ((2 * kLboB) >> 4));
+      umma_f16_ts(tb + acc * kNslots, tb + kAcol0 + kk * 8, db, idesc, i < 2 ? 0u : 1u);
     }
   }
 }
@@ -652,7 +657,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
      {
       asm volatile("cp.async.wait_group 2;" ::: "memory");  // the group of step t has landed
       struct { float i[NVT], f[NVT], g[NVT], o[NVT], c[NVT], cp[NVT]; } cur;
-      float dh[NVT], tcn[NVT], pref[NVT];
+      float dh[NVT], pref[NVT], fac[4][NVT];  // fac: everything of dG that does not depend on dh
       // everything that does not need dh is done before the wait
       {
         const float* src = ring + (t & 3) * kRingStage + tid;
@@ -664,8 +669,12 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
           cur.c[j] = sj[2 * (kEpiWarps * 32)];
           cur.cp[j] = sj[3 * (kEpiWarps * 32)];
           dh[j] = sj[4 * (kEpiWarps * 32)] + sj[5 * (kEpiWarps * 32)];
-          tcn[j] = tanh_fast(cur.c[j]);
-          pref[j] = cur.o[j] * (1.f - tcn[j] * tcn[j]);
+          const float tcn = tanh_fast(cur.c[j]);
+          pref[j] = cur.o[j] * (1.f - tcn * tcn);
+          fac[0][j] = cur.g[j] * cur.i[j] * (1.f - cur.i[j]);
+          fac[1][j] = cur.cp[j] * cur.f[j] * (1.f - cur.f[j]);
+          fac[2][j] = cur.i[j] * (1.f - cur.g[j] * cur.g[j]);
+          fac[3][j] = tcn * cur.o[j] * (1.f - cur.o[j]);
         }
       }
       const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps;
@@ -674,34 +683,32 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
         mbar_wait(sm.bar_acc, (n - 1) & 1);
         tcgen05_fence_after();
         if (do_prof) prof[512 + n * 8 + 0] = clock64();
-        // accumulators {0,1} belong to issuer warp 0, {2,3} to issuer warp 1; the odd ones exist iff ksteps_gate > 1
+        // accumulators {0,1} belong to issuer warp 0, {2,3} to issuer warp 1 (each half issues >= 2 K-steps)
         uint32_t r[kBwdAcc][NVT];
 #pragma unroll
-        for (int a = 0; a < kBwdAcc; ++a)
-          if ((a & 1) < ksteps_gate) tmem_ld<NVT>(lane_addr + a * kNslots, r[a]);
+        for (int a = 0; a < kBwdAcc; ++a) tmem_ld<NVT>(lane_addr + a * kNslots, r[a]);
         tmem_ld_wait();
         tcgen05_fence_before();
         if (do_prof) prof[512 + n * 8 + 1] = clock64();
 #pragma unroll
-        for (int a = 0; a < kBwdAcc; ++a)
-          if ((a & 1) < ksteps_gate) {
-#pragma unroll
-            for (int j = 0; j < NVT; ++j) dh[j] += __uint_as_float(r[a][j]);
-          }
+        for (int j = 0; j < NVT; ++j)
+          dh[j] += (__uint_as_float(r[0][j]) + __uint_as_float(r[1][j])) + (__uint_as_float(r[2][j]) + __uint_as_float(r[3][j]));
       }
       float dg[4][NVT];
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
         const float dct = fmaf(dh[j], pref[j], dc[j]);
-        dg[0][j] = dct * cur.g[j] * cur.i[j] * (1.f - cur.i[j]);
-        dg[1][j] = dct * cur.cp[j] * cur.f[j] * (1.f - cur.f[j]);
-        dg[2][j] = dct * cur.i[j] * (1.f - cur.g[j] * cur.g[j]);
-        dg[3][j] = dh[j] * tcn[j] * cur.o[j] * (1.f - cur.o[j]);
+        dg[0][j] = dct * fac[0][j];
+        dg[1][j] = dct * fac[1][j];
+        dg[2][j] = dct * fac[2][j];
+        dg[3][j] = dh[j] * fac[3][j];
         dc[j] = dct * cur.f[j];
-        if (active) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<__nv_bfloat16*>(sm.opb + canon_k_off(jb + j, g * 128 + u, kLboB, kSboB)) = __float2bfloat16_rn(dg[g][j]);
+        if (active) {  // contraction index 4u + g: the cell's four gate gradients are one aligned 8-byte store
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(dg[0][j], dg[1][j]), hi = __floats2bfloat162_rn(dg[2][j], dg[3][j]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(sm.opb + canon_k_off(jb + j, 4 * u, kLboB, kSboB)) = pk;
         }
       }
       if (do_prof) prof[512 + n * 8 + 2] = clock64();
