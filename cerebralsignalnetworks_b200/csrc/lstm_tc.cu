@@ -60,6 +60,7 @@ struct RecSmem {
   uint8_t* ring;      // prefetch ring / fused-projection operands (after a 128-byte barrier block)
 };
 constexpr int kPfStages = 4;
+constexpr int kBwdPfRow = 2048;  // backward prefetch ring, bytes per trial and stage: gates (<= 1 KB) | c_prev (<= 512 B) | d_hseq (<= 512 B)
 
 // `raw` is the 128-byte aligned dynamic shared array itself (no runtime alignment arithmetic): its address is a
 // link-time constant, so the B-operand descriptors of the unrolled MMA issue become immediates in uniform registers.
@@ -548,6 +549,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
   if (tid == 0) {
     mbar_init(sm.bar_in, kEpiWarps);
     mbar_init(sm.bar_acc, 2);  // one tcgen05.commit per issuer warp
+    for (int i = 0; i < kPfStages; ++i) mbar_init(sm.bar_pf + i, 1);
     fence_mbar_init();
   }
   if (warp == kIssuerWarp) tmem_alloc(sm.tmem_slot, kTmemCols);
@@ -566,9 +568,36 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
     constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
     const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
     const bool base0 = (tmem_base == 0);
+    // Issuer warp 1 is also the TMA producer of the per-step BPTT inputs: for every trial of the tile the row of gate
+    // activations (H x 8 B), the row of c_{t-1} (H x 4 B; c_t is carried in a register from the step before) and, when a
+    // layer above feeds gradients at every timestep, the row of d_hseq are bulk-copied into a 4-stage shared-memory
+    // ring three steps ahead, completion counted on one mbarrier per stage.  (They used to be per-thread 4-byte
+    // cp.async: six LDGSTS per cell per step in the epilogue warps, sitting in front of every fence of the hand-off.)
+    const int rows_valid = min(NV, B - b0);
+    const uint32_t g_bytes = uint32_t(H) * 8u, c_bytes = uint32_t(H) * 4u;
+    uint8_t* const pf_ring = sm.opb + b_bytes + 128;
+    auto prefetch_step = [&](int t) {  // elected lane of issuer warp 1 only; stage layout per trial: [gates | c_prev | dhs]
+      if (t < 0) return;
+      uint64_t* bar = sm.bar_pf + (t & (kPfStages - 1));
+      const uint32_t per_row = g_bytes + (t > 0 ? c_bytes : 0u) + (d_hseq ? c_bytes : 0u);
+      mbar_arrive_expect_tx(bar, per_row * uint32_t(rows_valid));
+      uint8_t* dst = pf_ring + size_t(t & (kPfStages - 1)) * NV * kBwdPfRow;
+      for (int j = 0; j < rows_valid; ++j) {
+        const size_t row = size_t(t) * B + b0 + j;
+        uint8_t* d = dst + size_t(j) * kBwdPfRow;
+        bulk_g2s(d, gates + row * 4 * H, g_bytes, bar);
+        if (t > 0) bulk_g2s(d + 1024, c_seq + (row - B) * H, c_bytes, bar);
+        if (d_hseq) bulk_g2s(d + 1536, d_hseq + row * H, c_bytes, bar);
+      }
+    };
     // one time loop PER issuer warp: the hoisted operand sets of the two halves must not be live together
     auto issue_loop = [&](auto half_tag) {
       constexpr int HALF = decltype(half_tag)::value;
+      if (HALF == 1) {
+        if (elect_one())
+          for (int k = 0; k < kPfStages; ++k) prefetch_step(T - 1 - k);
+        __syncwarp();
+      }
       int n = 0;
       for (int t = T - 1; t >= 0; --t, ++n) {
         handoff_wait<kRecThreadsBwd>();  // dG_t^T staged
@@ -581,6 +610,8 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
           else issue_bwd<false, KSTEPS, HALF>(tmem_base, db0, idesc, ksteps_gate);
           umma_commit(sm.bar_acc);
           if (pr) prof[512 + (n + 1) * 8 + 5] = clock64();
+          // every epilogue thread has read ring stage t & 3 before the hand-off above: refill it
+          if (HALF == 1) prefetch_step(t - kPfStages);
         }
         __syncwarp();
       }
@@ -600,75 +631,39 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
 #pragma unroll
     for (int j = 0; j < NVT; ++j) valid[j] = active && (b0 + jb + j < B);
 
-    // Per-step inputs (gate activations, c_t, c_{t-1}, upstream dh) are prefetched with cp.async into a 4-deep
-    // per-thread shared-memory ring three steps ahead (see the forward kernel); slots: [0,1] gates (8 B), [2] c_t,
-    // [3] c_{t-1}, [4] d_hseq, [5] d_hlast.  Every thread reads back only its own bytes.
-    constexpr int kSlots = 6;
-    float* ring = reinterpret_cast<float*>(sm.opb + b_bytes + 64);  // [4 stages][kSlots*NVT][256 threads]
-    constexpr int kRingStage = kSlots * NVT * (kEpiWarps * 32);
-    const uint32_t ring_base = smem_u32(ring + tid);
-    const size_t step_cells = size_t(B) * H;
-    const uint2* g_pf[NVT];     // reserve gates of the step being prefetched
-    const float* c_pf[NVT];     // c_t of the step being prefetched
-    const float* dhs_pf[NVT];   // d_hseq of the step being prefetched
-    __nv_bfloat16* dg_ptr[NVT]; // dG[t][b][.] output row
+    // Per-step inputs arrive through the TMA ring filled by issuer warp 1 (see prefetch_step): per trial
+    // [gates: H x (i,f,g,o) bf16 | c_{t-1}: H fp32 | d_hseq: H fp32]; c_t is carried over from the previous iteration.
+    const uint8_t* const pf_ring = sm.opb + b_bytes + 128;
+    __nv_bfloat16* dg_ptr[NVT];  // dG[t][b][.] output row
+    float c_cur[NVT], dhl[NVT];  // c_t of the step about to be processed; d_hlast (enters at t = T-1 only)
 #pragma unroll
     for (int j = 0; j < NVT; ++j) {
       const size_t row = size_t(b0 + jb + j);
-      const size_t cell_last = size_t(T - 1) * step_cells + row * H + u;
-      g_pf[j] = reinterpret_cast<const uint2*>(gates) + (valid[j] ? cell_last : 0);
-      c_pf[j] = c_seq + (valid[j] ? cell_last : 0);
-      dhs_pf[j] = d_hseq ? d_hseq + (valid[j] ? cell_last : 0) : nullptr;
       dg_ptr[j] = dG + (valid[j] ? (size_t(T - 1) * B + row) * 4 * H + u : 0);
+      c_cur[j] = valid[j] ? c_seq[(size_t(T - 1) * B + row) * H + u] : 0.f;
+      dhl[j] = (valid[j] && d_hlast) ? d_hlast[row * H + u] : 0.f;
     }
-    auto cp4 = [](uint32_t dst, const void* src, int nbytes) {
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-    };
-    auto prefetch = [&](int t) {  // one cp.async group per step; zero fill when out of range
-      const uint32_t dst = ring_base + uint32_t((t & 3) * kRingStage * 4);
-      constexpr uint32_t kSlotBytes = (kEpiWarps * 32) * 4;
-#pragma unroll
-      for (int j = 0; j < NVT; ++j) {
-        const bool ok = valid[j] && t >= 0;
-        const uint32_t d = dst + uint32_t(j * kSlots) * kSlotBytes;
-        const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(g_pf[j]);
-        cp4(d + 0 * kSlotBytes, gsrc, ok ? 4 : 0);
-        cp4(d + 1 * kSlotBytes, gsrc + 1, ok ? 4 : 0);
-        cp4(d + 2 * kSlotBytes, c_pf[j], ok ? 4 : 0);
-        cp4(d + 3 * kSlotBytes, c_pf[j] - step_cells, (ok && t > 0) ? 4 : 0);
-        cp4(d + 4 * kSlotBytes, dhs_pf[j] ? (const void*)dhs_pf[j] : (const void*)c_pf[j], (ok && dhs_pf[j]) ? 4 : 0);
-        cp4(d + 5 * kSlotBytes, d_hlast ? (const void*)(d_hlast + size_t(b0 + jb + j) * H + u) : (const void*)c_pf[j],
-            (ok && d_hlast && t == T - 1) ? 4 : 0);
-        if (t > 0) {  // keep the pointers inside the allocation
-          g_pf[j] -= step_cells;
-          c_pf[j] -= step_cells;
-          if (dhs_pf[j]) dhs_pf[j] -= step_cells;
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
     auto bf_lo = [](uint32_t w) { return __uint_as_float(w << 16); };
     auto bf_hi = [](uint32_t w) { return __uint_as_float(w & 0xffff0000u); };
-    prefetch(T - 1);
-    prefetch(T - 2);
-    prefetch(T - 3);
     int n = 0;
     for (int t = T - 1; t >= 0; --t) {
      {
-      asm volatile("cp.async.wait_group 2;" ::: "memory");  // the group of step t has landed
+      mbar_wait(sm.bar_pf + (t & (kPfStages - 1)), ((T - 1 - t) / kPfStages) & 1);  // the rows of step t have landed (long ago)
       struct { float i[NVT], f[NVT], g[NVT], o[NVT], c[NVT], cp[NVT]; } cur;
       float dh[NVT], pref[NVT], fac[4][NVT];  // fac: everything of dG that does not depend on dh
       // everything that does not need dh is done before the wait
       {
-        const float* src = ring + (t & 3) * kRingStage + tid;
+        const uint8_t* src = pf_ring + size_t(t & (kPfStages - 1)) * NV * kBwdPfRow;
 #pragma unroll
         for (int j = 0; j < NVT; ++j) {
-          const float* sj = src + j * kSlots * (kEpiWarps * 32);
-          const uint32_t w0 = __float_as_uint(sj[0]), w1 = __float_as_uint(sj[(kEpiWarps * 32)]);
-          cur.i[j] = bf_lo(w0); cur.f[j] = bf_hi(w0); cur.g[j] = bf_lo(w1); cur.o[j] = bf_hi(w1);
-          cur.c[j] = sj[2 * (kEpiWarps * 32)];
-          cur.cp[j] = sj[3 * (kEpiWarps * 32)];
-          dh[j] = sj[4 * (kEpiWarps * 32)] + sj[5 * (kEpiWarps * 32)];
+          const uint8_t* sj = src + size_t(jb + j) * kBwdPfRow;
+          const uint2 gq = valid[j] ? *reinterpret_cast<const uint2*>(sj + u * 8) : make_uint2(0u, 0u);
+          cur.i[j] = bf_lo(gq.x); cur.f[j] = bf_hi(gq.x); cur.g[j] = bf_lo(gq.y); cur.o[j] = bf_hi(gq.y);
+          cur.c[j] = c_cur[j];
+          cur.cp[j] = (valid[j] && t > 0) ? *reinterpret_cast<const float*>(sj + 1024 + u * 4) : 0.f;
+          dh[j] = (valid[j] && d_hseq) ? *reinterpret_cast<const float*>(sj + 1536 + u * 4) : 0.f;
+          if (t == T - 1) dh[j] += dhl[j];
+          c_cur[j] = cur.cp[j];
           const float tcn = tanh_fast(cur.c[j]);
           pref[j] = cur.o[j] * (1.f - tcn * tcn);
           fac[0][j] = cur.g[j] * cur.i[j] * (1.f - cur.i[j]);
@@ -716,8 +711,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
       handoff_arrive<kRecThreadsBwd>();
       if (do_prof) prof[512 + n * 8 + 3] = clock64();
       ++n;
-      // ---- off the critical path (prefetch first: see the forward kernel) ----
-      prefetch(t - 3);
+      // ---- off the critical path ----
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
         if (valid[j]) {
@@ -861,7 +855,7 @@ template <int NV, int KSTEPS>
 static int launch_bwd(const uint32_t* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
                       const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
                       cudaStream_t s) {
-  const size_t smem = size_t(4 * 128 / 8) * kLboB + 64 + size_t(4) * 6 * (NV / 2) * (kEpiWarps * 32) * 4 + 128;  // + prefetch ring
+  const size_t smem = size_t(4 * 128 / 8) * kLboB + 128 + size_t(kPfStages) * NV * kBwdPfRow + 128;  // operand + barriers + TMA ring
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
     CSN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<NV, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
