@@ -37,7 +37,11 @@ template <int NTHREADS>
 __device__ __forceinline__ void handoff_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(NTHREADS) : "memory"); }
 template <int NTHREADS>
 __device__ __forceinline__ void handoff_wait() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
-constexpr uint32_t kLboB = 256, kSboB = 128;   // 16-row operand: 2 core matrices per k-group
+// 16-row operand: 2 core matrices (2 x 128 B) per k-group.  The k-group stride is 272 B, not the dense 256: the epilogue
+// threads write their h / dG values one k-group apart per 2..8 lanes, and a 256-byte stride puts every k-group on the same
+// shared-memory banks (4-way conflict for the forward's 2-byte stores, 16-way for the backward's 8-byte stores, and the
+// MEMBAR of the hand-off waits for all of it); 272 = 256 + 16 rotates consecutive k-groups over the bank groups.
+constexpr uint32_t kLboB = 272, kSboB = 128;
 constexpr int kNslots = 16;                    // MMA N (batch slots per CTA); NV <= 16 of them are live
 constexpr int kBwdAcc = 4;                     // accumulators the backward K-steps rotate over
 constexpr int kProfSteps = 64;                 // bring-up instrumentation: clock64 stamps for the first steps of CTA 0
