@@ -31,6 +31,7 @@ using namespace tc;
 constexpr int kEpiWarps = 8, kIssuerWarp = 8;
 constexpr int kRecThreads = (kEpiWarps + 1) * 32;     // forward: one issuer warp
 constexpr int kRecThreadsBwd = (kEpiWarps + 2) * 32;  // backward: two issuer warps (see issue_bwd)
+constexpr int kBwdThreads = kRecThreadsBwd + 32;      // + the TMA producer warp of the per-step BPTT inputs
 // epilogue -> issuer hand-off: hardware named barrier 1 over all threads (the 256 epilogue threads ARRIVE without
 // blocking, the issuer warp(s) SYNC); ~2x lower latency than an mbarrier round trip, measured on the step stamps.
 template <int NTHREADS>
@@ -57,13 +58,13 @@ struct RecSmem {
   uint8_t* opb;       // B operand: h^T (fwd, KP/8 * 256 B) or dG^T (bwd, 4KP/8 * 256 B), canonical K-major
   uint64_t* bar_in;   // (unused since the named-barrier hand-off; kept initialised)
   uint64_t* bar_acc;  // accumulators ready (issuer -> epilogue)
-  uint64_t* bar_pf;   // [4] prefetch ring stages filled (TMA bulk copies -> epilogue)
+  uint64_t* bar_pf;   // [kPfStages] prefetch ring stages filled (TMA bulk copies -> epilogue)
   uint64_t* bar_xp;   // [2] fused input projection: Xp accumulator set filled (issuer -> epilogue / x-ring reuse)
   uint64_t* bar_w;    // fused input projection: W_ih operand image landed in shared memory
   uint32_t* tmem_slot;
   uint8_t* ring;      // prefetch ring / fused-projection operands (after a 128-byte barrier block)
 };
-constexpr int kPfStages = 4;
+constexpr int kPfStages = 8;  // prefetch ring depth: seven steps (~2.5 us at 0.35 us per step) ahead of the consumer covers the HBM latency under load
 constexpr int kBwdPfRow = 2048;  // backward prefetch ring, bytes per trial and stage: gates (<= 1 KB) | c_prev (<= 512 B) | d_hseq (<= 512 B)
 
 // `raw` is the 128-byte aligned dynamic shared array itself (no runtime alignment arithmetic): its address is a
@@ -385,8 +386,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
       // Follow the recurrent issuer through shared memory (NOT through the hand-off barrier: a bar.sync also drains
       // this warp's in-flight cp.async, one HBM round trip on the chain per block).  issued_step >= t also certifies
       // that every epilogue thread finished step t-1, the last reader of the set this warp starts to overwrite.
-      while (*issued_step < t) {
-      }
+      while (*issued_step < t) __nanosleep(40);  // (a tight poll by 32 lanes steals issue slots from the epilogue warps)
       tcgen05_fence_after();
       const bool next_blk = blk + 1 < n_blocks;
       if (c == 0 && next_blk) x_landed();  // block blk+1's inputs (requested one block ago) are in place
@@ -537,7 +537,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
 // ------------------------------------------------------------------------------------------------ backward
 // dh_{t-1}^T[k, b] = sum_{kk = g*KP + u} W_hh[g*H + u][k] * dG_t[b, kk]: M = hidden unit k (TMEM lane), K = 4*KP.
 template <int NV, int KSTEPS>
-__global__ void __launch_bounds__(kRecThreadsBwd, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
                    float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP,
@@ -549,8 +549,10 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
   const int b0 = blockIdx.x * NV;
   const int ksteps_gate = KP / 16;
 
-  for (int i = tid; i < (int)(b_bytes / 4); i += kRecThreadsBwd) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
+  for (int i = tid; i < (int)(b_bytes / 4); i += kBwdThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
+  volatile int* const progress = reinterpret_cast<volatile int*>(sm.tmem_slot + 1);  // hand-offs seen by issuer warp 0
   if (tid == 0) {
+    *progress = 0;
     mbar_init(sm.bar_in, kEpiWarps);
     mbar_init(sm.bar_acc, 2);  // one tcgen05.commit per issuer warp
     for (int i = 0; i < kPfStages; ++i) mbar_init(sm.bar_pf + i, 1);
@@ -568,40 +570,45 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
   __syncthreads();
   tcgen05_fence_after();
 
-  if (warp >= kIssuerWarp) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
-    const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
-    const bool base0 = (tmem_base == 0);
-    // Issuer warp 1 is also the TMA producer of the per-step BPTT inputs: for every trial of the tile the row of gate
+  if (warp == kIssuerWarp + 2) {
+    // TMA producer of the per-step BPTT inputs (own warp: on an issuer warp the copies delayed that warp's return to
+    // the hand-off barrier, i.e. the chain): for every trial of the tile the row of gate
     // activations (H x 8 B), the row of c_{t-1} (H x 4 B; c_t is carried in a register from the step before) and, when a
     // layer above feeds gradients at every timestep, the row of d_hseq are bulk-copied into a 4-stage shared-memory
     // ring three steps ahead, completion counted on one mbarrier per stage.  (They used to be per-thread 4-byte
     // cp.async: six LDGSTS per cell per step in the epilogue warps, sitting in front of every fence of the hand-off.)
+    // The warp follows issuer warp 0 through a shared-memory counter of the hand-offs it has seen: after hand-off n every
+    // epilogue thread is done with the ring stage of step T-1-n, which is then refilled with step T-1-n-4.
     const int rows_valid = min(NV, B - b0);
     const uint32_t g_bytes = uint32_t(H) * 8u, c_bytes = uint32_t(H) * 4u;
     uint8_t* const pf_ring = sm.opb + b_bytes + 128;
-    auto prefetch_step = [&](int t) {  // elected lane of issuer warp 1 only; stage layout per trial: [gates | c_prev | dhs]
-      if (t < 0) return;
+    // Lane 0 issues the copies.  The rows of the tile's trials are adjacent in the reserve ([t][b][...]), so one step is
+    // TWO bulk copies (gates, c_prev) plus one for d_hseq -- not two or three per trial: a cp.async.bulk costs the
+    // issuing thread a few hundred cycles, and with 4-6 of them per step the producer needed more than a step time per
+    // step (the ring ran dry after ~15 steps; measured with the ring-wait stamps of scripts/prof_lstm_steps.py).
+    auto prefetch_step = [&](int t) {  // stage layout: [gates of all trials | c_prev of all trials | dhs of all trials]
+      if (t < 0 || lane != 0) return;
       uint64_t* bar = sm.bar_pf + (t & (kPfStages - 1));
-      const uint32_t per_row = g_bytes + (t > 0 ? c_bytes : 0u) + (d_hseq ? c_bytes : 0u);
-      mbar_arrive_expect_tx(bar, per_row * uint32_t(rows_valid));
-      uint8_t* dst = pf_ring + size_t(t & (kPfStages - 1)) * NV * kBwdPfRow;
-      for (int j = 0; j < rows_valid; ++j) {
-        const size_t row = size_t(t) * B + b0 + j;
-        uint8_t* d = dst + size_t(j) * kBwdPfRow;
-        bulk_g2s(d, gates + row * 4 * H, g_bytes, bar);
-        if (t > 0) bulk_g2s(d + 1024, c_seq + (row - B) * H, c_bytes, bar);
-        if (d_hseq) bulk_g2s(d + 1536, d_hseq + row * H, c_bytes, bar);
-      }
+      const uint32_t rv = uint32_t(rows_valid);
+      mbar_arrive_expect_tx(bar, rv * (g_bytes + (t > 0 ? c_bytes : 0u) + (d_hseq ? c_bytes : 0u)));
+      const size_t row = size_t(t) * B + b0;
+      uint8_t* d = pf_ring + size_t(t & (kPfStages - 1)) * NV * kBwdPfRow;
+      bulk_g2s(d, gates + row * 4 * H, rv * g_bytes, bar);
+      if (t > 0) bulk_g2s(d + NV * 1024, c_seq + (row - B) * H, rv * c_bytes, bar);
+      if (d_hseq) bulk_g2s(d + NV * 1536, d_hseq + row * H, rv * c_bytes, bar);
     };
+    for (int k = 0; k < kPfStages; ++k) prefetch_step(T - 1 - k);
+    for (int n = 0; n + kPfStages < T; ++n) {
+      while (*progress <= n) __nanosleep(100);  // (a tight poll steals issue slots and LSU cycles from the epilogue warps)
+      prefetch_step(T - 1 - n - kPfStages);
+    }
+  } else if (warp >= kIssuerWarp) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
+    const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
+    const bool base0 = (tmem_base == 0);
     // one time loop PER issuer warp: the hoisted operand sets of the two halves must not be live together
     auto issue_loop = [&](auto half_tag) {
       constexpr int HALF = decltype(half_tag)::value;
-      if (HALF == 1) {
-        if (elect_one())
-          for (int k = 0; k < kPfStages; ++k) prefetch_step(T - 1 - k);
-        __syncwarp();
-      }
       int n = 0;
       for (int t = T - 1; t >= 0; --t, ++n) {
         handoff_wait<kRecThreadsBwd>();  // dG_t^T staged
@@ -614,8 +621,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
           else issue_bwd<false, KSTEPS, HALF>(tmem_base, db0, idesc, ksteps_gate);
           umma_commit(sm.bar_acc);
           if (pr) prof[512 + (n + 1) * 8 + 5] = clock64();
-          // every epilogue thread has read ring stage t & 3 before the hand-off above: refill it
-          if (HALF == 1) prefetch_step(t - kPfStages);
+          if (HALF == 0) *progress = n + 1;  // the producer warp may refill the ring stage of step t
         }
         __syncwarp();
       }
@@ -652,20 +658,22 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
     int n = 0;
     for (int t = T - 1; t >= 0; --t) {
      {
+      if (prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps) prof[1200 + n * 2] = clock64();
       mbar_wait(sm.bar_pf + (t & (kPfStages - 1)), ((T - 1 - t) / kPfStages) & 1);  // the rows of step t have landed (long ago)
+      if (prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps) prof[1200 + n * 2 + 1] = clock64();
       struct { float i[NVT], f[NVT], g[NVT], o[NVT], c[NVT], cp[NVT]; } cur;
       float dh[NVT], pref[NVT], fac[4][NVT];  // fac: everything of dG that does not depend on dh
       // everything that does not need dh is done before the wait
       {
-        const uint8_t* src = pf_ring + size_t(t & (kPfStages - 1)) * NV * kBwdPfRow;
+        const uint8_t* src = pf_ring + size_t(t & (kPfStages - 1)) * NV * kBwdPfRow;  // rows packed at their real pitch
 #pragma unroll
         for (int j = 0; j < NVT; ++j) {
-          const uint8_t* sj = src + size_t(jb + j) * kBwdPfRow;
-          const uint2 gq = valid[j] ? *reinterpret_cast<const uint2*>(sj + u * 8) : make_uint2(0u, 0u);
+          const size_t cell = size_t(jb + j) * H + u;
+          const uint2 gq = valid[j] ? *reinterpret_cast<const uint2*>(src + cell * 8) : make_uint2(0u, 0u);
           cur.i[j] = bf_lo(gq.x); cur.f[j] = bf_hi(gq.x); cur.g[j] = bf_lo(gq.y); cur.o[j] = bf_hi(gq.y);
           cur.c[j] = c_cur[j];
-          cur.cp[j] = (valid[j] && t > 0) ? *reinterpret_cast<const float*>(sj + 1024 + u * 4) : 0.f;
-          dh[j] = (valid[j] && d_hseq) ? *reinterpret_cast<const float*>(sj + 1536 + u * 4) : 0.f;
+          cur.cp[j] = (valid[j] && t > 0) ? *reinterpret_cast<const float*>(src + NV * 1024 + cell * 4) : 0.f;
+          dh[j] = (valid[j] && d_hseq) ? *reinterpret_cast<const float*>(src + NV * 1536 + cell * 4) : 0.f;
           if (t == T - 1) dh[j] += dhl[j];
           c_cur[j] = cur.cp[j];
           const float tcn = tanh_fast(cur.c[j]);
@@ -865,7 +873,7 @@ static int launch_bwd(const uint32_t* w_hh, const __nv_bfloat16* gates, const fl
     CSN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<NV, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kRecThreadsBwd, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf, 0u);
+  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kBwdThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf, 0u);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }

@@ -13,7 +13,7 @@ k = 1.0 / H ** 0.5
 w = [((torch.rand(4 * H, I) * 2 - 1) * k).cuda(), ((torch.rand(4 * H, H) * 2 - 1) * k).cuda(),
      ((torch.rand(4 * H) * 2 - 1) * k).cuda(), ((torch.rand(4 * H) * 2 - 1) * k).cuda()]
 x = torch.randn(T, B, I).cuda().bfloat16()
-buf = torch.zeros(2 * 64 * 8 + 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
 grads = tuple(torch.empty_like(t) for t in w)
 dh = torch.randn(B, H).cuda()
 def run():
@@ -32,6 +32,8 @@ print("   cycles since kernel start at t=1,8,64,200,400:", [int(ph[6 + i] - ph[1
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 h, r, ws = ops.lstm_layer_fwd(x, *w, torch.bfloat16, True)
 torch.cuda.synchronize(); e0.record(); h, r, ws = ops.lstm_layer_fwd(x, *w, torch.bfloat16, True); e1.record(); torch.cuda.synchronize()
+rw = buf[1200:1200 + 128].view(64, 2).cpu()
+print("bwd ring wait (cycles) steps 3..39:", [int(rw[i, 1] - rw[i, 0]) for i in range(3, 40)])
 print("lstm_layer_fwd (cast + pack + GEMM + recurrence) event time: %.1f us" % (1e3 * e0.elapsed_time(e1)))
 for name, p in (("forward", buf[:512].view(64, 8).cpu()), ("backward", buf[512:1024].view(64, 8).cpu())):
     print(name, "B =", B)
@@ -43,9 +45,11 @@ for name, p in (("forward", buf[:512].view(64, 8).cpu()), ("backward", buf[512:1
         d = int(p[t + 1, 4] - p[t, 3]); e = int(p[t + 1, 5] - p[t + 1, 4]); f = int(p[t + 1, 0] - p[t + 1, 5])
         wa = int(p[t + 1, 0] - p[t + 1, 6])   # how long thread 0 actually waited on the accumulator barrier
         st = int(p[t, 7] - p[t, 3]) if name == "backward" else 0  # off-path stores after the arrive
-        rows.append((period, a, b, c, d, e, f, wa, st))
+        pre = int(p[t + 1, 6] - p[t, 7]) if name == "backward" else int(p[t + 1, 6] - p[t, 3])  # loop top -> before the acc wait
+        rows.append((period, a, b, c, d, e, f, wa, st, pre))
         if t < 6:
             print(f"{t:3d} | {period:6d} | {a:6d} | {b:6d} | {c:6d} | {d:6d} | {e:6d} | {f:6d}")
     print("periods t=3..39:", [r[0] for r in rows])
     print("wait-on-acc   :", [r[7] for r in rows])
-    print("median", [int(statistics.median(r[i] for r in rows)) for i in range(9)], "(last two: time actually spent waiting on bar_acc, off-path stores)")
+    print("median", [int(statistics.median(r[i] for r in rows)) for i in range(10)], "(last three: time actually spent waiting on bar_acc, off-path stores, ring wait + dh-independent math before the acc wait)")
+    print("late steps (t >= 20) median", [int(statistics.median(r[i] for r in rows[17:])) for i in range(10)])
