@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-run() { name=$1; shift; env timeout -s KILL 900 "$@" > gpurun_out/$name.log 2>&1; echo "$name exit $?"; }
-run t15 python -m pytest tests -q -m gpu --timeout 300
+run() { name=$1; shift; env timeout -s KILL 240 "$@" > gpurun_out/$name.log 2>&1; echo "$name exit $?"; }
+run t15 python -m pytest tests -q -m gpu --timeout 90
 tail -n 3 gpurun_out/t15.log
 run smoke15 python __graft_entry__.py smoke; tail -n 3 gpurun_out/smoke15.log
 run bench15 python bench.py --no_cpu_baseline
