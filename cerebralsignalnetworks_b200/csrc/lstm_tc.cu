@@ -257,6 +257,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     mbar_init(sm.bar_xp + 1, 1);
     mbar_init(sm.bar_w, 1);
     *reinterpret_cast<volatile int*>(sm.tmem_slot + 1) = 0;
+    *reinterpret_cast<volatile int*>(sm.tmem_slot + 2) = 0;
     fence_mbar_init();
   }
   if (warp == kIssuerWarp) tmem_alloc(sm.tmem_slot, kTmemCols);
@@ -271,6 +272,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
   uint8_t* const xbuf = sm.ring;
   uint8_t* const wih_s = sm.ring + 2 * x_bytes;
   volatile int* const issued_step = reinterpret_cast<volatile int*>(sm.tmem_slot + 1);  // last step whose MMAs are queued
+  volatile int* const acc_done = reinterpret_cast<volatile int*>(sm.tmem_slot + 2);     // last step whose accumulators the epilogue has seen complete
   if (FX && tid == kXWarp * 32) {
     const uint32_t gate_bytes = 128u * uint32_t(KI) * 2u;
     mbar_arrive_expect_tx(sm.bar_w, 4 * gate_bytes);
@@ -383,13 +385,18 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     for (int t = 1; t <= T; ++t) {
       if (++c == TB) { c = 0; ++blk; }
       if (t == T) break;
-      // Follow the recurrent issuer through shared memory (NOT through the hand-off barrier: a bar.sync also drains
-      // this warp's in-flight cp.async, one HBM round trip on the chain per block).  issued_step >= t also certifies
-      // that every epilogue thread finished step t-1, the last reader of the set this warp starts to overwrite.
-      while (*issued_step < t) __nanosleep(40);  // (a tight poll by 32 lanes steals issue slots from the epilogue warps)
-      tcgen05_fence_after();
       const bool next_blk = blk + 1 < n_blocks;
       if (c == 0 && next_blk) x_landed();  // block blk+1's inputs (requested one block ago) are in place
+      // Use the tensor pipe's idle window: wait until this step's recurrent MMAs have COMPLETED (the accumulator
+      // barrier the epilogue waits on), then queue the chunk; it is done before the next step's MMAs are issued.
+      // Queued right behind the recurrent ISSUE instead, the pipe interleaved the chunk with the tail of the recurrent
+      // batch (+100 cycles on the chain).  Not the hand-off barrier either: a bar.sync drains this warp's in-flight
+      // cp.async (one HBM round trip on the chain per block).  A parity wait can miss a phase if the waiter lags two
+      // phases behind, so it is skipped when the epilogue's monotonic counter says the phase is already over.
+      // Completion of step t also certifies that every epilogue thread finished step t-1, the last reader of the
+      // accumulator set this warp starts to overwrite.
+      if (*acc_done < t) mbar_wait(sm.bar_acc, (t - 1) & 1);
+      tcgen05_fence_after();
       if (next_blk && elect_one()) {
         issue_x_chunk(blk + 1, c);
         if (c == TB - 1) umma_commit(sm.bar_xp + ((blk + 1) & 1));
@@ -456,6 +463,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
         if (do_prof) prof[t * 8 + 6] = clock64();
         mbar_wait(sm.bar_acc, (t - 1) & 1);
         tcgen05_fence_after();
+        if (FX && tid == 0) *acc_done = t;
         if (do_prof) prof[t * 8 + 0] = clock64();
         uint32_t r[4][NVT];
 #pragma unroll
