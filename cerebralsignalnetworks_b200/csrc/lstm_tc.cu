@@ -1,22 +1,26 @@
 // LSTM layer, bf16 tensor-core path: persistent tcgen05 recurrence + hand-written BPTT (H <= 128).
+// Replaces torch.nn.LSTM inside models.lstm.Model (call sites LstmDistillFromDinoV2Train.py:323,365,374).
 //
 // Forward (one CTA per batch tile of NV trials, the whole time loop inside the kernel):
-//   * W_hh is converted to bf16 once and stays RESIDENT in shared memory for all T steps as four 128 x KP
-//     K-major operand blocks (one per gate: rows = hidden unit, so TMEM lane = unit and a thread owns all four
-//     gates of its unit -- no cross-thread exchange in the epilogue).
-//   * per step the single issuer thread runs 4*KP/16 tcgen05.mma (M=128 units, N=16 batch slots, K=16) :
+//   * W_hh is converted to bf16 once and stays RESIDENT IN TENSOR MEMORY for all T steps (256 of the 512 columns:
+//     lane = hidden unit, gate g at columns 256 + 64 g, packed bf16 pairs) and is the TMEM A operand of tcgen05.mma,
+//     so a thread owns all four gates of its unit -- no cross-thread exchange in the epilogue.
+//   * per step one elected thread of the issuer warp runs 4*KP/16 tcgen05.mma (M=128 units, N=16 batch slots, K=16):
 //     gates^T[g] = W_hh[g] . h_{t-1}^T, fp32 accumulators in TMEM.
-//   * the four epilogue warps tcgen05.ld their lanes, add the hoisted input projection x_t W_ih^T + b (prefetched
-//     from HBM one step ahead), apply sigmoid/tanh (tanh.approx), update the fp32 cell state held in REGISTERS,
-//     write h_t as bf16 straight into the shared-memory operand layout the next step's MMA reads
-//     (generic-proxy store -> fence.proxy.async -> mbarrier), and stream h_t / gate activations / c_t to HBM
-//     for BPTT.
-// Backward mirrors it: W_hh^T resident (A operand, M = hidden unit k, K = 4 gates x units), per step
-//   dh_{t-1}^T = W_hh^T . dG_t^T on tcgen05, gate derivatives + dc carry in registers, dG_t streamed to HBM in
-//   bf16; dW_ih / dW_hh / dX are then three large tcgen05 GEMMs (gemm_tc.cu), db is accumulated in registers.
+//   * the input projection x_t W_ih^T is computed by the same CTA on the tensor pipe's idle slots (W_ih resident in
+//     shared memory, 16/NV timesteps per MMA block, a dedicated warp loads x and issues those MMAs; see
+//     lstm_fwd_tc_kernel) -- or, for I > 128, read from a hoisted projection GEMM through a TMA ring.
+//   * eight epilogue warps tcgen05.ld their lanes, add projection + biases, apply sigmoid/tanh (tanh.approx), update the
+//     fp32 cell state held in REGISTERS, write h_t as bf16 straight into the shared-memory operand layout the next
+//     step's MMA reads (generic-proxy store -> fence.proxy.async -> named-barrier hand-off), and only then stream
+//     h_t / gate activations / c_t to HBM for BPTT.
+// Backward mirrors it: W_hh^T resident in tensor memory (M = hidden unit k, gate-interleaved contraction index 4u+g),
+//   per step dh_{t-1}^T = W_hh^T . dG_t^T on tcgen05 (two issuer warps), gate derivatives + dc carry in registers, the
+//   step's inputs arrive through a TMA ring fed by a producer warp, dG_t is streamed to HBM in bf16; dW_ih / dW_hh / dX
+//   are then large tcgen05 GEMMs (gemm_tc.cu, the two dW products side by side), db is accumulated in registers.
 //
 // The serial chain (T steps) cannot be parallelised; what this design optimises is the per-step latency:
-// no HBM round trip, no grid-wide sync, one mbarrier hand-off in each direction per step.
+// no HBM round trip, no grid-wide sync, one hand-off in each direction per step (forward ~990, backward ~690 cycles).
 #include <mutex>
 #include <type_traits>
 
@@ -27,7 +31,8 @@ namespace csn {
 using namespace tc;
 
 // warps 0-7: epilogue -- warp w owns TMEM lane quadrant w % 4 (32 hidden units) and half (w / 4) of the CTA's batch
-// slots, so the per-step gate math / reserve traffic of a unit is split over two warps; warp 8: MMA issuer.
+// slots, so the per-step gate math / reserve traffic of a unit is split over two warps; warp 8: MMA issuer (backward:
+// warps 8-9); forward warp 9: projection loader / issuer; backward warp 10: TMA producer of the per-step inputs.
 constexpr int kEpiWarps = 8, kIssuerWarp = 8;
 constexpr int kRecThreads = (kEpiWarps + 1) * 32;     // forward: one issuer warp
 constexpr int kRecThreadsBwd = (kEpiWarps + 2) * 32;  // backward: two issuer warps (see issue_bwd)
