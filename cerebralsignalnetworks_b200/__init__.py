@@ -9,7 +9,8 @@ from ._lib import CsnError, LIB_PATH
 
 __all__ = ["CsnError", "LIB_PATH", "Model", "DINOHead", "DINOLoss", "MultiCropWrapper", "EEGFilters",
            "DistillTrainStep", "ops", "IndexFlatL2", "IndexFlatIP", "retrieval",
-           "FeatureDistributionLoss", "CosineSimilarityLoss", "HyperParams"]
+           "FeatureDistributionLoss", "CosineSimilarityLoss", "HyperParams", "loss_fn_kd", "loss_fn_kd_hinton",
+           "cosine_similarity_loss"]
 
 
 def __getattr__(name):  # lazy: keep `import cerebralsignalnetworks_b200` cheap and torch-free until used
@@ -25,7 +26,8 @@ def __getattr__(name):  # lazy: keep `import cerebralsignalnetworks_b200` cheap 
     if name == "DistillTrainStep":
         from .train_step import DistillTrainStep
         return DistillTrainStep
-    if name in ("FeatureDistributionLoss", "CosineSimilarityLoss", "HyperParams"):
+    if name in ("FeatureDistributionLoss", "CosineSimilarityLoss", "HyperParams", "loss_fn_kd", "loss_fn_kd_hinton",
+                "cosine_similarity_loss"):
         from . import losses
         return getattr(losses, name)
     if name in ("IndexFlatL2", "IndexFlatIP", "retrieval"):

@@ -7,6 +7,10 @@
 //     soft target: term2 = -mean_b sum_k p_s[b,k] * log_softmax(q_t[b,:])[k].  Reproduced as written.
 //   * CosineSimilarityLoss (LstmDistillFromDinoV2Train.py:36-43): 1 - mean_b cos(student_b, teacher_b)
 //     (nn.CosineSimilarity: dim = 1, eps = 1e-8, each norm clamped).
+//   * loss_fn_kd, the knowledge-distillation family of the older training scripts:
+//       LSTMDistillRetreival.py:40-70            w_soft * T^2/B * sum q (log q - log p) + w_ce * smooth_l1(student, teacher)
+//       LstmDistillFromDinoV2TrainSpampinato.py:107-121   nn.KLDivLoss()(log p, q) * alpha T^2 + CE(student, label) * (1 - alpha)
+//     with q = softmax(teacher / T), p = softmax(student / T): one kernel, three coefficients chosen by the host.
 #include "common.cuh"
 
 namespace csn {
@@ -148,6 +152,76 @@ __global__ void __launch_bounds__(kLossWarps * 32) cosine_loss_kernel(const floa
   block_atomic_sum(contrib, loss, scratch);
 }
 
+// loss = c_kl * sum_b KL(q_b || p_b) + c_sl1 * sum_{b,k} smooth_l1(s - t) + c_ce * sum_b CE(s_b, label_b)
+// q = softmax(t / T), p = softmax(s / T); smooth_l1 with beta = 1 (the F.smooth_l1_loss default).  The host folds the
+// reductions (1/B, 1/(B K), T^2, the loss weights) into the three coefficients.
+template <int EPT>
+__global__ void __launch_bounds__(kLossWarps * 32) kd_loss_kernel(const float* __restrict__ student,
+                                                                const float* __restrict__ teacher,
+                                                                const long long* __restrict__ label, float* __restrict__ loss,
+                                                                float* __restrict__ d_student, int B, int K, float inv_T,
+                                                                float c_kl, float c_sl1, float c_ce, float grad_scale) {
+  __shared__ float scratch[kLossWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * kLossWarps + warp;
+  float contrib = 0.f;
+  if (b < B) {
+    float s[EPT], t[EPT];
+    float ms = -INFINITY, mt = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int k = lane + 32 * i;
+      s[i] = (k < K) ? student[size_t(b) * K + k] : -INFINITY;
+      t[i] = (k < K) ? teacher[size_t(b) * K + k] : -INFINITY;
+      ms = fmaxf(ms, s[i]);
+      mt = fmaxf(mt, t[i]);
+    }
+    ms = warp_max(ms);
+    mt = warp_max(mt);
+    // three softmax denominators: student at T, teacher at T, student at 1 (cross-entropy term only)
+    float zs = 0.f, zt = 0.f, z1 = 0.f;
+    const float a2 = inv_T * kL2e;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      zs += ex2f_((s[i] - ms) * a2);
+      zt += ex2f_((t[i] - mt) * a2);
+      if (c_ce != 0.f) z1 += ex2f_((s[i] - ms) * kL2e);
+    }
+    zs = warp_sum(zs);
+    zt = warp_sum(zt);
+    const float lzs = __logf(zs), lzt = __logf(zt);
+    float lz1 = 0.f;
+    long long y = -1;
+    if (c_ce != 0.f) {
+      lz1 = __logf(warp_sum(z1));
+      y = label[b];
+    }
+    float kl = 0.f, sl1 = 0.f, ce = 0.f;
+    const float g_kl = grad_scale * c_kl * inv_T, g_sl1 = grad_scale * c_sl1, g_ce = grad_scale * c_ce;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) {
+        const float lp = (s[i] - ms) * inv_T - lzs, lq = (t[i] - mt) * inv_T - lzt;  // log-probabilities
+        const float pk = __expf(lp), qk = __expf(lq);
+        kl = fmaf(qk, lq - lp, kl);  // q = 0 contributes 0 (nn.KLDivLoss's xlogy convention)
+        const float d = s[i] - t[i], ad = fabsf(d);
+        sl1 += ad < 1.f ? 0.5f * d * d : ad - 0.5f;
+        float g = g_kl * (pk - qk) + g_sl1 * fminf(fmaxf(d, -1.f), 1.f);
+        if (c_ce != 0.f) {
+          const float l1 = (s[i] - ms) - lz1;
+          g += g_ce * (__expf(l1) - (k == y ? 1.f : 0.f));
+          if (k == y) ce = -l1;
+        }
+        d_student[size_t(b) * K + k] = g;
+      }
+    }
+    contrib = c_kl * kl + c_sl1 * sl1 + c_ce * ce;
+  }
+  contrib = warp_sum(contrib);
+  block_atomic_sum(contrib, loss, scratch);
+}
+
 }  // namespace csn
 
 using namespace csn;
@@ -187,6 +261,27 @@ extern "C" int csn_cosine_loss_fwd_bwd(const float* student, const float* teache
   else if (K <= 512) CSN_CL(16);
   else CSN_CL(32);
 #undef CSN_CL
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_kd_loss_fwd_bwd(const float* student, const float* teacher, const long long* label, float* loss,
+                                   float* d_student, int B, int K, float temperature, float c_kl, float c_sl1, float c_ce,
+                                   float grad_scale, void* stream) {
+  CSN_REQUIRE(student && teacher && loss && d_student, "csn_kd_loss_fwd_bwd: null pointer");
+  CSN_REQUIRE(B >= 1 && K >= 1 && K <= 1024, "csn_kd_loss_fwd_bwd: need B >= 1 and 1 <= K <= 1024 (got B=%d K=%d)", B, K);
+  CSN_REQUIRE(temperature != 0.f, "csn_kd_loss_fwd_bwd: temperature must be non-zero");
+  CSN_REQUIRE(c_ce == 0.f || label, "csn_kd_loss_fwd_bwd: the cross-entropy term needs labels");
+  cudaStream_t s = as_stream(stream);
+  CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  const int blocks = ceil_div(B, kLossWarps);
+#define CSN_KD(E) kd_loss_kernel<E><<<blocks, kLossWarps * 32, 0, s>>>(student, teacher, label, loss, d_student, B, K, \
+                                                                       1.f / temperature, c_kl, c_sl1, c_ce, grad_scale)
+  if (K <= 128) CSN_KD(4);
+  else if (K <= 256) CSN_KD(8);
+  else if (K <= 512) CSN_KD(16);
+  else CSN_KD(32);
+#undef CSN_KD
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }

@@ -103,3 +103,64 @@ class CosineSimilarityLoss(nn.Module):
     def forward(self, student_outputs, teacher_outputs):
         _lib.require_gpu()
         return _CosineFunction.apply(student_outputs.float().contiguous(), teacher_outputs.detach().float().contiguous(), self.eps)
+
+
+class Parameters:
+    """The class-level knobs of LSTMDistillRetreival.py:33-37 (`loss_fn_kd` reads alpha / temperature and the weights)."""
+    ce_loss_weight = 0.50
+    soft_target_loss_weight = 0.50
+    alpha = 1
+    temperature = 2
+
+
+class _KDFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher, label, temperature, c_kl, c_sl1, c_ce):
+        B, K = student.shape
+        loss = torch.empty((), dtype=torch.float32, device=student.device)
+        d_student = torch.empty_like(student)
+        call("csn_kd_loss_fwd_bwd", _p(student), _p(teacher), _p(label), _p(loss), _p(d_student), B, K, float(temperature),
+             float(c_kl), float(c_sl1), float(c_ce), 1.0, _stream())
+        ctx.save_for_backward(d_student)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (d_student,) = ctx.saved_tensors
+        return ops.scale_(d_student, dloss.contiguous().to(torch.float32)), None, None, None, None, None, None
+
+
+def _kd_inputs(student_logits, teacher_logits):
+    _lib.require_gpu()
+    s = student_logits.float().contiguous()
+    t = teacher_logits.detach().float().contiguous()
+    if s.dim() != 2 or s.shape != t.shape:
+        raise ValueError("loss_fn_kd: student / teacher logits must both be [B, K] (got %s, %s)" % (tuple(s.shape), tuple(t.shape)))
+    return s, t
+
+
+def loss_fn_kd(student_logits, labels, teacher_logits, params=Parameters):
+    """LSTMDistillRetreival.py:40-70: soft_target_loss_weight * T^2 / B * sum q (log q - log p) + ce_loss_weight *
+    F.smooth_l1_loss(student, teacher), q = softmax(teacher / T), p = softmax(student / T).  `labels` is unused there too."""
+    s, t = _kd_inputs(student_logits, teacher_logits)
+    B, K = s.shape
+    T = float(params.temperature)
+    return _KDFunction.apply(s, t, None, T, params.soft_target_loss_weight * T * T / B, params.ce_loss_weight / (B * K), 0.0)
+
+
+def loss_fn_kd_hinton(outputs, labels, teacher_outputs, params=Parameters):
+    """LstmDistillFromDinoV2TrainSpampinato.py:107-121: nn.KLDivLoss()(log_softmax(outputs / T), softmax(teacher / T)) *
+    (alpha T^2) + F.cross_entropy(outputs, labels) * (1 - alpha).  KLDivLoss's default reduction is the mean over ALL
+    B*K elements, kept as written."""
+    s, t = _kd_inputs(outputs, teacher_outputs)
+    B, K = s.shape
+    T, alpha = float(params.temperature), float(params.alpha)
+    lab = labels.to(device=s.device, dtype=torch.int64).contiguous() if alpha != 1.0 else None
+    return _KDFunction.apply(s, t, lab, T, alpha * T * T / (B * K), 0.0, (1.0 - alpha) / B)
+
+
+def cosine_similarity_loss(v1, v2):
+    """LSTMDistill.py:33-58 (what its loss_fn_kd returns, :60-98): -mean_b cos(v1_b, v2_b) with F.normalize's clamp
+    (each norm at least 1e-12)."""
+    _lib.require_gpu()
+    return _CosineFunction.apply(v1.float().contiguous(), v2.detach().float().contiguous(), 1e-12) - 1.0

@@ -178,6 +178,14 @@ int csn_feature_dist_loss_fwd_bwd(const float* student, const float* teacher, co
                                   float temperature, float alpha, float beta, float grad_scale, void* stream);
 int csn_cosine_loss_fwd_bwd(const float* student, const float* teacher, float* loss, float* d_student, int B, int K,
                             float eps, float grad_scale, void* stream);
+/* loss_fn_kd of the older training scripts (LSTMDistillRetreival.py:40-70, LstmDistillFromDinoV2TrainSpampinato.py:107-121):
+ *   loss = c_kl * sum_b KL(softmax(teacher_b / T) || softmax(student_b / T)) + c_sl1 * sum_{b,k} smooth_l1(student - teacher)
+ *        + c_ce * sum_b cross_entropy(student_b, label_b)
+ * (smooth_l1 with beta = 1).  The caller folds the reductions and weights into the coefficients, e.g. Retreival:
+ * c_kl = w_soft T^2 / B, c_sl1 = w_ce / (B K), c_ce = 0; Spampinato: c_kl = alpha T^2 / (B K), c_ce = (1 - alpha) / B.
+ * label [B] int64, may be NULL when c_ce == 0.  K <= 1024.  d_student [B,K] = gradient * grad_scale. */
+int csn_kd_loss_fwd_bwd(const float* student, const float* teacher, const long long* label, float* loss, float* d_student,
+                        int B, int K, float temperature, float c_kl, float c_sl1, float c_ce, float grad_scale, void* stream);
 
 /* ---- GPU-resident dataset batches ------------------------------------------------------
  * src [N, C, T_raw] fp32: the stacked "eeg" tensors of the .pth file ConvertToPth.py:170-201 writes.  For every b:

@@ -258,3 +258,26 @@ def feature_distribution_loss(student, teacher, temperature, label, pred_label, 
 def cosine_similarity_loss(student, teacher):
     """LstmDistillFromDinoV2Train.py:36-43."""
     return 1 - nn.CosineSimilarity()(student, teacher).mean()
+
+
+def kd_loss_retrieval(student_logits, teacher_logits, temperature, soft_target_loss_weight, ce_loss_weight):
+    """LSTMDistillRetreival.py:40-70 (`loss_fn_kd`): T^2-scaled soft-target divergence summed over the batch and divided
+    by B, plus the element-mean smooth-L1 between the raw logits."""
+    T = temperature
+    q = F.softmax(teacher_logits / T, dim=-1)
+    logp = F.log_softmax(student_logits / T, dim=-1)
+    soft = torch.sum(q * (q.log() - logp)) / logp.size(0) * (T ** 2)
+    return soft_target_loss_weight * soft + ce_loss_weight * F.smooth_l1_loss(student_logits, teacher_logits)
+
+
+def kd_loss_hinton(outputs, labels, teacher_outputs, temperature, alpha):
+    """LstmDistillFromDinoV2TrainSpampinato.py:107-121 (`loss_fn_kd`): nn.KLDivLoss() (element mean) * alpha T^2 +
+    cross-entropy on the hard labels * (1 - alpha)."""
+    T = temperature
+    kd = nn.KLDivLoss()(F.log_softmax(outputs / T, dim=1), F.softmax(teacher_outputs / T, dim=1)) * (alpha * T * T)
+    return kd + F.cross_entropy(outputs, labels) * (1.0 - alpha)
+
+
+def neg_cosine_loss(v1, v2):
+    """LSTMDistill.py:33-58 (`cosine_similarity_loss`, returned by its loss_fn_kd :60-98)."""
+    return -torch.mean(torch.sum(F.normalize(v1, p=2, dim=1) * F.normalize(v2, p=2, dim=1), dim=1))

@@ -198,6 +198,51 @@ def golden_alt_losses():
     np.savez(os.path.join(GOLD, "alt_losses.npz"), versions=str(VERS), **out)
 
 
+def golden_kd_losses():
+    """The `loss_fn_kd` family of the older training scripts, run through the REFERENCE'S OWN functions:
+    LSTMDistillRetreival.py:40-70 (soft targets + smooth-L1), LstmDistillFromDinoV2TrainSpampinato.py:107-121 (Hinton KD +
+    hard-label CE), LSTMDistill.py:60-98 (negative cosine)."""
+    import warnings
+    g = torch.Generator().manual_seed(51)
+    out = {}
+    ret = import_reference("LSTMDistillRetreival")
+    out["ret_T"], out["ret_w_soft"], out["ret_w_ce"] = (np.float64(ret.Parameters.temperature),
+                                                         np.float64(ret.Parameters.soft_target_loss_weight),
+                                                         np.float64(ret.Parameters.ce_loss_weight))
+    for i, (B, K, spread) in enumerate([(5, 40, 1.0), (7, 384, 0.6), (3, 768, 2.5)]):
+        s = (torch.randn(B, K, generator=g) * spread).requires_grad_(True)
+        t = torch.randn(B, K, generator=g) * spread
+        loss = ret.loss_fn_kd(s, None, t, ret.Parameters)
+        loss.backward()
+        out.update({f"ret_student{i}": s.detach().numpy(), f"ret_teacher{i}": t.numpy(), f"ret_loss{i}": loss.detach().numpy(),
+                    f"ret_dstudent{i}": s.grad.numpy()})
+    spa = import_reference("LstmDistillFromDinoV2TrainSpampinato")
+
+    class P:
+        pass
+    for i, (B, K, alpha, T) in enumerate([(6, 40, 0.9, 4.0), (4, 100, 0.5, 2.0), (5, 40, 1.0, 3.0)]):
+        P.alpha, P.temperature = alpha, T
+        s = torch.randn(B, K, generator=g, requires_grad=True)
+        t = torch.randn(B, K, generator=g) * 2.0
+        y = torch.randint(0, K, (B,), generator=g)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")   # KLDivLoss warns that reduction='mean' is not the batch mean
+            loss = spa.loss_fn_kd(s, y, t, P)
+        loss.backward()
+        out.update({f"hin_student{i}": s.detach().numpy(), f"hin_teacher{i}": t.numpy(), f"hin_label{i}": y.numpy(),
+                    f"hin_alpha{i}": np.float64(alpha), f"hin_T{i}": np.float64(T), f"hin_loss{i}": loss.detach().numpy(),
+                    f"hin_dstudent{i}": s.grad.numpy()})
+    dis = import_reference("LSTMDistill")
+    for i, (B, K) in enumerate([(4, 24), (6, 384)]):
+        s = torch.randn(B, K, generator=g, requires_grad=True)
+        t = torch.randn(B, K, generator=g)
+        loss = dis.loss_fn_kd(s, t, None, None, dis.Parameters)
+        loss.backward()
+        out.update({f"neg_student{i}": s.detach().numpy(), f"neg_teacher{i}": t.numpy(), f"neg_loss{i}": loss.detach().numpy(),
+                    f"neg_dstudent{i}": s.grad.numpy()})
+    np.savez(os.path.join(GOLD, "kd_losses.npz"), versions=str(VERS), **out)
+
+
 def golden_dataset():
     """The reference's own EEGDataset (utils/PerilsEEGDataset.py) on a small synthetic .pth file in the schema of
     ConvertToPth.py:170-201: dataset-level mean / std and the EEG tensor of every item, with and without normalisation."""
@@ -245,6 +290,10 @@ def main():
         golden_dataset()
         print("dataset.npz written")
         return 0
+    if "--only-kd-losses" in sys.argv:
+        golden_kd_losses()
+        print("kd_losses.npz written")
+        return 0
     if "--only-alt-losses" in sys.argv:
         golden_alt_losses()
         print("alt_losses.npz written")
@@ -256,6 +305,7 @@ def main():
     golden_filters()
     golden_lstm_step()
     golden_alt_losses()
+    golden_kd_losses()
     golden_dataset()
     print("golden vectors written to", GOLD)
     for f in sorted(os.listdir(GOLD)):
