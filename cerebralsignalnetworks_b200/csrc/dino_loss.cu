@@ -236,6 +236,10 @@ __global__ void __launch_bounds__(kLossThreads) dino_loss_kernel(const LossParam
 //   * the cluster exchange is a PUSH: warp 0 sends the CTA's (max, sum, dot) to every peer's mailbox with st.async
 //     (data + mbarrier complete_tx in one DSMEM packet), everybody waits on a local mbarrier.  No cluster.sync (and
 //     its L1 flush) and no remote loads on the critical path.
+// Measured and dropped: a two-pass variant that takes the exchange off the row chain (pass 1 of row r -> push, then pass 2
+// of row r - 1 re-reads its ring stage against the global statistics).  Parity-green but 60 -> 70 us at the cfg3 shape:
+// the stage of row r - 1 stays occupied one row longer, so only one row per CTA is in flight instead of two, and the
+// memory-level parallelism lost costs more than the exchange wait it hides.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -284,6 +288,12 @@ __device__ __forceinline__ float lg2_(float x) {
   return y;
 }
 
+// 16-byte vector reduction into global memory: one L2 atomic transaction instead of four (shared-centre modes: the
+// column sums of B rows meet in the same K floats)
+__device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 constexpr float kNegBig = -1.0e30f;   // padding logit: never the maximum, ex2(kNegBig - m) == 0, 0 * kNegBig == -0
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -311,27 +321,23 @@ __global__ void __launch_bounds__(kLossThreads, 2) dino_loss_staged_kernel(const
   __shared__ __align__(16) float4 warp_buf[kLossThreads / 32];
   __shared__ __align__(8) uint64_t xbar[kMaxRounds];       // one exchange barrier per round, never reused
   __shared__ int vlist[kMaxVs];
-  __shared__ int n_active_s;
 
-  if (tid == 0) {
-    int n = 0;
-    for (int v = 0; v < p.Vs; ++v)
-      if (p.mask[v]) vlist[n++] = v;
-    n_active_s = n;
-    for (int i = 0; i < S; ++i) mbar_init_(&full[i], 1);
-    for (int r = 0; r < p.Vt + n; ++r) {
-      mbar_init_(&xbar[r], 1);
-      mbar_expect_tx_(&xbar[r], cs * 16u);  // the phase completes when all cs mailboxes of the round have landed
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  cluster_arrive_();  // peers may push into our mailboxes once they have seen this arrive (waited for before push 0)
-  const int n_active = n_active_s;
+  // Prologue, spread over threads so that nothing serial sits in front of the first bulk copy: every thread counts the
+  // active views itself (a few constant-bank reads), warp 2 builds the view list with a ballot, the first threads of
+  // warp 0 initialise one exchange barrier each, and the PRODUCER thread initialises its own ring barriers and starts
+  // the first S row copies before the CTA even synchronises.
+  int n_active = 0;
+  for (int v = 0; v < p.Vs; ++v) n_active += p.mask[v] ? 1 : 0;
   const int nrows = p.Vt + n_active;
-  auto row_src = [&](int r) -> const float* {
+  auto nth_active = [&](int a) -> int {
+    int v = 0;
+    for (; v < p.Vs; ++v)
+      if (p.mask[v] && a-- == 0) break;
+    return v;
+  };
+  auto row_src = [&](int r) -> const float* {  // producer only
     if (r < p.Vt) return p.teacher + (size_t(r) * p.B + b) * p.K + k0;
-    return p.student + (size_t(vlist[r - p.Vt]) * p.B + b) * p.K + k0;
+    return p.student + (size_t(nth_active(r - p.Vt)) * p.B + b) * p.K + k0;
   };
   constexpr int kProducer = 32;  // warp 1 lane 0 feeds the ring; warp 0 owns the exchange
   auto issue = [&](int r) {
@@ -339,8 +345,23 @@ __global__ void __launch_bounds__(kLossThreads, 2) dino_loss_staged_kernel(const
     mbar_expect_tx_(bar, row_bytes);
     bulk_g2s(stages + size_t(r % S) * p.Kc, row_src(r), row_bytes, bar);
   };
-  if (tid == kProducer)
+  if (tid == kProducer) {
+    for (int i = 0; i < S; ++i) mbar_init_(&full[i], 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the inits are visible to the TMA unit
     for (int r = 0; r < S && r < nrows; ++r) issue(r);
+  } else if (tid < nrows) {
+    mbar_init_(&xbar[tid], 1);
+    mbar_expect_tx_(&xbar[tid], cs * 16u);  // the phase completes when all cs mailboxes of the round have landed
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    const bool act = lane < p.Vs && p.mask[lane < p.Vs ? lane : 0] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (act) vlist[__popc(bal & ((1u << lane) - 1u))] = lane;
+  }
+  __syncthreads();
+  // peers may push into our mailboxes once they have seen this arrive (waited for before push 0); the barrier inits
+  // were released by fence.mbarrier_init, so the arrive itself carries no memory fence
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
   auto in_range = [&](int it) { return (it * kLossThreads + tid) * 4 < p.Kc; };
   auto store_row = [&](float* base, const float (&src)[EPT]) {
@@ -469,10 +490,8 @@ __global__ void __launch_bounds__(kLossThreads, 2) dino_loss_staged_kernel(const
   } else {
 #pragma unroll
     for (int it = 0; it < NITER; ++it)
-      if (in_range(it)) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) atomicAdd(p.batch_center + k0 + (it * kLossThreads + tid) * 4 + j, bc[it * 4 + j]);
-      }
+      if (in_range(it))
+        red_add_f4(p.batch_center + k0 + (it * kLossThreads + tid) * 4, bc[it * 4], bc[it * 4 + 1], bc[it * 4 + 2], bc[it * 4 + 3]);
   }
 
   // ---- student rows ----
@@ -525,8 +544,9 @@ __global__ void __launch_bounds__(kLossThreads, 2) dino_loss_staged_kernel(const
   }
   if (crank == 0 && tid == 0) atomicAdd(p.loss, loss_acc);
   if (first_push) cluster_wait_();  // (no rows at all: still pair the arrive)
-  cluster_arrive_();                // nobody leaves while a peer could still be pushing to it / reading from it
-  cluster_wait_();
+  // No closing cluster barrier: a CTA gets here only after the LAST round's cs packets have landed in its mailbox, i.e.
+  // after every peer has issued its last push to it, and it never reads remote memory -- nobody can still touch the
+  // shared memory of a CTA that exits.  (A release-arrive here made every CTA wait for its gradient stores to drain.)
 }
 
 template <int NITER, bool ALLSAME>
