@@ -239,7 +239,9 @@ __global__ void __launch_bounds__(kLossThreads) dino_loss_kernel(const LossParam
 // Measured and dropped: a two-pass variant that takes the exchange off the row chain (pass 1 of row r -> push, then pass 2
 // of row r - 1 re-reads its ring stage against the global statistics).  Parity-green but 60 -> 70 us at the cfg3 shape:
 // the stage of row r - 1 stays occupied one row longer, so only one row per CTA is in flight instead of two, and the
-// memory-level parallelism lost costs more than the exchange wait it hides.
+// memory-level parallelism lost costs more than the exchange wait it hides.  Keeping the row's 2^(x - max) in registers
+// instead (gradient of row r deferred behind pass 1 of row r + 1, ring untouched) also measured 70 us: 32 more live
+// registers per thread spill at the 128-register cap of two CTAs per SM.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
