@@ -43,6 +43,29 @@ class DeviceEEGDataset:
         if not (0 <= self.time_low < self.time_high <= self.T_raw):
             raise _lib.CsnError("need 0 <= time_low < time_high <= %d" % self.T_raw)
 
+    @classmethod
+    def from_tensor(cls, eeg_nct, labels=None, image_index=None, time_low=20, time_high=480,
+                    apply_norm_with_stds_and_means=False, device="cuda"):
+        """Same dataset from an already stacked [N, C, T_raw] array (any device) instead of the .pth item list."""
+        _lib.require_gpu()
+        self = cls.__new__(cls)
+        self.class_labels, self.image_names = [], []
+        self.time_low, self.time_high = int(time_low), int(time_high)
+        self.apply_norm_with_stds_and_means = bool(apply_norm_with_stds_and_means)
+        self.device = torch.device(device)
+        self.eeg = torch.as_tensor(eeg_nct).to(device=self.device, dtype=torch.float32).contiguous()
+        if self.eeg.dim() != 3 or self.eeg.shape[0] == 0:
+            raise _lib.CsnError("from_tensor: need a non-empty [N, C, T_raw] array")
+        self.N, self.C, self.T_raw = self.eeg.shape
+        self.mean = float(self.eeg.mean(dim=(1, 2)).mean())   # mean of the per-item means / unbiased stds (:93-103)
+        self.std = float(self.eeg.std(dim=(1, 2)).mean())
+        n = self.N
+        self.labels = (torch.zeros(n, dtype=torch.int64) if labels is None else torch.as_tensor(labels, dtype=torch.int64)).to(self.device)
+        self.image_index = (torch.arange(n) if image_index is None else torch.as_tensor(image_index, dtype=torch.int64)).to(self.device)
+        if not (0 <= self.time_low < self.time_high <= self.T_raw):
+            raise _lib.CsnError("need 0 <= time_low < time_high <= %d" % self.T_raw)
+        return self
+
     def __len__(self):
         return self.N
 
@@ -63,6 +86,26 @@ class DeviceEEGDataset:
         call("csn_gather_trials", _p(self.eeg), _p(idx), _p(out), self.N, self.C, self.T_raw, B, self.time_low,
              self.time_high, float(mean), float(std), layout, _stream())
         return out, idx
+
+    def check_indices(self, indices):
+        """Host-side validation of a batch of trial indices (no device synchronisation) -> contiguous CPU int64 [B]."""
+        idx = torch.as_tensor(indices, dtype=torch.int64, device="cpu").contiguous()
+        if idx.dim() != 1:
+            raise _lib.CsnError("indices must be one-dimensional")
+        if idx.numel() and (int(idx.max()) >= self.N or int(idx.min()) < -self.N):
+            raise IndexError("trial index out of range for %d trials" % self.N)
+        return idx
+
+    def gather_into(self, out_bct, idx_dev):
+        """The gather kernel alone: trials `idx_dev` (device int64 [B], already validated) -> `out_bct` ([B, C, T]
+        float32, preallocated).  No allocation, no synchronisation: safe on any stream and under graph capture."""
+        B = idx_dev.numel()
+        if tuple(out_bct.shape) != (B, self.C, self.samples) or out_bct.dtype != torch.float32 or not out_bct.is_contiguous():
+            raise _lib.CsnError("gather_into: out must be contiguous float32 [%d, %d, %d]" % (B, self.C, self.samples))
+        mean, std = (self.mean, self.std) if self.apply_norm_with_stds_and_means else (0.0, 1.0)
+        call("csn_gather_trials", _p(self.eeg), _p(idx_dev), _p(out_bct), self.N, self.C, self.T_raw, B, self.time_low,
+             self.time_high, float(mean), float(std), LAYOUT_BCT, _stream())
+        return out_bct
 
     def batch(self, indices):
         """-> (eeg [B, C, T] float32 in the stored layout -- feed it to DistillTrainStep.step / Model.encode_trials --,

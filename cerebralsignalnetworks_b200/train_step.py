@@ -77,6 +77,7 @@ class DistillTrainStep:
         self._graph = None
         self._graph_tau = None
         self._static = None
+        self._idx_ring = None      # step_from_dataset: pinned index slots + their device copy
         self._resident = {}        # (eeg ptr, teacher ptr) -> (eeg, teacher): buffers with their own captured graph
         self._resident_graphs = {}  # (eeg ptr, teacher ptr, tau) -> (graph, loss tensor)
         self._pool = None
@@ -172,6 +173,35 @@ class DistillTrainStep:
         if not self.use_cuda_graph or self._stage_events is not None:
             return self._run(eeg_bct.contiguous(), teacher_feats.contiguous(), tau_t)
         return self._step_graphed(eeg_bct, teacher_feats, tau_t)
+
+    def step_from_dataset(self, dataset, indices, teacher_feats, epoch=0):
+        """One step on a batch of a GPU-RESIDENT dataset (dataset.DeviceEEGDataset): `indices` is a host int64 [B]
+        (e.g. from dataset.epoch_batches), `teacher_feats` float32 [B, K] on the host (pinned) or the device.  The trials
+        are gathered on the device straight into the step's static input buffer, so only the indices and the image
+        features cross PCIe (8 B + 4 K bytes per trial instead of 4 C T) -- the replacement for DataLoader + `.to(device)`
+        of LstmDistillFromDinoV2Train.py:358-363 when the .pth fits in HBM."""
+        idx = dataset.check_indices(indices)
+        B = idx.numel()
+        if self._static is None:
+            dev = dataset.eeg.device
+            self._static = (torch.empty(B, dataset.C, dataset.samples, dtype=torch.float32, device=dev),
+                            torch.empty(B, teacher_feats.shape[1], dtype=torch.float32, device=dev))
+        se, st = self._static
+        if se.shape[0] != B:
+            raise _lib.CsnError("step_from_dataset: batch size changed (%d -> %d)" % (se.shape[0], B))
+        if self._idx_ring is None:  # pinned index slots: a slot is rewritten only after its copy has completed
+            self._idx_ring = [(torch.empty(B, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._idx_dev = torch.empty(B, dtype=torch.int64, device=se.device)
+            self._idx_n = 0
+        h_idx, done = self._idx_ring[self._idx_n % len(self._idx_ring)]
+        self._idx_n += 1
+        done.synchronize()
+        h_idx.copy_(idx)
+        self._idx_dev.copy_(h_idx, non_blocking=True)
+        done.record()
+        dataset.gather_into(se, self._idx_dev)
+        st.copy_(teacher_feats, non_blocking=True)
+        return self.step(se, st, epoch)
 
     # CUDA-graph path.  The ~30 launches of a step are captured once and replayed with one submission.  Everything
     # that varies between steps lives on the device: the inputs are copied into static buffers (`input_buffers()`

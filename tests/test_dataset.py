@@ -100,3 +100,39 @@ def test_cli_trains_from_a_pth_dataset(tmp_path, capsys):
     assert "EPOCH 0 train_loss" in out and "EPOCH 1 train_loss" in out
     sd = torch.load(str(tmp_path / "logs" / "lstm_dinov2_last.pth"))
     assert "lstm.weight_ih_l0" in sd and all(torch.isfinite(v).all() for v in sd.values())
+
+
+@pytest.mark.gpu
+def test_step_from_resident_dataset_equals_step_on_gathered_batch():
+    """DistillTrainStep.step_from_dataset (indices -> device gather into the static input buffer) must be the same
+    step as step(dataset.batch(indices)): identical loss and identical weights after two updates."""
+    import copy
+    import cerebralsignalnetworks_b200 as csn
+    from cerebralsignalnetworks_b200.dataset import DeviceEEGDataset
+    torch.manual_seed(2)
+    N, C, T_raw, lo, hi, B, H, D = 40, 16, 72, 4, 68, 8, 32, 24
+    ds = DeviceEEGDataset.from_tensor(torch.randn(N, C, T_raw), time_low=lo, time_high=hi, apply_norm_with_stds_and_means=True)
+    assert ds.samples == hi - lo and len(ds) == N
+    sos = csn.EEGFilters(1000.0).sos(5.0, 95.0, 2)
+    feats = [torch.randn(B, D).pin_memory() for _ in range(2)]
+    batches = [torch.tensor([3, 39, 0, 17, -1, 8, 21, 5]), torch.tensor([9, 2, 30, 31, 11, 4, 6, 12])]
+    results = []
+    for mode in ("dataset", "batch"):
+        torch.manual_seed(7)
+        model = csn.Model(C, H, 1, D, compute_dtype=torch.float32).cuda()
+        loss_mod = csn.DINOLoss(D, 1, 1.5, 0.22, 5, 10).cuda()
+        step = csn.DistillTrainStep(model, loss_mod, lr=1e-2, sos=sos)
+        losses = []
+        for k in range(4):  # eager first call, then graph capture + replays
+            idx, f = batches[k % 2], feats[k % 2]
+            if mode == "dataset":
+                losses.append(float(step.step_from_dataset(ds, idx, f, epoch=0)))
+            else:
+                eeg, _, _ = ds.batch(idx)
+                losses.append(float(step.step(eeg, f.cuda(), epoch=0)))
+        results.append((losses, copy.deepcopy({k: v.cpu() for k, v in model.state_dict().items()})))
+    np.testing.assert_allclose(results[0][0], results[1][0], rtol=1e-6)
+    for k in results[0][1]:
+        np.testing.assert_allclose(results[0][1][k].numpy(), results[1][1][k].numpy(), rtol=1e-6, atol=1e-7, err_msg=k)
+    with pytest.raises(IndexError):
+        step.step_from_dataset(ds, torch.tensor([0, 1, 2, 3, 4, 5, 6, N]), feats[0])
