@@ -227,9 +227,20 @@ __global__ void __launch_bounds__(128) sosfilt_stream_kernel(const float* __rest
 // per 32-sample chunk) and the tile store (200).  This variant serves the common case (16-byte aligned rows, full
 // blocks of 32 series, time-major bf16/fp32 or channel-major fp32 output) with running pointers, a predicate-free
 // body for full chunks and one warp per block (warp-level barriers only): ~24 instructions per sample.
-template <int NSEC, typename OutT, bool TIME_MAJOR, bool UNIT_B2>
+// Optional fused GATHER (GPU-resident dataset): with `g.idx` set, batch row b of the input is trial
+// g.idx[b] of a [n_trials, C, row_stride] array, samples [t_off, t_off + T), optionally (x - mean) * inv_std -- the crop
+// / normalisation of EEGDataset.__getitem__ (utils/PerilsEEGDataset.py:541-573) folded into the filter's loads, so the
+// gathered batch is never written to HBM.
+struct GatherSrc {
+  const long long* idx;  // nullptr: x is the dense [B, C, T] batch
+  int n_trials, C, row_stride, t_off;
+  float mean, inv_std;   // applied when norm != 0
+  int norm;
+};
+
+template <int NSEC, typename OutT, bool TIME_MAJOR, bool UNIT_B2, bool GATHER>
 __global__ void __launch_bounds__(32) sosfilt_warp_kernel(const float* __restrict__ x, OutT* __restrict__ y,
-                                                         const SosCoef coef, int T, long long N) {
+                                                         const SosCoef coef, int T, long long N, const GatherSrc g) {
   constexpr int R = 32;
   extern __shared__ __align__(16) float smem[];
   float* in_tile = smem;                        // [kStages][R][kRS]
@@ -245,7 +256,15 @@ __global__ void __launch_bounds__(32) sosfilt_warp_kernel(const float* __restric
   // cp.async of a chunk: lane -> (row lane/8 + 4 j, 16-byte column lane%8), j = 0..7
   const int row8 = lane >> 3, c4 = lane & 7;
   const float* src = x + size_t(r0 + row8) * T + c4 * 4;   // advanced by kTC floats per issued chunk
-  const size_t src_jstride = size_t(4) * T;
+  size_t src_jstride = size_t(4) * T;
+  if constexpr (GATHER) {  // the block's 32 series are channels [c0, c0 + 32) of ONE batch row (C % 32 == 0)
+    const long long bi = r0 / g.C;
+    long long trial = g.idx[bi];
+    if (trial < 0) trial += g.n_trials;
+    const int c0 = (int)(r0 - bi * g.C);
+    src = x + (size_t(trial) * g.C + c0 + row8) * g.row_stride + g.t_off + c4 * 4;
+    src_jstride = size_t(4) * g.row_stride;
+  }
   const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(in_tile + row8 * kRS + c4 * 4);
   int t_issue = c4 * 4;                                     // first sample this lane fetches in the next chunk
   auto issue_load = [&](int buf) {
@@ -283,6 +302,10 @@ __global__ void __launch_bounds__(32) sosfilt_warp_kernel(const float* __restric
     for (int q = 0; q < kTC / 4; ++q) {
       const float4 v = *reinterpret_cast<const float4*>(row + q * 4);
       xin[q * 4 + 0] = v.x; xin[q * 4 + 1] = v.y; xin[q * 4 + 2] = v.z; xin[q * 4 + 3] = v.w;
+    }
+    if (GATHER && g.norm) {  // same two roundings as csn_gather_trials: the fused and the two-kernel path agree bit for bit
+#pragma unroll
+      for (int i = 0; i < kTC; ++i) xin[i] = (xin[i] - g.mean) * g.inv_std;
     }
     if constexpr (TIME_MAJOR) {
       cascade_chunk_skewed<NSEC, UNIT_B2>(xin, s1, s2, coef, [&](int idx, float yv) { out_tile[idx * R + lane] = yv; });
@@ -388,24 +411,36 @@ __global__ void __launch_bounds__(32) sosfiltfilt_kernel(const float* __restrict
 
 template <int NSEC, typename OutT>
 static int launch_sosfilt(const float* x, void* y, const SosCoef& coef, int B, int C, int T, int zero_phase,
-                          int layout, cudaStream_t s) {
+                          int layout, cudaStream_t s, const GatherSrc& gsrc = GatherSrc{}) {
   const long long n_series = (long long)B * C;
+  if (gsrc.idx) {  // fused gather: fast path only (the caller falls back to csn_gather_trials + csn_sosfilt_f32)
+    const bool ok = !zero_phase && T % 4 == 0 && C % 32 == 0 && gsrc.row_stride % 4 == 0 && gsrc.t_off % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                    (layout == CSN_LAYOUT_TBC || (layout == CSN_LAYOUT_BCT && sizeof(OutT) == 4));
+    if (!ok) {
+      set_error("csn_sosfilt_gather_f32: needs causal filtering, C %% 32 == 0, T / T_raw / time_low multiples of 4, 16-byte "
+                "aligned arrays and a TBC (or fp32 BCT) output");
+      return CSN_EUNSUPPORTED;
+    }
+  }
   static const bool no_fast = [] { const char* e = getenv("CSN_FILTER_NO_FAST"); return e && e[0] == '1'; }();
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-  if (!zero_phase && !no_fast && aligned16 && T % 4 == 0 && n_series % 32 == 0 &&
+  if (!zero_phase && (!no_fast || gsrc.idx) && aligned16 && T % 4 == 0 && n_series % 32 == 0 &&
       (layout == CSN_LAYOUT_TBC || (layout == CSN_LAYOUT_BCT && sizeof(OutT) == 4))) {
     const unsigned grid = (unsigned)(n_series / 32);
     bool unit_b2 = NSEC > 1;
     for (int k = 1; k < NSEC; ++k) unit_b2 = unit_b2 && coef.b2[k] == 1.0f;
-    if (layout == CSN_LAYOUT_TBC) {
-      const size_t smem = size_t(kStages) * 32 * kRS * 4 + size_t(kTC) * 32 * 4;
-      if (unit_b2) sosfilt_warp_kernel<NSEC, OutT, true, true><<<grid, 32, smem, s>>>(x, (OutT*)y, coef, T, n_series);
-      else sosfilt_warp_kernel<NSEC, OutT, true, false><<<grid, 32, smem, s>>>(x, (OutT*)y, coef, T, n_series);
+    const bool tm = layout == CSN_LAYOUT_TBC;
+    const size_t smem = size_t(kStages) * 32 * kRS * 4 + (tm ? size_t(kTC) * 32 * 4 : 0);
+#define CSN_FILT(TM, UB, GA) sosfilt_warp_kernel<NSEC, OutT, TM, UB, GA><<<grid, 32, smem, s>>>(x, (OutT*)y, coef, T, n_series, gsrc)
+    if (gsrc.idx) {
+      if (tm) { if (unit_b2) CSN_FILT(true, true, true); else CSN_FILT(true, false, true); }
+      else    { if (unit_b2) CSN_FILT(false, true, true); else CSN_FILT(false, false, true); }
     } else {
-      const size_t smem = size_t(kStages) * 32 * kRS * 4;
-      if (unit_b2) sosfilt_warp_kernel<NSEC, OutT, false, true><<<grid, 32, smem, s>>>(x, (OutT*)y, coef, T, n_series);
-      else sosfilt_warp_kernel<NSEC, OutT, false, false><<<grid, 32, smem, s>>>(x, (OutT*)y, coef, T, n_series);
+      if (tm) { if (unit_b2) CSN_FILT(true, true, false); else CSN_FILT(true, false, false); }
+      else    { if (unit_b2) CSN_FILT(false, true, false); else CSN_FILT(false, false, false); }
     }
+#undef CSN_FILT
     CSN_LAUNCH_CHECK();
     return CSN_OK;
   }
@@ -448,16 +483,16 @@ static int launch_sosfilt(const float* x, void* y, const SosCoef& coef, int B, i
 
 template <typename OutT>
 static int dispatch_nsec(int nsec, const float* x, void* y, const SosCoef& coef, int B, int C, int T, int zp,
-                         int layout, cudaStream_t s) {
+                         int layout, cudaStream_t s, const GatherSrc& g = GatherSrc{}) {
   switch (nsec) {
-    case 1: return launch_sosfilt<1, OutT>(x, y, coef, B, C, T, zp, layout, s);
-    case 2: return launch_sosfilt<2, OutT>(x, y, coef, B, C, T, zp, layout, s);
-    case 3: return launch_sosfilt<3, OutT>(x, y, coef, B, C, T, zp, layout, s);
-    case 4: return launch_sosfilt<4, OutT>(x, y, coef, B, C, T, zp, layout, s);
-    case 5: return launch_sosfilt<5, OutT>(x, y, coef, B, C, T, zp, layout, s);
-    case 6: return launch_sosfilt<6, OutT>(x, y, coef, B, C, T, zp, layout, s);
-    case 7: return launch_sosfilt<7, OutT>(x, y, coef, B, C, T, zp, layout, s);
-    case 8: return launch_sosfilt<8, OutT>(x, y, coef, B, C, T, zp, layout, s);
+    case 1: return launch_sosfilt<1, OutT>(x, y, coef, B, C, T, zp, layout, s, g);
+    case 2: return launch_sosfilt<2, OutT>(x, y, coef, B, C, T, zp, layout, s, g);
+    case 3: return launch_sosfilt<3, OutT>(x, y, coef, B, C, T, zp, layout, s, g);
+    case 4: return launch_sosfilt<4, OutT>(x, y, coef, B, C, T, zp, layout, s, g);
+    case 5: return launch_sosfilt<5, OutT>(x, y, coef, B, C, T, zp, layout, s, g);
+    case 6: return launch_sosfilt<6, OutT>(x, y, coef, B, C, T, zp, layout, s, g);
+    case 7: return launch_sosfilt<7, OutT>(x, y, coef, B, C, T, zp, layout, s, g);
+    case 8: return launch_sosfilt<8, OutT>(x, y, coef, B, C, T, zp, layout, s, g);
   }
   set_error("csn_sosfilt_f32: n_sections must be in [1, 8], got %d", nsec);
   return CSN_EINVAL;
@@ -467,20 +502,13 @@ static int dispatch_nsec(int nsec, const float* x, void* y, const SosCoef& coef,
 
 using namespace csn;
 
-extern "C" int csn_sosfilt_f32(const float* x, void* y, const double* sos, int n_sections, int B, int C, int T,
-                               int zero_phase, int out_layout, int out_dtype, void* stream) {
-  CSN_REQUIRE(B >= 0 && C >= 0 && T >= 0, "csn_sosfilt_f32: negative dimension");
-  if (B == 0 || C == 0 || T == 0) return CSN_OK;  // empty batch: nothing to do (pointers may be null)
-  CSN_REQUIRE(x && y && sos, "csn_sosfilt_f32: null pointer");
-  CSN_REQUIRE(n_sections >= 1 && n_sections <= kMaxSec, "csn_sosfilt_f32: n_sections must be in [1, %d]", kMaxSec);
-  CSN_REQUIRE(out_layout >= CSN_LAYOUT_BCT && out_layout <= CSN_LAYOUT_TBC, "csn_sosfilt_f32: bad out_layout");
-  CSN_REQUIRE(out_dtype == CSN_F32 || out_dtype == CSN_BF16, "csn_sosfilt_f32: bad out_dtype");
-  SosCoef c{};
+static int make_coef(const double* sos, int n_sections, SosCoef& c, const char* who) {
+  CSN_REQUIRE(n_sections >= 1 && n_sections <= kMaxSec, "%s: n_sections must be in [1, %d]", who, kMaxSec);
   int nb2 = 0, na2 = 0;
   double scale = 1.0;
   for (int k = 0; k < n_sections; ++k) {
     const double* r = sos + 6 * k;
-    CSN_REQUIRE(r[3] != 0.0, "csn_sosfilt_f32: a0 == 0 in section %d", k);
+    CSN_REQUIRE(r[3] != 0.0, "%s: a0 == 0 in section %d", who, k);
     double b0 = r[0] / r[3], b1 = r[1] / r[3], b2 = r[2] / r[3], a1 = r[4] / r[3], a2 = r[5] / r[3];
     c.b0[k] = (float)b0; c.b1[k] = (float)b1; c.b2[k] = (float)b2; c.a1[k] = (float)a1; c.a2[k] = (float)a2;
     if (r[2] == 0.0) ++nb2;
@@ -496,8 +524,42 @@ extern "C" int csn_sosfilt_f32(const float* x, void* y, const double* sos, int n
   }
   int ntaps = 2 * n_sections + 1 - (nb2 < na2 ? nb2 : na2);
   c.padlen = 3 * ntaps;
+  return CSN_OK;
+}
+
+extern "C" int csn_sosfilt_f32(const float* x, void* y, const double* sos, int n_sections, int B, int C, int T,
+                               int zero_phase, int out_layout, int out_dtype, void* stream) {
+  CSN_REQUIRE(B >= 0 && C >= 0 && T >= 0, "csn_sosfilt_f32: negative dimension");
+  if (B == 0 || C == 0 || T == 0) return CSN_OK;  // empty batch: nothing to do (pointers may be null)
+  CSN_REQUIRE(x && y && sos, "csn_sosfilt_f32: null pointer");
+  CSN_REQUIRE(out_layout >= CSN_LAYOUT_BCT && out_layout <= CSN_LAYOUT_TBC, "csn_sosfilt_f32: bad out_layout");
+  CSN_REQUIRE(out_dtype == CSN_F32 || out_dtype == CSN_BF16, "csn_sosfilt_f32: bad out_dtype");
+  SosCoef c{};
+  if (int rc = make_coef(sos, n_sections, c, "csn_sosfilt_f32")) return rc;
   if (zero_phase) CSN_REQUIRE(T > c.padlen, "csn_sosfilt_f32: zero-phase needs T > padlen (%d), got T=%d", c.padlen, T);
   cudaStream_t s = as_stream(stream);
   if (out_dtype == CSN_F32) return dispatch_nsec<float>(n_sections, x, y, c, B, C, T, zero_phase, out_layout, s);
   return dispatch_nsec<__nv_bfloat16>(n_sections, x, y, c, B, C, T, zero_phase, out_layout, s);
+}
+
+extern "C" int csn_sosfilt_gather_f32(const float* src, const long long* idx, int n_trials, int C, int T_raw, int time_low,
+                                      int time_high, float mean, float std, void* y, const double* sos, int n_sections,
+                                      int B, int out_layout, int out_dtype, void* stream) {
+  CSN_REQUIRE(n_trials >= 1 && C >= 1 && T_raw >= 1 && B >= 0, "csn_sosfilt_gather_f32: bad sizes");
+  CSN_REQUIRE(time_low >= 0 && time_high > time_low && time_high <= T_raw,
+              "csn_sosfilt_gather_f32: need 0 <= time_low < time_high <= T_raw (got %d, %d, T_raw=%d)", time_low, time_high, T_raw);
+  CSN_REQUIRE(std != 0.f, "csn_sosfilt_gather_f32: std must be non-zero");
+  if (B == 0) return CSN_OK;
+  CSN_REQUIRE(src && idx && y && sos, "csn_sosfilt_gather_f32: null pointer");
+  CSN_REQUIRE(out_layout >= CSN_LAYOUT_BCT && out_layout <= CSN_LAYOUT_TBC, "csn_sosfilt_gather_f32: bad out_layout");
+  CSN_REQUIRE(out_dtype == CSN_F32 || out_dtype == CSN_BF16, "csn_sosfilt_gather_f32: bad out_dtype");
+  SosCoef c{};
+  if (int rc = make_coef(sos, n_sections, c, "csn_sosfilt_gather_f32")) return rc;
+  GatherSrc g{};
+  g.idx = idx; g.n_trials = n_trials; g.C = C; g.row_stride = T_raw; g.t_off = time_low;
+  g.mean = mean; g.inv_std = 1.f / std; g.norm = (mean != 0.f || std != 1.f) ? 1 : 0;
+  const int T = time_high - time_low;
+  cudaStream_t s = as_stream(stream);
+  if (out_dtype == CSN_F32) return dispatch_nsec<float>(n_sections, src, y, c, B, C, T, 0, out_layout, s, g);
+  return dispatch_nsec<__nv_bfloat16>(n_sections, src, y, c, B, C, T, 0, out_layout, s, g);
 }

@@ -107,6 +107,13 @@ class DeviceEEGDataset:
              self.time_high, float(mean), float(std), LAYOUT_BCT, _stream())
         return out_bct
 
+    def fused_filter_ok(self):
+        """Whether csn_sosfilt_gather_f32 serves this dataset's shape (else gather_into + sosfilt)."""
+        return self.C % 32 == 0 and self.T_raw % 4 == 0 and self.time_low % 4 == 0 and self.samples % 4 == 0
+
+    def norm_scalars(self):
+        return (self.mean, self.std) if self.apply_norm_with_stds_and_means else (0.0, 1.0)
+
     def batch(self, indices):
         """-> (eeg [B, C, T] float32 in the stored layout -- feed it to DistillTrainStep.step / Model.encode_trials --,
         labels [B] int64, image indices [B] int64), all on the GPU."""

@@ -65,6 +65,22 @@ def sosfilt(x, sos, zero_phase=False, out_layout="BCT", out_dtype=torch.float32,
     return y
 
 
+def sosfilt_gather(src_nct, idx, time_low, time_high, sos, mean=0.0, std=1.0, out_layout="TBC", out_dtype=torch.float32):
+    """Causal band-pass of the trials `idx` (device int64 [B], validated by the caller) of a resident [N, C, T_raw]
+    array, cropped to [time_low, time_high) and optionally normalised -- gather fused into the filter's loads."""
+    _chk(src_nct, torch.float32, "src")
+    N, Cc, T_raw = src_nct.shape
+    B, T = idx.numel(), time_high - time_low
+    sos = np.ascontiguousarray(np.asarray(sos, dtype=np.float64))
+    if sos.ndim != 2 or sos.shape[1] != 6:
+        raise _lib.CsnError("sos must have shape [n_sections, 6]")
+    shape = {"BCT": (B, Cc, T), "BTC": (B, T, Cc), "TBC": (T, B, Cc)}[out_layout]
+    y = torch.empty(shape, dtype=out_dtype, device=src_nct.device)
+    call("csn_sosfilt_gather_f32", _p(src_nct), _p(idx), N, Cc, T_raw, int(time_low), int(time_high), float(mean), float(std),
+         _p(y), sos.ctypes.data_as(C.POINTER(C.c_double)), sos.shape[0], B, _LAYOUTS[out_layout], _dt(out_dtype), _stream())
+    return y
+
+
 def btc_to_tbc(x, out_dtype=torch.float32):
     _chk(x, torch.float32, "x")
     B, T, Cc = x.shape

@@ -78,6 +78,7 @@ class DistillTrainStep:
         self._graph_tau = None
         self._static = None
         self._idx_ring = None      # step_from_dataset: pinned index slots + their device copy
+        self._ds_graphs = {}       # (dataset, tau, input slot) -> (graph, loss) of the resident-dataset step
         self._resident = {}        # (eeg ptr, teacher ptr) -> (eeg, teacher): buffers with their own captured graph
         self._resident_graphs = {}  # (eeg ptr, teacher ptr, tau) -> (graph, loss tensor)
         self._pool = None
@@ -122,12 +123,19 @@ class DistillTrainStep:
         return out
 
     # ------------------------------------------------------------------------------------------------
-    def _run(self, eeg_bct, teacher, tau_t):
+    def _run(self, eeg_bct, teacher, tau_t, gather=None):
+        """`gather` = (dataset, idx_dev): the batch is trials idx_dev of a resident dataset, fetched by the filter itself."""
         m = self.model
         cd = m.compute_dtype
-        B = eeg_bct.shape[0]
+        B = teacher.shape[0]
         with self._stage("filter"):
-            x_tbc = ops.sosfilt(eeg_bct, self.sos, zero_phase=self.zero_phase, out_layout="TBC", out_dtype=cd)
+            if gather is not None:
+                ds, idx_dev = gather
+                mean, std = ds.norm_scalars()
+                x_tbc = ops.sosfilt_gather(ds.eeg, idx_dev, ds.time_low, ds.time_high, self.sos, mean, std,
+                                           out_layout="TBC", out_dtype=cd)
+            else:
+                x_tbc = ops.sosfilt(eeg_bct, self.sos, zero_phase=self.zero_phase, out_layout="TBC", out_dtype=cd)
         layers = m.lstm.layer_weights()
         with self._stage("encoder_fwd"):
             h_last, saved = encoder_fwd(x_tbc, layers, cd, training=True)
@@ -177,31 +185,68 @@ class DistillTrainStep:
     def step_from_dataset(self, dataset, indices, teacher_feats, epoch=0):
         """One step on a batch of a GPU-RESIDENT dataset (dataset.DeviceEEGDataset): `indices` is a host int64 [B]
         (e.g. from dataset.epoch_batches), `teacher_feats` float32 [B, K] on the host (pinned) or the device.  The trials
-        are gathered on the device straight into the step's static input buffer, so only the indices and the image
-        features cross PCIe (8 B + 4 K bytes per trial instead of 4 C T) -- the replacement for DataLoader + `.to(device)`
+        are fetched on the device (by the band-pass kernel's own loads when the shape allows, else by the gather
+        kernel), so only the indices and the image features cross PCIe (8 B + 4 K bytes per trial instead of 4 C T) -- the replacement for DataLoader + `.to(device)`
         of LstmDistillFromDinoV2Train.py:358-363 when the .pth fits in HBM."""
         idx = dataset.check_indices(indices)
-        B = idx.numel()
-        if self._static is None:
-            dev = dataset.eeg.device
-            self._static = (torch.empty(B, dataset.C, dataset.samples, dtype=torch.float32, device=dev),
-                            torch.empty(B, teacher_feats.shape[1], dtype=torch.float32, device=dev))
-        se, st = self._static
-        if se.shape[0] != B:
-            raise _lib.CsnError("step_from_dataset: batch size changed (%d -> %d)" % (se.shape[0], B))
-        if self._idx_ring is None:  # pinned index slots: a slot is rewritten only after its copy has completed
+        B, K = idx.numel(), teacher_feats.shape[1]
+        dev = dataset.eeg.device
+        if self._idx_ring is None:
+            # pinned index slots (a slot is rewritten only after its copy has completed) and TWO device-side input
+            # slots (indices + image features), so the copies of step i run on a copy stream under step i - 1
             self._idx_ring = [(torch.empty(B, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(4)]
-            self._idx_dev = torch.empty(B, dtype=torch.int64, device=se.device)
+            self._ds_slots = [{"idx": torch.zeros(B, dtype=torch.int64, device=dev),
+                               "feats": torch.empty(B, K, dtype=torch.float32, device=dev),
+                               "ready": torch.cuda.Event(), "consumed": torch.cuda.Event()} for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
             self._idx_n = 0
-        h_idx, done = self._idx_ring[self._idx_n % len(self._idx_ring)]
+        if self._ds_slots[0]["idx"].numel() != B:
+            raise _lib.CsnError("step_from_dataset: batch size changed (%d -> %d)" % (self._ds_slots[0]["idx"].numel(), B))
+        n = self._idx_n
         self._idx_n += 1
+        h_idx, done = self._idx_ring[n % len(self._idx_ring)]
+        slot = self._ds_slots[n % 2]
         done.synchronize()
         h_idx.copy_(idx)
-        self._idx_dev.copy_(h_idx, non_blocking=True)
-        done.record()
-        dataset.gather_into(se, self._idx_dev)
-        st.copy_(teacher_feats, non_blocking=True)
-        return self.step(se, st, epoch)
+        cur = torch.cuda.current_stream()
+        on_host = not teacher_feats.is_cuda
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(slot["consumed"])  # the step that last read this slot has finished
+            slot["idx"].copy_(h_idx, non_blocking=True)
+            done.record(self._copy_stream)
+            if on_host:
+                slot["feats"].copy_(teacher_feats, non_blocking=True)
+            slot["ready"].record(self._copy_stream)
+        cur.wait_event(slot["ready"])
+        if not on_host:  # produced on the caller's stream: copy it there
+            slot["feats"].copy_(teacher_feats, non_blocking=True)
+        try:
+            if self.zero_phase or not dataset.fused_filter_ok():
+                # general shapes: gather kernel into the static input buffer, then the ordinary step
+                if self._static is None:
+                    self._static = (torch.empty(B, dataset.C, dataset.samples, dtype=torch.float32, device=dev),
+                                    torch.empty(B, K, dtype=torch.float32, device=dev))
+                se, st = self._static
+                dataset.gather_into(se, slot["idx"])
+                st.copy_(slot["feats"], non_blocking=True)
+                return self.step(se, st, epoch)
+            # the filter's loads do the gather: the batch itself is never materialised
+            tau_t = float(self.loss.teacher_temp_schedule[epoch])
+            self.step_count += 1
+            gather = (dataset, slot["idx"])
+            if not self.use_cuda_graph or self._stage_events is not None or not self._warm:
+                self._warm = True
+                return self._run(None, slot["feats"], tau_t, gather=gather)
+            gkey = (id(dataset), tau_t, n % 2)
+            hit = self._ds_graphs.get(gkey)
+            if hit is None:
+                if len(self._ds_graphs) >= 8:  # epochs change tau: drop the stale captures
+                    self._ds_graphs.clear()
+                hit = self._ds_graphs[gkey] = self._capture(None, slot["feats"], tau_t, gather=gather)
+            hit[0].replay()
+            return hit[1]
+        finally:
+            slot["consumed"].record(cur)
 
     # CUDA-graph path.  The ~30 launches of a step are captured once and replayed with one submission.  Everything
     # that varies between steps lives on the device: the inputs are copied into static buffers (`input_buffers()`
@@ -224,13 +269,13 @@ class DistillTrainStep:
             raise _lib.CsnError("register_inputs: buffers must be contiguous")
         self._resident[(eeg_bct.data_ptr(), teacher_feats.data_ptr())] = (eeg_bct, teacher_feats)
 
-    def _capture(self, eeg, teacher, tau_t):
+    def _capture(self, eeg, teacher, tau_t, gather=None):
         torch.cuda.current_stream().synchronize()
         if self._pool is None:
             self._pool = torch.cuda.graph_pool_handle()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, pool=self._pool):
-            out = self._run(eeg, teacher, tau_t)
+            out = self._run(eeg, teacher, tau_t, gather=gather)
         return g, out
 
     def _step_graphed(self, eeg_bct, teacher, tau_t):

@@ -194,6 +194,14 @@ int csn_kd_loss_fwd_bwd(const float* student, const float* teacher, const long l
  * [B, C, T] (CSN_LAYOUT_BCT, what csn_sosfilt_f32 consumes) or [B, T, C] (CSN_LAYOUT_BTC, the DataLoader layout). */
 int csn_gather_trials(const float* src, const long long* idx, float* out, int N, int C, int T_raw, int B, int time_low,
                       int time_high, float mean, float std, int out_layout, void* stream);
+/* The same gather FUSED into the causal band-pass: y = sosfilt(crop / normalise(src[idx[b]])) without writing the gathered
+ * batch to HBM (the filter's loads do the gather).  Serves the train step's shape only -- C % 32 == 0, T_raw, time_low and
+ * time_high - time_low multiples of 4, 16-byte aligned arrays, out_layout TBC (or fp32 BCT) -- and returns
+ * CSN_EUNSUPPORTED otherwise (callers then run csn_gather_trials + csn_sosfilt_f32).  Indices are NOT range-checked on
+ * the device (negative values wrap once): validate them on the host. */
+int csn_sosfilt_gather_f32(const float* src, const long long* idx, int n_trials, int C, int T_raw, int time_low,
+                           int time_high, float mean, float std, void* y, const double* sos, int n_sections, int B,
+                           int out_layout, int out_dtype, void* stream);
 
 /* ---- exact top-k retrieval -------------------------------------------------------
  * Replaces faiss.IndexFlatL2(d).add(gallery) / .search(query, k) as called by utils/Utilities.py:45-58 (evaluate) from

@@ -103,14 +103,41 @@ def test_cli_trains_from_a_pth_dataset(tmp_path, capsys):
 
 
 @pytest.mark.gpu
-def test_step_from_resident_dataset_equals_step_on_gathered_batch():
-    """DistillTrainStep.step_from_dataset (indices -> device gather into the static input buffer) must be the same
-    step as step(dataset.batch(indices)): identical loss and identical weights after two updates."""
+@pytest.mark.parametrize("norm", [False, True])
+def test_filter_with_fused_gather_is_bit_identical_to_gather_then_filter(norm):
+    import cerebralsignalnetworks_b200 as csn
+    from cerebralsignalnetworks_b200 import ops
+    from cerebralsignalnetworks_b200.dataset import DeviceEEGDataset
+    torch.manual_seed(4)
+    N, C, T_raw, lo, hi = 23, 64, 120, 8, 108
+    ds = DeviceEEGDataset.from_tensor(torch.randn(N, C, T_raw) * 3 + 1, time_low=lo, time_high=hi, apply_norm_with_stds_and_means=norm)
+    assert ds.fused_filter_ok()
+    sos = csn.EEGFilters(1000.0).sos(5.0, 95.0, 4)
+    idx = torch.tensor([22, 0, -1, 7, 7, 13, -23, 4, 19])
+    mean, std = ds.norm_scalars()
+    for dtype in (torch.float32, torch.bfloat16):
+        fused = ops.sosfilt_gather(ds.eeg, idx.cuda(), lo, hi, sos, mean, std, out_layout="TBC", out_dtype=dtype)
+        eeg, _, _ = ds.batch(idx)
+        two = ops.sosfilt(eeg, sos, out_layout="TBC", out_dtype=dtype)
+        assert fused.shape == two.shape == (hi - lo, idx.numel(), C)
+        assert torch.equal(fused, two)
+    # shapes the fused path does not serve are refused, not silently mis-read
+    bad = DeviceEEGDataset.from_tensor(torch.randn(5, 24, 40), time_low=4, time_high=36)
+    assert not bad.fused_filter_ok()
+    with pytest.raises(csn.CsnError):
+        ops.sosfilt_gather(bad.eeg, torch.tensor([0, 1]).cuda(), 4, 36, sos)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C", [16, 32])   # 16: gather kernel + ordinary step; 32: gather fused into the filter
+def test_step_from_resident_dataset_equals_step_on_gathered_batch(C):
+    """DistillTrainStep.step_from_dataset (indices -> device gather) must be the same step as
+    step(dataset.batch(indices)): same loss and same weights after four updates (eager, capture, replays)."""
     import copy
     import cerebralsignalnetworks_b200 as csn
     from cerebralsignalnetworks_b200.dataset import DeviceEEGDataset
     torch.manual_seed(2)
-    N, C, T_raw, lo, hi, B, H, D = 40, 16, 72, 4, 68, 8, 32, 24
+    N, T_raw, lo, hi, B, H, D = 40, 72, 4, 68, 8, 32, 24
     ds = DeviceEEGDataset.from_tensor(torch.randn(N, C, T_raw), time_low=lo, time_high=hi, apply_norm_with_stds_and_means=True)
     assert ds.samples == hi - lo and len(ds) == N
     sos = csn.EEGFilters(1000.0).sos(5.0, 95.0, 2)
