@@ -450,6 +450,7 @@ def main():
     # device, a step receives host INDICES + host image features, the batch is gathered on the device.  Reported NEXT
     # TO `e2e` (which stays the strict host-buffer path): this is the framework's answer to the PCIe bound above.
     ds_ms, n_ds = None, 8 * B
+    ds = None
     try:
         from cerebralsignalnetworks_b200.dataset import DeviceEEGDataset
         g = torch.Generator(device=dev).manual_seed(11 + rank)
@@ -458,7 +459,13 @@ def main():
         del raw
         order = torch.Generator().manual_seed(5)
         batches = list(ds.epoch_batches(B, shuffle=True, generator=order))
-
+    except Exception as exc:  # report, do not hide
+        print("resident-dataset leg: setup failed:", repr(exc), file=sys.stderr)
+        ds = None
+    ds_ok = torch.tensor([1.0 if ds is not None else 0.0], device=dev)
+    if world > 1:  # every rank runs the leg or none does (its steps contain the gradient exchange)
+        dist.all_reduce(ds_ok, op=dist.ReduceOp.MIN)
+    if float(ds_ok) > 0:
         def ds_loop(n):
             for i in range(n):
                 l = step.step_from_dataset(ds, batches[i % len(batches)], h_feat[i % 2], epoch=0)
@@ -474,10 +481,6 @@ def main():
         if world > 1:
             dist.all_reduce(ds_ms, op=dist.ReduceOp.MAX)
         ds_ms = float(ds_ms)
-    except Exception as exc:  # report, do not hide
-        print("resident-dataset leg failed:", repr(exc), file=sys.stderr)
-        if world > 1:
-            raise
 
     def finish():
         # Multi-rank teardown: every rank meets at a barrier, then leaves without tearing NCCL down.  (Destroying the
