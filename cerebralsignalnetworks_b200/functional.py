@@ -9,9 +9,10 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU
 
 
 # ---------------------------------------------------------------------------------------------------- encoder
-def encoder_fwd(x_tbc, layer_weights, compute_dtype, training=True):
+def encoder_fwd(x_tbc, layer_weights, compute_dtype, training=True, cast_last=True):
     """Stacked LSTM over time-major input.  layer_weights: list of (w_ih, w_hh, b_ih, b_hh).
-    Returns (h_last fp32 [B,H], saved) where saved is what encoder_bwd needs."""
+    Returns (h_last fp32 [B,H], saved) where saved is what encoder_bwd needs.  cast_last=False hands back the last
+    hidden state in the recurrence's own dtype (a view of h_seq) for consumers that convert on load."""
     saved = []
     inp = x_tbc
     for (w_ih, w_hh, b_ih, b_hh) in layer_weights:
@@ -19,6 +20,8 @@ def encoder_fwd(x_tbc, layer_weights, compute_dtype, training=True):
         saved.append((inp, h_seq, reserve, workspace))
         inp = h_seq
     h_last = inp[-1]
+    if not cast_last:
+        return h_last.contiguous(), saved
     if h_last.dtype != torch.float32:
         h_last = ops.cast(h_last.contiguous(), torch.float32)
     else:

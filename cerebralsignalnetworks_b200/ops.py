@@ -264,6 +264,31 @@ def dino_loss_fwd_bwd(student, teacher, center, student_temp, teacher_temp, mode
     return loss, d_student.view(student.shape), batch_center
 
 
+def head_dino_supported(B, I, K):
+    """Whether csn_head_dino_fwd_bwd serves this head shape (else: gemm_f32 + dino_loss_fwd_bwd + gemm_f32)."""
+    return bool(_lib.load().csn_head_dino_supported(int(B), int(I), int(K)))
+
+
+def head_dino_fwd_bwd(h_last, w, bias, act, teacher, center, student_temp, teacher_temp, batch_center, grad_scale=1.0):
+    """Projection head + single-view DINO loss, forward and backward in one kernel.  h_last [B, I] fp32 or bf16 (the
+    recurrence's own output), w [K, I], teacher [B, K], center [K]; batch_center [K] is ACCUMULATED into.
+    Returns (loss scalar tensor, d_hlast [B, I] fp32, d_pre [B, K] fp32)."""
+    _chk(h_last, None, "h_last"); _chk(w, torch.float32, "w"); _chk(teacher, torch.float32, "teacher")
+    _chk(center, torch.float32, "center"); _chk(batch_center, torch.float32, "batch_center")
+    B, I = h_last.shape
+    K = w.shape[0]
+    if w.shape[1] != I or tuple(teacher.shape) != (B, K) or center.numel() != K or batch_center.numel() != K:
+        raise _lib.CsnError("head_dino_fwd_bwd: shapes do not match (h %s, w %s, teacher %s, center %d)"
+                            % (tuple(h_last.shape), tuple(w.shape), tuple(teacher.shape), center.numel()))
+    loss = torch.empty((), dtype=torch.float32, device=w.device)
+    d_hlast = torch.empty((B, I), dtype=torch.float32, device=w.device)
+    d_pre = torch.empty((B, K), dtype=torch.float32, device=w.device)
+    call("csn_head_dino_fwd_bwd", _p(h_last), _dt(h_last.dtype), _p(w), _p(bias), int(act), _p(teacher), _p(center),
+         float(student_temp), float(teacher_temp), _p(loss), _p(d_hlast), _p(d_pre), _p(batch_center), B, I, K,
+         float(grad_scale), _stream())
+    return loss, d_hlast, d_pre
+
+
 def center_ema(center, batch_center, momentum, scale):
     call("csn_center_ema", _p(center), _p(batch_center), center.numel(), float(momentum), float(scale), _stream())
     return center

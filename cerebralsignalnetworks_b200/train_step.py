@@ -11,6 +11,8 @@ Every arithmetic stage is a libcsn_b200 kernel; torch provides memory, streams, 
 from __future__ import annotations
 
 import numpy as np
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -78,6 +80,8 @@ class DistillTrainStep:
         self._graph_tau = None
         self._static = None
         self._idx_ring = None      # step_from_dataset: pinned index slots + their device copy
+        self._side = None          # side stream of the fused head's weight-gradient GEMM
+        self.fused_head = os.environ.get("CSN_NO_FUSED_HEAD", "0") != "1"
         self._ds_graphs = {}       # (dataset, tau, input slot) -> (graph, loss) of the resident-dataset step
         self._resident = {}        # (eeg ptr, teacher ptr) -> (eeg, teacher): buffers with their own captured graph
         self._resident_graphs = {}  # (eeg ptr, teacher ptr, tau) -> (graph, loss tensor)
@@ -137,25 +141,46 @@ class DistillTrainStep:
             else:
                 x_tbc = ops.sosfilt(eeg_bct, self.sos, zero_phase=self.zero_phase, out_layout="TBC", out_dtype=cd)
         layers = m.lstm.layer_weights()
-        with self._stage("encoder_fwd"):
-            h_last, saved = encoder_fwd(x_tbc, layers, cd, training=True)
         act = ACT_RELU if m.include_top else ACT_NONE
+        K = m.output.weight.shape[0]
+        fused_head = (self.fused_head and self.center.numel() == K and m.output.bias is not None
+                      and m.output.weight.data_ptr() % 16 == 0
+                      and ops.head_dino_supported(B, m.output.weight.shape[1], K))
+        with self._stage("encoder_fwd"):
+            h_last, saved = encoder_fwd(x_tbc, layers, cd, training=True, cast_last=not fused_head)
+        side = None
         with self._stage("head_loss"):
-            emb, pre = linear_fwd(h_last, m.output.weight, m.output.bias, act)
             if self.peer is not None:  # peers are done with the previous gradients; zero the centre-sum tail
                 ops.dp_wait_done_zero(self.peer.flags, self.world, self._step_dev, self.batch_center)
             else:
                 self.flat_g[self.n_param:].zero_()
-            loss, d_emb, _ = ops.dino_loss_fwd_bwd(emb, teacher, self.center, self.loss.student_temp, tau_t,
-                                                   DINO_SINGLE, batch_center=self.batch_center)
-            d_hlast, _, _ = linear_bwd(h_last, m.output.weight, pre, d_emb, act, need_dx=True,
-                                       dw_out=self.grad_of(m.output.weight), db_out=self.grad_of(m.output.bias))
+            if fused_head:
+                # Linear + loss + d_h in ONE kernel; the head's weight gradient (needs only d_pre and h_T) leaves the
+                # critical path: it runs on a side stream next to the backward recurrence and is joined before Adam
+                loss, d_hlast, d_pre = ops.head_dino_fwd_bwd(h_last, m.output.weight, m.output.bias, act, teacher, self.center,
+                                                             self.loss.student_temp, tau_t, self.batch_center)
+                cur = torch.cuda.current_stream()
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=h_last.device)
+                side = self._side
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    h32 = h_last if h_last.dtype == torch.float32 else ops.cast(h_last, torch.float32)
+                    ops.gemm_f32(d_pre, h32, True, False, out=self.grad_of(m.output.weight), rowsum=self.grad_of(m.output.bias))
+            else:
+                emb, pre = linear_fwd(h_last, m.output.weight, m.output.bias, act)
+                loss, d_emb, _ = ops.dino_loss_fwd_bwd(emb, teacher, self.center, self.loss.student_temp, tau_t,
+                                                       DINO_SINGLE, batch_center=self.batch_center)
+                d_hlast, _, _ = linear_bwd(h_last, m.output.weight, pre, d_emb, act, need_dx=True,
+                                           dw_out=self.grad_of(m.output.weight), db_out=self.grad_of(m.output.bias))
         grads = [tuple(self.grad_of(w) for w in layer) for layer in layers]
         with self._stage("encoder_bwd"):
             encoder_bwd(d_hlast, layers, saved, grads, cd)
         if m.include_top:  # the DINO loss does not reach the class head: zero gradient
             self.grad_of(m.classifier.weight).zero_()
             self.grad_of(m.classifier.bias).zero_()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)  # the head's dW / db are in the gradient buffer
         if self.peer is not None:
             with self._stage("adam_center"):  # all-reduce + Adam + centre EMA in one kernel over peer memory
                 pe = self.peer

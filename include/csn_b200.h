@@ -187,6 +187,19 @@ int csn_cosine_loss_fwd_bwd(const float* student, const float* teacher, float* l
 int csn_kd_loss_fwd_bwd(const float* student, const float* teacher, const long long* label, float* loss, float* d_student,
                         int B, int K, float temperature, float c_kl, float c_sl1, float c_ce, float grad_scale, void* stream);
 
+/* ---- projection head + single-view DINO loss, forward and backward in one kernel ----------------------------------
+ * The chain `output = Linear(h_T)` -> DINOLoss.forward -> d_output -> d_h_T of LstmDistillFromDinoV2Train.py:365-375 for the
+ * narrow heads (K <= 1024 targets on an I <= 128-wide encoder; csn_head_dino_supported says whether a shape is served):
+ *   pre = W h + bias, emb = act(pre) (CSN_ACT_NONE / CSN_ACT_RELU); loss = mean_b CE(softmax((t - c) / tau_t), emb / tau_s)
+ *   d_pre [B,K] = dLoss/dpre * grad_scale, d_hlast [B,I] = d_pre W, batch_center [K] += sum_b teacher (caller zeroes it).
+ * h_last [B,I] in h_dtype (CSN_F32 / CSN_BF16: the recurrence's own output, no cast pass), W [K,I], bias [K] or NULL,
+ * teacher [B,K], center [K].  loss: device scalar (overwritten).  The weight gradient dW = d_pre^T h, db = sum_b d_pre is
+ * left to the caller (csn_gemm_f32_rowsum): it is off the critical path of the step. */
+int csn_head_dino_supported(int B, int I, int K);
+int csn_head_dino_fwd_bwd(const void* h_last, int h_dtype, const float* W, const float* bias, int act, const float* teacher,
+                          const float* center, float student_temp, float teacher_temp, float* loss, float* d_hlast,
+                          float* d_pre, float* batch_center, int B, int I, int K, float grad_scale, void* stream);
+
 /* ---- GPU-resident dataset batches ------------------------------------------------------
  * src [N, C, T_raw] fp32: the stacked "eeg" tensors of the .pth file ConvertToPth.py:170-201 writes.  For every b:
  * trial idx[b] (int64, negative counts from the end), samples [time_low, time_high), (x - mean) / std (pass 0 / 1 for no
