@@ -7,6 +7,6 @@ $CMD > gpurun_out/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1
 echo "launch list exit $?"
 $CMD > gpurun_out/plain2_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"lstm_(fwd|bwd)_tc_kernel|sosfilt_(stream|warp)|gemm_tc_kernel|dino_loss_staged_kernel" -s 30 -c 12 -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"lstm_(fwd|bwd)_tc_kernel|sosfilt_(stream|warp)|gemm_tc_kernel|dino_loss_staged_kernel|head_dino_kernel" -s 30 -c 12 -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "full capture exit $?"
 ls -la gpurun_out | grep ${TAG}
