@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(1024, 1) head_dino_kernel(const HeadParams p) 
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
     const int jc = j >> 2, jo = j & 3;
+#pragma unroll 8
     for (int kk = kb; kk < ke; ++kk) {
       const float w = Ws[kk * I + 4 * (jc ^ (kk & 7)) + jo];
 #pragma unroll
