@@ -52,6 +52,7 @@ SIGNATURES = {
     "csn_head_dino_supported": [_i, _i, _i],
     "csn_head_dino_fwd_bwd": [_vp, _i, _vp, _vp, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "csn_sosfilt_gather_f32": [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, C.POINTER(C.c_double), _i, _i, _i, _i, _vp],
+    "csn_select_crop_zscore": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "csn_gather_trials": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i, _vp],
     "csn_topk_workspace_bytes": [_i, _i, _i, C.POINTER(_sz)],
     "csn_topk_search": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],

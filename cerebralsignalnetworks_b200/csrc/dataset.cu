@@ -42,9 +42,54 @@ __global__ void __launch_bounds__(256) gather_trials_kernel(const float* __restr
   }
 }
 
+// Channel selection of EEGDataset.__getitem__ (utils/PerilsEEGDataset.py:554-565, `filter_channels`): keep the listed
+// channels, crop [t_low, t_low + T), and -- `apply_channel_wise_norm` -- z-score every (trial, channel) row over the
+// cropped window with the POPULATION standard deviation (normlizeEEG :454-461 runs on a numpy array there).  One warp
+// per output row; done ONCE when the dataset is uploaded, the result is the resident tensor the batches are drawn from.
+__global__ void __launch_bounds__(256) select_crop_zscore_kernel(const float* __restrict__ src, const int* __restrict__ channels,
+                                                                float* __restrict__ out, long long rows, int C, int T_raw,
+                                                                int n_sel, int t_low, int T, int zscore) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long n = row / n_sel;
+  const int s = (int)(row - n * n_sel);
+  const float* x = src + (size_t(n) * C + channels[s]) * T_raw + t_low;
+  float* y = out + size_t(row) * T;
+  float mean = 0.f, sd = 1.f;
+  if (zscore) {
+    float a = 0.f;
+    for (int t = lane; t < T; t += 32) a += x[t];
+    mean = warp_sum(a) / float(T);
+    float v = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float d = x[t] - mean;
+      v = fmaf(d, d, v);
+    }
+    sd = sqrtf(warp_sum(v) / float(T));
+  }
+  for (int t = lane; t < T; t += 32) y[t] = (x[t] - mean) / sd;
+}
+
 }  // namespace csn
 
 using namespace csn;
+
+extern "C" int csn_select_crop_zscore(const float* src, const int* channels, float* out, int N, int C, int T_raw, int n_sel,
+                                      int time_low, int time_high, int zscore, void* stream) {
+  CSN_REQUIRE(N >= 0 && C >= 1 && T_raw >= 1 && n_sel >= 1, "csn_select_crop_zscore: bad sizes");
+  CSN_REQUIRE(time_low >= 0 && time_high > time_low && time_high <= T_raw,
+              "csn_select_crop_zscore: need 0 <= time_low < time_high <= T_raw (got %d, %d, T_raw=%d)", time_low, time_high, T_raw);
+  if (N == 0) return CSN_OK;
+  CSN_REQUIRE(src && channels && out, "csn_select_crop_zscore: null pointer");
+  const long long rows = (long long)N * n_sel;
+  const long long blocks = ceil_div<long long>(rows, 8);
+  CSN_REQUIRE(blocks <= 2147483647LL, "csn_select_crop_zscore: grid too large");
+  select_crop_zscore_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, channels, out, rows, C, T_raw, n_sel, time_low,
+                                                                            time_high - time_low, zscore ? 1 : 0);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
 
 extern "C" int csn_gather_trials(const float* src, const long long* idx, float* out, int N, int C, int T_raw, int B,
                                  int time_low, int time_high, float mean, float std, int out_layout, void* stream) {

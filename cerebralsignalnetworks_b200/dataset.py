@@ -16,7 +16,8 @@ from .ops import _p, _stream, call
 
 
 class DeviceEEGDataset:
-    def __init__(self, loaded, time_low=20, time_high=480, apply_norm_with_stds_and_means=False, device="cuda"):
+    def __init__(self, loaded, time_low=20, time_high=480, apply_norm_with_stds_and_means=False, device="cuda",
+                 filter_channels=(), apply_channel_wise_norm=False):
         _lib.require_gpu()
         if isinstance(loaded, str):
             loaded = torch.load(loaded, map_location="cpu", weights_only=False)
@@ -42,6 +43,26 @@ class DeviceEEGDataset:
         self.N, self.C, self.T_raw = self.eeg.shape
         if not (0 <= self.time_low < self.time_high <= self.T_raw):
             raise _lib.CsnError("need 0 <= time_low < time_high <= %d" % self.T_raw)
+        if len(filter_channels) > 0:
+            self.select_channels(filter_channels, apply_channel_wise_norm)
+
+    def select_channels(self, filter_channels, apply_channel_wise_norm=False):
+        """The `filter_channels` branch of EEGDataset.__getitem__ (utils/PerilsEEGDataset.py:554-565), applied once to the
+        resident tensor: keep the listed channels (in the listed order), crop [time_low, time_high), and with
+        `apply_channel_wise_norm` z-score every (trial, channel) row over the cropped window (normlizeEEG :454-461,
+        population standard deviation).  Afterwards the dataset serves [B, len(filter_channels), T] batches; the
+        dataset-level mean / std stay those of the original trials, as in the reference."""
+        ch = [int(c) for c in filter_channels]
+        if not ch or min(ch) < 0 or max(ch) >= self.C:
+            raise IndexError("filter_channels must be a non-empty list of channel indices in [0, %d)" % self.C)
+        ch_dev = torch.tensor(ch, dtype=torch.int32, device=self.device)
+        out = torch.empty((self.N, len(ch), self.samples), dtype=torch.float32, device=self.device)
+        call("csn_select_crop_zscore", _p(self.eeg), _p(ch_dev), _p(out), self.N, self.C, self.T_raw, len(ch), self.time_low,
+             self.time_high, 1 if apply_channel_wise_norm else 0, _stream())
+        self.eeg, self.C, self.T_raw = out, len(ch), self.samples
+        self.time_low, self.time_high = 0, self.T_raw
+        self.filter_channels = ch
+        return self
 
     @classmethod
     def from_tensor(cls, eeg_nct, labels=None, image_index=None, time_low=20, time_high=480,

@@ -207,6 +207,12 @@ int csn_head_dino_fwd_bwd(const void* h_last, int h_dtype, const float* W, const
  * [B, C, T] (CSN_LAYOUT_BCT, what csn_sosfilt_f32 consumes) or [B, T, C] (CSN_LAYOUT_BTC, the DataLoader layout). */
 int csn_gather_trials(const float* src, const long long* idx, float* out, int N, int C, int T_raw, int B, int time_low,
                       int time_high, float mean, float std, int out_layout, void* stream);
+/* Channel selection of EEGDataset.__getitem__ (`filter_channels`, utils/PerilsEEGDataset.py:554-565), applied once at
+ * upload: out [N, n_sel, T] = src[n, channels[s], time_low : time_high]; zscore != 0 additionally normalises every
+ * (trial, channel) row over the cropped window with the population standard deviation (`apply_channel_wise_norm`,
+ * normlizeEEG :454-461).  channels: device int32 [n_sel], values in [0, C) (validated by the caller). */
+int csn_select_crop_zscore(const float* src, const int* channels, float* out, int N, int C, int T_raw, int n_sel,
+                           int time_low, int time_high, int zscore, void* stream);
 /* The same gather FUSED into the causal band-pass: y = sosfilt(crop / normalise(src[idx[b]])) without writing the gathered
  * batch to HBM (the filter's loads do the gather).  Serves the train step's shape only -- C % 32 == 0, T_raw, time_low and
  * time_high - time_low multiples of 4, 16-byte aligned arrays, out_layout TBC (or fp32 BCT) -- and returns

@@ -24,3 +24,20 @@ def item_transform(eeg_ct, time_low, time_high, mean=None, std=None):
     if mean is not None:
         eeg = (eeg - mean) / std              # :572-573
     return eeg
+
+
+def item_transform_channels(eeg_ct, time_low, time_high, filter_channels, channel_wise_norm=False, mean=None, std=None):
+    """:554-565 (`filter_channels` branch) -> [len(filter_channels), T] float32 (the branch transposes back): selected
+    channels of the cropped window, each optionally z-scored with numpy's population std (normlizeEEG :454-461)."""
+    import numpy as np
+    eeg = eeg_ct.float().t().cpu().numpy()
+    out = np.zeros((time_high - time_low, len(filter_channels)), dtype=eeg.dtype)
+    for k, ch in enumerate(filter_channels):
+        out[:, k] = eeg[time_low:time_high, ch]
+        if channel_wise_norm:
+            col = out[:, k]
+            out[:, k] = (col - col.mean()) / col.std()
+    res = torch.from_numpy(out).t()
+    if mean is not None:
+        res = (res - mean) / std
+    return res

@@ -280,6 +280,18 @@ def golden_dataset():
             items = [ds[i] for i in range(len(ds))]
             out[f"items_{tag}"] = np.stack([it[0].numpy() for it in items])   # [N, T, C]
             out[f"labels_{tag}"] = np.array([int(it[1]) for it in items])
+        # the `filter_channels` branch of __getitem__ (:554-565), with and without the per-channel z-score.  The flags are
+        # set AFTER construction: passing apply_channel_wise_norm to the constructor runs transformEEGDataToChannelWiseNorm
+        # (:463-510), a different (label-wise) transform that rewrites the stored trials.
+        sel = [4, 0, 2]
+        out["filter_channels"] = np.array(sel)
+        for tag, chn in (("chsel", False), ("chsel_norm", True)):
+            ds = mod.EEGDataset(pth, None, subset="train", time_low=lo, time_high=hi, imagesRoot=root,
+                                apply_norm_with_stds_and_means=False, inference_mode=False)
+            ds.isDataTransformed = False
+            ds.filter_channels = sel
+            ds.apply_channel_wise_norm = chn
+            out[f"items_{tag}"] = np.stack([ds[i][0].numpy() for i in range(len(ds))])   # [N, len(sel), T]
     np.savez(os.path.join(GOLD, "dataset.npz"), versions=str(VERS), **out)
 
 

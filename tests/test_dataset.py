@@ -32,6 +32,34 @@ def test_oracle_item_transform_matches_reference_dataset(gold):
         np.testing.assert_allclose(item_transform(it["eeg"], lo, hi, mean, std).numpy(), gold["items_norm"][i], rtol=1e-6, atol=1e-7)
 
 
+def test_oracle_channel_selection_matches_reference_dataset(gold):
+    from oracle.dataset import item_transform_channels
+    loaded = _loaded(gold)
+    lo, hi, sel = int(gold["time_low"]), int(gold["time_high"]), [int(c) for c in gold["filter_channels"]]
+    for i, it in enumerate(loaded["dataset"]):
+        np.testing.assert_array_equal(item_transform_channels(it["eeg"], lo, hi, sel).numpy(), gold["items_chsel"][i])
+        np.testing.assert_allclose(item_transform_channels(it["eeg"], lo, hi, sel, True).numpy(), gold["items_chsel_norm"][i],
+                                   rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chnorm", [False, True])
+def test_device_dataset_channel_selection_matches_reference_items(gold, chnorm):
+    from cerebralsignalnetworks_b200.dataset import DeviceEEGDataset
+    lo, hi, sel = int(gold["time_low"]), int(gold["time_high"]), [int(c) for c in gold["filter_channels"]]
+    ds = DeviceEEGDataset(_loaded(gold), time_low=lo, time_high=hi, filter_channels=sel, apply_channel_wise_norm=chnorm)
+    assert (ds.C, ds.samples, len(ds)) == (len(sel), hi - lo, 7)
+    assert ds.mean == pytest.approx(float(gold["mean_plain"]), rel=1e-12)   # scalars of the ORIGINAL trials
+    got = ds.batch([6, 1, -7])[0].cpu().numpy()                             # [B, len(sel), T], the reference's item layout
+    want = gold["items_chsel_norm" if chnorm else "items_chsel"][[6, 1, 0]]
+    if chnorm:
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)
+    else:
+        np.testing.assert_array_equal(got, want)
+    with pytest.raises(IndexError):
+        DeviceEEGDataset(_loaded(gold), time_low=lo, time_high=hi, filter_channels=[0, 6])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("norm", [False, True])
 def test_device_dataset_batches_match_reference_items(gold, norm):
