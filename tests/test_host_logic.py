@@ -131,3 +131,31 @@ def test_schedules_match_reference_goldens(golden, tmp_path):
     assert S.restart_from_checkpoint(path, run_variables=run, student=other) and run["epoch"] == 7
     assert torch.equal(other["mlp"].weight, net["mlp"].weight)
     assert S.restart_from_checkpoint(str(tmp_path / "missing.pth")) is False
+
+
+def test_resident_dataset_host_side_batching_and_index_checks():
+    """The host half of DeviceEEGDataset (no device needed): epoch batches with the DistributedSampler + drop_last split
+    of LstmDistillation.py:406-414, and the index validation step_from_dataset relies on (the device does not re-check)."""
+    import pytest
+    import torch
+    from cerebralsignalnetworks_b200.dataset import DeviceEEGDataset
+    ds = DeviceEEGDataset.__new__(DeviceEEGDataset)   # host logic only: no upload
+    ds.N = 22
+    full = list(ds.epoch_batches(4, shuffle=False))
+    assert len(full) == 5 and torch.equal(torch.cat(full), torch.arange(20))            # drop_last
+    assert len(list(ds.epoch_batches(4, shuffle=False, drop_last=False))) == 6
+    shares = [list(ds.epoch_batches(4, shuffle=False, rank=r, world=2)) for r in range(2)]
+    assert len(shares[0]) == len(shares[1]) == 2                                       # 22 // (4 * 2) global batches
+    for k in range(2):  # every global batch of 8 is split contiguously over the ranks, no trial twice
+        both = torch.cat([shares[0][k], shares[1][k]])
+        assert torch.equal(both, torch.arange(8 * k, 8 * k + 8))
+    a = list(ds.epoch_batches(4, generator=torch.Generator().manual_seed(1)))
+    b = list(ds.epoch_batches(4, generator=torch.Generator().manual_seed(1)))
+    assert all(torch.equal(x, y) for x, y in zip(a, b))                                # ranks agree given the same seed
+    assert len(set(torch.cat(a).tolist())) == 20
+    idx = ds.check_indices([0, 21, -22, 5])
+    assert idx.dtype == torch.int64 and idx.device.type == "cpu" and idx.tolist() == [0, 21, -22, 5]
+    from cerebralsignalnetworks_b200 import CsnError
+    for bad, exc in (([22], IndexError), ([-23], IndexError), ([[0, 1]], CsnError)):
+        with pytest.raises(exc):
+            ds.check_indices(bad)
