@@ -243,6 +243,67 @@ def golden_kd_losses():
     np.savez(os.path.join(GOLD, "kd_losses.npz"), versions=str(VERS), **out)
 
 
+class _FlatL2Stub:
+    """What the reference's evaluate() needs from faiss.IndexFlatL2 (utils/Utilities.py:45-58), served by the float64
+    exhaustive search of oracle/retrieval.py -- faiss itself is absent from the image."""
+
+    def __init__(self, d):
+        self.d, self.is_trained, self.ntotal = d, True, 0
+        self._g = np.zeros((0, d), np.float32)
+
+    def add(self, x):
+        self._g = np.concatenate([self._g, np.asarray(x, dtype=np.float32).reshape(-1, self.d)])
+        self.ntotal = len(self._g)
+
+    def search(self, q, k):
+        from .retrieval import flat_search
+        D, I = flat_search(self._g, np.asarray(q, dtype=np.float32), k)
+        return D.astype(np.float32), I
+
+
+def run_reference_evaluate(gallery, query, gallery_ids, query_ids, k, n_classes):
+    """The reference's OWN Utilities.evaluate (recall / precision bookkeeping, :60-160) on plain arrays; only the faiss
+    index is a stand-in.  Returns (Recall_Total, Precision_Total)."""
+    import contextlib
+    import io
+    import types
+    saved = sys.modules.get("faiss")
+    stub = types.ModuleType("faiss")
+    stub.IndexFlatL2 = _FlatL2Stub
+    sys.modules["faiss"] = stub
+    try:
+        util = import_reference("utils.Utilities")
+        util.faiss = stub
+        names = {i: f"class{i}" for i in range(n_classes)}
+        ds = types.SimpleNamespace(class_id_to_str=names, class_str_to_id={v: kk for kk, v in names.items()})
+        lab = lambda ids: [{"ClassId": int(i), "ClassName": names[int(i)]} for i in ids]
+        with contextlib.redirect_stdout(io.StringIO()):
+            r, p = util.evaluate(types.SimpleNamespace(topK=k), gallery, query, lab(gallery_ids), lab(query_ids), ds)
+        return float(r), float(p)
+    finally:
+        if saved is not None:
+            sys.modules["faiss"] = saved
+        else:
+            sys.modules.pop("faiss", None)
+
+
+def golden_retrieval():
+    """Recall / precision of the reference's own evaluate() (utils/Utilities.py:28-169) on two synthetic galleries."""
+    from .retrieval import flat_search
+    rng = np.random.default_rng(52)
+    out = {}
+    for i, (nb, nq, d, k, ncls) in enumerate([(120, 40, 16, 5, 6), (300, 75, 32, 3, 11)]):
+        centres = rng.standard_normal((ncls, d)).astype(np.float32) * (0.35, 0.25)[i]
+        g_ids, q_ids = rng.integers(0, ncls, nb), rng.integers(0, ncls, nq)
+        g = (centres[g_ids] + rng.standard_normal((nb, d))).astype(np.float32)
+        q = (centres[q_ids] + rng.standard_normal((nq, d))).astype(np.float32)
+        r, p = run_reference_evaluate(g, q, g_ids, q_ids, k, ncls)
+        _, I = flat_search(g, q, k)
+        out.update({f"gallery{i}": g, f"query{i}": q, f"gallery_ids{i}": g_ids, f"query_ids{i}": q_ids, f"k{i}": np.int64(k),
+                    f"I{i}": I, f"recall{i}": np.float64(r), f"precision{i}": np.float64(p)})
+    np.savez(os.path.join(GOLD, "retrieval_scores.npz"), versions=str(VERS), **out)
+
+
 def golden_dataset():
     """The reference's own EEGDataset (utils/PerilsEEGDataset.py) on a small synthetic .pth file in the schema of
     ConvertToPth.py:170-201: dataset-level mean / std and the EEG tensor of every item, with and without normalisation."""
@@ -302,6 +363,10 @@ def main():
         golden_dataset()
         print("dataset.npz written")
         return 0
+    if "--only-retrieval" in sys.argv:
+        golden_retrieval()
+        print("retrieval_scores.npz written")
+        return 0
     if "--only-kd-losses" in sys.argv:
         golden_kd_losses()
         print("kd_losses.npz written")
@@ -318,6 +383,7 @@ def main():
     golden_lstm_step()
     golden_alt_losses()
     golden_kd_losses()
+    golden_retrieval()
     golden_dataset()
     print("golden vectors written to", GOLD)
     for f in sorted(os.listdir(GOLD)):

@@ -49,6 +49,50 @@ def test_class_scores_follow_the_reference_loop():
             assert c1[cls][key] == v[key], (cls, key)
 
 
+import os
+
+GOLD_SCORES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "retrieval_scores.npz")
+
+
+def test_scoring_matches_the_reference_evaluate_numbers():
+    """Recall / precision produced by the reference's OWN Utilities.evaluate (utils/Utilities.py:28-169; only faiss was a
+    stand-in when the fixture was generated) against the oracle loop and the product's host-side class_scores."""
+    from cerebralsignalnetworks_b200.retrieval import class_scores
+    gold = np.load(GOLD_SCORES, allow_pickle=True)
+    for i in range(2):
+        k = int(gold[f"k{i}"])
+        D, I = flat_search(gold[f"gallery{i}"], gold[f"query{i}"], k)
+        assert np.array_equal(I, gold[f"I{i}"])
+        r0, p0, _ = evaluate_scores(I, gold[f"gallery_ids{i}"].tolist(), gold[f"query_ids{i}"].tolist(), k)
+        r1, p1, _ = class_scores(I, gold[f"gallery_ids{i}"], gold[f"query_ids{i}"])
+        for r, p in ((r0, p0), (r1, p1)):
+            assert r == pytest.approx(float(gold[f"recall{i}"]), abs=1e-9)
+            assert p == pytest.approx(float(gold[f"precision{i}"]), abs=1e-9)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_retrieval_score_fixture_regenerates_from_the_reference():
+    from oracle.make_golden import run_reference_evaluate
+    gold = np.load(GOLD_SCORES, allow_pickle=True)
+    i = 0
+    r, p = run_reference_evaluate(gold[f"gallery{i}"], gold[f"query{i}"], gold[f"gallery_ids{i}"], gold[f"query_ids{i}"],
+                                  int(gold[f"k{i}"]), int(gold[f"gallery_ids{i}"].max()) + 1)
+    assert r == pytest.approx(float(gold[f"recall{i}"]), abs=1e-9) and p == pytest.approx(float(gold[f"precision{i}"]), abs=1e-9)
+
+
+@pytest.mark.gpu
+def test_index_search_reproduces_the_reference_evaluate_numbers():
+    import cerebralsignalnetworks_b200 as csn
+    from cerebralsignalnetworks_b200.retrieval import class_scores
+    gold = np.load(GOLD_SCORES, allow_pickle=True)
+    for i in range(2):
+        index = csn.IndexFlatL2(gold[f"gallery{i}"].shape[1])
+        index.add(gold[f"gallery{i}"])
+        _, I = index.search(gold[f"query{i}"], int(gold[f"k{i}"]))
+        r, p, _ = class_scores(I, gold[f"gallery_ids{i}"], gold[f"query_ids{i}"])
+        assert r == pytest.approx(float(gold[f"recall{i}"]), abs=1e-9) and p == pytest.approx(float(gold[f"precision{i}"]), abs=1e-9)
+
+
 def _check_against_oracle(g, q, k, metric):
     import cerebralsignalnetworks_b200 as csn
     index = (csn.IndexFlatL2 if metric == "l2" else csn.IndexFlatIP)(g.shape[1])
