@@ -243,6 +243,38 @@ def golden_kd_losses():
     np.savez(os.path.join(GOLD, "kd_losses.npz"), versions=str(VERS), **out)
 
 
+def golden_model_analogues():
+    """`models.lstm.Model` is absent from the reference, but two scripts ship the class it was derived from:
+    LSTMDistillRetreival.LSTMModel (:85-110: nn.LSTM -> last timestep -> fc) and LSTMDistill.LSTMModel (:112-142: fc over
+    all timesteps, class head on the features, ReLU on the returned features).  Both start with `x.view(B, C, T)`; on a
+    SQUARE input (T == C) that view is the identity, so there their forward is exactly what oracle.distill.Model restates.
+    Inputs, weights, outputs and weight gradients of the reference's own classes on square inputs."""
+    import contextlib
+    import io
+    import warnings
+    out = {}
+    torch.manual_seed(53)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")   # Variable(volatile=...) of the 0.3-era code
+        ret = import_reference("LSTMDistillRetreival")
+        m = ret.LSTMModel(input_size=24, hidden_size=16, n_layers=2, out_features=12)
+        x = torch.randn(3, 24, 24)
+        y = m(x)
+        y.pow(2).sum().backward()
+        out.update({"ret_x": x.numpy(), "ret_y": y.detach().numpy(), "ret_hidden": np.int64(16), "ret_layers": np.int64(2)})
+        out.update({f"ret_w_{k}": v.detach().numpy() for k, v in m.state_dict().items()})
+        out.update({f"ret_g_{k}": p.grad.numpy() for k, p in m.named_parameters()})
+        dis = import_reference("LSTMDistill")
+        m2 = dis.LSTMModel(input_size=20, hidden_size=16, n_layers=1, out_features=10, number_of_classes=7)
+        x2 = torch.randn(4, 20, 20)
+        with contextlib.redirect_stdout(io.StringIO()):   # the forward prints tensor sizes
+            f2, c2 = m2(x2)
+        out.update({"dis_x": x2.numpy(), "dis_feat_last": f2[:, -1, :].detach().numpy(), "dis_cls_last": c2[:, -1, :].detach().numpy(),
+                    "dis_hidden": np.int64(16), "dis_layers": np.int64(1)})
+        out.update({f"dis_w_{k}": v.detach().numpy() for k, v in m2.state_dict().items()})
+    np.savez(os.path.join(GOLD, "model_analogues.npz"), versions=str(VERS), **out)
+
+
 class _FlatL2Stub:
     """What the reference's evaluate() needs from faiss.IndexFlatL2 (utils/Utilities.py:45-58), served by the float64
     exhaustive search of oracle/retrieval.py -- faiss itself is absent from the image."""
@@ -363,6 +395,10 @@ def main():
         golden_dataset()
         print("dataset.npz written")
         return 0
+    if "--only-model" in sys.argv:
+        golden_model_analogues()
+        print("model_analogues.npz written")
+        return 0
     if "--only-retrieval" in sys.argv:
         golden_retrieval()
         print("retrieval_scores.npz written")
@@ -384,6 +420,7 @@ def main():
     golden_alt_losses()
     golden_kd_losses()
     golden_retrieval()
+    golden_model_analogues()
     golden_dataset()
     print("golden vectors written to", GOLD)
     for f in sorted(os.listdir(GOLD)):

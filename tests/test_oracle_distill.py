@@ -155,3 +155,41 @@ def test_live_reference_dino_multicrop_and_head(pg):
     w2 = od.MultiCropWrapper(Back(), torch.nn.Identity())
     xs = [torch.randn(2, 4, 16), torch.randn(2, 4, 16), torch.randn(2, 4, 8)]
     assert torch.equal(w1(xs), w2(xs))
+
+
+def test_oracle_model_matches_the_reference_analogue_classes_on_square_inputs():
+    """models.lstm.Model itself is absent from the reference; the two LSTMModel classes it derives from are not
+    (LSTMDistillRetreival.py:85-110, LSTMDistill.py:112-142).  On square inputs their leading `x.view(B, C, T)` is the
+    identity, and the restated Model must reproduce their outputs and weight gradients (fixture generated by
+    oracle/make_golden.py from the reference's own classes)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle.distill import Model
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_analogues.npz"), allow_pickle=True)
+
+    def load(prefix, model):
+        sd = {}
+        for k in g.files:
+            if k.startswith(prefix + "_w_"):
+                name = k[len(prefix) + 3:].replace("fc.", "output.").replace("class_pred.", "classifier.")
+                sd[name] = torch.from_numpy(g[k])
+        model.load_state_dict(sd)
+
+    x = torch.from_numpy(g["ret_x"])
+    m = Model(x.shape[2], int(g["ret_hidden"]), int(g["ret_layers"]), g["ret_y"].shape[1], include_top=False)
+    load("ret", m)
+    y = m(x)
+    np.testing.assert_allclose(y.detach().numpy(), g["ret_y"], rtol=1e-5, atol=1e-6)
+    y.pow(2).sum().backward()
+    for name, p in m.named_parameters():
+        want = g["ret_g_" + name.replace("output.", "fc.")]
+        np.testing.assert_allclose(p.grad.numpy(), want, rtol=1e-4, atol=1e-6, err_msg=name)
+
+    x2 = torch.from_numpy(g["dis_x"])
+    m2 = Model(x2.shape[2], int(g["dis_hidden"]), int(g["dis_layers"]), g["dis_feat_last"].shape[1], include_top=True,
+               n_classes=g["dis_cls_last"].shape[1])
+    load("dis", m2)
+    feat, cls = m2(x2)
+    np.testing.assert_allclose(feat.detach().numpy(), g["dis_feat_last"], rtol=1e-5, atol=1e-6)   # ReLU'd features
+    np.testing.assert_allclose(cls.detach().numpy(), g["dis_cls_last"], rtol=1e-5, atol=1e-6)     # class head on pre-ReLU features
