@@ -27,6 +27,8 @@ if ROOT not in sys.path:
 
 CFG = dict(batch_per_gpu=256, channels=128, samples=440, hidden=128, layers=1, feat=384, fs=1000.0, band=(5.0, 95.0),
            order=4, lr=1e-3, seed=43, n_resident_batches=8)
+WORKLOAD = ("distill_step cfg2: 128ch x 440 samples, LSTM L1 H128, 384-d targets, fused 5-95 Hz band-pass, "
+            "DINO CE + centre EMA, Adam")
 METRIC = "eeg_trials_per_sec_distill_train_step"
 UNIT = "trials/s"
 
@@ -225,10 +227,14 @@ def make_inputs(torch, n_batches, B, C, T, K, seed, device):
 def cpu_reference_step_rate(batch, steps, warmup, threads=None):
     """The reference PyTorch path on the host cores: scipy sosfilt -> restated Model on torch.nn.LSTM ->
     DINOLoss -> backward -> Adam (oracle/distill.py).  Returns (trials/s, ms/step, cores)."""
+    cores = threads or os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all the host cores it can (set before torch's
+    # thread pools are created, and again through the torch API in case they already exist)
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cores)
     import torch
     from oracle.distill import DistillStepOracle, synthetic_batch
 
-    cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     o = DistillStepOracle(CFG["channels"], CFG["hidden"], CFG["layers"], CFG["feat"], include_top=False, nepochs=100,
                           lr=CFG["lr"], low_hz=CFG["band"][0], high_hz=CFG["band"][1], fs=CFG["fs"], order=CFG["order"],
@@ -247,11 +253,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # bounded sample of the 256-trial cfg2 step: the largest of 64/32/16 trials per step whose K steps fit ~2 minutes
-    # of host time (probed with one timed step each; CPU step time is linear in the batch)
-    budget_s = float(os.environ.get("CSN_REF_BUDGET_S", "120"))
+    # The cfg2 step itself (256 trials) when its K steps fit the host-time budget, else a bounded sample of it: the
+    # largest of 128/64/32/16 trials per step that does (probed with one timed step each; CPU step time is linear in
+    # the batch)
+    budget_s = float(os.environ.get("CSN_REF_BUDGET_S", "150"))
     batch = 16
-    for cand in (64, 32, 16):
+    for cand in (CFG["batch_per_gpu"], 128, 64, 32, 16):
         _, ms_probe, _ = cpu_reference_step_rate(cand, 1, 1)
         batch = cand
         if ms_probe * 1e-3 * (args.steps + min(args.warmup, 3)) <= budget_s:
@@ -261,8 +268,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "distill_step cfg2: 128ch x 440 samples, LSTM L1 H128, 384-d targets, 5-95 Hz band-pass, Adam",
-                   "batch_per_step": batch},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "batch_per_step": batch, "same_batch_as_gpu_arm": batch == CFG["batch_per_gpu"]},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{batch}-trial steps of the cfg2 workload (torch-CPU LSTM + scipy sosfilt + DINO loss + Adam)"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -509,13 +515,12 @@ def main():
     peak_tf = peaks["tflops_sustained"] or peaks["tflops"]
     filt_ms = stages.get("filter", 0.0)
     filt_gbs = work["filter_bytes"] / (filt_ms * 1e-3) / 1e9 if filt_ms > 0 else None
+    phys_filter_bytes = (4.0 + (2.0 if dtype == torch.bfloat16 else 4.0)) * C * T * B
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
-        "config": {"workload": "distill_step cfg2: 128ch x 440 samples, LSTM L1 H128 (bf16 tcgen05 recurrence), 384-d targets, "
-                               "fused 5-95 Hz band-pass, DINO CE + centre EMA, Adam",
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2_policy": f"rotating {NB} resident input batches ({NB * B * C * T * 4 / 1e6:.0f} MB) > 126 MB L2"},
         "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": B * C * T * 4 + B * K * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
@@ -534,6 +539,11 @@ def main():
                      "tensor_pipe_active_sm": ncu_tensor_pipe()},
         "roofline_filter": {"bound": "hbm", "kernel": "sosfilt_warp_kernel", "achieved": filt_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": (filt_gbs / peaks["hbm_gbs"]) if filt_gbs else None, "traffic": ncu_traffic(["sosfilt_warp_kernel"]),
+                            "algorithmic_bytes": work["filter_bytes"], "algorithmic_note": "SURVEY 8(d): 8*C*T per trial (fp32 in + fp32 out)",
+                            # the timed variant writes the encoder's bf16 [T,B,C] input: 4 + 2 bytes per sample really move
+                            "physical_bytes": phys_filter_bytes,
+                            "achieved_physical": (phys_filter_bytes / (filt_ms * 1e-3) / 1e9) if filt_ms > 0 else None,
+                            "frac_physical": (phys_filter_bytes / (filt_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if filt_ms > 0 else None,
                             "peak_source": peaks["source"]},
         "roofline_loss": {"bound": "hbm", "kernel": "dino_loss_staged_kernel (cfg3 shape: 6 student + 2 teacher views, 64 trials, K=65536)",
                           "achieved": loss_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -544,7 +554,7 @@ def main():
         "dp_exchange": step.dp_exchange,
         "loss": final_loss,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # (N > 1: the N = 1 line carries it; ranks must not idle behind a CPU loop)
         rate, ms, cores = cpu_reference_step_rate(16, 10, 3)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
                                 "sample": "10 steps of the cfg1 workload (batch 16, same model) on the host cores: torch-CPU LSTM + "

@@ -35,22 +35,24 @@ SIGNATURES = {
     "csn_l2norm_bwd": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "csn_weight_norm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "csn_weight_norm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
-    "csn_gemm_bf16_tc": [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp],
+    "csn_gemm_bf16_tc": [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp],
     "csn_lstm_layer_bytes": [_i, _i, _i, _i, _i, C.POINTER(_sz), C.POINTER(_sz)],
     "csn_lstm_layer_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "csn_lstm_layer_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "csn_lstm_set_cta_budget": [_i],
-    "csn_dino_loss_fwd_bwd": [_vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    "csn_loss_workspace_bytes": [_i, C.POINTER(_sz)],
+    "csn_dino_loss_fwd_bwd": [_vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp],
     "csn_center_ema": [_vp, _vp, _sz, _f, _f, _vp],
     "csn_adam_step": [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _i, _f, _vp],
     "csn_adam_step_graph": [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _vp, _vp, _f, _vp],
+    "csn_dp_last_timeout": [C.POINTER(_i)],
     "csn_dp_wait_done_zero": [_vp, _i, _vp, _vp, _sz, _vp],
     "csn_dp_adam_step_peer": [_vp, _vp, _vp, _sz, _vp, _vp, _i, _i, _vp, _sz, _f, _f, _vp, _vp, _f, _f, _f, _f, _f, _i, _f, _vp],
-    "csn_feature_dist_loss_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp],
-    "csn_cosine_loss_fwd_bwd": [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp],
-    "csn_kd_loss_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _f, _vp],
+    "csn_feature_dist_loss_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp],
+    "csn_cosine_loss_fwd_bwd": [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp],
+    "csn_kd_loss_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _f, _vp, _vp],
     "csn_head_dino_supported": [_i, _i, _i],
-    "csn_head_dino_fwd_bwd": [_vp, _i, _vp, _vp, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
+    "csn_head_dino_fwd_bwd": [_vp, _i, _vp, _vp, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp],
     "csn_sosfilt_gather_f32": [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, C.POINTER(C.c_double), _i, _i, _i, _i, _vp],
     "csn_select_crop_zscore": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "csn_gather_trials": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i, _vp],
@@ -58,6 +60,9 @@ SIGNATURES = {
     "csn_topk_search": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "csn_ema_update": [_vp, _vp, _sz, _f, _vp],
     "csn_clip_grad_segments": [_vp, _vp, _i, C.c_longlong, _vp, _f, _vp],
+}
+# bring-up / self-test hooks (include/csn_b200_debug.h): not part of the product ABI, bound for tests and scripts only
+DEBUG_SIGNATURES = {
     "csn_dbg_umma_tile": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "csn_dbg_lstm_profile_buffer": [_vp],
     "csn_dbg_umma_bench": [_vp, _i, _i, _i, _i, _i, _vp],
@@ -88,7 +93,7 @@ def load():
     lib.csn_last_error.argtypes = []
     lib.csn_launch_count.restype = C.c_ulonglong
     lib.csn_launch_count.argtypes = []
-    for name, argtypes in SIGNATURES.items():
+    for name, argtypes in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
         fn = getattr(lib, name)
         fn.restype = _i
         fn.argtypes = argtypes

@@ -97,20 +97,24 @@ def main(argv=None):
     if ds is None:
         steps = max(1, FLAGS.trials_per_epoch // FLAGS.batch_size)
     for epoch in range(FLAGS.num_epochs):
-        t0, losses = time.time(), []
+        # step() hands back the step's STATIC loss tensor when the step is a replayed CUDA graph (every replay overwrites
+        # it), so the epoch mean is accumulated on the device, step by step, not stacked from aliases afterwards
+        t0, loss_sum, n_steps = time.time(), torch.zeros((), device="cuda"), 0
         if ds is not None:
             order = torch.Generator().manual_seed(FLAGS.seed + epoch)  # same permutation on every rank
             for idx in ds.epoch_batches(per_rank, shuffle=True, generator=order, rank=rank, world=world):
                 eeg, _, img = ds.batch(idx)
-                losses.append(step.step(eeg, feats_table[img].contiguous(), epoch))
+                loss_sum += step.step(eeg, feats_table[img].contiguous(), epoch)
+                n_steps += 1
         for _ in range(steps if ds is None else 0):
             eeg = torch.randn(per_rank, FLAGS.input_size, FLAGS.samples, device="cuda", generator=gen)
             eeg += 0.5 * torch.sin(2 * torch.pi * 40.0 * t_axis)  # utils/PerilsEEGDataset.py:140-147
             feats = torch.randn(per_rank, FLAGS.output_size, device="cuda", generator=gen)
-            losses.append(step.step(eeg, feats, epoch))
+            loss_sum += step.step(eeg, feats, epoch)
+            n_steps += 1
         torch.cuda.synchronize()
         if rank == 0:
-            mean = float(torch.stack(losses).mean())
+            mean = float(loss_sum) / max(1, n_steps)
             dt = time.time() - t0
             print(f"EPOCH {epoch} train_loss: {mean:.6f} T: {loss.teacher_temp_schedule[epoch]:.4f} "
                   f"({steps * FLAGS.batch_size / dt:.0f} trials/s)", flush=True)

@@ -60,4 +60,40 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- deterministic cross-CTA sum ("the last CTA folds") -----------------------------------------------------------
+// Float atomics make a result depend on the order in which CTAs happen to retire; the reference's CPU reductions do
+// not.  Every CTA stores its partial into a caller-provided scratch block, takes a ticket, and the LAST CTA to arrive
+// adds the partials in CTA order (lane-strided, then a fixed shuffle tree): same inputs -> same bits, every run.
+// Scratch layout: 64-byte header (word 0 = ticket, zeroed by the host wrapper before the launch) + one float per CTA.
+constexpr size_t kDetHeader = 64;
+inline size_t det_scratch_bytes(size_t n_partials) { return kDetHeader + ((n_partials * 4 + 63) & ~size_t(63)); }
+
+// Call from ALL threads of a participating CTA (it synchronises the CTA).  `v` is the CTA's partial, read from the
+// first thread only.  `cta` / `n_cta` index the participants.  *out = sum (overwritten) by the last CTA.
+__device__ __forceinline__ void det_cta_sum(float v, void* scratch, unsigned cta, unsigned n_cta, float* out) {
+  __shared__ int s_det_last;
+  unsigned* ticket = reinterpret_cast<unsigned*>(scratch);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + kDetHeader);
+  const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  if (tid == 0) {
+    __stcg(part + cta, v);
+    __threadfence();
+    s_det_last = (atomicAdd(ticket, 1u) == n_cta - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_det_last || tid >= 32) return;
+  __threadfence();
+  float a = 0.f;
+  for (unsigned i = tid; i < n_cta; i += 32) a += __ldcg(part + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (tid == 0) {
+    *out = a;
+    *ticket = 0u;
+  }
+}
+
+// out[n] (+)= sum_m x[m, n], fixed summation order (defined in optim_elementwise.cu)
+int colsum_det(const float* x, float* out, int M, int N, int ldx, int accumulate, cudaStream_t s);
+
 }  // namespace csn

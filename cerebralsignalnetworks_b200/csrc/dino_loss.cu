@@ -28,6 +28,7 @@ struct LossParams {
   float* loss;
   float* d_student;
   float* batch_center;
+  void* ws;         // deterministic loss fold: ticket + one partial per participating CTA (common.cuh)
   int center_rows;  // 1 or B
   int Vs, Vt, B, K, Kc;
   int mode;
@@ -176,14 +177,8 @@ __global__ void __launch_bounds__(kLossThreads) dino_loss_kernel(const LossParam
     }
   }
 
-  // ---- centre statistics ----
-  if (p.mode == CSN_DINO_MULTICROP_REF) {
-    store_row(p.batch_center + size_t(b) * p.K, bc);
-  } else {
-#pragma unroll
-    for (int i = 0; i < EPT; ++i)
-      if (elem(i) < p.Kc) atomicAdd(p.batch_center + k0 + elem(i), bc[i]);
-  }
+  // ---- centre statistics (shared-centre modes: a fixed-order column sum over the teacher follows the kernel) ----
+  if (p.mode == CSN_DINO_MULTICROP_REF) store_row(p.batch_center + size_t(b) * p.K, bc);
 
   // ---- student rows ----
   float loss_acc = 0.f;
@@ -220,8 +215,8 @@ __global__ void __launch_bounds__(kLossThreads) dino_loss_kernel(const LossParam
       u[i] = p.grad_coef * (W * __expf(u[i] - s.m) * inv_z - (w0 * q[0][i] + w1 * q[1][i]));
     store_row(gout, u);
   }
-  if (crank == 0 && tid == 0) atomicAdd(p.loss, loss_acc);
   if (cs > 1) cluster.sync();  // peers may still be reading our mailboxes
+  if (crank == 0) det_cta_sum(loss_acc, p.ws, (unsigned)b, (unsigned)p.B, p.loss);
 }
 
 
@@ -288,12 +283,6 @@ __device__ __forceinline__ float lg2_(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// 16-byte vector reduction into global memory: one L2 atomic transaction instead of four (shared-centre modes: the
-// column sums of B rows meet in the same K floats)
-__device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 constexpr float kNegBig = -1.0e30f;   // padding logit: never the maximum, ex2(kNegBig - m) == 0, 0 * kNegBig == -0
@@ -486,15 +475,8 @@ __global__ void __launch_bounds__(kLossThreads, 2) dino_loss_staged_kernel(const
     }
   }
 
-  // ---- centre statistics ----
-  if (p.mode == CSN_DINO_MULTICROP_REF) {
-    store_row(p.batch_center + size_t(b) * p.K, bc);
-  } else {
-#pragma unroll
-    for (int it = 0; it < NITER; ++it)
-      if (in_range(it))
-        red_add_f4(p.batch_center + k0 + (it * kLossThreads + tid) * 4, bc[it * 4], bc[it * 4 + 1], bc[it * 4 + 2], bc[it * 4 + 3]);
-  }
+  // ---- centre statistics (shared-centre modes: a fixed-order column sum over the teacher follows the kernel) ----
+  if (p.mode == CSN_DINO_MULTICROP_REF) store_row(p.batch_center + size_t(b) * p.K, bc);
 
   // ---- student rows ----
   float loss_acc = 0.f;
@@ -544,8 +526,8 @@ __global__ void __launch_bounds__(kLossThreads, 2) dino_loss_staged_kernel(const
     for (int i = 0; i < EPT; ++i) e[i] = p.grad_coef * fmaf(e[i], A, -Qv(i));
     store_row(p.d_student + (size_t(v) * p.B + b) * p.K, e);
   }
-  if (crank == 0 && tid == 0) atomicAdd(p.loss, loss_acc);
   if (first_push) cluster_wait_();  // (no rows at all: still pair the arrive)
+  if (crank == 0) det_cta_sum(loss_acc, p.ws, (unsigned)b, (unsigned)p.B, p.loss);
   // No closing cluster barrier: a CTA gets here only after the LAST round's cs packets have landed in its mailbox, i.e.
   // after every peer has issued its last push to it, and it never reads remote memory -- nobody can still touch the
   // shared memory of a CTA that exits.  (A release-arrive here made every CTA wait for its gradient stores to drain.)
@@ -600,7 +582,6 @@ __global__ void __launch_bounds__(kRowWarps * 32) dino_loss_rowwarp_kernel(const
   const bool row_ok = b < p.B;
   const int K = p.K;
   __shared__ float loss_part[kRowWarps];
-  extern __shared__ float bc_s[];  // [kRowWarps][K] (shared-centre modes only)
   const float ts = p.inv_tau_t * kLog2e, ss = p.inv_tau_s * kLog2e;
   float loss_acc = 0.f;
   float bc[EPT];
@@ -690,35 +671,19 @@ __global__ void __launch_bounds__(kRowWarps * 32) dino_loss_rowwarp_kernel(const
       }
     }
   }
-  // ---- CTA-level folds: loss (one atomic per CTA) and shared-centre statistics (one atomic per column per CTA) ----
+  // ---- loss: CTA fold in warp order, then the deterministic cross-CTA fold (the shared-centre column sums are a
+  //      fixed-order pass over the teacher after the kernel) ----
   if (lane == 0) loss_part[warp] = loss_acc;
-  if (p.mode != CSN_DINO_MULTICROP_REF) {
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) {
-      const int k = lane + 32 * i;
-      if (k < K) bc_s[warp * K + k] = bc[i];  // zero for rows past the batch
-    }
-  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
+  float t = 0.f;
+  if (threadIdx.x == 0)
     for (int w = 0; w < kRowWarps; ++w) t += loss_part[w];
-    atomicAdd(p.loss, t);
-  }
-  if (p.mode != CSN_DINO_MULTICROP_REF) {
-    for (int k = threadIdx.x; k < K; k += kRowWarps * 32) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kRowWarps; ++w) t += bc_s[w * K + k];
-      atomicAdd(p.batch_center + k, t);
-    }
-  }
+  det_cta_sum(t, p.ws, blockIdx.x, gridDim.x, p.loss);
 }
 
 template <int EPT>
 static int launch_loss_rowwarp(const LossParams& p, cudaStream_t s) {
-  const size_t smem = (p.mode != CSN_DINO_MULTICROP_REF) ? size_t(kRowWarps) * p.K * 4 : 0;
-  dino_loss_rowwarp_kernel<EPT><<<ceil_div(p.B, kRowWarps), kRowWarps * 32, smem, s>>>(p);
+  dino_loss_rowwarp_kernel<EPT><<<ceil_div(p.B, kRowWarps), kRowWarps * 32, 0, s>>>(p);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
@@ -755,15 +720,16 @@ using namespace csn;
 extern "C" int csn_dino_loss_fwd_bwd(const float* student, const float* teacher, const float* center, int center_rows,
                                      float student_temp, float teacher_temp, float* loss, float* d_student,
                                      float* batch_center, int Vs, int Vt, int B, int K, int mode, float grad_scale,
-                                     void* stream) {
-  CSN_REQUIRE(student && teacher && center && loss && d_student && batch_center, "csn_dino_loss_fwd_bwd: null pointer");
+                                     void* workspace, void* stream) {
+  CSN_REQUIRE(student && teacher && center && loss && d_student && workspace, "csn_dino_loss_fwd_bwd: null pointer");
+  CSN_REQUIRE(batch_center || mode != CSN_DINO_MULTICROP_REF, "csn_dino_loss_fwd_bwd: MULTICROP_REF needs batch_center");
   CSN_REQUIRE(Vs >= 1 && Vs <= kMaxVs && Vt >= 1 && Vt <= kMaxVt, "csn_dino_loss_fwd_bwd: need 1<=Vs<=%d, 1<=Vt<=%d", kMaxVs, kMaxVt);
   CSN_REQUIRE(B >= 1 && K >= 1 && B <= 65535, "csn_dino_loss_fwd_bwd: bad B/K");
   CSN_REQUIRE(center_rows == 1 || center_rows == B, "csn_dino_loss_fwd_bwd: center_rows must be 1 or B");
   CSN_REQUIRE(student_temp > 0.f && teacher_temp != 0.f, "csn_dino_loss_fwd_bwd: bad temperature");
   LossParams p{};
   p.student = student; p.teacher = teacher; p.center = center; p.loss = loss; p.d_student = d_student;
-  p.batch_center = batch_center; p.center_rows = center_rows;
+  p.batch_center = batch_center; p.center_rows = center_rows; p.ws = workspace;
   p.Vs = Vs; p.Vt = Vt; p.B = B; p.K = K; p.mode = mode;
   p.inv_tau_s = 1.f / student_temp; p.inv_tau_t = 1.f / teacher_temp;
   int n_terms = 0;
@@ -792,15 +758,21 @@ extern "C" int csn_dino_loss_fwd_bwd(const float* student, const float* teacher,
   p.grad_coef = p.coef * p.inv_tau_s * grad_scale;
 
   cudaStream_t s = as_stream(stream);
-  CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  CSN_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned), s));  // arrival ticket of the loss fold
+  // shared-centre modes: batch_center[K] += sum over (view, row) of the teacher, in a fixed order (runs after the loss)
+  auto center_sums = [&]() -> int {
+    if (mode == CSN_DINO_MULTICROP_REF || !batch_center) return CSN_OK;
+    return colsum_det(teacher, batch_center, Vt * B, K, K, 1, s);
+  };
 
   static const bool no_rowwarp = [] { const char* e = getenv("CSN_LOSS_NO_ROWWARP"); return e && e[0] == '1'; }();
   if (K <= 1024 && !no_rowwarp) {  // narrow heads: one warp per batch row
     p.Kc = K;
-    if (K <= 128) return launch_loss_rowwarp<4>(p, s);
-    if (K <= 256) return launch_loss_rowwarp<8>(p, s);
-    if (K <= 512) return launch_loss_rowwarp<16>(p, s);
-    return launch_loss_rowwarp<32>(p, s);
+    if (K <= 128) CSN_TRY(launch_loss_rowwarp<4>(p, s));
+    else if (K <= 256) CSN_TRY(launch_loss_rowwarp<8>(p, s));
+    else if (K <= 512) CSN_TRY(launch_loss_rowwarp<16>(p, s));
+    else CSN_TRY(launch_loss_rowwarp<32>(p, s));
+    return center_sums();
   }
 
   const bool aligned = ((reinterpret_cast<uintptr_t>(student) | reinterpret_cast<uintptr_t>(teacher) |
@@ -834,7 +806,7 @@ extern "C" int csn_dino_loss_fwd_bwd(const float* student, const float* teacher,
     if (S >= 1) {
       r = all_same ? dispatch_loss_staged<true>(per_thread, p, cs, S, s) : dispatch_loss_staged<false>(per_thread, p, cs, S, s);
       if (r == CSN_OK) count_launches(1);
-      return r;
+      return r == CSN_OK ? center_sums() : r;
     }
   }
   if (vec == 4) {
@@ -849,7 +821,13 @@ extern "C" int csn_dino_loss_fwd_bwd(const float* student, const float* teacher,
     else r = launch_loss<1, 8>(p, cs, s);
   }
   if (r == CSN_OK) count_launches(1);
-  return r;
+  return r == CSN_OK ? center_sums() : r;
+}
+
+extern "C" int csn_loss_workspace_bytes(int rows, size_t* bytes) {
+  CSN_REQUIRE(rows >= 1 && bytes, "csn_loss_workspace_bytes: bad arguments");
+  *bytes = det_scratch_bytes(size_t(rows));
+  return CSN_OK;
 }
 
 extern "C" int csn_center_ema(float* center, const float* batch_center, size_t n, float momentum, float scale,

@@ -24,23 +24,23 @@ __device__ __forceinline__ float ex2f_(float x) {
 }
 constexpr float kL2e = 1.4426950408889634f;
 
-// block-level fold of one float per warp into one atomicAdd
-__device__ __forceinline__ void block_atomic_sum(float v, float* dst, float* scratch) {
+// block-level fold of one float per warp (warp order), then the deterministic cross-CTA fold into *dst (common.cuh)
+__device__ __forceinline__ void block_det_sum(float v, float* dst, float* scratch, void* ws) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) scratch[warp] = v;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
+  float t = 0.f;
+  if (threadIdx.x == 0)
     for (int w = 0; w < kLossWarps; ++w) t += scratch[w];
-    atomicAdd(dst, t);
-  }
+  det_cta_sum(t, ws, blockIdx.x, gridDim.x, dst);
 }
 
 template <int EPT>
 __global__ void __launch_bounds__(kLossWarps * 32) feature_dist_loss_kernel(
     const float* __restrict__ student, const float* __restrict__ teacher, const float* __restrict__ pred,
     const long long* __restrict__ label, float* __restrict__ loss, float* __restrict__ d_student,
-    float* __restrict__ d_pred, int B, int K, int n_classes, float inv_T, float alpha, float beta, float grad_scale) {
+    float* __restrict__ d_pred, int B, int K, int n_classes, float inv_T, float alpha, float beta, float grad_scale,
+    void* __restrict__ ws) {
   __shared__ float scratch[kLossWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * kLossWarps + warp;
@@ -110,14 +110,15 @@ __global__ void __launch_bounds__(kLossWarps * 32) feature_dist_loss_kernel(
   }
   float lane_part = term1_lane + (lane == 0 ? term2_row : 0.f);
   lane_part = warp_sum(lane_part);
-  block_atomic_sum(lane_part, loss, scratch);
+  block_det_sum(lane_part, loss, scratch, ws);
 }
 
 template <int EPT>
 __global__ void __launch_bounds__(kLossWarps * 32) cosine_loss_kernel(const float* __restrict__ student,
                                                                     const float* __restrict__ teacher,
                                                                     float* __restrict__ loss, float* __restrict__ d_student,
-                                                                    int B, int K, float eps, float grad_scale) {
+                                                                    int B, int K, float eps, float grad_scale,
+                                                                    void* __restrict__ ws) {
   __shared__ float scratch[kLossWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * kLossWarps + warp;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) cosine_loss_kernel(const floa
     }
   }
   contrib = warp_sum(contrib);
-  block_atomic_sum(contrib, loss, scratch);
+  block_det_sum(contrib, loss, scratch, ws);
 }
 
 // loss = c_kl * sum_b KL(q_b || p_b) + c_sl1 * sum_{b,k} smooth_l1(s - t) + c_ce * sum_b CE(s_b, label_b)
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(kLossWarps * 32) kd_loss_kernel(const float* _
                                                                 const float* __restrict__ teacher,
                                                                 const long long* __restrict__ label, float* __restrict__ loss,
                                                                 float* __restrict__ d_student, int B, int K, float inv_T,
-                                                                float c_kl, float c_sl1, float c_ce, float grad_scale) {
+                                                                float c_kl, float c_sl1, float c_ce, float grad_scale,
+                                                                void* __restrict__ ws) {
   __shared__ float scratch[kLossWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * kLossWarps + warp;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) kd_loss_kernel(const float* _
     contrib = c_kl * kl + c_sl1 * sl1 + c_ce * ce;
   }
   contrib = warp_sum(contrib);
-  block_atomic_sum(contrib, loss, scratch);
+  block_det_sum(contrib, loss, scratch, ws);
 }
 
 }  // namespace csn
@@ -229,16 +231,16 @@ using namespace csn;
 extern "C" int csn_feature_dist_loss_fwd_bwd(const float* student, const float* teacher, const float* pred,
                                              const long long* label, float* loss, float* d_student, float* d_pred, int B,
                                              int K, int n_classes, float temperature, float alpha, float beta,
-                                             float grad_scale, void* stream) {
-  CSN_REQUIRE(student && teacher && loss && d_student, "csn_feature_dist_loss_fwd_bwd: null pointer");
+                                             float grad_scale, void* workspace, void* stream) {
+  CSN_REQUIRE(student && teacher && loss && d_student && workspace, "csn_feature_dist_loss_fwd_bwd: null pointer");
   CSN_REQUIRE(B >= 1 && K >= 1 && K <= 1024, "csn_feature_dist_loss_fwd_bwd: need B >= 1 and 1 <= K <= 1024 (got B=%d K=%d)", B, K);
   CSN_REQUIRE(temperature != 0.f, "csn_feature_dist_loss_fwd_bwd: temperature must be non-zero");
   CSN_REQUIRE(!pred || (label && d_pred && n_classes >= 1), "csn_feature_dist_loss_fwd_bwd: pred needs label, d_pred and n_classes");
   cudaStream_t s = as_stream(stream);
-  CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  CSN_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned), s));  // arrival ticket of the loss fold
   const int blocks = ceil_div(B, kLossWarps);
 #define CSN_FD(E) feature_dist_loss_kernel<E><<<blocks, kLossWarps * 32, 0, s>>>(student, teacher, pred, label, loss, d_student, \
-                                                                                 d_pred, B, K, n_classes, 1.f / temperature, alpha, beta, grad_scale)
+                                                                                 d_pred, B, K, n_classes, 1.f / temperature, alpha, beta, grad_scale, workspace)
   if (K <= 128) CSN_FD(4);
   else if (K <= 256) CSN_FD(8);
   else if (K <= 512) CSN_FD(16);
@@ -249,13 +251,13 @@ extern "C" int csn_feature_dist_loss_fwd_bwd(const float* student, const float* 
 }
 
 extern "C" int csn_cosine_loss_fwd_bwd(const float* student, const float* teacher, float* loss, float* d_student, int B, int K,
-                                       float eps, float grad_scale, void* stream) {
-  CSN_REQUIRE(student && teacher && loss && d_student, "csn_cosine_loss_fwd_bwd: null pointer");
+                                       float eps, float grad_scale, void* workspace, void* stream) {
+  CSN_REQUIRE(student && teacher && loss && d_student && workspace, "csn_cosine_loss_fwd_bwd: null pointer");
   CSN_REQUIRE(B >= 1 && K >= 1 && K <= 1024, "csn_cosine_loss_fwd_bwd: need B >= 1 and 1 <= K <= 1024 (got B=%d K=%d)", B, K);
   cudaStream_t s = as_stream(stream);
-  CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  CSN_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned), s));  // arrival ticket of the loss fold
   const int blocks = ceil_div(B, kLossWarps);
-#define CSN_CL(E) cosine_loss_kernel<E><<<blocks, kLossWarps * 32, 0, s>>>(student, teacher, loss, d_student, B, K, eps, grad_scale)
+#define CSN_CL(E) cosine_loss_kernel<E><<<blocks, kLossWarps * 32, 0, s>>>(student, teacher, loss, d_student, B, K, eps, grad_scale, workspace)
   if (K <= 128) CSN_CL(4);
   else if (K <= 256) CSN_CL(8);
   else if (K <= 512) CSN_CL(16);
@@ -267,16 +269,16 @@ extern "C" int csn_cosine_loss_fwd_bwd(const float* student, const float* teache
 
 extern "C" int csn_kd_loss_fwd_bwd(const float* student, const float* teacher, const long long* label, float* loss,
                                    float* d_student, int B, int K, float temperature, float c_kl, float c_sl1, float c_ce,
-                                   float grad_scale, void* stream) {
-  CSN_REQUIRE(student && teacher && loss && d_student, "csn_kd_loss_fwd_bwd: null pointer");
+                                   float grad_scale, void* workspace, void* stream) {
+  CSN_REQUIRE(student && teacher && loss && d_student && workspace, "csn_kd_loss_fwd_bwd: null pointer");
   CSN_REQUIRE(B >= 1 && K >= 1 && K <= 1024, "csn_kd_loss_fwd_bwd: need B >= 1 and 1 <= K <= 1024 (got B=%d K=%d)", B, K);
   CSN_REQUIRE(temperature != 0.f, "csn_kd_loss_fwd_bwd: temperature must be non-zero");
   CSN_REQUIRE(c_ce == 0.f || label, "csn_kd_loss_fwd_bwd: the cross-entropy term needs labels");
   cudaStream_t s = as_stream(stream);
-  CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  CSN_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned), s));  // arrival ticket of the loss fold
   const int blocks = ceil_div(B, kLossWarps);
 #define CSN_KD(E) kd_loss_kernel<E><<<blocks, kLossWarps * 32, 0, s>>>(student, teacher, label, loss, d_student, B, K, \
-                                                                       1.f / temperature, c_kl, c_sl1, c_ce, grad_scale)
+                                                                       1.f / temperature, c_kl, c_sl1, c_ce, grad_scale, workspace)
   if (K <= 128) CSN_KD(4);
   else if (K <= 256) CSN_KD(8);
   else if (K <= 512) CSN_KD(16);

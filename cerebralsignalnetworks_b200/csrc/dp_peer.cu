@@ -38,24 +38,61 @@ __device__ __forceinline__ float ld_peer_f(const float* p) {
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
-// spin until *flag >= target; a peer that never arrives (crashed rank) traps after ~10 s instead of hanging the GPU
-__device__ __forceinline__ void wait_flag_ge(const unsigned* flag, unsigned target) {
+// Watchdog of the flag waits.  A peer that never arrives (crashed rank) must not hang the GPU for ever, but ranks may
+// legitimately drift apart by minutes between steps (a rank-0-only checkpoint or evaluation, a slow torch.save, a
+// debugger): the limit is CSN_DP_TIMEOUT_S seconds (default 600, the order of NCCL's own watchdog; 0 = wait for
+// ever).  Before the trap the waiter records (1, rank, flag index, awaited epoch) in a pinned host slot that
+// csn_dp_last_timeout() reads back after the context has died.
+struct Watchdog {
+  unsigned long long limit_ns;  // 0: no limit
+  unsigned* host_slot;          // pinned, mapped; may be NULL
+  int rank;
+};
+__device__ __forceinline__ void wait_flag_ge(const unsigned* flag, unsigned target, const Watchdog& wd, int flag_index) {
   unsigned long long t0 = 0;
   unsigned spins = 0;
   while ((int)(ld_acquire_sys(flag) - target) < 0) {
-    if ((++spins & 1023u) == 0) {
+    if ((++spins & 1023u) == 0 && wd.limit_ns) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 10000000000ull) __trap();
+      else if (now - t0 > wd.limit_ns) {
+        if (wd.host_slot) {
+          wd.host_slot[1] = (unsigned)wd.rank;
+          wd.host_slot[2] = (unsigned)flag_index;
+          wd.host_slot[3] = target;
+          __threadfence_system();
+          wd.host_slot[0] = 1u;
+          __threadfence_system();
+        }
+        __trap();
+      }
     }
   }
 }
 
+static Watchdog make_watchdog(int rank) {
+  static const unsigned long long limit = [] {
+    const char* e = getenv("CSN_DP_TIMEOUT_S");
+    const double sec = e ? atof(e) : 600.0;
+    return sec > 0 ? (unsigned long long)(sec * 1e9) : 0ull;
+  }();
+  static unsigned* slot = [] {
+    unsigned* h = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), 4 * sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return (unsigned*)nullptr;
+    }
+    h[0] = h[1] = h[2] = h[3] = 0u;
+    return h;
+  }();
+  return Watchdog{limit, slot, rank};
+}
+
 __global__ void dp_wait_done_zero_kernel(const unsigned* __restrict__ flags_local, int world, const int* __restrict__ step_dev,
-                                         float* __restrict__ zero_ptr, size_t n) {
+                                         float* __restrict__ zero_ptr, size_t n, const Watchdog wd) {
   if (world > 1) {
-    if (threadIdx.x < world) wait_flag_ge(flags_local + kFlagDone + threadIdx.x, (unsigned)*step_dev);
+    if (threadIdx.x < world) wait_flag_ge(flags_local + kFlagDone + threadIdx.x, (unsigned)*step_dev, wd, kFlagDone + threadIdx.x);
     __syncthreads();
   }
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) zero_ptr[i] = 0.f;
@@ -66,7 +103,7 @@ __global__ void __launch_bounds__(256) dp_adam_peer_kernel(float* __restrict__ p
                                                           float* __restrict__ center, size_t K, float center_momentum,
                                                           float center_scale, int* __restrict__ step_dev, float lr, float b1,
                                                           float b2, float eps, float wd, int decoupled, float grad_scale,
-                                                          unsigned* __restrict__ ticket) {
+                                                          unsigned* __restrict__ ticket, const Watchdog dog) {
   __shared__ float s_consts[2];
   __shared__ int s_last;
   const int t = *step_dev + 1;  // this step's 1-based count (the counter is advanced by the last CTA)
@@ -75,7 +112,7 @@ __global__ void __launch_bounds__(256) dp_adam_peer_kernel(float* __restrict__ p
       __threadfence_system();
       st_release_sys(ps.flags[threadIdx.x] + kFlagReady + rank, (unsigned)t);
     }
-    if (threadIdx.x < world) wait_flag_ge(ps.flags[rank] + kFlagReady + threadIdx.x, (unsigned)t);
+    if (threadIdx.x < world) wait_flag_ge(ps.flags[rank] + kFlagReady + threadIdx.x, (unsigned)t, dog, kFlagReady + threadIdx.x);
   }
   // bias corrections 1 - beta^t = -expm1(t log beta): accurate in fp32 for small and large t alike, and cheap enough
   // to recompute in every CTA (a double-precision pow here, or in the last CTA, costs ~3 us of every step)
@@ -153,7 +190,7 @@ extern "C" int csn_dp_wait_done_zero(const void* flags_local, int world, const i
   CSN_REQUIRE(world >= 1 && world <= kMaxWorld, "csn_dp_wait_done_zero: world must be in [1, %d]", kMaxWorld);
   const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>(ceil_div<size_t>(n, 256), size_t(sm_count())));
   dp_wait_done_zero_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned*>(flags_local), world,
-                                                                  step_counter, zero_ptr, zero_ptr ? n : 0);
+                                                                  step_counter, zero_ptr, zero_ptr ? n : 0, make_watchdog(-1));
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
@@ -183,7 +220,14 @@ extern "C" int csn_dp_adam_step_peer(float* params, float* exp_avg, float* exp_a
   const unsigned blocks = (unsigned)std::min<size_t>(want, size_t(sm_count()) * 4);
   dp_adam_peer_kernel<<<blocks, 256, 0, as_stream(stream)>>>(params, exp_avg, exp_avg_sq, n_param, ps, world, rank, center, K,
                                                              center_momentum, center_scale, step_counter, lr, beta1, beta2, eps,
-                                                             weight_decay, decoupled, grad_scale, ticket);
+                                                             weight_decay, decoupled, grad_scale, ticket, make_watchdog(rank));
   CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_dp_last_timeout(int* out4) {
+  CSN_REQUIRE(out4, "csn_dp_last_timeout: null pointer");
+  const Watchdog wd = make_watchdog(-1);
+  for (int i = 0; i < 4; ++i) out4[i] = wd.host_slot ? (int)reinterpret_cast<volatile unsigned*>(wd.host_slot)[i] : 0;
   return CSN_OK;
 }

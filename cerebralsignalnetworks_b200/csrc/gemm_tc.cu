@@ -1,7 +1,8 @@
 // bf16 tensor-core GEMM for sm_100a: TMA (128B swizzle) -> shared-memory ring -> tcgen05.mma (fp32 accumulators
 // in TMEM) -> tcgen05.ld epilogue.  Warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (single thread),
-// warps 2..5 = epilogue (one TMEM lane quadrant each).  CTA tile 128 x 128 x 64, up to 4 stages, optional split-K
-// with fp32 atomics.  Both operands may be K-major or MN-major (the dW = dG^T Z products of BPTT contract over
+// warps 2..5 = epilogue (one TMEM lane quadrant each).  CTA tile 128 x 128 x 64, up to 4 stages.  Split-K writes one
+// partial slab per split (plain stores) and a small kernel adds the slabs in split order: no float atomics anywhere,
+// so the same inputs give the same bits on every run.  Both operands may be K-major or MN-major (the dW = dG^T Z products of BPTT contract over
 // the row index of both stored matrices).
 //
 // D[M,N] = op(A)[M,K] * op(B)[K,N] (+ bias[N]);  A: transA=0 stored [M,K] (K-major), transA=1 stored [K,M]
@@ -41,7 +42,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 tensor [outer, inner] with row pitch `pitch_elems`, box [box_outer, box_inner], 128B swizzle.
-static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
                         uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
@@ -270,11 +271,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (gm >= p.M || gn >= p.N) continue;
         if (f32_out) {
           float* d = reinterpret_cast<float*>(Dz) + size_t(gm) * p.ldd + gn;
-          if (p.atomic) {
-            atomicAdd(d, v.x);
-            if (gn + 1 < p.N) atomicAdd(d + 1, v.y);
-            if (gn + 2 < p.N) atomicAdd(d + 2, v.z);
-            if (gn + 3 < p.N) atomicAdd(d + 3, v.w);
+          if (p.atomic) {  // accumulate into D: this CTA owns the tile (split_k == 1), a plain read-modify-write
+            d[0] += v.x;
+            if (gn + 1 < p.N) d[1] += v.y;
+            if (gn + 2 < p.N) d[2] += v.z;
+            if (gn + 3 < p.N) d[3] += v.w;
           } else if (vec_ok && gn + 3 < p.N) {
             *reinterpret_cast<float4*>(d) = v;
           } else {
@@ -339,15 +340,53 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   return CSN_OK;
 }
 
+// D[m, n] (+)= sum_z slabs[z][m, n] (+ bias[n]), z ascending: the fixed-order tail of a split-K product
+__global__ void splitk_reduce_kernel(const float* __restrict__ slabs, size_t stride, int S, float* __restrict__ D, int ldd,
+                                     int M, int N, const float* __restrict__ bias, int accumulate) {
+  const size_t total = size_t(M) * N;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int m = int(i / N), n = int(i - size_t(m) * N);
+    float a = slabs[i];
+    for (int z = 1; z < S; ++z) a += slabs[size_t(z) * stride + i];
+    if (bias) a += bias[n];
+    float* d = D + size_t(m) * ldd + n;
+    *d = accumulate ? *d + a : a;
+  }
+}
+
+int gemm_tc_splits(int K, int split_k) {
+  const int k_iters = ceil_div(K, GBK);
+  split_k = std::max(1, std::min(split_k, k_iters));
+  return ceil_div(k_iters, ceil_div(k_iters, split_k));
+}
+
+int splitk_reduce(const float* slabs, size_t stride, int S, float* D, int ldd, int M, int N, const float* bias,
+                  int accumulate, cudaStream_t s) {
+  const size_t total = size_t(M) * N;
+  const int blocks = (int)std::min<size_t>(ceil_div<size_t>(total, 256), size_t(sm_count()) * 8);
+  splitk_reduce_kernel<<<blocks, 256, 0, s>>>(slabs, stride, S, D, ldd, M, N, bias, accumulate);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
 }  // namespace csn
 
 using namespace csn;
 
 extern "C" int csn_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B,
                                 int ldb, void* D, int ldd, int d_dtype, const float* bias, int accumulate, int split_k,
-                                void* stream) {
-  return gemm_tc_run(transA, transB, M, N, K, A, lda, B, ldb, D, ldd, d_dtype, bias, accumulate, split_k, nullptr,
-                     as_stream(stream));
+                                void* workspace, void* stream) {
+  cudaStream_t s = as_stream(stream);
+  if (split_k < 1) split_k = 1;
+  split_k = std::min(split_k, ceil_div(K, GBK));
+  if (split_k == 1) return gemm_tc_run(transA, transB, M, N, K, A, lda, B, ldb, D, ldd, d_dtype, bias, accumulate, 1, nullptr, s);
+  CSN_REQUIRE(workspace, "csn_gemm_bf16_tc: split_k > 1 needs a workspace of split_k * M * N floats (partial slabs)");
+  CSN_REQUIRE(d_dtype == CSN_F32 && D, "csn_gemm_bf16_tc: split-K needs an fp32 output");
+  GemmEpi slab{};
+  slab.split_stride = size_t(M) * N;
+  CSN_TRY(gemm_tc_run(transA, transB, M, N, K, A, lda, B, ldb, workspace, N, CSN_F32, nullptr, 0, split_k, &slab, s));
+  return splitk_reduce(reinterpret_cast<const float*>(workspace), slab.split_stride, gemm_tc_splits(K, split_k),
+                       reinterpret_cast<float*>(D), ldd, M, N, bias, accumulate, s);
 }
 
 int csn::gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* D,
@@ -389,13 +428,13 @@ int csn::gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A,
     CSN_REQUIRE(!cell->xp && d_dtype == CSN_F32 && !accumulate, "gemm_tc_run: split slabs need fp32 output without accumulation");
     p.split_stride = cell->split_stride;
   }
-  p.atomic = (!p.split_stride && (accumulate || split_k > 1)) ? 1 : 0;
+  CSN_REQUIRE(split_k == 1 || p.split_stride, "gemm_tc_run: split-K needs partial slabs (GemmEpi::split_stride)");
+  p.atomic = (!p.split_stride && accumulate) ? 1 : 0;  // read-modify-write epilogue
   p.stages = it_per_split < 4 ? (it_per_split < 2 ? 2 : it_per_split) : 4;
   if (cell && !cell->split_stride) {
     p.mode = 1; p.zero_acc = cell->zero_acc; p.H = cell->H; p.xp = cell->xp; p.c_prev = cell->c_prev;
     p.h_out = cell->h_out; p.gates_out = cell->gates_out; p.c_out = cell->c_out;
   }
-  if (split_k > 1 && !accumulate && !p.split_stride) CSN_CUDA(cudaMemset2DAsync(D, size_t(ldd) * 4, 0, size_t(N) * 4, M, s));
   dim3 grid(ceil_div(N, gbn), ceil_div(M, GBM), split_k);
   CSN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "csn_gemm_bf16_tc: grid too large");
   if (transA && !transB) return launch_gemm<true, true>(ta, tb, p, grid, s);

@@ -7,7 +7,8 @@
 //   column j" reading scalars in the backward product,
 //   pre = W h + b, emb = act(pre); teacher softmax ((t - c) / tau_t), student log-softmax (emb / tau_s), loss,
 //   d_emb = coef / tau_s (p - q), d_pre = act'(pre) d_emb      (block reductions: one round of maxima, one of sums),
-//   d_h = d_pre W (the gradient the BPTT kernel waits for), the batch-centre column sums (atomics, R rows pre-summed).
+//   d_h = d_pre W (the gradient the BPTT kernel waits for).  The loss is folded across CTAs in a fixed order (det_cta_sum);
+//   the batch-centre column sums are a separate fixed-order pass over the teacher (off the step's critical path).
 // d_pre is also written out: dW = d_pre^T h and db = sum_b d_pre are NOT on the critical path, the caller runs that GEMM
 // beside the backward recurrence.  Same log2-domain arithmetic as dino_loss_rowwarp_kernel.
 #include "common.cuh"
@@ -39,10 +40,10 @@ struct HeadParams {
   const float* bias;    // [K] or nullptr
   const float* teacher; // [B, K]
   const float* center;  // [K]
-  float* loss;          // scalar (zeroed by the caller of the kernel)
+  float* loss;          // scalar, written by the last CTA
+  void* ws;             // loss fold scratch (ticket + one partial per CTA)
   float* d_hlast;       // [B, I]
   float* d_pre;         // [B, K]
-  float* batch_center;  // [K], accumulated
   int B, I, K, act;
   float ss, ts;         // log2(e) / tau_s, log2(e) / tau_t
   float coef, grad_coef;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(1024, 1) head_dino_kernel(const HeadParams p) 
     sm[2 * R + r] = kv ? et[r] * sv[r] : 0.f;
   }
   block_reduce<3 * R, false>(sm, red1, warp, lane, nwarps);
-  float loss_cta = 0.f, tsum = 0.f;
+  float loss_cta = 0.f;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const bool rv = r < rows;
@@ -169,11 +170,8 @@ __global__ void __launch_bounds__(1024, 1) head_dino_kernel(const HeadParams p) 
       dps[r * K + k] = d;
       if (rv) p.d_pre[size_t(b0 + r) * K + k] = d;
     }
-    tsum += tt[r];
   }
-  if (kv) atomicAdd(p.batch_center + k, tsum);
-  if (tid == 0) atomicAdd(p.loss, p.coef * loss_cta);
-  __syncthreads();
+  det_cta_sum(p.coef * loss_cta, p.ws, blockIdx.x, gridDim.x, p.loss);  // (synchronises the CTA: dps is complete)
 
   // ---- backward: d_h[r][j] = sum_k d_pre[r][k] W[k][j]; G thread groups split the k range ----
   const int G = nthreads / I;
@@ -232,14 +230,15 @@ using namespace csn;
 extern "C" int csn_head_dino_supported(int B, int I, int K) {
   if (B < 1 || I < 32 || I % 32 != 0 || K < 1 || K > 1024) return 0;
   const int nthreads = ceil_div(K, 32) * 32 < I ? I : ceil_div(K, 32) * 32;
+  if (nthreads > 1024) return 0;  // one thread per output column / input column
   return head_smem_bytes<4>(I, K, nthreads) <= size_t(220) * 1024 ? 1 : 0;
 }
 
 extern "C" int csn_head_dino_fwd_bwd(const void* h_last, int h_dtype, const float* W, const float* bias, int act,
                                      const float* teacher, const float* center, float student_temp, float teacher_temp,
                                      float* loss, float* d_hlast, float* d_pre, float* batch_center, int B, int I, int K,
-                                     float grad_scale, void* stream) {
-  CSN_REQUIRE(h_last && W && teacher && center && loss && d_hlast && d_pre && batch_center,
+                                     float grad_scale, void* workspace, void* stream) {
+  CSN_REQUIRE(h_last && W && teacher && center && loss && d_hlast && d_pre && workspace,
               "csn_head_dino_fwd_bwd: null pointer");
   CSN_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, "csn_head_dino_fwd_bwd: W must be 16-byte aligned");
   CSN_REQUIRE(h_dtype == CSN_F32 || h_dtype == CSN_BF16, "csn_head_dino_fwd_bwd: h_dtype must be CSN_F32 or CSN_BF16");
@@ -252,16 +251,20 @@ extern "C" int csn_head_dino_fwd_bwd(const void* h_last, int h_dtype, const floa
   }
   HeadParams p{};
   p.h_last = h_last; p.W = W; p.bias = bias; p.teacher = teacher; p.center = center; p.loss = loss; p.d_hlast = d_hlast;
-  p.d_pre = d_pre; p.batch_center = batch_center; p.B = B; p.I = I; p.K = K; p.act = act;
+  p.d_pre = d_pre; p.ws = workspace; p.B = B; p.I = I; p.K = K; p.act = act;
   p.ss = kL2e_h / student_temp; p.ts = kL2e_h / teacher_temp;
   p.coef = 1.f / B;
   p.grad_coef = p.coef / student_temp * grad_scale;
   cudaStream_t s = as_stream(stream);
-  CSN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  CSN_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned), s));  // arrival ticket of the loss fold
   const int kt = ceil_div(K, 32) * 32;
   const int nthreads = kt < I ? I : kt;
   // two rows per CTA while that is at most ~2 waves of CTAs (each CTA re-stages W), else four
   const bool r2 = ceil_div(B, 2) <= 2 * sm_count();
-  if (h_dtype == CSN_BF16) return r2 ? launch_head<2, __nv_bfloat16>(p, nthreads, s) : launch_head<4, __nv_bfloat16>(p, nthreads, s);
-  return r2 ? launch_head<2, float>(p, nthreads, s) : launch_head<4, float>(p, nthreads, s);
+  if (h_dtype == CSN_BF16) CSN_TRY((r2 ? launch_head<2, __nv_bfloat16>(p, nthreads, s) : launch_head<4, __nv_bfloat16>(p, nthreads, s)));
+  else CSN_TRY((r2 ? launch_head<2, float>(p, nthreads, s) : launch_head<4, float>(p, nthreads, s)));
+  // batch_center [K] += sum_b teacher, fixed order; a caller that overlaps it with other work passes NULL and runs
+  // csn_colsum_f32 itself (the train step does, on its side stream)
+  if (batch_center) CSN_TRY(colsum_det(teacher, batch_center, B, K, K, 1, s));
+  return CSN_OK;
 }

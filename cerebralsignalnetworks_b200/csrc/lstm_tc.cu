@@ -25,6 +25,7 @@
 #include <type_traits>
 
 #include "tc.cuh"
+#include "gemm_tc.cuh"
 
 namespace csn {
 
@@ -553,7 +554,7 @@ template <int NV, int KSTEPS>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
-                   float* __restrict__ db_ih, float* __restrict__ db_hh, int T, int B, int H, int KP,
+                   float* __restrict__ db_part, int T, int B, int H, int KP,
                    long long* __restrict__ prof, const uint32_t uz) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const size_t b_bytes = size_t(4 * 128 / 8) * kLboB;  // gate stride fixed at 128 contraction elements
@@ -751,12 +752,11 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
       if (do_prof) prof[512 + (n - 1) * 8 + 7] = clock64();
      }
     }
+    // bias-gradient partial of this (CTA, batch half): plain stores, folded in partial order by bptt_finalize_kernel
     if (active) {
+      float* dst = db_part + (size_t(blockIdx.x) * 2 + (tid >> 7)) * 4 * H + u;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        atomicAdd(db_ih + g * H + u, dbacc[g]);
-        atomicAdd(db_hh + g * H + u, dbacc[g]);
-      }
+      for (int g = 0; g < 4; ++g) dst[g * H] = dbacc[g];
     }
   }
   tcgen05_fence_before();
@@ -764,6 +764,41 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
   if (warp == kIssuerWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// The fixed-order tail of BPTT (no float atomics anywhere in the backward pass): dW_ih / dW_hh = sum over the split-K slabs of
+// the weight-gradient products in split order, db_ih = db_hh = sum over the recurrence CTAs' partials in CTA order.
+__global__ void bptt_finalize_kernel(const float* __restrict__ slabs_ih, int s_ih, const float* __restrict__ slabs_hh, int s_hh,
+                                     const float* __restrict__ db_part, int n_part, float* __restrict__ dw_ih,
+                                     float* __restrict__ dw_hh, float* __restrict__ db_ih, float* __restrict__ db_hh, int H, int I,
+                                     int accumulate) {
+  const int n_ih = 4 * H * I, n_hh = 4 * H * H, n_b = 4 * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ih + n_hh + n_b; i += gridDim.x * blockDim.x) {
+    if (i < n_ih) {
+      float a = slabs_ih[i];
+      for (int z = 1; z < s_ih; ++z) a += slabs_ih[size_t(z) * n_ih + i];
+      dw_ih[i] = accumulate ? dw_ih[i] + a : a;
+    } else if (i < n_ih + n_hh) {
+      const int j = i - n_ih;
+      float a = 0.f;
+      for (int z = 0; z < s_hh; ++z) a += slabs_hh[size_t(z) * n_hh + j];  // s_hh == 0: a single timestep has no h_{t-1}
+      dw_hh[j] = accumulate ? dw_hh[j] + a : a;
+    } else {
+      const int j = i - n_ih - n_hh;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int q = 0;
+      for (; q + 3 < n_part; q += 4) {
+        a0 += db_part[size_t(q) * n_b + j];
+        a1 += db_part[size_t(q + 1) * n_b + j];
+        a2 += db_part[size_t(q + 2) * n_b + j];
+        a3 += db_part[size_t(q + 3) * n_b + j];
+      }
+      for (; q < n_part; ++q) a0 += db_part[size_t(q) * n_b + j];
+      const float a = (a0 + a1) + (a2 + a3);
+      db_ih[j] = accumulate ? db_ih[j] + a : a;
+      db_hh[j] = accumulate ? db_hh[j] + a : a;
+    }
   }
 }
 
@@ -800,6 +835,14 @@ int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, co
                          const float* d_hseq, const float* d_hlast, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
                          float* dx, void* workspace, int T, int B, int I, int H, int accumulate, cudaStream_t s);
 
+// scratch of the fixed-order BPTT tail: split-K slabs of the two dW products (sized for the requested split counts; the
+// GEMM may round them down) + one bias-gradient partial per (recurrence CTA, batch half) (NV >= 2: at most B partials)
+static int dw_split_req(int M, int N) { return std::max(1, sm_count() / (ceil_div(M, 128) * ceil_div(N, 128))); }
+static size_t bwd_tail_bytes(int B, int I, int H) {
+  return align256(size_t(dw_split_req(4 * H, I)) * 4 * H * I * 4) + align256(size_t(dw_split_req(4 * H, H)) * 4 * H * H * 4) +
+         align256(size_t(B + 1) * 4 * H * 4);
+}
+
 int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace) {
   if (H > 128) return lstm_large_bytes(T, B, I, H, reserve, workspace);  // per-step GEMM + fused cell epilogue
   if (I % 8 != 0 || H % 8 != 0) {
@@ -809,7 +852,7 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
   const size_t tb = size_t(T) * B;
   *reserve = align256(tb * 4 * H * 2) + align256(tb * H * 4);
   const size_t wf = align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2) + kWimgBytes + kWihImgBytes;
-  const size_t wb = align256(tb * 4 * H * 2) + align256(size_t(4) * H * I * 2) + kWimgBytes;
+  const size_t wb = align256(tb * 4 * H * 2) + align256(size_t(4) * H * I * 2) + kWimgBytes + bwd_tail_bytes(B, I, H);
   *workspace = wf > wb ? wf : wb;
   return CSN_OK;
 }
@@ -878,7 +921,7 @@ static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, 
 
 template <int NV, int KSTEPS>
 static int launch_bwd(const uint32_t* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
-                      const float* d_hlast, __nv_bfloat16* dG, float* db_ih, float* db_hh, int T, int B, int H, int KP,
+                      const float* d_hlast, __nv_bfloat16* dG, float* db_part, int T, int B, int H, int KP,
                       cudaStream_t s) {
   const size_t smem = size_t(4 * 128 / 8) * kLboB + 128 + size_t(kPfStages) * NV * kBwdPfRow + 128;  // operand + barriers + TMA ring
   static bool attr_set = false;
@@ -886,7 +929,7 @@ static int launch_bwd(const uint32_t* w_hh, const __nv_bfloat16* gates, const fl
     CSN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<NV, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kBwdThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, g_prof_buf, 0u);
+  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kBwdThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, g_prof_buf, 0u);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
@@ -911,7 +954,7 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   } else {
     CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
     // hoisted input projection: Xp[T*B, 4H] = x[T*B, I] . W_ih[4H, I]^T + b_ih  (fp32 out)
-    CSN_TRY(csn_gemm_bf16_tc(0, 1, (int)tb, 4 * H, I, x, I, wih_bf, I, xp, 4 * H, CSN_F32, b_ih, 0, 1, s));
+    CSN_TRY(gemm_tc_run(0, 1, (int)tb, 4 * H, I, x, I, wih_bf, I, xp, 4 * H, CSN_F32, b_ih, 0, 1, nullptr, s));
   }
   const int nv = pick_nv(B);
   __nv_bfloat16* g = training ? gates : nullptr;
@@ -957,15 +1000,18 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   const int nv = pick_nv(B);
   uint32_t* w_img = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 2) +
                                                 align256(size_t(4) * H * I * 2));
-  // W_hh^T image + (unless accumulating) zero the bias-gradient accumulators the recurrence adds into
-  lstm_prepare_kernel<<<4 * 128 * 64 / 256, 256, 0, s>>>(w_hh, w_img, H, 1, nullptr, nullptr, 0, 16, accumulate ? nullptr : db_ih,
-                                                         accumulate ? nullptr : db_hh, 4 * H);
+  // scratch of the fixed-order tail, behind the weight image
+  float* slabs_ih = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(w_img) + kWimgBytes);
+  float* slabs_hh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(slabs_ih) + align256(size_t(dw_split_req(4 * H, I)) * 4 * H * I * 4));
+  float* db_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(slabs_hh) + align256(size_t(dw_split_req(4 * H, H)) * 4 * H * H * 4));
+  const int n_part = 2 * ceil_div(B, nv);
+  lstm_prepare_kernel<<<4 * 128 * 64 / 256, 256, 0, s>>>(w_hh, w_img, H, 1, nullptr, nullptr, 0, 16, nullptr, nullptr, 0);  // W_hh^T image
   CSN_LAUNCH_CHECK();
-#define CSN_BWD(KS)                                                                                                        \
-  do {                                                                                                                     \
-    if (nv == 2) CSN_TRY((launch_bwd<2, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));      \
-    else if (nv == 4) CSN_TRY((launch_bwd<4, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s))); \
-    else CSN_TRY((launch_bwd<8, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_ih, db_hh, T, B, H, KP, s)));              \
+#define CSN_BWD(KS)                                                                                                   \
+  do {                                                                                                                \
+    if (nv == 2) CSN_TRY((launch_bwd<2, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, s)));      \
+    else if (nv == 4) CSN_TRY((launch_bwd<4, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, s))); \
+    else CSN_TRY((launch_bwd<8, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, s)));              \
   } while (0)
   if (KP == 128) CSN_BWD(8);
   else if (KP == 96) CSN_BWD(6);
@@ -975,31 +1021,35 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   // dW_ih[4H, I] = dG^T . x ; dW_hh[4H, H] = dG[1:]^T . h_seq[:-1]  (contraction over time*batch, split-K).
   // Both products stream the same dG (the dominant operand, 115 MB at cfg2): they run SIDE BY SIDE on half the SMs
   // each (fork / join on an internal stream, also valid under stream capture), so the second reader finds dG in L2.
-  const int sms = sm_count();
-  const int tiles_ih = ceil_div(4 * H, 128) * ceil_div(I, 128), tiles_hh = ceil_div(4 * H, 128) * ceil_div(H, 128);
+  // Split-K: every split stores its partial product to its own slab; bptt_finalize_kernel adds the slabs in split order.
   SideStream* side = (T > 1) ? side_stream() : nullptr;
   const int share = side ? 2 : 1;
   if (side) {
     CSN_CUDA(cudaEventRecord(side->fork, s));
     CSN_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
   }
-  CSN_TRY(csn_gemm_bf16_tc(1, 0, 4 * H, I, (int)tb, dG, 4 * H, x, I, dw_ih, I, CSN_F32, nullptr, accumulate,
-                           max(1, sms / (share * tiles_ih)), s));
+  GemmEpi slab_ih{}, slab_hh{};
+  slab_ih.split_stride = size_t(4) * H * I;
+  slab_hh.split_stride = size_t(4) * H * H;
+  const int s_ih = gemm_tc_splits((int)tb, max(1, dw_split_req(4 * H, I) / share));
+  const int s_hh = T > 1 ? gemm_tc_splits((int)(tb - B), max(1, dw_split_req(4 * H, H) / share)) : 0;
+  CSN_TRY(gemm_tc_run(1, 0, 4 * H, I, (int)tb, dG, 4 * H, x, I, slabs_ih, I, CSN_F32, nullptr, 0, s_ih, &slab_ih, s));
   if (T > 1) {
     cudaStream_t s2 = side ? side->st : s;
-    int r2 = csn_gemm_bf16_tc(1, 0, 4 * H, H, (int)(tb - B), dG + size_t(B) * 4 * H, 4 * H, h_seq, H, dw_hh, H, CSN_F32,
-                              nullptr, accumulate, max(1, sms / (share * tiles_hh)), s2);
+    int r2 = gemm_tc_run(1, 0, 4 * H, H, (int)(tb - B), dG + size_t(B) * 4 * H, 4 * H, h_seq, H, slabs_hh, H, CSN_F32, nullptr, 0,
+                         s_hh, &slab_hh, s2);
     if (side) {  // always rejoin (a capture must not end with a dangling fork)
       CSN_CUDA(cudaEventRecord(side->join, side->st));
       CSN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
     }
     CSN_TRY(r2);
-  } else if (!accumulate) {
-    CSN_CUDA(cudaMemsetAsync(dw_hh, 0, size_t(4) * H * H * 4, s));
   }
+  bptt_finalize_kernel<<<ceil_div(4 * H * (I + H + 1), 256), 256, 0, s>>>(slabs_ih, s_ih, slabs_hh, s_hh, db_part, n_part, dw_ih,
+                                                                          dw_hh, db_ih, db_hh, H, I, accumulate);
+  CSN_LAUNCH_CHECK();
   if (dx) {
     CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
-    CSN_TRY(csn_gemm_bf16_tc(0, 0, (int)tb, I, 4 * H, dG, 4 * H, wih_bf, I, dx, I, CSN_F32, nullptr, 0, 1, s));
+    CSN_TRY(gemm_tc_run(0, 0, (int)tb, I, 4 * H, dG, 4 * H, wih_bf, I, dx, I, CSN_F32, nullptr, 0, 1, nullptr, s));
   }
   return CSN_OK;
 }

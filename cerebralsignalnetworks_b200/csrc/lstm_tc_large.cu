@@ -40,13 +40,16 @@ __global__ void permute_bias_kernel(const float* __restrict__ b_ih, const float*
     dst[r] = b_ih[g * H + u] + b_hh[g * H + u];
   }
 }
-// dst[g*H+u, :] (+)= src[4u+g, 0:N] (src leading dimension lds)
-__global__ void unpermute_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int N, int lds, int accumulate) {
+// dst[g*H+u, :] (+)= sum_z src[z][4u+g, 0:N] (src leading dimension lds, split-K slabs `stride` floats apart, added in
+// split order: the fixed-order tail of the split-K weight-gradient products -- no float atomics)
+__global__ void unpermute_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int N, int lds, int accumulate,
+                                      int S, size_t stride) {
   const int r = blockIdx.x;
   const int u = r >> 2, g = r & 3;
   float* d = dst + size_t(g * H + u) * N;
   for (int c = threadIdx.x; c < N; c += blockDim.x) {
-    const float v = src[size_t(r) * lds + c];
+    float v = src[size_t(r) * lds + c];
+    for (int z = 1; z < S; ++z) v += src[size_t(z) * stride + size_t(r) * lds + c];
     d[c] = accumulate ? d[c] + v : v;
   }
 }
@@ -104,6 +107,11 @@ struct LargeWs {
   size_t total;
 };
 
+// splits of a [M, N] = A^T B product contracting over K rows: enough CTAs to fill the machine (what the GEMM launches)
+static int dw_splits(int M, int N, int K) {
+  return gemm_tc_splits(K, std::max(1, sm_count() / (ceil_div(M, 128) * ceil_div(N, 128))));
+}
+
 static LargeWs carve_ws(void* base, int T, int B, int I, int H) {
   const size_t tb = size_t(T) * B;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
@@ -117,9 +125,13 @@ static LargeWs carve_ws(void* base, int T, int B, int I, int H) {
   w.bias = reinterpret_cast<float*>(take(size_t(4) * H * 4));
   w.dh_rec = reinterpret_cast<float*>(take(size_t(8) * B * H * 4));
   w.dc = reinterpret_cast<float*>(take(size_t(B) * H * 4));
-  w.dwp = reinterpret_cast<float*>(take(size_t(4) * H * (I > H ? I : H) * 4));
+  // split-K slabs of the weight-gradient products (one partial [4H, N] per split, summed by unpermute_rows_kernel)
+  // (sized for the REQUESTED split count: the GEMM may round it down, never up)
+  auto req = [](int M, int N) { return size_t(std::max(1, sm_count() / (ceil_div(M, 128) * ceil_div(N, 128)))); };
+  const size_t s_ih = req(4 * H, I) * 4 * H * I, s_hh = req(4 * H, H) * 4 * H * H;
+  w.dwp = reinterpret_cast<float*>(take((s_ih > s_hh ? s_ih : s_hh) * 4));
   w.ones = reinterpret_cast<__nv_bfloat16*>(take(tb * 8 * 2));
-  w.dbp = reinterpret_cast<float*>(take(size_t(4) * H * 8 * 4));
+  w.dbp = reinterpret_cast<float*>(take(req(4 * H, 8) * 4 * H * 8 * 4));
   w.total = off;
   return w;
 }
@@ -224,15 +236,20 @@ int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, co
                           kparts, &slabs, s));
   }
   const int sms = sm_count();
-  auto splits = [&](int M, int N) { return max(1, sms / (ceil_div(M, 128) * ceil_div(N, 128))); };
-  // dW_ih (permuted rows) = dG^T . x, then scatter the rows back to PyTorch gate order
-  CSN_TRY(gemm_tc_run(1, 0, 4 * H, I, (int)tb, w.dG, 4 * H, x, I, w.dwp, I, CSN_F32, nullptr, 0, splits(4 * H, I), nullptr, s));
-  unpermute_rows_kernel<<<4 * H, 128, 0, s>>>(w.dwp, dw_ih, H, I, I, accumulate);
+  // dW_ih (permuted rows) = dG^T . x as split-K slabs, then add the slabs in split order while scattering the rows back
+  // to PyTorch gate order
+  GemmEpi dws{};
+  int ns = dw_splits(4 * H, I, (int)tb);
+  dws.split_stride = size_t(4) * H * I;
+  CSN_TRY(gemm_tc_run(1, 0, 4 * H, I, (int)tb, w.dG, 4 * H, x, I, w.dwp, I, CSN_F32, nullptr, 0, ns, &dws, s));
+  unpermute_rows_kernel<<<4 * H, 128, 0, s>>>(w.dwp, dw_ih, H, I, I, accumulate, ns, dws.split_stride);
   CSN_LAUNCH_CHECK();
   if (T > 1) {
+    ns = dw_splits(4 * H, H, (int)(tb - B));
+    dws.split_stride = size_t(4) * H * H;
     CSN_TRY(gemm_tc_run(1, 0, 4 * H, H, (int)(tb - B), w.dG + size_t(B) * 4 * H, 4 * H, h_seq, H, w.dwp, H, CSN_F32, nullptr, 0,
-                        splits(4 * H, H), nullptr, s));
-    unpermute_rows_kernel<<<4 * H, 128, 0, s>>>(w.dwp, dw_hh, H, H, H, accumulate);
+                        ns, &dws, s));
+    unpermute_rows_kernel<<<4 * H, 128, 0, s>>>(w.dwp, dw_hh, H, H, H, accumulate, ns, dws.split_stride);
     CSN_LAUNCH_CHECK();
   } else if (!accumulate) {
     CSN_CUDA(cudaMemsetAsync(dw_hh, 0, size_t(4) * H * H * 4, s));
@@ -240,10 +257,12 @@ int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, co
   // db = dG^T . 1  (tensor-core column sums of the bf16 dG)
   fill_bf16_kernel<<<min(ceil_div<size_t>(tb * 8, 256), size_t(sms) * 8), 256, 0, s>>>(w.ones, tb * 8, 1.f);
   CSN_LAUNCH_CHECK();
-  CSN_TRY(gemm_tc_run(1, 0, 4 * H, 8, (int)tb, w.dG, 4 * H, w.ones, 8, w.dbp, 8, CSN_F32, nullptr, 0, splits(4 * H, 8), nullptr, s));
-  unpermute_rows_kernel<<<4 * H, 32, 0, s>>>(w.dbp, db_ih, H, 1, 8, accumulate);
+  ns = dw_splits(4 * H, 8, (int)tb);
+  dws.split_stride = size_t(4) * H * 8;
+  CSN_TRY(gemm_tc_run(1, 0, 4 * H, 8, (int)tb, w.dG, 4 * H, w.ones, 8, w.dbp, 8, CSN_F32, nullptr, 0, ns, &dws, s));
+  unpermute_rows_kernel<<<4 * H, 32, 0, s>>>(w.dbp, db_ih, H, 1, 8, accumulate, ns, dws.split_stride);
   CSN_LAUNCH_CHECK();
-  unpermute_rows_kernel<<<4 * H, 32, 0, s>>>(w.dbp, db_hh, H, 1, 8, accumulate);
+  unpermute_rows_kernel<<<4 * H, 32, 0, s>>>(w.dbp, db_hh, H, 1, 8, accumulate, ns, dws.split_stride);
   CSN_LAUNCH_CHECK();
   if (dx) CSN_TRY(gemm_tc_run(0, 0, (int)tb, I, 4 * H, w.dG, 4 * H, w.wih, I, dx, I, CSN_F32, nullptr, 0, 1, nullptr, s));
   return CSN_OK;

@@ -84,22 +84,33 @@ __global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restr
   }
 }
 
-// out[n] (+)= sum_m x[m,n]: block = 32 columns x 8 row-lanes, grid.y splits rows; atomics across row splits.
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int ldx, int rows_per_block) {
-  __shared__ float red[8][33];
+// out[n] (+)= sum_m x[m,n] in a FIXED order (no atomics: the same input gives the same bits every run).  Block = 32
+// columns x RY row-lanes; row-lane y adds rows y, y + RY, ... into four rotating accumulators (independent loads in
+// flight), the lanes are folded in shared memory in lane order.  One CTA owns its 32 columns for all rows.
+template <int RY>
+__global__ void __launch_bounds__(32 * RY) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N,
+                                                        int ldx, int accumulate) {
+  __shared__ float red[RY][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
-  const int m0 = blockIdx.y * rows_per_block;
-  const int m1 = min(M, m0 + rows_per_block);
-  float acc = 0.f;
-  if (col < N)
-    for (int m = m0 + threadIdx.y; m < m1; m += 8) acc += x[size_t(m) * ldx + col];
-  red[threadIdx.y][threadIdx.x] = acc;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (col < N) {
+    const float* src = x + col;
+    int m = threadIdx.y;
+    for (; m + 3 * RY < M; m += 4 * RY) {
+      a0 += src[size_t(m) * ldx];
+      a1 += src[size_t(m + RY) * ldx];
+      a2 += src[size_t(m + 2 * RY) * ldx];
+      a3 += src[size_t(m + 3 * RY) * ldx];
+    }
+    for (; m < M; m += RY) a0 += src[size_t(m) * ldx];
+  }
+  red[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (threadIdx.y == 0 && col < N) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
-    atomicAdd(out + col, s);
+    for (int j = 0; j < RY; ++j) s += red[j][threadIdx.x];
+    out[col] = accumulate ? out[col] + s : s;
   }
 }
 
@@ -188,7 +199,7 @@ __device__ __forceinline__ int find_segment(const long long* __restrict__ seg_of
 }
 constexpr int kClipChunk = 2048;
 __global__ void seg_sumsq_kernel(const float* __restrict__ g, const long long* __restrict__ seg_off, int n_seg,
-                                 float* __restrict__ sumsq) {
+                                 float* __restrict__ chunk_sumsq) {
   // each block handles one chunk of kClipChunk elements that never straddles a segment (chunks are per segment)
   __shared__ float red[8];
   long long chunk = blockIdx.x;
@@ -201,7 +212,10 @@ __global__ void seg_sumsq_kernel(const float* __restrict__ g, const long long* _
     if (chunk < first + nc) break;
     first += nc;
   }
-  if (seg >= n_seg) return;
+  if (seg >= n_seg) {
+    if (threadIdx.x == 0) chunk_sumsq[chunk] = 0.f;
+    return;
+  }
   const long long beg = seg_off[seg] + (chunk - first) * kClipChunk;
   const long long end = min(beg + (long long)kClipChunk, seg_off[seg + 1]);
   float acc = 0.f;
@@ -212,8 +226,21 @@ __global__ void seg_sumsq_kernel(const float* __restrict__ g, const long long* _
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-    atomicAdd(sumsq + seg, s);
+    chunk_sumsq[chunk] = s;  // folded per segment, in chunk order, by seg_fold_kernel (no atomics)
   }
+}
+// one warp per segment: sumsq[seg] = sum of its chunks' partials, lane-strided then a fixed shuffle tree
+__global__ void seg_fold_kernel(const float* __restrict__ chunk_sumsq, const long long* __restrict__ seg_off, int n_seg,
+                                float* __restrict__ sumsq) {
+  const int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (seg >= n_seg) return;
+  long long first = 0;
+  for (int i = 0; i < seg; ++i) first += (seg_off[i + 1] - seg_off[i] + kClipChunk - 1) / kClipChunk;
+  const long long nc = (seg_off[seg + 1] - seg_off[seg] + kClipChunk - 1) / kClipChunk;
+  float a = 0.f;
+  for (long long c = lane; c < nc; c += 32) a += chunk_sumsq[first + c];
+  a = warp_sum(a);
+  if (lane == 0) sumsq[seg] = a;
 }
 __global__ void seg_clip_kernel(float* __restrict__ g, const long long* __restrict__ seg_off, int n_seg,
                                 const float* __restrict__ sumsq, float clip) {
@@ -291,8 +318,9 @@ extern "C" int csn_clip_grad_segments(float* grads, const long long* seg_off_dev
                                       float* sumsq_dev, float clip, void* stream) {
   CSN_REQUIRE(grads && seg_off_dev && sumsq_dev && n_seg >= 1 && n_chunks >= 1 && clip > 0.f, "csn_clip_grad_segments: bad arguments");
   cudaStream_t s = as_stream(stream);
-  CSN_CUDA(cudaMemsetAsync(sumsq_dev, 0, size_t(n_seg) * 4, s));
-  seg_sumsq_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(grads, seg_off_dev, n_seg, sumsq_dev);
+  seg_sumsq_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(grads, seg_off_dev, n_seg, sumsq_dev + n_seg);
+  CSN_LAUNCH_CHECK();
+  seg_fold_kernel<<<ceil_div(n_seg, 8), 256, 0, s>>>(sumsq_dev + n_seg, seg_off_dev, n_seg, sumsq_dev);
   CSN_LAUNCH_CHECK();
   seg_clip_kernel<<<sm_count() * 8, 256, 0, s>>>(grads, seg_off_dev, n_seg, sumsq_dev, clip);
   CSN_LAUNCH_CHECK();
@@ -314,18 +342,22 @@ extern "C" int csn_act_bwd(const float* x, const float* dy, float* dx, size_t n,
   return CSN_OK;
 }
 
-extern "C" int csn_colsum_f32(const float* x, float* out, int M, int N, int ldx, int accumulate, void* stream) {
-  CSN_REQUIRE(x && out && M >= 0 && N >= 1 && ldx >= N, "csn_colsum_f32: bad arguments");
-  cudaStream_t s = as_stream(stream);
-  if (!accumulate) CSN_CUDA(cudaMemsetAsync(out, 0, size_t(N) * 4, s));
-  if (M == 0) return CSN_OK;
-  int col_blocks = ceil_div(N, 32);
-  int row_splits = max(1, min(ceil_div(M, 64), ceil_div(sm_count() * 4, col_blocks)));
-  int rows_per_block = ceil_div(M, row_splits);
-  row_splits = ceil_div(M, rows_per_block);
-  colsum_kernel<<<dim3(col_blocks, row_splits), dim3(32, 8), 0, s>>>(x, out, M, N, ldx, rows_per_block);
+int csn::colsum_det(const float* x, float* out, int M, int N, int ldx, int accumulate, cudaStream_t s) {
+  if (M == 0) {
+    if (!accumulate) CSN_CUDA(cudaMemsetAsync(out, 0, size_t(N) * 4, s));
+    return CSN_OK;
+  }
+  const int col_blocks = ceil_div(N, 32);
+  // the row-lane count depends on the shape only, so the summation order is a function of (M, N) alone
+  if (M >= 512 && col_blocks < 4 * sm_count()) colsum_kernel<32><<<col_blocks, dim3(32, 32), 0, s>>>(x, out, M, N, ldx, accumulate);
+  else colsum_kernel<8><<<col_blocks, dim3(32, 8), 0, s>>>(x, out, M, N, ldx, accumulate);
   CSN_LAUNCH_CHECK();
   return CSN_OK;
+}
+
+extern "C" int csn_colsum_f32(const float* x, float* out, int M, int N, int ldx, int accumulate, void* stream) {
+  CSN_REQUIRE(x && out && M >= 0 && N >= 1 && ldx >= N, "csn_colsum_f32: bad arguments");
+  return colsum_det(x, out, M, N, ldx, accumulate, as_stream(stream));
 }
 
 extern "C" int csn_l2norm_fwd(const float* x, float* y, float* inv_norm, int M, int N, void* stream) {

@@ -38,7 +38,7 @@ class _FeatureDistFunction(torch.autograd.Function):
         d_pred = torch.empty_like(pred) if pred is not None else None
         call("csn_feature_dist_loss_fwd_bwd", _p(student), _p(teacher), _p(pred), _p(label), _p(loss), _p(d_student),
              _p(d_pred), B, K, 0 if pred is None else pred.shape[1], float(temperature), float(alpha), float(beta), 1.0,
-             _stream())
+             _p(ops.loss_workspace(B, student.device)), _stream())
         ctx.has_pred = pred is not None
         ctx.save_for_backward(d_student, d_pred) if ctx.has_pred else ctx.save_for_backward(d_student)
         return loss
@@ -83,7 +83,8 @@ class _CosineFunction(torch.autograd.Function):
         B, K = student.shape
         loss = torch.empty((), dtype=torch.float32, device=student.device)
         d_student = torch.empty_like(student)
-        call("csn_cosine_loss_fwd_bwd", _p(student), _p(teacher), _p(loss), _p(d_student), B, K, float(eps), 1.0, _stream())
+        call("csn_cosine_loss_fwd_bwd", _p(student), _p(teacher), _p(loss), _p(d_student), B, K, float(eps), 1.0,
+             _p(ops.loss_workspace(B, student.device)), _stream())
         ctx.save_for_backward(d_student)
         return loss
 
@@ -120,7 +121,7 @@ class _KDFunction(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=student.device)
         d_student = torch.empty_like(student)
         call("csn_kd_loss_fwd_bwd", _p(student), _p(teacher), _p(label), _p(loss), _p(d_student), B, K, float(temperature),
-             float(c_kl), float(c_sl1), float(c_ce), 1.0, _stream())
+             float(c_kl), float(c_sl1), float(c_ce), 1.0, _p(ops.loss_workspace(B, student.device)), _stream())
         ctx.save_for_backward(d_student)
         return loss
 

@@ -122,7 +122,8 @@ def gemm_f32(a, b, trans_a=False, trans_b=False, bias=None, act=ACT_NONE, out=No
 
 def gemm_bf16(a, b, trans_a=False, trans_b=False, bias=None, out=None, out_dtype=torch.float32, accumulate=False,
               split_k=1):
-    """tcgen05 GEMM; a, b bfloat16.  Same op() convention as gemm_f32."""
+    """tcgen05 GEMM; a, b bfloat16.  Same op() convention as gemm_f32.  split_k > 1: partial slabs in a scratch
+    tensor, added in split order by a second kernel (no atomics)."""
     _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b")
     M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
     K2, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
@@ -131,8 +132,9 @@ def gemm_bf16(a, b, trans_a=False, trans_b=False, bias=None, out=None, out_dtype
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=a.device)
     _chk(out, name="out")
+    ws = torch.empty((int(split_k), M, N), dtype=torch.float32, device=a.device) if split_k > 1 else None
     call("csn_gemm_bf16_tc", int(trans_a), int(trans_b), M, N, K, _p(a), a.shape[1], _p(b), b.shape[1], _p(out), N,
-         _dt(out.dtype), _p(bias), int(accumulate), int(split_k), _stream())
+         _dt(out.dtype), _p(bias), int(accumulate), int(split_k), _p(ws), _stream())
     return out
 
 
@@ -243,6 +245,13 @@ def lstm_layer_bwd(x, w_ih, w_hh, h_seq, reserve, workspace, d_hseq, d_hlast, gr
 
 
 # ------------------------------------------------------------------------------------------------ loss / optimiser
+def loss_workspace(rows, device):
+    """Scratch for the fixed-order cross-CTA loss fold of the loss kernels (csn_loss_workspace_bytes)."""
+    n = C.c_size_t()
+    call("csn_loss_workspace_bytes", int(rows), C.byref(n))
+    return torch.empty((n.value,), dtype=torch.uint8, device=device)
+
+
 def dino_loss_fwd_bwd(student, teacher, center, student_temp, teacher_temp, mode, grad_scale=1.0, batch_center=None):
     """student [Vs,B,K] / teacher [Vt,B,K] fp32 (2-D inputs are treated as one view).
     Returns (loss scalar tensor, d_student, batch_center)."""
@@ -260,7 +269,8 @@ def dino_loss_fwd_bwd(student, teacher, center, student_temp, teacher_temp, mode
         n = B * K if mode == _lib.DINO_MULTICROP_REF else K
         batch_center = torch.zeros((n,), dtype=torch.float32, device=s3.device)
     call("csn_dino_loss_fwd_bwd", _p(s3), _p(t3), _p(center), center_rows, float(student_temp), float(teacher_temp),
-         _p(loss), _p(d_student), _p(batch_center), Vs, Vt, B, K, int(mode), float(grad_scale), _stream())
+         _p(loss), _p(d_student), _p(batch_center), Vs, Vt, B, K, int(mode), float(grad_scale),
+         _p(loss_workspace(B, s3.device)), _stream())
     return loss, d_student.view(student.shape), batch_center
 
 
@@ -271,21 +281,27 @@ def head_dino_supported(B, I, K):
 
 def head_dino_fwd_bwd(h_last, w, bias, act, teacher, center, student_temp, teacher_temp, batch_center, grad_scale=1.0):
     """Projection head + single-view DINO loss, forward and backward in one kernel.  h_last [B, I] fp32 or bf16 (the
-    recurrence's own output), w [K, I], teacher [B, K], center [K]; batch_center [K] is ACCUMULATED into.
-    Returns (loss scalar tensor, d_hlast [B, I] fp32, d_pre [B, K] fp32)."""
+    recurrence's own output), w [K, I], teacher [B, K], center [K]; batch_center [K] is ACCUMULATED into (a fixed-order
+    column sum of the teacher after the kernel), or None to skip it (run `colsum(teacher, out, accumulate=True)` wherever
+    it overlaps best).  Returns (loss scalar tensor, d_hlast [B, I] fp32, d_pre [B, K] fp32)."""
     _chk(h_last, None, "h_last"); _chk(w, torch.float32, "w"); _chk(teacher, torch.float32, "teacher")
-    _chk(center, torch.float32, "center"); _chk(batch_center, torch.float32, "batch_center")
+    _chk(center, torch.float32, "center")
+    if batch_center is not None:
+        _chk(batch_center, torch.float32, "batch_center")
     B, I = h_last.shape
     K = w.shape[0]
-    if w.shape[1] != I or tuple(teacher.shape) != (B, K) or center.numel() != K or batch_center.numel() != K:
+    if (w.shape[1] != I or tuple(teacher.shape) != (B, K) or center.numel() != K
+            or (batch_center is not None and batch_center.numel() != K)):
         raise _lib.CsnError("head_dino_fwd_bwd: shapes do not match (h %s, w %s, teacher %s, center %d)"
                             % (tuple(h_last.shape), tuple(w.shape), tuple(teacher.shape), center.numel()))
+    if not head_dino_supported(B, I, K):
+        raise _lib.CsnError("head_dino_fwd_bwd: shape B=%d I=%d K=%d is not served by the fused head kernel" % (B, I, K))
     loss = torch.empty((), dtype=torch.float32, device=w.device)
     d_hlast = torch.empty((B, I), dtype=torch.float32, device=w.device)
     d_pre = torch.empty((B, K), dtype=torch.float32, device=w.device)
     call("csn_head_dino_fwd_bwd", _p(h_last), _dt(h_last.dtype), _p(w), _p(bias), int(act), _p(teacher), _p(center),
          float(student_temp), float(teacher_temp), _p(loss), _p(d_hlast), _p(d_pre), _p(batch_center), B, I, K,
-         float(grad_scale), _stream())
+         float(grad_scale), _p(loss_workspace(B, w.device)), _stream())
     return loss, d_hlast, d_pre
 
 

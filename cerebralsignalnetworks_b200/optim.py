@@ -66,7 +66,9 @@ class FusedAdam:
         self._seg_off = torch.tensor(offs, dtype=torch.int64, device=dev)
         self._n_seg = len(layout)
         self._n_chunks = sum((offs[i + 1] - offs[i] + 2047) // 2048 for i in range(len(layout)))
-        self._sumsq = torch.zeros(len(layout), dtype=torch.float32, device=dev)
+        # squared norms [n_seg] followed by the per-chunk partials they are folded from (fixed order, no atomics)
+        self._sumsq_buf = torch.zeros(len(layout) + self._n_chunks, dtype=torch.float32, device=dev)
+        self._sumsq = self._sumsq_buf[:len(layout)]
         self._layout = layout
 
     def clip_gradients(self, clip):
@@ -75,7 +77,7 @@ class FusedAdam:
         import ctypes as _C
         from . import _lib
         _lib.call("csn_clip_grad_segments", _C.c_void_p(self.flat_g.data_ptr()), _C.c_void_p(self._seg_off.data_ptr()),
-                  self._n_seg, self._n_chunks, _C.c_void_p(self._sumsq.data_ptr()), float(clip),
+                  self._n_seg, self._n_chunks, _C.c_void_p(self._sumsq_buf.data_ptr()), float(clip),
                   _C.c_void_p(torch.cuda.current_stream().cuda_stream))
         return self._sumsq
 

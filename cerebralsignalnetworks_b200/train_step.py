@@ -38,14 +38,23 @@ class DistillTrainStep:
         self.device = dev
 
         # ---- flat parameter / gradient / moment buffers; module parameters become views ----
-        params = [p for p in model.parameters()]
-        offs, total = [], 0
-        for p in params:
-            offs.append(total)
-            total += (p.numel() + 3) // 4 * 4
-        K = loss.center.shape[-1]
+        # Parameters the DINO loss cannot reach (the class head of include_top models) get no gradient in the reference
+        # (p.grad is None: torch's optimiser SKIPS them -- no moments, no weight decay).  They sit behind the optimised
+        # range of the flat buffer, so the fused Adam never touches them.
+        unreached = {id(p) for p in model.classifier.parameters()} if getattr(model, "include_top", False) else set()
+        params = [p for p in model.parameters() if id(p) not in unreached]
+        frozen = [p for p in model.parameters() if id(p) in unreached]
+        offs, n_all = [], 0
+        for i, p in enumerate(params + frozen):
+            if i == len(params):
+                total = n_all  # end of the optimised range
+            offs.append(n_all)
+            n_all += (p.numel() + 3) // 4 * 4
+        if not frozen:
+            total = n_all
         self.n_param = total
-        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        K = loss.center.shape[-1]
+        self.flat_p = torch.zeros(n_all, dtype=torch.float32, device=dev)
         # [grads | sum_b teacher].  Data parallel: the buffer is peer-mapped so that every rank's fused Adam reads all
         # ranks' gradients straight over NVLink (dp_exchange "peer"); "nccl" keeps one ncclAllReduce + local kernels;
         # "auto" tries peer and falls back to nccl when symmetric memory cannot be set up (no P2P / gloo group).
@@ -65,11 +74,15 @@ class DistillTrainStep:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self._grad_views = {}
-        for p, o in zip(params, offs):
+        for p, o in zip(params + frozen, offs):
             view = self.flat_p[o:o + p.numel()].view(p.shape)
             view.copy_(p.data)
             p.data = view
-            self._grad_views[id(p)] = self.flat_g[o:o + p.numel()].view(p.shape)
+            if id(p) in unreached:
+                self._grad_views[id(p)] = torch.zeros_like(view)  # never written: the loss does not reach it
+            else:
+                self._grad_views[id(p)] = self.flat_g[o:o + p.numel()].view(p.shape)
+        self.flat_p_opt = self.flat_p[:total]
         self.batch_center = self.flat_g[total:]
         self.center = loss.center.reshape(-1)
         if self.center.numel() != K:
@@ -158,13 +171,15 @@ class DistillTrainStep:
                 # Linear + loss + d_h in ONE kernel; the head's weight gradient (needs only d_pre and h_T) leaves the
                 # critical path: it runs on a side stream next to the backward recurrence and is joined before Adam
                 loss, d_hlast, d_pre = ops.head_dino_fwd_bwd(h_last, m.output.weight, m.output.bias, act, teacher, self.center,
-                                                             self.loss.student_temp, tau_t, self.batch_center)
+                                                             self.loss.student_temp, tau_t, None)
                 cur = torch.cuda.current_stream()
                 if self._side is None:
                     self._side = torch.cuda.Stream(device=h_last.device)
                 side = self._side
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
+                    # centre statistics sum_b teacher (fixed summation order), also off the critical path
+                    ops.colsum(teacher, out=self.batch_center, accumulate=True)
                     h32 = h_last if h_last.dtype == torch.float32 else ops.cast(h_last, torch.float32)
                     ops.gemm_f32(d_pre, h32, True, False, out=self.grad_of(m.output.weight), rowsum=self.grad_of(m.output.bias))
             else:
@@ -176,15 +191,12 @@ class DistillTrainStep:
         grads = [tuple(self.grad_of(w) for w in layer) for layer in layers]
         with self._stage("encoder_bwd"):
             encoder_bwd(d_hlast, layers, saved, grads, cd)
-        if m.include_top:  # the DINO loss does not reach the class head: zero gradient
-            self.grad_of(m.classifier.weight).zero_()
-            self.grad_of(m.classifier.bias).zero_()
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)  # the head's dW / db are in the gradient buffer
         if self.peer is not None:
             with self._stage("adam_center"):  # all-reduce + Adam + centre EMA in one kernel over peer memory
                 pe = self.peer
-                ops.dp_adam_step_peer(self.flat_p, self.exp_avg, self.exp_avg_sq, pe.grad_ptrs, pe.flag_ptrs, self.world,
+                ops.dp_adam_step_peer(self.flat_p_opt, self.exp_avg, self.exp_avg_sq, pe.grad_ptrs, pe.flag_ptrs, self.world,
                                       pe.rank, self.center, self.loss.center_momentum, 1.0 / (B * self.world),
                                       self._step_dev, pe.ticket, self.lr, self.betas[0], self.betas[1], self.eps,
                                       self.weight_decay, self.decoupled, grad_scale=1.0 / self.world)
@@ -192,7 +204,7 @@ class DistillTrainStep:
         with self._stage("allreduce"):
             dp.allreduce_flat_(self.flat_g)  # gradients and centre statistics in one NCCL call
         with self._stage("adam_center"):
-            ops.adam_step_graph(self.flat_p, self.flat_g[:self.n_param], self.exp_avg, self.exp_avg_sq, self._step_dev,
+            ops.adam_step_graph(self.flat_p_opt, self.flat_g[:self.n_param], self.exp_avg, self.exp_avg_sq, self._step_dev,
                                 self._adam_consts, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                 self.decoupled, grad_scale=1.0 / self.world)
             ops.center_ema(self.center, self.batch_center, self.loss.center_momentum, 1.0 / (B * self.world))
@@ -200,7 +212,9 @@ class DistillTrainStep:
 
     def step(self, eeg_bct, teacher_feats, epoch=0):
         """eeg_bct: float32 [B, C, T] on the GPU (raw trials, stored layout); teacher_feats: float32 [B, K].
-        Returns the loss as a 0-d device tensor (no host sync)."""
+        Returns the loss as a 0-d device tensor (no host sync).  ALIASING: on the CUDA-graph path this is the graph's
+        static output tensor -- the next step() overwrites it.  Consume it (add it to a running sum, .item(), .clone())
+        before the next call; do not collect the returned tensors in a list."""
         tau_t = float(self.loss.teacher_temp_schedule[epoch])
         self.step_count += 1
         if not self.use_cuda_graph or self._stage_events is not None:

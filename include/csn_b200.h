@@ -13,6 +13,9 @@
  *     aligned, unless the parameter says "host".  The library never allocates device memory in the step
  *     path; scratch is passed in (sizes come from the *_bytes queries).
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), and thread-safe across streams.
+ *   - NO floating-point atomics: every cross-CTA sum (loss scalars, centre column sums, bias / weight gradients,
+ *     split-K products) is folded in a fixed order, so the same inputs give the same bits on every run -- like the
+ *     reference's CPU reductions.  Entry points that need scratch for that take a `workspace` pointer.
  *   - tensors are row-major; "time-major" means [T, B, *].
  */
 #ifndef CSN_B200_H_
@@ -25,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CSN_VERSION 100 /* round 1 */
+#define CSN_VERSION 200 /* round 2: deterministic reductions (workspace arguments), overlapped recurrence */
 
 enum { CSN_OK = 0, CSN_EINVAL = -1, CSN_ECUDA = -2, CSN_EUNSUPPORTED = -3, CSN_EARCH = -4 };
 enum { CSN_F32 = 0, CSN_BF16 = 1 };
@@ -67,7 +70,7 @@ int csn_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const
 int csn_gemm_f32_rowsum(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                         const float* B, int ldb, float beta, float* C, int ldc, const float* bias, int act,
                         float* rowsum, int rowsum_accumulate, void* stream);
-/* out[n] (+)= sum_m x[m, n]   (bias gradients) */
+/* out[n] (+)= sum_m x[m, n]   (bias gradients, DINO centre column sums); fixed summation order */
 int csn_colsum_f32(const float* x, float* out, int M, int N, int ldx, int accumulate, void* stream);
 /* y = act(x); dx = dy * act'(x)  (x is the PRE-activation) */
 int csn_act_fwd(const float* x, float* y, size_t n, int act, void* stream);
@@ -85,10 +88,13 @@ int csn_weight_norm_bwd(const float* v, const float* g, const float* inv_norm, c
 
 /* ---- tensor-core GEMM (tcgen05 / TMEM / TMA, bf16 operands, fp32 accumulate) ----------------------------
  * D[M,N] (fp32 or bf16) = op(A) * op(B) (+ bias[N]); same op() convention as csn_gemm_f32 but A and B are bf16.
- * split_k > 1 accumulates partial products with fp32 atomics into a zeroed / pre-loaded D (fp32 only).
+ * accumulate != 0 adds into D (fp32 only).  split_k > 1 (fp32 only) cuts the contraction into split_k ranges: each range
+ * stores its partial product to its own slab of `workspace` (>= split_k * M * N floats, required then, else may be NULL)
+ * and a second kernel adds the slabs in range order.
  * Used for the hoisted LSTM input projection, dW / dX of BPTT and the DINO head. */
 int csn_gemm_bf16_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
-                     void* D, int ldd, int d_dtype, const float* bias, int accumulate, int split_k, void* stream);
+                     void* D, int ldd, int d_dtype, const float* bias, int accumulate, int split_k, void* workspace,
+                     void* stream);
 
 /* ---- LSTM encoder layer ---------------------------------------------------------------------------------
  * Replaces torch.nn.LSTM inside the (missing) models.lstm.Model -- call sites LstmDistillFromDinoV2Train.py:323,365;
@@ -119,12 +125,14 @@ int csn_lstm_layer_bwd(const void* x, const float* w_ih, const float* w_hh, cons
  * DINO (dino/main_dino.py:428-481) as MULTICROP_CANONICAL.
  * student [Vs,B,K], teacher [Vt,B,K] fp32; center [K] (center_rows==1) or [B,K] (center_rows==B, the
  * reference's post-first-step shape).  loss: device scalar, overwritten.  d_student [Vs,B,K] = dLoss/dstudent
- * * grad_scale.  batch_center: SINGLE/CANONICAL -> [K] += sum over (view,row) of teacher (caller zeroes);
- * MULTICROP_REF -> [B,K] = sum over views.  The EMA itself is csn_center_ema. */
+ * * grad_scale.  batch_center: SINGLE/CANONICAL -> [K] += sum over (view,row) of teacher (caller zeroes; may be NULL);
+ * MULTICROP_REF -> [B,K] = sum over views.  The EMA itself is csn_center_ema.
+ * workspace: csn_loss_workspace_bytes(B) bytes of scratch for the fixed-order loss fold (contents irrelevant). */
+int csn_loss_workspace_bytes(int rows, size_t* bytes);
 int csn_dino_loss_fwd_bwd(const float* student, const float* teacher, const float* center, int center_rows,
                           float student_temp, float teacher_temp, float* loss, float* d_student,
                           float* batch_center, int Vs, int Vt, int B, int K, int mode, float grad_scale,
-                          void* stream);
+                          void* workspace, void* stream);
 /* center = center*momentum + batch_center*scale*(1-momentum)   (scale = 1/(rows*world)) */
 int csn_center_ema(float* center, const float* batch_center, size_t n, float momentum, float scale, void* stream);
 
@@ -156,7 +164,12 @@ int csn_lstm_set_cta_budget(int max_ctas);
  * is the device-side count of completed steps (advanced by the call); ticket is one zero-initialised device word (CTA arrival
  * counter).
  * csn_dp_wait_done_zero must run on the stream before a rank writes the next step's gradients: it waits until every
- * peer has finished reading the previous ones, then zeroes n floats at zero_ptr (the centre-sum tail). */
+ * peer has finished reading the previous ones, then zeroes n floats at zero_ptr (the centre-sum tail).
+ * Watchdog: a flag wait longer than CSN_DP_TIMEOUT_S seconds (environment, default 600, 0 = no limit) records
+ * (1, rank, flag index, awaited epoch) in a pinned host slot and traps; csn_dp_last_timeout copies the slot to out4
+ * (host int[4]; out4[0] == 0: no timeout so far).  Ranks may therefore drift apart by up to that long between steps (a
+ * rank-0-only checkpoint or evaluation); put a barrier in front of anything longer. */
+int csn_dp_last_timeout(int* out4);
 int csn_dp_wait_done_zero(const void* flags_local, int world, const int* step_counter, float* zero_ptr, size_t n,
                           void* stream);
 int csn_dp_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, size_t n_param,
@@ -171,13 +184,15 @@ int csn_dp_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, size
  * -- the teacher probabilities are log-softmaxed once more and the student probabilities are the soft target, as
  * written in the reference.  student/teacher [B,K] fp32 (K <= 1024), pred [B,n_classes] fp32 or NULL, label [B] int64.
  * loss: device scalar (overwritten); d_student [B,K], d_pred [B,n_classes] = gradients * grad_scale.
+ * workspace (all three losses below): csn_loss_workspace_bytes(B) bytes of scratch for the fixed-order loss fold.
  * CosineSimilarityLoss.forward (LstmDistillFromDinoV2Train.py:36-43): loss = 1 - mean_b cos(student_b, teacher_b),
  * nn.CosineSimilarity semantics (dim 1, each norm clamped at eps). */
 int csn_feature_dist_loss_fwd_bwd(const float* student, const float* teacher, const float* pred, const long long* label,
                                   float* loss, float* d_student, float* d_pred, int B, int K, int n_classes,
-                                  float temperature, float alpha, float beta, float grad_scale, void* stream);
+                                  float temperature, float alpha, float beta, float grad_scale, void* workspace,
+                                  void* stream);
 int csn_cosine_loss_fwd_bwd(const float* student, const float* teacher, float* loss, float* d_student, int B, int K,
-                            float eps, float grad_scale, void* stream);
+                            float eps, float grad_scale, void* workspace, void* stream);
 /* loss_fn_kd of the older training scripts (LSTMDistillRetreival.py:40-70, LstmDistillFromDinoV2TrainSpampinato.py:107-121):
  *   loss = c_kl * sum_b KL(softmax(teacher_b / T) || softmax(student_b / T)) + c_sl1 * sum_{b,k} smooth_l1(student - teacher)
  *        + c_ce * sum_b cross_entropy(student_b, label_b)
@@ -185,20 +200,24 @@ int csn_cosine_loss_fwd_bwd(const float* student, const float* teacher, float* l
  * c_kl = w_soft T^2 / B, c_sl1 = w_ce / (B K), c_ce = 0; Spampinato: c_kl = alpha T^2 / (B K), c_ce = (1 - alpha) / B.
  * label [B] int64, may be NULL when c_ce == 0.  K <= 1024.  d_student [B,K] = gradient * grad_scale. */
 int csn_kd_loss_fwd_bwd(const float* student, const float* teacher, const long long* label, float* loss, float* d_student,
-                        int B, int K, float temperature, float c_kl, float c_sl1, float c_ce, float grad_scale, void* stream);
+                        int B, int K, float temperature, float c_kl, float c_sl1, float c_ce, float grad_scale,
+                        void* workspace, void* stream);
 
 /* ---- projection head + single-view DINO loss, forward and backward in one kernel ----------------------------------
  * The chain `output = Linear(h_T)` -> DINOLoss.forward -> d_output -> d_h_T of LstmDistillFromDinoV2Train.py:365-375 for the
  * narrow heads (K <= 1024 targets on an I <= 128-wide encoder; csn_head_dino_supported says whether a shape is served):
  *   pre = W h + bias, emb = act(pre) (CSN_ACT_NONE / CSN_ACT_RELU); loss = mean_b CE(softmax((t - c) / tau_t), emb / tau_s)
- *   d_pre [B,K] = dLoss/dpre * grad_scale, d_hlast [B,I] = d_pre W, batch_center [K] += sum_b teacher (caller zeroes it).
+ *   d_pre [B,K] = dLoss/dpre * grad_scale, d_hlast [B,I] = d_pre W, batch_center [K] += sum_b teacher (caller zeroes it;
+ *   NULL skips it: a caller that wants it off the critical path runs csn_colsum_f32 over the teacher on another stream).
  * h_last [B,I] in h_dtype (CSN_F32 / CSN_BF16: the recurrence's own output, no cast pass), W [K,I], bias [K] or NULL,
  * teacher [B,K], center [K].  loss: device scalar (overwritten).  The weight gradient dW = d_pre^T h, db = sum_b d_pre is
- * left to the caller (csn_gemm_f32_rowsum): it is off the critical path of the step. */
+ * left to the caller (csn_gemm_f32_rowsum): it is off the critical path of the step.
+ * workspace: csn_loss_workspace_bytes(B) bytes of scratch for the fixed-order loss fold. */
 int csn_head_dino_supported(int B, int I, int K);
 int csn_head_dino_fwd_bwd(const void* h_last, int h_dtype, const float* W, const float* bias, int act, const float* teacher,
                           const float* center, float student_temp, float teacher_temp, float* loss, float* d_hlast,
-                          float* d_pre, float* batch_center, int B, int I, int K, float grad_scale, void* stream);
+                          float* d_pre, float* batch_center, int B, int I, int K, float grad_scale, void* workspace,
+                          void* stream);
 
 /* ---- GPU-resident dataset batches ------------------------------------------------------
  * src [N, C, T_raw] fp32: the stacked "eeg" tensors of the .pth file ConvertToPth.py:170-201 writes.  For every b:
@@ -237,20 +256,10 @@ int csn_ema_update(float* dst, const float* src, size_t n, float momentum, void*
 
 /* Per-parameter gradient clipping without host syncs (utils/utils.py:132-141).  The flat gradient buffer is cut into
  * n_seg segments [seg_off[i], seg_off[i+1]) (device int64 array of n_seg+1 offsets); n_chunks = sum_i ceil(len_i/2048);
- * sumsq_dev: n_seg floats of scratch, left holding the squared norms (the norms the reference returns). */
+ * sumsq_dev: n_seg + n_chunks floats of scratch; the first n_seg are left holding the squared norms (the norms the
+ * reference returns), the rest the per-chunk partial sums they were folded from (chunk order, no atomics). */
 int csn_clip_grad_segments(float* grads, const long long* seg_off_dev, int n_seg, long long n_chunks, float* sumsq_dev,
                            float clip, void* stream);
-
-/* ---- bring-up / self-test hooks (tests only) --------------------------------------------------------------
- * One tcgen05.mma tile D[128,N] = A[128,K] * B[N,K]^T with operands staged in the no-swizzle canonical layouts
- * the recurrence kernel uses; a_mn_major / b_mn_major exercise the MN-major descriptors. */
-int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, int K, int a_mn_major, int b_mn_major, void* stream);
-/* a_mn_major = 2 stages A in tensor memory instead (the TS form the recurrence uses for the resident W_hh).
- * csn_dbg_lstm_profile_buffer: device buffer of >= 2*64*8 + 16 int64 that receives clock64 stamps of the first 64 forward
- * ([0,512)) and backward ([512,1024)) recurrence steps of CTA 0 (NULL switches the stamps off). */
-int csn_dbg_lstm_profile_buffer(long long* buf);
-/* tcgen05.mma issue/completion cost microbenchmark: out[2*rep] = issue cycles, out[2*rep+1] = cycles until commit arrives */
-int csn_dbg_umma_bench(long long* out, int M, int N, int n_acc, int a_mode, int reps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,10 +39,32 @@ def test_binding_table_matches_header():
         assert n_args == len(argtypes), "%s: header has %d args, binding %d" % (name, n_args, len(argtypes))
 
 
+def test_debug_hooks_stay_out_of_the_product_header():
+    """The bring-up hooks are declared in include/csn_b200_debug.h only (and are exported for the tests that use them)."""
+    from cerebralsignalnetworks_b200 import _lib
+    assert not [n for n in declared_functions() if n.startswith("csn_dbg_")]
+    dbg = open(os.path.join(ROOT, "include", "csn_b200_debug.h")).read()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _lib.DEBUG_SIGNATURES:
+        assert name in dbg and hasattr(lib, name)
+
+
+def test_no_float_atomics_in_the_library():
+    """Every cross-CTA sum is a fixed-order fold: the CUDA sources hold no float atomicAdd / red.global.add.f32."""
+    csrc = os.path.join(ROOT, "cerebralsignalnetworks_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith((".cu", ".cuh")):
+            continue
+        code = re.sub(r"//[^\n]*", "", open(os.path.join(csrc, f)).read())
+        assert "red.global.add" not in code, f
+        for m in re.finditer(r"atomicAdd\(([^;]*);", code):
+            assert "ticket" in m.group(1), "%s: atomicAdd on something other than an arrival ticket: %s" % (f, m.group(0))
+
+
 def test_version_and_error_string():
     from cerebralsignalnetworks_b200 import _lib
     lib = _lib.load()
-    assert lib.csn_version() == 100
+    assert lib.csn_version() == 200
     assert isinstance(lib.csn_last_error(), bytes)
 
 

@@ -38,7 +38,12 @@ def test_fused_head_matches_unfused_kernels(B, I, K, act, dtype):
     for got, want in ((d_h, r_dh), (d_pre, r_dpre)):
         scale = want.abs().max().item()
         assert (got - want).abs().max().item() <= 2e-4 * scale + 1e-12
-    np.testing.assert_allclose(bc.cpu().numpy(), r_bc.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # centre statistics: both paths are the SAME fixed-order column sum now (bit-equal), and within the fp32 bound of
+    # a B-term sum, B * u * max|t| (u = 2^-24), of the float64 column sum
+    assert torch.equal(bc, r_bc)
+    exact = teacher.double().sum(0).cpu().numpy()
+    bound = B * 2.0 ** -24 * teacher.abs().max().item()
+    assert np.abs(bc.cpu().numpy().astype(np.float64) - exact).max() <= bound
 
 
 def test_fused_head_matches_oracle_autograd():
@@ -62,7 +67,8 @@ def test_fused_head_matches_oracle_autograd():
                                              teacher.cuda(), center.cuda(), ts, tt, bc)
     np.testing.assert_allclose(loss.item(), ref.item(), rtol=2e-5)
     np.testing.assert_allclose(d_h.cpu().numpy(), hh.grad.numpy(), rtol=2e-3, atol=2e-4 * hh.grad.abs().max().item())
-    np.testing.assert_allclose(bc.cpu().numpy(), teacher.sum(0).numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(bc.cpu().numpy(), teacher.double().sum(0).numpy(), rtol=0,
+                               atol=B * 2.0 ** -24 * teacher.abs().max().item())
     # dW from d_pre: what the train step computes on its side stream
     dw = ops.gemm_f32(d_pre, h.cuda(), True, False)
     np.testing.assert_allclose(dw.cpu().numpy(), lin.weight.grad.numpy(), rtol=2e-3, atol=2e-4 * lin.weight.grad.abs().max().item())
@@ -73,6 +79,7 @@ def test_unserved_head_shapes_are_refused():
     from cerebralsignalnetworks_b200 import ops
     assert not ops.head_dino_supported(8, 512, 768)   # W does not fit in shared memory
     assert not ops.head_dino_supported(8, 100, 64)    # encoder width not a multiple of 32
+    assert not ops.head_dino_supported(8, 2048, 8)    # one thread per input column: at most 1024
     z = torch.zeros
     with pytest.raises(csn.CsnError):
         ops.head_dino_fwd_bwd(z(8, 512, device="cuda"), z(768, 512, device="cuda"), z(768, device="cuda"), 0,
