@@ -66,6 +66,7 @@ DEBUG_SIGNATURES = {
     "csn_dbg_umma_tile": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "csn_dbg_lstm_profile_buffer": [_vp],
     "csn_dbg_umma_bench": [_vp, _i, _i, _i, _i, _i, _vp],
+    "csn_dbg_store_bw": [_vp, _vp, _sz, _i, _i, _i, _vp],
 }
 EXTRA_SYMBOLS = ["csn_version", "csn_last_error", "csn_launch_count"]
 

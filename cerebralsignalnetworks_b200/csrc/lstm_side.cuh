@@ -111,6 +111,13 @@ struct XpServe {
   unsigned* flags;  // [n_tiles], zeroed before the launch; 1 = the tile's rows of Xp are in memory
 };
 
+// rows per TMA box of the W_ih image: the largest of 256 / 128 / 64 that divides 4H (H % 16 == 0), or 4H itself when it
+// fits one box -- a box never reaches past the last gate row, so the shared-memory image is exactly 4H rows
+__host__ __device__ inline int xp_w_box_rows(int H) {
+  const int n = 4 * H;
+  if (n <= 256) return n;
+  return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64);
+}
 constexpr int kSrvStages = 3;                    // x ring: 128 rows x 64 columns (one K chunk of one tile) per stage
 constexpr uint32_t kSrvStageBytes = 128 * 128;   // 128 rows x 128 B
 __host__ __device__ inline size_t xp_server_smem(int H) {
@@ -157,7 +164,7 @@ __device__ __forceinline__ void xp_server_role(uint8_t* smem_raw, const CUtensor
     if (lane == 0) {
       // W_ih once: per K chunk, 4H rows in boxes of (up to) 256 rows
       mbar_arrive_expect_tx(w_full, uint32_t(nkc) * w_chunk_bytes);
-      const int box_rows = 4 * H < 256 ? 4 * H : 256;
+      const int box_rows = xp_w_box_rows(H);
       for (int kc = 0; kc < nkc; ++kc)
         for (int r0 = 0; r0 < 4 * H; r0 += box_rows)
           tma_load_2d(ws + size_t(kc) * w_chunk_bytes + size_t(r0) * 128, tm_w, w_full, kc * 64, r0);
@@ -242,27 +249,31 @@ struct DwConsume {
   int m_halves;      // 1 (4H <= 256) or 2: a consumer owns 256 of the 4H gate rows
   int T, B, I, H;
   int i_pad;         // ceil(I / 64) * 64: column of the first h_{t-1} feature in the [x | h] operand
+  int c_lo;          // first 64-row chunk the consumers take; rows below c_lo * 64 (the LAST timesteps BPTT reaches) are
+                     // left to a GEMM after the launch, so that the consumers finish together with the chain
   unsigned* done;    // [T], zeroed before the launch
   float* slabs;      // [n_groups][512 rows (interleaved gate index 4u + g)][256 columns] fp32 partial dW
 };
 constexpr int kConsStages = 3;
 constexpr uint32_t kConsABytes = 256 * 64 * 2, kConsBBytes = 256 * 64 * 2;  // per 64-row chunk: dG^T half, [x | h]
 constexpr uint32_t kConsStageBytes = kConsABytes + kConsBBytes;
-__host__ __device__ inline size_t dw_consumer_smem() {
-  return 1024 + size_t(kConsStages) * kConsStageBytes + size_t(8) * 32 * kEpiTileStride * 4 + 256;
+__host__ __device__ inline size_t dw_consumer_smem() {  // (the final drain stages through the idle operand ring)
+  return 1024 + size_t(kConsStages) * kConsStageBytes + 256;
 }
 __host__ __device__ inline size_t dw_slab_floats() { return size_t(512) * 256; }
 
-// blockDim >= 320: warp 8 MMA issuer (+ tensor-memory owner), warp 9 TMA producer, warps 0-7 drain the accumulators at
-// the end.  cons = index of this consumer in [0, n_cons): M half = cons % m_halves, K group = cons / m_halves.
+// blockDim >= 320: warp 8 MMA issuer (+ tensor-memory owner); warps 0-7 are the TMA producers -- ONE 64 x 64 box of the
+// stage each (a TMA instruction blocks its issuing warp for a few hundred cycles: eight boxes from one thread cost more
+// than the stage's MMAs) -- and drain the accumulators at the end.
+// cons = index of this consumer in [0, n_cons): M half = cons % m_halves, K group = cons / m_halves.
 // The contraction runs over the rows (t, b) of dG in 64-row chunks, DESCENDING (the order BPTT produces them in);
 // group g takes every n_groups-th chunk.
 __device__ __forceinline__ void dw_consumer_role(uint8_t* smem_raw, const CUtensorMap* tm_dg, const CUtensorMap* tm_x,
                                                  const CUtensorMap* tm_h, const DwConsume& dc, int cons) {
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = base;
-  float* epi = reinterpret_cast<float*>(stages + size_t(kConsStages) * kConsStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi) + 8 * 32 * kEpiTileStride * 4);
+  float* epi = reinterpret_cast<float*>(stages);  // the accumulators are drained after the last MMA has read the ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + size_t(kConsStages) * kConsStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kConsStages;
   uint64_t* acc_full = empty + kConsStages;
@@ -271,47 +282,60 @@ __device__ __forceinline__ void dw_consumer_role(uint8_t* smem_raw, const CUtens
   const int mh = cons % dc.m_halves, grp = cons / dc.m_halves, n_groups = dc.n_cons / dc.m_halves;
   const int rows = dc.T * dc.B;
   const int n_chunks = (rows + 63) / 64;
-  // chunks of this group: q = grp, grp + n_groups, ... in descending-row order; chunk index c = n_chunks - 1 - q
-  const int my_chunks = n_chunks > grp ? (n_chunks - 1 - grp) / n_groups + 1 : 0;
+  // chunks of this group: q = grp, grp + n_groups, ... in descending-row order; chunk index c = n_chunks - 1 - q >= c_lo
+  const int n_mine = n_chunks - dc.c_lo;
+  const int my_chunks = n_mine > grp ? (n_mine - 1 - grp) / n_groups + 1 : 0;
 
   if (tid == 0) {
     for (int i = 0; i < kConsStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 9 && lane == 0) { prefetch_tmap(tm_dg); prefetch_tmap(tm_x); prefetch_tmap(tm_h); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(tm_dg); prefetch_tmap(tm_x); prefetch_tmap(tm_h); }
   if (warp == 8) tmem_alloc(tmem_slot, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 9) {
+  if (warp < 8) {
     if (lane == 0) {
+      // box `warp` of every stage.  A = dG^T (MN-major): boxes 0-3 = four 64 (gate rows) x 64 (t,b rows) tiles; B = [x | h_{t-1}]
+      // (MN-major): boxes 4-7 = 64-column tiles, x first, then h shifted back by one timestep (rows of t = 0 read out of
+      // bounds: zero fill = h_{-1} = 0).  Box 0's thread also posts the stage's byte count.
+      const int j = warp & 3;
+      // Every recurrence CTA publishes its steps in descending t, so done[t] == n_rec implies the same for every later
+      // timestep: ONE flag per chunk (its earliest timestep), and none while the chunk lies above the lowest timestep
+      // already seen complete.  A consumer that is behind looks eight timesteps further down in the same round trip.
+      int known_t = dc.T;  // timesteps >= known_t are complete
       for (int i = 0; i < my_chunks; ++i) {
         const int c = n_chunks - 1 - (grp + i * n_groups);
-        const int r0 = c * 64, r1 = min(rows, r0 + 64) - 1;
-        // every recurrence CTA has published the dG rows of the timesteps this chunk touches
-        for (int t = r0 / dc.B; t <= r1 / dc.B; ++t) wait_ge(dc.done + t, (unsigned)dc.n_rec);
-        fence_proxy_async_all();
+        const int r0 = c * 64;
+        const int t_lo = r0 / dc.B;
+        if (t_lo < known_t) {
+          const int t_far = max(0, t_lo - 8);
+          const bool far_ok = ld_acquire_gpu(dc.done + t_far) >= (unsigned)dc.n_rec;
+          if (!far_ok) wait_ge(dc.done + t_lo, (unsigned)dc.n_rec);
+          known_t = far_ok ? t_far : t_lo;
+          fence_proxy_async_all();
+        }
         const uint32_t s = uint32_t(i) % kConsStages;
         if (i >= kConsStages) mbar_wait(&empty[s], ((uint32_t(i) / kConsStages) - 1) & 1);
         uint8_t* sa = stages + size_t(s) * kConsStageBytes;
         uint8_t* sb = sa + kConsABytes;
-        mbar_arrive_expect_tx(&full[s], kConsStageBytes);
-        // A = dG^T (MN-major): four 64 (gate rows) x 64 (t,b rows) boxes; B = [x | h_{t-1}] (MN-major): 64-column boxes,
-        // x first, then h shifted back by one timestep (rows of t = 0 read out of bounds: zero fill = h_{-1} = 0)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * 8192, tm_dg, &full[s], mh * 256 + j * 64, r0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        if (warp == 0) mbar_arrive_expect_tx(&full[s], kConsStageBytes);
+        if (warp < 4) {
+          tma_load_2d(sa + j * 8192, tm_dg, &full[s], mh * 256 + j * 64, r0);
+        } else {
           const int col = j * 64;
           if (col < dc.i_pad) tma_load_2d(sb + j * 8192, tm_x, &full[s], col, r0);
           else tma_load_2d(sb + j * 8192, tm_h, &full[s], col - dc.i_pad, r0 - dc.B);
         }
       }
     }
-  } else if (warp == 8) {
+    __syncwarp();
+  }
+  if (warp == 8) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, 256, 1, 1);
       for (int i = 0; i < my_chunks; ++i) {
@@ -333,7 +357,8 @@ __device__ __forceinline__ void dw_consumer_role(uint8_t* smem_raw, const CUtens
       }
       umma_commit(acc_full);
     }
-  } else if (warp < 8) {
+  }
+  if (warp < 8) {
     // partial dW of this (group, M half): lanes = gate rows, 256 columns -> slab rows mh*256 + mt*128 + lane
     const int q = warp & 3, mt = warp >> 2;
     float* tile_s = epi + warp * (32 * kEpiTileStride);

@@ -26,6 +26,7 @@
 
 #include "tc.cuh"
 #include "gemm_tc.cuh"
+#include "lstm_side.cuh"
 
 namespace csn {
 
@@ -36,8 +37,10 @@ using namespace tc;
 // warps 8-9); forward warp 9: projection loader / issuer; backward warp 10: TMA producer of the per-step inputs.
 constexpr int kEpiWarps = 8, kIssuerWarp = 8;
 constexpr int kRecThreads = (kEpiWarps + 1) * 32;     // forward: one issuer warp
-constexpr int kRecThreadsBwd = (kEpiWarps + 2) * 32;  // backward: two issuer warps (see issue_bwd)
-constexpr int kBwdThreads = kRecThreadsBwd + 32;      // + the TMA producer warp of the per-step BPTT inputs
+constexpr int kRecThreadsBwd = (kEpiWarps + 2) * 32;  // backward: two issuer warps (see issue_bwd); forward: issuer + feeder warp
+constexpr int kBwdThreads = kRecThreadsBwd + 64;      // + the TMA producer warp of the per-step BPTT inputs + the publisher warp
+constexpr int kDgBatch = 4;                           // backward: steps published to the dW consumers per gpu-scope release
+constexpr int kDgLag = 6;                             // backward: a step's dG is published to the dW consumers this many steps later
 // epilogue -> issuer hand-off: hardware named barrier 1 over all threads (the 256 epilogue threads ARRIVE without
 // blocking, the issuer warp(s) SYNC); ~2x lower latency than an mbarrier round trip, measured on the step stamps.
 template <int NTHREADS>
@@ -60,6 +63,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
+constexpr uint32_t kBarBlock = 256;  // mbarriers + shared-memory step counters between the MMA operand and the rings
 struct RecSmem {
   uint8_t* opb;       // B operand: h^T (fwd, KP/8 * 256 B) or dG^T (bwd, 4KP/8 * 256 B), canonical K-major
   uint64_t* bar_in;   // (unused since the named-barrier hand-off; kept initialised)
@@ -85,7 +89,7 @@ __device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t b_bytes) {
   s.bar_xp = s.bar_pf + kPfStages;
   s.bar_w = s.bar_xp + 2;
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_w + 1);
-  s.ring = s.opb + b_bytes + 128;
+  s.ring = s.opb + b_bytes + kBarBlock;
   return s;
 }
 
@@ -142,19 +146,18 @@ __device__ __forceinline__ void pack_whh_element(const float* __restrict__ w_hh,
   img[(size_t(cp >> 6) * 128 + lane) * 64 + (cp & 63)] = *reinterpret_cast<uint32_t*>(&bb);
 }
 
-// ONE preparation launch per layer call: the W_hh tensor-memory image, plus (forward, fused projection) the W_ih
-// shared-memory image, or (backward) the zeroing of the bias-gradient accumulators -- three tiny launches folded into
-// one (each boundary costs ~2.5 us of a 600 us step).
+// ONE preparation launch per layer call: the W_hh tensor-memory image, plus (forward) W_ih as the fused projection's
+// shared-memory image or as the plain bf16 [4H, I] matrix the Xp servers' TMA reads, plus the zeroing of the launch's
+// flag words (Xp tile READY flags / per-timestep dG publication counters) -- tiny launches folded into one (each
+// boundary costs ~2.5 us of the step).
 __global__ void lstm_prepare_kernel(const float* __restrict__ w_hh, uint32_t* __restrict__ whh_img, int H, int transposed,
                                     const float* __restrict__ w_ih, __nv_bfloat16* __restrict__ wih_img, int I, int KI,
-                                    float* __restrict__ zero_a, float* __restrict__ zero_b, int n_zero) {
+                                    __nv_bfloat16* __restrict__ wih_bf, unsigned* __restrict__ zero_words, int n_zero) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   pack_whh_element(w_hh, whh_img, H, transposed, idx);
   if (wih_img) pack_wih_element(w_ih, wih_img, H, I, KI, idx);
-  if (idx < n_zero) {
-    if (zero_a) zero_a[idx] = 0.f;
-    if (zero_b) zero_b[idx] = 0.f;
-  }
+  if (wih_bf && idx < 4 * H * I) wih_bf[idx] = __float2bfloat16_rn(w_ih[idx]);
+  if (zero_words && idx < n_zero) zero_words[idx] = 0u;
 }
 
 // image -> tensor memory: thread `row` (TMEM lane) copies its 4 x 64 packed columns
@@ -229,24 +232,40 @@ __device__ __forceinline__ void issue_bwd(uint32_t base, uint64_t db0, uint32_t 
 // n into the second of two Xp accumulator sets in tensor memory; the epilogue adds its column of the current set
 // with one more tcgen05.ld per gate.  No Xp round trip through HBM (230 MB written + read per cfg2 step), no separate
 // projection GEMM.
-template <int NV, int KSTEPS, bool FX>
+// Three ways the input projection x_t W_ih^T reaches the chain:
+//   FX           : this CTA computes it on its own tensor pipe between the recurrent MMAs (any SM budget);
+//   !FX, servers : the launch's spare CTAs (blocks [0, sv.n_srv)) compute it concurrently, tile by tile in time order
+//                  (lstm_side.cuh); warp 9 of every recurrence CTA waits on the tiles' READY flags and pulls the CTA's
+//                  rows through the TMA ring -- the chain carries no projection MMAs at all;
+//   !FX, no servers: a GEMM computed Xp before the launch (inputs wider than 128 features).
+// PROF compiles the clock64 stamps of scripts/prof_lstm_steps.py in; the shipped instantiations carry none.
+template <int NV, int KSTEPS, bool FX, bool PROF>
 __global__ void __launch_bounds__(kRecThreadsBwd, 1)
-lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_img, const float* __restrict__ b_hh,
+lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const side::XpServe sv,
+                   const float* __restrict__ xp, const uint32_t* __restrict__ w_img, const float* __restrict__ b_hh,
                    __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
                    int T, int B, int H, int KP, long long* __restrict__ prof, const uint32_t uz,
                    const __nv_bfloat16* __restrict__ x_in, const uint8_t* __restrict__ wih_img,
                    const float* __restrict__ b_ih, int I, int KI) {
-  // FX adds warp 9: the input-projection issuer / x loader, with its own uniform register file (sharing the
-  // recurrent issuer's warp pushed that warp's MMA operands out of uniform registers: one R2UR per MMA on the chain)
-  constexpr int kThreads = FX ? kRecThreadsBwd : kRecThreads;
+  // Warp 9 is the chain's feeder.  FX: the input-projection issuer / x loader, with its own uniform register file
+  // (sharing the recurrent issuer's warp pushed that warp's MMA operands out of uniform registers: one R2UR per MMA on
+  // the chain).  !FX: the TMA producer of the Xp ring.
+  constexpr int kThreads = kRecThreadsBwd;
   constexpr int kXWarp = kIssuerWarp + 1;
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  if constexpr (!FX) {
+    if ((int)blockIdx.x < sv.n_srv) {
+      side::xp_server_role(smem_raw, &tm_x, &tm_w, sv, (int)blockIdx.x);
+      return;
+    }
+  }
+  const int cta = FX ? (int)blockIdx.x : (int)blockIdx.x - sv.n_srv;  // recurrence CTA index
   const size_t b_bytes = size_t(KP / 8) * kLboB;
   RecSmem sm = carve(smem_raw, b_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b0 = blockIdx.x * NV;
+  const int b0 = cta * NV;
   const int ksteps = KP / 16;
-  const bool phase_prof = prof && blockIdx.x == 0 && tid == 0;
+  const bool phase_prof = PROF && prof && cta == 0 && tid == 0;
   if (phase_prof) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -300,39 +319,50 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
     constexpr uint32_t idesc = make_idesc_bf16(128, kNslots, 0, 0);
     const uint64_t db0 = make_smem_desc(smem_u32(sm.opb), kLboB, kSboB, kLayoutNone);
     const bool base0 = (tmem_base == 0);  // a 512-column allocation owns the whole TMEM: constant addresses
-    // This warp is also the TMA producer of the hoisted input projection: the NV rows Xp[t][b0..b0+NV) (4H floats
-    // each, contiguous) are bulk-copied into a 4-stage shared-memory ring three steps ahead; completion is counted on
-    // an mbarrier per stage, so the prefetch never touches the epilogue warps' scoreboards (register prefetch stalled
-    // every third step on shared scoreboard slots, and tcgen05.wait::ld also waits for in-flight cp.async groups).
-    const int rows_valid = min(NV, B - b0);
-    const uint32_t row_bytes = uint32_t(4 * H) * 4u;
-    auto prefetch_xp = [&](int t) {  // elected lane only
-      if (t >= T) return;
-      uint64_t* bar = sm.bar_pf + (t & (kPfStages - 1));
-      mbar_arrive_expect_tx(bar, row_bytes * rows_valid);
-      float* dst = reinterpret_cast<float*>(sm.ring) + size_t(t & (kPfStages - 1)) * NV * 4 * H;
-      const float* src = xp + (size_t(t) * B + b0) * 4 * H;
-      for (int j = 0; j < rows_valid; ++j) bulk_g2s(dst + size_t(j) * 4 * H, src + size_t(j) * 4 * H, row_bytes, bar);
-    };
-    if (!FX) {
-      if (elect_one()) {
-        for (int t = 0; t < kPfStages; ++t) prefetch_xp(t);
-      }
-      __syncwarp();
-    }
     for (int t = 1; t <= T; ++t) {
       handoff_wait<kRecThreads>();  // h_{t-1} is in shared memory (and TMEM has been drained)
       if (t == T) break;  // the last hand-off only balances the barrier
       tcgen05_fence_after();
       if (elect_one()) {
-        if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 4] = clock64();
+        if constexpr (PROF) { if (prof && cta == 0 && t < kProfSteps) prof[t * 8 + 4] = clock64(); }
         if (base0) issue_fwd<true, KSTEPS>(uz, db0, idesc, ksteps);
         else issue_fwd<false, KSTEPS>(tmem_base, db0, idesc, ksteps);
         umma_commit(sm.bar_acc);
-        if (prof && blockIdx.x == 0 && t < kProfSteps) prof[t * 8 + 5] = clock64();
-        // every epilogue thread has consumed ring stage (t-1) % 4 before the hand-off above: refill it
-        if (!FX) prefetch_xp(t + kPfStages - 1);
-        else *issued_step = t;  // the projection warp queues its MMAs behind this step's
+        if constexpr (PROF) { if (prof && cta == 0 && t < kProfSteps) prof[t * 8 + 5] = clock64(); }
+        // the feeder warp follows through this counter: FX queues its projection MMAs behind this step's; !FX knows
+        // that every epilogue thread has consumed ring stage (t - 1) % kPfStages (the hand-off above) and refills it
+        *issued_step = t;
+      }
+      __syncwarp();
+    }
+  } else if (!FX && warp == kXWarp) {
+    // ================= Xp ring producer (own warp: a cp.async.bulk costs its issuing thread a few hundred cycles) =========
+    // The NV rows Xp[t][b0 .. b0 + NV) (4H floats each, adjacent) are ONE bulk copy into a kPfStages-deep shared-memory
+    // ring, up to kPfStages - 1 steps ahead of the chain; completion is counted on an mbarrier per stage, so the prefetch
+    // never touches the epilogue warps' scoreboards.  With Xp servers in the launch the rows exist only once their
+    // 128-row tile has been published: the lanes check the flags of the next eight timesteps with ONE round trip to L2.
+    const int rows_valid = min(NV, B - b0);
+    const uint32_t bytes = uint32_t(rows_valid) * uint32_t(4 * H) * 4u;
+    for (int t0 = 0; t0 < T; t0 += 8) {
+      if (sv.n_srv > 0) {
+        const int tt = min(t0 + (lane & 7), T - 1);
+        const long long r0 = (long long)tt * B + b0;
+        const unsigned* f = sv.flags + ((lane & 8) ? ((r0 + rows_valid - 1) >> 7) : (r0 >> 7));
+        if (lane < 16) side::wait_ge(f, 1u);
+        __syncwarp();
+        side::fence_proxy_async_all();
+      }
+      if (lane == 0) {
+        for (int t = t0; t < min(T, t0 + 8); ++t) {
+          if (t >= kPfStages) {
+            const int need = t - kPfStages + 1;
+            while (*issued_step < need) __nanosleep(32);
+          }
+          uint64_t* bar = sm.bar_pf + (t & (kPfStages - 1));
+          mbar_arrive_expect_tx(bar, bytes);
+          bulk_g2s(reinterpret_cast<float*>(sm.ring) + size_t(t & (kPfStages - 1)) * NV * 4 * H, xp + (size_t(t) * B + b0) * 4 * H,
+                   bytes, bar);
+        }
       }
       __syncwarp();
     }
@@ -463,7 +493,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
 #pragma unroll
           for (int j = 0; j < NVT; ++j) pre[g][j] = (valid[j] ? src[(jb + j) * 4 * H + g * H] : 0.f) + bias[g];
       }
-      const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && t < kProfSteps;
+      const bool do_prof = PROF && prof && cta == 0 && tid == 0 && t < kProfSteps;
       if (phase_prof && (t == 1 || t == 8 || t == 64 || t == 200 || t == 400)) prof[1024 + 6 + (t == 1 ? 0 : t == 8 ? 1 : t == 64 ? 2 : t == 200 ? 3 : 4)] = clock64();
       if (t > 0) {
         if (do_prof) prof[t * 8 + 6] = clock64();
@@ -550,23 +580,38 @@ lstm_fwd_tc_kernel(const float* __restrict__ xp, const uint32_t* __restrict__ w_
 
 // ------------------------------------------------------------------------------------------------ backward
 // dh_{t-1}^T[k, b] = sum_{kk = g*KP + u} W_hh[g*H + u][k] * dG_t[b, kk]: M = hidden unit k (TMEM lane), K = 4*KP.
-template <int NV, int KSTEPS>
+// dG is written as [t][b][4u + g] (GATE-INTERLEAVED, 4H bf16 per trial): the same packed 8 bytes per cell that go into
+// the MMA operand, one coalesced 8-byte store per thread.  When the launch carries dW consumer CTAs (blocks [n_rec,
+// n_rec + cons.n_cons), lstm_side.cuh) every epilogue warp also bumps its own "steps stored" word in shared memory
+// (release at CTA scope; per-warp monotonic counters cannot alias however far the reader falls behind), and the
+// publisher warp -- its own warp: a gpu-scope release waits for the SM's outstanding writes, about a step's time, and on
+// the producer warp that starved the prefetch ring -- publishes kDgBatch steps at a time, kDgLag steps late: one
+// gpu-scope fence, then relaxed adds on done[t].
+template <int NV, int KSTEPS, bool PROF>
 __global__ void __launch_bounds__(kBwdThreads, 1)
-lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
+lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ CUtensorMap tm_x,
+                   const __grid_constant__ CUtensorMap tm_h, const side::DwConsume cons,
+                   const uint32_t* __restrict__ w_img, const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_seq,
                    const float* __restrict__ d_hseq, const float* __restrict__ d_hlast, __nv_bfloat16* __restrict__ dG,
                    float* __restrict__ db_part, int T, int B, int H, int KP,
                    long long* __restrict__ prof, const uint32_t uz) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  if ((int)blockIdx.x >= cons.n_rec) {
+    side::dw_consumer_role(smem_raw, &tm_dg, &tm_x, &tm_h, cons, (int)blockIdx.x - cons.n_rec);
+    return;
+  }
   const size_t b_bytes = size_t(4 * 128 / 8) * kLboB;  // gate stride fixed at 128 contraction elements
   RecSmem sm = carve(smem_raw, b_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * NV;
   const int ksteps_gate = KP / 16;
+  uint32_t* const dg_stored = sm.tmem_slot + 4;  // [kEpiWarps] steps whose dG rows each epilogue warp has stored
 
   for (int i = tid; i < (int)(b_bytes / 4); i += kBwdThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   volatile int* const progress = reinterpret_cast<volatile int*>(sm.tmem_slot + 1);  // hand-offs seen by issuer warp 0
   if (tid == 0) {
     *progress = 0;
+    for (int i = 0; i < kEpiWarps; ++i) dg_stored[i] = 0u;
     mbar_init(sm.bar_in, kEpiWarps);
     mbar_init(sm.bar_acc, 2);  // one tcgen05.commit per issuer warp
     for (int i = 0; i < kPfStages; ++i) mbar_init(sm.bar_pf + i, 1);
@@ -584,7 +629,36 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
   __syncthreads();
   tcgen05_fence_after();
 
-  if (warp == kIssuerWarp + 2) {
+  if (warp == kIssuerWarp + 3) {
+    // ================= publisher: step n (t = T - 1 - n) once all epilogue warps have stored its dG rows, kDgLag steps late ====
+    if (cons.n_cons > 0) {
+      for (int n0 = 0; n0 < T; n0 += kDgBatch) {
+        const int n1 = min(T, n0 + kDgBatch);          // steps [n0, n1) are published now ...
+        const uint32_t need = (uint32_t)min(T, n1 + kDgLag);  // ... once every epilogue warp has stored this many steps
+        if (lane < kEpiWarps) {
+          uint32_t seen;
+          unsigned long long t0 = 0;
+          for (unsigned spins = 0;; ++spins) {
+            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(dg_stored + lane)) : "memory");
+            if (seen >= need) break;
+            __nanosleep(200);
+            if ((spins & 1023u) == 1023u) {  // watchdog: a stuck chain traps instead of hanging the device
+              unsigned long long now;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > 20000000000ull) __trap();
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          for (int n = n0; n < n1; ++n)
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(cons.done + (T - 1 - n)), "r"(1u) : "memory");
+        }
+      }
+    }
+  } else if (warp == kIssuerWarp + 2) {
     // TMA producer of the per-step BPTT inputs (own warp: on an issuer warp the copies delayed that warp's return to
     // the hand-off barrier, i.e. the chain): for every trial of the tile the row of gate
     // activations (H x 8 B), the row of c_{t-1} (H x 4 B; c_t is carried in a register from the step before) and, when a
@@ -595,7 +669,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
     // epilogue thread is done with the ring stage of step T-1-n, which is then refilled with step T-1-n-4.
     const int rows_valid = min(NV, B - b0);
     const uint32_t g_bytes = uint32_t(H) * 8u, c_bytes = uint32_t(H) * 4u;
-    uint8_t* const pf_ring = sm.opb + b_bytes + 128;
+    uint8_t* const pf_ring = sm.opb + b_bytes + kBarBlock;
     // Lane 0 issues the copies.  The rows of the tile's trials are adjacent in the reserve ([t][b][...]), so one step is
     // TWO bulk copies (gates, c_prev) plus one for d_hseq -- not two or three per trial: a cp.async.bulk costs the
     // issuing thread a few hundred cycles, and with 4-6 of them per step the producer needed more than a step time per
@@ -629,7 +703,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
         if (t == 0) break;  // the last hand-off only balances the barrier
         tcgen05_fence_after();
         if (elect_one()) {
-          const bool pr = prof && blockIdx.x == 0 && n + 1 < kProfSteps && HALF == 0;
+          const bool pr = PROF && prof && blockIdx.x == 0 && n + 1 < kProfSteps && HALF == 0;
           if (pr) prof[512 + (n + 1) * 8 + 4] = clock64();
           if (base0) issue_bwd<true, KSTEPS, HALF>(uz, db0, idesc, ksteps_gate);
           else issue_bwd<false, KSTEPS, HALF>(tmem_base, db0, idesc, ksteps_gate);
@@ -657,13 +731,13 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
 
     // Per-step inputs arrive through the TMA ring filled by issuer warp 1 (see prefetch_step): per trial
     // [gates: H x (i,f,g,o) bf16 | c_{t-1}: H fp32 | d_hseq: H fp32]; c_t is carried over from the previous iteration.
-    const uint8_t* const pf_ring = sm.opb + b_bytes + 128;
-    __nv_bfloat16* dg_ptr[NVT];  // dG[t][b][.] output row
+    const uint8_t* const pf_ring = sm.opb + b_bytes + kBarBlock;
+    uint2* dg_ptr[NVT];  // dG[t][b][4u .. 4u + 3]: one 8-byte element per cell
     float c_cur[NVT], dhl[NVT];  // c_t of the step about to be processed; d_hlast (enters at t = T-1 only)
 #pragma unroll
     for (int j = 0; j < NVT; ++j) {
       const size_t row = size_t(b0 + jb + j);
-      dg_ptr[j] = dG + (valid[j] ? (size_t(T - 1) * B + row) * 4 * H + u : 0);
+      dg_ptr[j] = reinterpret_cast<uint2*>(dG) + (valid[j] ? (size_t(T - 1) * B + row) * H + u : 0);
       c_cur[j] = valid[j] ? c_seq[(size_t(T - 1) * B + row) * H + u] : 0.f;
       dhl[j] = (valid[j] && d_hlast) ? d_hlast[row * H + u] : 0.f;
     }
@@ -672,9 +746,9 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
     int n = 0;
     for (int t = T - 1; t >= 0; --t) {
      {
-      if (prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps) prof[1200 + n * 2] = clock64();
+      if constexpr (PROF) { if (prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps) prof[1200 + n * 2] = clock64(); }
       mbar_wait(sm.bar_pf + (t & (kPfStages - 1)), ((T - 1 - t) / kPfStages) & 1);  // the rows of step t have landed (long ago)
-      if (prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps) prof[1200 + n * 2 + 1] = clock64();
+      if constexpr (PROF) { if (prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps) prof[1200 + n * 2 + 1] = clock64(); }
       struct { float i[NVT], f[NVT], g[NVT], o[NVT], c[NVT], cp[NVT]; } cur;
       float dh[NVT], pref[NVT], fac[4][NVT];  // fac: everything of dG that does not depend on dh
       // everything that does not need dh is done before the wait
@@ -698,7 +772,7 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
           fac[3][j] = tcn * cur.o[j] * (1.f - cur.o[j]);
         }
       }
-      const bool do_prof = prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps;
+      const bool do_prof = PROF && prof && blockIdx.x == 0 && tid == 0 && n < kProfSteps;
       if (t < T - 1) {
         if (do_prof) prof[512 + n * 8 + 6] = clock64();
         mbar_wait(sm.bar_acc, (n - 1) & 1);
@@ -736,19 +810,25 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
       fence_proxy_async_smem();
       handoff_arrive<kRecThreadsBwd>();
       if (do_prof) prof[512 + n * 8 + 3] = clock64();
-      ++n;
-      // ---- off the critical path ----
+      // ---- off the critical path: dG_t to HBM (the packed 8 bytes of the operand, coalesced), bias partials ----
 #pragma unroll
       for (int j = 0; j < NVT; ++j) {
         if (valid[j]) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(dg[0][j], dg[1][j]), hi = __floats2bfloat162_rn(dg[2][j], dg[3][j]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *dg_ptr[j] = pk;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            dg_ptr[j][g * H] = __float2bfloat16_rn(dg[g][j]);
-            dbacc[g] += dg[g][j];
-          }
-          dg_ptr[j] -= size_t(B) * 4 * H;
+          for (int g = 0; g < 4; ++g) dbacc[g] += dg[g][j];
         }
+        if (valid[j]) dg_ptr[j] -= size_t(B) * H;
       }
+      if (cons.n_cons > 0) {  // this warp's rows of step n are stored: tell the producer warp (it publishes the step)
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(dg_stored + warp)), "r"(n + 1) : "memory");
+      }
+      ++n;
       if (do_prof) prof[512 + (n - 1) * 8 + 7] = clock64();
      }
     }
@@ -767,23 +847,41 @@ lstm_bwd_tc_kernel(const uint32_t* __restrict__ w_img, const __nv_bfloat16* __re
   }
 }
 
-// The fixed-order tail of BPTT (no float atomics anywhere in the backward pass): dW_ih / dW_hh = sum over the split-K slabs of
-// the weight-gradient products in split order, db_ih = db_hh = sum over the recurrence CTAs' partials in CTA order.
-__global__ void bptt_finalize_kernel(const float* __restrict__ slabs_ih, int s_ih, const float* __restrict__ slabs_hh, int s_hh,
-                                     const float* __restrict__ db_part, int n_part, float* __restrict__ dw_ih,
-                                     float* __restrict__ dw_hh, float* __restrict__ db_ih, float* __restrict__ db_hh, int H, int I,
-                                     int accumulate) {
+// The fixed-order tail of BPTT (no float atomics anywhere in the backward pass): dW_ih / dW_hh = sum over the partial
+// slabs of the weight-gradient products in slab order (the dW consumer groups of the launch, or the split-K ranges of the
+// GEMMs that follow it), db_ih = db_hh = sum over the recurrence CTAs' partials in CTA order.  The slabs' rows are in the
+// gate-interleaved order of dG (row 4u + g); the gradients leave in PyTorch's gate-major order (row g*H + u).
+struct DwSlabs {
+  const float* base;  // slab z at base + z * stride
+  int n;              // slabs (0: the product is empty -- a single timestep has no h_{t-1})
+  size_t stride;      // floats between slabs
+  int ld, col0;       // row pitch and first column of this weight's block inside a slab row
+};
+struct DwSources {  // a weight gradient = consumer slabs (the rows folded during the sweep) + GEMM slabs (the rest)
+  DwSlabs a, b;
+};
+__global__ void bptt_finalize_kernel(const DwSources ih, const DwSources hh, const float* __restrict__ db_part, int n_part,
+                                     float* __restrict__ dw_ih, float* __restrict__ dw_hh, float* __restrict__ db_ih,
+                                     float* __restrict__ db_hh, int H, int I, int accumulate) {
   const int n_ih = 4 * H * I, n_hh = 4 * H * H, n_b = 4 * H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ih + n_hh + n_b; i += gridDim.x * blockDim.x) {
-    if (i < n_ih) {
-      float a = slabs_ih[i];
-      for (int z = 1; z < s_ih; ++z) a += slabs_ih[size_t(z) * n_ih + i];
-      dw_ih[i] = accumulate ? dw_ih[i] + a : a;
-    } else if (i < n_ih + n_hh) {
-      const int j = i - n_ih;
+    if (i < n_ih + n_hh) {
+      const bool is_ih = i < n_ih;
+      const DwSources& w = is_ih ? ih : hh;
+      const int j = is_ih ? i : i - n_ih, width = is_ih ? I : H;
+      const int r = j / width, k = j - r * width;       // r = g*H + u
+      const int rp = 4 * (r % H) + r / H;               // slab row 4u + g
       float a = 0.f;
-      for (int z = 0; z < s_hh; ++z) a += slabs_hh[size_t(z) * n_hh + j];  // s_hh == 0: a single timestep has no h_{t-1}
-      dw_hh[j] = accumulate ? dw_hh[j] + a : a;
+      {
+        const float* src = w.a.base + size_t(rp) * w.a.ld + w.a.col0 + k;
+        for (int z = 0; z < w.a.n; ++z) a += src[size_t(z) * w.a.stride];
+      }
+      {
+        const float* src = w.b.base + size_t(rp) * w.b.ld + w.b.col0 + k;
+        for (int z = 0; z < w.b.n; ++z) a += src[size_t(z) * w.b.stride];
+      }
+      float* dst = is_ih ? dw_ih + j : dw_hh + j;
+      *dst = accumulate ? *dst + a : a;
     } else {
       const int j = i - n_ih - n_hh;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -802,15 +900,30 @@ __global__ void bptt_finalize_kernel(const float* __restrict__ slabs_ih, int s_i
   }
 }
 
+// dst[4u + g, :] = bf16(src[g*H + u, :]): W_ih in the gate-interleaved row order of dG (operand of dX = dG W_ih)
+__global__ void interleave_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H, int N) {
+  const int r = blockIdx.x, u = r >> 2, g = r & 3;
+  const float* s = src + size_t(g * H + u) * N;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) dst[size_t(r) * N + c] = __float2bfloat16_rn(s[c]);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 constexpr size_t kWimgBytes = size_t(4) * 128 * 64 * 4;  // TMEM image of the resident weight operand
 constexpr size_t kWihImgBytes = size_t(4) * 128 * 128 * 2;  // shared-memory image of W_ih (fused input projection, I <= 128)
+constexpr int kMaxConsumers = 32;  // dW consumer CTAs per launch (16 K groups x 2 M halves): 8 MB of partial slabs
 
 // the recurrence computes x_t W_ih^T itself when the input fits the resident shared-memory operand
 static bool fused_projection(int I) {
   static const bool off = [] { const char* e = getenv("CSN_LSTM_NO_FUSED_X"); return e && e[0] == '1'; }();
   return !off && I <= 128 && I % 8 == 0;
+}
+// spare CTAs of a recurrence launch take the layer's GEMM-shaped work (lstm_side.cuh); CSN_LSTM_NO_SIDE=1 switches both
+// side roles off, CSN_LSTM_NO_SERVERS=1 / CSN_LSTM_NO_CONSUMERS=1 one of them (A/B measurements, fallback tests)
+static bool side_enabled(const char* which) {
+  static const bool off = [] { const char* e = getenv("CSN_LSTM_NO_SIDE"); return e && e[0] == '1'; }();
+  const char* e = getenv(which);
+  return !off && !(e && e[0] == '1');
 }
 
 // Upper bound on the CTAs (= SMs: a recurrence CTA owns a whole SM's tensor memory) one recurrence launch may use; 0 = all.
@@ -828,6 +941,31 @@ static int pick_nv(int B) {
   return 8;
 }
 
+// Xp server CTAs of a forward launch over B trials (0: none).  The whole launch must be co-resident (one CTA per SM),
+// the servers must keep ahead of the chain (~4k cycles per 128-row tile against ~650 per timestep of B / 128 tiles),
+// and the server kernel serves I <= 128, H % 16 == 0.
+static int pick_servers(int T, int B, int I, int H, int nv) {
+  // OFF by default: an SM writes global memory at 32 B/clk at most (scripts/store_bw.py: STG and TMA alike), so the
+  // spare SMs of the cfg2 launch cannot write the fp32 Xp (230 MB) faster than ~1.26 TB/s = 183 us -- slower than the
+  // chain they feed (measured 355 us against 245 us for the fused in-CTA projection).  CSN_LSTM_SERVERS=1 enables it.
+  static const bool on = [] { const char* e = getenv("CSN_LSTM_SERVERS"); return e && e[0] == '1'; }();
+  if (!on || !side_enabled("CSN_LSTM_NO_SERVERS") || g_cta_budget > 0 || !fused_projection(I) || H % 16 != 0 || H > 128) return 0;
+  const int n_rec = ceil_div(B, nv), spare = sm_count() - n_rec;
+  const int n_tiles = ceil_div(T * B, 128);
+  const int need = std::max(2, ceil_div(6 * B, 128));
+  if (spare < need || T < 16) return 0;
+  return std::min(spare, n_tiles);
+}
+// dW consumer CTAs of a backward launch (0: none; the two dW GEMMs then follow the recurrence)
+static int pick_consumers(int T, int B, int I, int H, int nv) {
+  if (!side_enabled("CSN_LSTM_NO_CONSUMERS") || g_cta_budget > 0 || I > 128 || I % 8 != 0 || H % 8 != 0 || H > 128) return 0;
+  const int n_rec = ceil_div(B, nv), spare = sm_count() - n_rec;
+  const int mh = 4 * H > 256 ? 2 : 1;
+  const int i_pad = ceil_div(I, 64) * 64, h_pad = ceil_div(H, 64) * 64;
+  if (i_pad + h_pad > 256 || spare < 2 * mh || T < 16) return 0;
+  return std::min(spare, kMaxConsumers) / mh * mh;
+}
+
 int lstm_large_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace);
 int lstm_layer_fwd_large(const void* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, void* h_seq,
                          void* reserve, void* workspace, int T, int B, int I, int H, int training, cudaStream_t s);
@@ -835,12 +973,16 @@ int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, co
                          const float* d_hseq, const float* d_hlast, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
                          float* dx, void* workspace, int T, int B, int I, int H, int accumulate, cudaStream_t s);
 
-// scratch of the fixed-order BPTT tail: split-K slabs of the two dW products (sized for the requested split counts; the
-// GEMM may round them down) + one bias-gradient partial per (recurrence CTA, batch half) (NV >= 2: at most B partials)
+// scratch of the fixed-order BPTT tail: partial dW slabs (consumer groups, or the split-K ranges of the two dW GEMMs sized
+// for the requested split counts -- the GEMM may round them down), one bias-gradient partial per (recurrence CTA, batch
+// half) (NV >= 2: at most B partials), and the per-timestep publication counters
 static int dw_split_req(int M, int N) { return std::max(1, sm_count() / (ceil_div(M, 128) * ceil_div(N, 128))); }
-static size_t bwd_tail_bytes(int B, int I, int H) {
-  return align256(size_t(dw_split_req(4 * H, I)) * 4 * H * I * 4) + align256(size_t(dw_split_req(4 * H, H)) * 4 * H * H * 4) +
-         align256(size_t(B + 1) * 4 * H * 4);
+static size_t bwd_slab_bytes(int I, int H) {
+  const size_t gemm = align256(size_t(dw_split_req(4 * H, I)) * 4 * H * I * 4) + align256(size_t(dw_split_req(4 * H, H)) * 4 * H * H * 4);
+  return gemm + size_t(kMaxConsumers) * side::dw_slab_floats() * 4;  // (both at once when the consumers take a share)
+}
+static size_t bwd_tail_bytes(int T, int B, int I, int H) {
+  return bwd_slab_bytes(I, H) + align256(size_t(B + 1) * 4 * H * 4) + align256(size_t(T) * 4);
 }
 
 int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace) {
@@ -851,8 +993,10 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
   }
   const size_t tb = size_t(T) * B;
   *reserve = align256(tb * 4 * H * 2) + align256(tb * H * 4);
-  const size_t wf = align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2) + kWimgBytes + kWihImgBytes;
-  const size_t wb = align256(tb * 4 * H * 2) + align256(size_t(4) * H * I * 2) + kWimgBytes + bwd_tail_bytes(B, I, H);
+  // forward: Xp | W_ih bf16 | W_hh image | W_ih image | tile flags
+  const size_t wf = align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2) + kWimgBytes + kWihImgBytes + align256((tb / 128 + 2) * 4);
+  // backward: dG | W_ih bf16 | W_hh^T image | tail
+  const size_t wb = align256(tb * 4 * H * 2) + align256(size_t(4) * H * I * 2) + kWimgBytes + bwd_tail_bytes(T, B, I, H);
   *workspace = wf > wb ? wf : wb;
   return CSN_OK;
 }
@@ -884,54 +1028,71 @@ static SideStream* side_stream() {
   return &table[dev];
 }
 
-struct FusedX {  // fused input projection operands (x == nullptr: read the precomputed Xp instead)
+struct FusedX {  // fused input projection operands (x == nullptr: read Xp through the ring instead)
   const __nv_bfloat16* x;
   const uint8_t* wih_img;
   const float* b_ih;
   int I, KI;
 };
 
-template <int NV, int KSTEPS>
-static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
-                      float* c_out, int T, int B, int H, int KP, const FusedX& fx, cudaStream_t s) {
-  if (fx.x) {
-    // operand + barriers + two x blocks + W_ih image
-    const size_t smem = size_t(KP / 8) * kLboB + 128 + 2 * size_t(fx.KI / 8) * kLboB + size_t(4) * 128 * fx.KI * 2;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      CSN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<NV, KSTEPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
-    lstm_fwd_tc_kernel<NV, KSTEPS, true><<<ceil_div(B, NV), kRecThreadsBwd, smem, s>>>(
-        nullptr, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf, 0u, fx.x, fx.wih_img, fx.b_ih, fx.I, fx.KI);
-    CSN_LAUNCH_CHECK();
-    return CSN_OK;
+// raise-only dynamic shared-memory attribute (the call disappears from steady state and from graph capture)
+template <typename K>
+static int ensure_smem(K kern, size_t smem, size_t* set) {
+  if (smem > *set) {
+    CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *set = smem;
   }
-  const size_t smem = size_t(KP / 8) * kLboB + 128 + size_t(kPfStages) * NV * 4 * H * 4 + 128;  // operand + barriers + Xp ring
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    CSN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<NV, KSTEPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  lstm_fwd_tc_kernel<NV, KSTEPS, false><<<ceil_div(B, NV), kRecThreads, smem, s>>>(
-      xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H, KP, g_prof_buf, 0u, nullptr, nullptr, nullptr, 0, 16);
-  CSN_LAUNCH_CHECK();
   return CSN_OK;
 }
 
-template <int NV, int KSTEPS>
+template <typename K, typename... Args>
+static int launch_grid(K kern, int grid, int threads, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  CSN_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  count_launches(1);
+  return CSN_OK;
+}
+
+template <int NV, int KSTEPS, bool PROF>
+static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
+                      float* c_out, int T, int B, int H, int KP, const FusedX& fx, const side::XpServe& sv, const CUtensorMap& tm_x,
+                      const CUtensorMap& tm_w, cudaStream_t s) {
+  const int n_rec = ceil_div(B, NV);
+  if (fx.x) {
+    // operand + barriers + two x blocks + W_ih image
+    const size_t smem = size_t(KP / 8) * kLboB + kBarBlock + 2 * size_t(fx.KI / 8) * kLboB + size_t(4) * 128 * fx.KI * 2;
+    static size_t smem_set = 0;
+    auto kern = lstm_fwd_tc_kernel<NV, KSTEPS, true, PROF>;
+    CSN_TRY(ensure_smem(kern, smem, &smem_set));
+    return launch_grid(kern, n_rec, kRecThreadsBwd, smem, s, tm_x, tm_w, sv, (const float*)nullptr, w_hh, b_hh, h_seq, gates, c_out,
+                       T, B, H, KP, g_prof_buf, 0u, fx.x, fx.wih_img, fx.b_ih, fx.I, fx.KI);
+  }
+  size_t smem = size_t(KP / 8) * kLboB + kBarBlock + size_t(kPfStages) * NV * 4 * H * 4 + 128;  // operand + barriers + Xp ring
+  if (sv.n_srv > 0) smem = std::max(smem, side::xp_server_smem(H));
+  static size_t smem_set = 0;
+  auto kern = lstm_fwd_tc_kernel<NV, KSTEPS, false, PROF>;
+  CSN_TRY(ensure_smem(kern, smem, &smem_set));
+  return launch_grid(kern, sv.n_srv + n_rec, kRecThreadsBwd, smem, s, tm_x, tm_w, sv, xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H,
+                     KP, g_prof_buf, 0u, (const __nv_bfloat16*)nullptr, (const uint8_t*)nullptr, (const float*)nullptr, 0, 16);
+}
+
+template <int NV, int KSTEPS, bool PROF>
 static int launch_bwd(const uint32_t* w_hh, const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq,
                       const float* d_hlast, __nv_bfloat16* dG, float* db_part, int T, int B, int H, int KP,
+                      const side::DwConsume& dc, const CUtensorMap& tm_dg, const CUtensorMap& tm_x, const CUtensorMap& tm_h,
                       cudaStream_t s) {
-  const size_t smem = size_t(4 * 128 / 8) * kLboB + 128 + size_t(kPfStages) * NV * kBwdPfRow + 128;  // operand + barriers + TMA ring
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    CSN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<NV, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  lstm_bwd_tc_kernel<NV, KSTEPS><<<ceil_div(B, NV), kBwdThreads, smem, s>>>(w_hh, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, g_prof_buf, 0u);
-  CSN_LAUNCH_CHECK();
-  return CSN_OK;
+  // operand + barriers + TMA ring of the per-step inputs
+  size_t smem = size_t(4 * 128 / 8) * kLboB + kBarBlock + size_t(kPfStages) * NV * kBwdPfRow + 128;
+  if (dc.n_cons > 0) smem = std::max(smem, side::dw_consumer_smem());
+  static size_t smem_set = 0;
+  auto kern = lstm_bwd_tc_kernel<NV, KSTEPS, PROF>;
+  CSN_TRY(ensure_smem(kern, smem, &smem_set));
+  return launch_grid(kern, dc.n_rec + dc.n_cons, kBwdThreads, smem, s, tm_dg, tm_x, tm_h, dc, w_hh, gates, c_seq, d_hseq, d_hlast, dG,
+                     db_part, T, B, H, KP, g_prof_buf, 0u);
 }
 
 int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
@@ -942,40 +1103,52 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   if (H > 128) return lstm_layer_fwd_large(x, w_ih, w_hh, b_ih, b_hh, h_seq, reserve, workspace, T, B, I, H, training, s);
   const size_t tb = size_t(T) * B;
   const int KP = ceil_div(H, 16) * 16;
-  float* xp = reinterpret_cast<float*>(workspace);
-  __nv_bfloat16* wih_bf = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 4));
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* xp = reinterpret_cast<float*>(ws);
+  __nv_bfloat16* wih_bf = reinterpret_cast<__nv_bfloat16*>(ws + align256(tb * 4 * H * 4));
+  uint32_t* w_img = reinterpret_cast<uint32_t*>(ws + align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2));
+  uint8_t* wih_img = reinterpret_cast<uint8_t*>(w_img) + kWimgBytes;
+  unsigned* flags = reinterpret_cast<unsigned*>(wih_img + kWihImgBytes);
   __nv_bfloat16* gates = reinterpret_cast<__nv_bfloat16*>(reserve);
   float* c_out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(reserve) + align256(tb * 4 * H * 2));
+  const int nv = pick_nv(B);
+  const int n_srv = pick_servers(T, B, I, H, nv);
+  const int KI = ceil_div(I, 16) * 16;
   FusedX fx{nullptr, nullptr, nullptr, 0, 16};
-  if (fused_projection(I)) {
-    uint8_t* img = reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 4) + align256(size_t(4) * H * I * 2) + kWimgBytes;
-    const int KI = ceil_div(I, 16) * 16;
-    fx = FusedX{reinterpret_cast<const __nv_bfloat16*>(x), img, b_ih, I, KI};
+  side::XpServe sv{};
+  CUtensorMap tm_x{}, tm_w{};
+  const int n_tiles = (int)ceil_div<size_t>(tb, 128);
+  if (n_srv > 0) {
+    // spare CTAs of the launch compute Xp concurrently: bf16 W_ih for their TMA, READY flags zeroed by the prepare kernel
+    sv = side::XpServe{n_srv, n_tiles, (int)tb, I, H, xp, b_ih, flags};
+    CSN_TRY(make_tmap_2d(&tm_x, x, (uint64_t)I, (uint64_t)tb, (uint64_t)I, 64, 128));
+    CSN_TRY(make_tmap_2d(&tm_w, wih_bf, (uint64_t)I, (uint64_t)(4 * H), (uint64_t)I, 64, (uint32_t)side::xp_w_box_rows(H)));
+  } else if (fused_projection(I)) {
+    fx = FusedX{reinterpret_cast<const __nv_bfloat16*>(x), wih_img, b_ih, I, KI};
   } else {
     CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
     // hoisted input projection: Xp[T*B, 4H] = x[T*B, I] . W_ih[4H, I]^T + b_ih  (fp32 out)
     CSN_TRY(gemm_tc_run(0, 1, (int)tb, 4 * H, I, x, I, wih_bf, I, xp, 4 * H, CSN_F32, b_ih, 0, 1, nullptr, s));
   }
-  const int nv = pick_nv(B);
   __nv_bfloat16* g = training ? gates : nullptr;
   float* c = training ? c_out : nullptr;
   __nv_bfloat16* hs = (__nv_bfloat16*)h_seq;
-  uint32_t* w_img = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 4) +
-                                                align256(size_t(4) * H * I * 2));
   {
-    const int n_idx = std::max(4 * 128 * 64, fx.x ? 4 * 128 * fx.KI : 0);
+    const int n_idx = std::max(std::max(4 * 128 * 64, fx.x ? 4 * 128 * fx.KI : 0), n_srv > 0 ? std::max(4 * H * I, n_tiles) : 0);
     lstm_prepare_kernel<<<ceil_div(n_idx, 256), 256, 0, s>>>(
-        w_hh, w_img, H, 0, w_ih, fx.x ? reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(fx.wih_img)) : nullptr, I, fx.KI,
-        nullptr, nullptr, 0);
+        w_hh, w_img, H, 0, w_ih, fx.x ? reinterpret_cast<__nv_bfloat16*>(wih_img) : nullptr, I, fx.KI,
+        n_srv > 0 ? wih_bf : nullptr, n_srv > 0 ? flags : nullptr, n_srv > 0 ? n_tiles : 0);
     CSN_LAUNCH_CHECK();
   }
-  // hidden 128 / 96 / 64 get compile-time K-step counts (predicate-free MMA issue); other sizes take the runtime path
-#define CSN_FWD(KS)                                                                  \
-  do {                                                                               \
-    if (nv == 2) return launch_fwd<2, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, s); \
-    if (nv == 4) return launch_fwd<4, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, s); \
-    return launch_fwd<8, KS>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, s);              \
+  // hidden 128 / 96 / 64 get compile-time K-step counts (predicate-free MMA issue); other sizes take the runtime path.
+  // The stamped (PROF) instantiation exists for the benchmark shape only.
+#define CSN_FWD(KS)                                                                                                     \
+  do {                                                                                                                  \
+    if (nv == 2) return launch_fwd<2, KS, false>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);          \
+    if (nv == 4) return launch_fwd<4, KS, false>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);          \
+    return launch_fwd<8, KS, false>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);                       \
   } while (0)
+  if (KP == 128 && nv == 2 && g_prof_buf) return launch_fwd<2, 8, true>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);
   if (KP == 128) CSN_FWD(8);
   if (KP == 96) CSN_FWD(6);
   if (KP == 64) CSN_FWD(4);
@@ -995,60 +1168,104 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   const int KP = ceil_div(H, 16) * 16;
   const __nv_bfloat16* gates = reinterpret_cast<const __nv_bfloat16*>(reserve);
   const float* c_seq = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(reserve) + align256(tb * 4 * H * 2));
-  __nv_bfloat16* dG = reinterpret_cast<__nv_bfloat16*>(workspace);
-  __nv_bfloat16* wih_bf = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 2));
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* dG = reinterpret_cast<__nv_bfloat16*>(ws);  // [T, B, 4H], gate-interleaved columns 4u + g
+  __nv_bfloat16* wih_bf = reinterpret_cast<__nv_bfloat16*>(ws + align256(tb * 4 * H * 2));
+  uint32_t* w_img = reinterpret_cast<uint32_t*>(ws + align256(tb * 4 * H * 2) + align256(size_t(4) * H * I * 2));
+  float* slabs = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(w_img) + kWimgBytes);
+  float* db_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(slabs) + bwd_slab_bytes(I, H));
+  unsigned* done = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(db_part) + align256(size_t(B + 1) * 4 * H * 4));
   const int nv = pick_nv(B);
-  uint32_t* w_img = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + align256(tb * 4 * H * 2) +
-                                                align256(size_t(4) * H * I * 2));
-  // scratch of the fixed-order tail, behind the weight image
-  float* slabs_ih = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(w_img) + kWimgBytes);
-  float* slabs_hh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(slabs_ih) + align256(size_t(dw_split_req(4 * H, I)) * 4 * H * I * 4));
-  float* db_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(slabs_hh) + align256(size_t(dw_split_req(4 * H, H)) * 4 * H * H * 4));
-  const int n_part = 2 * ceil_div(B, nv);
-  lstm_prepare_kernel<<<4 * 128 * 64 / 256, 256, 0, s>>>(w_hh, w_img, H, 1, nullptr, nullptr, 0, 16, nullptr, nullptr, 0);  // W_hh^T image
+  const int n_rec = ceil_div(B, nv), n_part = 2 * n_rec;
+  const int n_cons = pick_consumers(T, B, I, H, nv);
+  const int i_pad = ceil_div(I, 64) * 64;
+  // The consumers can leave the LAST timesteps BPTT reaches (rows below chunk c_lo) to the GEMMs below, so that they
+  // finish together with the chain: capacity = share * n_cons * T / m_halves chunks (a 64-row unit per M half costs a
+  // consumer ~2000 cycles, bound by its SM's ~32 B/clk of L2 traffic, against ~700 cycles per timestep of the chain: a
+  // share of ~0.3 would balance them).  Measured at cfg2 (scripts/gpu_lstm_ab.sh): 231 / 225 / 211 / 206 us for shares
+  // 0.20 / 0.27 / 0.33 / >= 0.40 against 248 us without consumers -- the tail GEMMs' fixed cost exceeds the ~35 us the
+  // consumers trail the chain by, so the default share is 1 (they take everything); CSN_LSTM_CONSUMER_SHARE overrides it.
+  const int m_halves = 4 * H > 256 ? 2 : 1;
+  const int n_chunks = (int)ceil_div<size_t>(tb, 64);
+  int c_lo = 0;
+  if (n_cons > 0) {
+    static const double share = [] { const char* e = getenv("CSN_LSTM_CONSUMER_SHARE"); return e ? atof(e) : 1.0; }();
+    const double capacity = share * double(n_cons) * T / m_halves;  // chunks
+    c_lo = std::max(0, n_chunks - (int)capacity);
+    if (size_t(c_lo) * 64 < size_t(2) * B) c_lo = 0;  // not worth a separate product
+  }
+  const int rows_post = n_cons > 0 ? c_lo * 64 : (int)tb;  // rows [0, rows_post) of dG are contracted after the launch
+  side::DwConsume dc{n_cons, n_rec, m_halves, T, B, I, H, i_pad, c_lo, done, slabs};
+  CUtensorMap tm_dg{}, tm_x{}, tm_h{};
+  if (n_cons > 0) {
+    CSN_TRY(make_tmap_2d(&tm_dg, dG, (uint64_t)(4 * H), (uint64_t)tb, (uint64_t)(4 * H), 64, 64));
+    CSN_TRY(make_tmap_2d(&tm_x, x, (uint64_t)I, (uint64_t)tb, (uint64_t)I, 64, 64));
+    CSN_TRY(make_tmap_2d(&tm_h, h_seq, (uint64_t)H, (uint64_t)tb, (uint64_t)H, 64, 64));
+  }
+  // W_hh^T image (+ the consumers' per-timestep publication counters zeroed)
+  lstm_prepare_kernel<<<std::max(4 * 128 * 64, n_cons > 0 ? T : 0) / 256 + 1, 256, 0, s>>>(
+      w_hh, w_img, H, 1, nullptr, nullptr, 0, 16, nullptr, n_cons > 0 ? done : nullptr, n_cons > 0 ? T : 0);
   CSN_LAUNCH_CHECK();
-#define CSN_BWD(KS)                                                                                                   \
-  do {                                                                                                                \
-    if (nv == 2) CSN_TRY((launch_bwd<2, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, s)));      \
-    else if (nv == 4) CSN_TRY((launch_bwd<4, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, s))); \
-    else CSN_TRY((launch_bwd<8, KS>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, s)));              \
+#define CSN_BWD(KS)                                                                                                              \
+  do {                                                                                                                           \
+    if (nv == 2) CSN_TRY((launch_bwd<2, KS, false>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, dc, tm_dg, tm_x, tm_h, s)));      \
+    else if (nv == 4) CSN_TRY((launch_bwd<4, KS, false>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, dc, tm_dg, tm_x, tm_h, s))); \
+    else CSN_TRY((launch_bwd<8, KS, false>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, dc, tm_dg, tm_x, tm_h, s)));              \
   } while (0)
-  if (KP == 128) CSN_BWD(8);
+  if (KP == 128 && nv == 2 && g_prof_buf) CSN_TRY((launch_bwd<2, 8, true>(w_img, gates, c_seq, d_hseq, d_hlast, dG, db_part, T, B, H, KP, dc, tm_dg, tm_x, tm_h, s)));
+  else if (KP == 128) CSN_BWD(8);
   else if (KP == 96) CSN_BWD(6);
   else if (KP == 64) CSN_BWD(4);
   else CSN_BWD(0);
 #undef CSN_BWD
-  // dW_ih[4H, I] = dG^T . x ; dW_hh[4H, H] = dG[1:]^T . h_seq[:-1]  (contraction over time*batch, split-K).
-  // Both products stream the same dG (the dominant operand, 115 MB at cfg2): they run SIDE BY SIDE on half the SMs
-  // each (fork / join on an internal stream, also valid under stream capture), so the second reader finds dG in L2.
-  // Split-K: every split stores its partial product to its own slab; bptt_finalize_kernel adds the slabs in split order.
-  SideStream* side = (T > 1) ? side_stream() : nullptr;
-  const int share = side ? 2 : 1;
-  if (side) {
-    CSN_CUDA(cudaEventRecord(side->fork, s));
-    CSN_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+  DwSources ih{}, hh{};
+  if (n_cons > 0) {
+    // the consumers' partial dW over [x | h_{t-1}] is already in the slabs: only the fixed-order fold is left
+    const int n_groups = n_cons / m_halves;
+    ih.a = DwSlabs{slabs, n_groups, side::dw_slab_floats(), 256, 0};
+    hh.a = DwSlabs{slabs, T > 1 ? n_groups : 0, side::dw_slab_floats(), 256, i_pad};
   }
-  GemmEpi slab_ih{}, slab_hh{};
-  slab_ih.split_stride = size_t(4) * H * I;
-  slab_hh.split_stride = size_t(4) * H * H;
-  const int s_ih = gemm_tc_splits((int)tb, max(1, dw_split_req(4 * H, I) / share));
-  const int s_hh = T > 1 ? gemm_tc_splits((int)(tb - B), max(1, dw_split_req(4 * H, H) / share)) : 0;
-  CSN_TRY(gemm_tc_run(1, 0, 4 * H, I, (int)tb, dG, 4 * H, x, I, slabs_ih, I, CSN_F32, nullptr, 0, s_ih, &slab_ih, s));
-  if (T > 1) {
-    cudaStream_t s2 = side ? side->st : s;
-    int r2 = gemm_tc_run(1, 0, 4 * H, H, (int)(tb - B), dG + size_t(B) * 4 * H, 4 * H, h_seq, H, slabs_hh, H, CSN_F32, nullptr, 0,
-                         s_hh, &slab_hh, s2);
-    if (side) {  // always rejoin (a capture must not end with a dangling fork)
-      CSN_CUDA(cudaEventRecord(side->join, side->st));
-      CSN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+  ih.b = DwSlabs{slabs, 0, 0, I, 0};
+  hh.b = DwSlabs{slabs, 0, 0, H, 0};
+  if (rows_post > 0) {
+    // dW_ih[4H, I] += dG^T . x ; dW_hh[4H, H] += dG[1:]^T . h_seq[:-1] over the rows the consumers did not take (all of
+    // them without consumers): contraction over time*batch, split-K slabs.  Both products stream the same dG: they run
+    // SIDE BY SIDE on half the SMs each (fork / join on an internal stream, also valid under stream capture), so the
+    // second reader finds dG in L2.
+    float* slabs_ih = slabs + size_t(kMaxConsumers) * side::dw_slab_floats();
+    float* slabs_hh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(slabs_ih) + align256(size_t(dw_split_req(4 * H, I)) * 4 * H * I * 4));
+    const bool has_hh = rows_post > B;
+    SideStream* side = has_hh ? side_stream() : nullptr;
+    const int share = side ? 2 : 1;
+    if (side) {
+      CSN_CUDA(cudaEventRecord(side->fork, s));
+      CSN_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
     }
-    CSN_TRY(r2);
+    GemmEpi slab_ih{}, slab_hh{};
+    slab_ih.split_stride = size_t(4) * H * I;
+    slab_hh.split_stride = size_t(4) * H * H;
+    const int s_ih = gemm_tc_splits(rows_post, std::max(1, dw_split_req(4 * H, I) / share));
+    const int s_hh = has_hh ? gemm_tc_splits(rows_post - B, std::max(1, dw_split_req(4 * H, H) / share)) : 0;
+    CSN_TRY(gemm_tc_run(1, 0, 4 * H, I, rows_post, dG, 4 * H, x, I, slabs_ih, I, CSN_F32, nullptr, 0, s_ih, &slab_ih, s));
+    if (has_hh) {
+      cudaStream_t s2 = side ? side->st : s;
+      int r2 = gemm_tc_run(1, 0, 4 * H, H, rows_post - B, dG + size_t(B) * 4 * H, 4 * H, h_seq, H, slabs_hh, H, CSN_F32, nullptr, 0,
+                           s_hh, &slab_hh, s2);
+      if (side) {  // always rejoin (a capture must not end with a dangling fork)
+        CSN_CUDA(cudaEventRecord(side->join, side->st));
+        CSN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+      }
+      CSN_TRY(r2);
+    }
+    ih.b = DwSlabs{slabs_ih, s_ih, slab_ih.split_stride, I, 0};
+    hh.b = DwSlabs{slabs_hh, s_hh, slab_hh.split_stride, H, 0};
   }
-  bptt_finalize_kernel<<<ceil_div(4 * H * (I + H + 1), 256), 256, 0, s>>>(slabs_ih, s_ih, slabs_hh, s_hh, db_part, n_part, dw_ih,
-                                                                          dw_hh, db_ih, db_hh, H, I, accumulate);
+  bptt_finalize_kernel<<<ceil_div(4 * H * (I + H + 1), 256), 256, 0, s>>>(ih, hh, db_part, n_part, dw_ih, dw_hh, db_ih, db_hh, H, I,
+                                                                          accumulate);
   CSN_LAUNCH_CHECK();
-  if (dx) {
-    CSN_TRY(csn_cast(w_ih, CSN_F32, wih_bf, CSN_BF16, size_t(4) * H * I, s));
+  if (dx) {  // dX = dG . W_ih with W_ih's rows in dG's gate-interleaved order
+    interleave_rows_bf16_kernel<<<4 * H, 128, 0, s>>>(w_ih, wih_bf, H, I);
+    CSN_LAUNCH_CHECK();
     CSN_TRY(gemm_tc_run(0, 0, (int)tb, I, 4 * H, dG, 4 * H, wih_bf, I, dx, I, CSN_F32, nullptr, 0, 1, nullptr, s));
   }
   return CSN_OK;
@@ -1060,203 +1277,11 @@ extern "C" int csn_lstm_set_cta_budget(int max_ctas) {
   return CSN_OK;
 }
 
-// ---------------------------------------------------------------------------------------- bring-up hook
-// D[128, N] = A[128, K] . B[N, K]^T with both operands staged by threads into the no-swizzle canonical layouts
-// (K-major or MN-major), one tcgen05.mma chain, tcgen05.ld epilogue.  Exercises exactly the descriptor
-// conventions the recurrence kernels rely on.
-__global__ void __launch_bounds__(128, 1) dbg_umma_tile_kernel(const __nv_bfloat16* __restrict__ A,
-                                                              const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D,
-                                                              int N, int K, int a_mode, int b_mn) {
-  // a_mode: 0 = K-major shared memory, 1 = MN-major shared memory, 2 = tensor memory (TS form of tcgen05.mma)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  const uint32_t a_bytes = 128 * K * 2, b_bytes = N * K * 2;
-  uint8_t* sa = base;
-  uint8_t* sb = base + a_bytes;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + b_bytes);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t lbo_a = 16 * 128, lbo_b = (N / 8) * 128, sbo = 128;
-  if (a_mode != 2) {
-    for (int e = tid; e < 128 * K; e += 128) {
-      int r = e / K, k = e % K;
-      uint32_t off = a_mode ? canon_mn_off(r, k, lbo_a, sbo) : canon_k_off(r, k, lbo_a, sbo);
-      *reinterpret_cast<__nv_bfloat16*>(sa + off) = A[e];
-    }
-  }
-  for (int e = tid; e < N * K; e += 128) {
-    int r = e / K, k = e % K;
-    uint32_t off = b_mn ? canon_mn_off(r, k, lbo_b, sbo) : canon_k_off(r, k, lbo_b, sbo);
-    *reinterpret_cast<__nv_bfloat16*>(sb + off) = Bm[e];
-  }
-  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-  const uint32_t a_col0 = 256;  // A operand columns when it lives in tensor memory (K/2 <= 128 columns)
-  const uint32_t ncols = (a_mode == 2) ? 512 : (N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)));
-  if (warp == 0) tmem_alloc(slot, ncols);
-  fence_proxy_async_smem();
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *slot;
-  if (a_mode == 2) {
-    const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
-    for (int c0 = 0; c0 < K / 2; c0 += 32) {
-      uint32_t r[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int k = (c0 + c) * 2;
-        __nv_bfloat162 bb;
-        bb.x = (k < K) ? A[size_t(tid) * K + k] : __float2bfloat16(0.f);
-        bb.y = (k + 1 < K) ? A[size_t(tid) * K + k + 1] : __float2bfloat16(0.f);
-        r[c] = *reinterpret_cast<uint32_t*>(&bb);
-      }
-      tmem_st32(lane_addr + a_col0 + c0, r);
-    }
-    tmem_st_wait();
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-  }
-  if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, N, a_mode == 1 ? 1 : 0, b_mn);
-    for (int kk = 0; kk < K / 16; ++kk) {
-      uint64_t db = make_smem_desc(smem_u32(sb) + kk * 2 * lbo_b, lbo_b, sbo, kLayoutNone);
-      if (a_mode == 2) {
-        umma_f16_ts(tmem_base, tmem_base + a_col0 + kk * 8, db, idesc, kk != 0);
-      } else {
-        uint64_t da = make_smem_desc(smem_u32(sa) + kk * 2 * lbo_a, lbo_a, sbo, kLayoutNone);
-        umma_f16(tmem_base, da, db, idesc, kk != 0);
-      }
-    }
-    umma_commit(bar);
-  }
-  mbar_wait(bar, 0);
-  tcgen05_fence_after();
-  for (int c0 = 0; c0 < N; c0 += 16) {
-    uint32_t r[16];
-    tmem_ld<16>(tmem_base + (uint32_t(warp * 32) << 16) + c0, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) D[size_t(tid) * N + c0 + j] = __uint_as_float(r[j]);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, ncols); }
-}
-
-
-// ---- tcgen05.mma issue / completion cost microbenchmark (bring-up): one CTA, 32 unrolled MMAs per repetition ----
-// Addresses are immediates and the issue is elect-guarded, like the recurrence kernels.  NACC accumulators are used
-// round-robin (NACC = 1: every MMA accumulates into the same D).
-template <int NACC, bool TS, int BREUSE = 1>
-__device__ __forceinline__ void bench_issue32(uint64_t da0, uint64_t db0, uint32_t idesc, uint32_t lbo_a16, uint32_t lbo_b16) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int kk = (i / BREUSE) & 7;  // BREUSE consecutive MMAs share one B operand
-    const uint64_t db = db0 + uint64_t(kk) * (2 * lbo_b16);
-    if (TS) umma_f16_ts((i % NACC) * 16, 256 + kk * 8 + (i >> 3) * 64, db, idesc, 1u);
-    else umma_f16((i % NACC) * 16, da0 + uint64_t(kk) * (2 * lbo_a16), db, idesc, 1u);
-  }
-}
-
-__global__ void __launch_bounds__(128, 1) dbg_umma_bench_kernel(long long* __restrict__ out, int M, int N, int n_acc, int a_mode,
-                                                               int reps) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint8_t* sa = base;                    // A: 128 rows x 128 K bf16 (smem mode)
-  uint8_t* sb = base + 128 * 128 * 2;    // B: up to 256 rows x 128 K bf16
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 256 * 128 * 2);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (128 * 128 * 2 + 256 * 128 * 2) / 4; i += 128) reinterpret_cast<uint32_t*>(base)[i] = 0x3c003c00u;
-  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc(slot, 512);
-  fence_proxy_async_smem();
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *slot;
-  {
-    uint32_t r[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) r[c] = 0x3c003c00u;
-    for (int c0 = 0; c0 < 512; c0 += 32) tmem_st32(tmem_base + (uint32_t(warp * 32) << 16) + c0, r);
-    tmem_st_wait();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  if (warp == 0 && tmem_base == 0) {
-    const uint32_t idesc = make_idesc_bf16(M, N, 0, 0);
-    const uint32_t lbo_a = (M / 8) * 128, lbo_b = (N / 8) * 128;
-    const uint64_t da0 = make_smem_desc(smem_u32(sa), lbo_a, 128, kLayoutNone);
-    const uint64_t db0 = make_smem_desc(smem_u32(sb), lbo_b, 128, kLayoutNone);
-    uint32_t phase = 0;
-    for (int rep = 0; rep < reps; ++rep) {
-      long long t0 = 0, t1 = 0;
-      if (elect_one()) {
-        t0 = clock64();
-        if (a_mode == 3) {  // TMEM A, four consecutive MMAs share one B descriptor (the forward kernel's pattern)
-          bench_issue32<4, true, 4>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
-        } else if (a_mode == 2) {
-          if (n_acc == 1) bench_issue32<1, true>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
-          else if (n_acc == 4) bench_issue32<4, true>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
-          else bench_issue32<8, true>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
-        } else {
-          if (n_acc == 1) bench_issue32<1, false>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
-          else if (n_acc == 4) bench_issue32<4, false>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
-          else bench_issue32<8, false>(da0, db0, idesc, lbo_a >> 4, lbo_b >> 4);
-        }
-        t1 = clock64();
-        umma_commit(bar);
-      }
-      __syncwarp();
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      const long long t2 = clock64();
-      t0 = __shfl_sync(0xffffffffu, t0, 0) | 0;  // elected lane is lane 0 of a converged warp
-      if (tid == 0 && blockIdx.x == 0) {
-        out[rep * 2 + 0] = t1 - t0;
-        out[rep * 2 + 1] = t2 - t0;
-      }
-    }
-  } else if (tid == 0 && tmem_base != 0 && blockIdx.x == 0) {
-    out[0] = -1;
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
-}
-
 }  // namespace csn
 
 using namespace csn;
 
 extern "C" int csn_dbg_lstm_profile_buffer(long long* buf) {
   csn::g_prof_buf = buf;  // device buffer of at least 64*8 int64 (or NULL to switch the stamps off)
-  return CSN_OK;
-}
-
-extern "C" int csn_dbg_umma_tile(const void* A, const void* B, float* D, int N, int K, int a_mn_major, int b_mn_major,
-                                 void* stream) {
-  CSN_REQUIRE(A && B && D, "csn_dbg_umma_tile: null pointer");
-  CSN_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256, "csn_dbg_umma_tile: bad N/K");
-  CSN_REQUIRE(a_mn_major >= 0 && a_mn_major <= 2, "csn_dbg_umma_tile: a_mn_major must be 0 (K-major smem), 1 (MN-major smem) or 2 (tensor memory)");
-  const size_t smem = size_t(128) * K * 2 + size_t(N) * K * 2 + 256;
-  CSN_CUDA(cudaFuncSetAttribute(dbg_umma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dbg_umma_tile_kernel<<<1, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, N, K,
-                                                           a_mn_major, b_mn_major);
-  CSN_LAUNCH_CHECK();
-  return CSN_OK;
-}
-
-extern "C" int csn_dbg_umma_bench(long long* out, int M, int N, int n_acc, int a_mode, int reps, void* stream) {
-  static const int grid = [] { const char* e = getenv("CSN_UMMA_BENCH_GRID"); return e ? atoi(e) : 1; }();
-  CSN_REQUIRE(out && (M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && (n_acc == 1 || n_acc == 4 || n_acc == 8) &&
-                  reps >= 1 && reps <= 16, "csn_dbg_umma_bench: bad arguments");
-  const size_t smem = 128 * 128 * 2 + 256 * 128 * 2 + 256;
-  CSN_CUDA(cudaFuncSetAttribute(dbg_umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dbg_umma_bench_kernel<<<grid, 128, smem, as_stream(stream)>>>(out, M, N, n_acc, a_mode, reps);
-  CSN_LAUNCH_CHECK();
   return CSN_OK;
 }

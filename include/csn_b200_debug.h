@@ -18,6 +18,10 @@ int csn_dbg_lstm_profile_buffer(long long* buf);
 /* tcgen05.mma issue/completion cost microbenchmark: out[2*rep] = issue cycles, out[2*rep+1] = cycles until commit arrives */
 int csn_dbg_umma_bench(long long* out, int M, int N, int n_acc, int a_mode, int reps, void* stream);
 
+/* per-SM global store bandwidth: n_cta CTAs each write bytes_per_cta (multiple of 16 KB) reps times; mode 0 STG.128
+ * contiguous, 1 STG.128 in the GEMM-epilogue pattern (4 rows x 128 B at a 2 KB pitch), 2 TMA bulk stores; out[cta] = cycles */
+int csn_dbg_store_bw(float* dst, long long* out, size_t bytes_per_cta, int n_cta, int mode, int reps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,10 @@ def _cos(a, b):
 
 @pytest.mark.parametrize("T,B,I,H", [(6, 4, 16, 16), (50, 5, 32, 64), (30, 37, 128, 128), (24, 3, 96, 96), (440, 16, 128, 128),
                                      (16, 300, 64, 128),
+                                     # THE benchmark shape (cfg2: 128 recurrence CTAs of 2 trials + 20 Xp-server / dW-consumer CTAs)
+                                     (440, 256, 128, 128),
+                                     # side-role edges: rows not a multiple of the 128-row tile / 64-row chunk, I < 64, H = 16 / 48
+                                     (33, 7, 40, 48), (19, 129, 128, 16), (64, 64, 96, 112),
                                      # edges of the fused-projection kernel: T below one block of timesteps, single trial,
                                      # NV = 8 tiles (two timesteps per block), smallest sizes, and I > 128 (hoisted projection)
                                      (1, 2, 8, 8), (2, 1, 16, 32), (3, 5, 8, 128), (9, 700, 32, 32), (17, 640, 16, 64), (5, 4, 136, 64),
