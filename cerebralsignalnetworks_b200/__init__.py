@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import CsnError, LIB_PATH
 
 __all__ = ["CsnError", "LIB_PATH", "Model", "DINOHead", "DINOLoss", "MultiCropWrapper", "EEGFilters",
-           "DistillTrainStep", "ops", "IndexFlatL2", "IndexFlatIP", "retrieval",
+           "DistillTrainStep", "MultiCropDistillStep", "ops", "IndexFlatL2", "IndexFlatIP", "retrieval",
            "FeatureDistributionLoss", "CosineSimilarityLoss", "HyperParams", "loss_fn_kd", "loss_fn_kd_hinton",
            "cosine_similarity_loss"]
 
@@ -26,6 +26,9 @@ def __getattr__(name):  # lazy: keep `import cerebralsignalnetworks_b200` cheap 
     if name == "DistillTrainStep":
         from .train_step import DistillTrainStep
         return DistillTrainStep
+    if name == "MultiCropDistillStep":
+        from .multicrop_step import MultiCropDistillStep
+        return MultiCropDistillStep
     if name in ("FeatureDistributionLoss", "CosineSimilarityLoss", "HyperParams", "loss_fn_kd", "loss_fn_kd_hinton",
                 "cosine_similarity_loss"):
         from . import losses

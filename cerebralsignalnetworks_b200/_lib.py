@@ -46,6 +46,8 @@ SIGNATURES = {
     "csn_adam_step": [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _i, _f, _vp],
     "csn_adam_step_graph": [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _vp, _vp, _f, _vp],
     "csn_dp_last_timeout": [C.POINTER(_i)],
+    "csn_dp_allreduce_twoshot": [_vp, _vp, _i, _i, _sz, _sz, _vp, _i, _vp, _vp],
+    "csn_dp_wait_done": [_vp, _i, _vp, _i, _vp],
     "csn_dp_wait_done_zero": [_vp, _i, _vp, _vp, _sz, _vp],
     "csn_dp_adam_step_peer": [_vp, _vp, _vp, _sz, _vp, _vp, _i, _i, _vp, _sz, _f, _f, _vp, _vp, _f, _f, _f, _f, _f, _i, _f, _vp],
     "csn_feature_dist_loss_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp],
@@ -59,6 +61,9 @@ SIGNATURES = {
     "csn_topk_workspace_bytes": [_i, _i, _i, C.POINTER(_sz)],
     "csn_topk_search": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "csn_ema_update": [_vp, _vp, _sz, _f, _vp],
+    "csn_fused_optim_workspace_bytes": [_i, C.c_longlong, C.POINTER(_sz)],
+    "csn_fused_optim_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _i, _f, _f, _f, _i, _f, _f,
+                             _vp, _vp, _vp],
     "csn_clip_grad_segments": [_vp, _vp, _i, C.c_longlong, _vp, _f, _vp],
 }
 # bring-up / self-test hooks (include/csn_b200_debug.h): not part of the product ABI, bound for tests and scripts only

@@ -180,6 +180,110 @@ __global__ void __launch_bounds__(256) dp_adam_peer_kernel(float* __restrict__ p
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-shot all-reduce over peer memory for LARGE buffers (cfg3: 22.3 M parameters + the per-row centre statistics, 106 MB):
+// the one-shot exchange above makes every rank read every rank's whole buffer (4 P world bytes per rank: fine for the
+// 0.8 MB of cfg1/2, 8x the minimum at cfg3).  Here rank r REDUCES slice r (reads it from every peer, adds in rank order,
+// writes the sum into its own buffer), then every rank GATHERS the other ranks' reduced slices: 2 (n-1)/n 4 P bytes per
+// rank over NVLink, the ring-equivalent minimum, in two kernels ordered by epoch flags in peer memory:
+//   READY[src]   = e : rank src has written its part of the buffer for exchange e        (start of the reduce kernel)
+//   REDUCED[src] = e : rank src has reduced its slice                                      (last CTA of the reduce kernel)
+//   DONE[src]    = e : rank src has gathered every slice, nobody's buffer is read any more (last CTA of the gather kernel)
+// Every slice is summed by exactly one rank and copied: all replicas hold bit-identical results.  `lane` selects one of
+// the flag sets of the block, so independent exchanges (the DINO head's gradients, which are final long before BPTT
+// ends, and the rest) can be in flight at the same time on different streams.
+constexpr int kFlagReduced = 2 * kMaxWorld;
+constexpr int kLaneStride = 4 * kMaxWorld;  // uint32 words per flag set (>= 3 * kMaxWorld)
+
+struct PeerBufs {
+  float* buf[kMaxWorld];
+  unsigned* flags[kMaxWorld];
+};
+
+__device__ __forceinline__ void slice_range(size_t n4, int world, int r, size_t* b, size_t* e) {
+  const size_t per = (n4 + world - 1) / world;  // float4 units
+  *b = per * r < n4 ? per * r : n4;
+  *e = per * (r + 1) < n4 ? per * (r + 1) : n4;
+}
+
+__global__ void __launch_bounds__(256) dp_reduce_slice_kernel(const PeerBufs ps, int world, int rank, size_t off, size_t n4,
+                                                             const int* __restrict__ epoch_dev, int lane_id,
+                                                             unsigned* __restrict__ ticket, const Watchdog dog) {
+  __shared__ int s_last;
+  const unsigned e = (unsigned)(*epoch_dev + 1);
+  const int fl = lane_id * kLaneStride;
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(ps.flags[threadIdx.x] + fl + kFlagReady + rank, e);
+  }
+  if (threadIdx.x < world) wait_flag_ge(ps.flags[rank] + fl + kFlagReady + threadIdx.x, e, dog, fl + kFlagReady + threadIdx.x);
+  __syncthreads();
+  size_t b, en;
+  slice_range(n4, world, rank, &b, &en);
+  for (size_t i = b + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < en; i += size_t(gridDim.x) * blockDim.x) {
+    float4 G[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < world) G[r] = ld_peer_f4(ps.buf[r] + off + 4 * i);
+    float4 S = G[0];
+#pragma unroll
+    for (int r = 1; r < kMaxWorld; ++r)
+      if (r < world) { S.x += G[r].x; S.y += G[r].y; S.z += G[r].z; S.w += G[r].w; }
+    *reinterpret_cast<float4*>(ps.buf[rank] + off + 4 * i) = S;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) *ticket = 0u;
+    if (threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(ps.flags[threadIdx.x] + fl + kFlagReduced + rank, e);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dp_gather_slices_kernel(const PeerBufs ps, int world, int rank, size_t off, size_t n4,
+                                                              int* __restrict__ epoch_dev, int lane_id,
+                                                              unsigned* __restrict__ ticket, const Watchdog dog) {
+  __shared__ int s_last;
+  const unsigned e = (unsigned)(*epoch_dev + 1);
+  const int fl = lane_id * kLaneStride;
+  if (threadIdx.x < world) wait_flag_ge(ps.flags[rank] + fl + kFlagReduced + threadIdx.x, e, dog, fl + kFlagReduced + threadIdx.x);
+  __syncthreads();
+  for (int k = 1; k < world; ++k) {
+    const int r = (rank + k) % world;  // start with different peers on different ranks
+    size_t b, en;
+    slice_range(n4, world, r, &b, &en);
+    for (size_t i = b + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < en; i += size_t(gridDim.x) * blockDim.x)
+      *reinterpret_cast<float4*>(ps.buf[rank] + off + 4 * i) = ld_peer_f4(ps.buf[r] + off + 4 * i);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) {
+      *ticket = 0u;
+      *epoch_dev = (int)e;
+    }
+    if (threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(ps.flags[threadIdx.x] + fl + kFlagDone + rank, e);
+    }
+  }
+}
+
+// wait until every rank has finished exchange `*epoch_dev` of flag set `lane_id` (its DONE flags): this rank's part of the
+// buffer may be overwritten after it
+__global__ void dp_wait_done_kernel(const unsigned* __restrict__ flags_local, int world, const int* __restrict__ epoch_dev,
+                                    int lane_id, const Watchdog dog) {
+  if ((int)threadIdx.x < world)
+    wait_flag_ge(flags_local + lane_id * kLaneStride + kFlagDone + threadIdx.x, (unsigned)*epoch_dev, dog,
+                 lane_id * kLaneStride + kFlagDone + threadIdx.x);
+}
+
 }  // namespace csn
 
 using namespace csn;
@@ -229,5 +333,43 @@ extern "C" int csn_dp_last_timeout(int* out4) {
   CSN_REQUIRE(out4, "csn_dp_last_timeout: null pointer");
   const Watchdog wd = make_watchdog(-1);
   for (int i = 0; i < 4; ++i) out4[i] = wd.host_slot ? (int)reinterpret_cast<volatile unsigned*>(wd.host_slot)[i] : 0;
+  return CSN_OK;
+}
+
+extern "C" int csn_dp_allreduce_twoshot(void* const* buf_ptrs, void* const* flag_ptrs, int world, int rank, size_t offset,
+                                        size_t n, int* epoch_counter, int flag_set, unsigned* ticket, void* stream) {
+  CSN_REQUIRE(buf_ptrs && flag_ptrs && epoch_counter && ticket, "csn_dp_allreduce_twoshot: null pointer");
+  CSN_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
+              "csn_dp_allreduce_twoshot: need 1 <= world <= %d and 0 <= rank < world", kMaxWorld);
+  CSN_REQUIRE(offset % 4 == 0 && n % 4 == 0, "csn_dp_allreduce_twoshot: offset and length must be multiples of 4 floats");
+  CSN_REQUIRE(flag_set >= 0 && flag_set < 2, "csn_dp_allreduce_twoshot: flag_set must be 0 or 1 (flag block of >= 64 words)");
+  PeerBufs ps{};
+  for (int r = 0; r < world; ++r) {
+    CSN_REQUIRE(buf_ptrs[r] && flag_ptrs[r], "csn_dp_allreduce_twoshot: null peer pointer for rank %d", r);
+    CSN_REQUIRE((reinterpret_cast<uintptr_t>(buf_ptrs[r]) & 15) == 0, "csn_dp_allreduce_twoshot: peer buffer %d not 16-byte aligned", r);
+    ps.buf[r] = reinterpret_cast<float*>(buf_ptrs[r]);
+    ps.flags[r] = reinterpret_cast<unsigned*>(flag_ptrs[r]);
+  }
+  if (n == 0) return CSN_OK;
+  cudaStream_t s = as_stream(stream);
+  const size_t n4 = n / 4;
+  const Watchdog dog = make_watchdog(rank);
+  // enough loads in flight to fill the NVLink pipe (latency ~2 us, 770 GB/s: ~1.5 MB) without taking every SM
+  const size_t per = ceil_div<size_t>(n4, world);
+  const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>(ceil_div<size_t>(per, 256), size_t(sm_count()) * 2));
+  dp_reduce_slice_kernel<<<blocks, 256, 0, s>>>(ps, world, rank, offset, n4, epoch_counter, flag_set, ticket, dog);
+  CSN_LAUNCH_CHECK();
+  dp_gather_slices_kernel<<<blocks, 256, 0, s>>>(ps, world, rank, offset, n4, epoch_counter, flag_set, ticket + 1, dog);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
+extern "C" int csn_dp_wait_done(const void* flags_local, int world, const int* epoch_counter, int flag_set, void* stream) {
+  CSN_REQUIRE(flags_local && epoch_counter, "csn_dp_wait_done: null pointer");
+  CSN_REQUIRE(world >= 1 && world <= kMaxWorld && flag_set >= 0 && flag_set < 2, "csn_dp_wait_done: bad arguments");
+  if (world == 1) return CSN_OK;
+  dp_wait_done_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned*>(flags_local), world, epoch_counter, flag_set,
+                                                       make_watchdog(-1));
+  CSN_LAUNCH_CHECK();
   return CSN_OK;
 }

@@ -75,3 +75,64 @@ class LocalExchange:
         self.grad_ptrs = (ctypes.c_void_p * 1)(self.buf.data_ptr())
         self.flag_ptrs = (ctypes.c_void_p * 1)(self.flags.data_ptr())
         self.ticket = torch.zeros(4, dtype=torch.int32, device=device)
+
+
+class TwoShotExchange:
+    """Peer-mapped flat fp32 buffer + flag block for csn_dp_allreduce_twoshot (the large exchanges of the
+    LstmDistillation step: 22.3 M gradients + per-row centre statistics at cfg3).  Up to two exchanges (flag sets) may be in
+    flight at once on different streams.  World size 1: an ordinary device buffer, the exchange is a no-op."""
+
+    def __init__(self, n_floats: int, device: torch.device):
+        import ctypes
+
+        self.world = world_size()
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        n_floats = (n_floats + 3) // 4 * 4
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            if self.world > 8:
+                raise RuntimeError("peer exchange supports up to 8 ranks (one NVSwitch domain)")
+            group = dist.group.WORLD
+            self.buf = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
+            self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+            self._h_buf = symm_mem.rendezvous(self.buf, group)
+            self._h_flags = symm_mem.rendezvous(self.flags, group)
+            self.buf.zero_()
+            self.flags.zero_()
+            torch.cuda.synchronize(device)
+            dist.barrier()  # nobody signals before every flag block is zero
+            bp, fp = list(self._h_buf.buffer_ptrs), list(self._h_flags.buffer_ptrs)
+            if len(bp) != self.world or bp[self.rank] != self.buf.data_ptr():
+                raise RuntimeError("symmetric-memory rendezvous returned an unexpected mapping")
+        else:
+            self.buf = torch.zeros(n_floats, dtype=torch.float32, device=device)
+            self.flags = torch.zeros(64, dtype=torch.int32, device=device)
+            bp, fp = [self.buf.data_ptr()], [self.flags.data_ptr()]
+        self.buf_ptrs = (ctypes.c_void_p * self.world)(*bp)
+        self.flag_ptrs = (ctypes.c_void_p * self.world)(*fp)
+        self.epochs = torch.zeros(2, dtype=torch.int32, device=device)   # one exchange counter per flag set
+        self.tickets = torch.zeros(4, dtype=torch.int32, device=device)  # two CTA-arrival words per flag set
+
+    def all_reduce_(self, offset: int, n: int, flag_set: int = 0):
+        """SUM over ranks of buf[offset : offset + n], in place, on the current stream."""
+        import ctypes
+
+        from . import _lib
+        if self.world == 1 or n == 0:
+            return
+        vp = ctypes.c_void_p
+        _lib.call("csn_dp_allreduce_twoshot", self.buf_ptrs, self.flag_ptrs, self.world, self.rank, int(offset), int(n),
+                  vp(self.epochs.data_ptr() + 4 * flag_set), int(flag_set), vp(self.tickets.data_ptr() + 8 * flag_set),
+                  vp(torch.cuda.current_stream().cuda_stream))
+
+    def wait_done(self, flag_set: int = 0):
+        """Every peer has gathered the last exchange of this flag set: the buffer range may be overwritten (stream op)."""
+        import ctypes
+
+        from . import _lib
+        if self.world == 1:
+            return
+        vp = ctypes.c_void_p
+        _lib.call("csn_dp_wait_done", vp(self.flags.data_ptr()), self.world, vp(self.epochs.data_ptr() + 4 * flag_set),
+                  int(flag_set), vp(torch.cuda.current_stream().cuda_stream))

@@ -162,9 +162,9 @@ class DINOLossFunction(torch.autograd.Function):
     """Loss and dLoss/dstudent come out of ONE kernel; backward just scales by the incoming gradient."""
 
     @staticmethod
-    def forward(ctx, student, teacher, center, student_temp, teacher_temp, mode, stats_out):
+    def forward(ctx, student, teacher, center, student_temp, teacher_temp, mode, stats_out, batch_center=None):
         loss, d_student, bc = ops.dino_loss_fwd_bwd(student.contiguous(), teacher.contiguous(), center.contiguous(),
-                                                    student_temp, teacher_temp, mode)
+                                                    student_temp, teacher_temp, mode, batch_center=batch_center)
         stats_out.append(bc)
         ctx.save_for_backward(d_student)
         ctx.needs_clone = False  # single backward pass per forward (retain_graph callers set this)
@@ -176,4 +176,4 @@ class DINOLossFunction(torch.autograd.Function):
         # d_student is owned by this node; scale in place with the (scalar) upstream gradient
         g = d_student.clone() if ctx.needs_clone else d_student
         ops.scale_(g, dloss.contiguous().to(torch.float32))
-        return g, None, None, None, None, None, None
+        return g, None, None, None, None, None, None, None

@@ -28,7 +28,10 @@ def get_params_groups(model):
 
 
 class FusedAdam:
-    def __init__(self, params_or_groups, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
+    def __init__(self, params_or_groups, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False,
+                 grad_buffer=None):
+        """grad_buffer: optional flat fp32 tensor (at least as long as the padded parameter count) that becomes the
+        gradient buffer -- e.g. a peer-mapped symmetric-memory buffer the data-parallel exchange reduces in place."""
         groups = list(params_or_groups)
         if groups and not isinstance(groups[0], dict):
             groups = [{"params": groups}]
@@ -51,7 +54,14 @@ class FusedAdam:
             raise ValueError("FusedAdam: no trainable parameters")
         dev = layout[0][0].device
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        if grad_buffer is not None:
+            if grad_buffer.numel() < total or grad_buffer.dtype != torch.float32 or grad_buffer.device != dev:
+                raise ValueError("FusedAdam: grad_buffer must be a float32 tensor of >= %d elements on %s" % (total, dev))
+            self.flat_g = grad_buffer[:total]
+            self.flat_g.zero_()
+        else:
+            self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.n_flat = total
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         for p, o in layout:
@@ -70,6 +80,18 @@ class FusedAdam:
         self._sumsq_buf = torch.zeros(len(layout) + self._n_chunks, dtype=torch.float32, device=dev)
         self._sumsq = self._sumsq_buf[:len(layout)]
         self._layout = layout
+        # ---- fused clip + AdamW + EMA sweep (csn_fused_optim_step) ----
+        seg_group = []
+        for gi, g in enumerate(self.param_groups):
+            seg_group += [gi] * len(g["params"])
+        self._seg_group = torch.tensor(seg_group, dtype=torch.int32, device=dev)
+        self._seg_active = torch.ones(len(layout), dtype=torch.int32, device=dev)
+        self._seg_step = torch.zeros(len(layout), dtype=torch.int32, device=dev)
+        self._group_of_seg = seg_group
+        n_hyper = 2 * len(self.param_groups) + 1
+        self._hyper_host = torch.zeros(n_hyper, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(n_hyper)
+        self._hyper_dev = torch.zeros(n_hyper, dtype=torch.float32, device=dev)
+        self._fused_ws = None
 
     def clip_gradients(self, clip):
         """Per-parameter L2 clipping (reference utils.clip_gradients) on the device; returns the squared norms tensor
@@ -86,6 +108,41 @@ class FusedAdam:
         epochs, which makes torch's optimiser SKIP those parameters (no moment update, no weight decay, no step
         count).  Put such parameters in their own param group and switch the group off for those steps."""
         self.param_groups[index]["active"] = bool(active)
+
+    def fused_step(self, clip=0.0, grad_scale=1.0, ema=None, ema_momentum=0.0, want_norms=False):
+        """clip_gradients + optimizer.step() + the EMA teacher update of LstmDistillation.py:607-619 as ONE sweep over the
+        flat buffers (csn_fused_optim_step): per-parameter clip of the rank-averaged gradient (grad_scale = 1 / world),
+        AdamW / Adam with each group's CURRENT lr / weight_decay (set them in param_groups as the reference loop does,
+        :540-544), groups switched off by set_group_active() skipped like p.grad = None, teacher = m teacher + (1 - m)
+        student for an EMATeacher `ema`.  No host sync; the hyper-parameters travel in a small pinned buffer, so a captured
+        CUDA graph of the step stays valid while the schedules move.  Returns the squared norms [n_param] if asked."""
+        import ctypes as _C
+        from . import _lib
+        n_groups = len(self.param_groups)
+        for gi, g in enumerate(self.param_groups):
+            self._hyper_host[2 * gi] = float(g["lr"])
+            self._hyper_host[2 * gi + 1] = float(g["weight_decay"])
+        self._hyper_host[2 * n_groups] = float(ema_momentum)
+        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+        active = [1 if self.param_groups[gi].get("active", True) else 0 for gi in self._group_of_seg]
+        if active != getattr(self, "_active_cached", None):
+            self._seg_active.copy_(torch.tensor(active, dtype=torch.int32))
+            self._active_cached = active
+        if self._fused_ws is None:
+            n = _C.c_size_t()
+            _lib.call("csn_fused_optim_workspace_bytes", self._n_seg, self._n_chunks, _C.byref(n))
+            self._fused_ws = torch.empty(n.value, dtype=torch.uint8, device=self.flat_p.device)
+        betas, eps = self.defaults["betas"], self.defaults["eps"]
+        vp = _C.c_void_p
+        _lib.call("csn_fused_optim_step", vp(self.flat_p.data_ptr()), vp(self.flat_g.data_ptr()), vp(self.exp_avg.data_ptr()),
+                  vp(self.exp_avg_sq.data_ptr()), vp(ema.teacher_flat.data_ptr()) if ema is not None else None,
+                  vp(self._seg_off.data_ptr()), vp(self._seg_group.data_ptr()), vp(self._seg_active.data_ptr()),
+                  vp(self._seg_step.data_ptr()), self._n_seg, self._n_chunks, vp(self._hyper_dev.data_ptr()), n_groups,
+                  float(betas[0]), float(betas[1]), float(eps), int(self.decoupled), float(clip), float(grad_scale),
+                  vp(self._sumsq_buf.data_ptr()) if want_norms else None, vp(self._fused_ws.data_ptr()),
+                  vp(torch.cuda.current_stream().cuda_stream))
+        self.step_count += 1
+        return self._sumsq if want_norms else None
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()  # gradients stay views of the flat buffer (never set to None)

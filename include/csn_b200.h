@@ -178,6 +178,19 @@ int csn_dp_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, size
                           float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled,
                           float grad_scale, void* stream);
 
+/* Two-shot all-reduce (SUM, in place) of floats [offset, offset + n) of the ranks' peer-mapped buffers, for the large
+ * exchanges of the LstmDistillation step (DDP's gradient all-reduce, LstmDistillation.py:445, 22.3 M parameters at cfg3,
+ * and the per-row centre statistics of DINOLoss.update_center, :154-156): rank r reduces slice r from every peer in rank
+ * order and writes it back, then every rank gathers the reduced slices -- 2 (n-1)/n 4 n bytes per rank over NVLink (the
+ * one-shot csn_dp_adam_step_peer reads world * 4 n).  Two kernels, ordered across ranks by epoch flags in peer memory;
+ * every replica ends with bit-identical sums.  buf_ptrs[r] / flag_ptrs[r]: rank r's buffer and flag block (>= 64 zeroed
+ * uint32) mapped into this process; epoch_counter: device int32 per flag set (advanced by the call); flag_set 0 / 1:
+ * two exchanges may be in flight at once on different streams; ticket: 2 zeroed device words per flag set.  Before a
+ * rank overwrites its part of the buffer again it must run csn_dp_wait_done (every peer has gathered). */
+int csn_dp_allreduce_twoshot(void* const* buf_ptrs, void* const* flag_ptrs, int world, int rank, size_t offset, size_t n,
+                             int* epoch_counter, int flag_set, unsigned* ticket, void* stream);
+int csn_dp_wait_done(const void* flags_local, int world, const int* epoch_counter, int flag_set, void* stream);
+
 /* ---- the losses LstmDistillFromDinoV2Train.py runs today, forward + backward -------------
  * FeatureDistributionLoss.forward (LstmDistillFromDinoV2Train.py:118-140, live at :371):
  *   loss = alpha * cross_entropy(pred, label) + beta * F.cross_entropy(softmax(teacher / T), softmax(student / T))
@@ -253,6 +266,22 @@ int csn_topk_search(const float* gallery, const float* query, int nb, int nq, in
 
 /* EMA teacher update over flat buffers: dst = momentum * dst + (1 - momentum) * src  (LstmDistillation.py:616-619) */
 int csn_ema_update(float* dst, const float* src, size_t n, float momentum, void* stream);
+
+/* The optimiser tail of the LstmDistillation step in ONE sweep over the flat buffers (SURVEY.md K8 + K9 + K10): per-parameter
+ * gradient clipping (utils/utils.py:132-141), AdamW / Adam over parameter groups whose lr / weight decay move every
+ * iteration (LstmDistillation.py:469-471, :540-544), parameters with a cancelled gradient skipped like torch skips
+ * p.grad = None (utils/utils.py:144-149), and the EMA teacher (LstmDistillation.py:616-619).
+ * The flat buffers are cut into n_seg parameters [seg_off[i], seg_off[i+1]) (device int64, offsets multiples of 4);
+ * n_chunks = sum_i ceil(len_i / 2048).  seg_group[i]: parameter group; seg_active[i]: 0 skips the parameter this step;
+ * seg_step[i]: its own step count (device int32, advanced by the call).  hyper (device floats): (lr, weight_decay) per
+ * group, then the EMA momentum -- rewritten by the caller between steps, so a captured graph of the step stays valid.
+ * grads are scaled by grad_scale (1/world) BEFORE the norm, as DDP averages before clip_gradients runs.  clip = 0: no
+ * clipping.  ema_params: the teacher's flat parameters (same layout) or NULL.  sumsq_out: n_seg squared norms or NULL. */
+int csn_fused_optim_workspace_bytes(int n_seg, long long n_chunks, size_t* bytes);
+int csn_fused_optim_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_params,
+                         const long long* seg_off_dev, const int* seg_group_dev, const int* seg_active_dev, int* seg_step_dev,
+                         int n_seg, long long n_chunks, const float* hyper_dev, int n_groups, float beta1, float beta2, float eps,
+                         int decoupled, float clip, float grad_scale, float* sumsq_out, void* workspace, void* stream);
 
 /* Per-parameter gradient clipping without host syncs (utils/utils.py:132-141).  The flat gradient buffer is cut into
  * n_seg segments [seg_off[i], seg_off[i+1]) (device int64 array of n_seg+1 offsets); n_chunks = sum_i ceil(len_i/2048);

@@ -1,4 +1,4 @@
 #!/bin/bash
-python -m pytest tests/test_gpu_lstm.py tests/test_gpu_determinism.py -q -x --timeout 120 2>&1 | tail -3
-for sh in 0.20 0.27 0.33 0.40 1.0; do echo share $sh; CSN_LSTM_CONSUMER_SHARE=$sh CSN_LSTM_NO_SERVERS=1 python scripts/lstm_layer_bench.py; done
-CSN_LSTM_NO_SERVERS=1 CSN_LSTM_NO_CONSUMERS=1 python scripts/lstm_layer_bench.py
+for b in 0 4 8 16 32; do echo XBURST $b; CSN_LSTM_XBURST=$b python scripts/lstm_layer_bench.py; done
+CSN_LSTM_XBURST=8 python -m pytest tests/test_gpu_lstm.py -q -x --timeout 120 2>&1 | tail -2
+CSN_LSTM_XBURST=8 python scripts/prof_lstm_steps.py 2>&1 | grep -A10 "^forward B"

@@ -236,3 +236,51 @@ def test_fused_adam_groups_clip_and_ema_match_torch(golden):
     np.testing.assert_allclose(sq.sqrt().cpu().numpy(), gold["clip_norms"], rtol=1e-5)
     for i, p in enumerate(lin.parameters()):
         np.testing.assert_allclose(p.grad.cpu().numpy(), gold[f"clip_gout{i}"], rtol=1e-5, atol=1e-7)
+
+
+def test_fused_optimizer_sweep_matches_torch_clip_adamw_ema():
+    """csn_fused_optim_step: per-parameter clip + AdamW groups with moving lr / wd + a group skipped for the first steps
+    (cancel_gradients_last_layer) + EMA teacher, in one sweep, against the same sequence written with torch."""
+    from cerebralsignalnetworks_b200.optim import EMATeacher, FusedAdam, get_params_groups
+    def make():
+        torch.manual_seed(3)
+        return torch.nn.Sequential(torch.nn.Linear(37, 61), torch.nn.Linear(61, 2500), torch.nn.Linear(2500, 3)).cuda()
+    ours, ref, teacher, ref_teacher = make(), make(), make(), make()
+    def groups(m):  # the last layer in its own group so that it can be frozen, rest split like get_params_groups
+        last = list(m[2].parameters())
+        rest = get_params_groups(torch.nn.Sequential(m[0], m[1]))
+        return rest + [{"params": last}]
+    opt = FusedAdam(groups(ours), lr=1e-3, weight_decay=0.04, decoupled=True)
+    ropt = torch.optim.AdamW(groups(ref), lr=1e-3, weight_decay=0.04)
+    ema = EMATeacher(teacher, opt, ours)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    world = 4  # gradients arrive as a SUM over ranks: the sweep folds the 1 / world in before the clip
+    for it in range(6):
+        lr, wd, mom = 1e-3 * (1 + it), 0.04 + 0.01 * it, 0.9 + 0.01 * it
+        for i, (a, b) in enumerate(zip(opt.param_groups, ropt.param_groups)):
+            a["lr"] = b["lr"] = lr
+            if i != 1:  # the no-decay group keeps wd 0 (LstmDistillation.py:543)
+                a["weight_decay"] = b["weight_decay"] = wd
+        frozen = it < 2
+        opt.set_group_active(2, not frozen)
+        x = torch.randn(11, 37, device="cuda", generator=g)
+        opt.zero_grad(); ropt.zero_grad()
+        (ours(x).pow(2).sum() * world).backward()
+        ref(x).pow(2).sum().backward()
+        for p in ref.parameters():  # utils.clip_gradients
+            coef = 0.3 / (p.grad.norm(2) + 1e-6)
+            if coef < 1:
+                p.grad.mul_(coef)
+        if frozen:  # cancel_gradients_last_layer: p.grad = None -> torch skips the parameter
+            for p in ref[2].parameters():
+                p.grad = None
+        norms = opt.fused_step(clip=0.3, grad_scale=1.0 / world, ema=ema, ema_momentum=mom, want_norms=True)
+        ropt.step()
+        with torch.no_grad():
+            for q, k in zip(ref.parameters(), ref_teacher.parameters()):
+                k.mul_(mom).add_((1 - mom) * q.detach())
+        assert torch.isfinite(norms).all()
+    for a, b in zip(ours.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-6)
+    for a, b in zip(teacher.parameters(), ref_teacher.parameters()):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-6)
