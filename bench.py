@@ -249,6 +249,128 @@ def cpu_reference_step_rate(batch, steps, warmup, threads=None):
     return batch * steps / dt, 1e3 * dt / steps, cores
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The other GPU configurations of BASELINE.json, measured in the same run at the same N (sub-records of the JSON line).
+def _timed_steps(torch, dist, world, dev, fn, n, warm):
+    """warm untimed + n timed calls of fn(i) bracketed by barrier + synchronize, CUDA events, max over ranks -> ms per call."""
+    for i in range(warm):
+        fn(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        fn(warm + i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / n
+
+
+def bench_cfg3(torch, dist, csn, dev, world, rank, steps, peaks):
+    """configs[2]: LstmDistillation DINO step -- 64 trials per GPU of 96 ch x 495 samples, 2 x 300 + 4 x 200 crops, 4-layer
+    LSTM (hidden 128) student / teacher, DINOHead K = 65536, reference multi-crop loss, two-shot gradient + centre exchange,
+    fused clip + AdamW + EMA sweep (MultiCropDistillStep)."""
+    import numpy as np
+    from cerebralsignalnetworks_b200.schedules import cosine_scheduler
+    B, C, T, H, L, K = 64, 96, 495, 128, 4, 65536
+    torch.manual_seed(CFG["seed"])
+    np.random.seed(CFG["seed"])  # same crop starts on every rank
+
+    def make():
+        return csn.MultiCropWrapper(csn.Model(C, H, L, H, include_top=False, compute_dtype=torch.bfloat16),
+                                    csn.DINOHead(H, K, compute_dtype=torch.bfloat16)).to(dev)
+    student, teacher = make(), make()
+    crit = csn.DINOLoss(K, 6, 0.04, 0.04, 30, 100).to(dev)
+    n_it = 4096
+    lr = cosine_scheduler(5e-4 * B * world / 256.0, 1e-6, 1, n_it, warmup_epochs=0)
+    wd = cosine_scheduler(0.04, 0.4, 1, n_it)
+    mom = cosine_scheduler(0.996, 1.0, 1, n_it)
+    step = csn.MultiCropDistillStep(student, teacher, crit, lr, wd, mom, clip_grad=3.0, freeze_last_layer=0, batch_size=B)
+    g = torch.Generator(device=dev).manual_seed(31 + rank)
+    eeg = [torch.randn(B, T, C, device=dev, generator=g) for _ in range(4)]
+    n = max(3, min(steps, 15))
+    ms = _timed_steps(torch, dist, world, dev, lambda i: step.step(eeg[i % 4], epoch=0), n, 3)
+    # algorithmic work per trial (SURVEY.md 8d): LSTM 4.88 GFLOP (student fwd + bwd, teacher fwd) + DINO head 0.87 GFLOP
+    flop = (4.88e9 + 0.87e9) * B
+    tf = flop / (ms * 1e-3) / 1e12
+    peak = peaks["tflops_sustained"] or peaks["tflops"]
+    n_param = step.opt.n_flat
+    del step, student, teacher, crit, eeg
+    torch.cuda.empty_cache()
+    return {"workload": "cfg3 LstmDistillation DINO step: 96ch x 495, crops 2x300 + 4x200, LSTM L4 H128 student + teacher, "
+                        "DINOHead K=65536, multi-crop loss, clip + AdamW + EMA", "batch_per_gpu": B, "global_batch": B * world,
+            "value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": n,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                         "note": "5.75 GFLOP algorithmic per trial (SURVEY 8d); three serial LSTM chains of 200-300 steps x 4 layers"},
+            "exchange": {"kind": "two-shot reduce-scatter + all-gather over peer memory" if world > 1 else "none",
+                         "floats": n_param + B * K, "bytes_per_rank_over_nvlink": (2.0 * (world - 1) / world * 4 * (n_param + B * K)) if world > 1 else 0}}
+
+
+def bench_cfg4(torch, dist, csn, dev, world, rank, steps, peaks):
+    """configs[3]: stacked 2-layer LSTM hidden 512, 768-d targets, global batch 1024 sharded over the ranks (N = 1: the
+    128-trial shard of the 8-GPU run)."""
+    B = 1024 // world if world > 1 else 128
+    torch.manual_seed(CFG["seed"])
+    model = csn.Model(128, 512, 2, 768, include_top=False, compute_dtype=torch.bfloat16).to(dev)
+    crit = csn.DINOLoss(768, 1, 1.5, 0.22, 50, 100).to(dev)
+    step = csn.DistillTrainStep(model, crit, lr=1e-3, sos=csn.EEGFilters(1000.0).sos(5.0, 95.0, 4))
+    g = torch.Generator(device=dev).manual_seed(41 + rank)
+    eeg = [torch.randn(B, 128, 440, device=dev, generator=g) for _ in range(3)]
+    feats = [torch.randn(B, 768, device=dev, generator=g) for _ in range(3)]
+    for e_, f_ in zip(eeg, feats):
+        step.register_inputs(e_, f_)
+    n = max(3, min(steps, 8))
+    ms = _timed_steps(torch, dist, world, dev, lambda i: step.step(eeg[i % 3], feats[i % 3], epoch=0), n, 4)
+    flop = 8.997e9 * B  # SURVEY 8d: train step, L2 H512 I128 T440
+    tf = flop / (ms * 1e-3) / 1e12
+    peak = peaks["tflops_sustained"] or peaks["tflops"]
+    ex = step.dp_exchange
+    step._graph = None
+    del step, model, crit, eeg, feats
+    torch.cuda.empty_cache()
+    return {"workload": "cfg4 distill step: 128ch x 440, stacked LSTM L2 H512, 768-d targets, band-pass, DINO CE, Adam",
+            "batch_per_gpu": B, "global_batch": B * world, "value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "steps": n, "dp_exchange": ex,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                         "note": "8.997 GFLOP algorithmic per trial (SURVEY 8d); one tcgen05 GEMM + fused cell epilogue per timestep"}}
+
+
+def bench_cfg5(torch, dist, csn, dev, world, rank, steps, peaks):
+    """configs[4]: Perils-shaped trials (63 ch x 2000 samples) -> band-pass -> encoder inference -> exact top-5 (squared L2,
+    what the reference's faiss IndexFlatL2 returns) over a 10 k gallery.  Replicas: every rank serves its own queries."""
+    from cerebralsignalnetworks_b200 import retrieval
+    B, C, T, H, D, NB, K = 256, 63, 2000, 128, 384, 10000, 5
+    torch.manual_seed(CFG["seed"])
+    model = csn.Model(C, H, 1, D, include_top=False, compute_dtype=torch.bfloat16).to(dev).eval()
+    sos = csn.EEGFilters(1000.0).sos(5.0, 95.0, 4)
+    g = torch.Generator(device=dev).manual_seed(51 + rank)
+    eeg = [torch.randn(B, C, T, device=dev, generator=g) for _ in range(3)]
+    gallery = torch.randn(NB, D, device=dev, generator=g)
+
+    def query(i):
+        emb = model.encode_trials(eeg[i % 3], sos=sos)
+        return retrieval.topk_search(gallery, emb, K, retrieval.METRIC_L2)
+    n = max(3, min(steps, 10))
+    ms = _timed_steps(torch, dist, world, dev, query, n, 2)
+    filt_bytes = 8.0 * C * T * B
+    del model, eeg, gallery
+    torch.cuda.empty_cache()
+    return {"workload": "cfg5 retrieval: 63ch x 2000 trials -> band-pass -> LSTM L1 H128 encoder inference -> top-5 L2 over a "
+                        "10k x 384 gallery", "batch_per_gpu": B, "value": world * B / (ms * 1e-3), "unit": "queries/s",
+            "ms_per_batch": ms, "steps": n, "scaling": "replicas",
+            "roofline": {"bound": "tensor (serial chain)", "note": "2000 dependent recurrence steps of 256 trials: latency bound; "
+                         "filter algorithmic bytes %d per batch" % filt_bytes,
+                         "achieved": 8.0 * T * H * (64 + H) * B / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                         "peak": peaks["tflops_sustained"] or peaks["tflops"],
+                         "frac": 8.0 * T * H * (64 + H) * B / (ms * 1e-3) / 1e12 / (peaks["tflops_sustained"] or peaks["tflops"])}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -286,6 +408,7 @@ def main():
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--batch_per_gpu", type=int, default=CFG["batch_per_gpu"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--configs", type=str, default="3,4,5", help="extra BASELINE.json configs measured as sub-records ('' = none)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -488,6 +611,19 @@ def main():
             dist.all_reduce(ds_ms, op=dist.ReduceOp.MAX)
         ds_ms = float(ds_ms)
 
+    # ---------------- the other configurations, same run, same N (sub-records) ----------------
+    extra = {}
+    peaks_ = measured_peaks()
+    step._graph = None
+    for tag, fn in (("3", bench_cfg3), ("4", bench_cfg4), ("5", bench_cfg5)):
+        if tag not in [c.strip() for c in args.configs.split(",") if c.strip()]:
+            continue
+        try:
+            extra["cfg" + tag] = fn(torch, dist, csn, dev, world, rank, args.steps, peaks_)
+        except Exception as exc:  # report, do not hide (deterministic across ranks: nobody is left in a collective)
+            extra["cfg" + tag] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            print("cfg%s sub-bench failed: %r" % (tag, exc), file=sys.stderr)
+
     def finish():
         # Multi-rank teardown: every rank meets at a barrier, then leaves without tearing NCCL down.  (Destroying the
         # process group while captured graphs still hold NCCL kernels hung rank teardown for minutes on the GPU box;
@@ -550,6 +686,7 @@ def main():
                           "frac": (loss_gbs / peaks["hbm_gbs"]) if loss_gbs else None, "traffic": ncu_traffic(["dino_loss_staged_kernel"]),
                           "peak_source": peaks["source"]},
         "stages_ms": stages,
+        "configs": extra,
         "step_submission": "cuda_graph_replay",
         "dp_exchange": step.dp_exchange,
         "loss": final_loss,

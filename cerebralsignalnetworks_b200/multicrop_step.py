@@ -97,6 +97,12 @@ class MultiCropDistillStep:
         self.concurrent = bool(concurrent)
         self.cta_budget = int(cta_budget)
         if self.concurrent:
+            # the student's two backbone passes run (and are differentiated) on their own streams on purpose
+            try:
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            except AttributeError:
+                pass
+        if self.concurrent:
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
         self.it = 0
 

@@ -193,3 +193,19 @@ def test_multicrop_step_two_ranks_match_reference_loop(tmp_path):
         assert torch.equal(out[0]["sp"][n], out[1]["sp"][n]), n
         assert torch.equal(out[0]["tp"][n], out[1]["tp"][n]), n
     assert torch.equal(out[0]["center"], out[1]["center"])
+
+
+def test_dino_cli_trains_and_checkpoints(tmp_path, capsys):
+    """`cli_dino` (the LstmDistillation.py entry point's flags) runs two synthetic epochs and writes log.txt + checkpoint.pth
+    with the reference's checkpoint keys (LstmDistillation.py:634-646)."""
+    import json
+    from cerebralsignalnetworks_b200 import cli_dino
+    out = str(tmp_path)
+    cli_dino.main(["--batch_size_per_gpu", "4", "--epochs", "2", "--out_dim", "64", "--channels", "16", "--samples", "330",
+                   "--lstm_size", "32", "--lstm_layers", "2", "--trials_per_epoch", "12", "--warmup_epochs", "1",
+                   "--warmup_teacher_temp_epochs", "1", "--saveckp_freq", "1", "--output_dir", out, "--precision", "fp32"])
+    lines = [json.loads(l) for l in open(os.path.join(out, "log.txt"))]
+    assert len(lines) == 2 and all(np.isfinite(l["train_loss"]) for l in lines)
+    ck = torch.load(os.path.join(out, "checkpoint.pth"), weights_only=False)
+    assert {"student", "teacher", "epoch", "args", "dino_loss"} <= set(ck)
+    assert any(k.startswith("backbone.lstm.weight_ih_l0") for k in ck["teacher"])

@@ -159,3 +159,16 @@ def test_resident_dataset_host_side_batching_and_index_checks():
     for bad, exc in (([22], IndexError), ([-23], IndexError), ([[0, 1]], CsnError)):
         with pytest.raises(exc):
             ds.check_indices(bad)
+
+
+def test_dino_cli_has_the_reference_flags_and_defaults():
+    """cli_dino mirrors LstmDistillation.py:187-348 (the flags SURVEY.md section 5 lists, with the reference's defaults)."""
+    from cerebralsignalnetworks_b200 import cli_dino
+    a = cli_dino.build_parser().parse_args([])
+    assert (a.batch_size_per_gpu, a.epochs, a.out_dim) == (8, 200, 384)
+    assert (a.warmup_teacher_temp, a.teacher_temp, a.warmup_teacher_temp_epochs) == (0.04, 0.04, 30)
+    assert (a.lr, a.min_lr, a.warmup_epochs, a.weight_decay, a.weight_decay_end) == (0.0005, 1e-06, 10, 0.04, 0.4)
+    assert (a.clip_grad, a.freeze_last_layer, a.momentum_teacher, a.local_crops_number, a.seed) == (3.0, 1, 0.996, 4, 43)
+    b = cli_dino.build_parser().parse_args(["--batch_size_per_gpu", "64", "--epochs", "100", "--out_dim", "65536",
+                                            "--norm_last_layer", "false"])
+    assert (b.batch_size_per_gpu, b.epochs, b.out_dim, b.norm_last_layer) == (64, 100, 65536, False)
