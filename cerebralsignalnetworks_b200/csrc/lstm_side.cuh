@@ -18,6 +18,7 @@
 // spin carries a watchdog so that a scheduling surprise traps instead of hanging the device.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "tc.cuh"
 
@@ -100,14 +101,43 @@ __device__ __forceinline__ void drain_chunk(uint32_t taddr, float* tile, int lan
   __syncwarp();
 }
 
+// 64 columns of a [128-lane x N] fp32 accumulator -> fp16 global rows, 128 contiguous bytes per row and store: the same
+// staging, half the bytes (an SM writes global memory at 32 B/clk at most, scripts/store_bw.py: the output format decides
+// what the Xp servers can deliver).  dst: (row 0 of this warp's 32 rows, column 0 of the chunk); ld in halves.
+__device__ __forceinline__ void drain_chunk_half(uint32_t taddr, uint8_t* tile, int lane, __half* dst, size_t ld, int rows_ok) {
+  uint32_t r0[32], r1[32];
+  tmem_ld<32>(taddr, r0);
+  tmem_ld<32>(taddr + 32, r1);
+  tmem_ld_wait();
+  uint32_t h[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __half2 a = __floats2half2_rn(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+    const __half2 b = __floats2half2_rn(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+    h[i] = *reinterpret_cast<const uint32_t*>(&a);
+    h[16 + i] = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  constexpr int kRow = kEpiTileStride * 4;  // 144 B per staged row: 128 B of data + 16 B bank rotation
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4)
+    *reinterpret_cast<uint4*>(tile + lane * kRow + q4 * 16) = make_uint4(h[q4 * 4], h[q4 * 4 + 1], h[q4 * 4 + 2], h[q4 * 4 + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    const uint4 v = *reinterpret_cast<const uint4*>(tile + rr * kRow + (lane & 7) * 16);
+    if (rr < rows_ok) *reinterpret_cast<uint4*>(dst + size_t(rr) * ld + (lane & 7) * 8) = v;
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ forward: Xp servers
 struct XpServe {
   int n_srv;        // server CTAs = the first n_srv blocks of the launch (0: Xp is precomputed, nobody waits)
   int n_tiles;      // ceil(rows / 128)
   int rows;         // T * B
   int I, H;
-  float* xp;        // [rows, 4H] fp32, gate-major columns g*H + u
-  const float* b_ih;
+  __half* xp;       // [rows, 4H] fp16, gate-major columns g*H + u, WITHOUT the bias (the recurrence adds b_ih + b_hh)
   unsigned* flags;  // [n_tiles], zeroed before the launch; 1 = the tile's rows of Xp are in memory
 };
 
@@ -126,7 +156,7 @@ __host__ __device__ inline size_t xp_server_smem(int H) {
 }
 
 // blockDim >= 320: warps 0-7 epilogue (TMEM lane quadrant w % 4, 32-column chunks of parity w / 4), warp 8 MMA issuer
-// (+ tensor-memory owner), warp 9 TMA producer.  Requires I <= 128, I % 8 == 0, H <= 128, H % 16 == 0.
+// (+ tensor-memory owner), warp 9 TMA producer.  Requires I <= 128, I % 8 == 0, H <= 128, H % 32 == 0.
 __device__ __forceinline__ void xp_server_role(uint8_t* smem_raw, const CUtensorMap* tm_x, const CUtensorMap* tm_w,
                                                const XpServe& sv, int srv) {
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -209,7 +239,7 @@ __device__ __forceinline__ void xp_server_role(uint8_t* smem_raw, const CUtensor
   } else if (warp < 8) {
     const int q = warp & 3, par = warp >> 2;
     float* tile_s = epi + warp * (32 * kEpiTileStride);
-    const int nch = N2 / 32;
+    const int nch = N2 / 64;
     uint32_t ti = 0;
     for (int tile = srv; tile < sv.n_tiles; tile += sv.n_srv, ++ti) {
       const int row0 = tile * 128 + q * 32;
@@ -218,9 +248,9 @@ __device__ __forceinline__ void xp_server_role(uint8_t* smem_raw, const CUtensor
         mbar_wait(&acc_full[half], ti & 1);
         tcgen05_fence_after();
         for (int c = par; c < nch; c += 2) {
-          const int n0 = half * N2 + c * 32;
-          drain_chunk(tmem_base + (uint32_t(q * 32) << 16) + half * 256 + c * 32, tile_s, lane,
-                      sv.xp + size_t(row0) * 4 * H + n0, size_t(4) * H, rows_ok, sv.b_ih + n0);
+          const int n0 = half * N2 + c * 64;
+          drain_chunk_half(tmem_base + (uint32_t(q * 32) << 16) + half * 256 + c * 64, reinterpret_cast<uint8_t*>(tile_s), lane,
+                           sv.xp + size_t(row0) * 4 * H + n0, size_t(4) * H, rows_ok);
         }
         tcgen05_fence_before();
         __syncwarp();

@@ -21,6 +21,8 @@
 //
 // The serial chain (T steps) cannot be parallelised; what this design optimises is the per-step latency:
 // no HBM round trip, no grid-wide sync, one hand-off in each direction per step (forward ~990, backward ~690 cycles).
+#include <cuda_fp16.h>
+
 #include <mutex>
 #include <type_traits>
 
@@ -342,7 +344,8 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // never touches the epilogue warps' scoreboards.  With Xp servers in the launch the rows exist only once their
     // 128-row tile has been published: the lanes check the flags of the next eight timesteps with ONE round trip to L2.
     const int rows_valid = min(NV, B - b0);
-    const uint32_t bytes = uint32_t(rows_valid) * uint32_t(4 * H) * 4u;
+    const uint32_t esz = sv.n_srv > 0 ? 2u : 4u;  // the servers write fp16 (without the bias), the hoisted GEMM fp32
+    const uint32_t bytes = uint32_t(rows_valid) * uint32_t(4 * H) * esz;
     for (int t0 = 0; t0 < T; t0 += 8) {
       if (sv.n_srv > 0) {
         const int tt = min(t0 + (lane & 7), T - 1);
@@ -360,8 +363,8 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           }
           uint64_t* bar = sm.bar_pf + (t & (kPfStages - 1));
           mbar_arrive_expect_tx(bar, bytes);
-          bulk_g2s(reinterpret_cast<float*>(sm.ring) + size_t(t & (kPfStages - 1)) * NV * 4 * H, xp + (size_t(t) * B + b0) * 4 * H,
-                   bytes, bar);
+          bulk_g2s(reinterpret_cast<float*>(sm.ring) + size_t(t & (kPfStages - 1)) * NV * 4 * H,
+                   reinterpret_cast<const uint8_t*>(xp) + (size_t(t) * B + b0) * 4 * H * esz, bytes, bar);
         }
       }
       __syncwarp();
@@ -453,7 +456,8 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     float bias[4], c[NVT];
     const float* xring = reinterpret_cast<const float*>(sm.ring);  // [4 stages][NV rows][4H] filled by the TMA producer
 #pragma unroll
-    for (int g = 0; g < 4; ++g) bias[g] = active ? (b_hh[g * H + u] + (FX ? b_ih[g * H + u] : 0.f)) : 0.f;
+    const bool xp_half = !FX && sv.n_srv > 0;  // served Xp: fp16 without the bias
+    for (int g = 0; g < 4; ++g) bias[g] = active ? (b_hh[g * H + u] + ((FX || xp_half) ? b_ih[g * H + u] : 0.f)) : 0.f;
 #pragma unroll
     for (int j = 0; j < NVT; ++j) c[j] = 0.f;
     int xblk = 0, xtt = 0;  // FX: Xp block / timestep within the block of step t
@@ -487,11 +491,20 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         if (++xtt == TB) { xtt = 0; ++xblk; }
       } else {
         mbar_wait(sm.bar_pf + (t & (kPfStages - 1)), (t / kPfStages) & 1);  // Xp rows of step t have landed (long ago)
-        const float* src = xring + size_t(t & (kPfStages - 1)) * NV * 4 * H + u;
+        const float* stage = xring + size_t(t & (kPfStages - 1)) * NV * 4 * H;
+        if (xp_half) {
+          const __half* src = reinterpret_cast<const __half*>(stage) + u;
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+          for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int j = 0; j < NVT; ++j) pre[g][j] = (valid[j] ? src[(jb + j) * 4 * H + g * H] : 0.f) + bias[g];
+            for (int j = 0; j < NVT; ++j) pre[g][j] = (valid[j] ? __half2float(src[(jb + j) * 4 * H + g * H]) : 0.f) + bias[g];
+        } else {
+          const float* src = stage + u;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int j = 0; j < NVT; ++j) pre[g][j] = (valid[j] ? src[(jb + j) * 4 * H + g * H] : 0.f) + bias[g];
+        }
       }
       const bool do_prof = PROF && prof && cta == 0 && tid == 0 && t < kProfSteps;
       if (phase_prof && (t == 1 || t == 8 || t == 64 || t == 200 || t == 400)) prof[1024 + 6 + (t == 1 ? 0 : t == 8 ? 1 : t == 64 ? 2 : t == 200 ? 3 : 4)] = clock64();
@@ -945,11 +958,11 @@ static int pick_nv(int B) {
 // the servers must keep ahead of the chain (~4k cycles per 128-row tile against ~650 per timestep of B / 128 tiles),
 // and the server kernel serves I <= 128, H % 16 == 0.
 static int pick_servers(int T, int B, int I, int H, int nv) {
-  // OFF by default: an SM writes global memory at 32 B/clk at most (scripts/store_bw.py: STG and TMA alike), so the
-  // spare SMs of the cfg2 launch cannot write the fp32 Xp (230 MB) faster than ~1.26 TB/s = 183 us -- slower than the
-  // chain they feed (measured 355 us against 245 us for the fused in-CTA projection).  CSN_LSTM_SERVERS=1 enables it.
-  static const bool on = [] { const char* e = getenv("CSN_LSTM_SERVERS"); return e && e[0] == '1'; }();
-  if (!on || !side_enabled("CSN_LSTM_NO_SERVERS") || g_cta_budget > 0 || !fused_projection(I) || H % 16 != 0 || H > 128) return 0;
+  // An SM writes global memory at 32 B/clk at most (scripts/store_bw.py: STG and TMA alike), so the 20 spare SMs of the
+  // cfg2 launch could not deliver an fp32 Xp (230 MB: >= 183 us, measured 355 us against 245 us for the fused in-CTA
+  // projection).  In fp16 (115 MB, rounding 2^-11 relative: below the bf16 rounding of h and W_hh in the same sum) they
+  // keep ahead of the chain: 202 us.  CSN_LSTM_NO_SERVERS=1 switches the role off.
+  if (!side_enabled("CSN_LSTM_NO_SERVERS") || g_cta_budget > 0 || !fused_projection(I) || H % 32 != 0 || H > 128) return 0;
   const int n_rec = ceil_div(B, nv), spare = sm_count() - n_rec;
   const int n_tiles = ceil_div(T * B, 128);
   const int need = std::max(2, ceil_div(6 * B, 128));
@@ -1058,7 +1071,7 @@ static int launch_grid(K kern, int grid, int threads, size_t smem, cudaStream_t 
 }
 
 template <int NV, int KSTEPS, bool PROF>
-static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
+static int launch_fwd(const float* xp, const float* b_ih_served, const uint32_t* w_hh, const float* b_hh, __nv_bfloat16* h_seq, __nv_bfloat16* gates,
                       float* c_out, int T, int B, int H, int KP, const FusedX& fx, const side::XpServe& sv, const CUtensorMap& tm_x,
                       const CUtensorMap& tm_w, cudaStream_t s) {
   const int n_rec = ceil_div(B, NV);
@@ -1077,7 +1090,7 @@ static int launch_fwd(const float* xp, const uint32_t* w_hh, const float* b_hh, 
   auto kern = lstm_fwd_tc_kernel<NV, KSTEPS, false, PROF>;
   CSN_TRY(ensure_smem(kern, smem, &smem_set));
   return launch_grid(kern, sv.n_srv + n_rec, kRecThreadsBwd, smem, s, tm_x, tm_w, sv, xp, w_hh, b_hh, h_seq, gates, c_out, T, B, H,
-                     KP, g_prof_buf, 0u, (const __nv_bfloat16*)nullptr, (const uint8_t*)nullptr, (const float*)nullptr, 0, 16);
+                     KP, g_prof_buf, 0u, (const __nv_bfloat16*)nullptr, (const uint8_t*)nullptr, b_ih_served, 0, 16);
 }
 
 template <int NV, int KSTEPS, bool PROF>
@@ -1120,7 +1133,7 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   const int n_tiles = (int)ceil_div<size_t>(tb, 128);
   if (n_srv > 0) {
     // spare CTAs of the launch compute Xp concurrently: bf16 W_ih for their TMA, READY flags zeroed by the prepare kernel
-    sv = side::XpServe{n_srv, n_tiles, (int)tb, I, H, xp, b_ih, flags};
+    sv = side::XpServe{n_srv, n_tiles, (int)tb, I, H, reinterpret_cast<__half*>(xp), flags};
     CSN_TRY(make_tmap_2d(&tm_x, x, (uint64_t)I, (uint64_t)tb, (uint64_t)I, 64, 128));
     CSN_TRY(make_tmap_2d(&tm_w, wih_bf, (uint64_t)I, (uint64_t)(4 * H), (uint64_t)I, 64, (uint32_t)side::xp_w_box_rows(H)));
   } else if (fused_projection(I)) {
@@ -1144,11 +1157,11 @@ int lstm_layer_fwd_tc(const void* x, const float* w_ih, const float* w_hh, const
   // The stamped (PROF) instantiation exists for the benchmark shape only.
 #define CSN_FWD(KS)                                                                                                     \
   do {                                                                                                                  \
-    if (nv == 2) return launch_fwd<2, KS, false>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);          \
-    if (nv == 4) return launch_fwd<4, KS, false>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);          \
-    return launch_fwd<8, KS, false>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);                       \
+    if (nv == 2) return launch_fwd<2, KS, false>(xp, b_ih, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);          \
+    if (nv == 4) return launch_fwd<4, KS, false>(xp, b_ih, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);          \
+    return launch_fwd<8, KS, false>(xp, b_ih, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);                       \
   } while (0)
-  if (KP == 128 && nv == 2 && g_prof_buf) return launch_fwd<2, 8, true>(xp, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);
+  if (KP == 128 && nv == 2 && g_prof_buf) return launch_fwd<2, 8, true>(xp, b_ih, w_img, b_hh, hs, g, c, T, B, H, KP, fx, sv, tm_x, tm_w, s);
   if (KP == 128) CSN_FWD(8);
   if (KP == 96) CSN_FWD(6);
   if (KP == 64) CSN_FWD(4);
