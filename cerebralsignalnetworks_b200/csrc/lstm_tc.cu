@@ -517,6 +517,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         uint32_t r[4][NVT];
 #pragma unroll
         for (int g = 0; g < 4; ++g) tmem_ld<NVT>(lane_addr + g * kNslots, r[g]);
+        if (do_prof) prof[t * 8 + 7] = clock64();
         tmem_ld_wait();
         tcgen05_fence_before();  // our TMEM reads are ordered before the MMAs the next hand-off releases
         if (do_prof) prof[t * 8 + 1] = clock64();
@@ -873,43 +874,57 @@ struct DwSlabs {
 struct DwSources {  // a weight gradient = consumer slabs (the rows folded during the sweep) + GEMM slabs (the rest)
   DwSlabs a, b;
 };
-__global__ void bptt_finalize_kernel(const DwSources ih, const DwSources hh, const float* __restrict__ db_part, int n_part,
-                                     float* __restrict__ dw_ih, float* __restrict__ dw_hh, float* __restrict__ db_ih,
-                                     float* __restrict__ db_hh, int H, int I, int accumulate) {
+__global__ void __launch_bounds__(256) bptt_finalize_kernel(const DwSources ih, const DwSources hh, const float* __restrict__ db_part,
+                                                           int n_part, float* __restrict__ dw_ih, float* __restrict__ dw_hh,
+                                                           float* __restrict__ db_ih, float* __restrict__ db_hh, int H, int I,
+                                                           int accumulate, int n_dw_blocks) {
   const int n_ih = 4 * H * I, n_hh = 4 * H * H, n_b = 4 * H;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ih + n_hh + n_b; i += gridDim.x * blockDim.x) {
-    if (i < n_ih + n_hh) {
-      const bool is_ih = i < n_ih;
-      const DwSources& w = is_ih ? ih : hh;
-      const int j = is_ih ? i : i - n_ih, width = is_ih ? I : H;
-      const int r = j / width, k = j - r * width;       // r = g*H + u
-      const int rp = 4 * (r % H) + r / H;               // slab row 4u + g
-      float a = 0.f;
-      {
-        const float* src = w.a.base + size_t(rp) * w.a.ld + w.a.col0 + k;
-        for (int z = 0; z < w.a.n; ++z) a += src[size_t(z) * w.a.stride];
-      }
-      {
-        const float* src = w.b.base + size_t(rp) * w.b.ld + w.b.col0 + k;
-        for (int z = 0; z < w.b.n; ++z) a += src[size_t(z) * w.b.stride];
-      }
-      float* dst = is_ih ? dw_ih + j : dw_hh + j;
-      *dst = accumulate ? *dst + a : a;
-    } else {
-      const int j = i - n_ih - n_hh;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int q = 0;
-      for (; q + 3 < n_part; q += 4) {
-        a0 += db_part[size_t(q) * n_b + j];
-        a1 += db_part[size_t(q + 1) * n_b + j];
-        a2 += db_part[size_t(q + 2) * n_b + j];
-        a3 += db_part[size_t(q + 3) * n_b + j];
-      }
-      for (; q < n_part; ++q) a0 += db_part[size_t(q) * n_b + j];
-      const float a = (a0 + a1) + (a2 + a3);
-      db_ih[j] = accumulate ? db_ih[j] + a : a;
-      db_hh[j] = accumulate ? db_hh[j] + a : a;
+  if ((int)blockIdx.x < n_dw_blocks) {
+    // ---- weight gradients: one element per thread, its slabs are independent loads ----
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ih + n_hh) return;
+    const bool is_ih = i < n_ih;
+    const DwSources& w = is_ih ? ih : hh;
+    const int j = is_ih ? i : i - n_ih, width = is_ih ? I : H;
+    const int r = j / width, k = j - r * width;       // r = g*H + u
+    const int rp = 4 * (r % H) + r / H;               // slab row 4u + g
+    float a = 0.f;
+    {
+      const float* src = w.a.base + size_t(rp) * w.a.ld + w.a.col0 + k;
+      for (int z = 0; z < w.a.n; ++z) a += src[size_t(z) * w.a.stride];
     }
+    {
+      const float* src = w.b.base + size_t(rp) * w.b.ld + w.b.col0 + k;
+      for (int z = 0; z < w.b.n; ++z) a += src[size_t(z) * w.b.stride];
+    }
+    float* dst = is_ih ? dw_ih + j : dw_hh + j;
+    *dst = accumulate ? *dst + a : a;
+    return;
+  }
+  // ---- bias gradients: 32 columns per CTA, eight threads per column each adding every eighth partial (four rotating
+  //      accumulators keep the loads independent), folded in thread order: a serial walk over the 256 partials of the
+  //      cfg2 launch was the longest chain of the whole kernel (~10 us of dependent L2 round trips) ----
+  __shared__ float red[8][33];
+  const int col = (blockIdx.x - n_dw_blocks) * 32 + (threadIdx.x & 31), sub = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (col < n_b) {
+    int q = sub;
+    for (; q + 24 < n_part; q += 32) {
+      a0 += db_part[size_t(q) * n_b + col];
+      a1 += db_part[size_t(q + 8) * n_b + col];
+      a2 += db_part[size_t(q + 16) * n_b + col];
+      a3 += db_part[size_t(q + 24) * n_b + col];
+    }
+    for (; q < n_part; q += 8) a0 += db_part[size_t(q) * n_b + col];
+  }
+  red[sub][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (sub == 0 && col < n_b) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += red[k][threadIdx.x];
+    db_ih[col] = accumulate ? db_ih[col] + a : a;
+    db_hh[col] = accumulate ? db_hh[col] + a : a;
   }
 }
 
@@ -1273,8 +1288,9 @@ int lstm_layer_bwd_tc(const void* x, const float* w_ih, const float* w_hh, const
     ih.b = DwSlabs{slabs_ih, s_ih, slab_ih.split_stride, I, 0};
     hh.b = DwSlabs{slabs_hh, s_hh, slab_hh.split_stride, H, 0};
   }
-  bptt_finalize_kernel<<<ceil_div(4 * H * (I + H + 1), 256), 256, 0, s>>>(ih, hh, db_part, n_part, dw_ih, dw_hh, db_ih, db_hh, H, I,
-                                                                          accumulate);
+  const int n_dw_blocks = ceil_div(4 * H * (I + H), 256);
+  bptt_finalize_kernel<<<n_dw_blocks + ceil_div(4 * H, 32), 256, 0, s>>>(ih, hh, db_part, n_part, dw_ih, dw_hh, db_ih, db_hh, H, I,
+                                                                         accumulate, n_dw_blocks);
   CSN_LAUNCH_CHECK();
   if (dx) {  // dX = dG . W_ih with W_ih's rows in dG's gate-interleaved order
     interleave_rows_bf16_kernel<<<4 * H, 128, 0, s>>>(w_ih, wih_bf, H, I);

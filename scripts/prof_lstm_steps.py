@@ -16,9 +16,11 @@ x = torch.randn(T, B, I).cuda().bfloat16()
 buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
 grads = tuple(torch.empty_like(t) for t in w)
 dh = torch.randn(B, H).cuda()
+TRAIN = os.environ.get("PTRAIN", "1") == "1"
 def run():
-    h, r, ws = ops.lstm_layer_fwd(x, *w, torch.bfloat16, True)
-    ops.lstm_layer_bwd(x, w[0], w[1], h, r, ws, None, dh, grads, False, torch.bfloat16)
+    h, r, ws = ops.lstm_layer_fwd(x, *w, torch.bfloat16, TRAIN)
+    if TRAIN:
+        ops.lstm_layer_bwd(x, w[0], w[1], h, r, ws, None, dh, grads, False, torch.bfloat16)
 for _ in range(2):
     run()
 _lib.call("csn_dbg_lstm_profile_buffer", ctypes.c_void_p(buf.data_ptr()))
@@ -49,6 +51,8 @@ for name, p in (("forward", buf[:512].view(64, 8).cpu()), ("backward", buf[512:1
         rows.append((period, a, b, c, d, e, f, wa, st, pre))
         if t < 6:
             print(f"{t:3d} | {period:6d} | {a:6d} | {b:6d} | {c:6d} | {d:6d} | {e:6d} | {f:6d}")
+    if name == "forward":
+        print("fwd: accwake -> tmem_ld issued:", [int(p[t, 7] - p[t, 0]) for t in range(3, 20)], " issued -> ld done:", [int(p[t, 1] - p[t, 7]) for t in range(3, 20)])
     print("periods t=3..39:", [r[0] for r in rows])
     print("wait-on-acc   :", [r[7] for r in rows])
     print("median", [int(statistics.median(r[i] for r in rows)) for i in range(10)], "(last three: time actually spent waiting on bar_acc, off-path stores, ring wait + dh-independent math before the acc wait)")
