@@ -23,7 +23,6 @@ import torch
 
 from . import _lib, dp, ops
 from ._lib import DINO_MULTICROP_REF
-from .functional import DINOLossFunction
 from .optim import EMATeacher, FusedAdam
 
 
@@ -53,7 +52,7 @@ def _split_params(student):
 class MultiCropDistillStep:
     def __init__(self, student, teacher, loss, lr_schedule, wd_schedule, momentum_schedule, clip_grad=3.0,
                  freeze_last_layer=1, betas=(0.9, 0.999), eps=1e-8, n_global=2, n_local=4, global_len=300, local_len=200,
-                 batch_size=None, concurrent=True, cta_budget=64, seed=None):
+                 batch_size=None, concurrent=True, cta_budget=(64, 64, 64, 64), seed=None, use_cuda_graph=True):
         """student / teacher: MultiCropWrapper(Model, DINOHead) on the GPU with identical architectures (the teacher is
         overwritten with the student's weights, LstmDistillation.py:446, and frozen); loss: DINOLoss(out_dim, n_global +
         n_local, ...); the three schedules are per-ITERATION arrays as built by utils.cosine_scheduler (:483-496).
@@ -95,7 +94,13 @@ class MultiCropDistillStep:
             for p in self._head_params:
                 p.register_post_accumulate_grad_hook(self._head_grad_ready)
         self.concurrent = bool(concurrent)
-        self.cta_budget = int(cta_budget)
+        # SM shares of the three forward chains (teacher, student global, student local) and of the backward chains: the
+        # recurrence picks the batch tile per CTA from its share, so the chains of a phase are co-resident instead of
+        # queueing for SMs (teacher 32 + global 32 + local 64 = 128 CTAs forward, global 64 + local 64 backward)
+        if isinstance(cta_budget, (tuple, list)):
+            self.cta_budget = tuple(int(b) for b in cta_budget)
+        else:
+            self.cta_budget = (int(cta_budget),) * 4
         if self.concurrent:
             # the student's two backbone passes run (and are differentiated) on their own streams on purpose
             try:
@@ -105,6 +110,16 @@ class MultiCropDistillStep:
         if self.concurrent:
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
         self.it = 0
+        # CUDA-graph path: the ~150 launches of a step (and the autograd bookkeeping around them: the eager step is bound
+        # by the HOST, 4.4 ms of Python per 4.4 ms step at cfg3) are captured once and replayed.  What varies between
+        # steps lives on the device: the crops are copied into static buffers, lr / wd / EMA momentum / frozen groups
+        # travel through the optimiser's device arrays, the exchange epochs are device counters.  The teacher temperature
+        # is a launch constant: a new epoch value captures a new graph.
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graphs = {}
+        self._pool = None
+        self._static = None
+        self._eager_steps = 0
 
     # ------------------------------------------------------------------------------------------------ hooks
     def _head_grad_ready(self, _param):
@@ -127,28 +142,26 @@ class MultiCropDistillStep:
                 s = int(self.rng.randint(0, T))
                 if s + length > T:
                     s -= s + length - T
-                out.append(eeg_btc[:, s:s + length, :].contiguous())
+                out.append(eeg_btc[:, s:s + length, :])
         return out[:self.n_global], out[self.n_global:]
 
-    def _forward(self, gv, lv):
+    def _forward(self, gcat, lcat, B):
         student, teacher = self.student, self.teacher
-        B = gv[0].shape[0]
-        gcat, lcat = torch.cat(gv), torch.cat(lv)
         if self.concurrent:
             cur = torch.cuda.current_stream()
             s_t, s_g, s_l = self._streams
             for st in self._streams:
                 st.wait_stream(cur)
-            ops.set_lstm_cta_budget(self.cta_budget)
-            try:
-                with torch.cuda.stream(s_t), torch.no_grad():
-                    t_feat = teacher.backbone(gcat)
-                with torch.cuda.stream(s_g):
-                    f_g = student.backbone(gcat)
-                with torch.cuda.stream(s_l):
-                    f_l = student.backbone(lcat)
-            finally:
-                pass  # the budget stays set through backward (the BPTT chains run side by side as well)
+            ops.set_lstm_cta_budget(self.cta_budget[0])
+            with torch.cuda.stream(s_t), torch.no_grad():
+                t_feat = teacher.backbone(gcat)
+            ops.set_lstm_cta_budget(self.cta_budget[1])
+            with torch.cuda.stream(s_g):
+                f_g = student.backbone(gcat)
+            ops.set_lstm_cta_budget(self.cta_budget[2])
+            with torch.cuda.stream(s_l):
+                f_l = student.backbone(lcat)
+            ops.set_lstm_cta_budget(self.cta_budget[3])  # stays set through backward (the BPTT chains run side by side)
             for st in self._streams:
                 cur.wait_stream(st)
         else:
@@ -161,13 +174,44 @@ class MultiCropDistillStep:
         return s_out, t_out
 
     # ------------------------------------------------------------------------------------------------ the step
+    def _run(self, gcat, lcat, B, epoch):
+        """Everything of one step that runs on the device (capturable): wait for the peers, forward, loss, backward,
+        exchange, fused optimiser sweep, centre EMA.  gcat [n_global * B, global_len, C], lcat [n_local * B, local_len, C]."""
+        opt, loss_mod = self.opt, self.loss
+        self.xchg.wait_done(0)  # the peers are done with the previous step's buffer: gradients may be written again
+        self.xchg.wait_done(1)
+        opt.zero_grad()
+        s_out, t_out = self._forward(gcat, lcat, B)
+        # ---- loss (reference multi-crop semantics); the per-row centre statistics land in the exchanged buffer ----
+        temp = float(loss_mod.teacher_temp_schedule[epoch])
+        # The loss kernel emits dLoss/dstudent together with the loss: backward starts from the student logits with that
+        # gradient (no autograd node for the loss, no pass over the 100 MB gradient to multiply it by d(loss)/d(loss) = 1)
+        bc_dst = self.center_sums if self.n_center else None
+        loss, d_student, bc = ops.dino_loss_fwd_bwd(s_out.detach().float().contiguous(), t_out.float().contiguous(),
+                                                    loss_mod.center.contiguous(), loss_mod.student_temp, temp,
+                                                    DINO_MULTICROP_REF, batch_center=bc_dst)
+        stats = [bc]
+        self._head_pending = len(self._head_params) if self.world > 1 else -1
+        torch.autograd.backward(s_out, grad_tensors=d_student.view(s_out.shape).to(s_out.dtype))
+        if self.concurrent:
+            ops.set_lstm_cta_budget(0)
+        # ---- exchange: the head went out from the hook; backbone gradients + centre statistics now ----
+        if self.world > 1:
+            self.xchg.all_reduce_(self.n_head, self.opt.n_flat - self.n_head + self.n_center, flag_set=1)
+            torch.cuda.current_stream().wait_event(self._head_done)
+        # ---- clip + AdamW + EMA teacher, one sweep (lr / wd / momentum are already on the device) ----
+        opt.fused_step(clip=self.clip_grad, grad_scale=1.0 / self.world, ema=self.ema, upload=False)
+        ops.center_ema(loss_mod.center, stats[0], loss_mod.center_momentum, 1.0 / (self.n_global * self.world))
+        return loss
+
     def step(self, eeg_btc, epoch, it=None, crops=None):
         """eeg_btc: float32 [B, T, C] on the GPU (the DataLoader layout, utils/PerilsEEGDataset.py:569).  `it` indexes the
-        per-iteration schedules (default: an internal counter).  Returns the loss (0-d device tensor, this rank's)."""
+        per-iteration schedules (default: an internal counter).  Returns the loss (0-d device tensor, this rank's; on the
+        CUDA-graph path it is the graph's static output: consume it before the next call)."""
         it = self.it if it is None else int(it)
         self.it = it + 1
         opt, loss_mod = self.opt, self.loss
-        B = eeg_btc.shape[0]
+        B, C = eeg_btc.shape[0], eeg_btc.shape[2]
         if self.n_center and B * self.K != self.n_center:
             raise _lib.CsnError("MultiCropDistillStep: batch size changed (%d trials, built for %d)" % (B, self.n_center // self.K))
         for i, g in enumerate(opt.param_groups):  # LstmDistillation.py:540-544
@@ -175,32 +219,35 @@ class MultiCropDistillStep:
             if not g["name"].endswith("noreg"):
                 g["weight_decay"] = float(self.wd_schedule[it])
         opt.set_group_active(1, epoch >= self.freeze_last_layer)  # cancel_gradients_last_layer (:610)
-        # the peers are done with the previous step's buffer: gradients may be written again
-        self.xchg.wait_done(0)
-        self.xchg.wait_done(1)
-        opt.zero_grad()
+        opt.upload_hyper(float(self.momentum_schedule[it]))
+        if loss_mod.center.numel() == self.K:  # the reference's centre becomes [1, B, K] at its first update
+            loss_mod.center = loss_mod.center.reshape(1, 1, self.K).expand(1, B, self.K).contiguous()
         gv, lv = crops if crops is not None else self.make_crops(eeg_btc)
-        s_out, t_out = self._forward(gv, lv)
-        # ---- loss (reference multi-crop semantics); the per-row centre statistics land in the exchanged buffer ----
-        temp = float(loss_mod.teacher_temp_schedule[epoch])
-        center = loss_mod.center
-        if center.numel() == self.K:  # the reference's centre becomes [1, B, K] at its first update
-            center = center.reshape(1, 1, self.K).expand(1, B, self.K).contiguous()
-            loss_mod.center = center
-        stats = []
-        bc_dst = self.center_sums if self.n_center else None
-        loss = DINOLossFunction.apply(s_out.float(), t_out.float(), center, loss_mod.student_temp, temp,
-                                      DINO_MULTICROP_REF, stats, bc_dst)
-        self._head_pending = len(self._head_params) if self.world > 1 else -1
-        loss.backward()
-        if self.concurrent:
-            ops.set_lstm_cta_budget(0)
-        # ---- exchange: the head went out from the hook; backbone gradients + centre statistics now ----
-        if self.world > 1:
-            self.xchg.all_reduce_(self.n_head, self.opt.n_flat - self.n_head + self.n_center, flag_set=1)
-            torch.cuda.current_stream().wait_event(self._head_done)
-        # ---- clip + AdamW + EMA teacher, one sweep ----
-        opt.fused_step(clip=self.clip_grad, grad_scale=1.0 / self.world, ema=self.ema,
-                       ema_momentum=float(self.momentum_schedule[it]))
-        ops.center_ema(loss_mod.center, stats[0], loss_mod.center_momentum, 1.0 / (self.n_global * self.world))
-        return loss.detach()
+        graphed = self.use_cuda_graph and self._eager_steps >= 2
+        if not graphed:
+            self._eager_steps += 1
+            return self._run(torch.cat(gv), torch.cat(lv), B, epoch)
+        # crops into the graph's static inputs, then replay (capture on first use of this teacher temperature)
+        if self._static is None or self._static[0].shape[0] != self.n_global * B:
+            self._static = (torch.empty(self.n_global * B, self.global_len, C, device=self.device),
+                            torch.empty(self.n_local * B, self.local_len, C, device=self.device))
+            self._graphs.clear()
+        gcat, lcat = self._static
+        for k, v in enumerate(gv):
+            gcat[k * B:(k + 1) * B].copy_(v)
+        for k, v in enumerate(lv):
+            lcat[k * B:(k + 1) * B].copy_(v)
+        key = float(loss_mod.teacher_temp_schedule[epoch])
+        hit = self._graphs.get(key)
+        if hit is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            torch.cuda.current_stream().synchronize()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._pool):
+                out = self._run(gcat, lcat, B, epoch)
+            hit = self._graphs[key] = (g, out)
+        hit[0].replay()
+        return hit[1]

@@ -89,7 +89,6 @@ class FusedAdam:
         self._seg_step = torch.zeros(len(layout), dtype=torch.int32, device=dev)
         self._group_of_seg = seg_group
         n_hyper = 2 * len(self.param_groups) + 1
-        self._hyper_host = torch.zeros(n_hyper, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(n_hyper)
         self._hyper_dev = torch.zeros(n_hyper, dtype=torch.float32, device=dev)
         self._fused_ws = None
 
@@ -109,7 +108,37 @@ class FusedAdam:
         count).  Put such parameters in their own param group and switch the group off for those steps."""
         self.param_groups[index]["active"] = bool(active)
 
-    def fused_step(self, clip=0.0, grad_scale=1.0, ema=None, ema_momentum=0.0, want_norms=False):
+    def upload_hyper(self, ema_momentum=0.0):
+        """Send every group's current lr / weight_decay, the EMA momentum and the groups' active flags to the device (tiny
+        async copies from rotating pinned slots, ordered on the current stream).  fused_step() does this itself unless it is
+        told the values are already there (a captured CUDA graph of the step: call this before every replay)."""
+        n_groups = len(self.param_groups)
+        if not hasattr(self, "_hyper_slots"):
+            pin = self._hyper_dev.device.type == "cuda"
+            self._hyper_slots = [torch.zeros(2 * n_groups + 1, dtype=torch.float32).pin_memory() if pin
+                                 else torch.zeros(2 * n_groups + 1) for _ in range(16)]
+            self._hyper_events = [None] * 16
+            self._hyper_n = 0
+        k = self._hyper_n % len(self._hyper_slots)
+        self._hyper_n += 1
+        if self._hyper_events[k] is not None:
+            self._hyper_events[k].synchronize()  # the copy that last read this slot is done (16 steps ago)
+        h = self._hyper_slots[k]
+        for gi, g in enumerate(self.param_groups):
+            h[2 * gi] = float(g["lr"])
+            h[2 * gi + 1] = float(g["weight_decay"])
+        h[2 * n_groups] = float(ema_momentum)
+        self._hyper_dev.copy_(h, non_blocking=True)
+        if self._hyper_dev.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record()
+            self._hyper_events[k] = ev
+        active = [1 if self.param_groups[gi].get("active", True) else 0 for gi in self._group_of_seg]
+        if active != getattr(self, "_active_cached", None):
+            self._seg_active.copy_(torch.tensor(active, dtype=torch.int32))
+            self._active_cached = active
+
+    def fused_step(self, clip=0.0, grad_scale=1.0, ema=None, ema_momentum=0.0, want_norms=False, upload=True):
         """clip_gradients + optimizer.step() + the EMA teacher update of LstmDistillation.py:607-619 as ONE sweep over the
         flat buffers (csn_fused_optim_step): per-parameter clip of the rank-averaged gradient (grad_scale = 1 / world),
         AdamW / Adam with each group's CURRENT lr / weight_decay (set them in param_groups as the reference loop does,
@@ -119,15 +148,8 @@ class FusedAdam:
         import ctypes as _C
         from . import _lib
         n_groups = len(self.param_groups)
-        for gi, g in enumerate(self.param_groups):
-            self._hyper_host[2 * gi] = float(g["lr"])
-            self._hyper_host[2 * gi + 1] = float(g["weight_decay"])
-        self._hyper_host[2 * n_groups] = float(ema_momentum)
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
-        active = [1 if self.param_groups[gi].get("active", True) else 0 for gi in self._group_of_seg]
-        if active != getattr(self, "_active_cached", None):
-            self._seg_active.copy_(torch.tensor(active, dtype=torch.int32))
-            self._active_cached = active
+        if upload:
+            self.upload_hyper(ema_momentum)
         if self._fused_ws is None:
             n = _C.c_size_t()
             _lib.call("csn_fused_optim_workspace_bytes", self._n_seg, self._n_chunks, _C.byref(n))

@@ -33,8 +33,8 @@ def _crop_starts():
 
 
 def _crops(eeg, starts):
-    g = [eeg[:, s:s + GLEN, :].contiguous() for s in starts[:2]]
-    l = [eeg[:, s:s + LLEN, :].contiguous() for s in starts[2:]]
+    g = [eeg[:, s:s + GLEN, :] for s in starts[:2]]
+    l = [eeg[:, s:s + LLEN, :] for s in starts[2:]]
     return g, l
 
 
