@@ -666,11 +666,13 @@ def main():
             "note": "DeviceEEGDataset: raw trials uploaded once, per step host indices + host image features -> device gather -> step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "LSTM encoder fwd+bwd (lstm_fwd_tc_kernel with fused input projection + lstm_bwd_tc_kernel + 2 dW GEMMs)",
+        "roofline": {"bound": "tensor", "kernel": "LSTM encoder fwd+bwd (lstm_fwd_tc_kernel: 128 recurrence CTAs + 20 input-projection server CTAs; "
+                               "lstm_bwd_tc_kernel: 128 recurrence CTAs + 20 dW consumer CTAs; bptt_finalize_kernel)",
                      "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved_tflops / peak_tf) if achieved_tflops else None,
-                     "traffic": ncu_traffic(["lstm_fwd_tc_kernel", "lstm_bwd_tc_kernel", "gemm_tc_kernel<1, 1,", "gemm_tc_kernel<1, 1,"]),
-                     "traffic_note": "DRAM read+write bytes per step of the encoder kernels (fwd recurrence with fused input projection, bwd recurrence, 2 dW GEMMs), ncu --set full, profiles/traffic.json",
+                     "traffic": ncu_traffic(["lstm_fwd_tc_kernel", "lstm_bwd_tc_kernel", "bptt_finalize_kernel"]),
+                     "traffic_note": "DRAM read+write bytes per step of the encoder kernels (forward launch incl. the fp16 input projection its server CTAs write, backward launch incl. the dW its consumer CTAs fold, the fixed-order finalize), ncu --set full, profiles/traffic.json",
+                     "algorithmic_flop_per_step": work["lstm_train_flop"], "stage_ms": enc_ms,
                      "peak_source": peaks["source"] + " (sustained: kernel timed inside the step)",
                      "tensor_pipe_active_sm": ncu_tensor_pipe()},
         "roofline_filter": {"bound": "hbm", "kernel": "sosfilt_warp_kernel", "achieved": filt_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
