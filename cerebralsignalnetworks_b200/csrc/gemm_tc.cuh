@@ -32,6 +32,10 @@ int gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A, int 
 int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
                  uint32_t box_outer);
 
+// TMA descriptor of a plain (unswizzled) 2-D tensor of 2- or 4-byte elements (elem_bytes: 2 = bf16, 4 = fp32)
+int make_tmap_2d_plain(CUtensorMap* tm, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                       uint32_t box_inner, uint32_t box_outer);
+
 // D[m, n] (+)= sum_z slabs[z * stride + m * N + n] (+ bias[n]), z ascending (the fixed-order tail of a split-K product)
 int splitk_reduce(const float* slabs, size_t stride, int S, float* D, int ldd, int M, int N, const float* bias,
                   int accumulate, cudaStream_t s);

@@ -1029,6 +1029,7 @@ int lstm_tc_bytes(int T, int B, int I, int H, size_t* reserve, size_t* workspace
   return CSN_OK;
 }
 
+void lstm_cluster_set_prof(long long* p);  // lstm_cluster.cu
 static long long* g_prof_buf = nullptr;  // set by csn_dbg_lstm_profile_buffer (bring-up only)
 
 // internal helper stream (one per device) for fork / join inside a C-ABI call; nullptr when disabled or on failure
@@ -1311,6 +1312,7 @@ extern "C" int csn_lstm_set_cta_budget(int max_ctas) {
 using namespace csn;
 
 extern "C" int csn_dbg_lstm_profile_buffer(long long* buf) {
+  csn::lstm_cluster_set_prof(buf);
   csn::g_prof_buf = buf;  // device buffer of at least 64*8 int64 (or NULL to switch the stamps off)
   return CSN_OK;
 }

@@ -15,6 +15,13 @@
 
 namespace csn {
 
+// lstm_cluster.cu: persistent cluster recurrence for H = 256 / 512
+bool lstm_cluster_supported(int H);
+int lstm_cluster_fwd(const float* xp, const __nv_bfloat16* whh_perm, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq, int T,
+                     int B, int H, cudaStream_t s);
+int lstm_cluster_bwd(const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq, const float* d_hlast,
+                     const __nv_bfloat16* whh_t, __nv_bfloat16* dG, int T, int B, int H, cudaStream_t s);
+
 static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
 
 // programmatic dependent launch for the per-timestep kernels (CSN_NO_PDL=1 switches it off for A/B measurements)
@@ -32,6 +39,19 @@ __global__ void permute_rows_bf16_kernel(const float* __restrict__ src, __nv_bfl
   const int u = r >> 2, g = r & 3;
   const float* s = src + size_t(g * H + u) * N;
   for (int c = threadIdx.x; c < N; c += blockDim.x) dst[size_t(r) * N + c] = __float2bfloat16_rn(s[c]);
+}
+// dst[m, 4u+g] = bf16(src[g*H+u, m]): W_hh^T with gate-interleaved columns (the cluster BPTT's resident operand rows);
+// 32 x 32 tiles through shared memory so that both the reads and the writes are coalesced
+__global__ void permute_transpose_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, m0 = blockIdx.x * 32;  // destination columns r = 4u+g in [r0, r0+32), rows m in [m0, m0+32)
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, u = r >> 2, g = r & 3;
+    tile[i][threadIdx.x] = src[size_t(g * H + u) * H + m0 + threadIdx.x];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    dst[size_t(m0 + i) * (4 * H) + r0 + threadIdx.x] = __float2bfloat16_rn(tile[threadIdx.x][i]);
 }
 __global__ void permute_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ dst, int H) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,6 +118,7 @@ struct LargeWs {
   __nv_bfloat16* dG;         // bwd: [TB,4H] bf16 (aliases xp)
   __nv_bfloat16* wih;        // [4H, I] permuted bf16
   __nv_bfloat16* whh;        // [4H, H] permuted bf16
+  __nv_bfloat16* whh_t;      // [H, 4H] transposed, columns permuted (cluster BPTT only)
   float* bias;               // [4H] permuted b_ih + b_hh
   float* dh_rec;             // 8 x [B, H]: split-K slabs of the recurrent gradient (summed by the cell kernel)
   float* dc;                 // [B, H]
@@ -122,6 +143,7 @@ static LargeWs carve_ws(void* base, int T, int B, int I, int H) {
   w.dG = reinterpret_cast<__nv_bfloat16*>(w.xp);
   w.wih = reinterpret_cast<__nv_bfloat16*>(take(size_t(4) * H * I * 2));
   w.whh = reinterpret_cast<__nv_bfloat16*>(take(size_t(4) * H * H * 2));
+  w.whh_t = reinterpret_cast<__nv_bfloat16*>(take(size_t(4) * H * H * 2));
   w.bias = reinterpret_cast<float*>(take(size_t(4) * H * 4));
   w.dh_rec = reinterpret_cast<float*>(take(size_t(8) * B * H * 4));
   w.dc = reinterpret_cast<float*>(take(size_t(B) * H * 4));
@@ -170,6 +192,8 @@ int lstm_layer_fwd_large(const void* x, const float* w_ih, const float* w_hh, co
   CSN_TRY(prep_weights(w, w_ih, w_hh, b_ih, b_hh, I, H, s));
   // hoisted input projection in gate-interleaved column order
   CSN_TRY(gemm_tc_run(0, 1, (int)tb, 4 * H, I, x, I, w.wih, I, w.xp, 4 * H, CSN_F32, w.bias, 0, 1, nullptr, s));
+  if (lstm_cluster_supported(H))  // the whole time loop in ONE persistent cluster launch
+    return lstm_cluster_fwd(w.xp, w.whh, hs, gates, c_seq, T, B, H, s);
   for (int t = 0; t < T; ++t) {
     GemmEpi cell{};
     cell.pdl = kPdl;
@@ -195,7 +219,14 @@ int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, co
   const __nv_bfloat16* gates = reinterpret_cast<const __nv_bfloat16*>(reserve);
   const float* c_seq = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(reserve) + al256(tb * 4 * H * 2));
   CSN_TRY(prep_weights(w, w_ih, w_hh, nullptr, nullptr, I, H, s));
-  CSN_CUDA(cudaMemsetAsync(w.dc, 0, size_t(B) * H * 4, s));
+  const bool cluster = lstm_cluster_supported(H);
+  if (cluster) {  // the whole BPTT recurrence in ONE persistent cluster launch (lstm_cluster.cu)
+    permute_transpose_bf16_kernel<<<dim3(H / 32, 4 * H / 32), dim3(32, 8), 0, s>>>(w_hh, w.whh_t, H);
+    CSN_LAUNCH_CHECK();
+    CSN_TRY(lstm_cluster_bwd(gates, c_seq, d_hseq, d_hlast, w.whh_t, w.dG, T, B, H, s));
+  } else {
+    CSN_CUDA(cudaMemsetAsync(w.dc, 0, size_t(B) * H * 4, s));
+  }
   const int cells = B * H;
   // dh_{t-1}[B,H] = dG_t[B,4H] . W_hh_perm[4H,H]: a contraction of 4H with only H/128 output tiles per batch tile, so
   // it is split over K to put up to 8x more CTAs on each step of the chain; every split stores its partial product to
@@ -210,7 +241,7 @@ int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, co
   GemmEpi slabs{};
   slabs.split_stride = size_t(B) * H;
   slabs.pdl = kPdl;
-  for (int t = T - 1; t >= 0; --t) {
+  for (int t = cluster ? -1 : T - 1; t >= 0; --t) {
     {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(ceil_div(cells, 256), 1, 1);

@@ -1,0 +1,178 @@
+// Microbenchmark behind the H = 512 cluster recurrence (lstm_cluster.cu): what does one all-gather round cost inside a
+// 16-CTA cluster, and how many such clusters are resident at once?
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o scripts/_bin/cluster_xchg_bench scripts/cluster_xchg_bench.cu
+// Every round each CTA pushes PIECE bytes to all CS CTAs of its cluster (itself included) and waits until the CS
+// pieces addressed to it have landed.  mode 0: cp.async.bulk shared::cta -> shared::cluster, one copy per destination
+// issued by CS lanes of one warp; mode 1: st.async 16-byte packets (data + complete_tx); mode 2: plain
+// st.shared::cluster.v4 + fence.acq_rel.cluster + one remote mbarrier arrive per warp.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa(uint32_t a, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint32_t cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+template <int CS, int PIECE, int MODE>
+__global__ void __launch_bounds__(160, 1) xchg_kernel(int rounds, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [0, 2*CS*PIECE): two receive buffers; then two staging pieces; then 2 mbarriers
+  uint8_t* rbuf = smem;
+  uint8_t* stage0 = smem + 2 * CS * PIECE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * PIECE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cta_rank();
+  constexpr int kSendThreads = 128;
+  constexpr uint32_t kArrivals = (MODE == 2) ? 1 + CS * (kSendThreads / 32) : 1;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bars + i)), "r"(kArrivals));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync();
+  long long t0 = clock64();
+  for (int r = 0; r < rounds; ++r) {
+    const int b = r & 1;
+    uint8_t* stage = stage0 + b * PIECE;
+    const uint32_t bar_local = s32(bars + b);
+    // arm this round's barrier (the local arrival; transaction bytes for the async modes)
+    if (tid == 0) {
+      if (MODE == 2) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_local) : "memory");
+      else asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local), "r"(CS * PIECE) : "memory");
+    }
+    // "epilogue": every sender thread refreshes its part of the staging piece
+    if (tid < kSendThreads) {
+      for (int i = tid; i < PIECE / 4; i += kSendThreads) reinterpret_cast<uint32_t*>(stage)[i] = rank * 1000 + i + r + 1;
+    }
+    if (MODE == 0) {
+      if (tid < kSendThreads) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 sender warps
+      }
+      if (warp == 0 && lane < CS) {
+        const uint32_t dst = mapa(s32(rbuf + (size_t)b * CS * PIECE + rank * PIECE), lane);
+        const uint32_t rb = mapa(bar_local, lane);
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "r"(s32(stage)), "r"(PIECE), "r"(rb) : "memory");
+      }
+    } else if (MODE == 1) {
+      if (tid < kSendThreads) {
+        // chunk c of the piece -> every destination; thread handles chunks tid, tid+128, ...
+        for (int c = tid; c < PIECE / 16; c += kSendThreads) {
+          const uint4 v = reinterpret_cast<const uint4*>(stage)[c];
+          const uint32_t off = s32(rbuf + (size_t)b * CS * PIECE + rank * PIECE + c * 16);
+#pragma unroll
+          for (int d = 0; d < CS; ++d) {
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                         ::"r"(mapa(off, d)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mapa(bar_local, d)) : "memory");
+          }
+        }
+      }
+    } else {
+      if (tid < kSendThreads) {
+        for (int c = tid; c < PIECE / 16; c += kSendThreads) {
+          const uint4 v = reinterpret_cast<const uint4*>(stage)[c];
+          const uint32_t off = s32(rbuf + (size_t)b * CS * PIECE + rank * PIECE + c * 16);
+#pragma unroll
+          for (int d = 0; d < CS; ++d)
+            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mapa(off, d)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        __syncwarp();
+        if (lane < CS)
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa(bar_local, lane)) : "memory");
+      }
+    }
+    // everyone waits for the CS pieces of this round
+    const uint32_t parity = (r >> 1) & 1;
+    for (unsigned spins = 0; !try_wait(bar_local, parity); ++spins) {
+      if (spins > 4000000u) { if (lane == 0) printf("stuck: block %d warp %d round %d\n", blockIdx.x, warp, r); __trap(); }
+    }
+  }
+  long long t1 = clock64();
+  cluster_sync();
+  if (tid == 0) {
+    out[blockIdx.x * 2] = t1 - t0;
+    // checksum of what arrived: piece of rank q starts with q*1000 + rounds (+ i)
+    long long bad = 0;
+    const int b = (rounds - 1) & 1;
+    for (int q = 0; q < CS; ++q) {
+      const uint32_t v = reinterpret_cast<const uint32_t*>(rbuf + (size_t)b * CS * PIECE + q * PIECE)[0];
+      if (v != (uint32_t)(q * 1000 + rounds)) ++bad;
+    }
+    out[blockIdx.x * 2 + 1] = bad;
+  }
+}
+
+template <int CS, int PIECE, int MODE>
+void run(int nclusters, int rounds) {
+  auto kern = xchg_kernel<CS, PIECE, MODE>;
+  const size_t smem = 2 * CS * PIECE + 2 * PIECE + 64;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * CS);
+  cfg.blockDim = dim3(160);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int maxc = -1;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&maxc, kern, &cfg);
+  long long* out;
+  CK(cudaMalloc(&out, sizeof(long long) * 2 * nclusters * CS));
+  CK(cudaMemset(out, 0, sizeof(long long) * 2 * nclusters * CS));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; ++rep) {
+    CK(cudaEventRecord(e0));
+    CK(cudaLaunchKernelEx(&cfg, kern, rounds, out));
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+  }
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  std::vector<long long> h(2 * nclusters * CS);
+  CK(cudaMemcpy(h.data(), out, h.size() * 8, cudaMemcpyDeviceToHost));
+  long long mn = 1ll << 60, mx = 0, bad = 0;
+  for (int i = 0; i < nclusters * CS; ++i) { mn = std::min(mn, h[2 * i]); mx = std::max(mx, h[2 * i]); bad += h[2 * i + 1]; }
+  printf("CS=%2d piece=%5d mode=%d clusters=%d (max active %d, occ query %s) : %.0f .. %.0f cycles/round, %.3f us/round, bad=%lld\n", CS, PIECE,
+         MODE, nclusters, maxc, e == cudaSuccess ? "ok" : cudaGetErrorString(e), double(mn) / rounds, double(mx) / rounds,
+         ms * 1e3 / rounds, bad);
+  CK(cudaFree(out));
+}
+
+int main(int argc, char** argv) {
+  setvbuf(stdout, nullptr, _IONBF, 0);
+  const int R = 4000;
+  const int which = argc > 1 ? atoi(argv[1]) : -1;  // one configuration per process: a trap must not take the others down
+  int k = 0;
+#define CASE(...) if (which == k++) { __VA_ARGS__; return 0; }
+  CASE(run<16, 1024, 0>(1, R)) CASE(run<16, 1024, 0>(8, R))
+  CASE(run<16, 1024, 1>(1, R)) CASE(run<16, 1024, 1>(8, R))
+  CASE(run<16, 1024, 2>(1, R)) CASE(run<16, 1024, 2>(8, R))
+  CASE(run<16, 2048, 0>(8, R)) CASE(run<16, 2048, 1>(8, R)) CASE(run<16, 2048, 2>(8, R))
+  CASE(run<16, 512, 0>(8, R)) CASE(run<16, 512, 1>(8, R))
+  CASE(run<8, 2048, 0>(16, R)) CASE(run<8, 2048, 1>(16, R))
+  CASE(run<8, 1024, 0>(16, R)) CASE(run<8, 1024, 1>(16, R))
+  CASE(run<16, 1024, 0>(9, R))
+  CASE(run<16, 4096, 0>(8, 500)) CASE(run<16, 4096, 0>(7, 500)) CASE(run<16, 4096, 0>(6, 500)) CASE(run<8, 8192, 0>(16, 500))
+  printf("cases: %d\n", k);
+  return 0;
+}
