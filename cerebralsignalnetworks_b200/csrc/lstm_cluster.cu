@@ -55,6 +55,9 @@ __device__ __forceinline__ void handoff_arrive() { asm volatile("bar.arrive 1, %
 template <int NTHREADS>
 __device__ __forceinline__ void handoff_wait() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
+__device__ __forceinline__ void handoff_arrive_id(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void handoff_wait_id(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 template <int CS>
 struct FwdSmem {
   static constexpr uint32_t h_bytes = CS * kPiece;            // one h operand buffer: [k-group H/8][trial 16][8 k] bf16
@@ -89,11 +92,11 @@ __device__ __forceinline__ void quad_transpose(float (&x)[4], int g) {
 // One step's MMAs of issuer warp HALF: K-steps [HALF * CS, (HALF + 1) * CS) (two per source CTA), alternating over the
 // warp's two accumulators; PART selects the first / second arrival group of the half.
 template <int CS, int HALF, int PART>
-__device__ __forceinline__ void issue_part(uint32_t tb, uint64_t db, uint32_t idesc) {
+__device__ __forceinline__ void issue_part(uint32_t tb, uint32_t acc, uint64_t db, uint32_t idesc) {
 #pragma unroll
   for (int i = PART * (CS / 2); i < (PART + 1) * (CS / 2); ++i) {
     const int kk = HALF * CS + i;
-    umma_f16_ts(tb + uint32_t(HALF * 2 + (i & 1)) * kNT, tb + kWcol0 + kk * 8, db + uint64_t((uint32_t(kk) * 2u * kLbo) >> 4), idesc,
+    umma_f16_ts(acc + uint32_t(HALF * 2 + (i & 1)) * kNT, tb + kWcol0 + kk * 8, db + uint64_t((uint32_t(kk) * 2u * kLbo) >> 4), idesc,
                 i < 2 ? 0u : 1u);
   }
 }
@@ -102,39 +105,55 @@ __device__ __forceinline__ void issue_part(uint32_t tb, uint64_t db, uint32_t id
 // xp: hoisted input projection incl. both biases, fp32 [T*B, 4H], gate-interleaved columns (4u + g) -- through tm_xp,
 // box = this CTA's 128 columns x 16 trials.  w_rows: W_hh as bf16 rows in the same interleaved order ([4H][H], read as
 // packed pairs).  Outputs: h_seq bf16 [T,B,H]; BPTT reserve gates bf16 [T,B,4H] (activations, interleaved) and c fp32 [T,B,H].
-template <int CS, bool PROF>
-__global__ void __launch_bounds__(kThreads, 1)
+//
+// G = trial GROUPS per cluster.  A step's all-gather keeps the SM idle for most of its ~1250 cycles, and only 7 clusters of
+// 16 CTAs are co-resident on a B200 (GPC sizes), so 8 groups of 16 trials (B = 128) would run as two waves.  With G = 2 a
+// cluster carries two independent groups of 16 trials, each with its own warps, operand buffers, accumulators and
+// barriers, sharing only the resident weights: one group's gather is in flight while the other multiplies and runs its
+// cells.  Warp map (12 G warps): epilogue warps [8 gi, 8 gi + 8), issuers 8 G + 2 gi + {0, 1}, sender 10 G + gi,
+// producer 11 G + gi.
+template <int CS, int G, bool PROF>
+__global__ void __launch_bounds__(kThreads * G, 1)
 lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_t* __restrict__ w_rows,
                         __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
                         int T, int B, long long* __restrict__ prof) {
   constexpr int H = CS * kUnits;
   using L = FwdSmem<CS>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t* const hbuf = smem_raw + L::off_h;
-  uint8_t* const stage = smem_raw + L::off_stage;
-  uint8_t* const xring = smem_raw + L::off_x;
-  uint64_t* const grp_bar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);  // [2][kGroups]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // role and trial group of this warp
+  const int gi = warp < 8 * G ? warp / 8 : warp < 10 * G ? (warp - 8 * G) / 2 : warp < 11 * G ? warp - 10 * G : warp - 11 * G;
+  uint8_t* const gbase = smem_raw + size_t(gi) * L::total;
+  uint8_t* const hbuf = gbase + L::off_h;
+  uint8_t* const stage = gbase + L::off_stage;
+  uint8_t* const xring = gbase + L::off_x;
+  uint64_t* const grp_bar = reinterpret_cast<uint64_t*>(gbase + L::off_bar);  // [2][kGroups]
   uint64_t* const acc_bar = grp_bar + 2 * kGroups;
   uint64_t* const xp_bar = acc_bar + 1;                                           // [kXStages]
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(xp_bar + kXStages);
-  volatile int* const progress = reinterpret_cast<volatile int*>(tmem_slot + 1);  // steps whose hand-off the sender has seen
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L::off_bar) + 2 * (2 * kGroups + 1 + kXStages);  // group 0's block
+  volatile int* const progress = reinterpret_cast<volatile int*>(xp_bar + kXStages) + 1;  // steps whose hand-off the sender has seen
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
-  const int b0 = (int)(blockIdx.x / CS) * kNT;
+  const int b0 = ((int)(blockIdx.x / CS) * G + gi) * kNT;
+  const int hbar = 1 + gi;  // named barrier of this group's hand-off
+  const bool prof_on = PROF && prof && blockIdx.x == 0 && gi == 0;
 
   if (tid == 0) {
-    for (int i = 0; i < 2 * kGroups; ++i) mbar_init(grp_bar + i, 1);
-    mbar_init(acc_bar, 2);  // one tcgen05.commit per issuer warp
-    for (int i = 0; i < kXStages; ++i) mbar_init(xp_bar + i, 1);
-    *progress = 0;
+    for (int k = 0; k < G; ++k) {
+      uint64_t* gb = reinterpret_cast<uint64_t*>(smem_raw + size_t(k) * L::total + L::off_bar);
+      for (int i = 0; i < 2 * kGroups; ++i) mbar_init(gb + i, 1);
+      mbar_init(gb + 2 * kGroups, 2);  // one tcgen05.commit per issuer warp
+      for (int i = 0; i < kXStages; ++i) mbar_init(gb + 2 * kGroups + 1 + i, 1);
+      *(reinterpret_cast<volatile int*>(gb + 2 * kGroups + 1 + kXStages) + 1) = 0;
+    }
     fence_mbar_init();
   }
-  if (warp == kIssuer0) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 8 * G) tmem_alloc(tmem_slot, kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_base = tmem_base + uint32_t(gi) * 64u;  // this group's four accumulators
   if (warp < 4) {  // resident weights: TMEM lane = gate row 4u + g of this CTA's units, column kWcol0 + k / 2
     const uint4* src = reinterpret_cast<const uint4*>(w_rows + (size_t(rank) * 128 + tid) * (H / 2));
     const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16) + kWcol0;
@@ -155,42 +174,42 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
   tcgen05_fence_after();
   cluster_sync_all();  // every CTA's barriers exist before a peer's first copy can complete on them
 
-  if (warp >= kIssuer0 && warp < kIssuer0 + 2) {
+  if (warp >= 8 * G && warp < 10 * G) {
     // ================= MMA issuers: step t consumes h_{t-1} from buffer t & 1 =================
     constexpr uint32_t idesc = make_idesc_bf16(128, kNT, 0, 0);
     const uint64_t db0 = make_smem_desc(smem_u32(hbuf), kLbo, kSbo, kLayoutNone);
     auto loop = [&](auto half_tag) {
       constexpr int HALF = decltype(half_tag)::value;
       for (int t = 1; t < T; ++t) {
-        handoff_wait<kHandoffThreads>();  // this CTA's epilogue has drained the accumulators of step t - 1
+        handoff_wait_id(hbar, kHandoffThreads);  // this group's epilogue has drained the accumulators of step t - 1
         const int b = t & 1;
         const uint32_t par = uint32_t((t - 1) >> 1) & 1u;
         const uint64_t db = db0 + uint64_t((uint32_t(b) * L::h_bytes) >> 4);
-        const bool pr = PROF && prof && blockIdx.x == 0 && lane == 0 && t < 128;
+        const bool pr = prof_on && lane == 0 && t < 128;
         if (pr) prof[HALF ? 1024 + t * 4 + 3 : t * 8 + 3] = clock64();  // hand-off seen
         mbar_wait(grp_bar + b * kGroups + 2 * HALF, par);
         tcgen05_fence_after();
         __syncwarp();
         if (pr) prof[HALF ? 1024 + t * 4 + 0 : t * 8 + 5] = clock64();
-        if (elect_one()) issue_part<CS, HALF, 0>(tmem_base, db, idesc);
+        if (elect_one()) issue_part<CS, HALF, 0>(tmem_base, acc_base, db, idesc);
         __syncwarp();
         mbar_wait(grp_bar + b * kGroups + 2 * HALF + 1, par);
         __syncwarp();
         if (pr) prof[HALF ? 1024 + t * 4 + 1 : t * 8 + 6] = clock64();
         if (elect_one()) {
-          issue_part<CS, HALF, 1>(tmem_base, db, idesc);
+          issue_part<CS, HALF, 1>(tmem_base, acc_base, db, idesc);
           umma_commit(acc_bar);
         }
         __syncwarp();
         if (pr) prof[HALF ? 1024 + t * 4 + 2 : t * 8 + 7] = clock64();
       }
     };
-    if (warp == kIssuer0) loop(std::integral_constant<int, 0>{});
+    if (((warp - 8 * G) & 1) == 0) loop(std::integral_constant<int, 0>{});
     else loop(std::integral_constant<int, 1>{});
-  } else if (warp == kSender) {
+  } else if (warp >= 10 * G && warp < 11 * G) {
     // ================= all-gather: this CTA's h_t slice -> buffer (t + 1) & 1 of every CTA of the cluster =================
     for (int t = 0; t + 1 < T; ++t) {
-      handoff_wait<kHandoffThreads>();  // the slice is staged (and fenced towards the async proxy by its writers)
+      handoff_wait_id(hbar, kHandoffThreads);  // the slice is staged (and fenced towards the async proxy by its writers)
       const int b = (t + 1) & 1;
       if (lane < kGroups) mbar_arrive_expect_tx(grp_bar + b * kGroups + lane, (CS / kGroups) * kPiece);
       if (lane < CS) {
@@ -200,9 +219,9 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
       }
       if (lane == 0) *progress = t + 1;
       __syncwarp();
-      if constexpr (PROF) { if (prof && blockIdx.x == 0 && lane == 0 && t + 1 < 128) prof[(t + 1) * 8 + 4] = clock64(); }  // copies of h_t issued
+      if (prof_on && lane == 0 && t + 1 < 128) prof[(t + 1) * 8 + 4] = clock64();  // copies of h_t issued
     }
-  } else if (warp == kProducer) {
+  } else if (warp >= 11 * G) {
     // ================= TMA ring of the hoisted input projection =================
     if (lane == 0) {
       for (int t = 0; t < T; ++t) {
@@ -217,10 +236,11 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
     }
   } else {
     // ================= epilogue: thread = (gate row 4u + g, eight of the sixteen trials) =================
-    const int q = warp & 3, half = warp >> 2;
+    const int wl = warp & 7;
+    const int q = wl & 3, half = wl >> 2;
     const int row = q * 32 + lane, ul = row >> 2, g = row & 3;
     const int jb = half * 8;
-    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + jb;
+    const uint32_t lane_addr = acc_base + (uint32_t(q * 32) << 16) + jb;
     const float sc = (g == 2) ? 1.f : 0.5f, off = (g == 2) ? 0.f : 0.5f;  // sigmoid(x) = 0.5 tanh(0.5 x) + 0.5
     float c[2] = {0.f, 0.f};
     // after the transposes this thread owns the cells (unit ul, trials jb + g and jb + 4 + g)
@@ -235,6 +255,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
       cell[i] = valid[i] ? size_t(b0 + n[i]) * H + rank * kUnits + ul : 0;
     }
     uint2* const gates2 = reinterpret_cast<uint2*>(gates_out);
+    const bool pr0 = prof_on && (tid & 255) == 0;
     for (int t = 0; t < T; ++t) {
       mbar_wait(xp_bar + (t & (kXStages - 1)), uint32_t(t / kXStages) & 1u);
       const float* xs = reinterpret_cast<const float*>(xring + size_t(t & (kXStages - 1)) * kXStageBytes) + row;
@@ -244,13 +265,13 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
       if (t > 0) {
         mbar_wait(acc_bar, uint32_t(t - 1) & 1u);
         tcgen05_fence_after();
-        if constexpr (PROF) { if (prof && blockIdx.x == 0 && tid == 0 && t < 128) prof[t * 8 + 0] = clock64(); }
+        if (pr0 && t < 128) prof[t * 8 + 0] = clock64();
         uint32_t r[4][8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) tmem_ld<8>(lane_addr + k * kNT, r[k]);
         tmem_ld_wait();
         tcgen05_fence_before();
-        if constexpr (PROF) { if (prof && blockIdx.x == 0 && tid == 0 && t < 128) prof[t * 8 + 1] = clock64(); }
+        if (pr0 && t < 128) prof[t * 8 + 1] = clock64();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           a[j] += (__uint_as_float(r[0][j]) + __uint_as_float(r[1][j])) + (__uint_as_float(r[2][j]) + __uint_as_float(r[3][j]));
@@ -272,8 +293,8 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
 #pragma unroll
         for (int i = 0; i < 2; ++i) *reinterpret_cast<__nv_bfloat16*>(st + n[i] * 16) = hb[i];
         fence_proxy_async_smem();
-        handoff_arrive<kHandoffThreads>();
-        if constexpr (PROF) { if (prof && blockIdx.x == 0 && tid == 0 && t < 128) prof[t * 8 + 2] = clock64(); }
+        handoff_arrive_id(hbar, kHandoffThreads);
+        if (pr0 && t < 128) prof[t * 8 + 2] = clock64();
       }
       // ---- off the chain: h_t and the BPTT reserve ----
 #pragma unroll
@@ -294,7 +315,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();  // no CTA retires while a peer's copy may still read its staging piece
-  if (warp == kIssuer0) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 8 * G) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -307,11 +328,11 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
 // (fixed order: deterministic), adds the gradient arriving from above, runs the cell backward for its 32 x 16 cells and
 // writes dG_t^T for its next MMAs.  The tiles' products are committed one by one, so the copies of the first tile's
 // blocks are in flight while the later tiles still multiply.
-constexpr int kBwdEpiThreads = kEpiWarps * 32;
-constexpr int kBwdIssuer0 = 8, kBwdSender0 = 10, kBwdProducer = 14;  // 4 sender warps: one per 4 destinations
-constexpr int kBwdThreads = 15 * 32;
+// G trial groups per cluster as in the forward kernel.  Warp map (15 G warps): epilogue [8 gi, 8 gi + 8), issuers
+// 8 G + 2 gi + {0, 1}, senders 10 G + 4 gi + tile, producer 14 G + gi.
+constexpr int kBwdWarps = 15;
 constexpr int kBwdHandoff = (kEpiWarps + 2) * 32;                   // epilogue (arrive) + two issuer warps (sync)
-constexpr int kBwdSendBar = (kEpiWarps + 1) * 32;                   // epilogue (arrive) + one sender warp (sync), barriers 2..5
+constexpr int kBwdSendBar = (kEpiWarps + 1) * 32;                   // epilogue (arrive) + one sender warp (sync)
 constexpr uint32_t kLboG = 272;                                     // dG^T operand k-group stride (bank rotation, see lstm_tc.cu)
 constexpr uint32_t kGBytes = 16 * kLboG;                            // K = 128 gate rows -> 16 k-groups
 constexpr int kBStages = 4;
@@ -325,49 +346,58 @@ struct BwdSmem {
   static constexpr uint32_t off_g = off_stage + 2 * r_bytes;        // dG^T operand
   static constexpr uint32_t off_ring = off_g + ((kGBytes + 127) & ~127u);
   static constexpr uint32_t off_bar = off_ring + kBStages * kBStageBytes;
-  static constexpr uint32_t total = off_bar + 256;
+  static constexpr uint32_t total = off_bar + 128;
 };
 
 // wt_rows: W_hh^T as bf16 [H][4H], column 4u + g (gate-interleaved): row m, columns [128c, 128c + 128) is CTA c's A row.
-template <int CS, bool PROF>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+template <int CS, int G, bool PROF>
+__global__ void __launch_bounds__(kBwdWarps * 32 * G, 1)
 lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __grid_constant__ CUtensorMap tm_c,
                         const __grid_constant__ CUtensorMap tm_dh, const uint32_t* __restrict__ wt_rows,
                         const float* __restrict__ c_seq, const float* __restrict__ d_hlast, int has_dhseq,
                         __nv_bfloat16* __restrict__ dG, int T, int B, long long* __restrict__ prof) {
   constexpr int H = CS * kUnits;
   constexpr int MT = H / 128;  // M tiles of the partial product; tile mt feeds destinations [4 mt, 4 mt + 4)
+  constexpr int kThreadsAll = kBwdWarps * 32 * G;
   using L = BwdSmem<CS>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t* const rbuf = smem_raw + L::off_r;
-  uint8_t* const stage = smem_raw + L::off_stage;
-  uint8_t* const gop = smem_raw + L::off_g;
-  uint8_t* const ring = smem_raw + L::off_ring;
-  uint64_t* const recv_bar = reinterpret_cast<uint64_t*>(smem_raw + L::off_bar);  // [2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gi = warp < 8 * G ? warp / 8 : warp < 10 * G ? (warp - 8 * G) / 2 : warp < 14 * G ? (warp - 10 * G) / 4 : warp - 14 * G;
+  uint8_t* const gbase = smem_raw + size_t(gi) * L::total;
+  uint8_t* const rbuf = gbase + L::off_r;
+  uint8_t* const stage = gbase + L::off_stage;
+  uint8_t* const gop = gbase + L::off_g;
+  uint8_t* const ring = gbase + L::off_ring;
+  uint64_t* const recv_bar = reinterpret_cast<uint64_t*>(gbase + L::off_bar);     // [2]
   uint64_t* const acc_bar = recv_bar + 2;                                          // [4] one per M tile
   uint64_t* const pf_bar = acc_bar + 4;                                            // [kBStages]
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(pf_bar + kBStages);
-  volatile int* const progress = reinterpret_cast<volatile int*>(tmem_slot + 1);   // hand-offs seen by issuer warp 0
+  volatile int* const progress = reinterpret_cast<volatile int*>(pf_bar + kBStages) + 1;  // hand-offs seen by issuer warp 0
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L::off_bar) + 2 * (2 + 4 + kBStages);  // group 0's block
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
-  const int b0 = (int)(blockIdx.x / CS) * kNT;
+  const int b0 = ((int)(blockIdx.x / CS) * G + gi) * kNT;
+  const int hbar = 1 + gi;            // named barrier of this group's hand-off
+  const int sbar0 = 1 + G + 4 * gi;   // first of this group's four send barriers
+  const bool prof_on = PROF && prof && blockIdx.x == 0 && gi == 0;
 
   if (tid == 0) {
-    mbar_init(recv_bar, 1);
-    mbar_init(recv_bar + 1, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(acc_bar + i, 1);
-    for (int i = 0; i < kBStages; ++i) mbar_init(pf_bar + i, 1);
-    *progress = 0;
+    for (int k = 0; k < G; ++k) {
+      uint64_t* gb = reinterpret_cast<uint64_t*>(smem_raw + size_t(k) * L::total + L::off_bar);
+      for (int i = 0; i < 2 + 4 + kBStages; ++i) mbar_init(gb + i, 1);
+      *(reinterpret_cast<volatile int*>(gb + 2 + 4 + kBStages) + 1) = 0;
+    }
     fence_mbar_init();
   }
-  for (int i = tid; i < (int)(kGBytes / 4); i += kBwdThreads) reinterpret_cast<uint32_t*>(gop)[i] = 0u;
-  if (warp == kBwdIssuer0) tmem_alloc(tmem_slot, kTmemCols);
+  for (int k = 0; k < G; ++k)
+    for (int i = tid; i < (int)(kGBytes / 4); i += kThreadsAll)
+      reinterpret_cast<uint32_t*>(smem_raw + size_t(k) * L::total + L::off_g)[i] = 0u;
+  if (warp == 8 * G) tmem_alloc(tmem_slot, kTmemCols);
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_base = tmem_base + uint32_t(gi) * 64u;
   if (warp < 4) {  // resident operand: tile mt, TMEM lane = output unit 128 mt + lane, column kWcol0 + 64 mt + kl / 2
     const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16) + kWcol0;
 #pragma unroll 1
@@ -391,37 +421,37 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __gr
   tcgen05_fence_after();
   cluster_sync_all();
 
-  if (warp >= kBwdIssuer0 && warp < kBwdIssuer0 + 2) {
+  if (warp >= 8 * G && warp < 10 * G) {
     // ================= MMA issuers: warp h multiplies tiles {2h, 2h + 1} (H = 256: one tile each) =================
     constexpr uint32_t idesc = make_idesc_bf16(128, kNT, 0, 0);
     const uint64_t db0 = make_smem_desc(smem_u32(gop), kLboG, kSbo, kLayoutNone);
-    const int hw = warp - kBwdIssuer0;
+    const int hw = (warp - 8 * G) & 1;
     constexpr int TPW = MT / 2;  // tiles per issuer warp
     for (int n = 0; n + 1 < T; ++n) {
-      handoff_wait<kBwdHandoff>();  // dG_t^T staged; every accumulator of the previous step has been read
+      handoff_wait_id(hbar, kBwdHandoff);  // dG_t^T staged; every accumulator of the previous step has been read
       tcgen05_fence_after();
       if (elect_one()) {
-        if constexpr (PROF) { if (prof && blockIdx.x == 0 && hw == 0 && n < 128) prof[2048 + n * 8 + 4] = clock64(); }
+        if (prof_on && hw == 0 && n < 128) prof[2048 + n * 8 + 4] = clock64();
 #pragma unroll
         for (int j = 0; j < TPW; ++j) {
           const int mt = hw * TPW + j;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16_ts(tmem_base + uint32_t(mt) * kNT, tmem_base + kWcol0 + uint32_t(mt) * 64 + kk * 8,
+            umma_f16_ts(acc_base + uint32_t(mt) * kNT, tmem_base + kWcol0 + uint32_t(mt) * 64 + kk * 8,
                         db0 + uint64_t((uint32_t(kk) * 2u * kLboG) >> 4), idesc, kk ? 1u : 0u);
           umma_commit(acc_bar + mt);
         }
-        if constexpr (PROF) { if (prof && blockIdx.x == 0 && hw == 0 && n < 128) prof[2048 + n * 8 + 5] = clock64(); }
+        if (prof_on && hw == 0 && n < 128) prof[2048 + n * 8 + 5] = clock64();
         if (hw == 0) *progress = n + 1;
       }
       __syncwarp();
     }
-  } else if (warp >= kBwdSender0 && warp < kBwdSender0 + 4) {
+  } else if (warp >= 10 * G && warp < 14 * G) {
     // ================= reduce-scatter: tile j's blocks -> buffer (n + 1) & 1 of CTAs 4 j .. 4 j + 3 =================
-    const int j = warp - kBwdSender0;
+    const int j = (warp - 10 * G) & 3;
     if (j < MT) {
       for (int n = 0; n + 1 < T; ++n) {
-        asm volatile("bar.sync %0, %1;" ::"r"(2 + j), "n"(kBwdSendBar) : "memory");  // tile j's blocks are staged and fenced
+        handoff_wait_id(sbar0 + j, kBwdSendBar);  // tile j's blocks are staged and fenced
         const int nb = (n + 1) & 1;
         if (j == 0 && lane == 0) mbar_arrive_expect_tx(recv_bar + nb, L::r_bytes);
         if (lane < 4) {
@@ -432,7 +462,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __gr
         __syncwarp();
       }
     }
-  } else if (warp == kBwdProducer) {
+  } else if (warp >= 14 * G) {
     // ================= TMA ring of the per-step inputs of this CTA's 32 units x 16 trials =================
     if (lane == 0) {
       const uint32_t bytes = kNT * (256 + 128) + (has_dhseq ? kNT * 128 : 0);
@@ -450,12 +480,13 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __gr
         if (has_dhseq) tma_load_2d(dst + kNT * 384, &tm_dh, bar, (int)rank * kUnits, t * B + b0);
       }
     }
-  } else if (warp < kEpiWarps) {
+  } else {
     // ================= epilogue =================
     // phase B (cells): thread = (unit ul, trials tn and tn + 8);  phase A (partials): thread = (TMEM lane, trial half)
-    const int ul = tid & 31, tn = tid >> 5;
-    const int q = warp & 3, half = warp >> 2;
-    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + half * 8;
+    const int et = tid & 255, wl = warp & 7;
+    const int ul = et & 31, tn = et >> 5;
+    const int q = wl & 3, half = wl >> 2;
+    const uint32_t lane_addr = acc_base + (uint32_t(q * 32) << 16) + half * 8;
     float dc[2] = {0.f, 0.f}, c_cur[2], dhl[2];
     bool valid[2];
     size_t cell[2];
@@ -473,16 +504,16 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __gr
     auto bf_hi = [](uint32_t w) { return __uint_as_float(w & 0xffff0000u); };
     for (int n = 0; n < T; ++n) {
       const int t = T - 1 - n;
-      const bool pr = PROF && prof && blockIdx.x == 0 && tid == 0 && n < 128;
+      const bool pr = prof_on && et == 0 && n < 128;
       // ---- phase B ----
       mbar_wait(pf_bar + (n & (kBStages - 1)), uint32_t(n / kBStages) & 1u);
       const uint8_t* st = ring + size_t(n & (kBStages - 1)) * kBStageBytes;
-      float gi[2], gf[2], gg[2], go[2], cp[2], dh[2], tcn[2];
+      float gi_[2], gf[2], gg[2], go[2], cp[2], dh[2], tcn[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int n_i = tn + 8 * i;
         const uint2 gq = *reinterpret_cast<const uint2*>(st + n_i * 256 + ul * 8);
-        gi[i] = bf_lo(gq.x); gf[i] = bf_hi(gq.x); gg[i] = bf_lo(gq.y); go[i] = bf_hi(gq.y);
+        gi_[i] = bf_lo(gq.x); gf[i] = bf_hi(gq.x); gg[i] = bf_lo(gq.y); go[i] = bf_hi(gq.y);
         cp[i] = *reinterpret_cast<const float*>(st + kNT * 256 + n_i * 128 + ul * 4);
         dh[i] = has_dhseq ? *reinterpret_cast<const float*>(st + kNT * 384 + n_i * 128 + ul * 4) : 0.f;
         if (n == 0) dh[i] += dhl[i];
@@ -510,9 +541,9 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __gr
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const float dct = fmaf(dh[i] * go[i], 1.f - tcn[i] * tcn[i], dc[i]);
-        const float d0 = dct * gg[i] * gi[i] * (1.f - gi[i]);
+        const float d0 = dct * gg[i] * gi_[i] * (1.f - gi_[i]);
         const float d1 = dct * cp[i] * gf[i] * (1.f - gf[i]);
-        const float d2 = dct * gi[i] * (1.f - gg[i] * gg[i]);
+        const float d2 = dct * gi_[i] * (1.f - gg[i] * gg[i]);
         const float d3 = dh[i] * tcn[i] * go[i] * (1.f - go[i]);
         dc[i] = dct * gf[i];
         const __nv_bfloat162 lo = __floats2bfloat162_rn(d0, d1), hi = __floats2bfloat162_rn(d2, d3);
@@ -524,7 +555,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __gr
       if (pr) prof[2048 + n * 8 + 1] = clock64();
       if (t > 0) {
         fence_proxy_async_smem();
-        handoff_arrive<kBwdHandoff>();
+        handoff_arrive_id(hbar, kBwdHandoff);
       }
       if (pr) prof[2048 + n * 8 + 2] = clock64();
 #pragma unroll
@@ -550,7 +581,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __gr
 #pragma unroll
         for (int k = 0; k < 8; ++k) *reinterpret_cast<__nv_bfloat16*>(dst + k * 64) = __float2bfloat16_rn(__uint_as_float(r[k]));
         fence_proxy_async_smem();
-        asm volatile("bar.arrive %0, %1;" ::"r"(2 + mt), "n"(kBwdSendBar) : "memory");
+        handoff_arrive_id(sbar0 + mt, kBwdSendBar);
       }
       if (pr) prof[2048 + n * 8 + 3] = clock64();
     }
@@ -558,7 +589,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __gr
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == kBwdIssuer0) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 8 * G) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace clus
@@ -576,32 +607,53 @@ constexpr size_t kOneCtaSmem = 120 * 1024;
 static long long* g_clus_prof = nullptr;
 void lstm_cluster_set_prof(long long* p) { g_clus_prof = p; }
 
-template <int CS>
-static int launch_fwd_cluster(const CUtensorMap& tm_xp, const uint32_t* w_rows, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq,
-                              int T, int B, cudaStream_t s) {
-  auto kern = g_clus_prof ? clus::lstm_fwd_cluster_kernel<CS, true> : clus::lstm_fwd_cluster_kernel<CS, false>;
-  const size_t smem = std::max<size_t>(clus::FwdSmem<CS>::total, kOneCtaSmem);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[g_clus_prof ? 1 : 0]) {
+// One cluster launch: grid = clusters x CS CTAs of `threads` threads; smem padded to one CTA per SM.
+template <typename K, typename... Args>
+static int launch_cluster(K kern, bool* attr_set, int cs, int clusters, int threads, size_t smem, cudaStream_t s, Args... args) {
+  smem = std::max<size_t>(smem, kOneCtaSmem);
+  if (!*attr_set) {
     CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (CS > 8) CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set[g_clus_prof ? 1 : 0] = true;
+    if (cs > 8) CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    *attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(ceil_div(B, clus::kNT) * CS), 1, 1);
-  cfg.blockDim = dim3(clus::kThreads, 1, 1);
+  cfg.gridDim = dim3((unsigned)(clusters * cs), 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.x = (unsigned)cs;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  CSN_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_xp, w_rows, h_seq, gates, c_seq, T, B, g_clus_prof));
+  CSN_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
   count_launches(1);
   return CSN_OK;
+}
+
+// Trial groups per cluster: one while all groups' clusters are co-resident (lowest step latency), two beyond that -- a
+// second wave would double the time, a second group per cluster hides in the first one's exchange.  A B200 holds 7
+// clusters of 16 CTAs / 15 of 8 at one CTA per SM (scripts/cluster_xchg_bench.cu: cudaOccupancyMaxActiveClusters).
+static int pick_groups(int B, int cs) {
+  static const int forced = [] { const char* e = getenv("CSN_CLUSTER_GROUPS"); return e ? atoi(e) : 0; }();
+  if (forced == 1 || forced == 2) return forced;
+  const int resident = cs > 8 ? 7 : 15;
+  return ceil_div(B, clus::kNT) > resident ? 2 : 1;
+}
+
+template <int CS, int G>
+static int launch_fwd_cluster(const CUtensorMap& tm_xp, const uint32_t* w_rows, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq,
+                              int T, int B, cudaStream_t s) {
+  static bool attr_set[2] = {false, false};
+  const int clusters = ceil_div(B, clus::kNT * G);
+  const size_t smem = size_t(G) * clus::FwdSmem<CS>::total;
+  if (g_clus_prof)
+    return launch_cluster(clus::lstm_fwd_cluster_kernel<CS, G, true>, &attr_set[1], CS, clusters, clus::kThreads * G, smem, s, tm_xp, w_rows,
+                          h_seq, gates, c_seq, T, B, g_clus_prof);
+  return launch_cluster(clus::lstm_fwd_cluster_kernel<CS, G, false>, &attr_set[0], CS, clusters, clus::kThreads * G, smem, s, tm_xp, w_rows,
+                        h_seq, gates, c_seq, T, B, g_clus_prof);
 }
 
 // Forward recurrence of one layer.  xp: [T*B, 4H] fp32 (input projection + biases, gate-interleaved columns);
@@ -611,38 +663,28 @@ int lstm_cluster_fwd(const float* xp, const __nv_bfloat16* whh_perm, __nv_bfloat
   CUtensorMap tm{};
   CSN_TRY(make_tmap_2d_plain(&tm, xp, 4, (uint64_t)(4 * H), (uint64_t)T * B, (uint64_t)(4 * H), 128, clus::kNT));
   const uint32_t* w_rows = reinterpret_cast<const uint32_t*>(whh_perm);
-  if (H == 512) return launch_fwd_cluster<16>(tm, w_rows, h_seq, gates, c_seq, T, B, s);
-  if (H == 256) return launch_fwd_cluster<8>(tm, w_rows, h_seq, gates, c_seq, T, B, s);
+  if (H == 512)
+    return pick_groups(B, 16) == 2 ? launch_fwd_cluster<16, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, s)
+                                   : launch_fwd_cluster<16, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, s);
+  if (H == 256)
+    return pick_groups(B, 8) == 2 ? launch_fwd_cluster<8, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, s)
+                                  : launch_fwd_cluster<8, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, s);
   set_error("lstm_cluster_fwd: unsupported hidden size %d", H);
   return CSN_EUNSUPPORTED;
 }
 
-template <int CS>
+template <int CS, int G>
 static int launch_bwd_cluster(const CUtensorMap& tm_g, const CUtensorMap& tm_c, const CUtensorMap& tm_dh, const uint32_t* wt_rows,
                               const float* c_seq, const float* d_hlast, int has_dhseq, __nv_bfloat16* dG, int T, int B, cudaStream_t s) {
-  auto kern = g_clus_prof ? clus::lstm_bwd_cluster_kernel<CS, true> : clus::lstm_bwd_cluster_kernel<CS, false>;
-  const size_t smem = std::max<size_t>(clus::BwdSmem<CS>::total, kOneCtaSmem);
   static bool attr_set[2] = {false, false};
-  if (!attr_set[g_clus_prof ? 1 : 0]) {
-    CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (CS > 8) CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set[g_clus_prof ? 1 : 0] = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(ceil_div(B, clus::kNT) * CS), 1, 1);
-  cfg.blockDim = dim3(clus::kBwdThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CS;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  CSN_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_g, tm_c, tm_dh, wt_rows, c_seq, d_hlast, has_dhseq, dG, T, B, g_clus_prof));
-  count_launches(1);
-  return CSN_OK;
+  const int clusters = ceil_div(B, clus::kNT * G);
+  const size_t smem = size_t(G) * clus::BwdSmem<CS>::total;
+  const int threads = clus::kBwdWarps * 32 * G;
+  if (g_clus_prof)
+    return launch_cluster(clus::lstm_bwd_cluster_kernel<CS, G, true>, &attr_set[1], CS, clusters, threads, smem, s, tm_g, tm_c, tm_dh,
+                          wt_rows, c_seq, d_hlast, has_dhseq, dG, T, B, g_clus_prof);
+  return launch_cluster(clus::lstm_bwd_cluster_kernel<CS, G, false>, &attr_set[0], CS, clusters, threads, smem, s, tm_g, tm_c, tm_dh,
+                        wt_rows, c_seq, d_hlast, has_dhseq, dG, T, B, g_clus_prof);
 }
 
 // Backward recurrence of one layer: dG [T*B, 4H] bf16 (gate-interleaved) from the reserve (gates, c_seq) and the gradients
@@ -655,8 +697,13 @@ int lstm_cluster_bwd(const __nv_bfloat16* gates, const float* c_seq, const float
   CSN_TRY(make_tmap_2d_plain(&tm_c, c_seq, 4, (uint64_t)H, tb, (uint64_t)H, clus::kUnits, clus::kNT));
   CSN_TRY(make_tmap_2d_plain(&tm_dh, d_hseq ? d_hseq : c_seq, 4, (uint64_t)H, tb, (uint64_t)H, clus::kUnits, clus::kNT));
   const uint32_t* wt = reinterpret_cast<const uint32_t*>(whh_t);
-  if (H == 512) return launch_bwd_cluster<16>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, d_hseq ? 1 : 0, dG, T, B, s);
-  if (H == 256) return launch_bwd_cluster<8>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, d_hseq ? 1 : 0, dG, T, B, s);
+  const int hd = d_hseq ? 1 : 0;
+  if (H == 512)
+    return pick_groups(B, 16) == 2 ? launch_bwd_cluster<16, 2>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, s)
+                                   : launch_bwd_cluster<16, 1>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, s);
+  if (H == 256)
+    return pick_groups(B, 8) == 2 ? launch_bwd_cluster<8, 2>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, s)
+                                  : launch_bwd_cluster<8, 1>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, s);
   set_error("lstm_cluster_bwd: unsupported hidden size %d", H);
   return CSN_EUNSUPPORTED;
 }
