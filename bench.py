@@ -338,7 +338,8 @@ def bench_cfg4(torch, dist, csn, dev, world, rank, steps, peaks):
             "batch_per_gpu": B, "global_batch": B * world, "value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
             "steps": n, "dp_exchange": ex,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-                         "note": "8.997 GFLOP algorithmic per trial (SURVEY 8d); one tcgen05 GEMM + fused cell epilogue per timestep"}}
+                         "note": "8.997 GFLOP algorithmic per trial (SURVEY 8d); persistent 16-CTA cluster recurrence (W_hh split over the cluster, "
+                                 "resident in tensor memory; per-step DSMEM all-gather / reduce-scatter), one launch per layer and direction"}}
 
 
 def bench_cfg5(torch, dist, csn, dev, world, rank, steps, peaks):

@@ -78,7 +78,11 @@ def _cos(a, b):
                                      # NV = 8 tiles (two timesteps per block), smallest sizes, and I > 128 (hoisted projection)
                                      (1, 2, 8, 8), (2, 1, 16, 32), (3, 5, 8, 128), (9, 700, 32, 32), (17, 640, 16, 64), (5, 4, 136, 64),
                                      # large-hidden path (per-step tcgen05 GEMM with the fused cell epilogue), cfg 4 sizes
-                                     (12, 5, 64, 256), (20, 130, 128, 512), (9, 3, 24, 136)])
+                                     (12, 5, 64, 256), (20, 130, 128, 512), (9, 3, 24, 136),
+                                     # cluster recurrence (H = 256 / 512, lstm_cluster.cu): a single timestep, one trial, a ragged
+                                     # last group, two trial groups per cluster at H = 256 (more than 15 groups of 16 trials),
+                                     # a wide input (I = 512, the second layer of cfg 4)
+                                     (1, 4, 32, 512), (3, 1, 16, 256), (37, 33, 64, 512), (6, 250, 32, 256), (10, 16, 512, 512)])
 @pytest.mark.parametrize("mode", ["last", "both"])
 def test_bf16_tensor_core_layer(T, B, I, H, mode):
     g = torch.Generator().manual_seed(T + B + I + H)
@@ -110,7 +114,7 @@ def test_bf16_unsupported_shape_is_an_error_not_a_fallback():
         ops.lstm_layer_bytes(10, 4, 64, 100, torch.bfloat16)
 
 
-@pytest.mark.parametrize("T,B,I,H", [(13, 6, 64, 128), (2000, 4, 64, 128), (7, 3, 136, 96), (11, 9, 32, 256)])
+@pytest.mark.parametrize("T,B,I,H", [(13, 6, 64, 128), (2000, 4, 64, 128), (7, 3, 136, 96), (11, 9, 32, 256), (600, 20, 64, 512)])
 def test_bf16_inference_only_forward(T, B, I, H):
     """training = 0 (no BPTT reserve): the path Model.encode_trials takes, including the 2000-sample trials of config 5."""
     from cerebralsignalnetworks_b200 import ops
