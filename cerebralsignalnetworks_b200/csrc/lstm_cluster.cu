@@ -58,6 +58,23 @@ __device__ __forceinline__ void handoff_wait() { asm volatile("bar.sync 1, %0;" 
 __device__ __forceinline__ void handoff_arrive_id(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void handoff_wait_id(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// spin (with back-off and a 20 s watchdog) until a flag word written by another kernel becomes non-zero
+__device__ __forceinline__ void wait_flag_set(const unsigned* p) {
+  unsigned v, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v) return;
+    __nanosleep(200);
+    if ((++spins & 4095u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
+  }
+}
+
 template <int CS>
 struct FwdSmem {
   static constexpr uint32_t h_bytes = CS * kPiece;            // one h operand buffer: [k-group H/8][trial 16][8 k] bf16
@@ -116,7 +133,7 @@ template <int CS, int G, bool PROF>
 __global__ void __launch_bounds__(kThreads * G, 1)
 lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_t* __restrict__ w_rows,
                         __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
-                        int T, int B, long long* __restrict__ prof) {
+                        int T, int B, const unsigned* __restrict__ xp_flags, int xp_chunk, long long* __restrict__ prof) {
   constexpr int H = CS * kUnits;
   using L = FwdSmem<CS>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -228,6 +245,12 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
         if (t >= kXStages) {
           const int need = t - kXStages + 1;  // step t - kXStages has been consumed by every epilogue thread
           while (*progress < need) __nanosleep(64);
+        }
+        if (xp_flags && t % xp_chunk == 0) {
+          // the projection GEMM runs beside this launch, one time chunk per GEMM: its rows exist once the chunk's flag is
+          // up (a one-thread kernel behind the GEMM in stream order); acquire, then order the TMA reads behind it
+          wait_flag_set(xp_flags + t / xp_chunk);
+          asm volatile("fence.proxy.async;" ::: "memory");
         }
         uint64_t* bar = xp_bar + (t & (kXStages - 1));
         mbar_arrive_expect_tx(bar, kXStageBytes);
@@ -643,32 +666,43 @@ static int pick_groups(int B, int cs) {
   return ceil_div(B, clus::kNT) > resident ? 2 : 1;
 }
 
+// May GEMM-shaped work run BESIDE the recurrence of B trials?  Only when the recurrence is one wave of clusters that
+// leaves at least half of the SMs free: with less, the GEMM chunks crawl (measured at B = 512: 16 clusters in three waves
+// of 112 SMs, the chunks on the 36 SMs left, forward 3.2 -> 21 ms) and the later waves queue behind them.
+bool lstm_cluster_overlap_ok(int B, int H) {
+  if (!lstm_cluster_supported(H)) return false;
+  const int cs = H / clus::kUnits;
+  const int clusters = ceil_div(B, clus::kNT * pick_groups(B, cs));
+  return clusters <= (cs > 8 ? 7 : 15) && 2 * clusters * cs <= sm_count();
+}
+
 template <int CS, int G>
 static int launch_fwd_cluster(const CUtensorMap& tm_xp, const uint32_t* w_rows, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq,
-                              int T, int B, cudaStream_t s) {
+                              int T, int B, const unsigned* xp_flags, int xp_chunk, cudaStream_t s) {
   static bool attr_set[2] = {false, false};
   const int clusters = ceil_div(B, clus::kNT * G);
   const size_t smem = size_t(G) * clus::FwdSmem<CS>::total;
   if (g_clus_prof)
     return launch_cluster(clus::lstm_fwd_cluster_kernel<CS, G, true>, &attr_set[1], CS, clusters, clus::kThreads * G, smem, s, tm_xp, w_rows,
-                          h_seq, gates, c_seq, T, B, g_clus_prof);
+                          h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, g_clus_prof);
   return launch_cluster(clus::lstm_fwd_cluster_kernel<CS, G, false>, &attr_set[0], CS, clusters, clus::kThreads * G, smem, s, tm_xp, w_rows,
-                        h_seq, gates, c_seq, T, B, g_clus_prof);
+                        h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, g_clus_prof);
 }
 
 // Forward recurrence of one layer.  xp: [T*B, 4H] fp32 (input projection + biases, gate-interleaved columns);
-// whh_perm: [4H, H] bf16, rows gate-interleaved.
+// whh_perm: [4H, H] bf16, rows gate-interleaved.  xp_flags (may be NULL): one word per chunk of xp_chunk timesteps, non-zero
+// once that chunk of xp has been written by the projection GEMM running beside this launch.
 int lstm_cluster_fwd(const float* xp, const __nv_bfloat16* whh_perm, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq, int T,
-                     int B, int H, cudaStream_t s) {
+                     int B, int H, const unsigned* xp_flags, int xp_chunk, cudaStream_t s) {
   CUtensorMap tm{};
   CSN_TRY(make_tmap_2d_plain(&tm, xp, 4, (uint64_t)(4 * H), (uint64_t)T * B, (uint64_t)(4 * H), 128, clus::kNT));
   const uint32_t* w_rows = reinterpret_cast<const uint32_t*>(whh_perm);
   if (H == 512)
-    return pick_groups(B, 16) == 2 ? launch_fwd_cluster<16, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, s)
-                                   : launch_fwd_cluster<16, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, s);
+    return pick_groups(B, 16) == 2 ? launch_fwd_cluster<16, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, s)
+                                   : launch_fwd_cluster<16, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, s);
   if (H == 256)
-    return pick_groups(B, 8) == 2 ? launch_fwd_cluster<8, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, s)
-                                  : launch_fwd_cluster<8, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, s);
+    return pick_groups(B, 8) == 2 ? launch_fwd_cluster<8, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, s)
+                                  : launch_fwd_cluster<8, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, s);
   set_error("lstm_cluster_fwd: unsupported hidden size %d", H);
   return CSN_EUNSUPPORTED;
 }

@@ -11,14 +11,17 @@
 //
 // A cluster-resident variant (W_hh split over a 16-CTA cluster, h exchanged through DSMEM) is the next step for this
 // size class; see DESIGN.md.
+#include <mutex>
+
 #include "gemm_tc.cuh"
 
 namespace csn {
 
 // lstm_cluster.cu: persistent cluster recurrence for H = 256 / 512
 bool lstm_cluster_supported(int H);
+bool lstm_cluster_overlap_ok(int B, int H);
 int lstm_cluster_fwd(const float* xp, const __nv_bfloat16* whh_perm, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq, int T,
-                     int B, int H, cudaStream_t s);
+                     int B, int H, const unsigned* xp_flags, int xp_chunk, cudaStream_t s);
 int lstm_cluster_bwd(const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq, const float* d_hlast,
                      const __nv_bfloat16* whh_t, __nv_bfloat16* dG, int T, int B, int H, cudaStream_t s);
 
@@ -113,6 +116,35 @@ __global__ void lstm_cell_bwd_kernel(const __nv_bfloat16* __restrict__ gates_t, 
   dc[cell] = dct * f;
 }
 
+// Helper stream (one per device) for the GEMM-shaped work that runs BESIDE a cluster recurrence: the recurrence occupies
+// 64-112 SMs for ~0.8 ms per layer, the rest of the machine takes the projection / weight-gradient GEMMs chunk by chunk.
+struct OverlapStream {
+  cudaStream_t st;
+  cudaEvent_t fork, first, join;
+};
+static OverlapStream* overlap_stream() {
+  static const bool off = [] { const char* e = getenv("CSN_LSTM_NO_OVERLAP"); return e && e[0] == '1'; }();
+  if (off) return nullptr;
+  static OverlapStream table[64];
+  static bool made[64] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!made[dev]) {
+    OverlapStream os{};
+    if (cudaStreamCreateWithFlags(&os.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&os.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&os.first, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&os.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    table[dev] = os;
+    made[dev] = true;
+  }
+  return &table[dev];
+}
+constexpr int kChunks = 8;  // time chunks of the overlapped GEMMs
+__global__ void set_flag_kernel(unsigned* flag) { *flag = 1u; }
+
 struct LargeWs {
   float* xp;                 // fwd: [TB,4H] fp32 ; bwd: unused
   __nv_bfloat16* dG;         // bwd: [TB,4H] bf16 (aliases xp)
@@ -125,6 +157,7 @@ struct LargeWs {
   float* dwp;                // [4H, max(I, H)] permuted dW scratch
   __nv_bfloat16* ones;       // [TB, 8]
   float* dbp;                // [4H, 8]
+  unsigned* flags;           // [2 * kChunks] chunk flags of the overlapped GEMMs
   size_t total;
 };
 
@@ -154,6 +187,7 @@ static LargeWs carve_ws(void* base, int T, int B, int I, int H) {
   w.dwp = reinterpret_cast<float*>(take((s_ih > s_hh ? s_ih : s_hh) * 4));
   w.ones = reinterpret_cast<__nv_bfloat16*>(take(tb * 8 * 2));
   w.dbp = reinterpret_cast<float*>(take(req(4 * H, 8) * 4 * H * 8 * 4));
+  w.flags = reinterpret_cast<unsigned*>(take(2 * kChunks * sizeof(unsigned)));
   w.total = off;
   return w;
 }
@@ -190,10 +224,35 @@ int lstm_layer_fwd_large(const void* x, const float* w_ih, const float* w_hh, co
   float* c_seq = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(reserve) + al256(tb * 4 * H * 2));
   __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(h_seq);
   CSN_TRY(prep_weights(w, w_ih, w_hh, b_ih, b_hh, I, H, s));
+  if (lstm_cluster_supported(H)) {
+    // The whole time loop in ONE persistent cluster launch.  The hoisted projection GEMM runs BESIDE it on the SMs the
+    // clusters leave free, one time chunk per GEMM; a one-thread kernel behind each chunk raises its flag and the
+    // recurrence's TMA producer waits for a chunk's flag before it touches that chunk's rows.
+    OverlapStream* os = (T >= 4 * kChunks && lstm_cluster_overlap_ok(B, H)) ? overlap_stream() : nullptr;
+    if (os) {
+      const int tc = ceil_div(T, kChunks);
+      CSN_CUDA(cudaMemsetAsync(w.flags, 0, kChunks * sizeof(unsigned), s));
+      CSN_CUDA(cudaEventRecord(os->fork, s));
+      CSN_CUDA(cudaStreamWaitEvent(os->st, os->fork, 0));
+      for (int c = 0; c * tc < T; ++c) {
+        const size_t r0 = size_t(c) * tc * B, rows = size_t(std::min(T, (c + 1) * tc) - c * tc) * B;
+        CSN_TRY(gemm_tc_run(0, 1, (int)rows, 4 * H, I, reinterpret_cast<const __nv_bfloat16*>(x) + r0 * I, I, w.wih, I, w.xp + r0 * 4 * H,
+                            4 * H, CSN_F32, w.bias, 0, 1, nullptr, os->st));
+        set_flag_kernel<<<1, 1, 0, os->st>>>(w.flags + c);
+        CSN_LAUNCH_CHECK();
+        if (c == 0) CSN_CUDA(cudaEventRecord(os->first, os->st));
+      }
+      CSN_CUDA(cudaEventRecord(os->join, os->st));
+      CSN_CUDA(cudaStreamWaitEvent(s, os->first, 0));
+      CSN_TRY(lstm_cluster_fwd(w.xp, w.whh, hs, gates, c_seq, T, B, H, w.flags, tc, s));
+      CSN_CUDA(cudaStreamWaitEvent(s, os->join, 0));
+      return CSN_OK;
+    }
+    CSN_TRY(gemm_tc_run(0, 1, (int)tb, 4 * H, I, x, I, w.wih, I, w.xp, 4 * H, CSN_F32, w.bias, 0, 1, nullptr, s));
+    return lstm_cluster_fwd(w.xp, w.whh, hs, gates, c_seq, T, B, H, nullptr, 1, s);
+  }
   // hoisted input projection in gate-interleaved column order
   CSN_TRY(gemm_tc_run(0, 1, (int)tb, 4 * H, I, x, I, w.wih, I, w.xp, 4 * H, CSN_F32, w.bias, 0, 1, nullptr, s));
-  if (lstm_cluster_supported(H))  // the whole time loop in ONE persistent cluster launch
-    return lstm_cluster_fwd(w.xp, w.whh, hs, gates, c_seq, T, B, H, s);
   for (int t = 0; t < T; ++t) {
     GemmEpi cell{};
     cell.pdl = kPdl;
