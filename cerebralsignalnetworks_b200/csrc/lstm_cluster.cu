@@ -378,7 +378,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32 * G, 1)
 lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __grid_constant__ CUtensorMap tm_c,
                         const __grid_constant__ CUtensorMap tm_dh, const uint32_t* __restrict__ wt_rows,
                         const float* __restrict__ c_seq, const float* __restrict__ d_hlast, int has_dhseq,
-                        __nv_bfloat16* __restrict__ dG, int T, int B, long long* __restrict__ prof) {
+                        __nv_bfloat16* __restrict__ dG, int T, int B, unsigned* __restrict__ done, int done_chunk,
+                        long long* __restrict__ prof) {
   constexpr int H = CS * kUnits;
   constexpr int MT = H / 128;  // M tiles of the partial product; tile mt feeds destinations [4 mt, 4 mt + 4)
   constexpr int kThreadsAll = kBwdWarps * 32 * G;
@@ -588,6 +589,13 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_gates, const __gr
           cell[i] -= step_cells;
         }
       }
+      if (done && t % done_chunk == 0) {
+        // every dG row of the time chunk that ends here is stored: publish it to the weight-gradient GEMMs that run beside
+        // this launch (each writer fences its own stores, one thread of the group counts the group in)
+        __threadfence();
+        handoff_wait_id(1 + 5 * G + gi, kEpiWarps * 32);
+        if (et == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(done + t / done_chunk), "r"(1u) : "memory");
+      }
       if (t == 0) break;
       // ---- phase A: the partial product tiles, rounded to bf16, one 1 KB block per destination ----
       uint8_t* const stg = stage + (n & 1) * L::r_bytes;
@@ -709,22 +717,30 @@ int lstm_cluster_fwd(const float* xp, const __nv_bfloat16* whh_perm, __nv_bfloat
 
 template <int CS, int G>
 static int launch_bwd_cluster(const CUtensorMap& tm_g, const CUtensorMap& tm_c, const CUtensorMap& tm_dh, const uint32_t* wt_rows,
-                              const float* c_seq, const float* d_hlast, int has_dhseq, __nv_bfloat16* dG, int T, int B, cudaStream_t s) {
+                              const float* c_seq, const float* d_hlast, int has_dhseq, __nv_bfloat16* dG, int T, int B, unsigned* done,
+                              int done_chunk, cudaStream_t s) {
   static bool attr_set[2] = {false, false};
   const int clusters = ceil_div(B, clus::kNT * G);
   const size_t smem = size_t(G) * clus::BwdSmem<CS>::total;
   const int threads = clus::kBwdWarps * 32 * G;
   if (g_clus_prof)
     return launch_cluster(clus::lstm_bwd_cluster_kernel<CS, G, true>, &attr_set[1], CS, clusters, threads, smem, s, tm_g, tm_c, tm_dh,
-                          wt_rows, c_seq, d_hlast, has_dhseq, dG, T, B, g_clus_prof);
+                          wt_rows, c_seq, d_hlast, has_dhseq, dG, T, B, done, done_chunk, g_clus_prof);
   return launch_cluster(clus::lstm_bwd_cluster_kernel<CS, G, false>, &attr_set[0], CS, clusters, threads, smem, s, tm_g, tm_c, tm_dh,
-                        wt_rows, c_seq, d_hlast, has_dhseq, dG, T, B, g_clus_prof);
+                        wt_rows, c_seq, d_hlast, has_dhseq, dG, T, B, done, done_chunk, g_clus_prof);
 }
 
 // Backward recurrence of one layer: dG [T*B, 4H] bf16 (gate-interleaved) from the reserve (gates, c_seq) and the gradients
 // arriving from above (d_hseq [T,B,H] and / or d_hlast [B,H], fp32).  whh_t: W_hh^T as bf16 [H][4H], columns interleaved.
+// done (may be NULL): zeroed counters, one per chunk of done_chunk timesteps; every (CTA, trial group) adds 1 to a chunk's
+// counter once all its dG rows of that chunk are stored -- lstm_cluster_participants(B, H) of them in total.
+int lstm_cluster_participants(int B, int H) {
+  const int cs = H / clus::kUnits, g = pick_groups(B, cs);
+  return ceil_div(B, clus::kNT * g) * cs * g;
+}
 int lstm_cluster_bwd(const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq, const float* d_hlast,
-                     const __nv_bfloat16* whh_t, __nv_bfloat16* dG, int T, int B, int H, cudaStream_t s) {
+                     const __nv_bfloat16* whh_t, __nv_bfloat16* dG, int T, int B, int H, unsigned* done, int done_chunk,
+                     cudaStream_t s) {
   CUtensorMap tm_g{}, tm_c{}, tm_dh{};
   const uint64_t tb = (uint64_t)T * B;
   CSN_TRY(make_tmap_2d_plain(&tm_g, gates, 2, (uint64_t)(4 * H), tb, (uint64_t)(4 * H), 128, clus::kNT));
@@ -733,11 +749,11 @@ int lstm_cluster_bwd(const __nv_bfloat16* gates, const float* c_seq, const float
   const uint32_t* wt = reinterpret_cast<const uint32_t*>(whh_t);
   const int hd = d_hseq ? 1 : 0;
   if (H == 512)
-    return pick_groups(B, 16) == 2 ? launch_bwd_cluster<16, 2>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, s)
-                                   : launch_bwd_cluster<16, 1>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, s);
+    return pick_groups(B, 16) == 2 ? launch_bwd_cluster<16, 2>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, done, done_chunk, s)
+                                   : launch_bwd_cluster<16, 1>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, done, done_chunk, s);
   if (H == 256)
-    return pick_groups(B, 8) == 2 ? launch_bwd_cluster<8, 2>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, s)
-                                  : launch_bwd_cluster<8, 1>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, s);
+    return pick_groups(B, 8) == 2 ? launch_bwd_cluster<8, 2>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, done, done_chunk, s)
+                                  : launch_bwd_cluster<8, 1>(tm_g, tm_c, tm_dh, wt, c_seq, d_hlast, hd, dG, T, B, done, done_chunk, s);
   set_error("lstm_cluster_bwd: unsupported hidden size %d", H);
   return CSN_EUNSUPPORTED;
 }

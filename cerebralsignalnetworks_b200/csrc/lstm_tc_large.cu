@@ -23,7 +23,9 @@ bool lstm_cluster_overlap_ok(int B, int H);
 int lstm_cluster_fwd(const float* xp, const __nv_bfloat16* whh_perm, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq, int T,
                      int B, int H, const unsigned* xp_flags, int xp_chunk, cudaStream_t s);
 int lstm_cluster_bwd(const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq, const float* d_hlast,
-                     const __nv_bfloat16* whh_t, __nv_bfloat16* dG, int T, int B, int H, cudaStream_t s);
+                     const __nv_bfloat16* whh_t, __nv_bfloat16* dG, int T, int B, int H, unsigned* done, int done_chunk,
+                     cudaStream_t s);
+int lstm_cluster_participants(int B, int H);
 
 static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -142,8 +144,27 @@ static OverlapStream* overlap_stream() {
   }
   return &table[dev];
 }
-constexpr int kChunks = 8;  // time chunks of the overlapped GEMMs
+constexpr int kChunks = 8;      // time chunks of the overlapped GEMMs
+constexpr int kChunkSplit = 4;  // split-K ranges inside one chunk (products with few output tiles)
 __global__ void set_flag_kernel(unsigned* flag) { *flag = 1u; }
+// one warp parks on a counter another (running) kernel bumps; everything behind it in its stream starts once the counter
+// has reached `target` (20 s watchdog: a stuck producer traps instead of hanging the device)
+__global__ void wait_counter_kernel(const unsigned* counter, unsigned target) {
+  if (threadIdx.x != 0) return;
+  unsigned v, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= target) return;
+    __nanosleep(500);
+    if ((++spins & 4095u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
+  }
+}
 
 struct LargeWs {
   float* xp;                 // fwd: [TB,4H] fp32 ; bwd: unused
@@ -155,6 +176,7 @@ struct LargeWs {
   float* dh_rec;             // 8 x [B, H]: split-K slabs of the recurrent gradient (summed by the cell kernel)
   float* dc;                 // [B, H]
   float* dwp;                // [4H, max(I, H)] permuted dW scratch
+  float* dwp2;               // second slab region (cluster BPTT: dW_ih and dW_hh chunk products are in flight together)
   __nv_bfloat16* ones;       // [TB, 8]
   float* dbp;                // [4H, 8]
   unsigned* flags;           // [2 * kChunks] chunk flags of the overlapped GEMMs
@@ -182,11 +204,13 @@ static LargeWs carve_ws(void* base, int T, int B, int I, int H) {
   w.dc = reinterpret_cast<float*>(take(size_t(B) * H * 4));
   // split-K slabs of the weight-gradient products (one partial [4H, N] per split, summed by unpermute_rows_kernel)
   // (sized for the REQUESTED split count: the GEMM may round it down, never up)
-  auto req = [](int M, int N) { return size_t(std::max(1, sm_count() / (ceil_div(M, 128) * ceil_div(N, 128)))); };
+  // (at least kChunks slabs: with the GEMMs overlapped, every time chunk's product is one slab)
+  auto req = [](int M, int N) { return size_t(std::max(kChunks, sm_count() / (ceil_div(M, 128) * ceil_div(N, 128)))); };
   const size_t s_ih = req(4 * H, I) * 4 * H * I, s_hh = req(4 * H, H) * 4 * H * H;
   w.dwp = reinterpret_cast<float*>(take((s_ih > s_hh ? s_ih : s_hh) * 4));
+  w.dwp2 = reinterpret_cast<float*>(take(lstm_cluster_supported(H) ? size_t(kChunks) * kChunkSplit * 4 * H * I * 4 : 0));
   w.ones = reinterpret_cast<__nv_bfloat16*>(take(tb * 8 * 2));
-  w.dbp = reinterpret_cast<float*>(take(req(4 * H, 8) * 4 * H * 8 * 4));
+  w.dbp = reinterpret_cast<float*>(take(std::max(req(4 * H, 8), size_t(kChunks) * kChunkSplit) * 4 * H * 8 * 4));
   w.flags = reinterpret_cast<unsigned*>(take(2 * kChunks * sizeof(unsigned)));
   w.total = off;
   return w;
@@ -282,7 +306,63 @@ int lstm_layer_bwd_large(const void* x, const float* w_ih, const float* w_hh, co
   if (cluster) {  // the whole BPTT recurrence in ONE persistent cluster launch (lstm_cluster.cu)
     permute_transpose_bf16_kernel<<<dim3(H / 32, 4 * H / 32), dim3(32, 8), 0, s>>>(w_hh, w.whh_t, H);
     CSN_LAUNCH_CHECK();
-    CSN_TRY(lstm_cluster_bwd(gates, c_seq, d_hseq, d_hlast, w.whh_t, w.dG, T, B, H, s));
+    OverlapStream* os = (T >= 4 * kChunks && lstm_cluster_overlap_ok(B, H)) ? overlap_stream() : nullptr;
+    if (os) {
+      // The weight-gradient / input-gradient GEMMs run BESIDE the recurrence on the SMs the clusters leave free, one time
+      // chunk per GEMM in the order the recurrence produces dG (last chunk first).  Every (CTA, trial group) of the
+      // recurrence counts itself into a chunk's counter once its dG rows of that chunk are stored; a one-warp kernel on
+      // the helper stream parks on the counter in front of the chunk's GEMMs.  Each chunk's product is one slab; the
+      // slabs are added in chunk order afterwards (fixed order: deterministic).
+      const int tc = ceil_div(T, kChunks), nc = ceil_div(T, tc);
+      unsigned* done = w.flags + kChunks;
+      const unsigned target = (unsigned)lstm_cluster_participants(B, H);
+      const int sms = sm_count();
+      CSN_CUDA(cudaMemsetAsync(done, 0, kChunks * sizeof(unsigned), s));
+      fill_bf16_kernel<<<min(ceil_div<size_t>(tb * 8, 256), size_t(sms) * 8), 256, 0, s>>>(w.ones, tb * 8, 1.f);
+      CSN_LAUNCH_CHECK();
+      CSN_CUDA(cudaEventRecord(os->fork, s));
+      CSN_CUDA(cudaStreamWaitEvent(os->st, os->fork, 0));
+      CSN_TRY(lstm_cluster_bwd(gates, c_seq, d_hseq, d_hlast, w.whh_t, w.dG, T, B, H, done, tc, s));
+      const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+      const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(h_seq);
+      // products with few output tiles are split over K inside a chunk so that a chunk's GEMM still fills the free SMs
+      const int sp_ih = std::max(1, std::min(kChunkSplit, 64 / (ceil_div(4 * H, 128) * ceil_div(I, 128))));
+      const int sp_b = std::max(1, std::min(kChunkSplit, 64 / ceil_div(4 * H, 128)));
+      int n_hh = 0, n_ih = 0, n_b = 0;  // slabs written so far (a chunk's split count follows its own row count)
+      GemmEpi slab{};
+      for (int c = nc - 1; c >= 0; --c) {
+        const size_t r0 = size_t(c) * tc * B, r1 = size_t(std::min(T, (c + 1) * tc)) * B, rr0 = std::max(r0, size_t(B));
+        wait_counter_kernel<<<1, 32, 0, os->st>>>(done + c, target);
+        CSN_LAUNCH_CHECK();
+        slab.split_stride = size_t(4) * H * H;
+        CSN_TRY(gemm_tc_run(1, 0, 4 * H, H, (int)(r1 - rr0), w.dG + rr0 * 4 * H, 4 * H, hb + (rr0 - B) * H, H,
+                            w.dwp + size_t(n_hh) * slab.split_stride, H, CSN_F32, nullptr, 0, 1, &slab, os->st));
+        n_hh += 1;
+        if (dx)  // the layer below waits for this one: ahead of the remaining weight-gradient products
+          CSN_TRY(gemm_tc_run(0, 0, (int)(r1 - r0), I, 4 * H, w.dG + r0 * 4 * H, 4 * H, w.wih, I, dx + r0 * I, I, CSN_F32, nullptr, 0,
+                              1, nullptr, os->st));
+        slab.split_stride = size_t(4) * H * I;
+        CSN_TRY(gemm_tc_run(1, 0, 4 * H, I, (int)(r1 - r0), w.dG + r0 * 4 * H, 4 * H, xb + r0 * I, I,
+                            w.dwp2 + size_t(n_ih) * slab.split_stride, I, CSN_F32, nullptr, 0, sp_ih, &slab, os->st));
+        n_ih += gemm_tc_splits((int)(r1 - r0), sp_ih);
+        slab.split_stride = size_t(4) * H * 8;
+        CSN_TRY(gemm_tc_run(1, 0, 4 * H, 8, (int)(r1 - r0), w.dG + r0 * 4 * H, 4 * H, w.ones + r0 * 8, 8,
+                            w.dbp + size_t(n_b) * slab.split_stride, 8, CSN_F32, nullptr, 0, sp_b, &slab, os->st));
+        n_b += gemm_tc_splits((int)(r1 - r0), sp_b);
+      }
+      CSN_CUDA(cudaEventRecord(os->join, os->st));
+      CSN_CUDA(cudaStreamWaitEvent(s, os->join, 0));
+      unpermute_rows_kernel<<<4 * H, 128, 0, s>>>(w.dwp, dw_hh, H, H, H, accumulate, n_hh, size_t(4) * H * H);
+      CSN_LAUNCH_CHECK();
+      unpermute_rows_kernel<<<4 * H, 128, 0, s>>>(w.dwp2, dw_ih, H, I, I, accumulate, n_ih, size_t(4) * H * I);
+      CSN_LAUNCH_CHECK();
+      unpermute_rows_kernel<<<4 * H, 32, 0, s>>>(w.dbp, db_ih, H, 1, 8, accumulate, n_b, size_t(4) * H * 8);
+      CSN_LAUNCH_CHECK();
+      unpermute_rows_kernel<<<4 * H, 32, 0, s>>>(w.dbp, db_hh, H, 1, 8, accumulate, n_b, size_t(4) * H * 8);
+      CSN_LAUNCH_CHECK();
+      return CSN_OK;
+    }
+    CSN_TRY(lstm_cluster_bwd(gates, c_seq, d_hseq, d_hlast, w.whh_t, w.dG, T, B, H, nullptr, 1, s));
   } else {
     CSN_CUDA(cudaMemsetAsync(w.dc, 0, size_t(B) * H * 4, s));
   }
