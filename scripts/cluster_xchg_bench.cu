@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <algorithm>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
@@ -158,6 +159,102 @@ void run(int nclusters, int rounds) {
   CK(cudaFree(out));
 }
 
+
+// Two independent exchanges per CTA (the G = 2 recurrence: two trial groups, each with its own warps, buffers and
+// barriers): does the second group hide in the first one's latency, and does it matter which engine pushes the bytes
+// (MODE_A / MODE_B as above: 0 = bulk copies, 1 = st.async)?
+template <int CS, int PIECE, int MODE_A, int MODE_B>
+__global__ void __launch_bounds__(320, 1) xchg2_kernel(int rounds, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int grp = threadIdx.x / 160;
+  const int tid = threadIdx.x % 160, warp = tid >> 5, lane = tid & 31;
+  uint8_t* base = smem + grp * (2 * CS * PIECE + 2 * PIECE + 64);
+  uint8_t* rbuf = base;
+  uint8_t* stage0 = base + 2 * CS * PIECE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + 2 * PIECE);
+  const uint32_t rank = cta_rank();
+  const int mode = grp ? MODE_B : MODE_A;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bars + i)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync();
+  long long t0 = clock64();
+  for (int r = 0; r < rounds; ++r) {
+    const int b = r & 1;
+    uint8_t* stage = stage0 + b * PIECE;
+    const uint32_t bar_local = s32(bars + b);
+    if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local), "r"(CS * PIECE) : "memory");
+    if (tid < 128) {
+      for (int i = tid; i < PIECE / 4; i += 128) reinterpret_cast<uint32_t*>(stage)[i] = rank * 1000 + i + r + 1;
+    }
+    if (mode == 0) {
+      if (tid < 128) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      }
+      if (warp == 0 && lane < CS) {
+        const uint32_t dst = mapa(s32(rbuf + (size_t)b * CS * PIECE + rank * PIECE), (rank + lane) % CS);
+        const uint32_t rb = mapa(bar_local, (rank + lane) % CS);
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "r"(s32(stage)), "r"(PIECE), "r"(rb) : "memory");
+      }
+    } else {
+      if (tid < 128) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        for (int c = tid; c < PIECE / 16; c += 128) {
+          const uint4 v = reinterpret_cast<const uint4*>(stage)[c];
+          const uint32_t off = s32(rbuf + (size_t)b * CS * PIECE + rank * PIECE + c * 16);
+#pragma unroll
+          for (int d = 0; d < CS; ++d) {
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                         ::"r"(mapa(off, d)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mapa(bar_local, d)) : "memory");
+          }
+        }
+      }
+    }
+    const uint32_t parity = (r >> 1) & 1;
+    for (unsigned spins = 0; !try_wait(bar_local, parity); ++spins) {
+      if (spins > 4000000u) { if (lane == 0) printf("stuck: block %d grp %d warp %d round %d\n", blockIdx.x, grp, warp, r); __trap(); }
+    }
+    // "compute": the other ~900 cycles of a recurrence step (MMAs + epilogue) during which this group sends nothing
+    if (tid < 128) { long long c0 = clock64(); while (clock64() - c0 < 900) { } }
+    asm volatile("bar.sync %0, 160;" ::"r"(3 + grp) : "memory");
+  }
+  long long t1 = clock64();
+  __syncthreads();
+  cluster_sync();
+  if (tid == 0) out[blockIdx.x * 4 + grp * 2] = t1 - t0;
+}
+
+template <int CS, int PIECE, int MODE_A, int MODE_B>
+void run2(int nclusters, int rounds) {
+  auto kern = xchg2_kernel<CS, PIECE, MODE_A, MODE_B>;
+  const size_t smem = 2 * (2 * CS * PIECE + 2 * PIECE + 64);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 120 * 1024)));
+  if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * CS);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = std::max<size_t>(smem, 120 * 1024);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  long long* out;
+  CK(cudaMalloc(&out, sizeof(long long) * 4 * nclusters * CS));
+  CK(cudaMemset(out, 0, sizeof(long long) * 4 * nclusters * CS));
+  for (int rep = 0; rep < 2; ++rep) { CK(cudaLaunchKernelEx(&cfg, kern, rounds, out)); CK(cudaDeviceSynchronize()); }
+  std::vector<long long> h(4 * nclusters * CS);
+  CK(cudaMemcpy(h.data(), out, h.size() * 8, cudaMemcpyDeviceToHost));
+  long long mn = 1ll << 60, mx = 0;
+  for (int i = 0; i < nclusters * CS; ++i) for (int g = 0; g < 2; ++g) { mn = std::min(mn, h[4 * i + 2 * g]); mx = std::max(mx, h[4 * i + 2 * g]); }
+  printf("TWO GROUPS CS=%2d piece=%5d modes=(%d,%d) clusters=%d : %.0f .. %.0f cycles/round (each round = exchange + 900 cycles of compute)\n", CS, PIECE,
+         MODE_A, MODE_B, nclusters, double(mn) / rounds, double(mx) / rounds);
+  CK(cudaFree(out));
+}
+
 int main(int argc, char** argv) {
   setvbuf(stdout, nullptr, _IONBF, 0);
   const int R = 4000;
@@ -173,6 +270,8 @@ int main(int argc, char** argv) {
   CASE(run<8, 1024, 0>(16, R)) CASE(run<8, 1024, 1>(16, R))
   CASE(run<16, 1024, 0>(9, R))
   CASE(run<16, 4096, 0>(8, 500)) CASE(run<16, 4096, 0>(7, 500)) CASE(run<16, 4096, 0>(6, 500)) CASE(run<8, 8192, 0>(16, 500))
+  CASE(run2<16, 1024, 0, 0>(4, R)) CASE(run2<16, 1024, 1, 1>(4, R)) CASE(run2<16, 1024, 0, 1>(4, R))
+  CASE(run<16, 1024, 0>(4, R)) CASE(run<16, 1024, 1>(4, R))
   printf("cases: %d\n", k);
   return 0;
 }

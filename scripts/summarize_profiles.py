@@ -90,6 +90,53 @@ if os.path.isfile(loss_rep):
             if w in lh:
                 f.write(f"| {w} | {r[lh.index(w)]} | {lu[lh.index(w)]} |\n")
         f.write("\n")
+
+# ---- cfg4 (H = 512 cluster recurrence): its own launch list and full capture (scripts/gpu_ncu_cfg4.sh) ----
+c4_csv = os.path.join(root, "gpurun_out", f"launches_cfg4_{tag}.csv")
+if os.path.isfile(c4_csv):
+    lines4 = [l for l in open(c4_csv, errors="ignore") if l.startswith('"')]
+    agg4, tot4 = collections.OrderedDict(), 0.0
+    for row in csv.DictReader(lines4):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = row["Kernel Name"].split("(")[0][:90]
+        val = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        val = val / 1000 if u == "ns" else (val * 1000 if u == "ms" else val)
+        a = agg4.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += val
+        tot4 += val
+    with open(os.path.join(out_dir, f"launches_cfg4_{tag}.md"), "w") as f:
+        f.write(f"# ncu launch list, cfg4 step ({tag}): `CSN_LSTM_NO_OVERLAP=1 NSTEPS=1 python scripts/bench_cfg4.py` (3 warm-up + 1 timed step, first 400 launches)\n\n")
+        f.write("L2 / H512 / 128 trials.  ncu serialises kernels, so the GEMMs that normally run BESIDE the cluster recurrence (and feed / follow it\n"
+                "through flags) are put back in sequence for the capture: the shares below are the sequential ones.  Cold-cache: compare SHARES.\n\n")
+        f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
+        for k, (n, t) in sorted(agg4.items(), key=lambda kv: -kv[1][1])[:16]:
+            f.write(f"| `{k}` | {n} | {t:.1f} | {t / n:.1f} | {100 * t / tot4:.1f}% |\n")
+        f.write(f"\ntotal {tot4:.0f} us over {sum(n for n, _ in agg4.values())} launches\n")
+c4_rep = os.path.join(root, "gpurun_out", f"prof_cfg4_{tag}.ncu-rep")
+if os.path.isfile(c4_rep):
+    craw = subprocess.run(["ncu", "-i", c4_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    crows = list(csv.reader(craw.splitlines()))
+    ch, cu = crows[0], crows[1]
+    cseen = collections.OrderedDict()
+    for r in crows[2:]:
+        cseen.setdefault(r[ch.index("Kernel Name")].split("(")[0][:80], r)
+    with open(os.path.join(out_dir, f"ncu_full_{tag}.md"), "a") as f:
+        for name, r in cseen.items():
+            f.write(f"## `{name}` (cfg4: T = 440, 128 trials, H = 512, two trial groups per 16-CTA cluster; `scripts/gpu_ncu_cfg4.sh`)\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for w in want[1:] + ["launch__cluster_max_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]:
+                if w in ch:
+                    f.write(f"| {w} | {r[ch.index(w)]} | {cu[ch.index(w)]} |\n")
+            f.write("\n")
+            key = name.replace("void ", "").replace("csn::", "")
+            traffic[key + " [cfg4, scripts/bench_cfg4.py]"] = {
+                "dram_read_bytes": _to_bytes(r[ch.index("dram__bytes_read.sum")], cu[ch.index("dram__bytes_read.sum")]),
+                "dram_write_bytes": _to_bytes(r[ch.index("dram__bytes_write.sum")], cu[ch.index("dram__bytes_write.sum")]),
+                "duration_us_under_ncu": float(r[ch.index("gpu__time_duration.sum")].replace(",", "")) * ({"ns": 1e-3, "us": 1, "ms": 1e3}.get(cu[ch.index("gpu__time_duration.sum")], 1)),
+                "tensor_pipe_active_pct": _opt(r, ch, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")}
+
 json.dump({"tag": tag, "source": f"ncu --set full, profiles/ncu_full_{tag}.md", "kernels": traffic},
           open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out_dir, f"launches_{tag}.md")).read()[:2500])
