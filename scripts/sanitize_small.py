@@ -26,6 +26,11 @@ for dtype in (torch.bfloat16, torch.float32):
 # large-hidden path (per-step GEMMs, PDL, split slabs)
 model = csn.Model(16, 136, 1, 24, include_top=False, compute_dtype=torch.bfloat16).cuda()
 out = model(torch.randn(5, 9, 16, device="cuda")); out.sum().backward(); print("H=136 ok", float(out.abs().mean()))
+# cluster recurrence (H = 256 / 512): one and two trial groups per cluster, ragged last group, with / without d_hseq
+for (T, B, I, H) in ((9, 5, 16, 256), (7, 130, 32, 512), (40, 20, 64, 512)):
+    model = csn.Model(I, H, 2, 24, include_top=False, compute_dtype=torch.bfloat16).cuda()
+    out = model(torch.randn(B, T, I, device="cuda")); out.sum().backward()
+    print("cluster H=%d B=%d ok" % (H, B), float(out.abs().mean()))
 # multi-crop loss (staged cluster kernel) at a small K, canonical and reference modes
 for K in (2048, 4096):
     s = torch.randn(4, 3, K, device="cuda"); t = torch.randn(2, 3, K, device="cuda")
