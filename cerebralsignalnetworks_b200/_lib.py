@@ -60,6 +60,8 @@ SIGNATURES = {
     "csn_gather_trials": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i, _vp],
     "csn_topk_workspace_bytes": [_i, _i, _i, C.POINTER(_sz)],
     "csn_topk_search": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "csn_topk_tc_workspace_bytes": [_i, _i, _i, _i, C.POINTER(_sz)],
+    "csn_topk_search_tc": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp],
     "csn_ema_update": [_vp, _vp, _sz, _f, _vp],
     "csn_fused_optim_workspace_bytes": [_i, C.c_longlong, C.POINTER(_sz)],
     "csn_fused_optim_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _i, _f, _f, _f, _i, _f, _f,

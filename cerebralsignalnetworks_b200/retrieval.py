@@ -29,11 +29,14 @@ def topk_search(gallery: torch.Tensor, query: torch.Tensor, k: int, metric: int 
     if d != d2:
         raise _lib.CsnError("topk_search: dimension mismatch (gallery %d, query %d)" % (d, d2))
     nbytes = C.c_size_t(0)
-    call("csn_topk_workspace_bytes", nq, nb, int(k), C.byref(nbytes))
+    call("csn_topk_tc_workspace_bytes", nq, nb, d, int(k), C.byref(nbytes))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=query.device)
     dist = torch.empty((nq, k), dtype=torch.float32, device=query.device)
     idx = torch.empty((nq, k), dtype=torch.int64, device=query.device)
-    call("csn_topk_search", _p(gallery), _p(query), nb, nq, d, int(k), int(metric), _p(dist), _p(idx), _p(ws), _stream())
+    # large galleries: tcgen05 distance GEMM pre-selects 32 candidates per query, exact fp32 re-scoring decides; other
+    # shapes run the fused fp32 scan (the entry point routes by shape, same contract either way)
+    call("csn_topk_search_tc", _p(gallery), _p(query), nb, nq, d, int(k), int(metric), _p(dist), _p(idx), _p(ws),
+         nbytes.value, _stream())
     return dist, idx
 
 

@@ -263,6 +263,14 @@ int csn_sosfilt_gather_f32(const float* src, const long long* idx, int n_trials,
 int csn_topk_workspace_bytes(int nq, int nb, int k, size_t* bytes);
 int csn_topk_search(const float* gallery, const float* query, int nb, int nq, int d, int k, int metric,
                     float* out_dist, long long* out_idx, void* workspace, void* stream);
+/* Same contract, tensor-core pre-selection for galleries of thousands of rows: a tcgen05 GEMM over bf16
+ * hi/lo splits of the rows scores every (query, gallery row) pair, each query's 32 best by that score are re-scored in
+ * exact fp32 (direct sum of squared differences / dot product) and the k best of those are returned -- the ranking follows
+ * exact fp32 distances, the GEMM only decides which 32 rows get the exact look.  Shapes it does not serve (nb < 2048,
+ * d % 8 != 0, k > 16) run csn_topk_search.  workspace_bytes >= csn_topk_tc_workspace_bytes(). */
+int csn_topk_tc_workspace_bytes(int nq, int nb, int d, int k, size_t* bytes);
+int csn_topk_search_tc(const float* gallery, const float* query, int nb, int nq, int d, int k, int metric,
+                       float* out_dist, long long* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* EMA teacher update over flat buffers: dst = momentum * dst + (1 - momentum) * src  (LstmDistillation.py:616-619) */
 int csn_ema_update(float* dst, const float* src, size_t n, float momentum, void* stream);

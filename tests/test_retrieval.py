@@ -148,6 +148,45 @@ def test_topk_ties_and_self_retrieval():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+@pytest.mark.parametrize("nq,nb,d,k", [(40, 40000, 64, 10), (9, 2048, 8, 16), (300, 5000, 136, 1)])
+def test_tensor_core_preselection_matches_oracle(metric, nq, nb, d, k):
+    """Galleries the tcgen05 pre-selection path serves (csn_topk_search_tc): two gallery chunks, the smallest shapes it
+    takes, a query count that is not a multiple of the GEMM tile."""
+    g, q = _data(nq, nb, d, 77 + nq)
+    if metric == "ip":
+        g /= np.maximum(np.linalg.norm(g, axis=1, keepdims=True), 1e-12)
+        q /= np.maximum(np.linalg.norm(q, axis=1, keepdims=True), 1e-12)
+    _check_against_oracle(g, q, k, metric)
+
+
+@pytest.mark.gpu
+def test_tensor_core_path_duplicates_and_agreement_with_the_scan_kernel():
+    """Exact duplicates in a large gallery: the exact re-scoring reports distance 0 and orders ties by index; and the
+    two product kernels (GEMM pre-selection + re-scoring, fused fp32 scan) return the same neighbours."""
+    import ctypes as C
+    import cerebralsignalnetworks_b200 as csn
+    from cerebralsignalnetworks_b200 import _lib
+    g, _ = _data(1, 6000, 32, 9)
+    g[3000:] = g[:3000]
+    index = csn.IndexFlatL2(32)
+    index.add(g)
+    D, I = index.search(g[:64], 2)
+    assert np.array_equal(I[:, 0], np.arange(64)) and np.array_equal(I[:, 1], np.arange(64) + 3000)
+    assert (D == 0).all()
+    gal, qry = torch.from_numpy(g).cuda(), torch.from_numpy(_data(50, 1, 32, 4)[1]).cuda()
+    Dt, It = csn.retrieval.topk_search(gal, qry, 5)
+    nbytes = C.c_size_t(0)
+    _lib.call("csn_topk_workspace_bytes", 50, 6000, 5, C.byref(nbytes))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    Ds, Is = torch.empty(50, 5, device="cuda"), torch.empty(50, 5, dtype=torch.int64, device="cuda")
+    _lib.call("csn_topk_search", gal.data_ptr(), qry.data_ptr(), 6000, 50, 32, 5, 0, Ds.data_ptr(), Is.data_ptr(), ws.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert torch.equal(It, Is)
+    np.testing.assert_allclose(Dt.cpu().numpy(), Ds.cpu().numpy(), rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_topk_rejects_bad_arguments():
     import cerebralsignalnetworks_b200 as csn
     index = csn.IndexFlatL2(8)
