@@ -35,13 +35,12 @@ constexpr int kNT = 16;                          // trials per cluster = MMA N
 constexpr int kUnits = 32;                       // hidden units per CTA: 128 gate rows = one M tile
 constexpr uint32_t kPiece = kUnits * kNT * 2;    // bytes of one CTA's h slice (bf16), contiguous in the operand layout
 constexpr int kEpiWarps = 8;                     // warp w: TMEM lane quadrant w % 4, trial half w / 4
-constexpr int kIssuer0 = 8, kSender = 10, kProducer = 11;
-constexpr int kThreads = 12 * 32;
+constexpr int kThreads = 12 * 32;                // per trial group: 8 epilogue + 2 issuer + sender + producer warps
 constexpr int kHandoffThreads = (kEpiWarps + 3) * 32;  // epilogue (arrive) + two issuer warps + sender warp (sync)
 constexpr int kXStages = 4;                      // TMA ring of the hoisted input projection (one stage = one timestep)
 constexpr uint32_t kXStageBytes = kNT * 128 * 4; // 16 trials x this CTA's 128 gate columns, fp32
 constexpr uint32_t kLbo = 256, kSbo = 128;       // h operand, canonical K-major: k-group stride 256 B (16 trials x 16 B)
-constexpr uint32_t kWcol0 = 256;                 // tensor memory: [0, 64) four accumulators x 16, [256, 256 + H/2) weights
+constexpr uint32_t kWcol0 = 256;                 // tensor memory: [64 gi, 64 gi + 64) four accumulators x 16 of trial group gi, [256, 256 + H/2) weights
 constexpr uint32_t kTmemCols = 512;
 constexpr int kGroups = 4;                       // arrival groups of the all-gather (CS / 4 source CTAs each)
 
@@ -50,10 +49,6 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-template <int NTHREADS>
-__device__ __forceinline__ void handoff_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(NTHREADS) : "memory"); }
-template <int NTHREADS>
-__device__ __forceinline__ void handoff_wait() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 __device__ __forceinline__ void handoff_arrive_id(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void handoff_wait_id(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
