@@ -6,7 +6,8 @@
     -> backward
     -> DDP gradient mean + centre all-reduce (:445, :154-156)         : two-shot exchange over NVLink peer memory; the
                                                                           DINO head's gradients (21.8 M of 22.3 M at
-                                                                          K = 65536) leave while BPTT still runs
+                                                                          K = 65536) and the centre statistics leave
+                                                                          while BPTT still runs
     -> clip_gradients(3.0) + cancel_gradients_last_layer + AdamW(param groups, cosine lr / wd) + EMA teacher (:607-619)
                                                                         : ONE fused sweep (csn_fused_optim_step)
 
@@ -129,6 +130,10 @@ class MultiCropDistillStep:
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
                 self.xchg.all_reduce_(0, self.n_head, flag_set=0)
+                # the per-row centre statistics (B x K floats: 16.8 MB at cfg3) were final when the loss kernel ended:
+                # they travel now, under BPTT, instead of with the backbone gradients after it
+                if self.n_center:
+                    self.xchg.all_reduce_(self.opt.n_flat, self.n_center, flag_set=0)
                 self._head_done.record(self._side)
 
     # ------------------------------------------------------------------------------------------------ pieces
@@ -195,9 +200,9 @@ class MultiCropDistillStep:
         torch.autograd.backward(s_out, grad_tensors=d_student.view(s_out.shape).to(s_out.dtype))
         if self.concurrent:
             ops.set_lstm_cta_budget(0)
-        # ---- exchange: the head went out from the hook; backbone gradients + centre statistics now ----
+        # ---- exchange: the head and the centre statistics went out from the hook; the backbone gradients (2 MB) now ----
         if self.world > 1:
-            self.xchg.all_reduce_(self.n_head, self.opt.n_flat - self.n_head + self.n_center, flag_set=1)
+            self.xchg.all_reduce_(self.n_head, self.opt.n_flat - self.n_head, flag_set=1)
             torch.cuda.current_stream().wait_event(self._head_done)
         # ---- clip + AdamW + EMA teacher, one sweep (lr / wd / momentum are already on the device) ----
         opt.fused_step(clip=self.clip_grad, grad_scale=1.0 / self.world, ema=self.ema, upload=False)
