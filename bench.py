@@ -82,6 +82,29 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
 
 
+def bind_to_gpu_numa_node(torch, device_index):
+    """Multi-GPU runs: pin this rank's host thread to the CPUs NVML reports as local to its GPU BEFORE any pinned host
+    buffer is allocated, so that the buffers the end-to-end leg copies from live on the GPU's own NUMA node (Linux
+    allocates on the node of the touching thread).  With all ranks' pinned memory on one node the eight H2D streams of an
+    8-GPU box share that node's memory controllers.  Returns the number of CPUs bound to (0: left alone)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # no NVML / no affinity information: keep the default placement
+        return 0
+
+
 class ClockSampler:
     """SM clock + throttle reasons DURING the timed regions.  NVML is polled from a thread every few ms (the timed
     region of a default run is short; `nvidia-smi -lms` needs ~0.5 s to produce its first row); nvidia-smi is the
@@ -429,6 +452,7 @@ def main():
         raise SystemExit("for --gpus > 1 launch through torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(torch, local) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if args.warmup < 3:
@@ -660,7 +684,9 @@ def main():
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2_policy": f"rotating {NB} resident input batches ({NB * B * C * T * 4 / 1e6:.0f} MB) > 126 MB L2"},
         "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": B * C * T * 4 + B * K * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+                "h2d_bytes_per_step": B * C * T * 4 + B * K * 4, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                "host_numa": ("rank bound to the %d CPUs local to its GPU before the pinned buffers were allocated" % numa_cpus)
+                             if numa_cpus else "default placement"},
         "e2e_resident_dataset": None if ds_ms is None else {
             "value": world * B * args.steps / (ds_ms * 1e-3), "unit": UNIT, "ms_per_step": ds_ms / args.steps,
             "h2d_bytes_per_step": B * 8 + B * K * 4, "d2h_bytes_per_step": 4, "dataset_trials_per_gpu": n_ds,
