@@ -128,7 +128,8 @@ template <int CS, int G, bool PROF>
 __global__ void __launch_bounds__(kThreads * G, 1)
 lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_t* __restrict__ w_rows,
                         __nv_bfloat16* __restrict__ h_seq, __nv_bfloat16* __restrict__ gates_out, float* __restrict__ c_out,
-                        int T, int B, const unsigned* __restrict__ xp_flags, int xp_chunk, long long* __restrict__ prof) {
+                        int T, int B, const unsigned* __restrict__ xp_flags, int xp_chunk, uint8_t* __restrict__ xchg,
+                        long long* __restrict__ prof) {
   constexpr int H = CS * kUnits;
   using L = FwdSmem<CS>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -224,7 +225,21 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tm_xp, const uint32_
       handoff_wait_id(hbar, kHandoffThreads);  // the slice is staged (and fenced towards the async proxy by its writers)
       const int b = (t + 1) & 1;
       if (lane < kGroups) mbar_arrive_expect_tx(grp_bar + b * kGroups + lane, (CS / kGroups) * kPiece);
-      if (lane < CS) {
+      if (xchg) {
+        // through L2: the slice goes to a global scratch (this warp: 64 chunks of 16 bytes), then ONE multicast bulk copy
+        // delivers it to the operand buffer of all CS CTAs and signals each CTA's group barrier.  One copy per CTA and step
+        // instead of CS: with two trial groups the copy engine's per-copy cost was the limit (scripts/cluster_xchg_bench.cu:
+        // 3300 -> 1950 cycles per round with two groups).
+        uint8_t* g = xchg + ((((size_t)(blockIdx.x / CS) * G + gi) * 2 + b) * CS + rank) * kPiece;
+#pragma unroll
+        for (int c = lane; c < (int)(kPiece / 16); c += 32)
+          reinterpret_cast<uint4*>(g)[c] = *reinterpret_cast<const uint4*>(stage + b * kPiece + c * 16);
+        asm volatile("fence.proxy.async.global;" ::: "memory");  // generic stores -> the copy engine's read
+        __syncwarp();
+        if (lane == 0)
+          bulk_g2s_multicast(hbuf + b * L::h_bytes + rank * kPiece, g, kPiece, grp_bar + b * kGroups + rank / (CS / kGroups),
+                             (uint16_t)((1u << CS) - 1));
+      } else if (lane < CS) {
         const uint32_t d = (rank + uint32_t(lane)) % CS;  // staggered: no destination is everybody's last
         bulk_s2c(mapa(smem_u32(hbuf + b * L::h_bytes + rank * kPiece), d), smem_u32(stage + b * kPiece), kPiece,
                  mapa(smem_u32(grp_bar + b * kGroups + rank / (CS / kGroups)), d));
@@ -681,31 +696,39 @@ bool lstm_cluster_overlap_ok(int B, int H) {
 
 template <int CS, int G>
 static int launch_fwd_cluster(const CUtensorMap& tm_xp, const uint32_t* w_rows, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq,
-                              int T, int B, const unsigned* xp_flags, int xp_chunk, cudaStream_t s) {
+                              int T, int B, const unsigned* xp_flags, int xp_chunk, uint8_t* xchg, cudaStream_t s) {
   static bool attr_set[2] = {false, false};
   const int clusters = ceil_div(B, clus::kNT * G);
   const size_t smem = size_t(G) * clus::FwdSmem<CS>::total;
   if (g_clus_prof)
     return launch_cluster(clus::lstm_fwd_cluster_kernel<CS, G, true>, &attr_set[1], CS, clusters, clus::kThreads * G, smem, s, tm_xp, w_rows,
-                          h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, g_clus_prof);
+                          h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, xchg, g_clus_prof);
   return launch_cluster(clus::lstm_fwd_cluster_kernel<CS, G, false>, &attr_set[0], CS, clusters, clus::kThreads * G, smem, s, tm_xp, w_rows,
-                        h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, g_clus_prof);
+                        h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, xchg, g_clus_prof);
 }
 
 // Forward recurrence of one layer.  xp: [T*B, 4H] fp32 (input projection + biases, gate-interleaved columns);
 // whh_perm: [4H, H] bf16, rows gate-interleaved.  xp_flags (may be NULL): one word per chunk of xp_chunk timesteps, non-zero
 // once that chunk of xp has been written by the projection GEMM running beside this launch.
+// xchg (may be NULL: DSMEM pushes instead): lstm_cluster_xchg_bytes(B, H) of global scratch for the per-step exchange.
+size_t lstm_cluster_xchg_bytes(int B, int H) {
+  // per 16-trial group: two buffers x CS slices (forward) / 2 x CS x CS partial blocks (backward)
+  const size_t cs = size_t(H / clus::kUnits);
+  return size_t(ceil_div(B, clus::kNT) + 1) * 2 * cs * cs * clus::kPiece;
+}
 int lstm_cluster_fwd(const float* xp, const __nv_bfloat16* whh_perm, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq, int T,
-                     int B, int H, const unsigned* xp_flags, int xp_chunk, cudaStream_t s) {
+                     int B, int H, const unsigned* xp_flags, int xp_chunk, void* xchg_v, cudaStream_t s) {
+  static const bool no_mc = [] { const char* e = getenv("CSN_CLUSTER_NO_MULTICAST"); return e && e[0] == '1'; }();
+  uint8_t* xchg = no_mc ? nullptr : reinterpret_cast<uint8_t*>(xchg_v);
   CUtensorMap tm{};
   CSN_TRY(make_tmap_2d_plain(&tm, xp, 4, (uint64_t)(4 * H), (uint64_t)T * B, (uint64_t)(4 * H), 128, clus::kNT));
   const uint32_t* w_rows = reinterpret_cast<const uint32_t*>(whh_perm);
   if (H == 512)
-    return pick_groups(B, 16) == 2 ? launch_fwd_cluster<16, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, s)
-                                   : launch_fwd_cluster<16, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, s);
+    return pick_groups(B, 16) == 2 ? launch_fwd_cluster<16, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, xchg, s)
+                                   : launch_fwd_cluster<16, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, xchg, s);
   if (H == 256)
-    return pick_groups(B, 8) == 2 ? launch_fwd_cluster<8, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, s)
-                                  : launch_fwd_cluster<8, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, s);
+    return pick_groups(B, 8) == 2 ? launch_fwd_cluster<8, 2>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, xchg, s)
+                                  : launch_fwd_cluster<8, 1>(tm, w_rows, h_seq, gates, c_seq, T, B, xp_flags, xp_chunk, xchg, s);
   set_error("lstm_cluster_fwd: unsupported hidden size %d", H);
   return CSN_EUNSUPPORTED;
 }

@@ -21,7 +21,8 @@ namespace csn {
 bool lstm_cluster_supported(int H);
 bool lstm_cluster_overlap_ok(int B, int H);
 int lstm_cluster_fwd(const float* xp, const __nv_bfloat16* whh_perm, __nv_bfloat16* h_seq, __nv_bfloat16* gates, float* c_seq, int T,
-                     int B, int H, const unsigned* xp_flags, int xp_chunk, cudaStream_t s);
+                     int B, int H, const unsigned* xp_flags, int xp_chunk, void* xchg, cudaStream_t s);
+size_t lstm_cluster_xchg_bytes(int B, int H);
 int lstm_cluster_bwd(const __nv_bfloat16* gates, const float* c_seq, const float* d_hseq, const float* d_hlast,
                      const __nv_bfloat16* whh_t, __nv_bfloat16* dG, int T, int B, int H, unsigned* done, int done_chunk,
                      cudaStream_t s);
@@ -180,6 +181,7 @@ struct LargeWs {
   __nv_bfloat16* ones;       // [TB, 8]
   float* dbp;                // [4H, 8]
   unsigned* flags;           // [2 * kChunks] chunk flags of the overlapped GEMMs
+  uint8_t* xchg;             // cluster recurrence: global scratch of the per-step exchange (lstm_cluster_xchg_bytes)
   size_t total;
 };
 
@@ -212,6 +214,7 @@ static LargeWs carve_ws(void* base, int T, int B, int I, int H) {
   w.ones = reinterpret_cast<__nv_bfloat16*>(take(tb * 8 * 2));
   w.dbp = reinterpret_cast<float*>(take(std::max(req(4 * H, 8), size_t(kChunks) * kChunkSplit) * 4 * H * 8 * 4));
   w.flags = reinterpret_cast<unsigned*>(take(2 * kChunks * sizeof(unsigned)));
+  w.xchg = reinterpret_cast<uint8_t*>(take(lstm_cluster_supported(H) ? lstm_cluster_xchg_bytes(B, H) : 0));
   w.total = off;
   return w;
 }
@@ -268,12 +271,12 @@ int lstm_layer_fwd_large(const void* x, const float* w_ih, const float* w_hh, co
       }
       CSN_CUDA(cudaEventRecord(os->join, os->st));
       CSN_CUDA(cudaStreamWaitEvent(s, os->first, 0));
-      CSN_TRY(lstm_cluster_fwd(w.xp, w.whh, hs, gates, c_seq, T, B, H, w.flags, tc, s));
+      CSN_TRY(lstm_cluster_fwd(w.xp, w.whh, hs, gates, c_seq, T, B, H, w.flags, tc, w.xchg, s));
       CSN_CUDA(cudaStreamWaitEvent(s, os->join, 0));
       return CSN_OK;
     }
     CSN_TRY(gemm_tc_run(0, 1, (int)tb, 4 * H, I, x, I, w.wih, I, w.xp, 4 * H, CSN_F32, w.bias, 0, 1, nullptr, s));
-    return lstm_cluster_fwd(w.xp, w.whh, hs, gates, c_seq, T, B, H, nullptr, 1, s);
+    return lstm_cluster_fwd(w.xp, w.whh, hs, gates, c_seq, T, B, H, nullptr, 1, w.xchg, s);
   }
   // hoisted input projection in gate-interleaved column order
   CSN_TRY(gemm_tc_run(0, 1, (int)tb, 4 * H, I, x, I, w.wih, I, w.xp, 4 * H, CSN_F32, w.bias, 0, 1, nullptr, s));

@@ -190,6 +190,14 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta,
                : "memory");
 }
 
+// ONE copy global -> the same shared-memory offset of every CTA in cta_mask; each destination's mbarrier (same offset as
+// `bar` in its own shared memory) receives complete_tx(bytes)
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

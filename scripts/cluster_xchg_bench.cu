@@ -163,8 +163,11 @@ void run(int nclusters, int rounds) {
 // Two independent exchanges per CTA (the G = 2 recurrence: two trial groups, each with its own warps, buffers and
 // barriers): does the second group hide in the first one's latency, and does it matter which engine pushes the bytes
 // (MODE_A / MODE_B as above: 0 = bulk copies, 1 = st.async)?
+// mode 3: the piece goes to a global scratch (L2) with ordinary stores, then ONE multicast bulk copy global -> shared::cluster
+// delivers it to every CTA of the cluster (same shared-memory offset and barrier offset in each): one copy instruction per CTA
+// and round instead of CS.
 template <int CS, int PIECE, int MODE_A, int MODE_B>
-__global__ void __launch_bounds__(320, 1) xchg2_kernel(int rounds, long long* out) {
+__global__ void __launch_bounds__(320, 1) xchg2_kernel(int rounds, long long* out, uint8_t* scratch) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int grp = threadIdx.x / 160;
   const int tid = threadIdx.x % 160, warp = tid >> 5, lane = tid & 31;
@@ -189,7 +192,20 @@ __global__ void __launch_bounds__(320, 1) xchg2_kernel(int rounds, long long* ou
     if (tid < 128) {
       for (int i = tid; i < PIECE / 4; i += 128) reinterpret_cast<uint32_t*>(stage)[i] = rank * 1000 + i + r + 1;
     }
-    if (mode == 0) {
+    if (mode == 3) {
+      // scratch layout: [cluster][group][buffer][rank][PIECE]
+      uint8_t* g = scratch + ((((size_t)(blockIdx.x / CS) * 2 + grp) * 2 + b) * CS + rank) * PIECE;
+      if (tid < 128) {
+        for (int i = tid; i < PIECE / 16; i += 128) reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(stage)[i];
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      }
+      if (tid == 0) {
+        const uint32_t dst = s32(rbuf + (size_t)b * CS * PIECE + rank * PIECE);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                     ::"r"(dst), "l"(g), "r"(PIECE), "r"(bar_local), "h"((uint16_t)((1u << CS) - 1)) : "memory");
+      }
+    } else if (mode == 0) {
       if (tid < 128) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -225,7 +241,15 @@ __global__ void __launch_bounds__(320, 1) xchg2_kernel(int rounds, long long* ou
   long long t1 = clock64();
   __syncthreads();
   cluster_sync();
-  if (tid == 0) out[blockIdx.x * 4 + grp * 2] = t1 - t0;
+  if (tid == 0) {
+    out[blockIdx.x * 4 + grp * 2] = t1 - t0;
+    long long bad = 0;
+    const int b = (rounds - 1) & 1;
+    for (int q = 0; q < CS; ++q)  // first and last word of every piece (the last one is staged / copied by another thread)
+      for (int i = 0; i < PIECE / 4; i += PIECE / 4 - 1)
+        if (reinterpret_cast<const uint32_t*>(rbuf + (size_t)b * CS * PIECE + q * PIECE)[i] != (uint32_t)(q * 1000 + i + rounds)) ++bad;
+    out[blockIdx.x * 4 + grp * 2 + 1] = bad;
+  }
 }
 
 template <int CS, int PIECE, int MODE_A, int MODE_B>
@@ -245,13 +269,15 @@ void run2(int nclusters, int rounds) {
   long long* out;
   CK(cudaMalloc(&out, sizeof(long long) * 4 * nclusters * CS));
   CK(cudaMemset(out, 0, sizeof(long long) * 4 * nclusters * CS));
-  for (int rep = 0; rep < 2; ++rep) { CK(cudaLaunchKernelEx(&cfg, kern, rounds, out)); CK(cudaDeviceSynchronize()); }
+  uint8_t* scratch;
+  CK(cudaMalloc(&scratch, (size_t)nclusters * 2 * 2 * CS * PIECE));
+  for (int rep = 0; rep < 2; ++rep) { CK(cudaLaunchKernelEx(&cfg, kern, rounds, out, scratch)); CK(cudaDeviceSynchronize()); }
   std::vector<long long> h(4 * nclusters * CS);
   CK(cudaMemcpy(h.data(), out, h.size() * 8, cudaMemcpyDeviceToHost));
-  long long mn = 1ll << 60, mx = 0;
-  for (int i = 0; i < nclusters * CS; ++i) for (int g = 0; g < 2; ++g) { mn = std::min(mn, h[4 * i + 2 * g]); mx = std::max(mx, h[4 * i + 2 * g]); }
-  printf("TWO GROUPS CS=%2d piece=%5d modes=(%d,%d) clusters=%d : %.0f .. %.0f cycles/round (each round = exchange + 900 cycles of compute)\n", CS, PIECE,
-         MODE_A, MODE_B, nclusters, double(mn) / rounds, double(mx) / rounds);
+  long long mn = 1ll << 60, mx = 0, bad = 0;
+  for (int i = 0; i < nclusters * CS; ++i) for (int g = 0; g < 2; ++g) { mn = std::min(mn, h[4 * i + 2 * g]); mx = std::max(mx, h[4 * i + 2 * g]); bad += h[4 * i + 2 * g + 1]; }
+  printf("TWO GROUPS CS=%2d piece=%5d modes=(%d,%d) clusters=%d : %.0f .. %.0f cycles/round (each round = exchange + 900 cycles of compute), bad=%lld\n", CS, PIECE,
+         MODE_A, MODE_B, nclusters, double(mn) / rounds, double(mx) / rounds, bad);
   CK(cudaFree(out));
 }
 
@@ -272,6 +298,7 @@ int main(int argc, char** argv) {
   CASE(run<16, 4096, 0>(8, 500)) CASE(run<16, 4096, 0>(7, 500)) CASE(run<16, 4096, 0>(6, 500)) CASE(run<8, 8192, 0>(16, 500))
   CASE(run2<16, 1024, 0, 0>(4, R)) CASE(run2<16, 1024, 1, 1>(4, R)) CASE(run2<16, 1024, 0, 1>(4, R))
   CASE(run<16, 1024, 0>(4, R)) CASE(run<16, 1024, 1>(4, R))
+  CASE(run2<16, 1024, 3, 3>(4, R)) CASE(run2<16, 1024, 3, 0>(4, R)) CASE(run2<16, 2048, 3, 3>(4, R)) CASE(run2<16, 1024, 3, 3>(7, R))
   printf("cases: %d\n", k);
   return 0;
 }
