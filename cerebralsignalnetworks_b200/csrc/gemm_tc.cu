@@ -361,6 +361,189 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   return CSN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant for plain products with MANY output tiles and a short K (the hoisted input projection of the
+// H = 512 encoder: 7040 tiles of K = 128; the K = 65536 DINO head: 1536 tiles of K = 256).  One tile per CTA pays
+// barrier init + TMEM allocation + the drain of a 64 KB tile for two to four k-iterations of tensor work, and nothing
+// overlaps the drain (measured: 332 us for the 29.5 GFLOP / 461 MB projection).  Here a CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...: the TMA producer and the MMA issuer run ahead into the next tile through the
+// same shared-memory ring, the accumulator is DOUBLE-BUFFERED in tensor memory (2 x 128 columns), and the four epilogue
+// warps drain tile i while tile i + 1 multiplies.  Plain store / bias / fp32 or bf16 output only.
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                             const __grid_constant__ CUtensorMap tmB,
+                                                                             const GemmEpi p, int tiles_n, int n_tiles) {
+  constexpr int GBN = 128;
+  constexpr uint32_t kStageBytes = stage_bytes<GBN>();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(S) * kStageBytes);
+  uint64_t* empty = full + 4;
+  uint64_t* accfull = empty + 4;    // [2]
+  uint64_t* accempty = accfull + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_it = (p.K + GBK - 1) / GBK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accempty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * GBN);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t git = 0;  // ring position, continuous over the tiles
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * GBM, n0 = (tile % tiles_n) * GBN;
+        for (int it = 0; it < n_it; ++it, ++git) {
+          const uint32_t s = git % S;
+          if (git >= (uint32_t)S) mbar_wait(&empty[s], ((git / S) - 1) & 1);
+          uint8_t* sa = smem + size_t(s) * kStageBytes;
+          uint8_t* sb = sa + GBM * GBK * 2;
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          const int k = it * GBK;
+          if (A_MN) {
+            tma_load_2d(sa, &tmA, &full[s], m0, k);
+            tma_load_2d(sa + 8192, &tmA, &full[s], m0 + 64, k);
+          } else {
+            tma_load_2d(sa, &tmA, &full[s], k, m0);
+          }
+          if (B_MN) {
+            tma_load_2d(sb, &tmB, &full[s], n0, k);
+            tma_load_2d(sb + 8192, &tmB, &full[s], n0 + 64, k);
+          } else {
+            tma_load_2d(sb, &tmB, &full[s], k, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GBM, GBN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      uint32_t git = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t a = lt & 1;
+        if (lt >= 2) mbar_wait(&accempty[a], ((lt >> 1) - 1) & 1);  // the epilogue has drained this buffer's previous tile
+        tcgen05_fence_after();
+        for (int it = 0; it < n_it; ++it, ++git) {
+          const uint32_t s = git % S;
+          mbar_wait(&full[s], (git / S) & 1);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + size_t(s) * kStageBytes);
+          const uint32_t sb = sa + GBM * GBK * 2;
+#pragma unroll
+          for (int kk = 0; kk < GBK / 16; ++kk) {
+            uint64_t da = A_MN ? make_smem_desc(sa + kk * 2048, 8192, 1024, kLayoutSw128)
+                               : make_smem_desc(sa + kk * 32, 16, 1024, kLayoutSw128);
+            uint64_t db = B_MN ? make_smem_desc(sb + kk * 2048, 8192, 1024, kLayoutSw128)
+                               : make_smem_desc(sb + kk * 32, 16, 1024, kLayoutSw128);
+            umma_f16(tmem_base + a * GBN, da, db, idesc, (it | kk) != 0);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&accfull[a]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    float* tile_s = reinterpret_cast<float*>(smem + size_t(S) * kStageBytes + 256) + quad * (32 * kEpiStride);
+    const bool f32_out = (p.d_dtype == CSN_F32);
+    const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / tiles_n) * GBM, n0 = (tile % tiles_n) * GBN;
+      const uint32_t a = lt & 1;
+      mbar_wait(&accfull[a], (lt >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < GBN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld<32>(tmem_base + (uint32_t(quad * 32) << 16) + a * GBN + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          *reinterpret_cast<uint4*>(tile_s + lane * kEpiStride + q4 * 4) = make_uint4(r[q4 * 4], r[q4 * 4 + 1], r[q4 * 4 + 2], r[q4 * 4 + 3]);
+        __syncwarp();
+        const int col4 = (lane & 7) * 4;
+        const int gn = n0 + c0 + col4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          bv.x = gn < p.N ? p.bias[gn] : 0.f;
+          bv.y = gn + 1 < p.N ? p.bias[gn + 1] : 0.f;
+          bv.z = gn + 2 < p.N ? p.bias[gn + 2] : 0.f;
+          bv.w = gn + 3 < p.N ? p.bias[gn + 3] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3);
+          const int gm = m0 + quad * 32 + rr;
+          float4 v = *reinterpret_cast<const float4*>(tile_s + rr * kEpiStride + col4);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (gm >= p.M || gn >= p.N) continue;
+          if (f32_out) {
+            float* d = reinterpret_cast<float*>(p.D) + size_t(gm) * p.ldd + gn;
+            if (vec_ok && gn + 3 < p.N) {
+              *reinterpret_cast<float4*>(d) = v;
+            } else {
+              d[0] = v.x;
+              if (gn + 1 < p.N) d[1] = v.y;
+              if (gn + 2 < p.N) d[2] = v.z;
+              if (gn + 3 < p.N) d[3] = v.w;
+            }
+          } else {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + size_t(gm) * p.ldd + gn;
+            if (vec_ok && gn + 3 < p.N) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+              uint2 o;
+              o.x = *reinterpret_cast<uint32_t*>(&lo);
+              o.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(d) = o;
+            } else {
+              d[0] = __float2bfloat16_rn(v.x);
+              if (gn + 1 < p.N) d[1] = __float2bfloat16_rn(v.y);
+              if (gn + 2 < p.N) d[2] = __float2bfloat16_rn(v.z);
+              if (gn + 3 < p.N) d[3] = __float2bfloat16_rn(v.w);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();  // this warp's TMEM reads are ordered before the MMAs the arrive below releases
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&accempty[a]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * GBN);
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& p, int tiles_m, int tiles_n,
+                                  cudaStream_t s) {
+  const size_t smem = size_t(p.stages) * stage_bytes<128>() + 1024 + 256 + kEpiBytes;
+  auto kern = gemm_tc_persistent_kernel<A_MN, B_MN>;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int n_tiles = tiles_m * tiles_n;
+  const int grid = std::min(n_tiles, sm_count());
+  kern<<<grid, kGemmThreads, smem, s>>>(ta, tb, p, tiles_n, n_tiles);
+  CSN_LAUNCH_CHECK();
+  return CSN_OK;
+}
+
 // D[m, n] (+)= sum_z slabs[z][m, n] (+ bias[n]), z ascending: the fixed-order tail of a split-K product
 __global__ void splitk_reduce_kernel(const float* __restrict__ slabs, size_t stride, int S, float* __restrict__ D, int ldd,
                                      int M, int N, const float* __restrict__ bias, int accumulate) {
@@ -457,6 +640,19 @@ int csn::gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A,
     p.h_out = cell->h_out; p.gates_out = cell->gates_out; p.c_out = cell->c_out;
   }
   dim3 grid(ceil_div(N, gbn), ceil_div(M, GBM), split_k);
+  {
+    // many output tiles, each with little tensor work: walk them with persistent CTAs (double-buffered accumulators)
+    static const bool no_persist = [] { const char* e = getenv("CSN_GEMM_NO_PERSISTENT"); return e && e[0] == '1'; }();
+    const long long tiles = (long long)grid.x * grid.y;
+    if (!no_persist && !cell && split_k == 1 && !accumulate && gbn == 128 && k_iters <= 16 && tiles >= 2ll * sm_count() &&
+        tiles < (1ll << 30)) {
+      p.stages = 4;
+      if (transA && !transB) return launch_gemm_persistent<true, true>(ta, tb, p, (int)grid.y, (int)grid.x, s);
+      if (transA && transB) return launch_gemm_persistent<true, false>(ta, tb, p, (int)grid.y, (int)grid.x, s);
+      if (!transA && !transB) return launch_gemm_persistent<false, true>(ta, tb, p, (int)grid.y, (int)grid.x, s);
+      return launch_gemm_persistent<false, false>(ta, tb, p, (int)grid.y, (int)grid.x, s);
+    }
+  }
   CSN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "csn_gemm_bf16_tc: grid too large");
   if (transA && !transB) return launch_gemm<true, true>(ta, tb, p, grid, s);
   if (transA && transB) return launch_gemm<true, false>(ta, tb, p, grid, s);

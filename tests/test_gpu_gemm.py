@@ -80,6 +80,26 @@ def test_gemm_bf16_tc(ta, tb, M, N, K, split):
     assert err <= 2e-3 * scale + 1e-3, (err, scale)
 
 
+@pytest.mark.parametrize("ta,tb", [(False, True), (True, False), (False, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(5000, 1024, 128), (5003, 1000, 72), (130, 40960, 256), (40000, 128, 512)])
+def test_gemm_bf16_persistent_tiles(ta, tb, M, N, K):
+    """Products with hundreds of output tiles and a short contraction walk the tiles with persistent CTAs (double-buffered
+    accumulators in tensor memory): ragged edges in both directions, every operand layout, fp32 and bf16 output."""
+    ops = _ops()
+    if ((M if ta else K) % 8) or ((K if tb else N) % 8):
+        pytest.skip("leading dimension not a multiple of 8 (rejected by the ABI)")
+    a = _mk((K, M) if ta else (M, K), 16).bfloat16()
+    b = _mk((N, K) if tb else (K, N), 17).bfloat16()
+    bias = _mk((N,), 18)
+    ref = (a.float().t() if ta else a.float()) @ (b.float().t() if tb else b.float()) + bias
+    out = ops.gemm_bf16(a.cuda(), b.cuda(), ta, tb, bias=bias.cuda()).cpu()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, (err, scale)
+    ob = ops.gemm_bf16(a.cuda(), b.cuda(), ta, tb, out_dtype=torch.bfloat16).cpu().float()
+    assert (ob - (ref - bias)).abs().max().item() <= 1e-2 * scale + 1e-2
+
+
 def test_gemm_bf16_accumulate_and_bf16_out():
     ops = _ops()
     a = _mk((256, 192), 9).bfloat16().cuda()
