@@ -644,7 +644,7 @@ int csn::gemm_tc_run(int transA, int transB, int M, int N, int K, const void* A,
     // many output tiles, each with little tensor work: walk them with persistent CTAs (double-buffered accumulators)
     static const bool no_persist = [] { const char* e = getenv("CSN_GEMM_NO_PERSISTENT"); return e && e[0] == '1'; }();
     const long long tiles = (long long)grid.x * grid.y;
-    if (!no_persist && !cell && split_k == 1 && !accumulate && gbn == 128 && k_iters <= 16 && tiles >= 2ll * sm_count() &&
+    if (!no_persist && !cell && split_k == 1 && !accumulate && gbn == 128 && k_iters <= 64 && tiles >= sm_count() + sm_count() / 4 &&
         tiles < (1ll << 30)) {
       p.stages = 4;
       if (transA && !transB) return launch_gemm_persistent<true, true>(ta, tb, p, (int)grid.y, (int)grid.x, s);
