@@ -80,7 +80,15 @@ def linear_bwd(x, w, pre, dy, act=ACT_NONE, compute_dtype=torch.float32, need_dx
         x_b = ops.cast(x, torch.bfloat16)
         M = x.shape[0]
         dw = ops.gemm_bf16(dpre_b, x_b, True, False, out=dw_out, split_k=max(1, min(16, M // 256)))
-        dx = ops.gemm_bf16(dpre_b, ops.cast(w, torch.bfloat16), False, False) if need_dx else None
+        dx = None
+        if need_dx:
+            # dX = dY W contracts over the OUTPUT features: for the K = 65536 DINO head that is 1024 k-iterations on the
+            # six 128 x 128 tiles of a [384, 256] result.  Split the contraction so the product fills the machine (partial
+            # slabs, added in split order: deterministic).
+            n_out, n_in = w.shape
+            tiles = ((M + 127) // 128) * ((n_in + 127) // 128)
+            split = max(1, min(32, 148 // max(1, tiles), n_out // 512))
+            dx = ops.gemm_bf16(dpre_b, ops.cast(w, torch.bfloat16), False, False, split_k=split)
     else:
         # fp32: the bias gradient rides on the dW product (row sums of dY^T from the same shared-memory strip)
         db = None
