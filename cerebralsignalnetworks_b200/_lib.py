@@ -33,6 +33,8 @@ SIGNATURES = {
     "csn_act_bwd": [_vp, _vp, _vp, _sz, _i, _vp],
     "csn_l2norm_fwd": [_vp, _vp, _vp, _i, _i, _vp],
     "csn_l2norm_bwd": [_vp, _vp, _vp, _vp, _i, _i, _vp],
+    "csn_batchnorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp],
+    "csn_batchnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "csn_weight_norm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "csn_weight_norm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "csn_gemm_bf16_tc": [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp],

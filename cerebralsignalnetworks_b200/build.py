@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
 LIB_PATH = os.path.join(HERE, "libcsn_b200.so")
 SOURCES = ["core.cu", "sosfilt.cu", "dino_loss.cu", "optim_elementwise.cu", "optim_fused.cu", "gemm_f32.cu", "lstm_f32.cu",
-           "lstm_api.cu", "gemm_tc.cu", "lstm_tc.cu", "dbg_umma.cu", "lstm_tc_large.cu", "lstm_cluster.cu", "dp_peer.cu", "retrieval.cu", "distill_losses.cu", "dataset.cu", "head_fused.cu"]
+           "lstm_api.cu", "gemm_tc.cu", "lstm_tc.cu", "dbg_umma.cu", "lstm_tc_large.cu", "lstm_cluster.cu", "dp_peer.cu", "retrieval.cu", "distill_losses.cu", "dataset.cu", "head_fused.cu", "batchnorm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

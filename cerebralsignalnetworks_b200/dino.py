@@ -14,13 +14,33 @@ import torch.nn as nn
 
 from . import _lib, ops
 from ._lib import ACT_GELU, ACT_NONE, DINO_MULTICROP_CANONICAL, DINO_MULTICROP_REF, DINO_SINGLE
-from .functional import ActFunction, DINOLossFunction, L2NormFunction, LinearFunction, WeightNormFunction
+from .functional import (ActFunction, BatchNormFunction, DINOLossFunction, L2NormFunction, LinearFunction,
+                         WeightNormFunction)
 from .lstm import Linear
 
 
 class GELU(nn.Module):
     def forward(self, x):
         return ActFunction.apply(x, ACT_GELU)
+
+
+class BatchNorm1d(nn.Module):
+    """nn.BatchNorm1d(num_features) for [M, N] activations with the same parameters / buffers (state_dict compatible)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    def forward(self, x):
+        if self.training:
+            self.num_batches_tracked += 1
+        return BatchNormFunction.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
+                                       self.training)
 
 
 class WeightNormLinear(nn.Module):
@@ -43,15 +63,19 @@ class DINOHead(nn.Module):
     def __init__(self, in_dim, out_dim, use_bn=False, norm_last_layer=True, nlayers=3, hidden_dim=2048,
                  bottleneck_dim=256, compute_dtype=torch.float32):
         super().__init__()
-        if use_bn:
-            raise NotImplementedError("use_bn=True is not on the EEG distillation path (LstmDistillation.py:432-439 uses False)")
         nlayers = max(nlayers, 1)
         if nlayers == 1:
             self.mlp = Linear(in_dim, bottleneck_dim, compute_dtype=compute_dtype)
         else:
-            layers = [Linear(in_dim, hidden_dim, compute_dtype=compute_dtype), GELU()]
+            layers = [Linear(in_dim, hidden_dim, compute_dtype=compute_dtype)]
+            if use_bn:
+                layers.append(BatchNorm1d(hidden_dim))
+            layers.append(GELU())
             for _ in range(nlayers - 2):
-                layers += [Linear(hidden_dim, hidden_dim, compute_dtype=compute_dtype), GELU()]
+                layers.append(Linear(hidden_dim, hidden_dim, compute_dtype=compute_dtype))
+                if use_bn:
+                    layers.append(BatchNorm1d(hidden_dim))
+                layers.append(GELU())
             layers.append(Linear(hidden_dim, bottleneck_dim, compute_dtype=compute_dtype))
             self.mlp = nn.Sequential(*layers)
         for m in self.modules():  # _init_weights, LstmDistillation.py:89-93

@@ -132,6 +132,25 @@ class ActFunction(torch.autograd.Function):
         return ops.act_bwd(x, dy.contiguous(), ctx.act), None
 
 
+class BatchNormFunction(torch.autograd.Function):
+    """nn.BatchNorm1d on [M, N] -- the use_bn layers of DINOHead (LstmDistillation.py:72-80)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, training):
+        x = x.contiguous()
+        y, sm, sr = ops.batchnorm_fwd(x, gamma, beta, running_mean, running_var, eps, momentum, training)
+        ctx.save_for_backward(x, gamma, sm, sr)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, sm, sr = ctx.saved_tensors
+        dx, dg, db = ops.batchnorm_bwd(x, dy.contiguous(), gamma, sm, sr, ctx.training, need_dx=ctx.needs_input_grad[0],
+                                       need_affine=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        return dx, dg, db, None, None, None, None, None
+
+
 class L2NormFunction(torch.autograd.Function):
     """F.normalize(x, dim=-1, p=2) -- LstmDistillation.py:97."""
 

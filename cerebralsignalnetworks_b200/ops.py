@@ -177,6 +177,31 @@ def l2norm_fwd(x):
     return y, inv
 
 
+def batchnorm_fwd(x, gamma, beta, running_mean, running_var, eps, momentum, training):
+    """nn.BatchNorm1d on x [M, N] float32.  Returns (y, save_mean, save_rstd); the running statistics move in place."""
+    _chk(x, torch.float32, "x")
+    M, N = x.shape
+    y = torch.empty_like(x)
+    sm = torch.empty(N, dtype=torch.float32, device=x.device)
+    sr = torch.empty(N, dtype=torch.float32, device=x.device)
+    call("csn_batchnorm_fwd", _p(x), _p(gamma) if gamma is not None else None, _p(beta) if beta is not None else None,
+         _p(running_mean) if running_mean is not None else None, _p(running_var) if running_var is not None else None,
+         _p(y), _p(sm), _p(sr), M, N, float(eps), float(momentum), 1 if training else 0, _stream())
+    return y, sm, sr
+
+
+def batchnorm_bwd(x, dy, gamma, save_mean, save_rstd, training, need_dx=True, need_affine=True):
+    _chk(x, torch.float32, "x"); _chk(dy, torch.float32, "dy")
+    M, N = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dg = torch.empty(N, dtype=torch.float32, device=x.device) if need_affine else None
+    db = torch.empty(N, dtype=torch.float32, device=x.device) if need_affine else None
+    call("csn_batchnorm_bwd", _p(x), _p(dy), _p(gamma) if gamma is not None else None, _p(save_mean), _p(save_rstd),
+         _p(dx) if dx is not None else None, _p(dg) if dg is not None else None, _p(db) if db is not None else None, M, N,
+         1 if training else 0, _stream())
+    return dx, dg, db
+
+
 def l2norm_bwd(y, inv, dy):
     M, N = y.shape
     dx = torch.empty_like(y)

@@ -80,6 +80,17 @@ int csn_scale_f32(float* x, size_t n, const float* scale_dev, float scale_host, 
 /* row-wise L2 normalise (F.normalize(p=2, eps=1e-12), LstmDistillation.py:97): y = x / max(||x||, eps); inv_norm[M] out */
 int csn_l2norm_fwd(const float* x, float* y, float* inv_norm, int M, int N, void* stream);
 int csn_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, float* dx, int M, int N, void* stream);
+
+/* nn.BatchNorm1d(N) on x [M, N] (the optional use_bn layers of DINOHead, LstmDistillation.py:72-80).  training != 0: batch
+ * statistics over the M rows (biased variance for the normalisation), running_mean / running_var (may be NULL) moved with
+ * `momentum` (unbiased variance), save_mean / save_rstd [N] kept for the backward pass; training == 0: the running
+ * statistics normalise.  gamma / beta may be NULL (affine=False).  Backward: dx (may be NULL), dgamma, dbeta (may be NULL);
+ * fixed-order column reductions. */
+int csn_batchnorm_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float* y, float* save_mean, float* save_rstd, int M, int N, float eps, float momentum, int training,
+                      void* stream);
+int csn_batchnorm_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_rstd,
+                      float* dx, float* dgamma, float* dbeta, int M, int N, int training, void* stream);
 /* weight-norm rows (nn.utils.weight_norm dim=0, LstmDistillation.py:86): w[n,:] = g[n] * v[n,:] / ||v[n,:]||; inv_norm[N] out */
 int csn_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int N, int K, void* stream);
 /* dv[n,:] = g/||v|| * (dw[n,:] - (dw[n,:].v[n,:]) v[n,:]/||v||^2); dg[n] = dw[n,:].v[n,:]/||v|| (dg may be NULL) */

@@ -111,6 +111,67 @@ def test_dino_head_golden(golden):
             np.testing.assert_allclose(p.grad.cpu().numpy(), g["grad." + n], rtol=1e-3, atol=1e-5, err_msg=n)
 
 
+@pytest.mark.parametrize("M,N", [(384, 2048), (7, 33), (2, 1), (600, 100)])
+def test_batchnorm_matches_torch(M, N):
+    """csn_batchnorm_fwd / _bwd against torch.nn.BatchNorm1d (what the reference's DINOHead(use_bn=True) calls,
+    LstmDistillation.py:72-80): training statistics, running statistics, gradients, then evaluation mode."""
+    from cerebralsignalnetworks_b200.dino import BatchNorm1d
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, N, generator=g) * 2.0 + 0.5
+    dy = torch.randn(M, N, generator=g)
+    ref = torch.nn.BatchNorm1d(N).double()
+    ours = BatchNorm1d(N).cuda()
+    with torch.no_grad():
+        w, b = torch.randn(N, generator=g), torch.randn(N, generator=g)
+        ref.weight.copy_(w); ref.bias.copy_(b); ours.weight.copy_(w); ours.bias.copy_(b)
+    for _ in range(2):  # two training steps: the running statistics move twice
+        xr = x.double().requires_grad_(True)
+        yr = ref(xr); yr.backward(dy.double())
+        xo = x.cuda().requires_grad_(True)
+        ours.zero_grad(); ref_w_grad = ref.weight.grad.clone(); ref_b_grad = ref.bias.grad.clone(); ref.zero_grad()
+        yo = ours(xo); yo.backward(dy.cuda())
+        np.testing.assert_allclose(yo.detach().cpu().numpy(), yr.detach().float().numpy(), rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(xo.grad.cpu().numpy(), xr.grad.float().numpy(), rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(ours.weight.grad.cpu().numpy(), ref_w_grad.float().numpy(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(ours.bias.grad.cpu().numpy(), ref_b_grad.float().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(ours.running_mean.cpu().numpy(), ref.running_mean.float().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ours.running_var.cpu().numpy(), ref.running_var.float().numpy(), rtol=1e-5, atol=1e-6)
+    assert int(ours.num_batches_tracked) == 2
+    ref.eval(); ours.eval()
+    xe = x.cuda().requires_grad_(True)
+    ye = ours(xe); ye.backward(dy.cuda())
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr); yr.backward(dy.double())
+    np.testing.assert_allclose(ye.detach().cpu().numpy(), yr.detach().float().numpy(), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(xe.grad.cpu().numpy(), xr.grad.float().numpy(), rtol=1e-4, atol=2e-5)
+
+
+def test_dino_head_with_batchnorm_matches_a_torch_head():
+    """DINOHead(use_bn=True): the layer layout of LstmDistillation.py:65-88 with nn.BatchNorm1d after the hidden Linears,
+    against the same stack built from torch modules with the same weights (fp32 mode)."""
+    import cerebralsignalnetworks_b200 as csn
+    torch.manual_seed(5)
+    head = csn.DINOHead(24, 96, use_bn=True, nlayers=3, hidden_dim=64, bottleneck_dim=32).cuda()
+    names = [type(m).__name__ for m in head.mlp]
+    assert names == ["Linear", "BatchNorm1d", "GELU", "Linear", "BatchNorm1d", "GELU", "Linear"]
+    tl = [torch.nn.Linear(24, 64), torch.nn.BatchNorm1d(64), torch.nn.GELU(), torch.nn.Linear(64, 64), torch.nn.BatchNorm1d(64),
+          torch.nn.GELU(), torch.nn.Linear(64, 32)]
+    ref = torch.nn.Sequential(*tl).double()
+    with torch.no_grad():
+        for i in (0, 3, 6):
+            ref[i].weight.copy_(head.mlp[i].weight.cpu()); ref[i].bias.copy_(head.mlp[i].bias.cpu())
+    x = torch.randn(40, 24)
+    out = head(x.cuda())
+    z = torch.nn.functional.normalize(ref(x.double()), dim=-1, p=2)
+    v, gw = head.last_layer.weight_v.detach().cpu().double(), head.last_layer.weight_g.detach().cpu().double()
+    want = z @ (gw * v / v.norm(dim=1, keepdim=True)).t()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want.detach().float().numpy(), rtol=2e-4, atol=2e-5)
+    out.square().sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for n, p in head.named_parameters() if p.requires_grad)
+    sd = head.state_dict()
+    assert "mlp.1.running_mean" in sd and "mlp.1.num_batches_tracked" in sd
+
+
 def test_multicrop_student_step_runs_like_the_reference_loop():
     """LstmDistillation.py:577-593 shape flow: 2 global + 4 local crops through MultiCropWrapper(Model, DINOHead),
     stacked [6,B,K] vs [2,B,K], reference multi-crop loss; compared with the CPU oracle on identical weights."""
