@@ -68,7 +68,6 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 constexpr uint32_t kBarBlock = 256;  // mbarriers + shared-memory step counters between the MMA operand and the rings
 struct RecSmem {
   uint8_t* opb;       // B operand: h^T (fwd, KP/8 * 256 B) or dG^T (bwd, 4KP/8 * 256 B), canonical K-major
-  uint64_t* bar_in;   // (unused since the named-barrier hand-off; kept initialised)
   uint64_t* bar_acc;  // accumulators ready (issuer -> epilogue)
   uint64_t* bar_pf;   // [kPfStages] prefetch ring stages filled (TMA bulk copies -> epilogue)
   uint64_t* bar_xp;   // [2] fused input projection: Xp accumulator set filled (issuer -> epilogue / x-ring reuse)
@@ -85,8 +84,7 @@ __device__ __forceinline__ RecSmem carve(uint8_t* raw, size_t b_bytes) {
   uint8_t* base = raw;
   RecSmem s;
   s.opb = base;
-  s.bar_in = reinterpret_cast<uint64_t*>(s.opb + b_bytes);
-  s.bar_acc = s.bar_in + 1;
+  s.bar_acc = reinterpret_cast<uint64_t*>(s.opb + b_bytes) + 1;  // (first word of the block: spare)
   s.bar_pf = s.bar_acc + 1;
   s.bar_xp = s.bar_pf + kPfStages;
   s.bar_w = s.bar_xp + 2;
@@ -277,7 +275,6 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
   for (int i = tid; i < (int)(b_bytes / 4); i += kThreads) reinterpret_cast<uint32_t*>(sm.opb)[i] = 0u;
   if (tid == 0) {
-    mbar_init(sm.bar_in, kEpiWarps);
     mbar_init(sm.bar_acc, 1);
     for (int i = 0; i < kPfStages; ++i) mbar_init(sm.bar_pf + i, 1);
     mbar_init(sm.bar_xp, 1);
@@ -626,7 +623,6 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_const
   if (tid == 0) {
     *progress = 0;
     for (int i = 0; i < kEpiWarps; ++i) dg_stored[i] = 0u;
-    mbar_init(sm.bar_in, kEpiWarps);
     mbar_init(sm.bar_acc, 2);  // one tcgen05.commit per issuer warp
     for (int i = 0; i < kPfStages; ++i) mbar_init(sm.bar_pf + i, 1);
     fence_mbar_init();
