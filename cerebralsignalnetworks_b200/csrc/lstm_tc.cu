@@ -955,11 +955,26 @@ static bool side_enabled(const char* which) {
 // teacher pass of LstmDistillation.py:581-589) gives each a share so that they are co-resident instead of queueing.
 static int g_cta_budget = 0;
 
+// A launch that runs under a CTA budget (several recurrences side by side) may still carry its side roles when the budget
+// has room for them: CSN_LSTM_BUDGET_SIDE=0 switches that off (the side roles then need the whole machine, as before).
+static bool budget_side() {
+  static const bool on = [] { const char* e = getenv("CSN_LSTM_BUDGET_SIDE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+static int sm_budget() { return g_cta_budget > 0 ? std::min(g_cta_budget, sm_count()) : sm_count(); }
+static int servers_needed(int B) { return std::max(2, ceil_div(6 * B, 128)); }
+
 static int pick_nv(int B) {
   // smallest batch tile that still fills the machine: per-step latency falls with NV (fewer MUFU ops per SM)
   static const int forced = [] { const char* e = getenv("CSN_LSTM_NV"); return e ? atoi(e) : 0; }();
   if (forced == 2 || forced == 4 || forced == 8) return forced;
-  const int sms = g_cta_budget > 0 ? std::min(g_cta_budget, sm_count()) : sm_count();
+  const int sms = sm_budget();
+  if (g_cta_budget > 0 && budget_side() && side_enabled("CSN_LSTM_NO_SERVERS")) {
+    // under a budget: the smallest tile that leaves room for the Xp servers / dW consumers of the launch -- a served
+    // chain with four trials per CTA steps faster than an unserved one with two (0.43 against 0.53 us per step at T = 300)
+    for (int nv = 2; nv <= 8; nv *= 2)
+      if (ceil_div(B, nv) + servers_needed(B) <= sms) return nv;
+  }
   if (ceil_div(B, 2) <= sms) return 2;
   if (ceil_div(B, 4) <= sms) return 4;
   return 8;
@@ -973,17 +988,17 @@ static int pick_servers(int T, int B, int I, int H, int nv) {
   // cfg2 launch could not deliver an fp32 Xp (230 MB: >= 183 us, measured 355 us against 245 us for the fused in-CTA
   // projection).  In fp16 (115 MB, rounding 2^-11 relative: below the bf16 rounding of h and W_hh in the same sum) they
   // keep ahead of the chain: 202 us.  CSN_LSTM_NO_SERVERS=1 switches the role off.
-  if (!side_enabled("CSN_LSTM_NO_SERVERS") || g_cta_budget > 0 || !fused_projection(I) || H % 32 != 0 || H > 128) return 0;
-  const int n_rec = ceil_div(B, nv), spare = sm_count() - n_rec;
+  if (!side_enabled("CSN_LSTM_NO_SERVERS") || (g_cta_budget > 0 && !budget_side()) || !fused_projection(I) || H % 32 != 0 || H > 128) return 0;
+  const int n_rec = ceil_div(B, nv), spare = sm_budget() - n_rec;
   const int n_tiles = ceil_div(T * B, 128);
-  const int need = std::max(2, ceil_div(6 * B, 128));
+  const int need = servers_needed(B);
   if (spare < need || T < 16) return 0;
   return std::min(spare, n_tiles);
 }
 // dW consumer CTAs of a backward launch (0: none; the two dW GEMMs then follow the recurrence)
 static int pick_consumers(int T, int B, int I, int H, int nv) {
-  if (!side_enabled("CSN_LSTM_NO_CONSUMERS") || g_cta_budget > 0 || I > 128 || I % 8 != 0 || H % 8 != 0 || H > 128) return 0;
-  const int n_rec = ceil_div(B, nv), spare = sm_count() - n_rec;
+  if (!side_enabled("CSN_LSTM_NO_CONSUMERS") || (g_cta_budget > 0 && !budget_side()) || I > 128 || I % 8 != 0 || H % 8 != 0 || H > 128) return 0;
+  const int n_rec = ceil_div(B, nv), spare = sm_budget() - n_rec;
   const int mh = 4 * H > 256 ? 2 : 1;
   const int i_pad = ceil_div(I, 64) * 64, h_pad = ceil_div(H, 64) * 64;
   if (i_pad + h_pad > 256 || spare < 2 * mh || T < 16) return 0;

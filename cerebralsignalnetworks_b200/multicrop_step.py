@@ -53,7 +53,7 @@ def _split_params(student):
 class MultiCropDistillStep:
     def __init__(self, student, teacher, loss, lr_schedule, wd_schedule, momentum_schedule, clip_grad=3.0,
                  freeze_last_layer=1, betas=(0.9, 0.999), eps=1e-8, n_global=2, n_local=4, global_len=300, local_len=200,
-                 batch_size=None, concurrent=True, cta_budget=(64, 64, 64, 64), seed=None, use_cuda_graph=True):
+                 batch_size=None, concurrent=True, cta_budget=(48, 48, 52, 74), seed=None, use_cuda_graph=True):
         """student / teacher: MultiCropWrapper(Model, DINOHead) on the GPU with identical architectures (the teacher is
         overwritten with the student's weights, LstmDistillation.py:446, and frozen); loss: DINOLoss(out_dim, n_global +
         n_local, ...); the three schedules are per-ITERATION arrays as built by utils.cosine_scheduler (:483-496).
@@ -95,9 +95,11 @@ class MultiCropDistillStep:
             for p in self._head_params:
                 p.register_post_accumulate_grad_hook(self._head_grad_ready)
         self.concurrent = bool(concurrent)
-        # SM shares of the three forward chains (teacher, student global, student local) and of the backward chains: the
-        # recurrence picks the batch tile per CTA from its share, so the chains of a phase are co-resident instead of
-        # queueing for SMs (teacher 32 + global 32 + local 64 = 128 CTAs forward, global 64 + local 64 backward)
+        # SM shares of the three forward chains (teacher, student global, student local) and of each backward chain: a
+        # recurrence launch picks its batch tile AND its side roles (Xp-server / dW-consumer CTAs) from its share, so the
+        # chains of a phase are co-resident instead of queueing for SMs.  Default (48, 48, 52 forward = 148 SMs; 74 + 74
+        # backward), measured at the cfg3 shape: 2.22 ms per step against 2.30 with (64, 64, 64, 64) and 2.98 without side
+        # roles under a budget (scripts/gpu_cfg3b.sh, gpu_cfg3c.sh).
         if isinstance(cta_budget, (tuple, list)):
             self.cta_budget = tuple(int(b) for b in cta_budget)
         else:

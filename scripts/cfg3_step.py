@@ -16,7 +16,7 @@ crit = csn.DINOLoss(K, 6, 0.04, 0.04, 30, 100).cuda()
 n_it = 4096
 step = csn.MultiCropDistillStep(student, teacher, crit, cosine_scheduler(5e-4 * B / 256, 1e-6, 1, n_it), cosine_scheduler(0.04, 0.4, 1, n_it),
                                 cosine_scheduler(0.996, 1.0, 1, n_it), clip_grad=3.0, freeze_last_layer=0, batch_size=B,
-                                concurrent=os.environ.get("CONCURRENT", "1") == "1", use_cuda_graph=os.environ.get("GRAPH", "1") == "1", cta_budget=tuple(int(v) for v in os.environ.get("CTA_BUDGET", "64,64,64,64").split(",")))
+                                concurrent=os.environ.get("CONCURRENT", "1") == "1", use_cuda_graph=os.environ.get("GRAPH", "1") == "1", cta_budget=tuple(int(v) for v in os.environ.get("CTA_BUDGET", "48,48,52,74").split(",")))
 g = torch.Generator(device="cuda").manual_seed(1)
 eeg = [torch.randn(B, T, C, device="cuda", generator=g) for _ in range(3)]
 n = int(os.environ.get("NSTEPS", "10"))

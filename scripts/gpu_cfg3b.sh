@@ -1,5 +1,7 @@
 #!/bin/bash
-mkdir -p gpurun_out
-for cfg in "0 0" "1 48" "1 64" "1 40"; do set -- $cfg
-  CONCURRENT=$1 CTA_BUDGET=$2 timeout -s KILL 300 python scripts/bench_cfg3.py > gpurun_out/cfg3_$1_$2.log 2>&1; echo "conc=$1 budget=$2 exit $?"; tail -n 2 gpurun_out/cfg3_$1_$2.log | head -1
+# cfg3 with side roles under the per-chain CTA budgets: parity, then step time for several budget splits (teacher, global, local, backward)
+timeout 600 python -m pytest tests/test_gpu_multicrop_step.py tests/test_gpu_step.py tests/test_gpu_lstm.py -x -q 2>&1 | tail -2
+for b in 64,64,64,64 44,44,60,74 40,40,68,74 38,38,72,74 48,48,52,74; do
+  echo "budgets $b"; CTA_BUDGET=$b timeout 200 python scripts/cfg3_step.py 2>&1 | tail -1
 done
+echo "side roles off under budgets"; CSN_LSTM_BUDGET_SIDE=0 timeout 200 python scripts/cfg3_step.py 2>&1 | tail -1
