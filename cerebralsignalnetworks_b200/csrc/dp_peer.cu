@@ -356,7 +356,11 @@ extern "C" int csn_dp_allreduce_twoshot(void* const* buf_ptrs, void* const* flag
   const Watchdog dog = make_watchdog(rank);
   // enough loads in flight to fill the NVLink pipe (latency ~2 us, 770 GB/s: ~1.5 MB) without taking every SM
   const size_t per = ceil_div<size_t>(n4, world);
-  const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>(ceil_div<size_t>(per, 256), size_t(sm_count()) * 2));
+  // CTAs of the two kernels.  The exchange usually runs BESIDE a latency-bound backward recurrence: more CTAs finish it
+  // sooner but take L2 / NVLink bandwidth and issue slots from the chain.  CSN_DP_XCHG_BLOCKS overrides the default.
+  static const int forced_blocks = [] { const char* e = getenv("CSN_DP_XCHG_BLOCKS"); return e ? atoi(e) : 0; }();
+  const size_t cap = forced_blocks > 0 ? size_t(forced_blocks) : size_t(sm_count()) * 2;
+  const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>(ceil_div<size_t>(per, 256), cap));
   dp_reduce_slice_kernel<<<blocks, 256, 0, s>>>(ps, world, rank, offset, n4, epoch_counter, flag_set, ticket, dog);
   CSN_LAUNCH_CHECK();
   dp_gather_slices_kernel<<<blocks, 256, 0, s>>>(ps, world, rank, offset, n4, epoch_counter, flag_set, ticket + 1, dog);

@@ -6,6 +6,10 @@ import torch
 import cerebralsignalnetworks_b200 as csn
 from cerebralsignalnetworks_b200 import _lib
 from cerebralsignalnetworks_b200.schedules import cosine_scheduler
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:  # torchrun: one rank per GPU, the step exchanges over peer memory
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 B, C, T, H, L, K = int(os.environ.get("PB", "64")), 96, 495, 128, 4, int(os.environ.get("PK", "65536"))
 torch.manual_seed(43); np.random.seed(43)
 def make():
@@ -33,5 +37,6 @@ e1.record()
 t_host = time.perf_counter() - t0
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print(f"cfg3 B={B} K={K}: {ms:.3f} ms/step ({B / ms * 1e3:.0f} trials/s), host enqueue {1e3 * t_host / n:.3f} ms/step, "
+if int(os.environ.get("RANK", "0")) == 0:
+    print(f"cfg3 B={B} K={K}: {ms:.3f} ms/step ({B / ms * 1e3:.0f} trials/s), host enqueue {1e3 * t_host / n:.3f} ms/step, "
       f"{(_lib.launch_count() - l0) // n} libcsn launches/step, loss {float(loss):.4f}")
