@@ -52,19 +52,25 @@ class Model(nn.Module):
 
 
 class DINOHead(nn.Module):
-    """Restatement of LstmDistillation.py:65-99 (use_bn=False path)."""
+    """Restatement of LstmDistillation.py:65-99 (both the default use_bn=False path and the BatchNorm1d layers of use_bn=True,
+    :72-80)."""
 
     def __init__(self, in_dim, out_dim, use_bn=False, norm_last_layer=True, nlayers=3, hidden_dim=2048,
                  bottleneck_dim=256):
         super().__init__()
-        assert not use_bn
         nlayers = max(nlayers, 1)
         if nlayers == 1:
             self.mlp = nn.Linear(in_dim, bottleneck_dim)
         else:
-            layers = [nn.Linear(in_dim, hidden_dim), nn.GELU()]
+            layers = [nn.Linear(in_dim, hidden_dim)]
+            if use_bn:
+                layers.append(nn.BatchNorm1d(hidden_dim))
+            layers.append(nn.GELU())
             for _ in range(nlayers - 2):
-                layers += [nn.Linear(hidden_dim, hidden_dim), nn.GELU()]
+                layers.append(nn.Linear(hidden_dim, hidden_dim))
+                if use_bn:
+                    layers.append(nn.BatchNorm1d(hidden_dim))
+                layers.append(nn.GELU())
             layers.append(nn.Linear(hidden_dim, bottleneck_dim))
             self.mlp = nn.Sequential(*layers)
         for m in self.modules():

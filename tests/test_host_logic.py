@@ -43,6 +43,21 @@ def test_dino_head_param_names_match_reference_layout(golden):
         assert tuple(p.shape) == g["param." + n].shape, n
 
 
+def test_dino_head_with_batchnorm_has_the_reference_state_layout():
+    """DINOHead(use_bn=True) (LstmDistillation.py:72-80): same module order and state_dict keys / shapes as the restated
+    reference head (itself checked against the reference class in tests/test_oracle_distill.py), so checkpoints interchange."""
+    import torch
+    from oracle import distill as od
+    from cerebralsignalnetworks_b200.dino import DINOHead
+    ours = DINOHead(16, 24, use_bn=True, hidden_dim=32, bottleneck_dim=8)
+    ref = od.DINOHead(16, 24, use_bn=True, hidden_dim=32, bottleneck_dim=8)
+    so, sr = ours.state_dict(), ref.state_dict()
+    assert list(so.keys()) == list(sr.keys())
+    assert all(tuple(so[k].shape) == tuple(sr[k].shape) and so[k].dtype == sr[k].dtype for k in so)
+    ours.load_state_dict(sr)
+    assert torch.equal(ours.mlp[1].running_var, ref.mlp[1].running_var)
+
+
 def test_dino_loss_signature_and_schedule(golden):
     g = golden("dino_loss_single.npz")
     sig = inspect.signature(csn.DINOLoss.__init__)

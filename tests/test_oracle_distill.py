@@ -147,6 +147,14 @@ def test_live_reference_dino_multicrop_and_head(pg):
     h2.load_state_dict(h1.state_dict())
     x = torch.randn(5, 16)
     assert torch.allclose(h1(x), h2(x), rtol=1e-6, atol=1e-7)
+    # the BatchNorm variant of the head (use_bn=True, :72-80): same layout, same training-mode outputs and running statistics
+    h1 = ref.DINOHead(16, 24, use_bn=True, hidden_dim=32, bottleneck_dim=8)
+    h2 = od.DINOHead(16, 24, use_bn=True, hidden_dim=32, bottleneck_dim=8)
+    assert list(h1.state_dict().keys()) == list(h2.state_dict().keys())
+    h2.load_state_dict(h1.state_dict())
+    xb = torch.randn(9, 16)
+    assert torch.allclose(h1(xb), h2(xb), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(h1.mlp[1].running_var, h2.mlp[1].running_var)
     # MultiCropWrapper grouping
     class Back(torch.nn.Module):
         def forward(self, x):
