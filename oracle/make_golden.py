@@ -87,6 +87,32 @@ def golden_dino_head():
     np.savez(os.path.join(GOLD, "dino_head.npz"), versions=str(VERS), **out)
 
 
+def golden_dino_head_bn():
+    """The use_bn=True head of the reference (LstmDistillation.py:72-80) in training mode: output, gradients and the
+    running statistics after one forward pass."""
+    ref = import_reference("LstmDistillation")
+    torch.manual_seed(46)
+    head = ref.DINOHead(in_dim=16, out_dim=24, use_bn=True, nlayers=3, hidden_dim=32, bottleneck_dim=8)
+    with torch.no_grad():
+        for p in head.parameters():
+            p.add_(torch.randn_like(p) * 0.3)
+        head.last_layer.weight_g.fill_(1)
+    out = {}
+    for n, b in head.state_dict().items():
+        out["state0." + n] = b.detach().clone().numpy()
+    x = torch.randn(12, 16, requires_grad=True)
+    y = head(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    out.update({"x": x.detach().numpy(), "y": y.detach().numpy(), "gy": gy.numpy(), "gx": x.grad.numpy()})
+    for n, p in head.named_parameters():
+        if p.grad is not None:
+            out["grad." + n] = p.grad.numpy()
+    for n, b in head.named_buffers():
+        out["buf1." + n] = b.detach().numpy()
+    np.savez(os.path.join(GOLD, "dino_head_bn.npz"), versions=str(VERS), **out)
+
+
 def golden_utils():
     u = import_reference("utils.utils")
     out = {
@@ -407,6 +433,10 @@ def main():
         golden_kd_losses()
         print("kd_losses.npz written")
         return 0
+    if "--only-head-bn" in sys.argv:
+        golden_dino_head_bn()
+        print("dino_head_bn.npz written")
+        return 0
     if "--only-alt-losses" in sys.argv:
         golden_alt_losses()
         print("alt_losses.npz written")
@@ -414,6 +444,7 @@ def main():
     golden_dino_single()
     golden_dino_multicrop()
     golden_dino_head()
+    golden_dino_head_bn()
     golden_utils()
     golden_filters()
     golden_lstm_step()

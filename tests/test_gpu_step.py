@@ -111,6 +111,26 @@ def test_dino_head_golden(golden):
             np.testing.assert_allclose(p.grad.cpu().numpy(), g["grad." + n], rtol=1e-3, atol=1e-5, err_msg=n)
 
 
+def test_dino_head_with_batchnorm_golden(golden):
+    """DINOHead(use_bn=True) against vectors the reference's own class produced (oracle/make_golden.py::golden_dino_head_bn,
+    LstmDistillation.py:65-99 in training mode): output, input / parameter gradients, running statistics after the step."""
+    import cerebralsignalnetworks_b200 as csn
+    g = golden("dino_head_bn.npz")
+    head = csn.DINOHead(16, 24, use_bn=True, nlayers=3, hidden_dim=32, bottleneck_dim=8).cuda()
+    head.load_state_dict({k[len("state0."):]: _t(g[k]) for k in g.files if k.startswith("state0.")})
+    head.train()
+    x = _t(g["x"]).cuda().requires_grad_(True)
+    y = head(x)
+    y.backward(_t(g["gy"]).cuda())
+    np.testing.assert_allclose(y.detach().cpu().numpy(), g["y"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["gx"], rtol=2e-3, atol=2e-5)
+    for n, p in head.named_parameters():
+        if p.requires_grad:
+            np.testing.assert_allclose(p.grad.cpu().numpy(), g["grad." + n], rtol=2e-3, atol=2e-5, err_msg=n)
+    for n, b in head.named_buffers():
+        np.testing.assert_allclose(b.cpu().numpy(), g["buf1." + n], rtol=1e-5, atol=1e-6, err_msg=n)
+
+
 @pytest.mark.parametrize("M,N", [(384, 2048), (7, 33), (2, 1), (600, 100)])
 def test_batchnorm_matches_torch(M, N):
     """csn_batchnorm_fwd / _bwd against torch.nn.BatchNorm1d (what the reference's DINOHead(use_bn=True) calls,
